@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""bench.py -- the network RHS `nw(du,u,p,t)` on BASELINE.json's headline configuration.
+
+  python bench.py --gpus 1 --steps 50 --warmup 5              our engine (CUDA, through the C ABI)
+  python bench.py --impl reference ...                        the reference's CPU path restated (oracle, OpenMP)
+  torchrun ... bench.py --gpus N ...                          vertex-partitioned, one rank per GPU
+
+A "step" is one RHS evaluation over the whole graph.  Workload at every N: BASELINE.json configs[1] -- heat
+diffusion (diffusion edge with one parameter + integrator vertex) on Erdos-Renyi N=1e6, mean degree 8, fp64;
+for N>1 every rank owns one such 1e6-vertex slice of an N-times larger ER graph (weak scaling) and the vertex
+outputs are exchanged every step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (vertices per GPU, edges per GPU)
+    "cfg2_diffusion_er_1e6": (1_000_000, 4_000_000),
+    "cfg2_small": (100_000, 400_000),
+}
+
+
+def algorithmic_bytes(nw, nentries):
+    """B_alg = 8*dim(u) [read u] + 8*dim(u) [write du] + 8*|p| + 4*(N+1) + 4*D"""
+    return 16 * nw.dim() + 8 * nw.pdim() + 4 * (nw.im.nv + 1) + 4 * nentries
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md, MEASURED_PEAKS.json absent)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region"""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.samples, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [int(s[0]) for s in self.samples if s and s[0].isdigit()]
+        mx = [int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def build_workload(nd, name, world):
+    nvp, nep = WORKLOADS[name]
+    t0 = time.time()
+    g = nd.erdos_renyi(nvp * world, nep * world, seed=1)
+    L = nd.Lib
+    return g, L.diffusion_vertex(), L.diffusion_edge(), time.time() - t0
+
+
+def run_reference(args):
+    """The reference's own CPU path (ThreadedExecution{true} + ThreadedAggregator, src/coreloop.jl:121-129,
+    src/aggregators.jl:159-235) restated in C/OpenMP (oracle/nd_oracle.c) -- Julia itself cannot run here."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import ndb200 as nd
+    from oracle import oracle as O
+    g, vm, em, _ = build_workload(nd, args.workload, 1)
+    onw = O.OracleNetwork(g.nv, g.src, g.dst, [O.VSPECS["diffusion_vertex"]], np.zeros(g.nv, np.int32),
+                          [O.ESPECS["diffusion_edge"]], np.zeros(g.ne, np.int32))
+    u = np.random.default_rng(1).random(onw.lastidx_dynamic)
+    p = np.random.default_rng(2).random(onw.lastidx_p)
+    du = np.empty_like(u)
+    threads = O.max_threads()
+    for _ in range(args.warmup):
+        onw.rhs_into(du, u, p, 0.0, threads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        onw.rhs_into(du, u, p, 0.0, threads=threads)
+    dt = time.perf_counter() - t0
+    val = g.ne * args.steps / dt
+    line = {"impl": "reference", "metric": "edge_evals_per_sec", "value": val, "unit": "edge-evals/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "rhs_per_sec": args.steps / dt,
+            "config": {"workload": args.workload, "graph": f"erdos_renyi(N={g.nv}, E={g.ne})", "vertex": "diffusion_vertex",
+                       "edge": "diffusion_edge(pdim=1)"},
+            "cpu_baseline": {"value": val, "unit": "edge-evals/s", "cores": threads, "kind": "port",
+                             "sample": f"{args.steps} full RHS evaluations of the same workload; C/OpenMP restatement of "
+                                       "ThreadedExecution{true}+ThreadedAggregator, not Julia"},
+            "e2e": {"value": val, "unit": "edge-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def cpu_baseline_leg(nd, g, budget_s=12.0):
+    from oracle import oracle as O
+    onw = O.OracleNetwork(g.nv, g.src, g.dst, [O.VSPECS["diffusion_vertex"]], np.zeros(g.nv, np.int32),
+                          [O.ESPECS["diffusion_edge"]], np.zeros(g.ne, np.int32))
+    u = np.random.default_rng(1).random(onw.lastidx_dynamic)
+    p = np.random.default_rng(2).random(onw.lastidx_p)
+    du = np.empty_like(u)
+    threads = O.max_threads()
+    for _ in range(2):
+        onw.rhs_into(du, u, p, 0.0, threads=threads)
+    n, t0 = 0, time.perf_counter()
+    while True:
+        onw.rhs_into(du, u, p, 0.0, threads=threads)
+        n += 1
+        el = time.perf_counter() - t0
+        if el > budget_s or n >= 200:
+            break
+    return {"value": g.ne * n / el, "unit": "edge-evals/s", "cores": threads, "kind": "port",
+            "sample": f"{n} full RHS evaluations of the same workload in {el:.1f} s; C/OpenMP restatement of the "
+                      "reference's ThreadedExecution{true}+ThreadedAggregator (oracle/nd_oracle.c), not Julia",
+            "ms_per_rhs": 1e3 * el / n}, du, u, p
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2_diffusion_er_1e6", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import ndb200 as nd
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    g, vm, em, t_graph = build_workload(nd, args.workload, world)
+    t0 = time.time()
+    if world == 1:
+        nw = nd.Network(g, vm, em, execution=nd.B200Execution(), aggregator=nd.B200Aggregator("+", keep_tables=False))
+        pnw = None
+    else:
+        from networkdynamics_jl_b200.distributed import PartitionedNetwork
+        pnw = PartitionedNetwork(g, vm, em, rank=rank, world=world, group=dist.group.WORLD)
+        nw = pnw.nw
+    t_build = time.time() - t0
+    sizes = nw.engine_sizes()
+    u_h = np.random.default_rng(1).random(nw.dim())
+    p_h = np.random.default_rng(2).random(nw.pdim())
+    u = torch.from_numpy(u_h).cuda()
+    p = torch.from_numpy(p_h).cuda()
+    du = torch.empty_like(u)
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")   # 256 MiB > 126 MB L2
+
+    def step():
+        if pnw is None:
+            nw(du, u, p, 0.0)
+        else:
+            pnw.rhs(du, u, p, 0.0)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        flush.zero_()
+        step()
+    sync_all()
+
+    # ---- timed region: K steps, L2 flushed between steps (flush outside the event brackets) ----------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    nw.set_timing(True)
+    launches0 = nw.launch_count()
+    sync_all()
+    for a, b in ev:
+        flush.zero_()
+        a.record()
+        step()
+        b.record()
+    sync_all()
+    launches = nw.launch_count() - launches0
+    tim = nw.timings()
+    nw.set_timing(False)
+    cold_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(sum(cold_ms))
+    # L2-warm variant (no flush), same number of steps, one event pair
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    a.record()
+    for _ in range(args.steps):
+        step()
+    b.record()
+    sync_all()
+    warm_ms = a.elapsed_time(b)
+    clocks = sampler.stop() if rank == 0 else None
+    if dist is not None:
+        t = torch.tensor([total_ms, warm_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, warm_ms = t.tolist()
+
+    # ---- end-to-end through the public call with HOST buffers (pinned), H2D + RHS + D2H every step ----------
+    e2e = None
+    if world == 1:
+        hu, hp, hdu = nd.pinned_empty(nw.dim()), nd.pinned_empty(nw.pdim()), nd.pinned_empty(nw.dim())
+        hu[:], hp[:] = u_h, p_h
+        for _ in range(3):
+            nw(hdu, hu, hp, 0.0)
+        torch.cuda.synchronize()
+        te = time.perf_counter()
+        for _ in range(args.steps):
+            nw(hdu, hu, hp, 0.0)       # synchronous: returns after the D2H copy completed
+        e2e_s = time.perf_counter() - te
+        e2e = {"value": g.ne * args.steps / e2e_s, "unit": "edge-evals/s", "h2d_bytes_per_step": 8 * (nw.dim() + nw.pdim()),
+               "d2h_bytes_per_step": 8 * nw.dim(), "ms_per_step": 1e3 * e2e_s / args.steps,
+               "how": "nw(du,u,p,t) with pinned host vectors -> nd_b200_rhs_host: cudaMemcpyAsync H2D (u,p), fused RHS, "
+                      "cudaMemcpyAsync D2H (du), stream sync; wall clock around the calls"}
+        assert np.array_equal(hdu, du.cpu().numpy()), "host-buffer path and device path disagree"
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak()
+    n_entries_all = sizes["nentries"] * world if world > 1 else sizes["nentries"]
+    b_alg = algorithmic_bytes(nw, sizes["nentries"]) if world == 1 else None
+    fused_ms = tim["fused_ms"]
+    roofline = None
+    if world == 1 and fused_ms > 0:
+        achieved = b_alg / (fused_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "kernel": "rhs_fused_kernel<1,1,E_DIFFUSION>", "kernel_ms_avg": fused_ms,
+                    "algorithmic_bytes_per_launch": b_alg, "peak_source": peak_src,
+                    "frac_of_nominal_8000": achieved / 8000.0,
+                    "note": "kernel time from CUDA events recorded by the engine on the launch stream around the fused "
+                            "kernel, L2 flushed before every launch"}
+    line = {
+        "metric": "edge_evals_per_sec", "value": g.ne * args.steps / (total_ms * 1e-3), "unit": "edge-evals/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "rhs_per_sec": args.steps / (total_ms * 1e-3),
+        "value_l2_warm": g.ne * args.steps / (warm_ms * 1e-3), "ms_per_step_l2_warm": warm_ms / args.steps,
+        "config": {"workload": args.workload, "graph": f"erdos_renyi(N={g.nv}, E={g.ne}), seed 1", "vertex": "diffusion_vertex",
+                   "edge": "diffusion_edge(pdim=1)", "directed_entries": n_entries_all,
+                   "l2": "flushed between timed steps by a 256 MiB write outside the event brackets; value_l2_warm = back-to-back",
+                   "partition": "none" if world == 1 else f"{world} contiguous vertex ranges, vertex outputs exchanged every step",
+                   "launch_shape": {"blocks": sizes["nblocks"], "long_rows": sizes["n_long_rows"]}},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "setup_s": {"graph": round(t_graph, 2), "network+csr": round(t_build, 2)},
+    }
+    if e2e is not None:
+        line["e2e"] = e2e
+    if roofline is not None:
+        line["roofline"] = roofline
+    if world == 1 and not args.no_cpu_baseline:
+        cb, du_cpu, _, _ = cpu_baseline_leg(nd, g)
+        line["cpu_baseline"] = cb
+        ref = du_cpu
+        got = du.cpu().numpy()
+        den = np.maximum(np.abs(ref), 1e-3 * np.max(np.abs(ref)))
+        line["parity_vs_oracle"] = float(np.max(np.abs(got - ref) / den))
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,151 @@
+/*
+ * nd_b200.h -- C ABI of the B200-native network right-hand-side engine.
+ *
+ * This is the drop-in boundary for ONE path of JuliaDynamics/NetworkDynamics.jl: the network RHS
+ * `nw(du, u, p, t)` (src/coreloop.jl:1-102).  The entry points are what a Julia `ccall` binding
+ * of `B200Execution` / `B200Aggregator` needs (see INTEGRATION.md and julia/NetworkDynamicsB200.jl):
+ * plain pointers, sizes and status codes; no C++ types, no torch types, no exceptions.
+ *
+ * Index conventions: everything the CALLER passes in a descriptor is in the reference's own
+ * convention -- 1-based Int64, exactly the numbers held by `IndexManager`
+ * (src/network_structure.jl:1-55) and `ComponentBatch` (src/network_structure.jl:176-222).
+ * `du`, `u`, `p` are raw DEVICE pointers in the reference's flat layout
+ * (u = [vertex batches | edge batches], src/network_structure.jl:224-258).
+ */
+#ifndef ND_B200_H
+#define ND_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ND_B200_ABI_VERSION 1
+
+/* status codes (Julia glue rethrows: EINVAL -> ArgumentError, others -> ErrorException) */
+enum {
+  ND_B200_OK = 0,
+  ND_B200_EINVAL = 1,        /* size / layout mismatch (src/coreloop.jl:2-7 raise ArgumentError) */
+  ND_B200_EUNSUPPORTED = 2,  /* component kind / feature outside the kernel registry: NO CPU fallback */
+  ND_B200_ECUDA = 3,
+  ND_B200_ENOMEM = 4
+};
+
+/* ---- kernel registry: vertex models ------------------------------------------------------- */
+enum {
+  ND_B200_V_DIFFUSION = 0,             /* test/ComponentLibrary.jl:42-46, benchmark_models.jl:16-20 */
+  ND_B200_V_KURAMOTO_FIRST = 1,        /* test/ComponentLibrary.jl:69-72, benchmark_models.jl:32-35 */
+  ND_B200_V_KURAMOTO_SECOND = 2,       /* test/ComponentLibrary.jl:59-67, p=(M,D,Pm)               */
+  ND_B200_V_KURAMOTO_SECOND_BENCH = 3, /* benchmark/benchmark_models.jl:37-42, p=(P,)              */
+  ND_B200_V_SWING_DQ = 4               /* test/ComponentLibrary.jl:139-161, p=(M,D,Pmech,V)        */
+};
+/* ---- kernel registry: edge models --------------------------------------------------------- */
+enum {
+  ND_B200_E_DIFFUSION = 0,             /* test/ComponentLibrary.jl:8-13,  e = p*(vs-vd)            */
+  ND_B200_E_DIFFUSION_NOP = 1,         /* benchmark/benchmark_models.jl:5-9, e = vs-vd             */
+  ND_B200_E_KURAMOTO = 2,              /* test/ComponentLibrary.jl:51-57, e = K*sin(ths-thd)       */
+  ND_B200_E_LINE_DQ = 3                /* test/ComponentLibrary.jl:212-245, p=(R,X,active)         */
+};
+/* edge output wrappers, src/component_functions.jl:117-203 */
+enum { ND_B200_ANTISYMMETRIC = 0, ND_B200_SYMMETRIC = 1, ND_B200_DIRECTED = 2 };
+
+/* One `ComponentBatch` of vertices (src/network_structure.jl:176-222 + register_vertices! :224-239).
+ * `*_first` are the `first` fields of the batch's BatchStrides (1-based); widths are the strides. */
+typedef struct nd_b200_vbatch {
+  int32_t kind;            /* ND_B200_V_*                                    */
+  int32_t dim, pdim, outdim;
+  int64_t count;
+  const int64_t* indices;  /* batch.indices: 1-based vertex ids              */
+  int64_t state_first;     /* statestride.first                              */
+  int64_t p_first;         /* pstride.first                                  */
+  int64_t out_first;       /* outbufstride.first                             */
+  int64_t aggr_first;      /* inbufstride.first (aggbuf)                     */
+} nd_b200_vbatch;
+
+/* One `ComponentBatch` of edges (register_edges!, src/network_structure.jl:240-258). */
+typedef struct nd_b200_ebatch {
+  int32_t kind;            /* ND_B200_E_*                                    */
+  int32_t coupling;        /* ND_B200_ANTISYMMETRIC | SYMMETRIC | DIRECTED   */
+  int32_t dim, pdim, outdim_src, outdim_dst;
+  int64_t count;
+  const int64_t* indices;  /* batch.indices: 1-based edge ids                */
+  int64_t state_first, p_first, out_first, gbuf_first;
+} nd_b200_ebatch;
+
+typedef struct nd_b200_desc {
+  int32_t abi_version;     /* ND_B200_ABI_VERSION                            */
+  int32_t device;          /* CUDA device ordinal                            */
+  int64_t nv, ne;
+  const int64_t* edge_src; /* im.edgevec[i].src, 1-based, edges(g) order     */
+  const int64_t* edge_dst;
+  int32_t vdepth, edepth;  /* im.vdepth, im.edepth                           */
+  int32_t n_vbatches, n_ebatches;
+  const nd_b200_vbatch* vbatches;
+  const nd_b200_ebatch* ebatches;
+  int64_t lastidx_dynamic, lastidx_p, lastidx_out, lastidx_aggr;
+  /* Multi-GPU vertex partition: this engine evaluates aggregation-slot rows
+   * [row_begin, row_end) (0-based, slot = (v_aggr.first-1)/edepth) and writes only their
+   * states in du.  row_end <= 0 means "all rows".                           */
+  int64_t row_begin, row_end;
+  /* rows with more than this many incoming entries are reduced by a whole thread block with a
+   * fixed-shape tree instead of one sequential thread; <= 0 -> default (128); INT32_MAX ->
+   * strictly sequential per-row accumulation everywhere (debug).            */
+  int32_t long_row_threshold;
+  int32_t flags;           /* ND_B200_FLAG_*                                 */
+} nd_b200_desc;
+
+#define ND_B200_FLAG_NO_EXPORT 1  /* do not keep host copies of the CSR for nd_b200_export_tables */
+
+typedef struct nd_b200_engine nd_b200_engine;
+
+/* Replaces: aggregator construction `aggregator(im, edgebatches)` (src/construction.jl:198) plus the
+ * device adaptation of ext/NetworkDynamicsCUDAExt.jl:16-45.  Builds the destination-sorted CSR. */
+int nd_b200_create(const nd_b200_desc* desc, nd_b200_engine** out);
+void nd_b200_destroy(nd_b200_engine*);
+/* message of the last failing call on this engine (engine == NULL: last failing create on this thread) */
+const char* nd_b200_last_error(const nd_b200_engine*);
+int nd_b200_abi_version(void);
+
+/* Replaces `(nw::Network)(du,u,p,t)` (src/coreloop.jl:1-102).  Device pointers; asynchronous on
+ * `stream` (a cudaStream_t; NULL = legacy default stream); no host synchronisation; p may be NULL
+ * when lastidx_p == 0.  Fully defines du for the rows this engine owns. */
+int nd_b200_rhs(nd_b200_engine*, double* du, const double* u, const double* p, double t, void* stream);
+
+/* Same call with HOST buffers (pageable or pinned): H2D copies of u and p, the RHS, D2H copy of du,
+ * then a stream synchronise.  This is the end-to-end form a CPU-resident caller would use. */
+int nd_b200_rhs_host(nd_b200_engine*, double* du_host, const double* u_host, const double* p_host, double t);
+
+/* Replaces `get_buffers(nw,u,p,t)` = RET=Val(:buf_init) (src/coreloop.jl:33-36,92-94,103-109):
+ * materialises the output buffer o (lastidx_out) and the aggregation buffer (lastidx_aggr). */
+int nd_b200_get_buffers(nd_b200_engine*, double* o, double* aggbuf, const double* u, const double* p,
+                        double t, void* stream);
+
+/* Classical fixed-step RK4 on device-resident u (in place), stage updates fused into the RHS
+ * kernels, step captured in a CUDA graph.  Replaces `solve(ODEProblem(nw,...), RK4(); dt, adaptive=false)`
+ * around src/post_utils.jl:43-100 for the registry models. */
+int nd_b200_rk4(nd_b200_engine*, double* u, const double* p, double t0, double dt, int64_t nsteps, void* stream);
+
+/* sizes[0]=nrows (owned) [1]=nentries [2]=nblocks [3]=n_long_rows [4]=gather_from_u (0/1)
+ * [5]=kernel launches per RHS [6]=row_begin [7]=row_end */
+int nd_b200_export_sizes(const nd_b200_engine*, int64_t sizes[8]);
+/* The CSR the engine built, for the bit-exact index check: rowptr[nrows+1] (0-based offsets),
+ * and per entry the 1-based neighbour vertex id, 1-based edge id, and side (0: this row is the
+ * edge's dst, 1: this row is the edge's src).  Entries of a row are in accumulation order. */
+int nd_b200_export_tables(const nd_b200_engine*, int64_t* rowptr, int64_t* nbr_vertex, int64_t* edge_id,
+                          int32_t* side);
+
+/* kernel launches issued by this engine since creation (bench.py's gpu_launches) */
+int64_t nd_b200_launch_count(const nd_b200_engine*);
+/* average device time [ms] of the fused RHS kernel over the last `nd_b200_rhs` calls made while
+ * timing was enabled (CUDA events on the caller's stream). */
+int nd_b200_set_timing(nd_b200_engine*, int enabled);
+int nd_b200_timings(nd_b200_engine*, double* fused_ms_avg, double* prepass_ms_avg, int64_t* ncalls);
+
+/* pinned host memory for nd_b200_rhs_host callers */
+void* nd_b200_host_alloc(int64_t bytes);
+void nd_b200_host_free(void*);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,130 @@
+"""ctypes view of include/nd_b200.h plus the in-tree nvcc build of libnd_b200.so.
+
+There is no CPU fallback: if the shared library (or a CUDA device) is missing, every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_PKG)
+LIB_PATH = os.path.join(_PKG, "libnd_b200.so")
+SOURCES = [os.path.join(_PKG, "csrc", "nd_b200.cu")]
+HEADERS = [os.path.join(_PKG, "csrc", "nd_b200_kernels.cuh"), os.path.join(_ROOT, "include", "nd_b200.h")]
+
+ABI_VERSION = 1
+OK, EINVAL, EUNSUPPORTED, ECUDA, ENOMEM = range(5)
+
+# registry ids (include/nd_b200.h)
+V_DIFFUSION, V_KURAMOTO_FIRST, V_KURAMOTO_SECOND, V_KURAMOTO_SECOND_BENCH, V_SWING_DQ = range(5)
+E_DIFFUSION, E_DIFFUSION_NOP, E_KURAMOTO, E_LINE_DQ = range(4)
+ANTISYMMETRIC, SYMMETRIC, DIRECTED = range(3)
+FLAG_NO_EXPORT = 1
+
+i64p = C.POINTER(C.c_int64)
+i32p = C.POINTER(C.c_int32)
+
+
+class VBatch(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("dim", C.c_int32), ("pdim", C.c_int32), ("outdim", C.c_int32),
+                ("count", C.c_int64), ("indices", i64p), ("state_first", C.c_int64), ("p_first", C.c_int64),
+                ("out_first", C.c_int64), ("aggr_first", C.c_int64)]
+
+
+class EBatch(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("coupling", C.c_int32), ("dim", C.c_int32), ("pdim", C.c_int32),
+                ("outdim_src", C.c_int32), ("outdim_dst", C.c_int32), ("count", C.c_int64), ("indices", i64p),
+                ("state_first", C.c_int64), ("p_first", C.c_int64), ("out_first", C.c_int64),
+                ("gbuf_first", C.c_int64)]
+
+
+class Desc(C.Structure):
+    _fields_ = [("abi_version", C.c_int32), ("device", C.c_int32), ("nv", C.c_int64), ("ne", C.c_int64),
+                ("edge_src", i64p), ("edge_dst", i64p), ("vdepth", C.c_int32), ("edepth", C.c_int32),
+                ("n_vbatches", C.c_int32), ("n_ebatches", C.c_int32), ("vbatches", C.POINTER(VBatch)),
+                ("ebatches", C.POINTER(EBatch)), ("lastidx_dynamic", C.c_int64), ("lastidx_p", C.c_int64),
+                ("lastidx_out", C.c_int64), ("lastidx_aggr", C.c_int64), ("row_begin", C.c_int64),
+                ("row_end", C.c_int64), ("long_row_threshold", C.c_int32), ("flags", C.c_int32)]
+
+
+EXPORTED_SYMBOLS = [
+    "nd_b200_create", "nd_b200_destroy", "nd_b200_last_error", "nd_b200_abi_version", "nd_b200_rhs",
+    "nd_b200_rhs_host", "nd_b200_get_buffers", "nd_b200_rk4", "nd_b200_export_sizes", "nd_b200_export_tables",
+    "nd_b200_launch_count", "nd_b200_set_timing", "nd_b200_timings", "nd_b200_host_alloc", "nd_b200_host_free",
+]
+
+
+def nvcc_path() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: the B200 engine cannot be built (there is no CPU fallback)")
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> networkdynamics.jl_b200/libnd_b200.so (in-tree)."""
+    newest = max(os.path.getmtime(f) for f in SOURCES + HEADERS)
+    if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= newest:
+        return LIB_PATH
+    cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+           "-fmad=false", "-Xcompiler", "-fPIC", "-shared", "-I", os.path.join(_ROOT, "include"),
+           "-o", LIB_PATH] + SOURCES
+    env = dict(os.environ)
+    # the image exports CC/CXX pointing at a gcc wrapper without a complete tool chain
+    if os.path.exists("/usr/bin/g++"):
+        cmd[1:1] = ["-ccbin", "/usr/bin/g++"]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.check_call(cmd, env=env)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """Load libnd_b200.so; fail loudly when it is absent (no fallback path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(the B200 engine has no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    dp = C.c_void_p  # raw device (or host) addresses
+    L.nd_b200_create.restype = C.c_int
+    L.nd_b200_create.argtypes = [C.POINTER(Desc), C.POINTER(C.c_void_p)]
+    L.nd_b200_destroy.restype = None
+    L.nd_b200_destroy.argtypes = [C.c_void_p]
+    L.nd_b200_last_error.restype = C.c_char_p
+    L.nd_b200_last_error.argtypes = [C.c_void_p]
+    L.nd_b200_abi_version.restype = C.c_int
+    L.nd_b200_rhs.restype = C.c_int
+    L.nd_b200_rhs.argtypes = [C.c_void_p, dp, dp, dp, C.c_double, C.c_void_p]
+    L.nd_b200_rhs_host.restype = C.c_int
+    L.nd_b200_rhs_host.argtypes = [C.c_void_p, dp, dp, dp, C.c_double]
+    L.nd_b200_get_buffers.restype = C.c_int
+    L.nd_b200_get_buffers.argtypes = [C.c_void_p, dp, dp, dp, dp, C.c_double, C.c_void_p]
+    L.nd_b200_rk4.restype = C.c_int
+    L.nd_b200_rk4.argtypes = [C.c_void_p, dp, dp, C.c_double, C.c_double, C.c_int64, C.c_void_p]
+    L.nd_b200_export_sizes.restype = C.c_int
+    L.nd_b200_export_sizes.argtypes = [C.c_void_p, i64p]
+    L.nd_b200_export_tables.restype = C.c_int
+    L.nd_b200_export_tables.argtypes = [C.c_void_p, i64p, i64p, i64p, i32p]
+    L.nd_b200_launch_count.restype = C.c_int64
+    L.nd_b200_launch_count.argtypes = [C.c_void_p]
+    L.nd_b200_set_timing.restype = C.c_int
+    L.nd_b200_set_timing.argtypes = [C.c_void_p, C.c_int]
+    L.nd_b200_timings.restype = C.c_int
+    L.nd_b200_timings.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), i64p]
+    L.nd_b200_host_alloc.restype = C.c_void_p
+    L.nd_b200_host_alloc.argtypes = [C.c_int64]
+    L.nd_b200_host_free.restype = None
+    L.nd_b200_host_free.argtypes = [C.c_void_p]
+    if L.nd_b200_abi_version() != ABI_VERSION:
+        raise RuntimeError("libnd_b200.so ABI version mismatch; rebuild")
+    _lib = L
+    return L

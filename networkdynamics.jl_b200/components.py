@@ -1,0 +1,187 @@
+"""Host-side mirror of the reference's component model types, for the RHS path only.
+
+Mirrors `VertexModel` / `EdgeModel` (src/component_functions.jl:251-329,532-567), `StateMask` (:81-99) and the
+edge output wrappers `AntiSymmetric` / `Symmetric` / `Directed` (:117-175).  In the reference `f` and `g` are
+arbitrary Julia functions; the B200 engine only runs hand-written kernels, so here `f`/`g` are tokens of a
+kernel registry (`RegisteredFunction`).  A model whose functions are not registered can still be described
+(layout queries work) but `Network(...; aggregator=B200Aggregator(+))` raises `ArgumentError` for it -- there is
+no CPU fallback.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Optional, Sequence, Tuple
+
+from . import _cabi
+
+
+class ArgumentError(ValueError):
+    """Julia's ArgumentError (what the reference throws on size / type mismatches, src/coreloop.jl:3,6)."""
+
+
+@dataclass(frozen=True)
+class RegisteredFunction:
+    """A component function with a hand-written sm_100a kernel.  `ref` cites the Julia source it restates."""
+    name: str
+    kind: int
+    role: str  # "vertex_f" | "vertex_g" | "edge_g"
+    ref: str = ""
+
+    def __call__(self, *a, **k):  # pragma: no cover - these are device kernels, not host callables
+        raise RuntimeError(f"{self.name} is a device kernel token; evaluate it through Network(...)")
+
+
+@dataclass(frozen=True)
+class StateMask:
+    """`StateMask(idxs)`: output k is state idxs[k] (1-based), src/component_functions.jl:81-99."""
+    idxs: Tuple[int, ...]
+
+    def __init__(self, idxs):
+        if isinstance(idxs, int):
+            idxs = (idxs,)
+        object.__setattr__(self, "idxs", tuple(int(i) for i in idxs))
+
+
+@dataclass(frozen=True)
+class AntiSymmetric:
+    """osrc = -odst, src/component_functions.jl:117-127"""
+    g: object
+    coupling = _cabi.ANTISYMMETRIC
+
+
+@dataclass(frozen=True)
+class Symmetric:
+    """osrc = odst, src/component_functions.jl:142-152"""
+    g: object
+    coupling = _cabi.SYMMETRIC
+
+
+@dataclass(frozen=True)
+class Directed:
+    """no src output (outdim.src = 0), src/component_functions.jl:167-175"""
+    g: object
+    coupling = _cabi.DIRECTED
+
+
+@dataclass(frozen=True)
+class VertexModel:
+    f: Optional[object]
+    g: object                      # StateMask or a RegisteredFunction (NoFeedForward g)
+    dim: int
+    pdim: int = 0
+    outdim: Optional[int] = None
+    sym: Tuple[str, ...] = ()
+    psym: Tuple[str, ...] = ()
+    name: str = "VertexModel"
+
+    def __post_init__(self):
+        if self.outdim is None:
+            if isinstance(self.g, StateMask):
+                object.__setattr__(self, "outdim", len(self.g.idxs))
+            else:
+                raise ArgumentError("outdim required when g is not a StateMask")
+
+    def component_hash(self):
+        """What batches are formed on: src/construction.jl:245-256 (name/metadata are not part of it)."""
+        return ("V", self.f, self.g, self.dim, self.outdim, self.pdim)
+
+    def kernel_kind(self) -> Optional[int]:
+        f = self.f
+        if not isinstance(f, RegisteredFunction) or f.role != "vertex_f":
+            return None
+        if f.kind == _cabi.V_SWING_DQ:
+            return f.kind if isinstance(self.g, RegisteredFunction) and self.g.kind == f.kind else None
+        # the StateMask kernels read output k from state k: mask must be 1:outdim
+        if isinstance(self.g, StateMask) and self.g.idxs == tuple(range(1, self.outdim + 1)):
+            return f.kind
+        return None
+
+
+@dataclass(frozen=True)
+class EdgeModel:
+    g: object                      # AntiSymmetric / Symmetric / Directed wrapping a RegisteredFunction
+    outdim: int = 1
+    pdim: int = 0
+    dim: int = 0
+    f: Optional[object] = None
+    psym: Tuple[str, ...] = ()
+    name: str = "EdgeModel"
+
+    @property
+    def coupling(self) -> Optional[int]:
+        return getattr(self.g, "coupling", None)
+
+    @property
+    def outdim_src(self) -> int:
+        return 0 if isinstance(self.g, Directed) else self.outdim
+
+    @property
+    def outdim_dst(self) -> int:
+        return self.outdim
+
+    def component_hash(self):
+        return ("E", self.f, self.g, self.dim, self.outdim_src, self.outdim_dst, self.pdim)
+
+    def kernel_kind(self) -> Optional[int]:
+        inner = getattr(self.g, "g", None)
+        if self.f is not None or self.dim != 0 or self.coupling is None:
+            return None
+        if isinstance(inner, RegisteredFunction) and inner.role == "edge_g":
+            return inner.kind
+        return None
+
+
+class Lib:
+    """The model zoo of test/ComponentLibrary.jl (module `Lib`) and benchmark/benchmark_models.jl, restricted
+    to the models with registered kernels."""
+    diffusionedge = RegisteredFunction("diffusionedge!", _cabi.E_DIFFUSION, "edge_g", "test/ComponentLibrary.jl:8-10")
+    diffusionedge_nop = RegisteredFunction("diffusionedge!", _cabi.E_DIFFUSION_NOP, "edge_g", "benchmark/benchmark_models.jl:5-8")
+    kuramoto_edge_f = RegisteredFunction("kuramoto_edge!", _cabi.E_KURAMOTO, "edge_g", "test/ComponentLibrary.jl:51-53")
+    line_dq_f = RegisteredFunction("StaticPowerLineDQ", _cabi.E_LINE_DQ, "edge_g", "test/ComponentLibrary.jl:212-245")
+    diffusionvertex = RegisteredFunction("diffusionvertex!", _cabi.V_DIFFUSION, "vertex_f", "test/ComponentLibrary.jl:42-45")
+    kuramoto_vertex = RegisteredFunction("kuramoto_vertex!", _cabi.V_KURAMOTO_FIRST, "vertex_f", "test/ComponentLibrary.jl:69-71")
+    kuramoto_inertia = RegisteredFunction("kuramoto_inertia!", _cabi.V_KURAMOTO_SECOND, "vertex_f", "test/ComponentLibrary.jl:59-63")
+    kuramoto_inertia_bench = RegisteredFunction("kuramoto_inertia!", _cabi.V_KURAMOTO_SECOND_BENCH, "vertex_f", "benchmark/benchmark_models.jl:37-41")
+    swing_dq_f = RegisteredFunction("SwingDQ.f", _cabi.V_SWING_DQ, "vertex_f", "test/ComponentLibrary.jl:139-161")
+    swing_dq_g = RegisteredFunction("SwingDQ.g", _cabi.V_SWING_DQ, "vertex_g", "test/ComponentLibrary.jl:158-159")
+
+    @staticmethod
+    def diffusion_edge():
+        return EdgeModel(g=AntiSymmetric(Lib.diffusionedge), outdim=1, pdim=1, name="diff_edge")
+
+    @staticmethod
+    def diffusion_edge_nop():
+        """benchmark variant without a parameter (benchmark/benchmark_models.jl:9)"""
+        return EdgeModel(g=AntiSymmetric(Lib.diffusionedge_nop), outdim=1, pdim=0, name="diff_edge")
+
+    @staticmethod
+    def diffusion_vertex():
+        return VertexModel(f=Lib.diffusionvertex, dim=1, pdim=0, g=StateMask((1,)), name="diffusion_vertex")
+
+    @staticmethod
+    def kuramoto_edge():
+        return EdgeModel(g=AntiSymmetric(Lib.kuramoto_edge_f), outdim=1, pdim=1, psym=("K",), name="kuramoto_edge")
+
+    @staticmethod
+    def kuramoto_first():
+        return VertexModel(f=Lib.kuramoto_vertex, dim=1, pdim=1, g=StateMask(1), sym=("θ",), psym=("ω",),
+                           name="kuramoto_first")
+
+    @staticmethod
+    def kuramoto_second():
+        return VertexModel(f=Lib.kuramoto_inertia, dim=2, pdim=3, g=StateMask(1), sym=("δ", "ω"),
+                           psym=("M", "D", "Pm"), name="kuramoto_second")
+
+    @staticmethod
+    def kuramoto_second_bench():
+        return VertexModel(f=Lib.kuramoto_inertia_bench, dim=2, pdim=1, g=StateMask((1,)), sym=("θ", "ω"),
+                           name="kuramoto_vertex_2d")
+
+    @staticmethod
+    def swing_dq():
+        return VertexModel(f=Lib.swing_dq_f, g=Lib.swing_dq_g, dim=2, pdim=4, outdim=2, sym=("θ", "ω"),
+                           psym=("M", "D", "Pmech", "V"), name="swing_dq")
+
+    @staticmethod
+    def line_dq():
+        return EdgeModel(g=AntiSymmetric(Lib.line_dq_f), outdim=2, pdim=3, psym=("R", "X", "active"), name="line_dq")

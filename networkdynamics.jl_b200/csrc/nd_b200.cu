@@ -1,0 +1,662 @@
+// nd_b200.cu -- engine object + C ABI (include/nd_b200.h) of the B200-native network RHS.
+//
+// Construction (host, C++): from the reference's own tables (IndexManager ranges + ComponentBatches,
+// src/network_structure.jl:1-55,176-258) build a destination-sorted CSR over aggregation slots whose
+// per-row entry order is the accumulation order of SequentialAggregator (src/aggregators.jl:140-151):
+// ascending position in the output buffer `o` = (edge batch, position in batch, src-out before dst-out).
+// Evaluation: see nd_b200_kernels.cuh.
+#include "nd_b200_kernels.cuh"
+
+#include <algorithm>
+#include <climits>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace ndb;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+constexpr int MAX_VB = 64;
+constexpr int MAX_EB = 255;   // edge batch id is stored per entry as uint8
+
+struct HostVB { int kind, dim, pdim, outdim; long long count, state0, p0, out0, row0; };
+struct HostEB { int kind, coupling, dim, pdim, osrc, odst; long long count, p0, out0; };
+
+}  // namespace
+
+struct nd_b200_engine {
+  int device = 0;
+  std::string err;
+  long long nv = 0, ne = 0;
+  int vdepth = 1, edepth = 1;
+  long long lastidx_dynamic = 0, lastidx_p = 0, lastidx_out = 0, lastidx_aggr = 0;
+  long long nrows_total = 0, row_begin = 0, row_end = 0;
+  long long nentries = 0;
+  int nblocks = 0, n_long = 0;
+  int long_thr = 128;
+  int gather_from_u = 1;
+  int ek = EK_GENERIC;        // edge kind of the single edge batch, or EK_GENERIC
+  int block = 256, ept = 8;   // launch shape of the fused kernel
+  std::vector<HostVB> hvb;
+  std::vector<HostEB> heb;
+  // device tables
+  int *d_rowptr = nullptr, *d_nbr = nullptr, *d_epar = nullptr, *d_blk_row = nullptr;
+  uint8_t* d_ebid = nullptr;
+  VBDev* d_vb = nullptr;
+  EBDev* d_eb = nullptr;
+  double *d_vout[2] = {nullptr, nullptr};
+  // get_buffers support (lazy)
+  std::vector<std::vector<int>> h_esrc_off, h_edst_off;   // per edge batch, gather offsets
+  std::vector<int*> d_esrc_off, d_edst_off;
+  // host copies for export
+  std::vector<long long> h_rowptr;
+  std::vector<int> h_nbr_vid, h_eid;
+  std::vector<uint8_t> h_side;
+  // rk4
+  double *d_tmpA = nullptr, *d_tmpB = nullptr, *d_ksum = nullptr;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
+  int graph_steps = 0;
+  const double *graph_u = nullptr, *graph_p = nullptr;
+  double graph_dt = 0.0;
+  cudaStream_t cap_stream = nullptr;
+  // host-buffer path
+  cudaStream_t own_stream = nullptr;
+  double *d_hu = nullptr, *d_hp = nullptr, *d_hdu = nullptr;
+  // stats
+  long long launches = 0;
+  bool timing = false;
+  std::vector<cudaEvent_t> ev;   // pairs: [2i] start, [2i+1] stop of the fused kernel; prepass pairs in ev_pre
+  std::vector<cudaEvent_t> ev_pre;
+  size_t ev_used = 0, ev_pre_used = 0;
+};
+
+namespace {
+
+int fail(nd_b200_engine* e, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (e) e->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CUDA_TRY(e, call)                                                                      \
+  do {                                                                                         \
+    cudaError_t _c = (call);                                                                   \
+    if (_c != cudaSuccess) return fail(e, ND_B200_ECUDA, "%s: %s", #call, cudaGetErrorString(_c)); \
+  } while (0)
+
+template <typename T>
+int upload(nd_b200_engine* e, T** dst, const std::vector<T>& src) {
+  size_t bytes = sizeof(T) * std::max<size_t>(src.size(), 1);
+  CUDA_TRY(e, cudaMalloc((void**)dst, bytes));
+  if (!src.empty()) CUDA_TRY(e, cudaMemcpy(*dst, src.data(), sizeof(T) * src.size(), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// registry: the (dim, pdim, outdim) each kernel was written for
+bool vertex_kind_ok(const nd_b200_vbatch& b, std::string& why) {
+  struct R { int kind, dim, pdim, outdim; };
+  static const R reg[] = {{ND_B200_V_DIFFUSION, 1, 0, 1}, {ND_B200_V_KURAMOTO_FIRST, 1, 1, 1},
+                          {ND_B200_V_KURAMOTO_SECOND, 2, 3, 1}, {ND_B200_V_KURAMOTO_SECOND_BENCH, 2, 1, 1},
+                          {ND_B200_V_SWING_DQ, 2, 4, 2}};
+  for (const R& r : reg)
+    if (r.kind == b.kind) {
+      if (r.dim != b.dim || r.pdim != b.pdim || r.outdim != b.outdim) {
+        why = "vertex kind " + std::to_string(b.kind) + " registered with (dim,pdim,outdim)=(" + std::to_string(r.dim) + "," +
+              std::to_string(r.pdim) + "," + std::to_string(r.outdim) + ")";
+        return false;
+      }
+      return true;
+    }
+  why = "vertex kind " + std::to_string(b.kind) + " is not in the B200 kernel registry";
+  return false;
+}
+bool edge_kind_ok(const nd_b200_ebatch& b, int vdepth, std::string& why) {
+  struct R { int kind, pdim, odst, vdepth; };
+  static const R reg[] = {{ND_B200_E_DIFFUSION, 1, 1, 1}, {ND_B200_E_DIFFUSION_NOP, 0, 1, 1},
+                          {ND_B200_E_KURAMOTO, 1, 1, 1}, {ND_B200_E_LINE_DQ, 3, 2, 2}};
+  for (const R& r : reg)
+    if (r.kind == b.kind) {
+      if (r.pdim != b.pdim || r.odst != b.outdim_dst || r.vdepth != vdepth) {
+        why = "edge kind " + std::to_string(b.kind) + " registered with (pdim,outdim,vdepth)=(" + std::to_string(r.pdim) + "," +
+              std::to_string(r.odst) + "," + std::to_string(r.vdepth) + ")";
+        return false;
+      }
+      return true;
+    }
+  why = "edge kind " + std::to_string(b.kind) + " is not in the B200 kernel registry";
+  return false;
+}
+
+void fill_params(const nd_b200_engine* e, KParams& P) {
+  memset(&P, 0, sizeof P);
+  P.rowptr = e->d_rowptr; P.nbr = e->d_nbr; P.epar = e->d_epar; P.ebid = e->d_ebid; P.blk_row = e->d_blk_row;
+  P.vb = e->d_vb; P.eb = e->d_eb; P.n_vb = (int)e->hvb.size(); P.n_eb = (int)e->heb.size();
+  P.row_base = (int)e->row_begin; P.long_thr = e->long_thr; P.gather_from_u = e->gather_from_u;
+}
+
+template <int VD, int ED, int EK>
+cudaError_t launch_shape(const nd_b200_engine* e, const KParams& P, cudaStream_t st) {
+  if (e->nblocks == 0) return cudaSuccess;
+  if (e->block == 256 && e->ept == 8) rhs_fused_kernel<VD, ED, EK, 256, 8><<<e->nblocks, 256, 0, st>>>(P);
+  else if (e->block == 256 && e->ept == 4) rhs_fused_kernel<VD, ED, EK, 256, 4><<<e->nblocks, 256, 0, st>>>(P);
+  else if (e->block == 128 && e->ept == 8) rhs_fused_kernel<VD, ED, EK, 128, 8><<<e->nblocks, 128, 0, st>>>(P);
+  else if (e->block == 128 && e->ept == 4) rhs_fused_kernel<VD, ED, EK, 128, 4><<<e->nblocks, 128, 0, st>>>(P);
+  else return cudaErrorInvalidConfiguration;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fused(nd_b200_engine* e, const KParams& P, cudaStream_t st) {
+  e->launches += (e->nblocks > 0);
+  if (e->vdepth == 2) return launch_shape<2, 2, ND_B200_E_LINE_DQ>(e, P, st);
+  switch (e->ek) {
+    case ND_B200_E_DIFFUSION: return launch_shape<1, 1, ND_B200_E_DIFFUSION>(e, P, st);
+    case ND_B200_E_DIFFUSION_NOP: return launch_shape<1, 1, ND_B200_E_DIFFUSION_NOP>(e, P, st);
+    case ND_B200_E_KURAMOTO: return launch_shape<1, 1, ND_B200_E_KURAMOTO>(e, P, st);
+    default: return launch_shape<1, 1, EK_GENERIC>(e, P, st);
+  }
+}
+
+cudaError_t launch_vout(nd_b200_engine* e, const double* u, const double* p, double* vout, cudaStream_t st) {
+  const int T = 256;
+  const int nb = (int)((e->nrows_total + T - 1) / T);
+  if (nb == 0) return cudaSuccess;
+  e->launches++;
+  vertex_out_kernel<<<nb, T, 0, st>>>(e->d_vb, (int)e->hvb.size(), e->vdepth, u, p, vout, (int)e->nrows_total);
+  return cudaGetLastError();
+}
+
+int ensure_events(nd_b200_engine* e, std::vector<cudaEvent_t>& v, size_t need) {
+  while (v.size() < need) {
+    cudaEvent_t ev;
+    CUDA_TRY(e, cudaEventCreate(&ev));
+    v.push_back(ev);
+  }
+  return 0;
+}
+
+int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
+  if (d->abi_version != ND_B200_ABI_VERSION) return fail(e, ND_B200_EINVAL, "descriptor abi_version %d != %d", d->abi_version, ND_B200_ABI_VERSION);
+  if (d->nv <= 0) return fail(e, ND_B200_EINVAL, "network needs at least one vertex");
+  if (d->n_vbatches <= 0 || d->n_vbatches > MAX_VB) return fail(e, ND_B200_EUNSUPPORTED, "number of vertex batches %d outside 1..%d", d->n_vbatches, MAX_VB);
+  if (d->n_ebatches < 0 || d->n_ebatches > MAX_EB) return fail(e, ND_B200_EUNSUPPORTED, "number of edge batches %d outside 0..%d", d->n_ebatches, MAX_EB);
+  if (d->ne > 0 && d->n_ebatches == 0) return fail(e, ND_B200_EINVAL, "edges without edge batches");
+  e->device = d->device;
+  e->nv = d->nv; e->ne = d->ne; e->vdepth = d->vdepth; e->edepth = d->ne > 0 ? d->edepth : d->vdepth;
+  e->lastidx_dynamic = d->lastidx_dynamic; e->lastidx_p = d->lastidx_p;
+  e->lastidx_out = d->lastidx_out; e->lastidx_aggr = d->lastidx_aggr;
+  if (!((d->vdepth == 1 && (d->ne == 0 || d->edepth == 1)) || (d->vdepth == 2 && d->edepth == 2)))
+    return fail(e, ND_B200_EUNSUPPORTED, "no kernel for (vdepth,edepth)=(%d,%d); available: (1,1),(2,2)", d->vdepth, d->edepth);
+  if (d->lastidx_dynamic >= INT_MAX || d->lastidx_p >= INT_MAX || d->lastidx_out >= (long long)INT_MAX * 2)
+    return fail(e, ND_B200_EUNSUPPORTED, "network too large for 32-bit offsets");
+  e->long_thr = d->long_row_threshold > 0 ? d->long_row_threshold : 128;
+
+  // ---- vertex batches: registry check, contiguity of rows/states (register_vertices!) ----------
+  std::vector<int> row_of_vertex((size_t)d->nv, -1);
+  long long row = 0, state_expect = 1, out_expect = 1;
+  const int ed = d->ne > 0 ? d->edepth : 0;
+  bool all_statemask1 = true;
+  for (int b = 0; b < d->n_vbatches; ++b) {
+    const nd_b200_vbatch& vb = d->vbatches[b];
+    std::string why;
+    if (!vertex_kind_ok(vb, why)) return fail(e, ND_B200_EUNSUPPORTED, "%s (no CPU fallback)", why.c_str());
+    if (vb.outdim != d->vdepth) return fail(e, ND_B200_EINVAL, "vertex batch %d outdim %d != vdepth %d", b + 1, vb.outdim, d->vdepth);
+    if (vb.count <= 0 || !vb.indices) return fail(e, ND_B200_EINVAL, "vertex batch %d is empty", b + 1);
+    if (vb.state_first != state_expect) return fail(e, ND_B200_EINVAL, "vertex batch %d: statestride.first %lld, expected %lld", b + 1, (long long)vb.state_first, state_expect);
+    if (vb.out_first != out_expect) return fail(e, ND_B200_EINVAL, "vertex batch %d: outbufstride.first %lld, expected %lld", b + 1, (long long)vb.out_first, out_expect);
+    if (ed > 0 && vb.aggr_first != row * ed + 1) return fail(e, ND_B200_EINVAL, "vertex batch %d: inbufstride.first %lld, expected %lld", b + 1, (long long)vb.aggr_first, row * ed + 1);
+    HostVB h{vb.kind, vb.dim, vb.pdim, vb.outdim, vb.count, vb.state_first - 1, vb.p_first - 1, vb.out_first - 1, row};
+    e->hvb.push_back(h);
+    for (long long i = 0; i < vb.count; ++i) {
+      long long vid = vb.indices[i];
+      if (vid < 1 || vid > d->nv || row_of_vertex[(size_t)vid - 1] >= 0) return fail(e, ND_B200_EINVAL, "vertex batch %d: bad or duplicate vertex id %lld", b + 1, vid);
+      row_of_vertex[(size_t)vid - 1] = (int)(row + i);
+    }
+    row += vb.count; state_expect += vb.count * vb.dim; out_expect += vb.count * vb.outdim;
+    if (vb.kind == ND_B200_V_SWING_DQ) all_statemask1 = false;
+  }
+  if (row != d->nv) return fail(e, ND_B200_EINVAL, "vertex batches cover %lld of %lld vertices", row, (long long)d->nv);
+  e->nrows_total = row;
+  e->gather_from_u = (all_statemask1 && d->vdepth == 1) ? 1 : 0;
+
+  e->row_begin = 0; e->row_end = e->nrows_total;
+  if (d->row_end > 0) {
+    if (d->row_begin < 0 || d->row_begin > d->row_end || d->row_end > e->nrows_total) return fail(e, ND_B200_EINVAL, "row partition [%lld,%lld) outside 0..%lld", (long long)d->row_begin, (long long)d->row_end, e->nrows_total);
+    e->row_begin = d->row_begin; e->row_end = d->row_end;
+  }
+  const long long nrows_owned = e->row_end - e->row_begin;
+
+  // gather offset of a vertex's output inside the gather source
+  std::vector<int> goff((size_t)d->nv);
+  for (int b = 0; b < d->n_vbatches; ++b) {
+    const HostVB& h = e->hvb[b];
+    for (long long i = 0; i < h.count; ++i) {
+      long long vid = d->vbatches[b].indices[i];
+      goff[(size_t)vid - 1] = e->gather_from_u ? (int)(h.state0 + i * h.dim) : (int)((h.row0 + i) * d->vdepth);
+    }
+  }
+
+  // ---- edge batches --------------------------------------------------------------------------
+  bool any_epar = false;
+  long long eout_expect = out_expect;
+  std::vector<char> edge_seen((size_t)std::max<long long>(d->ne, 1), 0);
+  for (int b = 0; b < d->n_ebatches; ++b) {
+    const nd_b200_ebatch& eb = d->ebatches[b];
+    std::string why;
+    if (!edge_kind_ok(eb, d->vdepth, why)) return fail(e, ND_B200_EUNSUPPORTED, "%s (no CPU fallback)", why.c_str());
+    if (eb.dim != 0) return fail(e, ND_B200_EUNSUPPORTED, "edge batch %d has dynamic states (ODE edges are not supported by the B200 engine)", b + 1);
+    if (eb.coupling != ND_B200_ANTISYMMETRIC && eb.coupling != ND_B200_SYMMETRIC && eb.coupling != ND_B200_DIRECTED)
+      return fail(e, ND_B200_EUNSUPPORTED, "edge batch %d: unsupported output wrapper %d", b + 1, eb.coupling);
+    const int osrc_expect = eb.coupling == ND_B200_DIRECTED ? 0 : eb.outdim_dst;
+    if (eb.outdim_src != osrc_expect) return fail(e, ND_B200_EINVAL, "edge batch %d: outdim.src %d inconsistent with wrapper", b + 1, eb.outdim_src);
+    if (eb.out_first != eout_expect) return fail(e, ND_B200_EINVAL, "edge batch %d: outbufstride.first %lld, expected %lld", b + 1, (long long)eb.out_first, eout_expect);
+    if (eb.count <= 0 || !eb.indices) return fail(e, ND_B200_EINVAL, "edge batch %d is empty", b + 1);
+    HostEB h{eb.kind, eb.coupling, eb.dim, eb.pdim, eb.outdim_src, eb.outdim_dst, eb.count, eb.p_first - 1, eb.out_first - 1};
+    e->heb.push_back(h);
+    eout_expect += eb.count * (eb.outdim_src + eb.outdim_dst);
+    if (eb.pdim > 0) any_epar = true;
+    for (long long i = 0; i < eb.count; ++i) {
+      long long eid = eb.indices[i];
+      if (eid < 1 || eid > d->ne || edge_seen[(size_t)eid - 1]) return fail(e, ND_B200_EINVAL, "edge batch %d: bad or duplicate edge id %lld", b + 1, eid);
+      edge_seen[(size_t)eid - 1] = 1;
+    }
+  }
+  if (eout_expect - 1 != d->lastidx_out) return fail(e, ND_B200_EINVAL, "lastidx_out %lld inconsistent with batches (%lld)", (long long)d->lastidx_out, eout_expect - 1);
+  if (state_expect - 1 != d->lastidx_dynamic) return fail(e, ND_B200_EINVAL, "lastidx_dynamic %lld inconsistent with vertex batches (%lld)", (long long)d->lastidx_dynamic, state_expect - 1);
+  e->ek = (d->n_ebatches == 1) ? d->ebatches[0].kind : EK_GENERIC;
+  if (d->vdepth == 2 && d->n_ebatches > 1) {
+    // all (2,2) batches must be LINE_DQ with one coupling (single templated kernel)
+    for (int b = 1; b < d->n_ebatches; ++b)
+      if (d->ebatches[b].coupling != d->ebatches[0].coupling) return fail(e, ND_B200_EUNSUPPORTED, "mixed wrappers for dq lines");
+  }
+
+  // ---- destination-sorted CSR over owned rows: count, then stable placement ---------------------
+  std::vector<long long> cnt((size_t)nrows_owned + 1, 0);
+  auto owned = [&](int r) { return r >= e->row_begin && r < e->row_end; };
+  for (int b = 0; b < d->n_ebatches; ++b) {
+    const nd_b200_ebatch& eb = d->ebatches[b];
+    for (long long i = 0; i < eb.count; ++i) {
+      const long long eid = eb.indices[i] - 1;
+      const long long s = d->edge_src[eid], t = d->edge_dst[eid];
+      if (s < 1 || s > d->nv || t < 1 || t > d->nv) return fail(e, ND_B200_EINVAL, "edge %lld endpoint out of range", eid + 1);
+      const int rs = row_of_vertex[(size_t)s - 1], rt = row_of_vertex[(size_t)t - 1];
+      if (eb.outdim_src > 0 && owned(rs)) cnt[(size_t)(rs - e->row_begin) + 1]++;
+      if (owned(rt)) cnt[(size_t)(rt - e->row_begin) + 1]++;
+    }
+  }
+  for (long long r = 0; r < nrows_owned; ++r) cnt[(size_t)r + 1] += cnt[(size_t)r];
+  e->nentries = cnt[(size_t)nrows_owned];
+  if (e->nentries >= INT_MAX) return fail(e, ND_B200_EUNSUPPORTED, "more than 2^31 directed entries on one device");
+  std::vector<int> h_rowptr((size_t)nrows_owned + 1);
+  for (size_t r = 0; r < h_rowptr.size(); ++r) h_rowptr[r] = (int)cnt[r];
+  const bool keep = !(d->flags & ND_B200_FLAG_NO_EXPORT);
+  std::vector<int> h_nbr((size_t)std::max<long long>(e->nentries, 1)), h_epar;
+  std::vector<uint8_t> h_ebid;
+  if (any_epar) h_epar.assign((size_t)std::max<long long>(e->nentries, 1), 0);
+  if (e->ek == EK_GENERIC && d->vdepth == 1) h_ebid.assign((size_t)std::max<long long>(e->nentries, 1), 0);
+  if (keep) { e->h_nbr_vid.resize((size_t)e->nentries); e->h_eid.resize((size_t)e->nentries); e->h_side.resize((size_t)e->nentries); }
+  {
+    std::vector<long long> cur(cnt.begin(), cnt.end() - 1);
+    for (int b = 0; b < d->n_ebatches; ++b) {
+      const nd_b200_ebatch& eb = d->ebatches[b];
+      for (long long i = 0; i < eb.count; ++i) {
+        const long long eid = eb.indices[i] - 1;
+        const long long s = d->edge_src[eid], t = d->edge_dst[eid];
+        const int rs = row_of_vertex[(size_t)s - 1], rt = row_of_vertex[(size_t)t - 1];
+        const int ep = (int)(eb.p_first - 1 + i * eb.pdim);
+        // src output precedes dst output in `o` (register_edges!, src/network_structure.jl:244-245)
+        if (eb.outdim_src > 0 && owned(rs)) {
+          const long long j = cur[(size_t)(rs - e->row_begin)]++;
+          h_nbr[(size_t)j] = ~goff[(size_t)t - 1];
+          if (any_epar) h_epar[(size_t)j] = ep;
+          if (!h_ebid.empty()) h_ebid[(size_t)j] = (uint8_t)b;
+          if (keep) { e->h_nbr_vid[(size_t)j] = (int)t; e->h_eid[(size_t)j] = (int)(eid + 1); e->h_side[(size_t)j] = 1; }
+        }
+        if (owned(rt)) {
+          const long long j = cur[(size_t)(rt - e->row_begin)]++;
+          h_nbr[(size_t)j] = goff[(size_t)s - 1];
+          if (any_epar) h_epar[(size_t)j] = ep;
+          if (!h_ebid.empty()) h_ebid[(size_t)j] = (uint8_t)b;
+          if (keep) { e->h_nbr_vid[(size_t)j] = (int)s; e->h_eid[(size_t)j] = (int)(eid + 1); e->h_side[(size_t)j] = 0; }
+        }
+      }
+    }
+  }
+  if (keep) e->h_rowptr.assign(cnt.begin(), cnt.end());
+
+  // get_buffers tables: gather offsets per edge in batch order
+  if (keep) {
+    e->h_esrc_off.resize((size_t)d->n_ebatches); e->h_edst_off.resize((size_t)d->n_ebatches);
+    for (int b = 0; b < d->n_ebatches; ++b) {
+      const nd_b200_ebatch& eb = d->ebatches[b];
+      e->h_esrc_off[(size_t)b].resize((size_t)eb.count); e->h_edst_off[(size_t)b].resize((size_t)eb.count);
+      for (long long i = 0; i < eb.count; ++i) {
+        const long long eid = eb.indices[i] - 1;
+        e->h_esrc_off[(size_t)b][(size_t)i] = goff[(size_t)d->edge_src[eid] - 1];
+        e->h_edst_off[(size_t)b][(size_t)i] = goff[(size_t)d->edge_dst[eid] - 1];
+      }
+    }
+  }
+
+  // ---- launch shape + thread-block row ranges ----------------------------------------------------
+  if (const char* s = getenv("ND_B200_BLOCK")) e->block = atoi(s);
+  if (const char* s = getenv("ND_B200_EPT")) e->ept = atoi(s);
+  if (!((e->block == 256 || e->block == 128) && (e->ept == 8 || e->ept == 4))) return fail(e, ND_B200_EINVAL, "ND_B200_BLOCK/ND_B200_EPT must be 128|256 / 4|8");
+  const int tile = e->block * e->ept;
+  std::vector<int> blk_row;
+  std::vector<VBDev> dvb;
+  e->n_long = 0;
+  for (size_t b = 0; b < e->hvb.size(); ++b) {
+    const HostVB& h = e->hvb[b];
+    VBDev v{h.kind, h.dim, h.pdim, (int)h.row0, (int)h.count, (int)blk_row.size(), h.state0, h.p0};
+    long long r = std::max<long long>(h.row0, e->row_begin);
+    const long long rend = std::min<long long>(h.row0 + h.count, e->row_end);
+    while (r < rend) {
+      blk_row.push_back((int)r);
+      const long long deg0 = cnt[(size_t)(r - e->row_begin) + 1] - cnt[(size_t)(r - e->row_begin)];
+      if (deg0 > e->long_thr) { e->n_long++; r++; continue; }
+      long long rr = r, ents = 0;
+      while (rr < rend && rr - r < e->block) {
+        const long long deg = cnt[(size_t)(rr - e->row_begin) + 1] - cnt[(size_t)(rr - e->row_begin)];
+        if (deg > e->long_thr || ents + deg > tile) break;
+        ents += deg; rr++;
+      }
+      if (rr == r) {   // a single short row that does not fit a tile: only when long_thr >= tile
+        return fail(e, ND_B200_EUNSUPPORTED, "row with %lld entries exceeds the %d-entry tile with long rows disabled", deg0, tile);
+      }
+      r = rr;
+    }
+    dvb.push_back(v);
+  }
+  e->nblocks = (int)blk_row.size();
+  blk_row.push_back((int)e->row_end);
+  std::vector<EBDev> deb;
+  for (const HostEB& h : e->heb) deb.push_back(EBDev{h.kind, h.coupling, h.pdim});
+
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  if (upload(e, &e->d_rowptr, h_rowptr) || upload(e, &e->d_nbr, h_nbr) || upload(e, &e->d_blk_row, blk_row) ||
+      upload(e, &e->d_vb, dvb) || upload(e, &e->d_eb, deb))
+    return ND_B200_ECUDA;
+  if (any_epar && upload(e, &e->d_epar, h_epar)) return ND_B200_ECUDA;
+  if (e->ek == EK_GENERIC && d->vdepth == 1 && upload(e, &e->d_ebid, h_ebid)) return ND_B200_ECUDA;
+  if (!e->gather_from_u) {
+    for (int k = 0; k < 2; ++k) CUDA_TRY(e, cudaMalloc((void**)&e->d_vout[k], sizeof(double) * (size_t)(e->nrows_total * e->vdepth)));
+  }
+  return ND_B200_OK;
+}
+
+int check_call(nd_b200_engine* e, const void* du, const void* u, const void* p) {
+  if (!e) return ND_B200_EINVAL;
+  if (!du || !u) return fail(e, ND_B200_EINVAL, "du or u is NULL (expected size %lld)", e->lastidx_dynamic);
+  if (e->lastidx_p > 0 && !p) return fail(e, ND_B200_EINVAL, "p is NULL but the network has %lld parameters", e->lastidx_p);
+  return 0;
+}
+
+int rhs_impl(nd_b200_engine* e, double* du, const double* u, const double* p, double t, cudaStream_t st, int mode,
+             double* aggbuf) {
+  KParams P;
+  fill_params(e, P);
+  P.u = u; P.p = p; P.du = du; P.mode = mode; P.aggbuf = aggbuf; P.t = t;
+  P.gsrc = u;
+  size_t ti = 0;
+  if (e->timing) {
+    if (ensure_events(e, e->ev, e->ev_used + 2) || ensure_events(e, e->ev_pre, e->ev_pre_used + 2)) return ND_B200_ECUDA;
+  }
+  if (!e->gather_from_u) {
+    if (e->timing) CUDA_TRY(e, cudaEventRecord(e->ev_pre[e->ev_pre_used], st));
+    CUDA_TRY(e, launch_vout(e, u, p, e->d_vout[0], st));
+    if (e->timing) { CUDA_TRY(e, cudaEventRecord(e->ev_pre[e->ev_pre_used + 1], st)); e->ev_pre_used += 2; }
+    P.gsrc = e->d_vout[0];
+  }
+  (void)ti;
+  if (e->timing) CUDA_TRY(e, cudaEventRecord(e->ev[e->ev_used], st));
+  CUDA_TRY(e, launch_fused(e, P, st));
+  if (e->timing) { CUDA_TRY(e, cudaEventRecord(e->ev[e->ev_used + 1], st)); e->ev_used += 2; }
+  return ND_B200_OK;
+}
+
+void destroy_graph(nd_b200_engine* e) {
+  if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
+  if (e->graph) cudaGraphDestroy(e->graph);
+  e->graph_exec = nullptr; e->graph = nullptr; e->graph_steps = 0;
+}
+
+// enqueue one fused RK4 step (4 launches) on st.  u is updated in place.
+int rk4_step_enqueue(nd_b200_engine* e, double* u, const double* p, double t, double dt, cudaStream_t st) {
+  KParams P;
+  fill_params(e, P);
+  P.p = p; P.mode = MODE_RK; P.u0 = u; P.ksum = e->d_ksum; P.h6 = dt / 6.0;
+  const double h2 = 0.5 * dt;
+  const double* in[4] = {u, e->d_tmpA, e->d_tmpB, e->d_tmpA};
+  double* out[4] = {e->d_tmpA, e->d_tmpB, e->d_tmpA, u};
+  const double hs[4] = {h2, h2, dt, 0.0};
+  const double ts[4] = {t, t + h2, t + h2, t + dt};
+  for (int s = 0; s < 4; ++s) {
+    P.stage = s + 1; P.u = in[s]; P.unext = out[s]; P.hs = hs[s]; P.t = ts[s];
+    if (e->gather_from_u) { P.gsrc = in[s]; P.vout_next = nullptr; }
+    else { P.gsrc = e->d_vout[s & 1]; P.vout_next = e->d_vout[(s + 1) & 1]; }   // stage 4 leaves outputs of the new u in d_vout[0]
+    CUDA_TRY(e, launch_fused(e, P, st));
+  }
+  return ND_B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int nd_b200_abi_version(void) { return ND_B200_ABI_VERSION; }
+
+int nd_b200_create(const nd_b200_desc* desc, nd_b200_engine** out) {
+  if (!desc || !out) return fail(nullptr, ND_B200_EINVAL, "null descriptor or output pointer");
+  *out = nullptr;
+  nd_b200_engine* e = new (std::nothrow) nd_b200_engine();
+  if (!e) return fail(nullptr, ND_B200_ENOMEM, "out of host memory");
+  int rc;
+  try {
+    rc = build_engine(e, desc);
+  } catch (const std::bad_alloc&) {
+    rc = fail(e, ND_B200_ENOMEM, "out of host memory while building the CSR");
+  } catch (...) {
+    rc = fail(e, ND_B200_EINVAL, "unexpected failure while building the CSR");
+  }
+  if (rc != ND_B200_OK) {
+    g_create_error = e->err;
+    nd_b200_destroy(e);
+    return rc;
+  }
+  *out = e;
+  return ND_B200_OK;
+}
+
+void nd_b200_destroy(nd_b200_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  destroy_graph(e);
+  cudaFree(e->d_rowptr); cudaFree(e->d_nbr); cudaFree(e->d_epar); cudaFree(e->d_blk_row); cudaFree(e->d_ebid);
+  cudaFree(e->d_vb); cudaFree(e->d_eb); cudaFree(e->d_vout[0]); cudaFree(e->d_vout[1]);
+  for (int* q : e->d_esrc_off) cudaFree(q);
+  for (int* q : e->d_edst_off) cudaFree(q);
+  cudaFree(e->d_tmpA); cudaFree(e->d_tmpB); cudaFree(e->d_ksum);
+  cudaFree(e->d_hu); cudaFree(e->d_hp); cudaFree(e->d_hdu);
+  if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
+  if (e->own_stream) cudaStreamDestroy(e->own_stream);
+  for (cudaEvent_t ev : e->ev) cudaEventDestroy(ev);
+  for (cudaEvent_t ev : e->ev_pre) cudaEventDestroy(ev);
+  delete e;
+}
+
+const char* nd_b200_last_error(const nd_b200_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+int nd_b200_rhs(nd_b200_engine* e, double* du, const double* u, const double* p, double t, void* stream) {
+  if (int rc = check_call(e, du, u, p)) return rc;
+  return rhs_impl(e, du, u, p, t, (cudaStream_t)stream, MODE_DU, nullptr);
+}
+
+int nd_b200_rhs_host(nd_b200_engine* e, double* du_host, const double* u_host, const double* p_host, double t) {
+  if (int rc = check_call(e, du_host, u_host, p_host)) return rc;
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  if (!e->own_stream) CUDA_TRY(e, cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+  const size_t nb = sizeof(double) * (size_t)e->lastidx_dynamic, pb = sizeof(double) * (size_t)e->lastidx_p;
+  if (!e->d_hu) {
+    CUDA_TRY(e, cudaMalloc((void**)&e->d_hu, std::max<size_t>(nb, 8)));
+    CUDA_TRY(e, cudaMalloc((void**)&e->d_hdu, std::max<size_t>(nb, 8)));
+    CUDA_TRY(e, cudaMalloc((void**)&e->d_hp, std::max<size_t>(pb, 8)));
+  }
+  cudaStream_t st = e->own_stream;
+  CUDA_TRY(e, cudaMemcpyAsync(e->d_hu, u_host, nb, cudaMemcpyHostToDevice, st));
+  if (pb) CUDA_TRY(e, cudaMemcpyAsync(e->d_hp, p_host, pb, cudaMemcpyHostToDevice, st));
+  if (int rc = rhs_impl(e, e->d_hdu, e->d_hu, pb ? e->d_hp : nullptr, t, st, MODE_DU, nullptr)) return rc;
+  // only the states of owned rows are defined; for a partitioned engine copy the whole vector anyway
+  CUDA_TRY(e, cudaMemcpyAsync(du_host, e->d_hdu, nb, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(e, cudaStreamSynchronize(st));
+  return ND_B200_OK;
+}
+
+int nd_b200_get_buffers(nd_b200_engine* e, double* o, double* aggbuf, const double* u, const double* p, double t,
+                        void* stream) {
+  if (!e) return ND_B200_EINVAL;
+  if (!u || (e->lastidx_p > 0 && !p)) return fail(e, ND_B200_EINVAL, "u or p is NULL");
+  if (e->h_esrc_off.size() != e->heb.size()) return fail(e, ND_B200_EUNSUPPORTED, "engine was created with ND_B200_FLAG_NO_EXPORT");
+  cudaStream_t st = (cudaStream_t)stream;
+  const double* gsrc = u;
+  if (!e->gather_from_u) {
+    CUDA_TRY(e, launch_vout(e, u, p, e->d_vout[0], st));
+    gsrc = e->d_vout[0];
+  }
+  if (o) {
+    // vertex outputs occupy o[0 .. nv*vdepth) in row order (register_vertices!)
+    CUDA_TRY(e, launch_vout(e, u, p, o, st));
+    if (e->d_esrc_off.empty()) {
+      e->d_esrc_off.assign(e->heb.size(), nullptr); e->d_edst_off.assign(e->heb.size(), nullptr);
+      for (size_t b = 0; b < e->heb.size(); ++b)
+        if (upload(e, &e->d_esrc_off[b], e->h_esrc_off[b]) || upload(e, &e->d_edst_off[b], e->h_edst_off[b])) return ND_B200_ECUDA;
+    }
+    for (size_t b = 0; b < e->heb.size(); ++b) {
+      const HostEB& h = e->heb[b];
+      const int T = 256;
+      const int nb = (int)((h.count + T - 1) / T);
+      e->launches++;
+      if (e->vdepth == 2)
+        edge_out_kernel<2, 2><<<nb, T, 0, st>>>(h.kind, h.coupling, h.pdim, h.osrc, h.count, e->d_esrc_off[b], e->d_edst_off[b], h.p0, h.out0, gsrc, p, o);
+      else
+        edge_out_kernel<1, 1><<<nb, T, 0, st>>>(h.kind, h.coupling, h.pdim, h.osrc, h.count, e->d_esrc_off[b], e->d_edst_off[b], h.p0, h.out0, gsrc, p, o);
+      CUDA_TRY(e, cudaGetLastError());
+    }
+  }
+  if (aggbuf) {
+    KParams P;
+    fill_params(e, P);
+    P.u = u; P.p = p; P.gsrc = gsrc; P.mode = MODE_AGG; P.aggbuf = aggbuf; P.t = t;
+    CUDA_TRY(e, launch_fused(e, P, st));
+  }
+  return ND_B200_OK;
+}
+
+int nd_b200_rk4(nd_b200_engine* e, double* u, const double* p, double t0, double dt, int64_t nsteps, void* stream) {
+  if (int rc = check_call(e, u, u, p)) return rc;
+  if (e->row_end - e->row_begin != e->nrows_total) return fail(e, ND_B200_EUNSUPPORTED, "nd_b200_rk4 on a partitioned engine: drive the stages from the host (halo exchange between stages)");
+  if (nsteps <= 0) return ND_B200_OK;
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t nb = sizeof(double) * (size_t)e->lastidx_dynamic;
+  if (!e->d_tmpA) {
+    CUDA_TRY(e, cudaMalloc((void**)&e->d_tmpA, nb));
+    CUDA_TRY(e, cudaMalloc((void**)&e->d_tmpB, nb));
+    CUDA_TRY(e, cudaMalloc((void**)&e->d_ksum, nb));
+  }
+  if (!e->gather_from_u) CUDA_TRY(e, launch_vout(e, u, p, e->d_vout[0], st));
+  // The registry models are autonomous, so one captured step can be replayed for every t.
+  const int UNROLL = 8;
+  const int per_graph = (int)std::min<int64_t>(UNROLL, nsteps);
+  if (!e->graph_exec || e->graph_u != u || e->graph_p != p || e->graph_dt != dt || e->graph_steps != per_graph) {
+    destroy_graph(e);
+    if (!e->cap_stream) CUDA_TRY(e, cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
+    CUDA_TRY(e, cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal));
+    const long long launches_before = e->launches;
+    int rc = ND_B200_OK;
+    for (int s = 0; s < per_graph && rc == ND_B200_OK; ++s) rc = rk4_step_enqueue(e, u, p, t0 + s * dt, dt, e->cap_stream);
+    cudaError_t ce = cudaStreamEndCapture(e->cap_stream, &e->graph);
+    e->launches = launches_before;   // captured, not launched
+    if (rc != ND_B200_OK) return rc;
+    CUDA_TRY(e, ce);
+    CUDA_TRY(e, cudaGraphInstantiate(&e->graph_exec, e->graph, 0));
+    e->graph_u = u; e->graph_p = p; e->graph_dt = dt; e->graph_steps = per_graph;
+  }
+  const long long per_step = 4;
+  int64_t done = 0;
+  while (nsteps - done >= per_graph) {
+    CUDA_TRY(e, cudaGraphLaunch(e->graph_exec, st));
+    e->launches += per_step * per_graph;
+    done += per_graph;
+  }
+  for (; done < nsteps; ++done)
+    if (int rc = rk4_step_enqueue(e, u, p, t0 + (double)done * dt, dt, st)) return rc;
+  return ND_B200_OK;
+}
+
+int nd_b200_export_sizes(const nd_b200_engine* e, int64_t sizes[8]) {
+  if (!e || !sizes) return ND_B200_EINVAL;
+  sizes[0] = e->row_end - e->row_begin; sizes[1] = e->nentries; sizes[2] = e->nblocks; sizes[3] = e->n_long;
+  sizes[4] = e->gather_from_u; sizes[5] = e->gather_from_u ? 1 : 2; sizes[6] = e->row_begin; sizes[7] = e->row_end;
+  return ND_B200_OK;
+}
+
+int nd_b200_export_tables(const nd_b200_engine* e, int64_t* rowptr, int64_t* nbr_vertex, int64_t* edge_id, int32_t* side) {
+  if (!e) return ND_B200_EINVAL;
+  if (e->h_rowptr.empty()) return fail(const_cast<nd_b200_engine*>(e), ND_B200_EUNSUPPORTED, "engine was created with ND_B200_FLAG_NO_EXPORT");
+  for (size_t r = 0; r < e->h_rowptr.size(); ++r) rowptr[r] = e->h_rowptr[r];
+  for (size_t j = 0; j < (size_t)e->nentries; ++j) {
+    nbr_vertex[j] = e->h_nbr_vid[j]; edge_id[j] = e->h_eid[j]; side[j] = e->h_side[j];
+  }
+  return ND_B200_OK;
+}
+
+int64_t nd_b200_launch_count(const nd_b200_engine* e) { return e ? e->launches : 0; }
+
+int nd_b200_set_timing(nd_b200_engine* e, int enabled) {
+  if (!e) return ND_B200_EINVAL;
+  e->timing = enabled != 0;
+  e->ev_used = 0; e->ev_pre_used = 0;
+  return ND_B200_OK;
+}
+
+int nd_b200_timings(nd_b200_engine* e, double* fused_ms_avg, double* prepass_ms_avg, int64_t* ncalls) {
+  if (!e) return ND_B200_EINVAL;
+  CUDA_TRY(e, cudaDeviceSynchronize());
+  double sum = 0.0, sum_pre = 0.0;
+  for (size_t i = 0; i + 1 < e->ev_used; i += 2) {
+    float ms = 0.f;
+    CUDA_TRY(e, cudaEventElapsedTime(&ms, e->ev[i], e->ev[i + 1]));
+    sum += ms;
+  }
+  for (size_t i = 0; i + 1 < e->ev_pre_used; i += 2) {
+    float ms = 0.f;
+    CUDA_TRY(e, cudaEventElapsedTime(&ms, e->ev_pre[i], e->ev_pre[i + 1]));
+    sum_pre += ms;
+  }
+  const int64_t n = (int64_t)(e->ev_used / 2);
+  if (fused_ms_avg) *fused_ms_avg = n ? sum / (double)n : 0.0;
+  if (prepass_ms_avg) *prepass_ms_avg = e->ev_pre_used ? sum_pre / (double)(e->ev_pre_used / 2) : 0.0;
+  if (ncalls) *ncalls = n;
+  e->ev_used = 0; e->ev_pre_used = 0;
+  return ND_B200_OK;
+}
+
+void* nd_b200_host_alloc(int64_t bytes) {
+  void* q = nullptr;
+  if (cudaHostAlloc(&q, (size_t)std::max<int64_t>(bytes, 8), cudaHostAllocDefault) != cudaSuccess) return nullptr;
+  return q;
+}
+void nd_b200_host_free(void* q) { if (q) cudaFreeHost(q); }
+
+}  // extern "C"

@@ -1,0 +1,409 @@
+// nd_b200_kernels.cuh -- sm_100a kernels of the fused network RHS.
+//
+// One fused kernel replaces the reference's per-call pipeline
+//   fill!(du) / fill!(o,NaN) / fill!(aggbuf)            src/coreloop.jl:24-30
+//   PASS 1 vertex g (StateMask)                         src/coreloop.jl:39
+//   gather!(gbuf, o)                                    src/coreloop.jl:67, src/gbufs.jl:25
+//   PASS 5 edge g                                       src/coreloop.jl:78
+//   aggregate!(aggbuf, o)                               src/coreloop.jl:90, src/aggregators.jl:140-151
+//   PASS 6 vertex f                                     src/coreloop.jl:97
+// over a destination-sorted CSR whose rows are the aggregation slots and whose entries are in the
+// reference's accumulation order (ascending position in `o`).  Neither `o`, `gbuf` nor `aggbuf`
+// exist in memory: edge values live in shared memory, row sums in registers.
+//
+// Compiled with -fmad=false: the reference (Julia) never contracts a*b+c, so neither do we.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "nd_b200.h"
+
+namespace ndb {
+
+struct VBDev {          // one vertex ComponentBatch, 0-based offsets
+  int kind, dim, pdim;
+  int row0, nrows;      // aggregation-slot rows [row0, row0+nrows) of this batch (global numbering)
+  int blk0;             // first thread block working on this batch
+  long long state0, p0; // offsets into u / p
+};
+struct EBDev {          // one edge ComponentBatch
+  int kind, coupling, pdim;
+};
+
+enum { MODE_DU = 0, MODE_AGG = 1, MODE_RK = 2 };
+constexpr int EK_GENERIC = -1;   // several edge batches: per-entry batch id lookup
+
+struct KParams {
+  const int* __restrict__ rowptr;      // [nrows_owned+1], entries of owned rows, relative to row_base
+  const int* __restrict__ nbr;         // per entry: offset of the neighbour's output in gsrc; ~offset when this row is the edge's src
+  const int* __restrict__ epar;        // per entry: offset of the edge's parameter block in p (nullptr when no edge has parameters)
+  const uint8_t* __restrict__ ebid;    // per entry: edge batch id (EK_GENERIC only)
+  const int* __restrict__ blk_row;     // [nblocks+1] first (global) row of each thread block
+  const VBDev* __restrict__ vb;
+  const EBDev* __restrict__ eb;
+  int n_vb, n_eb;
+  int row_base;                        // first owned row
+  int long_thr;                        // rows with more entries are reduced by the whole block
+  int gather_from_u;                   // 1: vertex outputs are read straight from u (all StateMask, vdepth 1)
+  int mode;
+  const double* __restrict__ u;        // state vector the vertex models read
+  const double* __restrict__ gsrc;     // gather source: u (gather_from_u) or the materialised vertex outputs
+  const double* __restrict__ p;
+  double* __restrict__ du;             // MODE_DU
+  double* __restrict__ aggbuf;         // MODE_AGG
+  // MODE_RK: fused classical RK4 stage (see nd_b200_rk4)
+  int stage;                           // 1..4
+  const double* __restrict__ u0;       // state at the start of the step
+  double* __restrict__ unext;          // stage 1-3: next stage input; stage 4: u0 itself
+  double* __restrict__ ksum;           // running k1 + 2k2 + 2k3
+  double* __restrict__ vout_next;      // materialised outputs of unext (when !gather_from_u)
+  double hs;                           // dt/2, dt/2, dt for stages 1..3
+  double h6;                           // dt/6
+  double t;
+};
+
+// ------------------------------------------------------------------------------------------------
+// model arithmetic -- expression order exactly as the cited reference source (and as oracle/nd_oracle.c)
+// ------------------------------------------------------------------------------------------------
+
+// inner edge function: writes the DST output, g(odst, vsrc, vdst, p, t)
+template <int VD, int ED>
+__device__ __forceinline__ void edge_g_dst(int kind, double* odst, const double* vs, const double* vd,
+                                           const double* __restrict__ pe) {
+  if constexpr (VD == 1 && ED == 1) {
+    switch (kind) {
+      case ND_B200_E_DIFFUSION:      // test/ComponentLibrary.jl:8-10
+        odst[0] = pe[0] * (vs[0] - vd[0]);
+        break;
+      case ND_B200_E_DIFFUSION_NOP:  // benchmark/benchmark_models.jl:5-8
+        odst[0] = vs[0] - vd[0];
+        break;
+      case ND_B200_E_KURAMOTO:       // test/ComponentLibrary.jl:51-53
+        odst[0] = pe[0] * sin(vs[0] - vd[0]);
+        break;
+      default: odst[0] = 0.0;
+    }
+  } else if constexpr (VD == 2 && ED == 2) {
+    // ND_B200_E_LINE_DQ, test/ComponentLibrary.jl:212-245: idst = active*1/Z*(Vsrc-Vdst), Z = R+jX
+    double R = pe[0], X = pe[1], active = pe[2];
+    double dr = vs[0] - vd[0];
+    double di = vs[1] - vd[1];
+    double den = R * R + X * X;
+    odst[0] = active * ((R * dr + X * di) / den);
+    odst[1] = active * ((R * di - X * dr) / den);
+  }
+}
+
+// value an entry contributes to ITS row: the dst output if the row is the edge's dst, else the src
+// output produced by the wrapper (AntiSymmetric: -odst, Symmetric: odst; src/component_functions.jl:117-152)
+template <int VD, int ED>
+__device__ __forceinline__ void entry_value(int kind, int coupling, int side, const double* self,
+                                            const double* xn, const double* __restrict__ pe, double* val) {
+  const double* vs = side ? self : xn;
+  const double* vd = side ? xn : self;
+  edge_g_dst<VD, ED>(kind, val, vs, vd, pe);
+  if (side && coupling == ND_B200_ANTISYMMETRIC) {
+#pragma unroll
+    for (int d = 0; d < ED; ++d) val[d] = -val[d];
+  }
+}
+
+// vertex g for non-StateMask models: NoFeedForward g(out,u,p,t)
+__device__ __forceinline__ void vertex_g(int kind, int outdim, double* out, const double* v,
+                                         const double* __restrict__ pv) {
+  if (kind == ND_B200_V_SWING_DQ) {   // test/ComponentLibrary.jl:158-159
+    double V = pv[3];
+    out[0] = V * cos(v[0]);
+    out[1] = V * sin(v[0]);
+  } else {                            // StateMask(1:outdim), src/component_functions.jl:81-99
+    for (int k = 0; k < outdim; ++k) out[k] = v[k];
+  }
+}
+
+// vertex f: f(dv, v, acc, p, t).  selfout = this vertex's own outputs (only used by SWING_DQ, whose f
+// recomputes u_r,u_i with the same expressions as its g).
+template <int VD, int ED>
+__device__ __forceinline__ void vertex_f(int kind, double* dv, const double* v, const double* acc,
+                                         const double* __restrict__ pv, const double* selfout) {
+  switch (kind) {
+    case ND_B200_V_DIFFUSION:            // test/ComponentLibrary.jl:42-45
+      dv[0] = acc[0];
+      break;
+    case ND_B200_V_KURAMOTO_FIRST:       // test/ComponentLibrary.jl:69-71
+      dv[0] = pv[0] + acc[0];
+      break;
+    case ND_B200_V_KURAMOTO_SECOND: {    // test/ComponentLibrary.jl:59-63
+      double M = pv[0], D = pv[1], Pm = pv[2];
+      dv[0] = v[1];
+      dv[1] = 1.0 / M * (Pm - D * v[1] + acc[0]);
+    } break;
+    case ND_B200_V_KURAMOTO_SECOND_BENCH: {  // benchmark/benchmark_models.jl:37-41
+      double P = pv[0];
+      dv[0] = v[1];
+      dv[1] = P - 1.0 * v[1];
+      dv[1] += acc[0];
+    } break;
+    case ND_B200_V_SWING_DQ: {           // test/ComponentLibrary.jl:139-161
+      if constexpr (VD == 2 && ED == 2) {
+        double M = pv[0], D = pv[1], Pmech = pv[2];
+        double Pel = selfout[0] * acc[0] + selfout[1] * acc[1];
+        double Pdamping = -D * v[1];
+        dv[0] = v[1];
+        dv[1] = 1.0 / M * (Pmech + Pdamping + Pel);
+      }
+    } break;
+  }
+}
+
+// PASS 6 for one row + the epilogue selected by mode
+template <int VD, int ED>
+__device__ __forceinline__ void vertex_phase(const KParams& P, const VBDev& B, int row, const double* acc,
+                                             const double* selfout) {
+  if (P.mode == MODE_AGG) {
+#pragma unroll
+    for (int d = 0; d < ED; ++d) P.aggbuf[(long long)row * ED + d] = acc[d];
+    return;
+  }
+  const long long i = row - B.row0;
+  const long long s = B.state0 + i * B.dim;
+  const double* __restrict__ pv = P.p + B.p0 + i * B.pdim;
+  double v[2] = {0.0, 0.0}, dv[2] = {0.0, 0.0};
+  const int dim = B.dim;  // registry: dim <= 2
+  if (dim == 2 && ((s & 1) == 0)) {
+    double2 t2 = *reinterpret_cast<const double2*>(P.u + s);
+    v[0] = t2.x; v[1] = t2.y;
+  } else {
+    for (int c = 0; c < dim; ++c) v[c] = P.u[s + c];
+  }
+  vertex_f<VD, ED>(B.kind, dv, v, acc, pv, selfout);
+  if (P.mode == MODE_DU) {
+    if (dim == 2 && ((s & 1) == 0)) {
+      *reinterpret_cast<double2*>(P.du + s) = make_double2(dv[0], dv[1]);
+    } else {
+      for (int c = 0; c < dim; ++c) P.du[s + c] = dv[c];
+    }
+    return;
+  }
+  // MODE_RK: classical RK4, operation order of oracle/nd_oracle.c ndo_rk4:
+  //   u <- u + (dt/6)*(((k1 + 2k2) + 2k3) + k4)
+  double un[2] = {0.0, 0.0};
+  for (int c = 0; c < dim; ++c) {
+    const long long idx = s + c;
+    if (P.stage == 1) {
+      P.ksum[idx] = dv[c];
+      un[c] = v[c] + P.hs * dv[c];          // u == u0 in stage 1
+    } else if (P.stage < 4) {
+      P.ksum[idx] = P.ksum[idx] + 2.0 * dv[c];
+      un[c] = P.u0[idx] + P.hs * dv[c];
+    } else {
+      un[c] = P.u0[idx] + P.h6 * (P.ksum[idx] + dv[c]);
+    }
+    P.unext[idx] = un[c];
+  }
+  if (!P.gather_from_u) {
+    double out[VD];
+    vertex_g(B.kind, VD, out, un, pv);
+#pragma unroll
+    for (int k = 0; k < VD; ++k) P.vout_next[(long long)row * VD + k] = out[k];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused gather -> edge -> ordered row reduce -> vertex kernel
+// ------------------------------------------------------------------------------------------------
+template <int VD, int ED, int EK, int BLOCK, int EPT>
+__global__ void __launch_bounds__(BLOCK) rhs_fused_kernel(const __grid_constant__ KParams P) {
+  constexpr int TILE = BLOCK * EPT;
+  static_assert(BLOCK <= 256, "row ids are stored as uint8");
+  __shared__ double s_val[TILE * ED];
+  __shared__ double s_self[BLOCK * VD];
+  __shared__ int s_rp[BLOCK + 1];
+  __shared__ uint8_t s_rowid[TILE];
+
+  const int tid = threadIdx.x;
+  const int blk = blockIdx.x;
+  const int r0 = P.blk_row[blk];
+  const int nrows = P.blk_row[blk + 1] - r0;
+  int b = 0;
+  for (int i = 1; i < P.n_vb; ++i)
+    if (blk >= P.vb[i].blk0) b = i;
+  const VBDev B = P.vb[b];
+  const int e0 = P.rowptr[r0 - P.row_base];
+  const int ne = P.rowptr[r0 - P.row_base + nrows] - e0;
+  const int kind0 = (EK == EK_GENERIC) ? 0 : EK;
+  const int coupling0 = P.n_eb > 0 ? P.eb[0].coupling : 0;
+  const bool has_epar = P.epar != nullptr;
+
+  // ---------------- long row: whole block reduces one row with a fixed-shape tree -----------------
+  if (nrows == 1 && ne > P.long_thr) {
+    double self[VD];
+    const long long sidx = P.gather_from_u ? (B.state0 + (long long)(r0 - B.row0) * B.dim) : (long long)r0 * VD;
+#pragma unroll
+    for (int k = 0; k < VD; ++k) self[k] = P.gsrc[sidx + k];
+    double part[ED];
+#pragma unroll
+    for (int d = 0; d < ED; ++d) part[d] = 0.0;
+    for (int jj = tid; jj < ne; jj += BLOCK) {
+      int nb = P.nbr[e0 + jj];
+      const int side = nb < 0;
+      nb = side ? ~nb : nb;
+      double xn[VD];
+#pragma unroll
+      for (int k = 0; k < VD; ++k) xn[k] = P.gsrc[(long long)nb + k];
+      const double* pe = has_epar ? P.p + P.epar[e0 + jj] : P.p;
+      int kind = kind0, coupling = coupling0;
+      if constexpr (EK == EK_GENERIC) {
+        const EBDev E = P.eb[P.ebid[e0 + jj]];
+        kind = E.kind; coupling = E.coupling;
+      }
+      double val[ED];
+      entry_value<VD, ED>(kind, coupling, side, self, xn, pe, val);
+#pragma unroll
+      for (int d = 0; d < ED; ++d) part[d] = part[d] + val[d];
+    }
+#pragma unroll
+    for (int d = 0; d < ED; ++d) s_val[tid * ED + d] = part[d];
+    __syncthreads();
+    for (int s = BLOCK / 2; s > 0; s >>= 1) {
+      if (tid < s) {
+#pragma unroll
+        for (int d = 0; d < ED; ++d) s_val[tid * ED + d] = s_val[tid * ED + d] + s_val[(tid + s) * ED + d];
+      }
+      __syncthreads();
+    }
+    if (tid == 0) {
+      double acc[ED];
+#pragma unroll
+      for (int d = 0; d < ED; ++d) acc[d] = s_val[d];
+      vertex_phase<VD, ED>(P, B, r0, acc, self);
+    }
+    return;
+  }
+
+  // ---------------- regular tile: <= BLOCK rows, <= TILE entries ---------------------------------
+  // (1) coalesced index loads, issued first so they overlap the row bookkeeping
+  int nb[EPT], ep[EPT];
+#pragma unroll
+  for (int k = 0; k < EPT; ++k) {
+    const int jj = k * BLOCK + tid;
+    nb[k] = 0; ep[k] = 0;
+    if (jj < ne) {
+      nb[k] = P.nbr[e0 + jj];
+      if (has_epar) ep[k] = P.epar[e0 + jj];
+    }
+  }
+  // (2) row pointers + own outputs of the block's rows
+  if (tid < nrows) {
+    s_rp[tid] = P.rowptr[r0 - P.row_base + tid] - e0;
+    const long long sidx = P.gather_from_u ? (B.state0 + (long long)(r0 + tid - B.row0) * B.dim)
+                                           : (long long)(r0 + tid) * VD;
+#pragma unroll
+    for (int k = 0; k < VD; ++k) s_self[tid * VD + k] = P.gsrc[sidx + k];
+  }
+  if (tid == 0) s_rp[nrows] = ne;
+  __syncthreads();
+  // (3) entry -> local row map
+  if (tid < nrows) {
+    const int a = s_rp[tid], z = s_rp[tid + 1];
+    for (int jj = a; jj < z; ++jj) s_rowid[jj] = (uint8_t)tid;
+  }
+  // (4) the gather: EPT independent random reads per thread
+  double xn[EPT][VD];
+#pragma unroll
+  for (int k = 0; k < EPT; ++k) {
+    const int jj = k * BLOCK + tid;
+    const int off = nb[k] < 0 ? ~nb[k] : nb[k];
+#pragma unroll
+    for (int q = 0; q < VD; ++q) xn[k][q] = 0.0;
+    if (jj < ne) {
+      if constexpr (VD == 2) {
+        const double2 t2 = *reinterpret_cast<const double2*>(P.gsrc + off);
+        xn[k][0] = t2.x; xn[k][1] = t2.y;
+      } else {
+#pragma unroll
+        for (int q = 0; q < VD; ++q) xn[k][q] = P.gsrc[(long long)off + q];
+      }
+    }
+  }
+  __syncthreads();
+  // (5) edge evaluation, one entry per thread per k
+#pragma unroll
+  for (int k = 0; k < EPT; ++k) {
+    const int jj = k * BLOCK + tid;
+    if (jj < ne) {
+      const int side = nb[k] < 0;
+      const int r = s_rowid[jj];
+      double self[VD];
+#pragma unroll
+      for (int q = 0; q < VD; ++q) self[q] = s_self[r * VD + q];
+      int kind = kind0, coupling = coupling0;
+      if constexpr (EK == EK_GENERIC) {
+        const EBDev E = P.eb[P.ebid[e0 + jj]];
+        kind = E.kind; coupling = E.coupling;
+      }
+      double val[ED];
+      entry_value<VD, ED>(kind, coupling, side, self, xn[k], P.p + ep[k], val);
+#pragma unroll
+      for (int d = 0; d < ED; ++d) s_val[jj * ED + d] = val[d];
+    }
+  }
+  __syncthreads();
+  // (6) ordered per-row accumulation (the reference's sequential order) + vertex model
+  if (tid < nrows) {
+    double acc[ED];
+#pragma unroll
+    for (int d = 0; d < ED; ++d) acc[d] = 0.0;
+    const int a = s_rp[tid], z = s_rp[tid + 1];
+    for (int jj = a; jj < z; ++jj) {
+#pragma unroll
+      for (int d = 0; d < ED; ++d) acc[d] = acc[d] + s_val[jj * ED + d];
+    }
+    double self[VD];
+#pragma unroll
+    for (int q = 0; q < VD; ++q) self[q] = s_self[tid * VD + q];
+    vertex_phase<VD, ED>(P, B, r0 + tid, acc, self);
+  }
+}
+
+// PASS 1 for networks whose vertex outputs are not plain state copies: vout[row*VD + k] = g_v(u, p)
+__global__ void vertex_out_kernel(const VBDev* __restrict__ vb, int n_vb, int vd, const double* __restrict__ u,
+                                  const double* __restrict__ p, double* __restrict__ vout, int nrows_total) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= nrows_total) return;
+  int b = 0;
+  for (int i = 1; i < n_vb; ++i)
+    if (row >= vb[i].row0) b = i;
+  const VBDev B = vb[b];
+  const long long i = row - B.row0;
+  double v[2] = {0.0, 0.0}, out[2] = {0.0, 0.0};
+  for (int c = 0; c < B.dim && c < 2; ++c) v[c] = u[B.state0 + i * B.dim + c];
+  vertex_g(B.kind, vd, out, v, p + B.p0 + i * B.pdim);
+  for (int k = 0; k < vd; ++k) vout[(long long)row * vd + k] = out[k];
+}
+
+// get_buffers support: edge outputs into the reference's `o` layout (src range first, dst right after)
+template <int VD, int ED>
+__global__ void edge_out_kernel(int kind, int coupling, int pdim, int osrc, long long count,
+                                const int* __restrict__ esrc_off, const int* __restrict__ edst_off,
+                                long long p0, long long out0, const double* __restrict__ gsrc,
+                                const double* __restrict__ p, double* __restrict__ o) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  double vs[VD], vd[VD], val[ED];
+#pragma unroll
+  for (int k = 0; k < VD; ++k) { vs[k] = gsrc[(long long)esrc_off[i] + k]; vd[k] = gsrc[(long long)edst_off[i] + k]; }
+  edge_g_dst<VD, ED>(kind, val, vs, vd, p + p0 + i * pdim);
+  double* oo = o + out0 + i * (osrc + ED);
+  if (osrc) {
+#pragma unroll
+    for (int d = 0; d < ED; ++d) oo[d] = (coupling == ND_B200_ANTISYMMETRIC) ? -val[d] : val[d];
+  }
+#pragma unroll
+  for (int d = 0; d < ED; ++d) oo[osrc + d] = val[d];
+}
+
+__global__ void copy_vout_to_o_kernel(const double* __restrict__ src, double* __restrict__ o, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) o[i] = src[i];
+}
+
+}  // namespace ndb

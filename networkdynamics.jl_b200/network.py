@@ -1,0 +1,459 @@
+"""`Network(g, vertexm, edgem; execution=B200Execution(), aggregator=B200Aggregator(+))` -- the reference's
+constructor and call interface for the RHS path, with the B200 engine plugged into its two extension points.
+
+Mirrors (reference file:line):
+  * `Network(g, vertexm, edgem; execution, aggregator, ...)`      src/construction.jl:31-236
+  * `IndexManager`, `register_vertices!`, `register_edges!`        src/network_structure.jl:1-55,224-289
+  * batching by `_component_hash` / `find_identical`               src/construction.jl:238-256, src/utils.jl:197-217
+  * `ExecutionStyle{buffered}` singletons                          src/executionstyles.jl:13-47
+  * aggregator constructor convention `(im, batches) -> Aggregator`  src/aggregators.jl:1-16,137
+  * `(nw::Network)(du, u, p, t)`                                    src/coreloop.jl:1-102
+  * `get_buffers`                                                   src/coreloop.jl:103-109
+The host side only builds index tables (numpy, vectorised); all arithmetic runs in libnd_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _cabi
+from .components import ArgumentError, EdgeModel, VertexModel
+
+
+# ---------------------------------------------------------------------------------------------------
+# execution style / aggregator tags
+# ---------------------------------------------------------------------------------------------------
+class ExecutionStyle:
+    buffered = False
+
+
+class B200Execution(ExecutionStyle):
+    """Field-less tag like the reference's execution styles (only its type is stored in `Network{EX,...}`,
+    src/network_structure.jl:83,102-116).  `buffered=False`: the engine never materialises a gather buffer, so
+    the Lazy provider is selected (src/construction.jl:210-214)."""
+    buffered = False
+
+    def __repr__(self):
+        return "B200Execution{false}()"
+
+
+def usebuffer(ex) -> bool:
+    return bool(getattr(ex, "buffered", False))
+
+
+def iscudacompatible(x) -> bool:
+    return isinstance(x, (B200Execution, B200Aggregator)) or x in (B200Execution, B200Aggregator)
+
+
+@dataclass
+class ComponentBatch:
+    """src/network_structure.jl:176-222 (strides flattened to first + width)."""
+    kind: str                 # "vertex" | "edge"
+    model: object
+    indices: np.ndarray       # 1-based component ids, ascending
+    state_first: int
+    p_first: int
+    in_first: int             # aggbuf (vertices) / gbuf (edges)
+    out_first: int
+
+    def __len__(self):
+        return int(self.indices.size)
+
+
+class IndexManager:
+    """All flat index ranges (1-based firsts; widths come from the models)."""
+
+    def __init__(self, g, vertexm: Sequence[VertexModel], vtype: np.ndarray, edgem: Sequence[EdgeModel],
+                 etype: np.ndarray):
+        self.g = g
+        self.nv, self.ne = g.nv, g.ne
+        self.edge_src, self.edge_dst = g.src, g.dst            # edgevec, src/network_structure.jl:37
+        self.vertexm, self.edgem = list(vertexm), list(edgem)
+        self.vtype, self.etype = vtype, etype
+        vd = {m.outdim for m in self.vertexm}
+        if len(vd) != 1:                                        # src/construction.jl:99-102
+            raise ArgumentError("All vertices must have the same output dimension")
+        ed = {m.outdim_dst for m in self.edgem}
+        if len(ed) > 1:                                         # src/construction.jl:103-106
+            raise ArgumentError("All edges must have the same output dimension")
+        self.vdepth = vd.pop()
+        self.edepth = ed.pop() if ed else 0
+        self.lastidx_dynamic = self.lastidx_out = self.lastidx_p = 0
+        self.lastidx_aggr = self.lastidx_gbuf = 0
+        z = lambda n: np.zeros(n, dtype=np.int64)
+        self.v_data, self.v_out, self.v_para, self.v_aggr = z(self.nv), z(self.nv), z(self.nv), z(self.nv)
+        self.e_data, self.e_out_src, self.e_out_dst = z(self.ne), z(self.ne), z(self.ne)
+        self.e_para, self.e_gbuf_src, self.e_gbuf_dst = z(self.ne), z(self.ne), z(self.ne)
+
+    def _next(self, which: str, count: int, width: int) -> np.ndarray:
+        last = getattr(self, which)
+        setattr(self, which, last + count * width)
+        return last + 1 + np.arange(count, dtype=np.int64) * width
+
+    def register_vertices(self, idxs: np.ndarray, m: VertexModel) -> ComponentBatch:
+        """src/network_structure.jl:224-239"""
+        n = idxs.size
+        i0 = idxs - 1
+        self.v_data[i0] = self._next("lastidx_dynamic", n, m.dim)
+        self.v_out[i0] = self._next("lastidx_out", n, m.outdim)
+        self.v_para[i0] = self._next("lastidx_p", n, m.pdim)
+        self.v_aggr[i0] = self._next("lastidx_aggr", n, self.edepth)
+        f = i0[0]
+        return ComponentBatch("vertex", m, idxs, int(self.v_data[f]), int(self.v_para[f]), int(self.v_aggr[f]),
+                              int(self.v_out[f]))
+
+    def register_edges(self, idxs: np.ndarray, m: EdgeModel) -> ComponentBatch:
+        """src/network_structure.jl:240-258: src output range first, dst range immediately after"""
+        n = idxs.size
+        i0 = idxs - 1
+        self.e_data[i0] = self._next("lastidx_dynamic", n, m.dim)
+        w = m.outdim_src + m.outdim_dst
+        first = self._next("lastidx_out", n, w)
+        self.e_out_src[i0] = first
+        self.e_out_dst[i0] = first + m.outdim_src
+        self.e_para[i0] = self._next("lastidx_p", n, m.pdim)
+        gf = self._next("lastidx_gbuf", n, 2 * self.vdepth)
+        self.e_gbuf_src[i0] = gf
+        self.e_gbuf_dst[i0] = gf + self.vdepth
+        f = i0[0]
+        return ComponentBatch("edge", m, idxs, int(self.e_data[f]), int(self.e_para[f]), int(self.e_gbuf_src[f]),
+                              int(self.e_out_src[f]))
+
+
+def find_identical(keys: np.ndarray) -> List[np.ndarray]:
+    """src/utils.jl:197-217: groups in first-occurrence order, members ascending (1-based)."""
+    uniq, first = np.unique(keys, return_index=True)
+    order = np.argsort(first, kind="stable")
+    return [np.nonzero(keys == uniq[k])[0].astype(np.int64) + 1 for k in order]
+
+
+def _expand_models(models, n, what):
+    """Accept one model (broadcast, src/construction.jl:42-46), a list of n models, or a
+    (unique_models, type_index_array) pair for very large networks."""
+    if isinstance(models, (VertexModel, EdgeModel)):
+        return [models], np.zeros(n, dtype=np.int64), True
+    if isinstance(models, tuple) and len(models) == 2 and isinstance(models[1], np.ndarray):
+        uniq, types = list(models[0]), np.asarray(models[1], dtype=np.int64)
+        if types.size != n:
+            raise ArgumentError(f"Number of {what} models does not match the graph")
+        # merge models with equal component hash (object identity is not what the reference batches on)
+        hashes, remap = {}, np.zeros(len(uniq), dtype=np.int64)
+        merged = []
+        for i, m in enumerate(uniq):
+            h = m.component_hash()
+            if h not in hashes:
+                hashes[h] = len(merged)
+                merged.append(m)
+            remap[i] = hashes[h]
+        return merged, remap[types], False
+    models = list(models)
+    if len(models) != n:                                        # src/construction.jl:48-51
+        raise ArgumentError(f"Number of {what} models does not match the graph")
+    hashes, uniq, types = {}, [], np.empty(n, dtype=np.int64)
+    for i, m in enumerate(models):
+        h = m.component_hash()
+        k = hashes.get(h)
+        if k is None:
+            k = hashes[h] = len(uniq)
+            uniq.append(m)
+        types[i] = k
+    return uniq, types, False
+
+
+# ---------------------------------------------------------------------------------------------------
+# the aggregator that owns the engine
+# ---------------------------------------------------------------------------------------------------
+class B200Aggregator:
+    """`B200Aggregator(+)` is, like every reference aggregator, a constructor closure: calling it with
+    `(im, edgebatches)` after all batches are registered (src/construction.jl:198) builds the aggregator -- here
+    the whole device engine, because the execution-style tag cannot carry state.  Keeps an `f` field
+    (read as `nw.layer.aggregator.f`, test/testutils.jl:50)."""
+
+    def __init__(self, f="+", *, device: Optional[int] = None, row_range=None, long_row_threshold: int = 0,
+                 keep_tables: bool = True):
+        if f not in ("+", sum, np.add) and getattr(f, "__name__", "") != "add":
+            raise ArgumentError("B200Aggregator only supports + as the reducer (no CPU fallback for others)")
+        self.f = "+"
+        self._opts = dict(device=device, row_range=row_range, long_row_threshold=long_row_threshold,
+                          keep_tables=keep_tables)
+        self.handle = None
+        self._keep = None
+
+    def __repr__(self):
+        return "B200Aggregator(+)"
+
+    # -- constructor-closure protocol ------------------------------------------------------------
+    def __call__(self, im: IndexManager, edgebatches: List[ComponentBatch]):
+        """`aggregator(im, edgebatches)`; the vertex batches are read from the fully populated IndexManager
+        (in Julia: rebuilt from im.v_* and im.vertexm, which are complete at src/construction.jl:198)."""
+        agg = B200Aggregator(self.f, **self._opts)
+        agg._build(im, im.vertexbatches, edgebatches)
+        return agg
+
+    def _build(self, im, vertexbatches, edgebatches):
+        L = _cabi.lib()
+        vb = (_cabi.VBatch * len(vertexbatches))()
+        keep = []
+        for k, b in enumerate(vertexbatches):
+            kind = b.model.kernel_kind()
+            if kind is None:
+                raise ArgumentError(f"vertex model {b.model.name!r} has no kernel in the B200 registry "
+                                    "(unsupported components raise instead of falling back to the CPU)")
+            idx = np.ascontiguousarray(b.indices, dtype=np.int64)
+            keep.append(idx)
+            vb[k] = _cabi.VBatch(kind, b.model.dim, b.model.pdim, b.model.outdim, idx.size,
+                                 idx.ctypes.data_as(_cabi.i64p), b.state_first, b.p_first, b.out_first, b.in_first)
+        eb = (_cabi.EBatch * max(1, len(edgebatches)))()
+        for k, b in enumerate(edgebatches):
+            kind = b.model.kernel_kind()
+            if kind is None:
+                raise ArgumentError(f"edge model {b.model.name!r} has no kernel in the B200 registry "
+                                    "(unsupported components raise instead of falling back to the CPU)")
+            idx = np.ascontiguousarray(b.indices, dtype=np.int64)
+            keep.append(idx)
+            eb[k] = _cabi.EBatch(kind, b.model.coupling, b.model.dim, b.model.pdim, b.model.outdim_src,
+                                 b.model.outdim_dst, idx.size, idx.ctypes.data_as(_cabi.i64p), b.state_first,
+                                 b.p_first, b.out_first, b.in_first)
+        dev = self._opts["device"]
+        if dev is None:
+            dev = _current_device()
+        rr = self._opts["row_range"] or (0, 0)
+        src = np.ascontiguousarray(im.edge_src, dtype=np.int64)
+        dst = np.ascontiguousarray(im.edge_dst, dtype=np.int64)
+        desc = _cabi.Desc(_cabi.ABI_VERSION, int(dev), im.nv, im.ne, src.ctypes.data_as(_cabi.i64p),
+                          dst.ctypes.data_as(_cabi.i64p), im.vdepth, im.edepth, len(vertexbatches),
+                          len(edgebatches), vb, eb, im.lastidx_dynamic, im.lastidx_p, im.lastidx_out,
+                          im.lastidx_aggr, int(rr[0]), int(rr[1]), int(self._opts["long_row_threshold"]),
+                          0 if self._opts["keep_tables"] else _cabi.FLAG_NO_EXPORT)
+        h = C.c_void_p()
+        rc = L.nd_b200_create(C.byref(desc), C.byref(h))
+        if rc != _cabi.OK:
+            msg = L.nd_b200_last_error(None).decode()
+            raise (ArgumentError if rc in (_cabi.EINVAL, _cabi.EUNSUPPORTED) else RuntimeError)(msg)
+        self.handle = h
+        self.device = int(dev)
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h:
+            try:
+                _cabi.lib().nd_b200_destroy(h)
+            except Exception:
+                pass
+
+
+def get_aggr_constructor(agg: B200Aggregator):
+    """src/aggregators.jl:287-292: recover the constructor closure from a built aggregator."""
+    return B200Aggregator(agg.f, **agg._opts)
+
+
+def _current_device() -> int:
+    try:
+        import torch
+        if torch.cuda.is_available():
+            return torch.cuda.current_device()
+    except Exception:
+        pass
+    return 0
+
+
+def _addr(x):
+    """raw address + (is_device, nbytes/8) of a flat float64 buffer: torch tensor, numpy array, CUDA array
+    interface object, or None."""
+    if x is None:
+        return None, None, 0
+    if isinstance(x, np.ndarray):
+        if x.dtype != np.float64 or not x.flags.c_contiguous:
+            raise ArgumentError("expected a contiguous Float64 vector")
+        return x.ctypes.data, False, x.size
+    if hasattr(x, "data_ptr"):  # torch
+        import torch
+        if x.dtype != torch.float64 or not x.is_contiguous():
+            raise ArgumentError("expected a contiguous Float64 vector")
+        return x.data_ptr(), bool(x.is_cuda), x.numel()
+    cai = getattr(x, "__cuda_array_interface__", None)
+    if cai is not None:
+        if cai["typestr"] not in ("<f8", "=f8"):
+            raise ArgumentError("expected a Float64 device vector")
+        return cai["data"][0], True, int(np.prod(cai["shape"]))
+    raise ArgumentError(f"unsupported array type {type(x)}")
+
+
+def _stream_handle(stream) -> Optional[int]:
+    if stream is None:
+        try:
+            import torch
+            if torch.cuda.is_available():
+                return torch.cuda.current_stream().cuda_stream or None
+        except Exception:
+            return None
+        return None
+    return getattr(stream, "cuda_stream", stream) or None
+
+
+class NetworkLayer:
+    """src/network_structure.jl:57-75 (only what the RHS path reads)"""
+
+    def __init__(self, g, edgebatches, aggregator, edepth, vdepth):
+        self.g, self.edgebatches, self.aggregator = g, edgebatches, aggregator
+        self.edepth, self.vdepth = edepth, vdepth
+
+
+class Network:
+    """`Network(g, vertexm, edgem; execution=B200Execution(), aggregator=B200Aggregator("+"))`."""
+
+    def __init__(self, g, vertexm, edgem, *, execution=None, aggregator=None, verbose=False):
+        execution = B200Execution() if execution is None else execution
+        aggregator = B200Aggregator("+") if aggregator is None else aggregator
+        if not isinstance(execution, ExecutionStyle):                       # src/construction.jl:96
+            raise ArgumentError("execution must be an ExecutionStyle")
+        vm, vtype, _ = _expand_models(vertexm, g.nv, "vertex")
+        em, etype, _ = _expand_models(edgem, g.ne, "edge")
+        for m in vm:
+            if not isinstance(m, VertexModel):
+                raise ArgumentError("vertexm must be VertexModel(s)")
+        for m in em:
+            if not isinstance(m, EdgeModel):
+                raise ArgumentError("edgem must be EdgeModel(s)")
+        im = IndexManager(g, vm, vtype, em, etype)
+        self.im = im
+        # batches: all vertex batches first, then all edge batches (src/construction.jl:171-195)
+        self.vertexbatches = [im.register_vertices(idxs, vm[vtype[idxs[0] - 1]]) for idxs in find_identical(vtype)]
+        edgebatches = [im.register_edges(idxs, em[etype[idxs[0] - 1]]) for idxs in find_identical(etype)] if g.ne else []
+        if verbose:
+            for b in self.vertexbatches + edgebatches:
+                print(f" - {b.kind} batch {b.model.name}: {len(b)} components")
+        im.vertexbatches = self.vertexbatches
+        agg = aggregator(im, edgebatches)                                   # src/construction.jl:198
+        self.layer = NetworkLayer(g, edgebatches, agg, im.edepth, im.vdepth)
+        self.execution = execution
+        self._L = _cabi.lib()
+
+    # -- sizes (src/network_structure.jl:118-131) ---------------------------------------------------
+    def dim(self):
+        return self.im.lastidx_dynamic
+
+    def pdim(self):
+        return self.im.lastidx_p
+
+    @property
+    def handle(self):
+        return self.layer.aggregator.handle
+
+    def _fail(self, rc):
+        msg = self._L.nd_b200_last_error(self.handle).decode()
+        raise (ArgumentError if rc in (_cabi.EINVAL, _cabi.EUNSUPPORTED) else RuntimeError)(msg)
+
+    def _check_sizes(self, n_du, n_u, n_p, has_p):
+        if n_du != self.im.lastidx_dynamic or n_u != self.im.lastidx_dynamic:   # src/coreloop.jl:2-4
+            raise ArgumentError(f"du or u does not have expected size {self.im.lastidx_dynamic}")
+        if self.im.lastidx_p > 0 and (not has_p or n_p != self.im.lastidx_p):    # src/coreloop.jl:5-7
+            raise ArgumentError(f"p does not has expecte size {self.im.lastidx_p}")
+
+    # -- the RHS -----------------------------------------------------------------------------------
+    def __call__(self, du, u, p, t, *, stream=None, perturb=None, RET="du"):
+        """In-place `nw(du, u, p, t)`; returns None (src/coreloop.jl:101).  Device vectors run asynchronously on
+        the current stream; numpy (host) vectors take the end-to-end host path (H2D, RHS, D2H, synchronise)."""
+        if perturb is not None or RET != "du":
+            raise ArgumentError("B200Execution supports neither `perturb` nor RET != :du; keep a CPU twin network "
+                                "for initialisation / linear analysis")
+        a_du, dev_du, n_du = _addr(du)
+        a_u, dev_u, n_u = _addr(u)
+        a_p, dev_p, n_p = _addr(p)
+        self._check_sizes(n_du, n_u, n_p, p is not None)
+        kinds = {d for d in (dev_du, dev_u, dev_p) if d is not None}
+        if len(kinds) != 1:
+            raise ArgumentError("du, u and p must all live on the device or all on the host")
+        if kinds.pop():
+            rc = self._L.nd_b200_rhs(self.handle, a_du, a_u, a_p, float(t), _stream_handle(stream))
+        else:
+            rc = self._L.nd_b200_rhs_host(self.handle, a_du, a_u, a_p, float(t))
+        if rc:
+            self._fail(rc)
+        return None
+
+    def get_buffers(self, o, aggbuf, u, p, t, *, stream=None):
+        """`get_buffers(nw, u, p, t)` (src/coreloop.jl:103-109) into caller-provided device vectors."""
+        a_o, _, n_o = _addr(o)
+        a_a, _, n_a = _addr(aggbuf)
+        a_u, _, n_u = _addr(u)
+        a_p, _, n_p = _addr(p)
+        if n_o != self.im.lastidx_out or n_a != self.im.lastidx_aggr:
+            raise ArgumentError("output / aggregation buffer has the wrong size")
+        self._check_sizes(n_u, n_u, n_p, p is not None)
+        rc = self._L.nd_b200_get_buffers(self.handle, a_o, a_a, a_u, a_p, float(t), _stream_handle(stream))
+        if rc:
+            self._fail(rc)
+
+    def rk4(self, u, p, t0, dt, nsteps, *, stream=None):
+        """fixed-step classical RK4, u advanced in place on the device"""
+        a_u, dev, n_u = _addr(u)
+        a_p, _, n_p = _addr(p)
+        if not dev:
+            raise ArgumentError("rk4 needs device-resident u")
+        self._check_sizes(n_u, n_u, n_p, p is not None)
+        rc = self._L.nd_b200_rk4(self.handle, a_u, a_p, float(t0), float(dt), int(nsteps), _stream_handle(stream))
+        if rc:
+            self._fail(rc)
+
+    # -- introspection -----------------------------------------------------------------------------
+    def engine_sizes(self):
+        s = (C.c_int64 * 8)()
+        rc = self._L.nd_b200_export_sizes(self.handle, s)
+        if rc:
+            self._fail(rc)
+        keys = ["nrows", "nentries", "nblocks", "n_long_rows", "gather_from_u", "launches_per_rhs", "row_begin",
+                "row_end"]
+        return dict(zip(keys, [int(x) for x in s]))
+
+    def export_tables(self):
+        sz = self.engine_sizes()
+        rowptr = np.zeros(sz["nrows"] + 1, dtype=np.int64)
+        n = max(sz["nentries"], 1)
+        nbr, eid, side = np.zeros(n, dtype=np.int64), np.zeros(n, dtype=np.int64), np.zeros(n, dtype=np.int32)
+        rc = self._L.nd_b200_export_tables(self.handle, rowptr.ctypes.data_as(_cabi.i64p),
+                                           nbr.ctypes.data_as(_cabi.i64p), eid.ctypes.data_as(_cabi.i64p),
+                                           side.ctypes.data_as(_cabi.i32p))
+        if rc:
+            self._fail(rc)
+        k = sz["nentries"]
+        return rowptr, nbr[:k], eid[:k], side[:k]
+
+    def launch_count(self) -> int:
+        return int(self._L.nd_b200_launch_count(self.handle))
+
+    def set_timing(self, enabled: bool):
+        self._L.nd_b200_set_timing(self.handle, int(enabled))
+
+    def timings(self):
+        f, pre, n = C.c_double(), C.c_double(), C.c_int64()
+        rc = self._L.nd_b200_timings(self.handle, C.byref(f), C.byref(pre), C.byref(n))
+        if rc:
+            self._fail(rc)
+        return dict(fused_ms=f.value, prepass_ms=pre.value, ncalls=int(n.value))
+
+
+def dim(nw: Network) -> int:
+    return nw.dim()
+
+
+def pdim(nw: Network) -> int:
+    return nw.pdim()
+
+
+def pinned_empty(n: int) -> np.ndarray:
+    """float64 host vector in page-locked memory (for the host-buffer RHS path)."""
+    L = _cabi.lib()
+    ptr = L.nd_b200_host_alloc(int(n) * 8)
+    if not ptr:
+        raise RuntimeError("cudaHostAlloc failed")
+    buf = (C.c_double * int(n)).from_address(ptr)
+    arr = np.frombuffer(buf, dtype=np.float64, count=int(n))
+    _PINNED[arr.ctypes.data] = ptr
+    return arr
+
+
+_PINNED = {}

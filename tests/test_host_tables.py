@@ -1,0 +1,79 @@
+"""Host-side mirror of the reference's index construction (networkdynamics.jl_b200/network.py) against the oracle's
+independent restatement: bit-exact equality of every table (no GPU needed: the aggregator closure is a no-op)."""
+import numpy as np
+import pytest
+
+from helpers import null_aggregator, oracle_network
+
+
+def _cases(nd):
+    L = nd.Lib
+    rng = np.random.default_rng(5)
+    n = 300
+    half = np.array([0] * (n // 2) + [1] * (n // 2))
+    yield "cfg1-like", nd.watts_strogatz(200, 10, 0.1, seed=1), L.kuramoto_first(), L.kuramoto_edge()
+    yield "cfg2-like", nd.erdos_renyi(400, 1600, seed=1), L.diffusion_vertex(), L.diffusion_edge()
+    yield "cfg3-like", nd.barabasi_albert(n, 4, seed=1), ([L.kuramoto_first(), L.kuramoto_second()], rng.permutation(half)), L.kuramoto_edge()
+    yield "cfg4-like", nd.grid_graph(8, 7), L.swing_dq(), L.line_dq()
+    g = nd.watts_strogatz(60, 4, 0.5, seed=3, directed=True)
+    em = [L.kuramoto_edge(), L.diffusion_edge(), nd.EdgeModel(g=nd.Directed(L.kuramoto_edge_f), outdim=1, pdim=1, name="dir")]
+    yield "directed-mixed", g, [L.kuramoto_first(), L.kuramoto_second_bench()] * 30, [em[k] for k in rng.integers(0, 3, g.ne)]
+
+
+def test_tables_match_oracle(nd):
+    for name, g, vm, em in _cases(nd):
+        nw = nd.Network(g, vm, em, aggregator=null_aggregator)
+        onw = oracle_network(g, vm, em)
+        im = nw.im
+        for t in ["v_data", "v_out", "v_para", "v_aggr", "e_data", "e_out_src", "e_out_dst", "e_para", "e_gbuf_src",
+                  "e_gbuf_dst"]:
+            assert np.array_equal(getattr(im, t), onw.table(t)), (name, t)
+        for a in ["lastidx_dynamic", "lastidx_p", "lastidx_out", "lastidx_aggr", "lastidx_gbuf", "vdepth", "edepth"]:
+            assert getattr(im, a) == getattr(onw, a), (name, a)
+        ob = onw.batches("vertex") + onw.batches("edge")
+        pb = nw.vertexbatches + nw.layer.edgebatches
+        assert len(ob) == len(pb)
+        for (_, oi), b in zip(ob, pb):
+            assert np.array_equal(oi, b.indices), name
+        assert nd.dim(nw) == onw.lastidx_dynamic and nd.pdim(nw) == onw.lastidx_p
+
+
+def test_graph_canonical_edge_order(nd):
+    """edges(g) order: src<dst, sorted by (src,dst); docs/src/mathematical_model.md:108-115"""
+    g = nd.SimpleGraph(5, [5, 3, 2, 1, 4, 2], [1, 1, 3, 2, 2, 1])
+    assert list(zip(g.src, g.dst)) == [(1, 2), (1, 3), (1, 5), (2, 3), (2, 4)]
+    d = nd.SimpleDiGraph(3, [3, 1, 2, 1], [1, 3, 1, 2])
+    assert list(zip(d.src, d.dst)) == [(1, 2), (1, 3), (2, 1), (3, 1)]
+    for g in (nd.erdos_renyi(1000, 4000, seed=2), nd.barabasi_albert(1000, 4, seed=2), nd.watts_strogatz(1000, 10, 0.1)):
+        key = g.src * (g.nv + 1) + g.dst
+        assert np.all(np.diff(key) > 0) and np.all(g.src < g.dst)
+    assert nd.erdos_renyi(1000, 4000, seed=2).ne == 4000
+    assert nd.grid_graph(400, 500).ne == 399100
+
+
+def test_constructor_argument_errors(nd):
+    L = nd.Lib
+    g = nd.complete_graph(4)
+    with pytest.raises(nd.ArgumentError):        # src/construction.jl:48-51
+        nd.Network(g, [L.kuramoto_first()] * 3, L.kuramoto_edge(), aggregator=null_aggregator)
+    with pytest.raises(nd.ArgumentError):        # src/construction.jl:99-102 (different vertex outdim)
+        nd.Network(g, [L.kuramoto_first(), L.swing_dq()] * 2, L.kuramoto_edge(), aggregator=null_aggregator)
+    with pytest.raises(nd.ArgumentError):        # src/construction.jl:96
+        nd.Network(g, L.kuramoto_first(), L.kuramoto_edge(), execution="sequential", aggregator=null_aggregator)
+    with pytest.raises(nd.ArgumentError):        # only + is supported, no fallback
+        nd.B200Aggregator(max)
+
+
+def test_unregistered_component_is_rejected_before_any_device_work(nd):
+    """north_star: unsupported component types raise an error instead of silently running elsewhere"""
+    L = nd.Lib
+    g = nd.complete_graph(3)
+    custom = nd.VertexModel(f=lambda dv, v, acc, p, t: None, g=nd.StateMask(1), dim=1, pdim=0, name="custom")
+    with pytest.raises(nd.ArgumentError, match="no kernel in the B200 registry"):
+        nd.Network(g, custom, L.kuramoto_edge())
+    ode_edge = nd.EdgeModel(g=nd.AntiSymmetric(L.kuramoto_edge_f), f=L.kuramoto_vertex, dim=1, outdim=1, pdim=1, name="ode")
+    with pytest.raises(nd.ArgumentError, match="no kernel in the B200 registry"):
+        nd.Network(g, L.kuramoto_first(), ode_edge)
+    masked = nd.VertexModel(f=L.kuramoto_inertia, g=nd.StateMask(2), dim=2, pdim=3, name="mask2")
+    with pytest.raises(nd.ArgumentError):
+        nd.Network(g, masked, L.kuramoto_edge())

@@ -1,0 +1,186 @@
+"""Pin the CPU oracle against the reference's own Julia-free known answers.
+
+The reference is Julia and cannot run here, and it ships no golden vectors; what its tests DO hold for this path
+are closed-form answers and layout facts.  Each test names the reference test it restates.
+"""
+import numpy as np
+import pytest
+
+from helpers import espec_of, oracle_network, vspec_of
+from oracle import oracle as O
+from oracle import oracle_np as ONP
+
+
+def _np_im(g, vm, vt, em, et):
+    return ONP.IndexManager(g.nv, g.src, g.dst, [vspec_of(m) for m in vm], list(vt), [espec_of(m) for m in em], list(et))
+
+
+def test_find_identical_order(nd):
+    """test/utils_test.jl:43-61: [v1,v2,v3,v2,v2,v1,v1,v3] -> [[1,6,7],[2,4,5],[3,8]]"""
+    assert ONP.find_identical(["v1", "v2", "v3", "v2", "v2", "v1", "v1", "v3"]) == [[1, 6, 7], [2, 4, 5], [3, 8]]
+    L = nd.Lib
+    vs = [L.kuramoto_second(), L.diffusion_vertex(), L.kuramoto_first(), L.diffusion_vertex(), L.diffusion_vertex(),
+          L.kuramoto_second(), L.kuramoto_second(), L.kuramoto_first()]
+    g = nd.path_graph(8)
+    onw = oracle_network(g, vs, L.kuramoto_edge())
+    assert [list(idx) for _, idx in onw.batches("vertex")] == [[1, 6, 7], [2, 4, 5], [3, 8]]
+    assert [list(i) for i in nd.find_identical(np.array([0, 1, 2, 1, 1, 0, 0, 2]))] == [[1, 6, 7], [2, 4, 5], [3, 8]]
+
+
+def test_handworked_three_vertex_layout(nd):
+    """complete_graph(3), [kuramoto_first, kuramoto_second, kuramoto_first], kuramoto_edge."""
+    L = nd.Lib
+    g = nd.complete_graph(3)
+    assert list(zip(g.src, g.dst)) == [(1, 2), (1, 3), (2, 3)]
+    onw = oracle_network(g, [L.kuramoto_first(), L.kuramoto_second(), L.kuramoto_first()], L.kuramoto_edge())
+    assert [list(i) for _, i in onw.batches("vertex")] == [[1, 3], [2]]
+    assert list(onw.table("v_data")) == [1, 3, 2]
+    assert list(onw.table("v_out")) == [1, 3, 2]
+    assert list(onw.table("v_para")) == [1, 3, 2]
+    assert list(onw.table("v_aggr")) == [1, 3, 2]
+    assert list(onw.table("e_out_src")) == [4, 6, 8] and list(onw.table("e_out_dst")) == [5, 7, 9]
+    assert list(onw.table("e_para")) == [6, 7, 8]
+    assert list(onw.table("e_gbuf_src")) == [1, 3, 5] and list(onw.table("e_gbuf_dst")) == [2, 4, 6]
+    assert list(onw.table("gbufmap")) == [1, 3, 1, 2, 3, 2]
+    assert (onw.aggmap_first, onw.aggmap_len) == (4, 6)
+    assert list(onw.table("aggmap")) == [1, 3, 1, 2, 3, 2]
+    assert (onw.lastidx_dynamic, onw.lastidx_p, onw.lastidx_out, onw.lastidx_aggr, onw.lastidx_gbuf) == (4, 8, 9, 3, 6)
+    # u = [th1, th3, d2, w2], p = [w1, w3, M2, D2, Pm2, K1, K2, K3]
+    th1, th3, d2, w2 = 0.3, -0.7, 1.1, 0.25
+    w1, w3, M2, D2, Pm2, K1, K2, K3 = 0.5, -0.2, 1.7, 0.1, 0.9, 2.0, 3.0, 5.0
+    du, o, agg = onw.rhs([th1, th3, d2, w2], [w1, w3, M2, D2, Pm2, K1, K2, K3], return_bufs=True)
+    e12, e13, e23 = K1 * np.sin(th1 - d2), K2 * np.sin(th1 - th3), K3 * np.sin(d2 - th3)
+    assert np.array_equal(o, [th1, th3, d2, -e12, e12, -e13, e13, -e23, e23])
+    assert agg[0] == (0.0 + -e12) + -e13 and agg[2] == e12 + -e23 and agg[1] == e13 + e23
+    assert du[0] == w1 + agg[0] and du[1] == w3 + agg[1]
+    assert du[2] == w2 and du[3] == 1.0 / M2 * (Pm2 - D2 * w2 + agg[2])
+
+
+def test_homogeneous_two_state_layout(nd):
+    """test/symbolicindexing_test.jl:27-29,42-62: 3 kuramoto_second vertices: VIndex(3,:ω) <-> u[6]; parameters
+    are all vertices (M,D,Pm each) then all edges (K)."""
+    L = nd.Lib
+    g = nd.complete_graph(3)
+    onw = oracle_network(g, L.kuramoto_second(), L.kuramoto_edge())
+    assert onw.table("v_data")[2] + 1 == 6                       # ω is state 2 of vertex 3
+    assert list(onw.table("v_para")) == [1, 4, 7] and list(onw.table("e_para")) == [10, 11, 12]
+    # observed order [EIndex(1,:₋P), EIndex(1,:P), ...]: src output precedes dst output (:46)
+    assert list(onw.table("e_out_src")) == [4, 6, 8] and list(onw.table("e_out_dst")) == [5, 7, 9]
+
+
+def test_heterogeneous_complete4_layout(nd):
+    """test/symbolicindexing_test.jl:84-111: complete_graph(4), vf=[k2,diff,k2,diff], ef=[ode,kura,kura,fid,ode,fid]:
+    variable_index(nw, EIndex(1,:e_dst)) == 7 (all vertex batches precede edge states, edge 1 is in edge batch 1)."""
+    g = nd.complete_graph(4)
+    vs = [O.VSpec(O.V_KURAMOTO_SECOND, 2, 3, 1), O.VSpec(O.V_DIFFUSION, 1, 0, 1)]
+    es = [O.ESpec(O.E_OPAQUE, O.FIDUCIAL, 2, 1, 1, 1),      # diffusion_odeedge: dim 2, pdim 1
+          O.ESpec(O.E_KURAMOTO, O.ANTISYMMETRIC, 0, 1, 1, 1),
+          O.ESpec(O.E_OPAQUE, O.FIDUCIAL, 0, 1, 1, 1)]      # diffusion_edge_fid
+    onw = O.OracleNetwork(4, g.src, g.dst, vs, [0, 1, 0, 1], es, [0, 1, 1, 2, 0, 2])
+    assert onw.table("e_data")[0] == 7
+    assert list(onw.table("v_data")) == [1, 5, 3, 6]
+    assert [list(i) for _, i in onw.batches("edge")] == [[1, 5], [2, 3], [4, 6]]
+    assert onw.lastidx_dynamic == 10
+    with pytest.raises(ValueError):
+        onw.rhs(np.zeros(10), np.zeros(onw.lastidx_p))       # opaque kinds have no RHS in the oracle
+
+
+def _ba_like(nd, n, m, seed):
+    return nd.barabasi_albert(n, m, seed=seed)
+
+
+@pytest.mark.parametrize("edge", ["diffusion_edge", "diffusion_edge_nop"])
+def test_diffusion_equals_minus_laplacian(nd, edge):
+    """test/diffusion_test.jl:80-90: nw(dx, x, nothing, 0) ≈ -L*x for 30 random x on barabasi_albert(10,5)."""
+    g = _ba_like(nd, 10, 5, seed=42)
+    Lm = g.laplacian()
+    em = getattr(nd.Lib, edge)()
+    onw = oracle_network(g, nd.Lib.diffusion_vertex(), em)
+    p = np.ones(onw.lastidx_p)
+    rng = np.random.default_rng(42)
+    for _ in range(30):
+        x = rng.standard_normal(g.nv)
+        dx = onw.rhs(x, p)
+        assert np.allclose(dx, -Lm @ x, rtol=1e-13, atol=1e-13)
+        assert np.array_equal(dx, onw.rhs(x, p, threads=3))
+
+
+def test_diffusion_trajectory_vs_matrix_exponential(nd):
+    """test/diffusion_test.jl:119-129 restated with the oracle's fixed-step RK4: |x(t) - exp(-tL) x0| < 1e-6."""
+    from scipy.linalg import expm
+    g = _ba_like(nd, 10, 5, seed=7)
+    Lm = g.laplacian()
+    onw = oracle_network(g, nd.Lib.diffusion_vertex(), nd.Lib.diffusion_edge_nop())
+    x0 = np.random.default_rng(3).random(g.nv)
+    x = onw.rk4(x0, None, 0.0, 1e-3, 1000)
+    assert np.max(np.abs(x - expm(-1.0 * Lm) @ x0)) < 1e-6
+
+
+def _mixed_case(nd, seed):
+    L = nd.Lib
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(5, 40))
+    g = nd.watts_strogatz(n, 4, 0.3, seed=seed)
+    choices = [L.kuramoto_first(), L.kuramoto_second(), L.kuramoto_second_bench(), L.diffusion_vertex()]
+    vm = [choices[k] for k in rng.integers(0, len(choices), size=n)]
+    echoices = [L.kuramoto_edge(), L.diffusion_edge(), L.diffusion_edge_nop(),
+                nd.EdgeModel(g=nd.Symmetric(L.diffusionedge), outdim=1, pdim=1, name="sym"),
+                nd.EdgeModel(g=nd.Directed(L.kuramoto_edge_f), outdim=1, pdim=1, name="dir")]
+    em = [echoices[k] for k in rng.integers(0, len(echoices), size=g.ne)]
+    return g, vm, em
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_c_oracle_equals_numpy_twin(nd, seed):
+    """Two independent restatements (C and pure Python) agree bit for bit: tables, o, aggbuf and du."""
+    from helpers import model_types
+    g, vm, em = _mixed_case(nd, seed)
+    onw = oracle_network(g, vm, em)
+    uv, vt = model_types(vm, g.nv)
+    ue, et = model_types(em, g.ne)
+    im = _np_im(g, uv, vt, ue, et)
+    assert [list(i) for _, i in onw.batches("vertex")] == [i for _, i in im.vbatches]
+    assert [list(i) for _, i in onw.batches("edge")] == [i for _, i in im.ebatches]
+    assert list(onw.table("v_data")) == [im.v_data[i + 1].first for i in range(g.nv)]
+    assert list(onw.table("e_out_dst")) == [im.e_out[i + 1][1].first for i in range(g.ne)]
+    assert np.array_equal(onw.table("gbufmap"), im.gbuf_map())
+    first, amap = im.aggregation_map()
+    assert onw.aggmap_first == first and np.array_equal(onw.table("aggmap"), amap)
+    rng = np.random.default_rng(seed)
+    u, p = rng.random(onw.lastidx_dynamic), rng.random(onw.lastidx_p) + 0.5
+    du, o, agg = onw.rhs(u, p, return_bufs=True)
+    du2, o2, agg2 = ONP.rhs(im, u, p)
+    assert np.array_equal(o, o2, equal_nan=True) and np.array_equal(agg, agg2) and np.array_equal(du, du2)
+    assert np.array_equal(du, onw.rhs(u, p, threads=4))
+
+
+def test_dq_powergrid_oracle_matches_twin(nd):
+    L = nd.Lib
+    g = nd.grid_graph(5, 4)
+    onw = oracle_network(g, L.swing_dq(), L.line_dq())
+    im = _np_im(g, [L.swing_dq()], np.zeros(g.nv, int), [L.line_dq()], np.zeros(g.ne, int))
+    rng = np.random.default_rng(0)
+    u, p = rng.random(onw.lastidx_dynamic), rng.random(onw.lastidx_p) + 0.5
+    du, o, agg = onw.rhs(u, p, return_bufs=True)
+    du2, o2, agg2 = ONP.rhs(im, u, p)
+    assert np.array_equal(o, o2) and np.array_equal(agg, agg2) and np.array_equal(du, du2)
+    assert (onw.vdepth, onw.edepth) == (2, 2)
+    assert onw.lastidx_out == 2 * g.nv + 4 * g.ne and onw.lastidx_aggr == 2 * g.nv
+
+
+def test_rk4_threaded_equals_sequential(nd):
+    g, vm, em = _mixed_case(nd, 3)
+    onw = oracle_network(g, vm, em)
+    rng = np.random.default_rng(1)
+    u, p = rng.random(onw.lastidx_dynamic), rng.random(onw.lastidx_p) + 0.5
+    assert np.array_equal(onw.rk4(u, p, 0.0, 1e-3, 20), onw.rk4(u, p, 0.0, 1e-3, 20, threads=3))
+
+
+def test_size_checks_raise(nd):
+    """src/coreloop.jl:2-7: wrong-size u / p raise ArgumentError"""
+    g = nd.complete_graph(3)
+    onw = oracle_network(g, nd.Lib.kuramoto_first(), nd.Lib.kuramoto_edge())
+    with pytest.raises(ValueError):
+        onw.rhs(np.zeros(4), np.zeros(6))
+    with pytest.raises(ValueError):
+        onw.rhs(np.zeros(3), np.zeros(5))
