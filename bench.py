@@ -46,34 +46,45 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region"""
-    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock + throttle reasons sampled through NVML every few ms DURING the timed region (nvidia-smi -lms is
+    too coarse for a region that lasts tens of milliseconds)."""
 
     def __init__(self, index=0):
-        self.samples, self.proc, self.index = [], None, index
+        self.index, self.samples, self.reasons, self._stop, self._thr, self.max_mhz = index, [], set(), False, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
+            import pynvml as N
+            N.nvmlInit()
+            h = N.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = int(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+            bits = {"hw_slowdown": N.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": N.nvmlClocksEventReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": N.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": N.nvmlClocksEventReasonSwPowerCap}
+        except Exception as e:  # NVML missing: report no samples rather than fail the bench
+            self.err = repr(e)
+            return
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.samples.append([x.strip() for x in line.split(",")])
+        def loop():
+            while not self._stop:
+                try:
+                    self.samples.append(int(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)))
+                    r = int(N.nvmlDeviceGetCurrentClocksEventReasons(h))
+                    for name, bit in bits.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+                time.sleep(0.002)
+        self._thr = threading.Thread(target=loop, daemon=True)
+        self._thr.start()
 
     def stop(self):
-        if self.proc:
-            self.proc.terminate()
-        sm = [int(s[0]) for s in self.samples if s and s[0].isdigit()]
-        mx = [int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
-        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        self._stop = True
+        if self._thr:
+            self._thr.join(timeout=1.0)
+        sm = self.samples
+        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(sm)}
 
 
 def build_workload(nd, name, world):
@@ -134,7 +145,7 @@ def cpu_baseline_leg(nd, g, budget_s=12.0):
         onw.rhs_into(du, u, p, 0.0, threads=threads)
         n += 1
         el = time.perf_counter() - t0
-        if el > budget_s or n >= 200:
+        if el > budget_s or n >= 2000:
             break
     return {"value": g.ne * n / el, "unit": "edge-evals/s", "cores": threads, "kind": "port",
             "sample": f"{n} full RHS evaluations of the same workload in {el:.1f} s; C/OpenMP restatement of the "
@@ -201,6 +212,13 @@ def main():
     for _ in range(args.warmup):
         flush.zero_()
         step()
+    sync_all()
+    # keep the device busy ~0.3 s more so SM clocks have ramped from idle before the timed region
+    t_pre = time.perf_counter()
+    while time.perf_counter() - t_pre < 0.3:
+        for _ in range(20):
+            step()
+        torch.cuda.synchronize()
     sync_all()
 
     # ---- timed region: K steps, L2 flushed between steps (flush outside the event brackets) ----------------

@@ -51,6 +51,14 @@ struct nd_b200_engine {
   VBDev* d_vb = nullptr;
   EBDev* d_eb = nullptr;
   double *d_vout[2] = {nullptr, nullptr};
+  // pipelined kernel (v2): tile descriptors + tile-padded entry arrays
+  int kernel_version = 1;   // 1: occupancy-driven fused kernel (default, faster on B200); 2: persistent cp.async pipeline (ND_B200_KERNEL=v2)
+  int ntiles = 0, grid2 = 0;
+  size_t smem2 = 0;
+  int4* d_tiles = nullptr;
+  unsigned short* d_rp16 = nullptr;
+  int *d_nbr2 = nullptr, *d_epar2 = nullptr;
+  uint8_t* d_ebid2 = nullptr;
   // get_buffers support (lazy)
   std::vector<std::vector<int>> h_esrc_off, h_edst_off;   // per edge batch, gather offsets
   std::vector<int*> d_esrc_off, d_edst_off;
@@ -143,27 +151,72 @@ void fill_params(const nd_b200_engine* e, KParams& P) {
   P.rowptr = e->d_rowptr; P.nbr = e->d_nbr; P.epar = e->d_epar; P.ebid = e->d_ebid; P.blk_row = e->d_blk_row;
   P.vb = e->d_vb; P.eb = e->d_eb; P.n_vb = (int)e->hvb.size(); P.n_eb = (int)e->heb.size();
   P.row_base = (int)e->row_begin; P.long_thr = e->long_thr; P.gather_from_u = e->gather_from_u;
+  P.tiles = e->d_tiles; P.ntiles = e->ntiles; P.rp16 = e->d_rp16; P.nbr2 = e->d_nbr2; P.epar2 = e->d_epar2; P.ebid2 = e->d_ebid2;
 }
 
-template <int VD, int ED, int EK>
+// ---- v2 (pipelined) launch plumbing ---------------------------------------------------------------
+template <int VD, int ED, int EK, int PE, int BLOCK, int EPT>
+cudaError_t pipe_config(nd_b200_engine* e) {
+  auto kern = rhs_pipe_kernel<VD, ED, EK, PE, BLOCK, EPT>;
+  const size_t smem = sizeof(PipeSmem<VD, ED, EK, PE, BLOCK, EPT>);
+  cudaError_t c = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (c != cudaSuccess) return c;
+  int per_sm = 0, sms = 0;
+  c = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, smem);
+  if (c != cudaSuccess) return c;
+  c = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device);
+  if (c != cudaSuccess) return c;
+  if (per_sm < 1) return cudaErrorInvalidConfiguration;
+  if (const char* s = getenv("ND_B200_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(s)));
+  e->smem2 = smem;
+  e->grid2 = std::max(1, std::min(e->ntiles, per_sm * sms));
+  return cudaSuccess;
+}
+template <int VD, int ED, int EK, int PE, int BLOCK, int EPT>
+cudaError_t pipe_launch(const nd_b200_engine* e, const KParams& P, cudaStream_t st) {
+  rhs_pipe_kernel<VD, ED, EK, PE, BLOCK, EPT><<<e->grid2, BLOCK, e->smem2, st>>>(P);
+  return cudaGetLastError();
+}
+// dispatch over the compiled (model family, launch shape) instantiations; CONFIG=true only sets attributes
+template <bool CONFIG, int VD, int ED, int EK, int PE>
+cudaError_t pipe_shape(nd_b200_engine* e, const KParams* P, cudaStream_t st) {
+  if (e->block == 256 && e->ept == 8) { if constexpr (CONFIG) return pipe_config<VD, ED, EK, PE, 256, 8>(e); else return pipe_launch<VD, ED, EK, PE, 256, 8>(e, *P, st); }
+  if (e->block == 256 && e->ept == 4) { if constexpr (CONFIG) return pipe_config<VD, ED, EK, PE, 256, 4>(e); else return pipe_launch<VD, ED, EK, PE, 256, 4>(e, *P, st); }
+  if (e->block == 128 && e->ept == 8) { if constexpr (CONFIG) return pipe_config<VD, ED, EK, PE, 128, 8>(e); else return pipe_launch<VD, ED, EK, PE, 128, 8>(e, *P, st); }
+  if (e->block == 128 && e->ept == 4) { if constexpr (CONFIG) return pipe_config<VD, ED, EK, PE, 128, 4>(e); else return pipe_launch<VD, ED, EK, PE, 128, 4>(e, *P, st); }
+  return cudaErrorInvalidConfiguration;
+}
+template <bool CONFIG>
+cudaError_t pipe_dispatch(nd_b200_engine* e, const KParams* P, cudaStream_t st) {
+  if (e->vdepth == 2) return pipe_shape<CONFIG, 2, 2, ND_B200_E_LINE_DQ, 3>(e, P, st);
+  switch (e->ek) {
+    case ND_B200_E_DIFFUSION: return pipe_shape<CONFIG, 1, 1, ND_B200_E_DIFFUSION, 1>(e, P, st);
+    case ND_B200_E_DIFFUSION_NOP: return pipe_shape<CONFIG, 1, 1, ND_B200_E_DIFFUSION_NOP, 0>(e, P, st);
+    case ND_B200_E_KURAMOTO: return pipe_shape<CONFIG, 1, 1, ND_B200_E_KURAMOTO, 1>(e, P, st);
+    default: return pipe_shape<CONFIG, 1, 1, EK_GENERIC, 1>(e, P, st);
+  }
+}
+
+template <int VD, int ED, int EK, int PE>
 cudaError_t launch_shape(const nd_b200_engine* e, const KParams& P, cudaStream_t st) {
   if (e->nblocks == 0) return cudaSuccess;
-  if (e->block == 256 && e->ept == 8) rhs_fused_kernel<VD, ED, EK, 256, 8><<<e->nblocks, 256, 0, st>>>(P);
-  else if (e->block == 256 && e->ept == 4) rhs_fused_kernel<VD, ED, EK, 256, 4><<<e->nblocks, 256, 0, st>>>(P);
-  else if (e->block == 128 && e->ept == 8) rhs_fused_kernel<VD, ED, EK, 128, 8><<<e->nblocks, 128, 0, st>>>(P);
-  else if (e->block == 128 && e->ept == 4) rhs_fused_kernel<VD, ED, EK, 128, 4><<<e->nblocks, 128, 0, st>>>(P);
+  if (e->block == 256 && e->ept == 8) rhs_fused_kernel<VD, ED, EK, PE, 256, 8><<<e->nblocks, 256, 0, st>>>(P);
+  else if (e->block == 256 && e->ept == 4) rhs_fused_kernel<VD, ED, EK, PE, 256, 4><<<e->nblocks, 256, 0, st>>>(P);
+  else if (e->block == 128 && e->ept == 8) rhs_fused_kernel<VD, ED, EK, PE, 128, 8><<<e->nblocks, 128, 0, st>>>(P);
+  else if (e->block == 128 && e->ept == 4) rhs_fused_kernel<VD, ED, EK, PE, 128, 4><<<e->nblocks, 128, 0, st>>>(P);
   else return cudaErrorInvalidConfiguration;
   return cudaGetLastError();
 }
 
 cudaError_t launch_fused(nd_b200_engine* e, const KParams& P, cudaStream_t st) {
   e->launches += (e->nblocks > 0);
-  if (e->vdepth == 2) return launch_shape<2, 2, ND_B200_E_LINE_DQ>(e, P, st);
+  if (e->kernel_version == 2) return e->nblocks > 0 ? pipe_dispatch<false>(e, &P, st) : cudaSuccess;
+  if (e->vdepth == 2) return launch_shape<2, 2, ND_B200_E_LINE_DQ, 3>(e, P, st);
   switch (e->ek) {
-    case ND_B200_E_DIFFUSION: return launch_shape<1, 1, ND_B200_E_DIFFUSION>(e, P, st);
-    case ND_B200_E_DIFFUSION_NOP: return launch_shape<1, 1, ND_B200_E_DIFFUSION_NOP>(e, P, st);
-    case ND_B200_E_KURAMOTO: return launch_shape<1, 1, ND_B200_E_KURAMOTO>(e, P, st);
-    default: return launch_shape<1, 1, EK_GENERIC>(e, P, st);
+    case ND_B200_E_DIFFUSION: return launch_shape<1, 1, ND_B200_E_DIFFUSION, 1>(e, P, st);
+    case ND_B200_E_DIFFUSION_NOP: return launch_shape<1, 1, ND_B200_E_DIFFUSION_NOP, 0>(e, P, st);
+    case ND_B200_E_KURAMOTO: return launch_shape<1, 1, ND_B200_E_KURAMOTO, 1>(e, P, st);
+    default: return launch_shape<1, 1, EK_GENERIC, 1>(e, P, st);
   }
 }
 
@@ -313,7 +366,7 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
         const long long eid = eb.indices[i] - 1;
         const long long s = d->edge_src[eid], t = d->edge_dst[eid];
         const int rs = row_of_vertex[(size_t)s - 1], rt = row_of_vertex[(size_t)t - 1];
-        const int ep = (int)(eb.p_first - 1 + i * eb.pdim);
+        const int ep = eb.pdim > 0 ? (int)(eb.p_first - 1 + i * eb.pdim) : 0;
         // src output precedes dst output in `o` (register_edges!, src/network_structure.jl:244-245)
         if (eb.outdim_src > 0 && owned(rs)) {
           const long long j = cur[(size_t)(rs - e->row_begin)]++;
@@ -349,6 +402,7 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
   }
 
   // ---- launch shape + thread-block row ranges ----------------------------------------------------
+  e->block = 128; e->ept = 4;   // measured best on B200 for every registry family (profiles/r01_tuning.md)
   if (const char* s = getenv("ND_B200_BLOCK")) e->block = atoi(s);
   if (const char* s = getenv("ND_B200_EPT")) e->ept = atoi(s);
   if (!((e->block == 256 || e->block == 128) && (e->ept == 8 || e->ept == 4))) return fail(e, ND_B200_EINVAL, "ND_B200_BLOCK/ND_B200_EPT must be 128|256 / 4|8");
@@ -380,6 +434,55 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
   }
   e->nblocks = (int)blk_row.size();
   blk_row.push_back((int)e->row_end);
+
+  // ---- v2 tiles: one per thread-block row range, entry arrays padded so every tile starts 16-byte aligned -----
+  if (const char* s = getenv("ND_B200_KERNEL")) e->kernel_version = (atoi(s) == 2 || !strcmp(s, "v2")) ? 2 : 1;
+  std::vector<int4> tiles;
+  std::vector<unsigned short> rp16;
+  std::vector<int> nbr2, epar2;
+  std::vector<uint8_t> ebid2;
+  {
+    const bool v2 = e->kernel_version == 2;
+    const bool generic1 = (e->ek == EK_GENERIC && d->vdepth == 1);
+    tiles.reserve((size_t)e->nblocks);
+    if (v2) nbr2.reserve((size_t)e->nentries + 16 * (size_t)e->nblocks + 16);
+    size_t bi = 0;
+    for (int k = 0; k < e->nblocks; ++k) {
+      const int r0 = blk_row[(size_t)k], r1 = blk_row[(size_t)k + 1];
+      while (bi + 1 < dvb.size() && k >= dvb[bi + 1].blk0) ++bi;
+      const long long a = cnt[(size_t)(r0 - e->row_begin)], z = cnt[(size_t)(r1 - e->row_begin)];
+      const long long ne = z - a;
+      const bool is_long = (r1 - r0 == 1) && ne > e->long_thr;
+      const int e0 = v2 ? (int)nbr2.size() : (int)a;
+      if (v2) {
+        for (long long j = a; j < z; ++j) {
+          nbr2.push_back(h_nbr[(size_t)j]);
+          if (any_epar) epar2.push_back(h_epar[(size_t)j]);
+          if (generic1) ebid2.push_back(h_ebid[(size_t)j]);
+        }
+        while (nbr2.size() % 16) { nbr2.push_back(0); if (any_epar) epar2.push_back(0); if (generic1) ebid2.push_back(0); }
+      }
+      int4 t;
+      t.x = r0; t.y = e0;
+      if (is_long) {
+        t.z = (int)ne;
+        t.w = (int)(0x80000000u | ((unsigned)bi << 25) | (1u << 16));
+      } else {
+        t.z = (int)rp16.size();
+        if (v2) {
+          for (int r = r0; r <= r1; ++r) rp16.push_back((unsigned short)(cnt[(size_t)(r - e->row_begin)] - a));
+          while (rp16.size() % 8) rp16.push_back(0);
+        }
+        t.w = (int)((unsigned)ne | ((unsigned)(r1 - r0) << 16) | ((unsigned)bi << 25));
+      }
+      tiles.push_back(t);
+    }
+    if (v2) {
+      for (int k = 0; k < 16; ++k) { nbr2.push_back(0); if (any_epar) epar2.push_back(0); if (generic1) ebid2.push_back(0); }
+      for (int k = 0; k < 8; ++k) rp16.push_back(0);
+    }
+    e->ntiles = (int)tiles.size();
+  }
   std::vector<EBDev> deb;
   for (const HostEB& h : e->heb) deb.push_back(EBDev{h.kind, h.coupling, h.pdim});
 
@@ -391,6 +494,16 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
   if (e->ek == EK_GENERIC && d->vdepth == 1 && upload(e, &e->d_ebid, h_ebid)) return ND_B200_ECUDA;
   if (!e->gather_from_u) {
     for (int k = 0; k < 2; ++k) CUDA_TRY(e, cudaMalloc((void**)&e->d_vout[k], sizeof(double) * (size_t)(e->nrows_total * e->vdepth)));
+  }
+  if (upload(e, &e->d_tiles, tiles)) return ND_B200_ECUDA;
+  if (e->kernel_version == 2) {
+    if (upload(e, &e->d_rp16, rp16) || upload(e, &e->d_nbr2, nbr2)) return ND_B200_ECUDA;
+    if (any_epar && upload(e, &e->d_epar2, epar2)) return ND_B200_ECUDA;
+    if (!ebid2.empty() && upload(e, &e->d_ebid2, ebid2)) return ND_B200_ECUDA;
+    if (e->ntiles > 0) CUDA_TRY(e, pipe_dispatch<true>(e, nullptr, nullptr));
+    // the v1 copies are not needed by the pipelined kernel
+    cudaFree(e->d_nbr); cudaFree(e->d_epar); cudaFree(e->d_ebid); cudaFree(e->d_rowptr);
+    e->d_nbr = nullptr; e->d_epar = nullptr; e->d_ebid = nullptr; e->d_rowptr = nullptr;
   }
   return ND_B200_OK;
 }
@@ -408,7 +521,6 @@ int rhs_impl(nd_b200_engine* e, double* du, const double* u, const double* p, do
   fill_params(e, P);
   P.u = u; P.p = p; P.du = du; P.mode = mode; P.aggbuf = aggbuf; P.t = t;
   P.gsrc = u;
-  size_t ti = 0;
   if (e->timing) {
     if (ensure_events(e, e->ev, e->ev_used + 2) || ensure_events(e, e->ev_pre, e->ev_pre_used + 2)) return ND_B200_ECUDA;
   }
@@ -418,7 +530,6 @@ int rhs_impl(nd_b200_engine* e, double* du, const double* u, const double* p, do
     if (e->timing) { CUDA_TRY(e, cudaEventRecord(e->ev_pre[e->ev_pre_used + 1], st)); e->ev_pre_used += 2; }
     P.gsrc = e->d_vout[0];
   }
-  (void)ti;
   if (e->timing) CUDA_TRY(e, cudaEventRecord(e->ev[e->ev_used], st));
   CUDA_TRY(e, launch_fused(e, P, st));
   if (e->timing) { CUDA_TRY(e, cudaEventRecord(e->ev[e->ev_used + 1], st)); e->ev_used += 2; }
@@ -484,6 +595,7 @@ void nd_b200_destroy(nd_b200_engine* e) {
   destroy_graph(e);
   cudaFree(e->d_rowptr); cudaFree(e->d_nbr); cudaFree(e->d_epar); cudaFree(e->d_blk_row); cudaFree(e->d_ebid);
   cudaFree(e->d_vb); cudaFree(e->d_eb); cudaFree(e->d_vout[0]); cudaFree(e->d_vout[1]);
+  cudaFree(e->d_tiles); cudaFree(e->d_rp16); cudaFree(e->d_nbr2); cudaFree(e->d_epar2); cudaFree(e->d_ebid2);
   for (int* q : e->d_esrc_off) cudaFree(q);
   for (int* q : e->d_edst_off) cudaFree(q);
   cudaFree(e->d_tmpA); cudaFree(e->d_tmpB); cudaFree(e->d_ksum);

@@ -262,7 +262,8 @@ def test_launch_shapes_agree(nd, cuda, monkeypatch):
     g, vm, em = _configs(nd, scale=0.2)["cfg3_mixed_kuramoto_ba"]
     onw = oracle_network(g, vm, em)
     outs = []
-    for block, ept in ((256, 8), (256, 4), (128, 8), (128, 4)):
+    for kernel, block, ept in (("v2", 256, 8), ("v2", 256, 4), ("v2", 128, 8), ("v2", 128, 4), ("v1", 256, 8), ("v1", 128, 4)):
+        monkeypatch.setenv("ND_B200_KERNEL", kernel)
         monkeypatch.setenv("ND_B200_BLOCK", str(block))
         monkeypatch.setenv("ND_B200_EPT", str(ept))
         nw = nd.Network(g, vm, em)
