@@ -1,0 +1,140 @@
+"""Vertex-partitioned multi-GPU RHS: one process per GPU (`torch.distributed`, NCCL on GPUs, gloo in CPU tests).
+
+The reference has no multi-device path; this follows SURVEY.md 8(e):
+  * aggregation-slot rows are split into `world` CONTIGUOUS ranges of (nearly) equal directed-entry count;
+  * rank r owns the states / du entries of its rows and evaluates only those rows (engine `row_range`);
+  * per RHS one exchange step: every rank publishes the states of its rows (the vertex outputs are state copies
+    or functions of the owner's states) so that all ranks hold the full state vector the gathers read from.
+Accumulation order per row is untouched (a row is never split across ranks), so `du` is identical to the
+single-GPU result, bit for bit.
+
+Host logic (partitioning, segment bookkeeping, the exchange) is plain torch and runs on CPU tensors with gloo.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import numpy as np
+
+from .network import B200Aggregator, B200Execution, ComponentBatch, IndexManager, Network
+
+
+def row_of_vertex(im: IndexManager) -> np.ndarray:
+    """aggregation-slot row (0-based) of every vertex: (v_aggr.first - 1) / edepth; rows follow batch order."""
+    if im.edepth > 0:
+        return (im.v_aggr - 1) // im.edepth
+    row = np.empty(im.nv, dtype=np.int64)
+    k = 0
+    for b in im.vertexbatches:
+        row[b.indices - 1] = k + np.arange(len(b))
+        k += len(b)
+    return row
+
+
+def row_entry_counts(im: IndexManager, edgebatches: Sequence[ComponentBatch]) -> np.ndarray:
+    """directed entries per row = number of edge outputs aggregated into the row (dst outputs + src outputs)"""
+    rov = row_of_vertex(im)
+    cnt = np.zeros(im.nv, dtype=np.int64)
+    for b in edgebatches:
+        e = b.indices - 1
+        cnt += np.bincount(rov[im.edge_dst[e] - 1], minlength=im.nv)
+        if b.model.outdim_src > 0:
+            cnt += np.bincount(rov[im.edge_src[e] - 1], minlength=im.nv)
+    return cnt
+
+
+def partition_rows(entry_counts: np.ndarray, world: int) -> List[Tuple[int, int]]:
+    """`world` contiguous row ranges with (nearly) equal entry count (+1 per row so that edge-less rows spread too)."""
+    w = np.cumsum(entry_counts + 1)
+    total = int(w[-1]) if w.size else 0
+    cuts = [0]
+    for r in range(1, world):
+        cuts.append(int(np.searchsorted(w, total * r / world, side="left")))
+    cuts.append(int(entry_counts.size))
+    cuts = [min(max(c, cuts[i - 1] if i else 0), entry_counts.size) for i, c in enumerate(cuts)]
+    return [(cuts[i], cuts[i + 1]) for i in range(world)]
+
+
+def state_segments(vertexbatches: Sequence[ComponentBatch], r0: int, r1: int) -> List[Tuple[int, int]]:
+    """0-based [start, stop) ranges of the flat state vector owned by rows [r0, r1): one range per vertex batch the
+    row range intersects (states of a batch are contiguous and in row order, src/network_structure.jl:224-239)."""
+    segs, row = [], 0
+    for b in vertexbatches:
+        n, dim = len(b), b.model.dim
+        lo, hi = max(r0, row), min(r1, row + n)
+        if lo < hi and dim > 0:
+            first = b.state_first - 1
+            segs.append((first + (lo - row) * dim, first + (hi - row) * dim))
+        row += n
+    return segs
+
+
+def exchange_states(u, segments_by_rank: Sequence[Sequence[Tuple[int, int]]], group=None, async_op: bool = False):
+    """Every rank publishes its owned state ranges into everybody's copy of `u` (in place).  Implemented as one
+    broadcast per (owner, range); ranges are contiguous so no packing is needed."""
+    import torch.distributed as dist
+    works = []
+    ranks = dist.get_process_group_ranks(group) if group is not None else list(range(dist.get_world_size()))
+    for r, segs in enumerate(segments_by_rank):
+        for a, b in segs:
+            works.append(dist.broadcast(u[a:b], src=ranks[r], group=group, async_op=True))
+    if async_op:
+        return works
+    for w in works:
+        w.wait()
+    return None
+
+
+class PartitionedNetwork:
+    """`Network` evaluated cooperatively by `world` ranks.  `rhs(du, u, p, t)`: exchange the owned states of `u`, then
+    evaluate the owned rows into `du` (only the owned entries of `du` are written)."""
+
+    def __init__(self, g, vertexm, edgem, *, rank: int, world: int, group=None, device=None,
+                 long_row_threshold: int = 0):
+        # host tables first (no device work) to compute the partition
+        probe = Network(g, vertexm, edgem, execution=B200Execution(), aggregator=lambda im, eb: None)
+        self.rank, self.world, self.group = rank, world, group
+        self.entry_counts = row_entry_counts(probe.im, probe.layer.edgebatches)
+        self.row_ranges = partition_rows(self.entry_counts, world)
+        self.segments = [state_segments(probe.vertexbatches, a, b) for a, b in self.row_ranges]
+        self.nw = Network(g, vertexm, edgem, execution=B200Execution(),
+                          aggregator=B200Aggregator("+", device=device, row_range=self.row_ranges[rank],
+                                                    long_row_threshold=long_row_threshold, keep_tables=False))
+
+    def dim(self):
+        return self.nw.dim()
+
+    def pdim(self):
+        return self.nw.pdim()
+
+    @property
+    def owned_segments(self):
+        return self.segments[self.rank]
+
+    def exchange(self, u):
+        exchange_states(u, self.segments, self.group)
+
+    def rhs(self, du, u, p, t, *, exchange: bool = True):
+        if exchange:
+            self.exchange(u)
+        self.nw(du, u, p, t)
+
+    def rk4_step(self, u, p, t, dt, work):
+        """one classical RK4 step on the owned states (same operation order as the single-GPU engine); `work` is a
+        dict of scratch tensors reused across steps"""
+        import torch
+        k = work.setdefault("k", [torch.empty_like(u) for _ in range(4)])
+        tmp = work.setdefault("tmp", torch.empty_like(u))
+        h2 = 0.5 * dt
+        self.rhs(k[0], u, p, t)
+        for a, b in self.owned_segments:
+            tmp[a:b] = u[a:b] + h2 * k[0][a:b]
+        self.rhs(k[1], tmp, p, t + h2)
+        for a, b in self.owned_segments:
+            tmp[a:b] = u[a:b] + h2 * k[1][a:b]
+        self.rhs(k[2], tmp, p, t + h2)
+        for a, b in self.owned_segments:
+            tmp[a:b] = u[a:b] + dt * k[2][a:b]
+        self.rhs(k[3], tmp, p, t + dt)
+        for a, b in self.owned_segments:
+            u[a:b] = u[a:b] + (dt / 6.0) * (((k[0][a:b] + 2.0 * k[1][a:b]) + 2.0 * k[2][a:b]) + k[3][a:b])

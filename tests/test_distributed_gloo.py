@@ -1,0 +1,123 @@
+"""N>1 host logic on CPU: world_size-2 gloo run of the vertex partition + state exchange.
+The device kernel is replaced by the oracle restricted to the owned rows, so what is tested is exactly the multi-rank
+plumbing the GPU path uses: partition_rows / state_segments / exchange_states and the stage algebra of rk4_step."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _case(nd):
+    L = nd.Lib
+    n = 400
+    rng = np.random.default_rng(4)
+    half = np.array([0] * (n // 2) + [1] * (n // 2))
+    g = nd.barabasi_albert(n, 4, seed=2)
+    return g, ([L.kuramoto_first(), L.kuramoto_second()], rng.permutation(half)), L.kuramoto_edge()
+
+
+def test_partition_and_segments(nd):
+    from networkdynamics_jl_b200 import distributed as D
+    from helpers import null_aggregator
+    g, vm, em = _case(nd)
+    nw = nd.Network(g, vm, em, aggregator=null_aggregator)
+    cnt = D.row_entry_counts(nw.im, nw.layer.edgebatches)
+    assert cnt.sum() == 2 * g.ne
+    deg = np.bincount(np.concatenate([g.src, g.dst]) - 1, minlength=g.nv)
+    assert np.array_equal(cnt[D.row_of_vertex(nw.im)], deg)
+    for world in (1, 2, 3, 8):
+        rr = D.partition_rows(cnt, world)
+        assert rr[0][0] == 0 and rr[-1][1] == g.nv and all(rr[i][1] == rr[i + 1][0] for i in range(world - 1))
+        loads = [cnt[a:b].sum() + (b - a) for a, b in rr]
+        assert max(loads) - min(loads) <= cnt.max() + 2          # balanced up to one row
+        segs = [D.state_segments(nw.vertexbatches, a, b) for a, b in rr]
+        owner = np.full(nw.dim(), -1)
+        for r, ss in enumerate(segs):
+            for a, b in ss:
+                assert np.all(owner[a:b] == -1)
+                owner[a:b] = r
+        assert np.all(owner >= 0)                                   # every state has exactly one owner
+        rov = D.row_of_vertex(nw.im)
+        for v in range(g.nv):                                       # the owner of a state is the owner of its row
+            r = next(i for i, (a, b) in enumerate(rr) if a <= rov[v] < b)
+            assert owner[nw.im.v_data[v] - 1] == r
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch
+    import torch.distributed as dist
+    import ndb200 as nd
+    from networkdynamics_jl_b200 import distributed as D
+    from helpers import condition_params, null_aggregator, oracle_network
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g, vm, em = _case(nd)
+    nw = nd.Network(g, vm, em, aggregator=null_aggregator)
+    onw = oracle_network(g, vm, em)
+    cnt = D.row_entry_counts(nw.im, nw.layer.edgebatches)
+    rr = D.partition_rows(cnt, world)
+    segs = [D.state_segments(nw.vertexbatches, a, b) for a, b in rr]
+    u0 = np.random.default_rng(1).random(nw.dim())
+    p = condition_params(nw, np.random.default_rng(2).random(nw.pdim()))
+
+    class FakeLocal(D.PartitionedNetwork):       # same plumbing, oracle instead of the device kernel
+        def __init__(self):
+            self.rank, self.world, self.group, self.segments, self.row_ranges = rank, world, None, segs, rr
+
+        def rhs(self, du, u, p_, t, *, exchange=True):
+            if exchange:
+                self.exchange(u)
+            full = onw.rhs(u.numpy(), p_)
+            du.fill_(float("nan"))
+            for a, b in self.owned_segments:
+                du[a:b] = torch.from_numpy(full[a:b])
+
+    pn = FakeLocal()
+    # (1) one RHS: start from a vector where only the owned states are valid
+    u = torch.full((nw.dim(),), float("nan"), dtype=torch.float64)
+    for a, b in pn.owned_segments:
+        u[a:b] = torch.from_numpy(u0[a:b])
+    du = torch.empty_like(u)
+    pn.rhs(du, u, p, 0.0)
+    assert np.array_equal(u.numpy(), u0)                      # exchange rebuilt the full state everywhere
+    ref = onw.rhs(u0, p)
+    for a, b in pn.owned_segments:
+        assert np.array_equal(du[a:b].numpy(), ref[a:b])
+    # (2) ten RK4 steps
+    work = {}
+    for s in range(10):
+        pn.rk4_step(u, p, s * 1e-3, 1e-3, work)
+    pn.exchange(u)
+    np.save(os.path.join(out_dir, f"u_rank{rank}.npy"), u.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_rhs_and_rk4(nd, tmp_path):
+    import torch.multiprocessing as mp
+    from helpers import condition_params, null_aggregator, oracle_network
+    world, port = 2, _free_port()
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    g, vm, em = _case(nd)
+    nw = nd.Network(g, vm, em, aggregator=null_aggregator)
+    onw = oracle_network(g, vm, em)
+    u0 = np.random.default_rng(1).random(nw.dim())
+    p = condition_params(nw, np.random.default_rng(2).random(nw.pdim()))
+    ref = onw.rk4(u0, p, 0.0, 1e-3, 10)
+    got = [np.load(tmp_path / f"u_rank{r}.npy") for r in range(world)]
+    assert np.array_equal(got[0], got[1])
+    assert np.max(np.abs(got[0] - ref)) <= 1e-14 * max(1.0, np.max(np.abs(ref)))
