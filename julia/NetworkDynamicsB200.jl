@@ -1,0 +1,157 @@
+# NetworkDynamicsB200.jl -- reference-side binding of libnd_b200.so (include/nd_b200.h).
+#
+# NOT EXECUTED IN THIS REPOSITORY'S CI: the build image has no Julia toolchain.  It is the glue a maintainer
+# would add (as a package extension next to ext/NetworkDynamicsCUDAExt.jl) so that
+#
+#     nw = Network(g, vertexm, edgem; execution=B200Execution(), aggregator=B200Aggregator(+))
+#     nw(du, u, p, t)          # du, u, p :: CuArray{Float64}
+#
+# runs the hand-written sm_100a engine instead of the KernelAbstractions path.  The Python mirror in
+# networkdynamics.jl_b200/network.py implements the same flattening and is what the tests exercise.
+module NetworkDynamicsB200
+
+using NetworkDynamics
+using NetworkDynamics: ExecutionStyle, Aggregator, IndexManager, ComponentBatch, Network,
+                       AntiSymmetric, Symmetric, Directed, StateMask, _find_identical_components,
+                       compf, compg, dim, pdim, outdim
+using CUDA: CuArray, CuPtr, stream
+import NetworkDynamics: aggregate!, get_aggr_constructor, iscudacompatible, aggfun
+
+const libnd_b200 = get(ENV, "ND_B200_LIB", "libnd_b200.so")
+const ABI_VERSION = Cint(1)
+
+# ---- tags ---------------------------------------------------------------------------------------------------------
+"`ExecutionStyle` tag (field-less: only its type is stored in `Network{EX,...}`, src/network_structure.jl:83,116)."
+struct B200Execution{buffered} <: ExecutionStyle{buffered} end
+B200Execution() = B200Execution{false}()      # Lazy gather provider: nothing is materialised (src/construction.jl:210-214)
+iscudacompatible(::Type{<:B200Execution}) = true
+
+# ---- kernel registry ------------------------------------------------------------------------------------------------
+# Users opt a component function into a hand-written kernel by adding a method; anything else raises ArgumentError.
+vertex_kernel(f, g) = nothing
+edge_kernel(g) = nothing
+const V_DIFFUSION, V_KURAMOTO_FIRST, V_KURAMOTO_SECOND, V_KURAMOTO_SECOND_BENCH, V_SWING_DQ = Cint.(0:4)
+const E_DIFFUSION, E_DIFFUSION_NOP, E_KURAMOTO, E_LINE_DQ = Cint.(0:3)
+# e.g. (test/ComponentLibrary.jl):
+#   NetworkDynamicsB200.edge_kernel(::typeof(Lib.kuramoto_edge!))       = NetworkDynamicsB200.E_KURAMOTO
+#   NetworkDynamicsB200.vertex_kernel(::typeof(Lib.kuramoto_vertex!), ::StateMask) = NetworkDynamicsB200.V_KURAMOTO_FIRST
+
+coupling_of(::AntiSymmetric) = Cint(0)
+coupling_of(::Symmetric) = Cint(1)
+coupling_of(::Directed) = Cint(2)
+coupling_of(x) = throw(ArgumentError("B200 engine: edge output wrapper $(typeof(x)) is not supported (no CPU fallback)"))
+
+# ---- C structs (mirror include/nd_b200.h) ---------------------------------------------------------------------------
+struct CVBatch
+    kind::Cint; dim::Cint; pdim::Cint; outdim::Cint
+    count::Int64; indices::Ptr{Int64}
+    state_first::Int64; p_first::Int64; out_first::Int64; aggr_first::Int64
+end
+struct CEBatch
+    kind::Cint; coupling::Cint; dim::Cint; pdim::Cint; outdim_src::Cint; outdim_dst::Cint
+    count::Int64; indices::Ptr{Int64}
+    state_first::Int64; p_first::Int64; out_first::Int64; gbuf_first::Int64
+end
+struct CDesc
+    abi_version::Cint; device::Cint
+    nv::Int64; ne::Int64
+    edge_src::Ptr{Int64}; edge_dst::Ptr{Int64}
+    vdepth::Cint; edepth::Cint; n_vbatches::Cint; n_ebatches::Cint
+    vbatches::Ptr{CVBatch}; ebatches::Ptr{CEBatch}
+    lastidx_dynamic::Int64; lastidx_p::Int64; lastidx_out::Int64; lastidx_aggr::Int64
+    row_begin::Int64; row_end::Int64
+    long_row_threshold::Cint; flags::Cint
+end
+
+# ---- the aggregator owns the engine ---------------------------------------------------------------------------------
+mutable struct B200Aggregator{F} <: Aggregator
+    f::F                      # read as nw.layer.aggregator.f (test/testutils.jl:50) and by aggfun
+    handle::Ptr{Cvoid}
+end
+"Constructor-closure convention of every reference aggregator (src/aggregators.jl:1-16,137)."
+function B200Aggregator(f)
+    f === (+) || throw(ArgumentError("B200Aggregator supports only + (no CPU fallback for other reducers)"))
+    (im, batches) -> B200Aggregator(im, batches, f)
+end
+get_aggr_constructor(a::B200Aggregator) = B200Aggregator(a.f)
+iscudacompatible(::Type{<:B200Aggregator}) = true
+Base.show(io::IO, a::B200Aggregator) = print(io, "B200Aggregator(", a.f, ")")
+
+function _check(rc, handle)
+    rc == 0 && return
+    msg = unsafe_string(ccall((:nd_b200_last_error, libnd_b200), Cstring, (Ptr{Cvoid},), handle))
+    rc in (1, 2) ? throw(ArgumentError(msg)) : error(msg)
+end
+
+function B200Aggregator(im::IndexManager, edgebatches, f)
+    # vertex batches: same grouping the constructor used (src/construction.jl:156-168,238-243); `im` is fully
+    # populated when the aggregator closure runs (src/construction.jl:198)
+    vidxs = _find_identical_components(im.vertexm)
+    keep = Any[]
+    vb = map(vidxs) do idxs
+        m = im.vertexm[first(idxs)]
+        kind = vertex_kernel(compf(m), compg(m))
+        isnothing(kind) && throw(ArgumentError("vertex model $(m.name) has no kernel in the B200 registry (no CPU fallback)"))
+        ix = Vector{Int64}(idxs); push!(keep, ix)
+        i1 = first(idxs)
+        CVBatch(kind, dim(m), pdim(m), outdim(m), length(ix), pointer(ix),
+                first(im.v_data[i1]), first(im.v_para[i1]), first(im.v_out[i1]), first(im.v_aggr[i1]))
+    end
+    eb = map(collect(edgebatches)) do b
+        g = compg(b)
+        kind = edge_kernel(g.g)
+        (isnothing(kind) || !isnothing(compf(b))) &&
+            throw(ArgumentError("edge batch $(typeof(g)) has no kernel in the B200 registry (no CPU fallback)"))
+        ix = Vector{Int64}(b.indices); push!(keep, ix)
+        od = outdim(b)
+        CEBatch(kind, coupling_of(g), dim(b), pdim(b), od.src, od.dst, length(ix), pointer(ix),
+                b.statestride.first, b.pstride.first, b.outbufstride.first, b.inbufstride.first)
+    end
+    esrc = Int64[e.src for e in im.edgevec]; edst = Int64[e.dst for e in im.edgevec]
+    handle = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve keep vb eb esrc edst begin
+        desc = CDesc(ABI_VERSION, Cint(CUDA.deviceid()), length(im.vertexm), length(im.edgevec),
+                     pointer(esrc), pointer(edst), im.vdepth, im.edepth, length(vb), length(eb),
+                     pointer(vb), pointer(eb), im.lastidx_dynamic, im.lastidx_p, im.lastidx_out, im.lastidx_aggr,
+                     0, 0, Cint(0), Cint(0))
+        rc = ccall((:nd_b200_create, libnd_b200), Cint, (Ref{CDesc}, Ref{Ptr{Cvoid}}), desc, handle)
+        _check(rc, C_NULL)
+    end
+    a = B200Aggregator{typeof(f)}(f, handle[])
+    finalizer(x -> ccall((:nd_b200_destroy, libnd_b200), Cvoid, (Ptr{Cvoid},), x.handle), a)
+    a
+end
+
+# ---- the RHS ---------------------------------------------------------------------------------------------------------
+# Replaces (nw::Network)(du,u,p,t) (src/coreloop.jl:1-102) for B200Execution networks.
+function (nw::Network{<:B200Execution})(du, u, p, t; perturb=nothing, perturb_maps=nothing, RET=Val(:du))
+    (isnothing(perturb) && RET == Val(:du)) ||
+        throw(ArgumentError("B200Execution supports neither `perturb` nor RET != :du; keep a CPU twin " *
+                            "Network(nw; execution=SequentialExecution{true}(), aggregator=SequentialAggregator(+))"))
+    (du isa CuArray{Float64} && u isa CuArray{Float64}) || throw(ArgumentError("B200Execution needs CuArray{Float64} du/u"))
+    (length(du) == length(u) == nw.im.lastidx_dynamic) ||
+        throw(ArgumentError("du or u does not have expected size $(nw.im.lastidx_dynamic)"))
+    pp = NetworkDynamics.pdim(nw) > 0 ? pointer(p::CuArray{Float64}) : CuPtr{Float64}(0)
+    NetworkDynamics.pdim(nw) > 0 && length(p) != nw.im.lastidx_p &&
+        throw(ArgumentError("p does not has expecte size $(nw.im.lastidx_p)"))
+    h = nw.layer.aggregator.handle
+    rc = ccall((:nd_b200_rhs, libnd_b200), Cint,
+               (Ptr{Cvoid}, CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, Cdouble, Ptr{Cvoid}),
+               h, pointer(du), pointer(u), pp, Float64(t), stream().handle)   # CUDA.jl task-local stream: no host sync
+    _check(rc, h)
+    nothing
+end
+
+"Fixed-step classical RK4 with stage updates fused into the RHS kernels (device-resident `u`, advanced in place)."
+function rk4!(nw::Network{<:B200Execution}, u::CuArray{Float64}, p, t0, dt, nsteps)
+    h = nw.layer.aggregator.handle
+    pp = NetworkDynamics.pdim(nw) > 0 ? pointer(p::CuArray{Float64}) : CuPtr{Float64}(0)
+    rc = ccall((:nd_b200_rk4, libnd_b200), Cint,
+               (Ptr{Cvoid}, CuPtr{Float64}, CuPtr{Float64}, Cdouble, Cdouble, Int64, Ptr{Cvoid}),
+               h, pointer(u), pp, Float64(t0), Float64(dt), Int64(nsteps), stream().handle)
+    _check(rc, h)
+    u
+end
+
+export B200Execution, B200Aggregator, rk4!
+end # module
