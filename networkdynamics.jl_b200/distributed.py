@@ -43,8 +43,16 @@ def row_entry_counts(im: IndexManager, edgebatches: Sequence[ComponentBatch]) ->
     return cnt
 
 
-def partition_rows(entry_counts: np.ndarray, world: int) -> List[Tuple[int, int]]:
-    """`world` contiguous row ranges with (nearly) equal entry count (+1 per row so that edge-less rows spread too)."""
+def partition_rows(entry_counts: np.ndarray, world: int, prefer_equal_rows: float = 0.05) -> List[Tuple[int, int]]:
+    """`world` contiguous row ranges with (nearly) equal entry count (+1 per row so that edge-less rows spread too).
+    When the plain equal-rows split is within `prefer_equal_rows` of that balance (homogeneous graphs such as ER) it is
+    used instead, because equal ranges allow one in-place all-gather for the exchange."""
+    n = int(entry_counts.size)
+    if world > 1 and n % world == 0 and n > 0:
+        step = n // world
+        loads = (entry_counts + 1).reshape(world, step).sum(axis=1)
+        if loads.max() <= (1.0 + prefer_equal_rows) * loads.mean():
+            return [(r * step, (r + 1) * step) for r in range(world)]
     w = np.cumsum(entry_counts + 1)
     total = int(w[-1]) if w.size else 0
     cuts = [0]
@@ -69,10 +77,27 @@ def state_segments(vertexbatches: Sequence[ComponentBatch], r0: int, r1: int) ->
     return segs
 
 
+def _uniform_allgather_layout(segments_by_rank, n) -> bool:
+    """True when rank r owns exactly [r*len, (r+1)*len) and the ranges tile the whole vector."""
+    world = len(segments_by_rank)
+    if n % world or any(len(s) != 1 for s in segments_by_rank):
+        return False
+    step = n // world
+    return all(tuple(s[0]) == (r * step, (r + 1) * step) for r, s in enumerate(segments_by_rank))
+
+
 def exchange_states(u, segments_by_rank: Sequence[Sequence[Tuple[int, int]]], group=None, async_op: bool = False):
-    """Every rank publishes its owned state ranges into everybody's copy of `u` (in place).  Implemented as one
-    broadcast per (owner, range); ranges are contiguous so no packing is needed."""
+    """Every rank publishes its owned state ranges into everybody's copy of `u` (in place).  Equal tiling ranges: ONE
+    in-place all-gather; otherwise one broadcast per (owner, range) -- ranges are contiguous, so nothing is packed."""
     import torch.distributed as dist
+    if _uniform_allgather_layout(segments_by_rank, u.numel()):
+        rank = dist.get_rank(group)
+        a, b = segments_by_rank[rank][0]
+        w = dist.all_gather_into_tensor(u, u[a:b], group=group, async_op=True)
+        if async_op:
+            return [w]
+        w.wait()
+        return None
     works = []
     ranks = dist.get_process_group_ranks(group) if group is not None else list(range(dist.get_world_size()))
     for r, segs in enumerate(segments_by_rank):

@@ -121,3 +121,33 @@ def test_two_rank_gloo_rhs_and_rk4(nd, tmp_path):
     got = [np.load(tmp_path / f"u_rank{r}.npy") for r in range(world)]
     assert np.array_equal(got[0], got[1])
     assert np.max(np.abs(got[0] - ref)) <= 1e-14 * max(1.0, np.max(np.abs(ref)))
+
+
+def _worker_uniform(rank, world, port, out_dir):
+    """single vertex batch, equal ranges -> the exchange is ONE in-place all_gather_into_tensor"""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch
+    import torch.distributed as dist
+    import ndb200 as nd
+    from networkdynamics_jl_b200 import distributed as D
+    from helpers import null_aggregator
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = nd.erdos_renyi(600, 2400, seed=3)
+    nw = nd.Network(g, nd.Lib.kuramoto_first(), nd.Lib.kuramoto_edge(), aggregator=null_aggregator)
+    cnt = D.row_entry_counts(nw.im, nw.layer.edgebatches)
+    rr = D.partition_rows(cnt, world, prefer_equal_rows=0.5)
+    segs = [D.state_segments(nw.vertexbatches, a, b) for a, b in rr]
+    assert rr == [(r * 200, (r + 1) * 200) for r in range(world)] and D._uniform_allgather_layout(segs, nw.dim())
+    u = torch.full((nw.dim(),), float("nan"), dtype=torch.float64)
+    u[rr[rank][0]:rr[rank][1]] = torch.arange(rr[rank][0], rr[rank][1], dtype=torch.float64)
+    D.exchange_states(u, segs)
+    assert torch.equal(u, torch.arange(nw.dim(), dtype=torch.float64))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_three_rank_gloo_allgather_exchange(nd, tmp_path):
+    import torch.multiprocessing as mp
+    mp.spawn(_worker_uniform, args=(3, _free_port(), str(tmp_path)), nprocs=3, join=True)
