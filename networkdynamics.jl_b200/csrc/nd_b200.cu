@@ -51,14 +51,17 @@ struct nd_b200_engine {
   VBDev* d_vb = nullptr;
   EBDev* d_eb = nullptr;
   double *d_vout[2] = {nullptr, nullptr};
-  // pipelined kernel (v2): tile descriptors + tile-padded entry arrays
-  int kernel_version = 1;   // 1: occupancy-driven fused kernel (default, faster on B200); 2: persistent cp.async pipeline (ND_B200_KERNEL=v2)
-  int ntiles = 0, grid2 = 0;
-  size_t smem2 = 0;
-  int4* d_tiles = nullptr;
-  unsigned short* d_rp16 = nullptr;
-  int *d_nbr2 = nullptr, *d_epar2 = nullptr;
-  uint8_t* d_ebid2 = nullptr;
+  int4* d_tiles = nullptr;   // one descriptor per thread block
+  int ntiles = 0;
+  // evaluation mode: 0 = single fused kernel (default); 1 = edge pass + row pass around the edge-output buffer
+  // ("edge once", ND_B200_KERNEL=split; not available for row-partitioned engines)
+  int split = 0;
+  long long ne_all = 0;       // edges in `o` order
+  long long oedge_len = 0;    // scalars in the edge part of `o`
+  long long oedge_base = 0;   // = nv*vdepth: position of the edge part inside `o`
+  int *d_es = nullptr, *d_et = nullptr, *d_eepar = nullptr, *d_eooff = nullptr, *d_oidx = nullptr;
+  uint8_t* d_eebid = nullptr;
+  double* d_oedge = nullptr;
   // get_buffers support (lazy)
   std::vector<std::vector<int>> h_esrc_off, h_edst_off;   // per edge batch, gather offsets
   std::vector<int*> d_esrc_off, d_edst_off;
@@ -151,50 +154,42 @@ void fill_params(const nd_b200_engine* e, KParams& P) {
   P.rowptr = e->d_rowptr; P.nbr = e->d_nbr; P.epar = e->d_epar; P.ebid = e->d_ebid; P.blk_row = e->d_blk_row;
   P.vb = e->d_vb; P.eb = e->d_eb; P.n_vb = (int)e->hvb.size(); P.n_eb = (int)e->heb.size();
   P.row_base = (int)e->row_begin; P.long_thr = e->long_thr; P.gather_from_u = e->gather_from_u;
-  P.tiles = e->d_tiles; P.ntiles = e->ntiles; P.rp16 = e->d_rp16; P.nbr2 = e->d_nbr2; P.epar2 = e->d_epar2; P.ebid2 = e->d_ebid2;
+  P.tiles = e->d_tiles; P.ntiles = e->ntiles; P.oidx = e->d_oidx; P.oedge = e->d_oedge;
 }
 
-// ---- v2 (pipelined) launch plumbing ---------------------------------------------------------------
-template <int VD, int ED, int EK, int PE, int BLOCK, int EPT>
-cudaError_t pipe_config(nd_b200_engine* e) {
-  auto kern = rhs_pipe_kernel<VD, ED, EK, PE, BLOCK, EPT>;
-  const size_t smem = sizeof(PipeSmem<VD, ED, EK, PE, BLOCK, EPT>);
-  cudaError_t c = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (c != cudaSuccess) return c;
-  int per_sm = 0, sms = 0;
-  c = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, smem);
-  if (c != cudaSuccess) return c;
-  c = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device);
-  if (c != cudaSuccess) return c;
-  if (per_sm < 1) return cudaErrorInvalidConfiguration;
-  if (const char* s = getenv("ND_B200_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(s)));
-  e->smem2 = smem;
-  e->grid2 = std::max(1, std::min(e->ntiles, per_sm * sms));
-  return cudaSuccess;
-}
-template <int VD, int ED, int EK, int PE, int BLOCK, int EPT>
-cudaError_t pipe_launch(const nd_b200_engine* e, const KParams& P, cudaStream_t st) {
-  rhs_pipe_kernel<VD, ED, EK, PE, BLOCK, EPT><<<e->grid2, BLOCK, e->smem2, st>>>(P);
+// ---- split mode launches --------------------------------------------------------------------------------
+template <int VD, int ED, int EK, int PE>
+cudaError_t launch_edge_pass_t(const nd_b200_engine* e, const EParams& Q, cudaStream_t st) {
+  constexpr int BLOCK = 256, EPT = 2;
+  const long long per = BLOCK * EPT;
+  const int grid = (int)((e->ne_all + per - 1) / per);
+  if (grid == 0) return cudaSuccess;
+  edge_pass_kernel<VD, ED, EK, PE, BLOCK, EPT><<<grid, BLOCK, 0, st>>>(Q);
   return cudaGetLastError();
 }
-// dispatch over the compiled (model family, launch shape) instantiations; CONFIG=true only sets attributes
-template <bool CONFIG, int VD, int ED, int EK, int PE>
-cudaError_t pipe_shape(nd_b200_engine* e, const KParams* P, cudaStream_t st) {
-  if (e->block == 256 && e->ept == 8) { if constexpr (CONFIG) return pipe_config<VD, ED, EK, PE, 256, 8>(e); else return pipe_launch<VD, ED, EK, PE, 256, 8>(e, *P, st); }
-  if (e->block == 256 && e->ept == 4) { if constexpr (CONFIG) return pipe_config<VD, ED, EK, PE, 256, 4>(e); else return pipe_launch<VD, ED, EK, PE, 256, 4>(e, *P, st); }
-  if (e->block == 128 && e->ept == 8) { if constexpr (CONFIG) return pipe_config<VD, ED, EK, PE, 128, 8>(e); else return pipe_launch<VD, ED, EK, PE, 128, 8>(e, *P, st); }
-  if (e->block == 128 && e->ept == 4) { if constexpr (CONFIG) return pipe_config<VD, ED, EK, PE, 128, 4>(e); else return pipe_launch<VD, ED, EK, PE, 128, 4>(e, *P, st); }
-  return cudaErrorInvalidConfiguration;
-}
-template <bool CONFIG>
-cudaError_t pipe_dispatch(nd_b200_engine* e, const KParams* P, cudaStream_t st) {
-  if (e->vdepth == 2) return pipe_shape<CONFIG, 2, 2, ND_B200_E_LINE_DQ, 3>(e, P, st);
+cudaError_t launch_edge_pass(nd_b200_engine* e, const double* gsrc, const double* p, cudaStream_t st) {
+  EParams Q;
+  memset(&Q, 0, sizeof Q);
+  Q.esrc = e->d_es; Q.edst = e->d_et; Q.epar = e->d_eepar; Q.eooff = e->d_eooff; Q.ebid = e->d_eebid; Q.eb = e->d_eb;
+  Q.ne = e->ne_all; Q.gsrc = gsrc; Q.p = p; Q.oedge = e->d_oedge;
+  if (!e->heb.empty()) { Q.p0 = e->heb[0].p0; Q.coupling0 = e->heb[0].coupling; }
+  e->launches += (e->ne_all > 0);
+  if (e->vdepth == 2) return launch_edge_pass_t<2, 2, ND_B200_E_LINE_DQ, 3>(e, Q, st);
   switch (e->ek) {
-    case ND_B200_E_DIFFUSION: return pipe_shape<CONFIG, 1, 1, ND_B200_E_DIFFUSION, 1>(e, P, st);
-    case ND_B200_E_DIFFUSION_NOP: return pipe_shape<CONFIG, 1, 1, ND_B200_E_DIFFUSION_NOP, 0>(e, P, st);
-    case ND_B200_E_KURAMOTO: return pipe_shape<CONFIG, 1, 1, ND_B200_E_KURAMOTO, 1>(e, P, st);
-    default: return pipe_shape<CONFIG, 1, 1, EK_GENERIC, 1>(e, P, st);
+    case ND_B200_E_DIFFUSION: return launch_edge_pass_t<1, 1, ND_B200_E_DIFFUSION, 1>(e, Q, st);
+    case ND_B200_E_DIFFUSION_NOP: return launch_edge_pass_t<1, 1, ND_B200_E_DIFFUSION_NOP, 0>(e, Q, st);
+    case ND_B200_E_KURAMOTO: return launch_edge_pass_t<1, 1, ND_B200_E_KURAMOTO, 1>(e, Q, st);
+    default: return launch_edge_pass_t<1, 1, EK_GENERIC, 1>(e, Q, st);
   }
+}
+template <int VD, int ED>
+cudaError_t launch_row_pass_t(const nd_b200_engine* e, const KParams& P, cudaStream_t st) {
+  if (e->block == 256 && e->ept == 8) row_pass_kernel<VD, ED, 256, 8><<<e->nblocks, 256, 0, st>>>(P);
+  else if (e->block == 256 && e->ept == 4) row_pass_kernel<VD, ED, 256, 4><<<e->nblocks, 256, 0, st>>>(P);
+  else if (e->block == 128 && e->ept == 8) row_pass_kernel<VD, ED, 128, 8><<<e->nblocks, 128, 0, st>>>(P);
+  else if (e->block == 128 && e->ept == 4) row_pass_kernel<VD, ED, 128, 4><<<e->nblocks, 128, 0, st>>>(P);
+  else return cudaErrorInvalidConfiguration;
+  return cudaGetLastError();
 }
 
 template <int VD, int ED, int EK, int PE>
@@ -209,8 +204,14 @@ cudaError_t launch_shape(const nd_b200_engine* e, const KParams& P, cudaStream_t
 }
 
 cudaError_t launch_fused(nd_b200_engine* e, const KParams& P, cudaStream_t st) {
+  if (e->split) {
+    // edge pass (PASS 5) then row pass (aggregate + PASS 6); P.gsrc is the gather source of this evaluation
+    cudaError_t c1 = launch_edge_pass(e, P.gsrc, P.p, st);
+    if (c1 != cudaSuccess || e->nblocks == 0) return c1;
+    e->launches++;
+    return e->vdepth == 2 ? launch_row_pass_t<2, 2>(e, P, st) : launch_row_pass_t<1, 1>(e, P, st);
+  }
   e->launches += (e->nblocks > 0);
-  if (e->kernel_version == 2) return e->nblocks > 0 ? pipe_dispatch<false>(e, &P, st) : cudaSuccess;
   if (e->vdepth == 2) return launch_shape<2, 2, ND_B200_E_LINE_DQ, 3>(e, P, st);
   switch (e->ek) {
     case ND_B200_E_DIFFUSION: return launch_shape<1, 1, ND_B200_E_DIFFUSION, 1>(e, P, st);
@@ -358,7 +359,20 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
   if (any_epar) h_epar.assign((size_t)std::max<long long>(e->nentries, 1), 0);
   if (e->ek == EK_GENERIC && d->vdepth == 1) h_ebid.assign((size_t)std::max<long long>(e->nentries, 1), 0);
   if (keep) { e->h_nbr_vid.resize((size_t)e->nentries); e->h_eid.resize((size_t)e->nentries); e->h_side.resize((size_t)e->nentries); }
+  // split mode tables: per entry its position in the edge part of `o`; per edge (in `o` order) the gather offsets
+  const bool generic_edges = (e->ek == EK_GENERIC && d->vdepth == 1);
+  e->oedge_base = d->nv * (long long)d->vdepth;
+  e->oedge_len = d->lastidx_out - e->oedge_base;
+  e->ne_all = d->ne;
+  bool want_split = false;
+  if (const char* s = getenv("ND_B200_KERNEL")) want_split = !strcmp(s, "split") && nrows_owned == e->nrows_total && !(d->vdepth == 2 && d->n_ebatches > 1);
+  if (want_split && e->oedge_len >= INT_MAX) return fail(e, ND_B200_EUNSUPPORTED, "edge output buffer exceeds 2^31 scalars on one device");
+  std::vector<int> h_oidx(want_split ? (size_t)std::max<long long>(e->nentries, 1) : 1), h_es(want_split ? (size_t)std::max<long long>(d->ne, 1) : 1), h_et(want_split ? (size_t)std::max<long long>(d->ne, 1) : 1);
+  std::vector<int> h_eepar, h_eooff;
+  std::vector<uint8_t> h_eebid;
+  if (generic_edges && want_split) { h_eepar.assign((size_t)std::max<long long>(d->ne, 1), 0); h_eooff.assign((size_t)std::max<long long>(d->ne, 1), 0); h_eebid.assign((size_t)std::max<long long>(d->ne, 1), 0); }
   {
+    long long kedge = 0;
     std::vector<long long> cur(cnt.begin(), cnt.end() - 1);
     for (int b = 0; b < d->n_ebatches; ++b) {
       const nd_b200_ebatch& eb = d->ebatches[b];
@@ -367,9 +381,14 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
         const long long s = d->edge_src[eid], t = d->edge_dst[eid];
         const int rs = row_of_vertex[(size_t)s - 1], rt = row_of_vertex[(size_t)t - 1];
         const int ep = eb.pdim > 0 ? (int)(eb.p_first - 1 + i * eb.pdim) : 0;
+        const long long oo = (eb.out_first - 1) + i * (eb.outdim_src + eb.outdim_dst) - e->oedge_base;   // this edge's block in the edge part of o
+        if (want_split) { h_es[(size_t)kedge] = goff[(size_t)s - 1]; h_et[(size_t)kedge] = goff[(size_t)t - 1]; }
+        if (generic_edges && want_split) { h_eepar[(size_t)kedge] = ep; h_eooff[(size_t)kedge] = (int)oo; h_eebid[(size_t)kedge] = (uint8_t)b; }
+        ++kedge;
         // src output precedes dst output in `o` (register_edges!, src/network_structure.jl:244-245)
         if (eb.outdim_src > 0 && owned(rs)) {
           const long long j = cur[(size_t)(rs - e->row_begin)]++;
+          if (want_split) h_oidx[(size_t)j] = (int)oo;
           h_nbr[(size_t)j] = ~goff[(size_t)t - 1];
           if (any_epar) h_epar[(size_t)j] = ep;
           if (!h_ebid.empty()) h_ebid[(size_t)j] = (uint8_t)b;
@@ -377,6 +396,7 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
         }
         if (owned(rt)) {
           const long long j = cur[(size_t)(rt - e->row_begin)]++;
+          if (want_split) h_oidx[(size_t)j] = (int)(oo + eb.outdim_src);
           h_nbr[(size_t)j] = goff[(size_t)s - 1];
           if (any_epar) h_epar[(size_t)j] = ep;
           if (!h_ebid.empty()) h_ebid[(size_t)j] = (uint8_t)b;
@@ -435,17 +455,12 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
   e->nblocks = (int)blk_row.size();
   blk_row.push_back((int)e->row_end);
 
-  // ---- v2 tiles: one per thread-block row range, entry arrays padded so every tile starts 16-byte aligned -----
-  if (const char* s = getenv("ND_B200_KERNEL")) e->kernel_version = (atoi(s) == 2 || !strcmp(s, "v2")) ? 2 : 1;
+  // ---- one 16-byte descriptor per thread block -----------------------------------------------------------
+  e->split = 0;   // default: fused kernel (faster on B200 for every config whose state vector fits in L2)
+  if (want_split) e->split = 1;
   std::vector<int4> tiles;
-  std::vector<unsigned short> rp16;
-  std::vector<int> nbr2, epar2;
-  std::vector<uint8_t> ebid2;
   {
-    const bool v2 = e->kernel_version == 2;
-    const bool generic1 = (e->ek == EK_GENERIC && d->vdepth == 1);
     tiles.reserve((size_t)e->nblocks);
-    if (v2) nbr2.reserve((size_t)e->nentries + 16 * (size_t)e->nblocks + 16);
     size_t bi = 0;
     for (int k = 0; k < e->nblocks; ++k) {
       const int r0 = blk_row[(size_t)k], r1 = blk_row[(size_t)k + 1];
@@ -453,33 +468,11 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
       const long long a = cnt[(size_t)(r0 - e->row_begin)], z = cnt[(size_t)(r1 - e->row_begin)];
       const long long ne = z - a;
       const bool is_long = (r1 - r0 == 1) && ne > e->long_thr;
-      const int e0 = v2 ? (int)nbr2.size() : (int)a;
-      if (v2) {
-        for (long long j = a; j < z; ++j) {
-          nbr2.push_back(h_nbr[(size_t)j]);
-          if (any_epar) epar2.push_back(h_epar[(size_t)j]);
-          if (generic1) ebid2.push_back(h_ebid[(size_t)j]);
-        }
-        while (nbr2.size() % 16) { nbr2.push_back(0); if (any_epar) epar2.push_back(0); if (generic1) ebid2.push_back(0); }
-      }
       int4 t;
-      t.x = r0; t.y = e0;
-      if (is_long) {
-        t.z = (int)ne;
-        t.w = (int)(0x80000000u | ((unsigned)bi << 25) | (1u << 16));
-      } else {
-        t.z = (int)rp16.size();
-        if (v2) {
-          for (int r = r0; r <= r1; ++r) rp16.push_back((unsigned short)(cnt[(size_t)(r - e->row_begin)] - a));
-          while (rp16.size() % 8) rp16.push_back(0);
-        }
-        t.w = (int)((unsigned)ne | ((unsigned)(r1 - r0) << 16) | ((unsigned)bi << 25));
-      }
+      t.x = r0; t.y = (int)a;
+      if (is_long) { t.z = (int)ne; t.w = (int)(0x80000000u | ((unsigned)bi << 25) | (1u << 16)); }
+      else { t.z = 0; t.w = (int)((unsigned)ne | ((unsigned)(r1 - r0) << 16) | ((unsigned)bi << 25)); }
       tiles.push_back(t);
-    }
-    if (v2) {
-      for (int k = 0; k < 16; ++k) { nbr2.push_back(0); if (any_epar) epar2.push_back(0); if (generic1) ebid2.push_back(0); }
-      for (int k = 0; k < 8; ++k) rp16.push_back(0);
     }
     e->ntiles = (int)tiles.size();
   }
@@ -496,14 +489,13 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
     for (int k = 0; k < 2; ++k) CUDA_TRY(e, cudaMalloc((void**)&e->d_vout[k], sizeof(double) * (size_t)(e->nrows_total * e->vdepth)));
   }
   if (upload(e, &e->d_tiles, tiles)) return ND_B200_ECUDA;
-  if (e->kernel_version == 2) {
-    if (upload(e, &e->d_rp16, rp16) || upload(e, &e->d_nbr2, nbr2)) return ND_B200_ECUDA;
-    if (any_epar && upload(e, &e->d_epar2, epar2)) return ND_B200_ECUDA;
-    if (!ebid2.empty() && upload(e, &e->d_ebid2, ebid2)) return ND_B200_ECUDA;
-    if (e->ntiles > 0) CUDA_TRY(e, pipe_dispatch<true>(e, nullptr, nullptr));
-    // the v1 copies are not needed by the pipelined kernel
-    cudaFree(e->d_nbr); cudaFree(e->d_epar); cudaFree(e->d_ebid); cudaFree(e->d_rowptr);
-    e->d_nbr = nullptr; e->d_epar = nullptr; e->d_ebid = nullptr; e->d_rowptr = nullptr;
+  if (e->split) {
+    if (upload(e, &e->d_oidx, h_oidx) || upload(e, &e->d_es, h_es) || upload(e, &e->d_et, h_et)) return ND_B200_ECUDA;
+    if (generic_edges && (upload(e, &e->d_eepar, h_eepar) || upload(e, &e->d_eooff, h_eooff) || upload(e, &e->d_eebid, h_eebid))) return ND_B200_ECUDA;
+    CUDA_TRY(e, cudaMalloc((void**)&e->d_oedge, sizeof(double) * (size_t)std::max<long long>(e->oedge_len, 2)));
+    // the fused kernel's per-entry arrays are not needed
+    cudaFree(e->d_nbr); cudaFree(e->d_epar); cudaFree(e->d_ebid);
+    e->d_nbr = nullptr; e->d_epar = nullptr; e->d_ebid = nullptr;
   }
   return ND_B200_OK;
 }
@@ -595,7 +587,8 @@ void nd_b200_destroy(nd_b200_engine* e) {
   destroy_graph(e);
   cudaFree(e->d_rowptr); cudaFree(e->d_nbr); cudaFree(e->d_epar); cudaFree(e->d_blk_row); cudaFree(e->d_ebid);
   cudaFree(e->d_vb); cudaFree(e->d_eb); cudaFree(e->d_vout[0]); cudaFree(e->d_vout[1]);
-  cudaFree(e->d_tiles); cudaFree(e->d_rp16); cudaFree(e->d_nbr2); cudaFree(e->d_epar2); cudaFree(e->d_ebid2);
+  cudaFree(e->d_tiles); cudaFree(e->d_oidx); cudaFree(e->d_es); cudaFree(e->d_et); cudaFree(e->d_eepar); cudaFree(e->d_eooff);
+  cudaFree(e->d_eebid); cudaFree(e->d_oedge);
   for (int* q : e->d_esrc_off) cudaFree(q);
   for (int* q : e->d_edst_off) cudaFree(q);
   cudaFree(e->d_tmpA); cudaFree(e->d_tmpB); cudaFree(e->d_ksum);
@@ -719,7 +712,7 @@ int nd_b200_rk4(nd_b200_engine* e, double* u, const double* p, double t0, double
 int nd_b200_export_sizes(const nd_b200_engine* e, int64_t sizes[8]) {
   if (!e || !sizes) return ND_B200_EINVAL;
   sizes[0] = e->row_end - e->row_begin; sizes[1] = e->nentries; sizes[2] = e->nblocks; sizes[3] = e->n_long;
-  sizes[4] = e->gather_from_u; sizes[5] = e->gather_from_u ? 1 : 2; sizes[6] = e->row_begin; sizes[7] = e->row_end;
+  sizes[4] = e->gather_from_u; sizes[5] = (e->gather_from_u ? 0 : 1) + (e->split ? 2 : 1); sizes[6] = e->row_begin; sizes[7] = e->row_end;
   return ND_B200_OK;
 }
 

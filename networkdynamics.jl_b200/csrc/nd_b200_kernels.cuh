@@ -59,13 +59,27 @@ struct KParams {
   double hs;                           // dt/2, dt/2, dt for stages 1..3
   double h6;                           // dt/6
   double t;
-  // pipelined kernel (rhs_pipe_kernel): tile-padded copies of the entry arrays
-  const int4* __restrict__ tiles;      // per tile {row0, e0 (multiple of 4), rp0 (multiple of 8) | ne of a long tile, ne | nrows<<16 | batch<<25 | long<<31}
+  const int4* __restrict__ tiles;      // per thread block {row0, e0, ne of a long row, ne | nrows<<16 | batch<<25 | long<<31}
   int ntiles;
-  const unsigned short* __restrict__ rp16;  // per tile nrows+1 row offsets relative to e0
-  const int* __restrict__ nbr2;
-  const int* __restrict__ epar2;
-  const uint8_t* __restrict__ ebid2;
+  // split mode (edge pass + row pass): per entry the position of its value in the edge-output buffer
+  const int* __restrict__ oidx;
+  const double* __restrict__ oedge;    // edge part of the reference's output buffer `o` (src range, dst range per edge)
+};
+
+// parameters of the edge pass (split mode)
+struct EParams {
+  const int* __restrict__ esrc;        // per edge (in `o` order): gather offset of the src vertex output
+  const int* __restrict__ edst;        // ... of the dst vertex output
+  const int* __restrict__ epar;        // generic only: offset of the edge's parameters in p
+  const int* __restrict__ eooff;       // generic only: offset of the edge's block in oedge
+  const uint8_t* __restrict__ ebid;    // generic only: edge batch id
+  const EBDev* __restrict__ eb;
+  long long ne;
+  long long p0;                        // single batch: parameters of edge k at p0 + k*PE
+  int coupling0;                       // single batch: wrapper
+  const double* __restrict__ gsrc;
+  const double* __restrict__ p;
+  double* __restrict__ oedge;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -422,249 +436,166 @@ __global__ void edge_out_kernel(int kind, int coupling, int pdim, int osrc, long
 
 
 // ------------------------------------------------------------------------------------------------
-// v2: persistent, software-pipelined version of the fused kernel.
+// split mode ("edge once"): PASS 5 and the aggregation as two kernels around the reference's own
+// edge-output buffer.
 //
-// The v1 kernel is bound by dependent memory phases (index -> gather -> parameters -> reduce), each
-// exposed to the full L1TEX/L2 queueing latency (ncu: long_scoreboard dominant, L1TEX 57 % busy).
-// Here every CTA is persistent and walks its tiles with a 3-deep pipeline built on cp.async
-// (LDGSTS), so the index stream of tile i+2 and the random gathers of tile i+1 are in flight while
-// tile i is evaluated and reduced:
-//   stage A(i+2): cp.async.cg 16 B   nbr / epar / row offsets  -> shared        (coalesced stream)
-//   stage B(i+1): cp.async.ca  8 B   gsrc[nbr], p[epar], row self/state/params -> shared (gathers)
-//   stage C(i)  : edge values in place in shared memory, ordered per-row sums, vertex model, store
-// Accumulation order per row is unchanged (strictly sequential, the reference's order).
+// Optional (ND_B200_KERNEL=split).  The fused kernel evaluates every edge from both endpoints: per undirected edge
+// 2 random neighbour reads + 1 random parameter read and 2 evaluations of g.  Here each edge is evaluated once.
+// Measured on B200 (profiles/r01_tuning.md): slower than the fused kernel whenever u fits in L2 (the random reads
+// move from the 8 MB state vector to the 64 MB edge-output buffer), ~9 % faster when nothing fits (config 5 scale).
+//   edge_pass_kernel : one thread per edge in `o` order; src output nearly coalesced (edges are sorted by
+//                      src), dst output random, parameters coalesced; writes [osrc | odst] exactly like
+//                      PASS 5 (src/coreloop.jl:78) -> 1 random request and 1 evaluation of g per edge;
+//   row_pass_kernel  : ordered per-row sum over the entries' positions in `o` (the SequentialAggregator
+//                      sweep restricted to one row, src/aggregators.jl:140-151) + vertex model; entries that
+//                      are this row's src outputs are consecutive in `o` -> coalesce; dst outputs random
+//                      -> 1 random request per edge.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
 template <int VD, int ED, int EK, int PE, int BLOCK, int EPT>
-struct PipeSmem {
-  static constexpr int TILE = BLOCK * EPT;
-  int4 desc[4];
-  double xn[2][TILE * VD];                 // gathered neighbour outputs; overwritten in place by the edge values
-  double pe[2][PE > 0 ? TILE * PE : 2];    // gathered edge parameters
-  double self[2][BLOCK * VD];              // own outputs of the tile's rows
-  double vu[2][BLOCK * 2];                 // states of the tile's rows (dim <= 2)
-  double vp[2][BLOCK * 4];                 // parameters of the tile's rows (pdim <= 4)
-  int nbr[2][TILE];
-  int epar[2][PE > 0 ? TILE : 4];
-  unsigned short rp[2][BLOCK + 8];
-  uint8_t rowid[2][TILE];
-  uint8_t ebid[2][EK == EK_GENERIC ? TILE : 16];
-};
+__global__ void __launch_bounds__(BLOCK) edge_pass_kernel(const __grid_constant__ EParams Q) {
+  const long long base = (long long)blockIdx.x * (BLOCK * EPT) + threadIdx.x;
+  int so[EPT], to[EPT];
+#pragma unroll
+  for (int k = 0; k < EPT; ++k) {
+    const long long e = base + (long long)k * BLOCK;
+    so[k] = 0; to[k] = 0;
+    if (e < Q.ne) { so[k] = Q.esrc[e]; to[k] = Q.edst[e]; }
+  }
+  double vs[EPT][VD], vd[EPT][VD];
+#pragma unroll
+  for (int k = 0; k < EPT; ++k) {
+    const long long e = base + (long long)k * BLOCK;
+#pragma unroll
+    for (int q = 0; q < VD; ++q) { vs[k][q] = 0.0; vd[k][q] = 0.0; }
+    if (e < Q.ne) {
+      if constexpr (VD == 2) {
+        const double2 a = *reinterpret_cast<const double2*>(Q.gsrc + so[k]);
+        const double2 b = *reinterpret_cast<const double2*>(Q.gsrc + to[k]);
+        vs[k][0] = a.x; vs[k][1] = a.y; vd[k][0] = b.x; vd[k][1] = b.y;
+      } else {
+        vs[k][0] = Q.gsrc[so[k]]; vd[k][0] = Q.gsrc[to[k]];
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < EPT; ++k) {
+    const long long e = base + (long long)k * BLOCK;
+    if (e >= Q.ne) continue;
+    int kind = EK, coupling = Q.coupling0;
+    const double* pe = Q.p + Q.p0 + e * PE;
+    long long ooff;
+    if constexpr (EK == EK_GENERIC) {
+      const EBDev E = Q.eb[Q.ebid[e]];
+      kind = E.kind; coupling = E.coupling;
+      pe = Q.p + Q.epar[e];
+      ooff = Q.eooff[e];
+    } else {
+      ooff = e * (coupling == ND_B200_DIRECTED ? ED : 2 * ED);
+    }
+    double val[ED];
+    edge_g_dst<VD, ED>(kind, val, vs[k], vd[k], pe);
+    double* oo = Q.oedge + ooff;
+    if (coupling == ND_B200_DIRECTED) {
+#pragma unroll
+      for (int q = 0; q < ED; ++q) oo[q] = val[q];
+    } else {
+      // AntiSymmetric: osrc = -odst; Symmetric: osrc = odst (src/component_functions.jl:117-152)
+      double sv[ED];
+#pragma unroll
+      for (int q = 0; q < ED; ++q) sv[q] = (coupling == ND_B200_ANTISYMMETRIC) ? -val[q] : val[q];
+      if constexpr (EK == EK_GENERIC) {     // mixed wrappers: blocks of width ED (Directed) shift the alignment
+#pragma unroll
+        for (int q = 0; q < ED; ++q) { oo[q] = sv[q]; oo[ED + q] = val[q]; }
+      } else if constexpr (ED == 1) {
+        *reinterpret_cast<double2*>(oo) = make_double2(sv[0], val[0]);
+      } else {
+        *reinterpret_cast<double2*>(oo) = make_double2(sv[0], sv[1]);
+        *reinterpret_cast<double2*>(oo + 2) = make_double2(val[0], val[1]);
+      }
+    }
+  }
+}
 
-__device__ __forceinline__ int tile_ne(const int4& d) { return d.w & 0xFFFF; }
-__device__ __forceinline__ int tile_nrows(const int4& d) { return (d.w >> 16) & 0x1FF; }
-__device__ __forceinline__ int tile_batch(const int4& d) { return (d.w >> 25) & 0x3F; }
-__device__ __forceinline__ bool tile_long(const int4& d) { return d.w < 0; }
-
-template <int VD, int ED, int EK, int PE, int BLOCK, int EPT>
-__global__ void __launch_bounds__(BLOCK) rhs_pipe_kernel(const __grid_constant__ KParams P) {
-  static_assert(VD == ED, "edge values overwrite the gathered neighbour values in place");
-  static_assert(BLOCK <= 256 && EPT % 4 == 0, "row ids are uint8; index chunks are 16 bytes");
-  using Smem = PipeSmem<VD, ED, EK, PE, BLOCK, EPT>;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  Smem& S = *reinterpret_cast<Smem*>(smem_raw);
+template <int VD, int ED, int BLOCK, int EPT>
+__global__ void __launch_bounds__(BLOCK, 2048 / BLOCK) row_pass_kernel(const __grid_constant__ KParams P) {
+  constexpr int TILE = BLOCK * EPT;
+  __shared__ double s_val[TILE * ED];
+  __shared__ int s_rp[BLOCK + 1];
   const int tid = threadIdx.x;
-  const int G = gridDim.x;
-  const int first = blockIdx.x;
-  const int coupling0 = P.n_eb > 0 ? P.eb[0].coupling : 0;
-  auto tile_of = [&](int i) { return first + i * G; };
+  const int4 d = __ldg(&P.tiles[blockIdx.x]);
+  const int r0 = d.x, e0 = d.y;
+  const bool is_long = d.w < 0;
+  const int nrows = (d.w >> 16) & 0x1FF;
+  const int ne = is_long ? d.z : (d.w & 0xFFFF);
+  const VBDev B = P.vb[(d.w >> 25) & 0x3F];
 
-  // prologue: descriptors of the first three tiles of this CTA
-  if (tid < 3) {
-    const int t = tile_of(tid);
-    S.desc[tid] = t < P.ntiles ? P.tiles[t] : make_int4(0, 0, 0, 0);
+  if (is_long) {   // hub row: strided partial sums + fixed-shape tree
+    double part[ED];
+#pragma unroll
+    for (int q = 0; q < ED; ++q) part[q] = 0.0;
+    for (int jj = tid; jj < ne; jj += BLOCK) {
+      const int oi = P.oidx[e0 + jj];
+#pragma unroll
+      for (int q = 0; q < ED; ++q) part[q] = part[q] + P.oedge[(long long)oi + q];
+    }
+#pragma unroll
+    for (int q = 0; q < ED; ++q) s_val[tid * ED + q] = part[q];
+    __syncthreads();
+    for (int s = BLOCK / 2; s > 0; s >>= 1) {
+      if (tid < s) {
+#pragma unroll
+        for (int q = 0; q < ED; ++q) s_val[tid * ED + q] = s_val[tid * ED + q] + s_val[(tid + s) * ED + q];
+      }
+      __syncthreads();
+    }
+    if (tid == 0) {
+      double acc[ED], v[2], self[VD];
+#pragma unroll
+      for (int q = 0; q < ED; ++q) acc[q] = s_val[q];
+#pragma unroll
+      for (int q = 0; q < VD; ++q) self[q] = P.gather_from_u ? 0.0 : P.gsrc[(long long)r0 * VD + q];
+      load_vertex_state(P, B, r0, v);
+      vertex_phase<VD, ED>(P, B, r0, acc, self, v, P.p + B.p0 + (long long)(r0 - B.row0) * B.pdim);
+    }
+    return;
+  }
+
+  int oi[EPT];
+#pragma unroll
+  for (int k = 0; k < EPT; ++k) {
+    const int jj = k * BLOCK + tid;
+    oi[k] = jj < ne ? P.oidx[e0 + jj] : 0;
+  }
+  if (tid < nrows) s_rp[tid] = P.rowptr[(r0 - P.row_base) + tid] - e0;
+  if (tid == 0) s_rp[nrows] = ne;
+#pragma unroll
+  for (int k = 0; k < EPT; ++k) {
+    const int jj = k * BLOCK + tid;
+    if (jj < ne) {
+      if constexpr (ED == 2) {
+        const double2 t2 = *reinterpret_cast<const double2*>(P.oedge + oi[k]);
+        s_val[jj * 2] = t2.x; s_val[jj * 2 + 1] = t2.y;
+      } else {
+        s_val[jj] = P.oedge[oi[k]];
+      }
+    }
   }
   __syncthreads();
-
-  unsigned side_cur = 0, side_nxt = 0;   // per-thread side bits of its EPT entries (tile i / tile i+1)
-  unsigned rng_cur = 0, rng_nxt = 0;     // row-thread entry range (a | z << 16)
-
-  const int my_tiles = first < P.ntiles ? (P.ntiles - first + G - 1) / G : 0;
-  for (int i = -2; i < my_tiles; ++i) {
-    // ---- S1: stage A of tile i+1 has landed; everybody is done with tile i-1 ----------------------
-    cp_async_wait<1>();
-    __syncthreads();
-
-    // ---- stage D(i+3) + A(i+2): descriptor and index stream -------------------------------------
-    {
-      const int t3 = tile_of(i + 3);
-      if (tid == 0 && i + 3 >= 3 && t3 < P.ntiles) cp_async16(&S.desc[(i + 3) & 3], &P.tiles[t3]);
-      const int ia = i + 2;
-      if (ia >= 0 && ia < my_tiles) {
-        const int4 d = S.desc[ia & 3];
-        if (!tile_long(d)) {
-          const int b = ia & 1;
-          const int ne = tile_ne(d), nr = tile_nrows(d);
-          const int nchunk = (ne + 3) >> 2;
-          for (int c = tid; c < nchunk; c += BLOCK) {
-            cp_async16(&S.nbr[b][c * 4], P.nbr2 + d.y + c * 4);
-            if constexpr (PE > 0) cp_async16(&S.epar[b][c * 4], P.epar2 + d.y + c * 4);
-          }
-          if constexpr (EK == EK_GENERIC) {
-            const int nc16 = (ne + 15) >> 4;
-            for (int c = tid; c < nc16; c += BLOCK) cp_async16(&S.ebid[b][c * 16], P.ebid2 + d.y + c * 16);
-          }
-          const int nrc = (nr + 1 + 7) >> 3;
-          if (tid < nrc) cp_async16(&S.rp[b][tid * 8], P.rp16 + d.z + tid * 8);
-        }
-      }
-      cp_async_commit();
+  if (tid < nrows) {
+    double acc[ED];
+#pragma unroll
+    for (int q = 0; q < ED; ++q) acc[q] = 0.0;
+    const int a = s_rp[tid], z = s_rp[tid + 1];
+    for (int jj = a; jj < z; ++jj) {
+#pragma unroll
+      for (int q = 0; q < ED; ++q) acc[q] = acc[q] + s_val[jj * ED + q];
     }
-
-    // ---- stage B(i+1): gathers ---------------------------------------------------------------------
-    {
-      const int ib = i + 1;
-      side_nxt = 0; rng_nxt = 0;
-      if (ib >= 0 && ib < my_tiles) {
-        const int4 d = S.desc[ib & 3];
-        if (!tile_long(d)) {
-          const int b = ib & 1;
-          const int ne = tile_ne(d), nr = tile_nrows(d);
+    double self[VD], v[2];
 #pragma unroll
-          for (int k = 0; k < EPT; ++k) {
-            const int jj = k * BLOCK + tid;
-            if (jj < ne) {
-              const int nb = S.nbr[b][jj];
-              const int off = nb < 0 ? ~nb : nb;
-              side_nxt |= (nb < 0 ? 1u : 0u) << k;
-              if constexpr (VD == 2) cp_async16(&S.xn[b][jj * 2], P.gsrc + off);
-              else cp_async8(&S.xn[b][jj], P.gsrc + off);
-              if constexpr (PE > 0) {
-                const int ep = S.epar[b][jj];
-#pragma unroll
-                for (int q = 0; q < PE; ++q) cp_async8(&S.pe[b][jj * PE + q], P.p + ep + q);
-              }
-            }
-          }
-          if (tid < nr) {
-            const VBDev B = P.vb[tile_batch(d)];
-            const int row = d.x + tid;
-            const long long li = row - B.row0;
-            const long long s = B.state0 + li * B.dim;
-            const long long sidx = P.gather_from_u ? s : (long long)row * VD;
-            if constexpr (VD == 2) cp_async16(&S.self[b][tid * 2], P.gsrc + sidx);
-            else cp_async8(&S.self[b][tid], P.gsrc + sidx);
-            if (P.mode != MODE_AGG) {
-              for (int c = 0; c < B.dim; ++c) cp_async8(&S.vu[b][tid * 2 + c], P.u + s + c);
-              for (int c = 0; c < B.pdim; ++c) cp_async8(&S.vp[b][tid * 4 + c], P.p + B.p0 + li * B.pdim + c);
-            }
-            const unsigned a = S.rp[b][tid], z = S.rp[b][tid + 1];
-            rng_nxt = a | (z << 16);
-            for (unsigned jj = a; jj < z; ++jj) S.rowid[b][jj] = (uint8_t)tid;
-          }
-        }
-      }
-      cp_async_commit();
-    }
-
-    // ---- S2: the gathers of tile i have landed ------------------------------------------------------
-    cp_async_wait<2>();
-    __syncthreads();
-
-    if (i >= 0) {
-      const int4 d = S.desc[i & 3];
-      const int b = i & 1;
-      const VBDev B = P.vb[tile_batch(d)];
-      if (tile_long(d)) {
-        // ---- long row: the whole CTA reduces one row with a fixed-shape tree (direct loads) ---------
-        const int row = d.x, e0 = d.y, ne = d.z;
-        double self[VD];
-        const long long sidx = P.gather_from_u ? (B.state0 + (long long)(row - B.row0) * B.dim) : (long long)row * VD;
-#pragma unroll
-        for (int k = 0; k < VD; ++k) self[k] = P.gsrc[sidx + k];
-        double part[ED];
-#pragma unroll
-        for (int q = 0; q < ED; ++q) part[q] = 0.0;
-        for (int jj = tid; jj < ne; jj += BLOCK) {
-          int nb = P.nbr2[e0 + jj];
-          const int side = nb < 0;
-          nb = side ? ~nb : nb;
-          double xn[VD];
-#pragma unroll
-          for (int k = 0; k < VD; ++k) xn[k] = P.gsrc[(long long)nb + k];
-          const double* pe = P.p;
-          if constexpr (PE > 0) pe = P.p + P.epar2[e0 + jj];
-          int kind = EK, coupling = coupling0;
-          if constexpr (EK == EK_GENERIC) {
-            const EBDev E = P.eb[P.ebid2[e0 + jj]];
-            kind = E.kind; coupling = E.coupling;
-          }
-          double val[ED];
-          entry_value<VD, ED>(kind, coupling, side, self, xn, pe, val);
-#pragma unroll
-          for (int q = 0; q < ED; ++q) part[q] = part[q] + val[q];
-        }
-#pragma unroll
-        for (int q = 0; q < ED; ++q) S.xn[b][tid * ED + q] = part[q];
-        __syncthreads();
-        for (int s = BLOCK / 2; s > 0; s >>= 1) {
-          if (tid < s) {
-#pragma unroll
-            for (int q = 0; q < ED; ++q) S.xn[b][tid * ED + q] = S.xn[b][tid * ED + q] + S.xn[b][(tid + s) * ED + q];
-          }
-          __syncthreads();
-        }
-        if (tid == 0) {
-          double acc[ED], v[2];
-#pragma unroll
-          for (int q = 0; q < ED; ++q) acc[q] = S.xn[b][q];
-          load_vertex_state(P, B, row, v);
-          vertex_phase<VD, ED>(P, B, row, acc, self, v, P.p + B.p0 + (long long)(row - B.row0) * B.pdim);
-        }
-      } else {
-        // ---- stage C(i): edge values in place ----------------------------------------------------------
-        const int ne = tile_ne(d), nr = tile_nrows(d);
-#pragma unroll
-        for (int k = 0; k < EPT; ++k) {
-          const int jj = k * BLOCK + tid;
-          if (jj < ne) {
-            const int r = S.rowid[b][jj];
-            double self[VD], xn[VD], val[ED];
-#pragma unroll
-            for (int q = 0; q < VD; ++q) { self[q] = S.self[b][r * VD + q]; xn[q] = S.xn[b][jj * VD + q]; }
-            int kind = EK, coupling = coupling0;
-            if constexpr (EK == EK_GENERIC) {
-              const EBDev E = P.eb[S.ebid[b][jj]];
-              kind = E.kind; coupling = E.coupling;
-            }
-            entry_value<VD, ED>(kind, coupling, (side_cur >> k) & 1u, self, xn, &S.pe[b][PE > 0 ? jj * PE : 0], val);
-#pragma unroll
-            for (int q = 0; q < ED; ++q) S.xn[b][jj * ED + q] = val[q];
-          }
-        }
-        __syncthreads();
-        // ---- ordered per-row accumulation (reference order) + vertex model -------------------------------
-        if (tid < nr) {
-          double acc[ED];
-#pragma unroll
-          for (int q = 0; q < ED; ++q) acc[q] = 0.0;
-          const int a = rng_cur & 0xFFFF, z = rng_cur >> 16;
-          for (int jj = a; jj < z; ++jj) {
-#pragma unroll
-            for (int q = 0; q < ED; ++q) acc[q] = acc[q] + S.xn[b][jj * ED + q];
-          }
-          double self[VD];
-#pragma unroll
-          for (int q = 0; q < VD; ++q) self[q] = S.self[b][tid * VD + q];
-          vertex_phase<VD, ED>(P, B, d.x + tid, acc, self, &S.vu[b][tid * 2], &S.vp[b][tid * 4]);
-        }
-      }
-    }
-    side_cur = side_nxt;
-    rng_cur = rng_nxt;
+    for (int q = 0; q < VD; ++q) self[q] = P.gather_from_u ? 0.0 : P.gsrc[(long long)(r0 + tid) * VD + q];
+    load_vertex_state(P, B, r0 + tid, v);
+    vertex_phase<VD, ED>(P, B, r0 + tid, acc, self, v, P.p + B.p0 + (long long)(r0 + tid - B.row0) * B.pdim);
   }
-  cp_async_wait<0>();
 }
 
 }  // namespace ndb

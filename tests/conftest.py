@@ -26,3 +26,10 @@ def cuda():
     import ndb200
     ndb200._cabi.lib()  # raises loudly if libnd_b200.so is missing
     return torch
+
+
+@pytest.fixture(params=["split", "fused"])
+def kernel_mode(request, monkeypatch):
+    """run a test once per evaluation mode of the engine (edge-once split passes / single fused kernel)"""
+    monkeypatch.setenv("ND_B200_KERNEL", request.param)
+    return request.param

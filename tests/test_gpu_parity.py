@@ -44,7 +44,7 @@ def _run_gpu(torch, nw, u, p, t=0.0):
 
 @pytest.mark.parametrize("name", ["cfg1_kuramoto_ws", "cfg2_diffusion_er", "cfg2_diffusion_er_nop", "cfg3_mixed_kuramoto_ba",
                                   "cfg3b_bench_inertia_ba", "cfg4_powergrid_grid", "cfg5_kuramoto_er"])
-def test_rhs_matches_sequential_oracle(nd, cuda, name):
+def test_rhs_matches_sequential_oracle(nd, cuda, kernel_mode, name):
     g, vm, em = _configs(nd)[name]
     nw = nd.Network(g, vm, em, execution=nd.B200Execution(), aggregator=nd.B200Aggregator("+"))
     onw = oracle_network(g, vm, em)
@@ -90,7 +90,7 @@ def test_csr_is_bit_exact(nd, cuda, name):
     assert np.array_equal((v_aggr[own - 1] - 1) // ed, np.repeat(np.arange(g.nv), np.diff(rowptr)))
 
 
-def test_mixed_edge_batches_directed_graph(nd, cuda):
+def test_mixed_edge_batches_directed_graph(nd, cuda, kernel_mode):
     """test/aggregators_test.jl:14-67 restated for the registry: directed WS graph, random mix of vertex and edge types
     with AntiSymmetric / Symmetric / Directed wrappers -> generic multi-batch kernel."""
     L = nd.Lib
@@ -111,7 +111,7 @@ def test_mixed_edge_batches_directed_graph(nd, cuda):
     assert err <= TOL_DU, err
 
 
-def test_reference_gpu_test_network(nd, cuda):
+def test_reference_gpu_test_network(nd, cuda, kernel_mode):
     """test/GPU_test.jl:12-69 restated for the registry models: complete_graph(4), two vertex types, several edge types."""
     L = nd.Lib
     g = nd.complete_graph(4)
@@ -124,7 +124,7 @@ def test_reference_gpu_test_network(nd, cuda):
     assert floored_rel_err(du, onw.rhs(u, p)) <= TOL_DU
 
 
-def test_edge_cases(nd, cuda):
+def test_edge_cases(nd, cuda, kernel_mode):
     L = nd.Lib
     # no edges at all: du = f_v(u, 0, p)
     g = nd.SimpleGraph(5, [], [])
@@ -153,7 +153,7 @@ def test_edge_cases(nd, cuda):
         assert nw.engine_sizes()["n_long_rows"] == 1
 
 
-def test_diffusion_bit_exact_and_laplacian(nd, cuda):
+def test_diffusion_bit_exact_and_laplacian(nd, cuda, kernel_mode):
     """diffusion has no transcendental: with the reference's accumulation order the result is BIT-identical to the
     sequential oracle (rows below the long-row threshold), and equals -L*x (test/diffusion_test.jl:80-90)."""
     g = nd.erdos_renyi(2000, 8000, seed=9)
@@ -172,7 +172,7 @@ def test_diffusion_bit_exact_and_laplacian(nd, cuda):
     assert np.allclose(du, -Lm @ x, rtol=1e-12, atol=1e-12)
 
 
-def test_get_buffers_matches_oracle(nd, cuda):
+def test_get_buffers_matches_oracle(nd, cuda, kernel_mode):
     """get_buffers / RET=:buf_init (src/coreloop.jl:103-109): o and aggbuf in the reference layout"""
     torch = cuda
     for name in ("cfg3_mixed_kuramoto_ba", "cfg4_powergrid_grid"):
@@ -227,7 +227,7 @@ def test_host_buffer_path_and_errors(nd, cuda):
 
 
 @pytest.mark.parametrize("name", ["cfg4_powergrid_grid", "cfg1_kuramoto_ws", "cfg3_mixed_kuramoto_ba"])
-def test_rk4_trajectory(nd, cuda, name):
+def test_rk4_trajectory(nd, cuda, kernel_mode, name):
     """north_star: trajectories agree within 1e-9 after 1000 fixed-step RK4 steps (dt = 1e-3)."""
     torch = cuda
     g, vm, em = _configs(nd, scale=0.1)[name]
@@ -262,7 +262,8 @@ def test_launch_shapes_agree(nd, cuda, monkeypatch):
     g, vm, em = _configs(nd, scale=0.2)["cfg3_mixed_kuramoto_ba"]
     onw = oracle_network(g, vm, em)
     outs = []
-    for kernel, block, ept in (("v2", 256, 8), ("v2", 256, 4), ("v2", 128, 8), ("v2", 128, 4), ("v1", 256, 8), ("v1", 128, 4)):
+    for kernel, block, ept in (("split", 256, 8), ("split", 256, 4), ("split", 128, 8), ("split", 128, 4), ("fused", 256, 8),
+                               ("fused", 256, 4), ("fused", 128, 8), ("fused", 128, 4)):
         monkeypatch.setenv("ND_B200_KERNEL", kernel)
         monkeypatch.setenv("ND_B200_BLOCK", str(block))
         monkeypatch.setenv("ND_B200_EPT", str(ept))
