@@ -161,6 +161,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2_diffusion_er_1e6", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"], help="multi-GPU state exchange")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -186,7 +187,7 @@ def main():
         pnw = None
     else:
         from networkdynamics_jl_b200.distributed import PartitionedNetwork
-        pnw = PartitionedNetwork(g, vm, em, rank=rank, world=world, group=dist.group.WORLD)
+        pnw = PartitionedNetwork(g, vm, em, rank=rank, world=world, group=dist.group.WORLD, exchange=args.exchange)
         nw = pnw.nw
     t_build = time.time() - t0
     sizes = nw.engine_sizes()
@@ -273,6 +274,9 @@ def main():
                       "cudaMemcpyAsync D2H (du), stream sync; wall clock around the calls"}
         assert np.array_equal(hdu, du.cpu().numpy()), "host-buffer path and device path disagree"
 
+    if pnw is not None:
+        assert not pnw.comm_timed_out(), "a rank timed out waiting for a peer's states"
+        pnw.close()
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -300,7 +304,8 @@ def main():
         "config": {"workload": args.workload, "graph": f"erdos_renyi(N={g.nv}, E={g.ne}), seed 1", "vertex": "diffusion_vertex",
                    "edge": "diffusion_edge(pdim=1)", "directed_entries": n_entries_all,
                    "l2": "flushed between timed steps by a 256 MiB write outside the event brackets; value_l2_warm = back-to-back",
-                   "partition": "none" if world == 1 else f"{world} contiguous vertex ranges, vertex outputs exchanged every step",
+                   "partition": "none" if world == 1 else f"{world} contiguous vertex ranges, vertex outputs exchanged every step "
+                                f"({pnw.exchange_kind}: " + ("NVLink peer stores + arrival flags, wait fused into the RHS kernel)" if pnw.exchange_kind == "p2p" else "torch.distributed all-gather)"),
                    "launch_shape": {"blocks": sizes["nblocks"], "long_rows": sizes["n_long_rows"]}},
         "gpu_launches": int(launches), "clocks": clocks,
         "setup_s": {"graph": round(t_graph, 2), "network+csr": round(t_build, 2)},

@@ -141,6 +141,26 @@ int64_t nd_b200_launch_count(const nd_b200_engine*);
 int nd_b200_set_timing(nd_b200_engine*, int enabled);
 int nd_b200_timings(nd_b200_engine*, double* fused_ms_avg, double* prepass_ms_avg, int64_t* ncalls);
 
+/* ---- multi-GPU: state exchange over NVLink peer memory (one process per GPU) -----------------------------------
+ * The reference has no multi-device path.  A `comm` owns this rank's double-buffered replica of the
+ * full state vector plus an arrival-flag array, all in ONE device allocation that the other ranks map through CUDA
+ * IPC.  nd_b200_rhs_exchange = "publish my rows' states into every rank's replica with plain NVLink stores, raise my
+ * flag everywhere" + "RHS kernel that waits for all flags and gathers from the local replica".  No NCCL, no host
+ * synchronisation on the data path.  Collective: every rank must make the same sequence of calls. */
+typedef struct nd_b200_comm nd_b200_comm;
+#define ND_B200_IPC_HANDLE_BYTES 64
+int nd_b200_comm_create(int32_t device, int32_t rank, int32_t world, int64_t nstates, nd_b200_comm** out);
+/* opaque handle (ND_B200_IPC_HANDLE_BYTES bytes) to ship to the peers (e.g. torch.distributed all_gather_object) */
+int nd_b200_comm_export(nd_b200_comm*, void* handle_out);
+int nd_b200_comm_open_peer(nd_b200_comm*, int32_t peer, const void* handle);
+/* replaces `(nw::Network)(du,u,p,t)` for a row-partitioned engine: only the owned states of u need to be valid */
+int nd_b200_rhs_exchange(nd_b200_engine*, nd_b200_comm*, double* du, const double* u, const double* p, double t,
+                         void* stream);
+/* *timed_out = 1 if some RHS kernel gave up waiting for a peer (~2 s spin budget; results are then invalid) */
+int nd_b200_comm_status(nd_b200_comm*, int32_t* timed_out);
+const char* nd_b200_comm_last_error(const nd_b200_comm*);
+void nd_b200_comm_destroy(nd_b200_comm*);
+
 /* pinned host memory for nd_b200_rhs_host callers */
 void* nd_b200_host_alloc(int64_t bytes);
 void nd_b200_host_free(void*);

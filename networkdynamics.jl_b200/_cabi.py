@@ -54,7 +54,10 @@ EXPORTED_SYMBOLS = [
     "nd_b200_create", "nd_b200_destroy", "nd_b200_last_error", "nd_b200_abi_version", "nd_b200_rhs",
     "nd_b200_rhs_host", "nd_b200_get_buffers", "nd_b200_rk4", "nd_b200_export_sizes", "nd_b200_export_tables",
     "nd_b200_launch_count", "nd_b200_set_timing", "nd_b200_timings", "nd_b200_host_alloc", "nd_b200_host_free",
+    "nd_b200_comm_create", "nd_b200_comm_export", "nd_b200_comm_open_peer", "nd_b200_rhs_exchange", "nd_b200_comm_status",
+    "nd_b200_comm_last_error", "nd_b200_comm_destroy",
 ]
+IPC_HANDLE_BYTES = 64
 
 
 def nvcc_path() -> str:
@@ -124,6 +127,20 @@ def lib():
     L.nd_b200_host_alloc.argtypes = [C.c_int64]
     L.nd_b200_host_free.restype = None
     L.nd_b200_host_free.argtypes = [C.c_void_p]
+    L.nd_b200_comm_create.restype = C.c_int
+    L.nd_b200_comm_create.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.POINTER(C.c_void_p)]
+    L.nd_b200_comm_export.restype = C.c_int
+    L.nd_b200_comm_export.argtypes = [C.c_void_p, C.c_char_p]
+    L.nd_b200_comm_open_peer.restype = C.c_int
+    L.nd_b200_comm_open_peer.argtypes = [C.c_void_p, C.c_int32, C.c_char_p]
+    L.nd_b200_rhs_exchange.restype = C.c_int
+    L.nd_b200_rhs_exchange.argtypes = [C.c_void_p, C.c_void_p, dp, dp, dp, C.c_double, C.c_void_p]
+    L.nd_b200_comm_status.restype = C.c_int
+    L.nd_b200_comm_status.argtypes = [C.c_void_p, i32p]
+    L.nd_b200_comm_last_error.restype = C.c_char_p
+    L.nd_b200_comm_last_error.argtypes = [C.c_void_p]
+    L.nd_b200_comm_destroy.restype = None
+    L.nd_b200_comm_destroy.argtypes = [C.c_void_p]
     if L.nd_b200_abi_version() != ABI_VERSION:
         raise RuntimeError("libnd_b200.so ABI version mismatch; rebuild")
     _lib = L

@@ -51,6 +51,7 @@ struct nd_b200_engine {
   VBDev* d_vb = nullptr;
   EBDev* d_eb = nullptr;
   double *d_vout[2] = {nullptr, nullptr};
+  std::vector<std::pair<long long, long long>> own_segs;   // owned state ranges (0-based start, length)
   int4* d_tiles = nullptr;   // one descriptor per thread block
   int ntiles = 0;
   // evaluation mode: 0 = single fused kernel (default); 1 = edge pass + row pass around the edge-output buffer
@@ -455,6 +456,11 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
   e->nblocks = (int)blk_row.size();
   blk_row.push_back((int)e->row_end);
 
+  // owned state ranges: one per vertex batch the row range intersects
+  for (const HostVB& h : e->hvb) {
+    const long long lo = std::max<long long>(e->row_begin, h.row0), hi = std::min<long long>(e->row_end, h.row0 + h.count);
+    if (lo < hi && h.dim > 0) e->own_segs.push_back({h.state0 + (lo - h.row0) * h.dim, (hi - lo) * h.dim});
+  }
   // ---- one 16-byte descriptor per thread block -----------------------------------------------------------
   e->split = 0;   // default: fused kernel (faster on B200 for every config whose state vector fits in L2)
   if (want_split) e->split = 1;
@@ -507,12 +513,15 @@ int check_call(nd_b200_engine* e, const void* du, const void* u, const void* p) 
   return 0;
 }
 
+struct WaitSpec { const double* gsrc; const unsigned long long* flags; unsigned long long seq; int world; int* timeout; };
+
 int rhs_impl(nd_b200_engine* e, double* du, const double* u, const double* p, double t, cudaStream_t st, int mode,
-             double* aggbuf) {
+             double* aggbuf, const WaitSpec* w = nullptr) {
   KParams P;
   fill_params(e, P);
   P.u = u; P.p = p; P.du = du; P.mode = mode; P.aggbuf = aggbuf; P.t = t;
   P.gsrc = u;
+  if (w) { P.gsrc = w->gsrc; P.wait_flags = w->flags; P.wait_seq = w->seq; P.wait_world = w->world; P.wait_timeout = w->timeout; }
   if (e->timing) {
     if (ensure_events(e, e->ev, e->ev_used + 2) || ensure_events(e, e->ev_pre, e->ev_pre_used + 2)) return ND_B200_ECUDA;
   }
@@ -763,5 +772,138 @@ void* nd_b200_host_alloc(int64_t bytes) {
   return q;
 }
 void nd_b200_host_free(void* q) { if (q) cudaFreeHost(q); }
+
+}  // extern "C"
+
+// ---- multi-GPU exchange object ------------------------------------------------------------------------------------------
+struct nd_b200_comm {
+  int device = 0, rank = 0, world = 1;
+  long long nstates = 0;
+  size_t replica_bytes = 0;               // bytes of ONE replica, rounded up to 256
+  unsigned char* base[HALO_MAX_WORLD] = {nullptr};   // [r]: rank r's shared block (own: cudaMalloc, peers: IPC mapping)
+  unsigned int* d_done = nullptr;
+  int* d_timeout = nullptr;
+  unsigned long long seq = 0;
+  std::string err;
+  double* replica(int r, int parity) const { return reinterpret_cast<double*>(base[r] + (size_t)parity * replica_bytes); }
+  unsigned long long* flags(int r) const { return reinterpret_cast<unsigned long long*>(base[r] + 2 * replica_bytes); }
+};
+
+namespace {
+int cfail(nd_b200_comm* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf; else g_create_error = buf;
+  return code;
+}
+#define COMM_TRY(c, call)                                                                        \
+  do {                                                                                           \
+    cudaError_t _c = (call);                                                                     \
+    if (_c != cudaSuccess) return cfail(c, ND_B200_ECUDA, "%s: %s", #call, cudaGetErrorString(_c)); \
+  } while (0)
+}  // namespace
+
+extern "C" {
+
+int nd_b200_comm_create(int32_t device, int32_t rank, int32_t world, int64_t nstates, nd_b200_comm** out) {
+  if (!out || world < 1 || world > HALO_MAX_WORLD || rank < 0 || rank >= world || nstates <= 0)
+    return cfail(nullptr, ND_B200_EINVAL, "nd_b200_comm_create: bad arguments (world must be 1..%d)", HALO_MAX_WORLD);
+  nd_b200_comm* c = new (std::nothrow) nd_b200_comm();
+  if (!c) return cfail(nullptr, ND_B200_ENOMEM, "out of host memory");
+  c->device = device; c->rank = rank; c->world = world; c->nstates = nstates;
+  c->replica_bytes = ((size_t)nstates * sizeof(double) + 255) / 256 * 256;
+  const size_t total = 2 * c->replica_bytes + 256;
+  cudaError_t ce = cudaSetDevice(device);
+  if (ce == cudaSuccess) ce = cudaMalloc((void**)&c->base[rank], total);
+  if (ce == cudaSuccess) ce = cudaMemset(c->base[rank], 0, total);
+  if (ce == cudaSuccess) ce = cudaMalloc((void**)&c->d_done, sizeof(unsigned int));
+  if (ce == cudaSuccess) ce = cudaMemset(c->d_done, 0, sizeof(unsigned int));
+  if (ce == cudaSuccess) ce = cudaMalloc((void**)&c->d_timeout, sizeof(int));
+  if (ce == cudaSuccess) ce = cudaMemset(c->d_timeout, 0, sizeof(int));
+  if (ce == cudaSuccess) ce = cudaDeviceSynchronize();
+  if (ce != cudaSuccess) {
+    cfail(nullptr, ND_B200_ECUDA, "nd_b200_comm_create: %s", cudaGetErrorString(ce));
+    nd_b200_comm_destroy(c);
+    return ND_B200_ECUDA;
+  }
+  *out = c;
+  return ND_B200_OK;
+}
+
+int nd_b200_comm_export(nd_b200_comm* c, void* handle_out) {
+  if (!c || !handle_out) return ND_B200_EINVAL;
+  static_assert(sizeof(cudaIpcMemHandle_t) <= ND_B200_IPC_HANDLE_BYTES, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  COMM_TRY(c, cudaSetDevice(c->device));
+  COMM_TRY(c, cudaIpcGetMemHandle(&h, c->base[c->rank]));
+  memset(handle_out, 0, ND_B200_IPC_HANDLE_BYTES);
+  memcpy(handle_out, &h, sizeof h);
+  return ND_B200_OK;
+}
+
+int nd_b200_comm_open_peer(nd_b200_comm* c, int32_t peer, const void* handle) {
+  if (!c || !handle || peer < 0 || peer >= c->world) return ND_B200_EINVAL;
+  if (peer == c->rank) return ND_B200_OK;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof h);
+  COMM_TRY(c, cudaSetDevice(c->device));
+  void* q = nullptr;
+  COMM_TRY(c, cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess));
+  c->base[peer] = static_cast<unsigned char*>(q);
+  return ND_B200_OK;
+}
+
+int nd_b200_comm_status(nd_b200_comm* c, int32_t* timed_out) {
+  if (!c || !timed_out) return ND_B200_EINVAL;
+  int v = 0;
+  COMM_TRY(c, cudaSetDevice(c->device));
+  COMM_TRY(c, cudaMemcpy(&v, c->d_timeout, sizeof v, cudaMemcpyDeviceToHost));
+  *timed_out = v;
+  return ND_B200_OK;
+}
+
+const char* nd_b200_comm_last_error(const nd_b200_comm* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+void nd_b200_comm_destroy(nd_b200_comm* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (int r = 0; r < c->world; ++r) {
+    if (!c->base[r]) continue;
+    if (r == c->rank) cudaFree(c->base[r]); else cudaIpcCloseMemHandle(c->base[r]);
+  }
+  cudaFree(c->d_done); cudaFree(c->d_timeout);
+  delete c;
+}
+
+int nd_b200_rhs_exchange(nd_b200_engine* e, nd_b200_comm* c, double* du, const double* u, const double* p, double t,
+                         void* stream) {
+  if (int rc = check_call(e, du, u, p)) return rc;
+  if (!c) return fail(e, ND_B200_EINVAL, "nd_b200_rhs_exchange: comm is NULL");
+  if (!e->gather_from_u || e->split) return fail(e, ND_B200_EUNSUPPORTED, "nd_b200_rhs_exchange needs StateMask vertices and the fused kernel");
+  if (c->nstates != e->lastidx_dynamic) return fail(e, ND_B200_EINVAL, "comm was created for %lld states, the network has %lld", c->nstates, e->lastidx_dynamic);
+  if (e->own_segs.size() > (size_t)HALO_MAX_SEGS) return fail(e, ND_B200_EUNSUPPORTED, "more than %d owned state ranges", HALO_MAX_SEGS);
+  for (int r = 0; r < c->world; ++r)
+    if (!c->base[r]) return fail(e, ND_B200_EINVAL, "peer %d has not been opened", r);
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned long long seq = ++c->seq;
+  const int parity = (int)(seq & 1ull);
+  HaloParams H;
+  memset(&H, 0, sizeof H);
+  for (int r = 0; r < c->world; ++r) { H.replica[r] = c->replica(r, parity); H.flags[r] = c->flags(r); }
+  long long total = 0;
+  H.nsegs = (int)e->own_segs.size();
+  for (int s = 0; s < H.nsegs; ++s) { H.seg_start[s] = e->own_segs[(size_t)s].first; H.seg_len[s] = e->own_segs[(size_t)s].second; total += H.seg_len[s]; }
+  H.world = c->world; H.rank = c->rank; H.seq = seq; H.src = u; H.done_counter = c->d_done;
+  const int grid = (int)std::max<long long>(1, std::min<long long>(148, (total / 2 + 255) / 256));
+  halo_publish_kernel<<<grid, 256, 0, st>>>(H);
+  CUDA_TRY(e, cudaGetLastError());
+  e->launches++;
+  WaitSpec w{c->replica(c->rank, parity), c->flags(c->rank), seq, c->world, c->d_timeout};
+  return rhs_impl(e, du, u, p, t, st, MODE_DU, nullptr, &w);
+}
 
 }  // extern "C"

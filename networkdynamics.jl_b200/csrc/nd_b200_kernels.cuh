@@ -64,6 +64,12 @@ struct KParams {
   // split mode (edge pass + row pass): per entry the position of its value in the edge-output buffer
   const int* __restrict__ oidx;
   const double* __restrict__ oedge;    // edge part of the reference's output buffer `o` (src range, dst range per edge)
+  // multi-GPU: the gather source is this rank's replica of the state vector, filled by the peers' publish kernels
+  // through NVLink; the kernel waits until every peer's arrival flag has reached wait_seq (see halo_publish_kernel)
+  const unsigned long long* wait_flags;
+  unsigned long long wait_seq;
+  int wait_world;
+  int* wait_timeout;                   // set to 1 if a flag did not arrive within the spin budget
 };
 
 // parameters of the edge pass (split mode)
@@ -236,6 +242,91 @@ __device__ __forceinline__ void load_vertex_state(const KParams& P, const VBDev&
 // ------------------------------------------------------------------------------------------------
 // fused gather -> edge -> ordered row reduce -> vertex kernel
 // ------------------------------------------------------------------------------------------------
+
+// ------------------------------------------------------------------------------------------------
+// multi-GPU halo exchange over NVLink peer memory (no NCCL on the data path)
+//
+// Every rank owns contiguous state ranges.  halo_publish_kernel copies the owner's ranges into the state replica of
+// EVERY rank (its own and, through peer-mapped pointers, all others: plain st.global over NVLink 5 / NVSwitch), then
+// -- after a system-scope fence -- the last block to finish stores the sequence number into slot [owner] of every
+// rank's arrival-flag array.  The consuming RHS kernel (next in the peer's stream) spins on its LOCAL flag array until
+// all `world` slots have reached the sequence number, then gathers from its LOCAL replica.  Replicas are double-buffered
+// by sequence parity, which is enough: a rank can only publish sequence s+2 after it has consumed every peer's s+1,
+// which those peers published after finishing their own reads of s.
+// ------------------------------------------------------------------------------------------------
+constexpr int HALO_MAX_WORLD = 8;
+constexpr int HALO_MAX_SEGS = 8;
+struct HaloParams {
+  double* replica[HALO_MAX_WORLD];                 // [rank] -> that rank's replica (this sequence's parity)
+  unsigned long long* flags[HALO_MAX_WORLD];       // [rank] -> that rank's arrival-flag array
+  long long seg_start[HALO_MAX_SEGS], seg_len[HALO_MAX_SEGS];
+  int nsegs, world, rank;
+  unsigned long long seq;
+  const double* src;                                // the owner's state vector (full layout, owned ranges valid)
+  unsigned int* done_counter;                       // local: blocks finished (reset by the last block)
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(256) halo_publish_kernel(const __grid_constant__ HaloParams H) {
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nthreads = (long long)gridDim.x * blockDim.x;
+  for (int s = 0; s < H.nsegs; ++s) {
+    const long long a = H.seg_start[s], n = H.seg_len[s];
+    // 16-byte body when the range start is even (8-byte elements), scalar head/tail otherwise
+    const long long head = (a & 1) ? 1 : 0;
+    const long long nvec = (n - head) / 2;
+    if (tid < head) {
+      const double v = H.src[a];
+      for (int r = 0; r < H.world; ++r) H.replica[r][a] = v;
+    }
+    for (long long i = tid; i < nvec; i += nthreads) {
+      const long long j = a + head + 2 * i;
+      const double2 v = *reinterpret_cast<const double2*>(H.src + j);
+      for (int r = 0; r < H.world; ++r) *reinterpret_cast<double2*>(H.replica[r] + j) = v;
+    }
+    if (tid == 0 && head + 2 * nvec < n) {
+      const long long j = a + n - 1;
+      const double v = H.src[j];
+      for (int r = 0; r < H.world; ++r) H.replica[r][j] = v;
+    }
+  }
+  // make this block's peer stores visible system-wide, then count the block as done
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(H.done_counter, 1u);
+    if (prev == gridDim.x - 1) {
+      *H.done_counter = 0;
+      __threadfence_system();
+      for (int r = 0; r < H.world; ++r) st_release_sys(H.flags[r] + H.rank, H.seq);
+    }
+  }
+}
+
+// called at the top of the consuming kernels
+__device__ __forceinline__ void halo_wait(const KParams& P) {
+  if (P.wait_flags == nullptr) return;
+  if (threadIdx.x < P.wait_world) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(P.wait_flags + threadIdx.x) < P.wait_seq) {
+      if (clock64() - t0 > 4000000000LL) {   // ~2 s: a peer died; do not hang the GPU
+        *P.wait_timeout = 1;
+        break;
+      }
+      __nanosleep(100);
+    }
+  }
+  __syncthreads();
+}
+
 // Occupancy is the lever for this kernel (it is bound by the L2 sector bandwidth of the random gathers and hides
 // latency with many independent blocks), so registers are capped through the min-blocks launch bound.
 // Measured on B200 (profiles/r01_tuning.md): 64 resident warps/SM (32 registers) is best for the arithmetic-free
@@ -261,6 +352,7 @@ __global__ void __launch_bounds__(BLOCK, (fused_warps_per_sm(EK) * 32) / BLOCK) 
   const int ne = is_long ? d.z : (d.w & 0xFFFF);
   const VBDev B = P.vb[(d.w >> 25) & 0x3F];
   const int coupling0 = P.n_eb > 0 ? P.eb[0].coupling : 0;
+  halo_wait(P);   // multi-GPU only: peers' states have landed in the local replica
 
   // ---------------- long row: whole block reduces one row with a fixed-shape tree -----------------
   if (is_long) {

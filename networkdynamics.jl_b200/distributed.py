@@ -115,7 +115,11 @@ class PartitionedNetwork:
     evaluate the owned rows into `du` (only the owned entries of `du` are written)."""
 
     def __init__(self, g, vertexm, edgem, *, rank: int, world: int, group=None, device=None,
-                 long_row_threshold: int = 0):
+                 long_row_threshold: int = 0, exchange: str = "auto"):
+        """exchange: "p2p"  -- states are pushed into every rank's replica with NVLink peer stores by the engine's
+        publish kernel and the RHS kernel waits on arrival flags (nd_b200_rhs_exchange; no NCCL on the data path);
+        "nccl" -- torch.distributed collectives on the caller's `u`; "auto" -- p2p when the network allows it
+        (all vertices StateMask) and CUDA IPC works, else nccl."""
         # host tables first (no device work) to compute the partition
         probe = Network(g, vertexm, edgem, execution=B200Execution(), aggregator=lambda im, eb: None)
         self.rank, self.world, self.group = rank, world, group
@@ -125,6 +129,68 @@ class PartitionedNetwork:
         self.nw = Network(g, vertexm, edgem, execution=B200Execution(),
                           aggregator=B200Aggregator("+", device=device, row_range=self.row_ranges[rank],
                                                     long_row_threshold=long_row_threshold, keep_tables=False))
+        self.comm = None
+        self.exchange_kind = "nccl"
+        if exchange in ("p2p", "auto") and world > 1:
+            try:
+                self._setup_p2p()
+                self.exchange_kind = "p2p"
+            except Exception:
+                if exchange == "p2p":
+                    raise
+
+    # -- NVLink peer-memory exchange ----------------------------------------------------------------------------
+    def _setup_p2p(self):
+        import ctypes as C
+        import torch.distributed as dist
+        from . import _cabi
+        L = _cabi.lib()
+        if not self.nw.engine_sizes()["gather_from_u"]:
+            raise RuntimeError("p2p exchange needs StateMask vertices (the gather source must be the state vector)")
+        h = C.c_void_p()
+        dev = self.nw.layer.aggregator.device
+        rc = L.nd_b200_comm_create(dev, self.rank, self.world, self.nw.dim(), C.byref(h))
+        ok = rc == 0
+        handle = C.create_string_buffer(_cabi.IPC_HANDLE_BYTES)
+        if ok:
+            ok = L.nd_b200_comm_export(h, handle) == 0
+        # every rank must take the same branch: agree on success before mapping anything
+        flags = [None] * self.world
+        dist.all_gather_object(flags, (bool(ok), handle.raw), group=self.group)
+        if not all(f[0] for f in flags):
+            if h:
+                L.nd_b200_comm_destroy(h)
+            raise RuntimeError("nd_b200_comm_create failed on some rank: " + L.nd_b200_comm_last_error(None).decode())
+        opened = all(L.nd_b200_comm_open_peer(h, r, flags[r][1]) == 0 for r in range(self.world))
+        res = [None] * self.world
+        dist.all_gather_object(res, bool(opened), group=self.group)
+        if not all(res):
+            msg = L.nd_b200_comm_last_error(h).decode()
+            L.nd_b200_comm_destroy(h)
+            raise RuntimeError("CUDA IPC mapping of a peer replica failed: " + msg)
+        self.comm = h
+        dist.barrier(group=self.group)
+
+    def comm_timed_out(self) -> bool:
+        import ctypes as C
+        from . import _cabi
+        if self.comm is None:
+            return False
+        v = C.c_int32(0)
+        _cabi.lib().nd_b200_comm_status(self.comm, C.byref(v))
+        return bool(v.value)
+
+    def close(self):
+        """collective: all ranks must call it (peers' mappings are closed before the owners free their replicas)"""
+        import torch.distributed as dist
+        from . import _cabi
+        if self.comm is not None:
+            import torch
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)
+            _cabi.lib().nd_b200_comm_destroy(self.comm)
+            self.comm = None
+            dist.barrier(group=self.group)
 
     def dim(self):
         return self.nw.dim()
@@ -139,7 +205,19 @@ class PartitionedNetwork:
     def exchange(self, u):
         exchange_states(u, self.segments, self.group)
 
-    def rhs(self, du, u, p, t, *, exchange: bool = True):
+    def rhs(self, du, u, p, t, *, exchange: bool = True, stream=None):
+        """`nw(du,u,p,t)` for the owned rows; only the owned states of `u` need to be valid on entry"""
+        if exchange and self.comm is not None:
+            from .network import _addr, _stream_handle
+            from . import _cabi
+            a_du, _, n_du = _addr(du)
+            a_u, _, n_u = _addr(u)
+            a_p, _, n_p = _addr(p)
+            self.nw._check_sizes(n_du, n_u, n_p, p is not None)
+            rc = _cabi.lib().nd_b200_rhs_exchange(self.nw.handle, self.comm, a_du, a_u, a_p, float(t), _stream_handle(stream))
+            if rc:
+                self.nw._fail(rc)
+            return
         if exchange:
             self.exchange(u)
         self.nw(du, u, p, t)

@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, exchange):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -26,7 +26,8 @@ def _worker(rank, world, port, out_dir):
     half = np.array([0] * (n // 2) + [1] * (n // 2))
     vm = ([L.kuramoto_first(), L.kuramoto_second()], np.random.default_rng(4).permutation(half))
     g = nd.barabasi_albert(n, 4, seed=2)
-    pn = PartitionedNetwork(g, vm, L.kuramoto_edge(), rank=rank, world=world)
+    pn = PartitionedNetwork(g, vm, L.kuramoto_edge(), rank=rank, world=world, exchange=exchange)
+    assert pn.exchange_kind == exchange
     u0 = np.random.default_rng(1).random(pn.dim())
     p = condition_params(pn.nw, np.random.default_rng(2).random(pn.pdim()))
     u = torch.full((pn.dim(),), float("nan"), dtype=torch.float64, device="cuda")
@@ -41,6 +42,8 @@ def _worker(rank, world, port, out_dir):
         pn.rk4_step(u, pd, s * 1e-3, 1e-3, work)
     pn.exchange(u)
     torch.cuda.synchronize()
+    assert not pn.comm_timed_out()
+    pn.close()
     if rank == 0:
         np.save(os.path.join(out_dir, "du.npy"), du.cpu().numpy())
         np.save(os.path.join(out_dir, "u.npy"), u.cpu().numpy())
@@ -48,14 +51,15 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-def test_two_gpu_partitioned_rhs(nd, cuda, tmp_path):
+@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
+def test_two_gpu_partitioned_rhs(nd, cuda, tmp_path, exchange):
     torch = cuda
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     from helpers import condition_params, floored_rel_err, null_aggregator, oracle_network
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
-    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, str(tmp_path), exchange), nprocs=2, join=True)
     L = nd.Lib
     n = 20000
     half = np.array([0] * (n // 2) + [1] * (n // 2))
