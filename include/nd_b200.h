@@ -95,6 +95,8 @@ typedef struct nd_b200_desc {
 } nd_b200_desc;
 
 #define ND_B200_FLAG_NO_EXPORT 1  /* do not keep host copies of the CSR for nd_b200_export_tables */
+#define ND_B200_FLAG_HOST_ONLY 2  /* build every table on the host and stop: no CUDA call is made, the engine can only
+                                     export its tables (layout tests on machines without a GPU) */
 
 typedef struct nd_b200_engine nd_b200_engine;
 
@@ -133,6 +135,14 @@ int nd_b200_export_sizes(const nd_b200_engine*, int64_t sizes[8]);
  * edge's dst, 1: this row is the edge's src).  Entries of a row are in accumulation order. */
 int nd_b200_export_tables(const nd_b200_engine*, int64_t* rowptr, int64_t* nbr_vertex, int64_t* edge_id,
                           int32_t* side);
+
+/* The jagged device layout of the default kernel (rhs_jag_kernel), ND_B200_FLAG_HOST_ONLY engines only.
+ * sizes[0]=slices (-1: engine uses a tile kernel) [1]=rows reduced by a whole block [2]=row split width [3]=entries.
+ * slices[4*s..] = {entry base, first row, vertex batch, max parts}; lanes[32*s+l] = len | rowrel<<6 | head<<11 |
+ * valid<<12; longs[4*k..] = {entry base, row, entries, vertex batch}; order[k] = CSR entry (as exported by
+ * nd_b200_export_tables) stored at jagged position k. */
+int nd_b200_export_jag_sizes(const nd_b200_engine*, int64_t sizes[4]);
+int nd_b200_export_jag(const nd_b200_engine*, int32_t* slices, uint16_t* lanes, int32_t* longs, int32_t* order);
 
 /* kernel launches issued by this engine since creation (bench.py's gpu_launches) */
 int64_t nd_b200_launch_count(const nd_b200_engine*);

@@ -23,6 +23,7 @@ V_DIFFUSION, V_KURAMOTO_FIRST, V_KURAMOTO_SECOND, V_KURAMOTO_SECOND_BENCH, V_SWI
 E_DIFFUSION, E_DIFFUSION_NOP, E_KURAMOTO, E_LINE_DQ = range(4)
 ANTISYMMETRIC, SYMMETRIC, DIRECTED = range(3)
 FLAG_NO_EXPORT = 1
+FLAG_HOST_ONLY = 2
 
 i64p = C.POINTER(C.c_int64)
 i32p = C.POINTER(C.c_int32)
@@ -55,7 +56,7 @@ EXPORTED_SYMBOLS = [
     "nd_b200_rhs_host", "nd_b200_get_buffers", "nd_b200_rk4", "nd_b200_export_sizes", "nd_b200_export_tables",
     "nd_b200_launch_count", "nd_b200_set_timing", "nd_b200_timings", "nd_b200_host_alloc", "nd_b200_host_free",
     "nd_b200_comm_create", "nd_b200_comm_export", "nd_b200_comm_open_peer", "nd_b200_rhs_exchange", "nd_b200_comm_status",
-    "nd_b200_comm_last_error", "nd_b200_comm_destroy",
+    "nd_b200_comm_last_error", "nd_b200_comm_destroy", "nd_b200_export_jag_sizes", "nd_b200_export_jag",
 ]
 IPC_HANDLE_BYTES = 64
 
@@ -117,6 +118,10 @@ def lib():
     L.nd_b200_export_sizes.argtypes = [C.c_void_p, i64p]
     L.nd_b200_export_tables.restype = C.c_int
     L.nd_b200_export_tables.argtypes = [C.c_void_p, i64p, i64p, i64p, i32p]
+    L.nd_b200_export_jag_sizes.restype = C.c_int
+    L.nd_b200_export_jag_sizes.argtypes = [C.c_void_p, i64p]
+    L.nd_b200_export_jag.restype = C.c_int
+    L.nd_b200_export_jag.argtypes = [C.c_void_p, i32p, C.POINTER(C.c_uint16), i32p, i32p]
     L.nd_b200_launch_count.restype = C.c_int64
     L.nd_b200_launch_count.argtypes = [C.c_void_p]
     L.nd_b200_set_timing.restype = C.c_int

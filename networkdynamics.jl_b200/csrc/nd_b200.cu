@@ -63,6 +63,18 @@ struct nd_b200_engine {
   int *d_es = nullptr, *d_et = nullptr, *d_eepar = nullptr, *d_eooff = nullptr, *d_oidx = nullptr;
   uint8_t* d_eebid = nullptr;
   double* d_oedge = nullptr;
+  // jagged layout (ND_B200_KERNEL=jag): warp slices, see rhs_jag_kernel
+  int jag = 0, jag_u = 4, jag_wps = 0, jsplit = 32;
+  int nslices = 0, n_jag_blocks = 0, n_jlong = 0;
+  int4 *d_jslices = nullptr, *d_jlong = nullptr;
+  uint16_t* d_jlanes = nullptr;
+  int* d_jnbr = nullptr;
+  int2* d_jent = nullptr;
+  uint8_t* d_jebid = nullptr;
+  bool host_only = false;     // ND_B200_FLAG_HOST_ONLY: tables built, nothing uploaded (layout tests without a GPU)
+  std::vector<int4> h_jslices, h_jlong;
+  std::vector<uint16_t> h_jlanes;
+  std::vector<int> h_jorder;  // jagged position -> CSR entry
   // get_buffers support (lazy)
   std::vector<std::vector<int>> h_esrc_off, h_edst_off;   // per edge batch, gather offsets
   std::vector<int*> d_esrc_off, d_edst_off;
@@ -156,6 +168,8 @@ void fill_params(const nd_b200_engine* e, KParams& P) {
   P.vb = e->d_vb; P.eb = e->d_eb; P.n_vb = (int)e->hvb.size(); P.n_eb = (int)e->heb.size();
   P.row_base = (int)e->row_begin; P.long_thr = e->long_thr; P.gather_from_u = e->gather_from_u;
   P.tiles = e->d_tiles; P.ntiles = e->ntiles; P.oidx = e->d_oidx; P.oedge = e->d_oedge;
+  P.jslices = e->d_jslices; P.jlanes = e->d_jlanes; P.jnbr = e->d_jnbr; P.jent = e->d_jent; P.jebid = e->d_jebid;
+  P.jlong = e->d_jlong; P.nslices = e->nslices; P.n_jag_blocks = e->n_jag_blocks;
 }
 
 // ---- split mode launches --------------------------------------------------------------------------------
@@ -204,7 +218,35 @@ cudaError_t launch_shape(const nd_b200_engine* e, const KParams& P, cudaStream_t
   return cudaGetLastError();
 }
 
+// ---- jagged kernel launches ------------------------------------------------------------------------------
+template <int VD, int ED, int EK, int PE, int U>
+cudaError_t launch_jag_u(const nd_b200_engine* e, const KParams& P, cudaStream_t st) {
+  constexpr int BLOCK = 128;
+  const int grid = e->n_jag_blocks + e->n_jlong;
+  if (grid == 0) return cudaSuccess;
+  const int wps = e->jag_wps > 0 ? e->jag_wps : jag_warps_per_sm_default(EK);
+  if (wps >= 64) rhs_jag_kernel<VD, ED, EK, PE, BLOCK, U, 64><<<grid, BLOCK, 0, st>>>(P);
+  else if (wps >= 48) rhs_jag_kernel<VD, ED, EK, PE, BLOCK, U, 48><<<grid, BLOCK, 0, st>>>(P);
+  else rhs_jag_kernel<VD, ED, EK, PE, BLOCK, U, 32><<<grid, BLOCK, 0, st>>>(P);
+  return cudaGetLastError();
+}
+template <int VD, int ED, int EK, int PE>
+cudaError_t launch_jag_t(const nd_b200_engine* e, const KParams& P, cudaStream_t st) {
+  return e->jag_u >= 4 ? launch_jag_u<VD, ED, EK, PE, 4>(e, P, st) : launch_jag_u<VD, ED, EK, PE, 2>(e, P, st);
+}
+cudaError_t launch_jag(nd_b200_engine* e, const KParams& P, cudaStream_t st) {
+  e->launches += (e->n_jag_blocks + e->n_jlong > 0);
+  if (e->vdepth == 2) return launch_jag_t<2, 2, ND_B200_E_LINE_DQ, 3>(e, P, st);
+  switch (e->ek) {
+    case ND_B200_E_DIFFUSION: return launch_jag_t<1, 1, ND_B200_E_DIFFUSION, 1>(e, P, st);
+    case ND_B200_E_DIFFUSION_NOP: return launch_jag_t<1, 1, ND_B200_E_DIFFUSION_NOP, 0>(e, P, st);
+    case ND_B200_E_KURAMOTO: return launch_jag_t<1, 1, ND_B200_E_KURAMOTO, 1>(e, P, st);
+    default: return launch_jag_t<1, 1, EK_GENERIC, 1>(e, P, st);
+  }
+}
+
 cudaError_t launch_fused(nd_b200_engine* e, const KParams& P, cudaStream_t st) {
+  if (e->jag) return launch_jag(e, P, st);
   if (e->split) {
     // edge pass (PASS 5) then row pass (aggregate + PASS 6); P.gsrc is the gather source of this evaluation
     cudaError_t c1 = launch_edge_pass(e, P.gsrc, P.p, st);
@@ -485,7 +527,106 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
   std::vector<EBDev> deb;
   for (const HostEB& h : e->heb) deb.push_back(EBDev{h.kind, h.coupling, h.pdim});
 
+  // ---- jagged layout: 32-lane slices, column-major compacted entries (rhs_jag_kernel) ------------------------
+  // default evaluation mode; ND_B200_KERNEL=fused|split select the tile kernels.  A strictly sequential
+  // long_row_threshold beyond what one lane can hold (63 entries) needs the tile kernel.
+  e->jag = 1;
+  if (const char* s = getenv("ND_B200_KERNEL")) e->jag = !strcmp(s, "jag") ? 1 : ((!strcmp(s, "fused") || !strcmp(s, "split") || !strcmp(s, "v1")) ? 0 : 1);
+  if (e->split) e->jag = 0;
+  if (d->long_row_threshold > 63 * 32) e->jag = 0;
+  std::vector<int4> jslices, jlong;
+  std::vector<uint16_t> jlanes;
+  std::vector<int> jnbr;
+  std::vector<int2> jent;
+  std::vector<uint8_t> jebid;
+  const bool jag_pe = any_epar || generic_edges;   // kernels instantiated with PE > 0 read {nbr, epar} pairs
+  if (e->jag) {
+    e->jsplit = 32;
+    if (const char* s = getenv("ND_B200_JAG_SPLIT")) e->jsplit = std::min(63, std::max(1, atoi(s)));
+    if (const char* s = getenv("ND_B200_JAG_U")) e->jag_u = atoi(s);
+    if (const char* s = getenv("ND_B200_JAG_WPS")) e->jag_wps = atoi(s);
+    // rows longer than this are reduced by a whole block: explicit threshold if the caller gave one, else what a
+    // slice can hold
+    const long long block_thr = d->long_row_threshold > 0 ? std::min<long long>(d->long_row_threshold, 32LL * e->jsplit) : 32LL * e->jsplit;
+    std::vector<int> order;
+    order.reserve((size_t)e->nentries);
+    struct Lane { int rowrel, len, head; long long start; };
+    std::vector<Lane> lanes;
+    std::vector<std::pair<long long, int>> long_rows;   // (row, batch)
+    for (size_t b = 0; b < e->hvb.size(); ++b) {
+      const HostVB& h = e->hvb[b];
+      const long long lo = std::max<long long>(h.row0, e->row_begin), hi = std::min<long long>(h.row0 + h.count, e->row_end);
+      long long row0 = -1;
+      int maxparts = 1;
+      auto flush = [&]() {
+        if (lanes.empty()) return;
+        int maxlen = 0;
+        for (const Lane& L : lanes) maxlen = std::max(maxlen, L.len);
+        const int e0 = (int)order.size();
+        for (int j = 0; j < maxlen; ++j)
+          for (const Lane& L : lanes)
+            if (L.len > j) order.push_back((int)(L.start + j));
+        jslices.push_back(make_int4(e0, (int)row0, (int)b, maxparts));
+        for (int l = 0; l < 32; ++l) {
+          uint16_t v = 0;
+          if (l < (int)lanes.size()) v = (uint16_t)(lanes[(size_t)l].len | (lanes[(size_t)l].rowrel << 6) | (lanes[(size_t)l].head << 11) | (1 << 12));
+          jlanes.push_back(v);
+        }
+        lanes.clear(); row0 = -1; maxparts = 1;
+      };
+      for (long long r = lo; r < hi; ++r) {
+        const long long a = cnt[(size_t)(r - e->row_begin)], deg = cnt[(size_t)(r - e->row_begin) + 1] - a;
+        const int nparts = (int)std::max<long long>(1, (deg + e->jsplit - 1) / e->jsplit);
+        if (deg > block_thr || nparts > 32) { long_rows.push_back({r, (int)b}); continue; }
+        if ((int)lanes.size() + nparts > 32 || (row0 >= 0 && r - row0 >= 32)) flush();
+        if (lanes.empty()) row0 = r;
+        for (int k = 0; k < nparts; ++k) {
+          const long long len = std::min<long long>(e->jsplit, deg - (long long)k * e->jsplit);
+          lanes.push_back(Lane{(int)(r - row0), (int)std::max<long long>(len, 0), k == 0, a + (long long)k * e->jsplit});
+        }
+        maxparts = std::max(maxparts, nparts);
+      }
+      flush();
+    }
+    for (const auto& lr : long_rows) {
+      const long long a = cnt[(size_t)(lr.first - e->row_begin)], deg = cnt[(size_t)(lr.first - e->row_begin) + 1] - a;
+      jlong.push_back(make_int4((int)order.size(), (int)lr.first, (int)deg, lr.second));
+      for (long long j = 0; j < deg; ++j) order.push_back((int)(a + j));
+    }
+    if ((long long)order.size() != e->nentries) return fail(e, ND_B200_EINVAL, "internal: jagged layout holds %lld of %lld entries", (long long)order.size(), e->nentries);
+    if (jag_pe) {
+      jent.resize(std::max<size_t>(order.size(), 1));
+      for (size_t k = 0; k < order.size(); ++k) jent[k] = make_int2(h_nbr[(size_t)order[k]], any_epar ? h_epar[(size_t)order[k]] : 0);
+    } else {
+      jnbr.resize(std::max<size_t>(order.size(), 1));
+      for (size_t k = 0; k < order.size(); ++k) jnbr[k] = h_nbr[(size_t)order[k]];
+    }
+    if (!h_ebid.empty()) {
+      jebid.resize(std::max<size_t>(order.size(), 1));
+      for (size_t k = 0; k < order.size(); ++k) jebid[k] = h_ebid[(size_t)order[k]];
+    }
+    e->host_only = (d->flags & ND_B200_FLAG_HOST_ONLY) != 0;
+    if (e->host_only) { e->h_jslices = jslices; e->h_jlong = jlong; e->h_jlanes = jlanes; e->h_jorder = order; }
+    e->nslices = (int)jslices.size();
+    e->n_jag_blocks = (e->nslices + 3) / 4;   // BLOCK = 128: four slices per thread block
+    e->n_jlong = (int)jlong.size();
+    e->nblocks = e->n_jag_blocks + e->n_jlong;
+    e->n_long = e->n_jlong;
+  }
+
+  if (d->flags & ND_B200_FLAG_HOST_ONLY) { e->host_only = true; return ND_B200_OK; }
   CUDA_TRY(e, cudaSetDevice(e->device));
+  if (e->jag) {
+    if (upload(e, &e->d_vb, dvb) || upload(e, &e->d_eb, deb) || upload(e, &e->d_jslices, jslices) || upload(e, &e->d_jlanes, jlanes) ||
+        upload(e, &e->d_jlong, jlong))
+      return ND_B200_ECUDA;
+    if (jag_pe ? upload(e, &e->d_jent, jent) : upload(e, &e->d_jnbr, jnbr)) return ND_B200_ECUDA;
+    if (!jebid.empty() && upload(e, &e->d_jebid, jebid)) return ND_B200_ECUDA;
+    if (!e->gather_from_u) {
+      for (int k = 0; k < 2; ++k) CUDA_TRY(e, cudaMalloc((void**)&e->d_vout[k], sizeof(double) * (size_t)(e->nrows_total * e->vdepth)));
+    }
+    return ND_B200_OK;
+  }
   if (upload(e, &e->d_rowptr, h_rowptr) || upload(e, &e->d_nbr, h_nbr) || upload(e, &e->d_blk_row, blk_row) ||
       upload(e, &e->d_vb, dvb) || upload(e, &e->d_eb, deb))
     return ND_B200_ECUDA;
@@ -508,6 +649,7 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
 
 int check_call(nd_b200_engine* e, const void* du, const void* u, const void* p) {
   if (!e) return ND_B200_EINVAL;
+  if (e->host_only) return fail(e, ND_B200_EUNSUPPORTED, "engine was created with ND_B200_FLAG_HOST_ONLY (tables only, no device)");
   if (!du || !u) return fail(e, ND_B200_EINVAL, "du or u is NULL (expected size %lld)", e->lastidx_dynamic);
   if (e->lastidx_p > 0 && !p) return fail(e, ND_B200_EINVAL, "p is NULL but the network has %lld parameters", e->lastidx_p);
   return 0;
@@ -592,12 +734,14 @@ int nd_b200_create(const nd_b200_desc* desc, nd_b200_engine** out) {
 
 void nd_b200_destroy(nd_b200_engine* e) {
   if (!e) return;
+  if (e->host_only) { delete e; return; }
   cudaSetDevice(e->device);
   destroy_graph(e);
   cudaFree(e->d_rowptr); cudaFree(e->d_nbr); cudaFree(e->d_epar); cudaFree(e->d_blk_row); cudaFree(e->d_ebid);
   cudaFree(e->d_vb); cudaFree(e->d_eb); cudaFree(e->d_vout[0]); cudaFree(e->d_vout[1]);
   cudaFree(e->d_tiles); cudaFree(e->d_oidx); cudaFree(e->d_es); cudaFree(e->d_et); cudaFree(e->d_eepar); cudaFree(e->d_eooff);
   cudaFree(e->d_eebid); cudaFree(e->d_oedge);
+  cudaFree(e->d_jslices); cudaFree(e->d_jlanes); cudaFree(e->d_jnbr); cudaFree(e->d_jent); cudaFree(e->d_jebid); cudaFree(e->d_jlong);
   for (int* q : e->d_esrc_off) cudaFree(q);
   for (int* q : e->d_edst_off) cudaFree(q);
   cudaFree(e->d_tmpA); cudaFree(e->d_tmpB); cudaFree(e->d_ksum);
@@ -732,6 +876,22 @@ int nd_b200_export_tables(const nd_b200_engine* e, int64_t* rowptr, int64_t* nbr
   for (size_t j = 0; j < (size_t)e->nentries; ++j) {
     nbr_vertex[j] = e->h_nbr_vid[j]; edge_id[j] = e->h_eid[j]; side[j] = e->h_side[j];
   }
+  return ND_B200_OK;
+}
+
+int nd_b200_export_jag_sizes(const nd_b200_engine* e, int64_t sizes[4]) {
+  if (!e || !sizes) return ND_B200_EINVAL;
+  sizes[0] = e->jag ? (int64_t)e->nslices : -1; sizes[1] = e->n_jlong; sizes[2] = e->jsplit; sizes[3] = (int64_t)e->h_jorder.size();
+  return ND_B200_OK;
+}
+
+int nd_b200_export_jag(const nd_b200_engine* e, int32_t* slices, uint16_t* lanes, int32_t* longs, int32_t* order) {
+  if (!e) return ND_B200_EINVAL;
+  if (!e->jag || !e->host_only) return fail(const_cast<nd_b200_engine*>(e), ND_B200_EUNSUPPORTED, "jagged tables are kept only by ND_B200_FLAG_HOST_ONLY engines in jag mode");
+  for (size_t k = 0; k < e->h_jslices.size(); ++k) { slices[4 * k] = e->h_jslices[k].x; slices[4 * k + 1] = e->h_jslices[k].y; slices[4 * k + 2] = e->h_jslices[k].z; slices[4 * k + 3] = e->h_jslices[k].w; }
+  for (size_t k = 0; k < e->h_jlanes.size(); ++k) lanes[k] = e->h_jlanes[k];
+  for (size_t k = 0; k < e->h_jlong.size(); ++k) { longs[4 * k] = e->h_jlong[k].x; longs[4 * k + 1] = e->h_jlong[k].y; longs[4 * k + 2] = e->h_jlong[k].z; longs[4 * k + 3] = e->h_jlong[k].w; }
+  for (size_t k = 0; k < e->h_jorder.size(); ++k) order[k] = e->h_jorder[k];
   return ND_B200_OK;
 }
 

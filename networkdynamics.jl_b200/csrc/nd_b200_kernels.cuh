@@ -70,6 +70,14 @@ struct KParams {
   unsigned long long wait_seq;
   int wait_world;
   int* wait_timeout;                   // set to 1 if a flag did not arrive within the spin budget
+  // jagged ("warp-sliced") layout, see rhs_jag_kernel
+  const int4* __restrict__ jslices;    // per 32-lane slice {entry base, first row, vertex batch, max parts of a split row}
+  const uint16_t* __restrict__ jlanes; // per lane: len | rowrel<<6 | head<<11 | valid<<12
+  const int* __restrict__ jnbr;        // per entry, slice-local column-major compacted order (PE == 0 kernels)
+  const int2* __restrict__ jent;       // per entry {nbr, epar} (PE > 0 kernels)
+  const uint8_t* __restrict__ jebid;   // per entry edge batch id (EK_GENERIC)
+  const int4* __restrict__ jlong;      // rows reduced by a whole block {entry base, row, entries, vertex batch}
+  int nslices, n_jag_blocks;
 };
 
 // parameters of the edge pass (split mode)
@@ -687,6 +695,208 @@ __global__ void __launch_bounds__(BLOCK, 2048 / BLOCK) row_pass_kernel(const __g
     for (int q = 0; q < VD; ++q) self[q] = P.gather_from_u ? 0.0 : P.gsrc[(long long)(r0 + tid) * VD + q];
     load_vertex_state(P, B, r0 + tid, v);
     vertex_phase<VD, ED>(P, B, r0 + tid, acc, self, v, P.p + B.p0 + (long long)(r0 + tid - B.row0) * B.pdim);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// jagged ("warp-sliced") fused kernel: gather -> edge -> ordered row sum -> vertex model with NO shared memory
+// and NO block barrier on the regular path.
+//
+// Why: ncu on rhs_fused_kernel (profiles/r01b_fused_cfg2_ncu_summary.txt) shows the L1TEX data pipe as the busiest
+// unit (78-84 %), one third of its wavefronts being the shared-memory round trip of the edge values (entry -> row map,
+// value store, conflict-prone per-row reads) -- traffic that exists only to turn an entry-parallel gather into a
+// row-ordered sum.  Here one LANE owns one row (thread-per-row, so the sum is a register accumulated in the reference's
+// sequential order, src/aggregators.jl:140-151) and the index stream is laid out so that the lanes' loads still
+// coalesce: a slice = 32 lanes; its entries are stored column-major and COMPACTED -- column j holds the j-th entry of
+// every lane that has more than j entries, in lane order.  A lane finds its slot with one ballot + popc per column.
+// No padding is stored, rows keep their natural order (coalesced u / du / vertex parameters).
+//
+// Rows with more than `jsplit` (<= 63, default 32) entries are cut into consecutive parts of jsplit entries that sit
+// on consecutive lanes of the same slice; the head lane adds the parts' sums in order with shuffles (deterministic;
+// differs from the sequential sum only in association, like the block tree of the long rows).  Rows that would need
+// more than 32 lanes go to the whole-block path (same code as rhs_fused_kernel's long rows).
+// ------------------------------------------------------------------------------------------------
+constexpr int jag_warps_per_sm_default(int ek) {
+  return (ek == ND_B200_E_DIFFUSION || ek == ND_B200_E_DIFFUSION_NOP) ? 64 : 48;
+}
+
+template <int VD, int ED, int EK, int PE, int BLOCK>
+__device__ __forceinline__ void long_row_block(const KParams& P, const int4 d, double* s_val) {
+  const int tid = threadIdx.x;
+  const int e0 = d.x, r0 = d.y, ne = d.z;
+  const VBDev B = P.vb[d.w];
+  const int coupling0 = P.n_eb > 0 ? P.eb[0].coupling : 0;
+  double self[VD];
+  const long long sidx = P.gather_from_u ? (B.state0 + (long long)(r0 - B.row0) * B.dim) : (long long)r0 * VD;
+#pragma unroll
+  for (int k = 0; k < VD; ++k) self[k] = P.gsrc[sidx + k];
+  double part[ED];
+#pragma unroll
+  for (int q = 0; q < ED; ++q) part[q] = 0.0;
+  for (int jj = tid; jj < ne; jj += BLOCK) {
+    int nb, ep = 0;
+    if constexpr (PE > 0) { const int2 t2 = P.jent[e0 + jj]; nb = t2.x; ep = t2.y; }
+    else nb = P.jnbr[e0 + jj];
+    const int side = nb < 0;
+    nb = side ? ~nb : nb;
+    double xn[VD];
+#pragma unroll
+    for (int k = 0; k < VD; ++k) xn[k] = P.gsrc[(long long)nb + k];
+    int kind = EK, coupling = coupling0, pd = PE;
+    if constexpr (EK == EK_GENERIC) {
+      const EBDev E = P.eb[P.jebid[e0 + jj]];
+      kind = E.kind; coupling = E.coupling; pd = E.pdim;
+    }
+    double pl[PE > 0 ? PE : 1];
+    pl[0] = 0.0;
+    if constexpr (PE > 0) {
+      if (pd > 0) {
+#pragma unroll
+        for (int k = 0; k < PE; ++k) pl[k] = P.p[(long long)ep + k];
+      }
+    }
+    double val[ED];
+    entry_value<VD, ED>(kind, coupling, side, self, xn, pl, val);
+#pragma unroll
+    for (int q = 0; q < ED; ++q) part[q] = part[q] + val[q];
+  }
+#pragma unroll
+  for (int q = 0; q < ED; ++q) s_val[tid * ED + q] = part[q];
+  __syncthreads();
+  for (int s = BLOCK / 2; s > 0; s >>= 1) {
+    if (tid < s) {
+#pragma unroll
+      for (int q = 0; q < ED; ++q) s_val[tid * ED + q] = s_val[tid * ED + q] + s_val[(tid + s) * ED + q];
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    double acc[ED], v[2];
+#pragma unroll
+    for (int q = 0; q < ED; ++q) acc[q] = s_val[q];
+    load_vertex_state(P, B, r0, v);
+    vertex_phase<VD, ED>(P, B, r0, acc, self, v, P.p + B.p0 + (long long)(r0 - B.row0) * B.pdim);
+  }
+}
+
+template <int VD, int ED, int EK, int PE, int BLOCK, int U, int WPS>
+__global__ void __launch_bounds__(BLOCK, (WPS * 32) / BLOCK) rhs_jag_kernel(const __grid_constant__ KParams P) {
+  __shared__ double s_val[BLOCK * ED];   // long rows only
+  halo_wait(P);   // multi-GPU only
+  if ((int)blockIdx.x >= P.n_jag_blocks) {
+    long_row_block<VD, ED, EK, PE, BLOCK>(P, __ldg(&P.jlong[blockIdx.x - P.n_jag_blocks]), s_val);
+    return;
+  }
+  const int lane = threadIdx.x & 31;
+  const int sl = blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5);
+  if (sl >= P.nslices) return;           // warp-uniform
+  const int4 S = __ldg(&P.jslices[sl]);
+  const unsigned desc = __ldg(&P.jlanes[(long long)sl * 32 + lane]);
+  const int len = desc & 63;
+  const int row = S.y + ((desc >> 6) & 31);
+  const bool head = (desc >> 11) & 1, valid = (desc >> 12) & 1;
+  const VBDev B = P.vb[S.z];
+  const int coupling0 = P.n_eb > 0 ? P.eb[0].coupling : 0;
+  const unsigned lt = (1u << lane) - 1u;
+
+  double self[VD];
+#pragma unroll
+  for (int k = 0; k < VD; ++k) self[k] = 0.0;
+  if (valid) {
+    const long long sidx = P.gather_from_u ? (B.state0 + (long long)(row - B.row0) * B.dim) : (long long)row * VD;
+#pragma unroll
+    for (int k = 0; k < VD; ++k) self[k] = P.gsrc[sidx + k];
+  }
+  double acc[ED];
+#pragma unroll
+  for (int q = 0; q < ED; ++q) acc[q] = 0.0;
+
+  int base = S.x;
+  for (int j = 0;; j += U) {
+    const unsigned m0 = __ballot_sync(0xffffffffu, j < len);
+    if (m0 == 0u) break;
+    // (1) slots of this lane in the next U columns
+    int pos[U];
+    bool act[U];
+#pragma unroll
+    for (int q = 0; q < U; ++q) {
+      act[q] = (j + q) < len;
+      const unsigned m = q == 0 ? m0 : __ballot_sync(0xffffffffu, act[q]);
+      pos[q] = base + __popc(m & lt);
+      base += __popc(m);
+    }
+    // (2) coalesced index loads
+    int nb[U], ep[U];
+#pragma unroll
+    for (int q = 0; q < U; ++q) {
+      nb[q] = 0; ep[q] = 0;
+      if (act[q]) {
+        if constexpr (PE > 0) { const int2 t2 = __ldcs(&P.jent[pos[q]]); nb[q] = t2.x; ep[q] = t2.y; }
+        else nb[q] = __ldcs(&P.jnbr[pos[q]]);
+      }
+    }
+    // (3) the gathers and the edge parameters: 2U independent random reads per lane
+    double xn[U][VD], pl[U][PE > 0 ? PE : 1];
+    int kind[U], coupling[U];
+#pragma unroll
+    for (int q = 0; q < U; ++q) {
+      const int off = nb[q] < 0 ? ~nb[q] : nb[q];
+#pragma unroll
+      for (int k = 0; k < VD; ++k) xn[q][k] = 0.0;
+      pl[q][0] = 0.0;
+      kind[q] = EK; coupling[q] = coupling0;
+      if (act[q]) {
+        if constexpr (VD == 2) {
+          const double2 t2 = *reinterpret_cast<const double2*>(P.gsrc + off);
+          xn[q][0] = t2.x; xn[q][1] = t2.y;
+        } else {
+          xn[q][0] = P.gsrc[off];
+        }
+        int pd = PE;
+        if constexpr (EK == EK_GENERIC) {
+          const EBDev E = P.eb[P.jebid[pos[q]]];
+          kind[q] = E.kind; coupling[q] = E.coupling; pd = E.pdim;
+        }
+        if constexpr (PE > 0) {
+          if (pd > 0) {
+#pragma unroll
+            for (int k = 0; k < PE; ++k) pl[q][k] = P.p[(long long)ep[q] + k];
+          }
+        }
+      }
+    }
+    // (4) edge model + sequential accumulation in entry order
+#pragma unroll
+    for (int q = 0; q < U; ++q) {
+      if (act[q]) {
+        double val[ED];
+        entry_value<VD, ED>(kind[q], coupling[q], nb[q] < 0, self, xn[q], pl[q], val);
+#pragma unroll
+        for (int d = 0; d < ED; ++d) acc[d] = acc[d] + val[d];
+      }
+    }
+  }
+  // (5) rows cut into several lanes: the head lane adds the parts in order
+  if (S.w > 1) {
+    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+    const unsigned hmask = __ballot_sync(0xffffffffu, head);
+    const unsigned cont = vmask & ~hmask;
+    // number of continuation lanes directly above this lane
+    const unsigned above = lane == 31 ? 0u : (~cont >> (lane + 1));
+    const int nparts = 1 + (lane == 31 ? 0 : (above ? __ffs(above) - 1 : 31 - lane));
+    for (int k = 1; k < S.w; ++k) {
+#pragma unroll
+      for (int d = 0; d < ED; ++d) {
+        const double v = __shfl_down_sync(0xffffffffu, acc[d], k);
+        if (head && k < nparts) acc[d] = acc[d] + v;
+      }
+    }
+  }
+  // (6) vertex model
+  if (head) {
+    double v[2];
+    load_vertex_state(P, B, row, v);
+    vertex_phase<VD, ED>(P, B, row, acc, self, v, P.p + B.p0 + (long long)(row - B.row0) * B.pdim);
   }
 }
 

@@ -173,12 +173,13 @@ class B200Aggregator:
     (read as `nw.layer.aggregator.f`, test/testutils.jl:50)."""
 
     def __init__(self, f="+", *, device: Optional[int] = None, row_range=None, long_row_threshold: int = 0,
-                 keep_tables: bool = True):
+                 keep_tables: bool = True, host_only: bool = False):
         if f not in ("+", sum, np.add) and getattr(f, "__name__", "") != "add":
             raise ArgumentError("B200Aggregator only supports + as the reducer (no CPU fallback for others)")
         self.f = "+"
+        # host_only: build the engine's tables without touching a device (layout tests); such a network cannot be called
         self._opts = dict(device=device, row_range=row_range, long_row_threshold=long_row_threshold,
-                          keep_tables=keep_tables)
+                          keep_tables=keep_tables, host_only=host_only)
         self.handle = None
         self._keep = None
 
@@ -227,7 +228,8 @@ class B200Aggregator:
                           dst.ctypes.data_as(_cabi.i64p), im.vdepth, im.edepth, len(vertexbatches),
                           len(edgebatches), vb, eb, im.lastidx_dynamic, im.lastidx_p, im.lastidx_out,
                           im.lastidx_aggr, int(rr[0]), int(rr[1]), int(self._opts["long_row_threshold"]),
-                          0 if self._opts["keep_tables"] else _cabi.FLAG_NO_EXPORT)
+                          (0 if self._opts["keep_tables"] else _cabi.FLAG_NO_EXPORT)
+                          | (_cabi.FLAG_HOST_ONLY if self._opts["host_only"] else 0))
         h = C.c_void_p()
         rc = L.nd_b200_create(C.byref(desc), C.byref(h))
         if rc != _cabi.OK:
@@ -421,6 +423,27 @@ class Network:
             self._fail(rc)
         k = sz["nentries"]
         return rowptr, nbr[:k], eid[:k], side[:k]
+
+    def export_jag(self):
+        """the jagged device layout of the default kernel (host_only engines): slices[n,4], lanes[n,32], longs[m,4],
+        order[entries] -- see include/nd_b200.h"""
+        sz = np.zeros(4, dtype=np.int64)
+        rc = self._L.nd_b200_export_jag_sizes(self.handle, sz.ctypes.data_as(_cabi.i64p))
+        if rc:
+            self._fail(rc)
+        ns, nl, split, ne = (int(v) for v in sz)
+        if ns < 0:
+            raise ArgumentError("engine does not use the jagged layout")
+        slices = np.zeros((max(ns, 1), 4), dtype=np.int32)
+        lanes = np.zeros((max(ns, 1), 32), dtype=np.uint16)
+        longs = np.zeros((max(nl, 1), 4), dtype=np.int32)
+        order = np.zeros(max(ne, 1), dtype=np.int32)
+        rc = self._L.nd_b200_export_jag(self.handle, slices.ctypes.data_as(_cabi.i32p),
+                                        lanes.ctypes.data_as(C.POINTER(C.c_uint16)), longs.ctypes.data_as(_cabi.i32p),
+                                        order.ctypes.data_as(_cabi.i32p))
+        if rc:
+            self._fail(rc)
+        return dict(slices=slices[:ns], lanes=lanes[:ns], longs=longs[:nl], order=order[:ne], split=split)
 
     def launch_count(self) -> int:
         return int(self._L.nd_b200_launch_count(self.handle))

@@ -28,8 +28,9 @@ def cuda():
     return torch
 
 
-@pytest.fixture(params=["split", "fused"])
+@pytest.fixture(params=["split", "fused", "jag"])
 def kernel_mode(request, monkeypatch):
-    """run a test once per evaluation mode of the engine (edge-once split passes / single fused kernel)"""
+    """run a test once per evaluation mode of the engine (edge-once split passes / fused tile kernel / jagged
+    warp-slice kernel = default)"""
     monkeypatch.setenv("ND_B200_KERNEL", request.param)
     return request.param

@@ -271,6 +271,15 @@ def test_launch_shapes_agree(nd, cuda, monkeypatch):
         u, p = rand_inputs(nw.dim(), nw.pdim(), layout=lambda q: condition_params(nw, q))
         outs.append(_run_gpu(cuda, nw, u, p))
         assert floored_rel_err(outs[-1], onw.rhs(u, p)) <= TOL_DU
+    # jagged kernel: columns per iteration x occupancy cap x row-split width (7 forces many split rows on BA hubs)
+    monkeypatch.setenv("ND_B200_KERNEL", "jag")
+    for unroll, wps, split in ((2, 32, 32), (2, 48, 32), (2, 64, 32), (4, 32, 32), (4, 48, 32), (4, 64, 32), (2, 48, 7), (4, 64, 63)):
+        monkeypatch.setenv("ND_B200_JAG_U", str(unroll))
+        monkeypatch.setenv("ND_B200_JAG_WPS", str(wps))
+        monkeypatch.setenv("ND_B200_JAG_SPLIT", str(split))
+        nw = nd.Network(g, vm, em)
+        u, p = rand_inputs(nw.dim(), nw.pdim(), layout=lambda q: condition_params(nw, q))
+        assert floored_rel_err(_run_gpu(cuda, nw, u, p), onw.rhs(u, p)) <= TOL_DU, (unroll, wps, split)
 
 
 def test_full_size_properties_cfg2(nd, cuda):
