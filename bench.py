@@ -290,7 +290,7 @@ def main():
     if world == 1 and fused_ms > 0:
         achieved = b_alg / (fused_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "kernel": "rhs_fused_kernel<1,1,E_DIFFUSION>", "kernel_ms_avg": fused_ms,
+                    "traffic": None, "kernel": nw.kernel_name() + "<1,1,E_DIFFUSION>", "kernel_ms_avg": fused_ms,
                     "algorithmic_bytes_per_launch": b_alg, "peak_source": peak_src,
                     "frac_of_nominal_8000": achieved / 8000.0,
                     "note": "kernel time from CUDA events recorded by the engine on the launch stream around the fused "

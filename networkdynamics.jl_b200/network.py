@@ -17,6 +17,8 @@ import ctypes as C
 from dataclasses import dataclass
 from typing import List, Optional, Sequence
 
+import os
+
 import numpy as np
 
 from . import _cabi
@@ -423,6 +425,14 @@ class Network:
             self._fail(rc)
         k = sz["nentries"]
         return rowptr, nbr[:k], eid[:k], side[:k]
+
+    def kernel_name(self) -> str:
+        """name of the kernel family that evaluates this network (rhs_jag_kernel unless ND_B200_KERNEL selects a tile kernel)"""
+        sz = np.zeros(4, dtype=np.int64)
+        self._L.nd_b200_export_jag_sizes(self.handle, sz.ctypes.data_as(_cabi.i64p))
+        if sz[0] >= 0:
+            return "rhs_jag_kernel"
+        return "edge_pass_kernel+row_pass_kernel" if os.environ.get("ND_B200_KERNEL") == "split" else "rhs_fused_kernel"
 
     def export_jag(self):
         """the jagged device layout of the default kernel (host_only engines): slices[n,4], lanes[n,32], longs[m,4],

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Time the RHS (and RK4) on all BASELINE.json configs that fit one GPU; one JSON line per config.
-   python tools/bench_configs.py [cfg1 cfg2 cfg2nop cfg3 cfg4 cfg5s] [--check]"""
+"""Time the RHS (and RK4) on all BASELINE.json configs that fit one GPU; one JSON line per (config, mode).
+   python tools/bench_configs.py [cfg1 cfg2 cfg2nop cfg3 cfg4 cfg5s] [--check] [--quick]
+                                 [--modes=name:ENV=VAL,ENV=VAL;name2:...]     engine env switches per mode"""
 import json, os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -25,48 +26,65 @@ def make(name):
     if name == "cfg5s": return nd.erdos_renyi(5_000_000, 40_000_000, seed=1), L.kuramoto_first(), L.kuramoto_edge()
     raise SystemExit(name)
 
+def parse_modes():
+    for a in sys.argv[1:]:
+        if a.startswith("--modes="):
+            out = []
+            for m in a[len("--modes="):].split(";"):
+                name, _, envs = m.partition(":")
+                out.append((name, dict(kv.split("=") for kv in envs.split(",") if kv)))
+            return out
+    return [("default", {})]
+
+
 def main():
     names = [a for a in sys.argv[1:] if not a.startswith("--")] or ["cfg1", "cfg2", "cfg2nop", "cfg3", "cfg4"]
     check = "--check" in sys.argv
+    quick = "--quick" in sys.argv
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")
     for name in names:
         g, vm, em = make(name)
-        t0 = time.time()
-        nw = nd.Network(g, vm, em, aggregator=nd.B200Aggregator("+", keep_tables=False))
-        tb = time.time() - t0
-        sz = nw.engine_sizes()
-        u_h = np.random.default_rng(1).random(nw.dim())
-        p_h = condition_params(nw, np.random.default_rng(2).random(nw.pdim()))
-        u, p = torch.from_numpy(u_h).cuda(), torch.from_numpy(p_h).cuda()
-        du = torch.empty_like(u)
-        for _ in range(50): nw(du, u, p, 0.0)
-        torch.cuda.synchronize()
-        K = 100
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-        for a, b in ev:
-            flush.zero_(); a.record(); nw(du, u, p, 0.0); b.record()
-        torch.cuda.synchronize()
-        cold = np.array([a.elapsed_time(b) for a, b in ev])
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(K): nw(du, u, p, 0.0)
-        b.record(); torch.cuda.synchronize()
-        warm = a.elapsed_time(b) / K
-        b_alg = 16 * nw.dim() + 8 * nw.pdim() + 4 * (g.nv + 1) + 4 * sz["nentries"]
-        line = {"config": name, "nv": g.nv, "ne": g.ne, "entries": sz["nentries"], "blocks": sz["nblocks"], "long_rows": sz["n_long_rows"],
-                "rhs_us_cold_mean": float(cold.mean() * 1e3), "rhs_us_cold_min": float(cold.min() * 1e3), "rhs_us_warm": warm * 1e3,
-                "b_alg_MB": b_alg / 1e6, "GBs_cold": b_alg / cold.mean() / 1e6, "GBs_warm": b_alg / warm / 1e6,
-                "edge_evals_per_s_cold": g.ne / (cold.mean() * 1e-3), "build_s": round(tb, 2)}
-        # RK4: 200 steps
-        ur = u.clone()
-        nw.rk4(ur, p, 0.0, 1e-3, 8); torch.cuda.synchronize()
-        a.record(); nw.rk4(ur, p, 0.0, 1e-3, 200); b.record(); torch.cuda.synchronize()
-        line["rk4_us_per_step"] = a.elapsed_time(b) / 200 * 1e3
-        if check:
-            onw = oracle_network(g, vm, em)
-            line["parity"] = floored_rel_err(du.cpu().numpy(), onw.rhs(u_h, p_h, threads=8))
-        print(json.dumps(line), flush=True)
-        del nw
+        onw = oracle_network(g, vm, em) if check else None
+        for mode, envs in parse_modes():
+            for k in [k for k in os.environ if k.startswith("ND_B200_") and k != "ND_B200_LIB"]:
+                del os.environ[k]
+            os.environ.update(envs)
+            t0 = time.time()
+            nw = nd.Network(g, vm, em, aggregator=nd.B200Aggregator("+", keep_tables=False))
+            tb = time.time() - t0
+            sz = nw.engine_sizes()
+            u_h = np.random.default_rng(1).random(nw.dim())
+            p_h = condition_params(nw, np.random.default_rng(2).random(nw.pdim()))
+            u, p = torch.from_numpy(u_h).cuda(), torch.from_numpy(p_h).cuda()
+            du = torch.empty_like(u)
+            for _ in range(5 if quick else 50): nw(du, u, p, 0.0)
+            torch.cuda.synchronize()
+            K = 5 if quick else 100
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+            for a, b in ev:
+                flush.zero_(); a.record(); nw(du, u, p, 0.0); b.record()
+            torch.cuda.synchronize()
+            cold = np.array([a.elapsed_time(b) for a, b in ev])
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(K): nw(du, u, p, 0.0)
+            b.record(); torch.cuda.synchronize()
+            warm = a.elapsed_time(b) / K
+            b_alg = 16 * nw.dim() + 8 * nw.pdim() + 4 * (g.nv + 1) + 4 * sz["nentries"]
+            line = {"config": name, "mode": mode, "nv": g.nv, "ne": g.ne, "entries": sz["nentries"], "blocks": sz["nblocks"], "long_rows": sz["n_long_rows"],
+                    "rhs_us_cold_mean": float(cold.mean() * 1e3), "rhs_us_cold_min": float(cold.min() * 1e3), "rhs_us_warm": warm * 1e3,
+                    "b_alg_MB": b_alg / 1e6, "GBs_cold": b_alg / cold.mean() / 1e6, "GBs_warm": b_alg / warm / 1e6,
+                    "edge_evals_per_s_cold": g.ne / (cold.mean() * 1e-3), "build_s": round(tb, 2)}
+            if not quick:   # RK4: 200 steps
+                ur = u.clone()
+                nw.rk4(ur, p, 0.0, 1e-3, 8); torch.cuda.synchronize()
+                a.record(); nw.rk4(ur, p, 0.0, 1e-3, 200); b.record(); torch.cuda.synchronize()
+                line["rk4_us_per_step"] = a.elapsed_time(b) / 200 * 1e3
+            if check:
+                line["parity"] = floored_rel_err(du.cpu().numpy(), onw.rhs(u_h, p_h, threads=8))
+            print(json.dumps(line), flush=True)
+            del nw
+
 
 if __name__ == "__main__":
     main()
