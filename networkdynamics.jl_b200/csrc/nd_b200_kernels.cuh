@@ -78,6 +78,12 @@ struct KParams {
   const uint8_t* __restrict__ jebid;   // per entry edge batch id (EK_GENERIC)
   const int4* __restrict__ jlong;      // rows reduced by a whole block {entry base, row, entries, vertex batch}
   int nslices, n_jag_blocks;
+  // multi-GPU packed halo (jagged kernel only): gather offsets >= halo_base address the halo buffer that the peers'
+  // publish kernels fill with exactly the remote vertex outputs this rank's rows read; slices >= wait_from_slice
+  // (the ones that read remote outputs) wait for the arrival flags, interior slices run while the halo is in flight
+  const double* halo;
+  int halo_base;
+  int wait_from_slice;
 };
 
 // parameters of the edge pass (split mode)
@@ -263,12 +269,13 @@ __device__ __forceinline__ void load_vertex_state(const KParams& P, const VBDev&
 // which those peers published after finishing their own reads of s.
 // ------------------------------------------------------------------------------------------------
 constexpr int HALO_MAX_WORLD = 8;
-constexpr int HALO_MAX_SEGS = 8;
 struct HaloParams {
-  double* replica[HALO_MAX_WORLD];                 // [rank] -> that rank's replica (this sequence's parity)
-  unsigned long long* flags[HALO_MAX_WORLD];       // [rank] -> that rank's arrival-flag array
-  long long seg_start[HALO_MAX_SEGS], seg_len[HALO_MAX_SEGS];
-  int nsegs, world, rank;
+  double* halo[HALO_MAX_WORLD];                    // [peer] -> that rank's halo buffer (this sequence's parity), peer-mapped
+  unsigned long long* flags[HALO_MAX_WORLD];       // [peer] -> that rank's arrival-flag array
+  const int* send_idx[HALO_MAX_WORLD];             // [peer] -> offsets (into src) of the outputs that peer reads, ascending
+  long long send_n[HALO_MAX_WORLD];                //          how many
+  long long dst_off[HALO_MAX_WORLD];               //          where this rank's block starts inside the peer's halo buffer
+  int world, rank;
   unsigned long long seq;
   const double* src;                                // the owner's state vector (full layout, owned ranges valid)
   unsigned int* done_counter;                       // local: blocks finished (reset by the last block)
@@ -283,28 +290,18 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// pack + publish: for every peer, gather the outputs it needs from the owner's state vector (ascending offsets: the
+// reads are nearly coalesced) and store them contiguously into the peer's halo buffer (coalesced NVLink stores); the
+// last block to finish raises this rank's arrival flag on every rank.
 __global__ void __launch_bounds__(256) halo_publish_kernel(const __grid_constant__ HaloParams H) {
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long nthreads = (long long)gridDim.x * blockDim.x;
-  for (int s = 0; s < H.nsegs; ++s) {
-    const long long a = H.seg_start[s], n = H.seg_len[s];
-    // 16-byte body when the range start is even (8-byte elements), scalar head/tail otherwise
-    const long long head = (a & 1) ? 1 : 0;
-    const long long nvec = (n - head) / 2;
-    if (tid < head) {
-      const double v = H.src[a];
-      for (int r = 0; r < H.world; ++r) H.replica[r][a] = v;
-    }
-    for (long long i = tid; i < nvec; i += nthreads) {
-      const long long j = a + head + 2 * i;
-      const double2 v = *reinterpret_cast<const double2*>(H.src + j);
-      for (int r = 0; r < H.world; ++r) *reinterpret_cast<double2*>(H.replica[r] + j) = v;
-    }
-    if (tid == 0 && head + 2 * nvec < n) {
-      const long long j = a + n - 1;
-      const double v = H.src[j];
-      for (int r = 0; r < H.world; ++r) H.replica[r][j] = v;
-    }
+  for (int r = 0; r < H.world; ++r) {
+    if (r == H.rank) continue;
+    const long long n = H.send_n[r];
+    const int* __restrict__ idx = H.send_idx[r];
+    double* __restrict__ dst = H.halo[r] + H.dst_off[r];
+    for (long long i = tid; i < n; i += nthreads) dst[i] = H.src[idx[i]];
   }
   // make this block's peer stores visible system-wide, then count the block as done
   __threadfence_system();
@@ -333,6 +330,28 @@ __device__ __forceinline__ void halo_wait(const KParams& P) {
     }
   }
   __syncthreads();
+}
+
+// warp-level variant for the jagged kernel: only the warps whose slice reads remote outputs wait
+__device__ __forceinline__ void halo_wait_warp(const KParams& P) {
+  if (P.wait_flags == nullptr) return;
+  const int lane = threadIdx.x & 31;
+  if (lane < P.wait_world) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(P.wait_flags + lane) < P.wait_seq) {
+      if (clock64() - t0 > 4000000000LL) {
+        *P.wait_timeout = 1;
+        break;
+      }
+      __nanosleep(100);
+    }
+  }
+  __syncwarp();
+}
+
+// gather source of an offset: the state vector (or materialised vertex outputs) below halo_base, the halo buffer above
+__device__ __forceinline__ const double* gather_ptr(const KParams& P, int off) {
+  return (off >= P.halo_base ? P.halo - P.halo_base : P.gsrc) + off;
 }
 
 // Occupancy is the lever for this kernel (it is bound by the L2 sector bandwidth of the random gathers and hides
@@ -740,8 +759,9 @@ __device__ __forceinline__ void long_row_block(const KParams& P, const int4 d, d
     const int side = nb < 0;
     nb = side ? ~nb : nb;
     double xn[VD];
+    const double* gp = gather_ptr(P, nb);
 #pragma unroll
-    for (int k = 0; k < VD; ++k) xn[k] = P.gsrc[(long long)nb + k];
+    for (int k = 0; k < VD; ++k) xn[k] = gp[k];
     int kind = EK, coupling = coupling0, pd = PE;
     if constexpr (EK == EK_GENERIC) {
       const EBDev E = P.eb[P.jebid[e0 + jj]];
@@ -782,14 +802,15 @@ __device__ __forceinline__ void long_row_block(const KParams& P, const int4 d, d
 template <int VD, int ED, int EK, int PE, int BLOCK, int U, int WPS>
 __global__ void __launch_bounds__(BLOCK, (WPS * 32) / BLOCK) rhs_jag_kernel(const __grid_constant__ KParams P) {
   __shared__ double s_val[BLOCK * ED];   // long rows only
-  halo_wait(P);   // multi-GPU only
   if ((int)blockIdx.x >= P.n_jag_blocks) {
+    halo_wait(P);   // multi-GPU only
     long_row_block<VD, ED, EK, PE, BLOCK>(P, __ldg(&P.jlong[blockIdx.x - P.n_jag_blocks]), s_val);
     return;
   }
   const int lane = threadIdx.x & 31;
   const int sl = blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5);
   if (sl >= P.nslices) return;           // warp-uniform
+  if (sl >= P.wait_from_slice) halo_wait_warp(P);   // multi-GPU only: this slice reads the halo
   const int4 S = __ldg(&P.jslices[sl]);
   const unsigned desc = __ldg(&P.jlanes[(long long)sl * 32 + lane]);
   const int len = desc & 63;
@@ -846,11 +867,12 @@ __global__ void __launch_bounds__(BLOCK, (WPS * 32) / BLOCK) rhs_jag_kernel(cons
       pl[q][0] = 0.0;
       kind[q] = EK; coupling[q] = coupling0;
       if (act[q]) {
+        const double* gp = gather_ptr(P, off);
         if constexpr (VD == 2) {
-          const double2 t2 = *reinterpret_cast<const double2*>(P.gsrc + off);
+          const double2 t2 = *reinterpret_cast<const double2*>(gp);
           xn[q][0] = t2.x; xn[q][1] = t2.y;
         } else {
-          xn[q][0] = P.gsrc[off];
+          xn[q][0] = gp[0];
         }
         int pd = PE;
         if constexpr (EK == EK_GENERIC) {
