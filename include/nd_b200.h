@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define ND_B200_ABI_VERSION 1
+#define ND_B200_ABI_VERSION 2
 
 /* status codes (Julia glue rethrows: EINVAL -> ArgumentError, others -> ErrorException) */
 enum {
@@ -92,6 +92,13 @@ typedef struct nd_b200_desc {
    * strictly sequential per-row accumulation everywhere (debug).            */
   int32_t long_row_threshold;
   int32_t flags;           /* ND_B200_FLAG_*                                 */
+  /* Multi-GPU packed halo (optional, NULL = none; needs StateMask vertices with one output, i.e. the gather
+   * source is the state vector).  gather_offset[v-1] = 0-based position of vertex v's output in the gather
+   * source of THIS engine: positions < lastidx_dynamic address the caller's state vector u (vertices of owned
+   * rows must map to their own state), positions in [lastidx_dynamic, gather_len) address the halo buffer that
+   * the peers fill through nd_b200_rhs_exchange.  Vertices this engine never reads may hold any valid value. */
+  const int64_t* gather_offset;
+  int64_t gather_len;
 } nd_b200_desc;
 
 #define ND_B200_FLAG_NO_EXPORT 1  /* do not keep host copies of the CSR for nd_b200_export_tables */
@@ -137,11 +144,12 @@ int nd_b200_export_tables(const nd_b200_engine*, int64_t* rowptr, int64_t* nbr_v
                           int32_t* side);
 
 /* The jagged device layout of the default kernel (rhs_jag_kernel), ND_B200_FLAG_HOST_ONLY engines only.
- * sizes[0]=slices (-1: engine uses a tile kernel) [1]=rows reduced by a whole block [2]=row split width [3]=entries.
+ * sizes[0]=slices (-1: engine uses a tile kernel) [1]=rows reduced by a whole block [2]=row split width [3]=entries
+ * [4]=first slice (tile, for the tile kernel) that reads the halo [5]=outputs in the halo (-1: no halo layout).
  * slices[4*s..] = {entry base, first row, vertex batch, max parts}; lanes[32*s+l] = len | rowrel<<6 | head<<11 |
  * valid<<12; longs[4*k..] = {entry base, row, entries, vertex batch}; order[k] = CSR entry (as exported by
  * nd_b200_export_tables) stored at jagged position k. */
-int nd_b200_export_jag_sizes(const nd_b200_engine*, int64_t sizes[4]);
+int nd_b200_export_jag_sizes(const nd_b200_engine*, int64_t sizes[6]);
 int nd_b200_export_jag(const nd_b200_engine*, int32_t* slices, uint16_t* lanes, int32_t* longs, int32_t* order);
 
 /* kernel launches issued by this engine since creation (bench.py's gpu_launches) */
@@ -151,18 +159,25 @@ int64_t nd_b200_launch_count(const nd_b200_engine*);
 int nd_b200_set_timing(nd_b200_engine*, int enabled);
 int nd_b200_timings(nd_b200_engine*, double* fused_ms_avg, double* prepass_ms_avg, int64_t* ncalls);
 
-/* ---- multi-GPU: state exchange over NVLink peer memory (one process per GPU) -----------------------------------
- * The reference has no multi-device path.  A `comm` owns this rank's double-buffered replica of the
- * full state vector plus an arrival-flag array, all in ONE device allocation that the other ranks map through CUDA
- * IPC.  nd_b200_rhs_exchange = "publish my rows' states into every rank's replica with plain NVLink stores, raise my
- * flag everywhere" + "RHS kernel that waits for all flags and gathers from the local replica".  No NCCL, no host
- * synchronisation on the data path.  Collective: every rank must make the same sequence of calls. */
+/* ---- multi-GPU: packed halo exchange over NVLink peer memory (one process per GPU) ---------------------------------
+ * The reference has no multi-device path.  A `comm` owns this rank's double-buffered HALO buffer -- the
+ * outputs of exactly the remote vertices its rows read, grouped by owner rank and sorted by state offset -- plus an
+ * arrival-flag array, all in ONE device allocation that the other ranks map through CUDA IPC.  The engine is created
+ * with nd_b200_desc.gather_offset pointing into [u | halo].  nd_b200_rhs_exchange = "pack the outputs every peer needs
+ * from my state vector straight into that peer's halo buffer with NVLink stores, raise my flag everywhere" + "RHS kernel
+ * whose interior tiles start at once and whose boundary tiles wait for the flags".  No NCCL, no host synchronisation on
+ * the data path.  Collective: every rank must make the same sequence of calls, all on one stream per rank. */
 typedef struct nd_b200_comm nd_b200_comm;
 #define ND_B200_IPC_HANDLE_BYTES 64
-int nd_b200_comm_create(int32_t device, int32_t rank, int32_t world, int64_t nstates, nd_b200_comm** out);
+/* halo_len: outputs in THIS rank's halo; max_halo_len: the largest halo_len among the ranks (one layout everywhere) */
+int nd_b200_comm_create(int32_t device, int32_t rank, int32_t world, int64_t halo_len, int64_t max_halo_len,
+                        nd_b200_comm** out);
 /* opaque handle (ND_B200_IPC_HANDLE_BYTES bytes) to ship to the peers (e.g. torch.distributed all_gather_object) */
 int nd_b200_comm_export(nd_b200_comm*, void* handle_out);
 int nd_b200_comm_open_peer(nd_b200_comm*, int32_t peer, const void* handle);
+/* what this rank sends to `peer` on every exchange: the 0-based state offsets (ascending) of the outputs that peer's
+ * rows read from this rank, stored contiguously from position dst_offset of the peer's halo buffer */
+int nd_b200_comm_set_send(nd_b200_comm*, int32_t peer, const int64_t* state_offsets, int64_t n, int64_t dst_offset);
 /* replaces `(nw::Network)(du,u,p,t)` for a row-partitioned engine: only the owned states of u need to be valid */
 int nd_b200_rhs_exchange(nd_b200_engine*, nd_b200_comm*, double* du, const double* u, const double* p, double t,
                          void* stream);

@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("ND_B200_LIB") or os.path.join(_PKG, "libnd_b200.so") 
 SOURCES = [os.path.join(_PKG, "csrc", "nd_b200.cu")]
 HEADERS = [os.path.join(_PKG, "csrc", "nd_b200_kernels.cuh"), os.path.join(_ROOT, "include", "nd_b200.h")]
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 OK, EINVAL, EUNSUPPORTED, ECUDA, ENOMEM = range(5)
 
 # registry ids (include/nd_b200.h)
@@ -48,14 +48,15 @@ class Desc(C.Structure):
                 ("n_vbatches", C.c_int32), ("n_ebatches", C.c_int32), ("vbatches", C.POINTER(VBatch)),
                 ("ebatches", C.POINTER(EBatch)), ("lastidx_dynamic", C.c_int64), ("lastidx_p", C.c_int64),
                 ("lastidx_out", C.c_int64), ("lastidx_aggr", C.c_int64), ("row_begin", C.c_int64),
-                ("row_end", C.c_int64), ("long_row_threshold", C.c_int32), ("flags", C.c_int32)]
+                ("row_end", C.c_int64), ("long_row_threshold", C.c_int32), ("flags", C.c_int32),
+                ("gather_offset", i64p), ("gather_len", C.c_int64)]
 
 
 EXPORTED_SYMBOLS = [
     "nd_b200_create", "nd_b200_destroy", "nd_b200_last_error", "nd_b200_abi_version", "nd_b200_rhs",
     "nd_b200_rhs_host", "nd_b200_get_buffers", "nd_b200_rk4", "nd_b200_export_sizes", "nd_b200_export_tables",
     "nd_b200_launch_count", "nd_b200_set_timing", "nd_b200_timings", "nd_b200_host_alloc", "nd_b200_host_free",
-    "nd_b200_comm_create", "nd_b200_comm_export", "nd_b200_comm_open_peer", "nd_b200_rhs_exchange", "nd_b200_comm_status",
+    "nd_b200_comm_create", "nd_b200_comm_export", "nd_b200_comm_open_peer", "nd_b200_comm_set_send", "nd_b200_rhs_exchange", "nd_b200_comm_status",
     "nd_b200_comm_last_error", "nd_b200_comm_destroy", "nd_b200_export_jag_sizes", "nd_b200_export_jag",
 ]
 IPC_HANDLE_BYTES = 64
@@ -133,7 +134,9 @@ def lib():
     L.nd_b200_host_free.restype = None
     L.nd_b200_host_free.argtypes = [C.c_void_p]
     L.nd_b200_comm_create.restype = C.c_int
-    L.nd_b200_comm_create.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.POINTER(C.c_void_p)]
+    L.nd_b200_comm_create.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.POINTER(C.c_void_p)]
+    L.nd_b200_comm_set_send.restype = C.c_int
+    L.nd_b200_comm_set_send.argtypes = [C.c_void_p, C.c_int32, i64p, C.c_int64, C.c_int64]
     L.nd_b200_comm_export.restype = C.c_int
     L.nd_b200_comm_export.argtypes = [C.c_void_p, C.c_char_p]
     L.nd_b200_comm_open_peer.restype = C.c_int

@@ -64,13 +64,16 @@ struct nd_b200_engine {
   uint8_t* d_eebid = nullptr;
   double* d_oedge = nullptr;
   // jagged layout (ND_B200_KERNEL=jag): warp slices, see rhs_jag_kernel
-  int jag = 0, jag_u = 4, jag_wps = 0, jsplit = 32;
+  int jag = 0, jag_u = 2, jag_wps = 0, jsplit = 32;
   int nslices = 0, n_jag_blocks = 0, n_jlong = 0;
   int4 *d_jslices = nullptr, *d_jlong = nullptr;
   uint16_t* d_jlanes = nullptr;
   int* d_jnbr = nullptr;
   int2* d_jent = nullptr;
   uint8_t* d_jebid = nullptr;
+  int halo_base = INT_MAX;    // gather offsets >= halo_base address the halo buffer (multi-GPU packed halo)
+  long long gather_len = 0;
+  int wait_from = 0;          // first tile / slice that reads the halo
   bool host_only = false;     // ND_B200_FLAG_HOST_ONLY: tables built, nothing uploaded (layout tests without a GPU)
   std::vector<int4> h_jslices, h_jlong;
   std::vector<uint16_t> h_jlanes;
@@ -170,6 +173,7 @@ void fill_params(const nd_b200_engine* e, KParams& P) {
   P.tiles = e->d_tiles; P.ntiles = e->ntiles; P.oidx = e->d_oidx; P.oedge = e->d_oedge;
   P.jslices = e->d_jslices; P.jlanes = e->d_jlanes; P.jnbr = e->d_jnbr; P.jent = e->d_jent; P.jebid = e->d_jebid;
   P.jlong = e->d_jlong; P.nslices = e->nslices; P.n_jag_blocks = e->n_jag_blocks;
+  P.halo = nullptr; P.halo_base = e->halo_base; P.wait_from = e->wait_from;
 }
 
 // ---- split mode launches --------------------------------------------------------------------------------
@@ -342,6 +346,20 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
       goff[(size_t)vid - 1] = e->gather_from_u ? (int)(h.state0 + i * h.dim) : (int)((h.row0 + i) * d->vdepth);
     }
   }
+  if (d->gather_offset) {
+    // multi-GPU packed halo: remote vertices are read from the halo buffer appended (logically) to the state vector
+    if (!e->gather_from_u) return fail(e, ND_B200_EUNSUPPORTED, "gather_offset needs StateMask vertices with one output");
+    if (d->gather_len < d->lastidx_dynamic || d->gather_len >= INT_MAX) return fail(e, ND_B200_EINVAL, "gather_len %lld outside [lastidx_dynamic, 2^31)", (long long)d->gather_len);
+    for (long long v = 0; v < d->nv; ++v) {
+      const long long o = d->gather_offset[v];
+      if (o < 0 || o >= d->gather_len) return fail(e, ND_B200_EINVAL, "gather_offset[%lld] = %lld outside [0, %lld)", v + 1, o, (long long)d->gather_len);
+      const int r = row_of_vertex[(size_t)v];
+      if (r >= e->row_begin && r < e->row_end && o != goff[(size_t)v]) return fail(e, ND_B200_EINVAL, "gather_offset of vertex %lld (an owned row) must be its own state offset", v + 1);
+      goff[(size_t)v] = (int)o;
+    }
+    e->halo_base = (int)d->lastidx_dynamic;
+    e->gather_len = d->gather_len;
+  }
 
   // ---- edge batches --------------------------------------------------------------------------
   bool any_epar = false;
@@ -449,6 +467,15 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
     }
   }
   if (keep) e->h_rowptr.assign(cnt.begin(), cnt.end());
+  // rows that read the halo ("boundary" rows); everything else can run while the halo is in flight
+  std::vector<char> row_remote((size_t)nrows_owned, 0);
+  if (d->gather_offset) {
+    for (long long r = 0; r < nrows_owned; ++r)
+      for (long long j = cnt[(size_t)r]; j < cnt[(size_t)r + 1]; ++j) {
+        const int o = h_nbr[(size_t)j] < 0 ? ~h_nbr[(size_t)j] : h_nbr[(size_t)j];
+        if (o >= e->halo_base) { row_remote[(size_t)r] = 1; break; }
+      }
+  }
 
   // get_buffers tables: gather offsets per edge in batch order
   if (keep) {
@@ -523,17 +550,47 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
       tiles.push_back(t);
     }
     e->ntiles = (int)tiles.size();
+    e->wait_from = 0;
+    if (d->gather_offset) {
+      // interior tiles first, tiles that read the halo last (each descriptor is self-contained)
+      auto reads_halo = [&](const int4& t) {
+        const int nr = (t.w < 0) ? 1 : ((t.w >> 16) & 0x1FF);
+        for (int r = 0; r < nr; ++r)
+          if (row_remote[(size_t)(t.x + r - e->row_begin)]) return true;
+        return false;
+      };
+      auto mid = std::stable_partition(tiles.begin(), tiles.end(), [&](const int4& t) { return !reads_halo(t); });
+      e->wait_from = (int)(mid - tiles.begin());
+    }
   }
   std::vector<EBDev> deb;
   for (const HostEB& h : e->heb) deb.push_back(EBDev{h.kind, h.coupling, h.pdim});
 
   // ---- jagged layout: 32-lane slices, column-major compacted entries (rhs_jag_kernel) ------------------------
-  // default evaluation mode; ND_B200_KERNEL=fused|split select the tile kernels.  A strictly sequential
-  // long_row_threshold beyond what one lane can hold (63 entries) needs the tile kernel.
-  e->jag = 1;
-  if (const char* s = getenv("ND_B200_KERNEL")) e->jag = !strcmp(s, "jag") ? 1 : ((!strcmp(s, "fused") || !strcmp(s, "split") || !strcmp(s, "v1")) ? 0 : 1);
+  // ND_B200_KERNEL=jag|fused|split overrides the automatic choice.  A strictly sequential long_row_threshold beyond
+  // what one lane can hold (63 entries) needs the tile kernel.
+  // Kernel family (measured on B200, profiles/r01c_sweep_fused_vs_jag.jsonl): the tile kernel wins whenever degrees
+  // vary (idle lanes in the jagged walk: ER cfg2 72 vs 76 us, BA cfg3 91 vs 148 us) or the graph is small (latency of the
+  // per-lane walk: cfg1); the jagged kernel wins on large regular-degree graphs (cfg4 grid: RK4 step 45 vs 55 us).
+  // auto = jagged iff lane utilisation of the walk >= 0.8 and there are enough rows to fill the machine.
+  {
+    long long sum_max = 0;
+    for (long long r = 0; r < nrows_owned; r += 32) {
+      long long m = 0;
+      for (long long q = r; q < std::min<long long>(r + 32, nrows_owned); ++q) m = std::max(m, cnt[(size_t)q + 1] - cnt[(size_t)q]);
+      sum_max += m;
+    }
+    const double util = sum_max > 0 ? (double)e->nentries / (32.0 * (double)sum_max) : 0.0;
+    e->jag = (util >= 0.8 && nrows_owned >= 65536) ? 1 : 0;
+  }
+  if (const char* s = getenv("ND_B200_KERNEL")) {
+    if (!strcmp(s, "jag")) e->jag = 1;
+    else if (!strcmp(s, "fused") || !strcmp(s, "split") || !strcmp(s, "v1")) e->jag = 0;
+  }
   if (e->split) e->jag = 0;
   if (d->long_row_threshold > 63 * 32) e->jag = 0;
+  e->jag_u = 2;
+  e->jag_wps = d->vdepth == 2 ? 32 : 48;   // spill-free register budgets, best measured
   std::vector<int4> jslices, jlong;
   std::vector<uint16_t> jlanes;
   std::vector<int> jnbr;
@@ -553,6 +610,10 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
     struct Lane { int rowrel, len, head; long long start; };
     std::vector<Lane> lanes;
     std::vector<std::pair<long long, int>> long_rows;   // (row, batch)
+    int jag_wait_from = 0;
+    const int nclasses = d->gather_offset ? 2 : 1;   // class 0: interior rows, class 1: rows that read the halo
+    for (int cls = 0; cls < nclasses; ++cls) {
+    if (cls == 1) jag_wait_from = (int)jslices.size();
     for (size_t b = 0; b < e->hvb.size(); ++b) {
       const HostVB& h = e->hvb[b];
       const long long lo = std::max<long long>(h.row0, e->row_begin), hi = std::min<long long>(h.row0 + h.count, e->row_end);
@@ -575,6 +636,7 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
         lanes.clear(); row0 = -1; maxparts = 1;
       };
       for (long long r = lo; r < hi; ++r) {
+        if (nclasses == 2 && row_remote[(size_t)(r - e->row_begin)] != cls) continue;
         const long long a = cnt[(size_t)(r - e->row_begin)], deg = cnt[(size_t)(r - e->row_begin) + 1] - a;
         const int nparts = (int)std::max<long long>(1, (deg + e->jsplit - 1) / e->jsplit);
         if (deg > block_thr || nparts > 32) { long_rows.push_back({r, (int)b}); continue; }
@@ -588,6 +650,8 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
       }
       flush();
     }
+    }
+    if (nclasses == 1) jag_wait_from = 0;
     for (const auto& lr : long_rows) {
       const long long a = cnt[(size_t)(lr.first - e->row_begin)], deg = cnt[(size_t)(lr.first - e->row_begin) + 1] - a;
       jlong.push_back(make_int4((int)order.size(), (int)lr.first, (int)deg, lr.second));
@@ -607,6 +671,7 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
     }
     e->host_only = (d->flags & ND_B200_FLAG_HOST_ONLY) != 0;
     if (e->host_only) { e->h_jslices = jslices; e->h_jlong = jlong; e->h_jlanes = jlanes; e->h_jorder = order; }
+    e->wait_from = jag_wait_from;
     e->nslices = (int)jslices.size();
     e->n_jag_blocks = (e->nslices + 3) / 4;   // BLOCK = 128: four slices per thread block
     e->n_jlong = (int)jlong.size();
@@ -655,15 +720,16 @@ int check_call(nd_b200_engine* e, const void* du, const void* u, const void* p) 
   return 0;
 }
 
-struct WaitSpec { const double* gsrc; const unsigned long long* flags; unsigned long long seq; int world; int* timeout; };
+struct WaitSpec { const double* halo; const unsigned long long* flags; unsigned long long seq; int world; int* timeout; };
 
 int rhs_impl(nd_b200_engine* e, double* du, const double* u, const double* p, double t, cudaStream_t st, int mode,
              double* aggbuf, const WaitSpec* w = nullptr) {
+  if (e->halo_base != INT_MAX && !w) return fail(e, ND_B200_EINVAL, "this engine reads a halo buffer (gather_offset): call it through nd_b200_rhs_exchange");
   KParams P;
   fill_params(e, P);
   P.u = u; P.p = p; P.du = du; P.mode = mode; P.aggbuf = aggbuf; P.t = t;
   P.gsrc = u;
-  if (w) { P.gsrc = w->gsrc; P.wait_flags = w->flags; P.wait_seq = w->seq; P.wait_world = w->world; P.wait_timeout = w->timeout; }
+  if (w) { P.halo = w->halo; P.wait_flags = w->flags; P.wait_seq = w->seq; P.wait_world = w->world; P.wait_timeout = w->timeout; }
   if (e->timing) {
     if (ensure_events(e, e->ev, e->ev_used + 2) || ensure_events(e, e->ev_pre, e->ev_pre_used + 2)) return ND_B200_ECUDA;
   }
@@ -785,6 +851,7 @@ int nd_b200_get_buffers(nd_b200_engine* e, double* o, double* aggbuf, const doub
   if (!e) return ND_B200_EINVAL;
   if (!u || (e->lastidx_p > 0 && !p)) return fail(e, ND_B200_EINVAL, "u or p is NULL");
   if (e->h_esrc_off.size() != e->heb.size()) return fail(e, ND_B200_EUNSUPPORTED, "engine was created with ND_B200_FLAG_NO_EXPORT");
+  if (e->halo_base != INT_MAX || e->host_only) return fail(e, ND_B200_EUNSUPPORTED, "nd_b200_get_buffers on a halo / host-only engine");
   cudaStream_t st = (cudaStream_t)stream;
   const double* gsrc = u;
   if (!e->gather_from_u) {
@@ -822,7 +889,7 @@ int nd_b200_get_buffers(nd_b200_engine* e, double* o, double* aggbuf, const doub
 
 int nd_b200_rk4(nd_b200_engine* e, double* u, const double* p, double t0, double dt, int64_t nsteps, void* stream) {
   if (int rc = check_call(e, u, u, p)) return rc;
-  if (e->row_end - e->row_begin != e->nrows_total) return fail(e, ND_B200_EUNSUPPORTED, "nd_b200_rk4 on a partitioned engine: drive the stages from the host (halo exchange between stages)");
+  if (e->row_end - e->row_begin != e->nrows_total || e->halo_base != INT_MAX) return fail(e, ND_B200_EUNSUPPORTED, "nd_b200_rk4 on a partitioned engine: drive the stages from the host (halo exchange between stages)");
   if (nsteps <= 0) return ND_B200_OK;
   CUDA_TRY(e, cudaSetDevice(e->device));
   cudaStream_t st = (cudaStream_t)stream;
@@ -879,9 +946,10 @@ int nd_b200_export_tables(const nd_b200_engine* e, int64_t* rowptr, int64_t* nbr
   return ND_B200_OK;
 }
 
-int nd_b200_export_jag_sizes(const nd_b200_engine* e, int64_t sizes[4]) {
+int nd_b200_export_jag_sizes(const nd_b200_engine* e, int64_t sizes[6]) {
   if (!e || !sizes) return ND_B200_EINVAL;
   sizes[0] = e->jag ? (int64_t)e->nslices : -1; sizes[1] = e->n_jlong; sizes[2] = e->jsplit; sizes[3] = (int64_t)e->h_jorder.size();
+  sizes[4] = e->wait_from; sizes[5] = e->halo_base == INT_MAX ? -1 : e->gather_len - e->lastidx_dynamic;
   return ND_B200_OK;
 }
 
@@ -936,17 +1004,24 @@ void nd_b200_host_free(void* q) { if (q) cudaFreeHost(q); }
 }  // extern "C"
 
 // ---- multi-GPU exchange object ------------------------------------------------------------------------------------------
+// Packed halo over NVLink peer memory.  Every rank owns ONE device allocation [halo parity 0 | halo parity 1 | flags]
+// that the peers map through CUDA IPC.  halo = the outputs of exactly the remote vertices this rank's rows read, grouped
+// by owner rank (ascending) and sorted by state offset inside a group; the engine was built with gather offsets that
+// point into it (nd_b200_desc.gather_offset).
 struct nd_b200_comm {
   int device = 0, rank = 0, world = 1;
-  long long nstates = 0;
-  size_t replica_bytes = 0;               // bytes of ONE replica, rounded up to 256
+  long long halo_len = 0;                 // doubles in this rank's halo buffer
+  size_t halo_bytes = 0;                  // bytes of ONE parity of the LARGEST halo among the ranks (same layout everywhere), 256-aligned
   unsigned char* base[HALO_MAX_WORLD] = {nullptr};   // [r]: rank r's shared block (own: cudaMalloc, peers: IPC mapping)
+  int* d_send_idx[HALO_MAX_WORLD] = {nullptr};       // [r]: state offsets of the outputs rank r reads from this rank
+  long long send_n[HALO_MAX_WORLD] = {0};
+  long long dst_off[HALO_MAX_WORLD] = {0};           // [r]: where this rank's block starts inside rank r's halo
   unsigned int* d_done = nullptr;
   int* d_timeout = nullptr;
   unsigned long long seq = 0;
   std::string err;
-  double* replica(int r, int parity) const { return reinterpret_cast<double*>(base[r] + (size_t)parity * replica_bytes); }
-  unsigned long long* flags(int r) const { return reinterpret_cast<unsigned long long*>(base[r] + 2 * replica_bytes); }
+  double* halo(int r, int parity) const { return reinterpret_cast<double*>(base[r] + (size_t)parity * halo_bytes); }
+  unsigned long long* flags(int r) const { return reinterpret_cast<unsigned long long*>(base[r] + 2 * halo_bytes); }
 };
 
 namespace {
@@ -968,14 +1043,15 @@ int cfail(nd_b200_comm* c, int code, const char* fmt, ...) {
 
 extern "C" {
 
-int nd_b200_comm_create(int32_t device, int32_t rank, int32_t world, int64_t nstates, nd_b200_comm** out) {
-  if (!out || world < 1 || world > HALO_MAX_WORLD || rank < 0 || rank >= world || nstates <= 0)
-    return cfail(nullptr, ND_B200_EINVAL, "nd_b200_comm_create: bad arguments (world must be 1..%d)", HALO_MAX_WORLD);
+int nd_b200_comm_create(int32_t device, int32_t rank, int32_t world, int64_t halo_len, int64_t max_halo_len,
+                        nd_b200_comm** out) {
+  if (!out || world < 1 || world > HALO_MAX_WORLD || rank < 0 || rank >= world || halo_len < 0 || max_halo_len < halo_len)
+    return cfail(nullptr, ND_B200_EINVAL, "nd_b200_comm_create: bad arguments (world must be 1..%d, 0 <= halo_len <= max_halo_len)", HALO_MAX_WORLD);
   nd_b200_comm* c = new (std::nothrow) nd_b200_comm();
   if (!c) return cfail(nullptr, ND_B200_ENOMEM, "out of host memory");
-  c->device = device; c->rank = rank; c->world = world; c->nstates = nstates;
-  c->replica_bytes = ((size_t)nstates * sizeof(double) + 255) / 256 * 256;
-  const size_t total = 2 * c->replica_bytes + 256;
+  c->device = device; c->rank = rank; c->world = world; c->halo_len = halo_len;
+  c->halo_bytes = ((size_t)std::max<int64_t>(max_halo_len, 1) * sizeof(double) + 255) / 256 * 256;
+  const size_t total = 2 * c->halo_bytes + 256;
   cudaError_t ce = cudaSetDevice(device);
   if (ce == cudaSuccess) ce = cudaMalloc((void**)&c->base[rank], total);
   if (ce == cudaSuccess) ce = cudaMemset(c->base[rank], 0, total);
@@ -1016,6 +1092,24 @@ int nd_b200_comm_open_peer(nd_b200_comm* c, int32_t peer, const void* handle) {
   return ND_B200_OK;
 }
 
+int nd_b200_comm_set_send(nd_b200_comm* c, int32_t peer, const int64_t* state_offsets, int64_t n, int64_t dst_offset) {
+  if (!c || peer < 0 || peer >= c->world || peer == c->rank || n < 0 || dst_offset < 0 || (n > 0 && !state_offsets))
+    return cfail(c, ND_B200_EINVAL, "nd_b200_comm_set_send: bad arguments");
+  COMM_TRY(c, cudaSetDevice(c->device));
+  cudaFree(c->d_send_idx[peer]);
+  c->d_send_idx[peer] = nullptr;
+  c->send_n[peer] = n; c->dst_off[peer] = dst_offset;
+  if (n == 0) return ND_B200_OK;
+  std::vector<int> idx((size_t)n);
+  for (int64_t i = 0; i < n; ++i) {
+    if (state_offsets[i] < 0 || state_offsets[i] >= INT_MAX) return cfail(c, ND_B200_EINVAL, "send offset %lld out of range", (long long)state_offsets[i]);
+    idx[(size_t)i] = (int)state_offsets[i];
+  }
+  COMM_TRY(c, cudaMalloc((void**)&c->d_send_idx[peer], sizeof(int) * (size_t)n));
+  COMM_TRY(c, cudaMemcpy(c->d_send_idx[peer], idx.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice));
+  return ND_B200_OK;
+}
+
 int nd_b200_comm_status(nd_b200_comm* c, int32_t* timed_out) {
   if (!c || !timed_out) return ND_B200_EINVAL;
   int v = 0;
@@ -1032,6 +1126,7 @@ void nd_b200_comm_destroy(nd_b200_comm* c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   for (int r = 0; r < c->world; ++r) {
+    cudaFree(c->d_send_idx[r]);
     if (!c->base[r]) continue;
     if (r == c->rank) cudaFree(c->base[r]); else cudaIpcCloseMemHandle(c->base[r]);
   }
@@ -1043,9 +1138,9 @@ int nd_b200_rhs_exchange(nd_b200_engine* e, nd_b200_comm* c, double* du, const d
                          void* stream) {
   if (int rc = check_call(e, du, u, p)) return rc;
   if (!c) return fail(e, ND_B200_EINVAL, "nd_b200_rhs_exchange: comm is NULL");
-  if (!e->gather_from_u || e->split) return fail(e, ND_B200_EUNSUPPORTED, "nd_b200_rhs_exchange needs StateMask vertices and the fused kernel");
-  if (c->nstates != e->lastidx_dynamic) return fail(e, ND_B200_EINVAL, "comm was created for %lld states, the network has %lld", c->nstates, e->lastidx_dynamic);
-  if (e->own_segs.size() > (size_t)HALO_MAX_SEGS) return fail(e, ND_B200_EUNSUPPORTED, "more than %d owned state ranges", HALO_MAX_SEGS);
+  if (!e->gather_from_u || e->split) return fail(e, ND_B200_EUNSUPPORTED, "nd_b200_rhs_exchange needs StateMask vertices and a fused kernel");
+  if (e->halo_base == INT_MAX) return fail(e, ND_B200_EINVAL, "the engine was created without gather_offset (no halo layout)");
+  if (e->gather_len - e->lastidx_dynamic != c->halo_len) return fail(e, ND_B200_EINVAL, "comm halo holds %lld outputs, the engine expects %lld", c->halo_len, e->gather_len - e->lastidx_dynamic);
   for (int r = 0; r < c->world; ++r)
     if (!c->base[r]) return fail(e, ND_B200_EINVAL, "peer %d has not been opened", r);
   cudaStream_t st = (cudaStream_t)stream;
@@ -1053,16 +1148,18 @@ int nd_b200_rhs_exchange(nd_b200_engine* e, nd_b200_comm* c, double* du, const d
   const int parity = (int)(seq & 1ull);
   HaloParams H;
   memset(&H, 0, sizeof H);
-  for (int r = 0; r < c->world; ++r) { H.replica[r] = c->replica(r, parity); H.flags[r] = c->flags(r); }
   long long total = 0;
-  H.nsegs = (int)e->own_segs.size();
-  for (int s = 0; s < H.nsegs; ++s) { H.seg_start[s] = e->own_segs[(size_t)s].first; H.seg_len[s] = e->own_segs[(size_t)s].second; total += H.seg_len[s]; }
+  for (int r = 0; r < c->world; ++r) {
+    H.halo[r] = c->halo(r, parity); H.flags[r] = c->flags(r);
+    H.send_idx[r] = c->d_send_idx[r]; H.send_n[r] = c->send_n[r]; H.dst_off[r] = c->dst_off[r];
+    total += c->send_n[r];
+  }
   H.world = c->world; H.rank = c->rank; H.seq = seq; H.src = u; H.done_counter = c->d_done;
-  const int grid = (int)std::max<long long>(1, std::min<long long>(148, (total / 2 + 255) / 256));
+  const int grid = (int)std::max<long long>(1, std::min<long long>(148 * 2, (total + 1023) / 1024));
   halo_publish_kernel<<<grid, 256, 0, st>>>(H);
   CUDA_TRY(e, cudaGetLastError());
   e->launches++;
-  WaitSpec w{c->replica(c->rank, parity), c->flags(c->rank), seq, c->world, c->d_timeout};
+  WaitSpec w{c->halo(c->rank, parity), c->flags(c->rank), seq, c->world, c->d_timeout};
   return rhs_impl(e, du, u, p, t, st, MODE_DU, nullptr, &w);
 }
 

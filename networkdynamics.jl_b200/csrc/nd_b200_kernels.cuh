@@ -83,7 +83,7 @@ struct KParams {
   // (the ones that read remote outputs) wait for the arrival flags, interior slices run while the halo is in flight
   const double* halo;
   int halo_base;
-  int wait_from_slice;
+  int wait_from;                       // first slice (jagged) / tile (tile kernel) that reads the halo
 };
 
 // parameters of the edge pass (split mode)
@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(BLOCK, (fused_warps_per_sm(EK) * 32) / BLOCK) 
   const int ne = is_long ? d.z : (d.w & 0xFFFF);
   const VBDev B = P.vb[(d.w >> 25) & 0x3F];
   const int coupling0 = P.n_eb > 0 ? P.eb[0].coupling : 0;
-  halo_wait(P);   // multi-GPU only: peers' states have landed in the local replica
+  if ((int)blockIdx.x >= P.wait_from) halo_wait(P);   // multi-GPU only: this tile reads the halo (block-uniform)
 
   // ---------------- long row: whole block reduces one row with a fixed-shape tree -----------------
   if (is_long) {
@@ -395,8 +395,9 @@ __global__ void __launch_bounds__(BLOCK, (fused_warps_per_sm(EK) * 32) / BLOCK) 
       const int side = nb < 0;
       nb = side ? ~nb : nb;
       double xn[VD];
+      const double* gp = gather_ptr(P, nb);
 #pragma unroll
-      for (int k = 0; k < VD; ++k) xn[k] = P.gsrc[(long long)nb + k];
+      for (int k = 0; k < VD; ++k) xn[k] = gp[k];
       const double* pe = P.p;
       if constexpr (PE > 0) pe = P.p + P.epar[e0 + jj];
       int kind = EK, coupling = coupling0;
@@ -467,11 +468,12 @@ __global__ void __launch_bounds__(BLOCK, (fused_warps_per_sm(EK) * 32) / BLOCK) 
 #pragma unroll
     for (int q = 0; q < VD; ++q) xn[k][q] = 0.0;
     if (jj < ne) {
+      const double* gp = gather_ptr(P, off);
       if constexpr (VD == 2) {
-        const double2 t2 = *reinterpret_cast<const double2*>(P.gsrc + off);
+        const double2 t2 = *reinterpret_cast<const double2*>(gp);
         xn[k][0] = t2.x; xn[k][1] = t2.y;
       } else {
-        xn[k][0] = P.gsrc[off];
+        xn[k][0] = gp[0];
       }
     }
   }
@@ -810,7 +812,7 @@ __global__ void __launch_bounds__(BLOCK, (WPS * 32) / BLOCK) rhs_jag_kernel(cons
   const int lane = threadIdx.x & 31;
   const int sl = blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5);
   if (sl >= P.nslices) return;           // warp-uniform
-  if (sl >= P.wait_from_slice) halo_wait_warp(P);   // multi-GPU only: this slice reads the halo
+  if (sl >= P.wait_from) halo_wait_warp(P);   // multi-GPU only: this slice reads the halo
   const int4 S = __ldg(&P.jslices[sl]);
   const unsigned desc = __ldg(&P.jlanes[(long long)sl * 32 + lane]);
   const int len = desc & 63;

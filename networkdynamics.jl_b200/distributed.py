@@ -3,8 +3,10 @@
 The reference has no multi-device path; this follows SURVEY.md 8(e):
   * aggregation-slot rows are split into `world` CONTIGUOUS ranges of (nearly) equal directed-entry count;
   * rank r owns the states / du entries of its rows and evaluates only those rows (engine `row_range`);
-  * per RHS one exchange step: every rank publishes the states of its rows (the vertex outputs are state copies
-    or functions of the owner's states) so that all ranks hold the full state vector the gathers read from.
+  * per RHS one exchange step.  "p2p" (default on GPUs): every rank packs, for each peer, exactly the vertex outputs
+    that peer's rows read (the boundary outputs of cut edges, `halo_plan`) and stores them straight into the peer's
+    halo buffer over NVLink; rows that read no remote output are evaluated while the halo is in flight.
+    "nccl" (and the gloo CPU tests): owned state ranges are all-gathered into every rank's copy of `u`.
 Accumulation order per row is untouched (a row is never split across ranks), so `du` is identical to the
 single-GPU result, bit for bit.
 
@@ -77,6 +79,57 @@ def state_segments(vertexbatches: Sequence[ComponentBatch], r0: int, r1: int) ->
     return segs
 
 
+def owner_of_rows(rows: np.ndarray, row_ranges: Sequence[Tuple[int, int]]) -> np.ndarray:
+    """rank that owns each row (row ranges are contiguous and ascending)"""
+    ends = np.array([b for _, b in row_ranges], dtype=np.int64)
+    return np.searchsorted(ends, rows, side="right")
+
+
+def halo_plan(im: IndexManager, edgebatches: Sequence[ComponentBatch], row_ranges: Sequence[Tuple[int, int]], rank: int):
+    """Who reads what across the cut ("each rank sends the outputs of its boundary vertices needed by
+    rank q to q").  Needs vertices whose single output is their first state (StateMask), so outputs live in `u`.
+
+    need[r] = the remote vertices read by the rows of rank r, ordered by (owner rank, state offset).  Rank r's halo
+    buffer holds their outputs in that order, logically appended to the state vector: position lastidx_dynamic + k.
+    Returns for `rank`: gather_offset (per vertex, what nd_b200_desc.gather_offset takes), gather_len, halo_lens (per
+    rank), sends = {peer: (state offsets this rank packs for peer, start position inside peer's halo)}, and
+    need (vertex ids, 0-based, in halo order) for tests."""
+    world = len(row_ranges)
+    nv = im.nv
+    vowner = owner_of_rows(row_of_vertex(im), row_ranges)
+    goff = np.asarray(im.v_data, dtype=np.int64) - 1
+    needed = np.zeros((world, nv), dtype=bool)
+    for b in edgebatches:
+        e = np.asarray(b.indices, dtype=np.int64) - 1
+        s, t = np.asarray(im.edge_src)[e] - 1, np.asarray(im.edge_dst)[e] - 1
+        needed[vowner[t], s] = True                   # the dst row reads the src vertex's output
+        if b.model.outdim_src > 0:
+            needed[vowner[s], t] = True               # ... and the src row (wrapper output) reads the dst vertex's
+    needed[vowner, np.arange(nv)] = False             # own vertices are read from u
+    vorder = np.lexsort((goff, vowner))
+    need = [vorder[needed[r][vorder]] for r in range(world)]
+    counts = np.array([np.bincount(vowner[n], minlength=world) for n in need], dtype=np.int64)   # [reader, owner]
+    starts = np.concatenate([np.zeros((world, 1), dtype=np.int64), np.cumsum(counts, axis=1)], axis=1)
+    halo_lens = [int(n.size) for n in need]
+    nstates = int(im.lastidx_dynamic)
+    gather_offset = goff.copy()
+    gather_offset[need[rank]] = nstates + np.arange(need[rank].size, dtype=np.int64)
+    sends = {}
+    for r in range(world):
+        if r == rank:
+            continue
+        mine = need[r][vowner[need[r]] == rank]
+        sends[r] = (np.ascontiguousarray(goff[mine]), int(starts[r, rank]))
+    return dict(gather_offset=gather_offset, gather_len=nstates + halo_lens[rank], halo_lens=halo_lens, sends=sends,
+                need=need[rank], recv_counts=counts[rank], vowner=vowner)
+
+
+def statemask_outputs(vertexbatches: Sequence[ComponentBatch], vdepth: int) -> bool:
+    """True when every vertex output is its first state (the gather source is the state vector itself)"""
+    from . import _cabi
+    return vdepth == 1 and all(b.model.kernel_kind() not in (None, _cabi.V_SWING_DQ) for b in vertexbatches)
+
+
 def _uniform_allgather_layout(segments_by_rank, n) -> bool:
     """True when rank r owns exactly [r*len, (r+1)*len) and the ranges tile the whole vector."""
     world = len(segments_by_rank)
@@ -126,18 +179,34 @@ class PartitionedNetwork:
         self.entry_counts = row_entry_counts(probe.im, probe.layer.edgebatches)
         self.row_ranges = partition_rows(self.entry_counts, world)
         self.segments = [state_segments(probe.vertexbatches, a, b) for a, b in self.row_ranges]
-        self.nw = Network(g, vertexm, edgem, execution=B200Execution(),
-                          aggregator=B200Aggregator("+", device=device, row_range=self.row_ranges[rank],
-                                                    long_row_threshold=long_row_threshold, keep_tables=False))
         self.comm = None
         self.exchange_kind = "nccl"
-        if exchange in ("p2p", "auto") and world > 1:
+        self.plan = None
+
+        def engine(plan):
+            return Network(g, vertexm, edgem, execution=B200Execution(),
+                           aggregator=B200Aggregator("+", device=device, row_range=self.row_ranges[rank],
+                                                     long_row_threshold=long_row_threshold, keep_tables=False,
+                                                     gather_offset=None if plan is None else plan["gather_offset"],
+                                                     gather_len=0 if plan is None else plan["gather_len"]))
+
+        want_p2p = exchange in ("p2p", "auto") and world > 1
+        if want_p2p and not statemask_outputs(probe.vertexbatches, probe.im.vdepth):
+            if exchange == "p2p":
+                raise RuntimeError("p2p exchange needs StateMask vertices (the gather source must be the state vector)")
+            want_p2p = False
+        if want_p2p:
+            self.plan = halo_plan(probe.im, probe.layer.edgebatches, self.row_ranges, rank)
+            self.nw = engine(self.plan)
             try:
                 self._setup_p2p()
                 self.exchange_kind = "p2p"
             except Exception:
                 if exchange == "p2p":
                     raise
+                self.plan, self.nw = None, engine(None)     # every rank fails together (see _setup_p2p): NCCL path
+        else:
+            self.nw = engine(None)
 
     # -- NVLink peer-memory exchange ----------------------------------------------------------------------------
     def _setup_p2p(self):
@@ -145,29 +214,33 @@ class PartitionedNetwork:
         import torch.distributed as dist
         from . import _cabi
         L = _cabi.lib()
-        if not self.nw.engine_sizes()["gather_from_u"]:
-            raise RuntimeError("p2p exchange needs StateMask vertices (the gather source must be the state vector)")
+        plan = self.plan
         h = C.c_void_p()
         dev = self.nw.layer.aggregator.device
-        rc = L.nd_b200_comm_create(dev, self.rank, self.world, self.nw.dim(), C.byref(h))
+        rc = L.nd_b200_comm_create(dev, self.rank, self.world, plan["halo_lens"][self.rank], max(plan["halo_lens"]), C.byref(h))
         ok = rc == 0
         handle = C.create_string_buffer(_cabi.IPC_HANDLE_BYTES)
         if ok:
             ok = L.nd_b200_comm_export(h, handle) == 0
+        if ok:
+            for peer, (offs, start) in plan["sends"].items():
+                offs = np.ascontiguousarray(offs, dtype=np.int64)
+                ok = ok and L.nd_b200_comm_set_send(h, peer, offs.ctypes.data_as(_cabi.i64p), offs.size, start) == 0
         # every rank must take the same branch: agree on success before mapping anything
         flags = [None] * self.world
         dist.all_gather_object(flags, (bool(ok), handle.raw), group=self.group)
         if not all(f[0] for f in flags):
+            msg = (L.nd_b200_comm_last_error(h) if h else L.nd_b200_comm_last_error(None)).decode()
             if h:
                 L.nd_b200_comm_destroy(h)
-            raise RuntimeError("nd_b200_comm_create failed on some rank: " + L.nd_b200_comm_last_error(None).decode())
+            raise RuntimeError("nd_b200_comm setup failed on some rank: " + msg)
         opened = all(L.nd_b200_comm_open_peer(h, r, flags[r][1]) == 0 for r in range(self.world))
         res = [None] * self.world
         dist.all_gather_object(res, bool(opened), group=self.group)
         if not all(res):
             msg = L.nd_b200_comm_last_error(h).decode()
             L.nd_b200_comm_destroy(h)
-            raise RuntimeError("CUDA IPC mapping of a peer replica failed: " + msg)
+            raise RuntimeError("CUDA IPC mapping of a peer halo buffer failed: " + msg)
         self.comm = h
         dist.barrier(group=self.group)
 

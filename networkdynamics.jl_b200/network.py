@@ -175,13 +175,15 @@ class B200Aggregator:
     (read as `nw.layer.aggregator.f`, test/testutils.jl:50)."""
 
     def __init__(self, f="+", *, device: Optional[int] = None, row_range=None, long_row_threshold: int = 0,
-                 keep_tables: bool = True, host_only: bool = False):
+                 keep_tables: bool = True, host_only: bool = False, gather_offset=None, gather_len: int = 0):
         if f not in ("+", sum, np.add) and getattr(f, "__name__", "") != "add":
             raise ArgumentError("B200Aggregator only supports + as the reducer (no CPU fallback for others)")
         self.f = "+"
         # host_only: build the engine's tables without touching a device (layout tests); such a network cannot be called
+        # gather_offset / gather_len: multi-GPU packed halo layout (nd_b200_desc.gather_offset), see distributed.py
         self._opts = dict(device=device, row_range=row_range, long_row_threshold=long_row_threshold,
-                          keep_tables=keep_tables, host_only=host_only)
+                          keep_tables=keep_tables, host_only=host_only, gather_offset=gather_offset,
+                          gather_len=gather_len)
         self.handle = None
         self._keep = None
 
@@ -231,7 +233,15 @@ class B200Aggregator:
                           len(edgebatches), vb, eb, im.lastidx_dynamic, im.lastidx_p, im.lastidx_out,
                           im.lastidx_aggr, int(rr[0]), int(rr[1]), int(self._opts["long_row_threshold"]),
                           (0 if self._opts["keep_tables"] else _cabi.FLAG_NO_EXPORT)
-                          | (_cabi.FLAG_HOST_ONLY if self._opts["host_only"] else 0))
+                          | (_cabi.FLAG_HOST_ONLY if self._opts["host_only"] else 0),
+                          None, 0)
+        if self._opts["gather_offset"] is not None:
+            go = np.ascontiguousarray(self._opts["gather_offset"], dtype=np.int64)
+            if go.size != im.nv:
+                raise ArgumentError("gather_offset needs one entry per vertex")
+            keep.append(go)
+            desc.gather_offset = go.ctypes.data_as(_cabi.i64p)
+            desc.gather_len = int(self._opts["gather_len"])
         h = C.c_void_p()
         rc = L.nd_b200_create(C.byref(desc), C.byref(h))
         if rc != _cabi.OK:
@@ -428,7 +438,7 @@ class Network:
 
     def kernel_name(self) -> str:
         """name of the kernel family that evaluates this network (rhs_jag_kernel unless ND_B200_KERNEL selects a tile kernel)"""
-        sz = np.zeros(4, dtype=np.int64)
+        sz = np.zeros(6, dtype=np.int64)
         self._L.nd_b200_export_jag_sizes(self.handle, sz.ctypes.data_as(_cabi.i64p))
         if sz[0] >= 0:
             return "rhs_jag_kernel"
@@ -437,11 +447,11 @@ class Network:
     def export_jag(self):
         """the jagged device layout of the default kernel (host_only engines): slices[n,4], lanes[n,32], longs[m,4],
         order[entries] -- see include/nd_b200.h"""
-        sz = np.zeros(4, dtype=np.int64)
+        sz = np.zeros(6, dtype=np.int64)
         rc = self._L.nd_b200_export_jag_sizes(self.handle, sz.ctypes.data_as(_cabi.i64p))
         if rc:
             self._fail(rc)
-        ns, nl, split, ne = (int(v) for v in sz)
+        ns, nl, split, ne, wait_from, halo_len = (int(v) for v in sz)
         if ns < 0:
             raise ArgumentError("engine does not use the jagged layout")
         slices = np.zeros((max(ns, 1), 4), dtype=np.int32)
@@ -453,7 +463,8 @@ class Network:
                                         order.ctypes.data_as(_cabi.i32p))
         if rc:
             self._fail(rc)
-        return dict(slices=slices[:ns], lanes=lanes[:ns], longs=longs[:nl], order=order[:ne], split=split)
+        return dict(slices=slices[:ns], lanes=lanes[:ns], longs=longs[:nl], order=order[:ne], split=split,
+                    wait_from=wait_from, halo_len=halo_len)
 
     def launch_count(self) -> int:
         return int(self._L.nd_b200_launch_count(self.handle))

