@@ -71,6 +71,13 @@ struct nd_b200_engine {
   int* d_jnbr = nullptr;
   int2* d_jent = nullptr;
   uint8_t* d_jebid = nullptr;
+  // host-buffer pipeline (nd_b200_rhs_host): per thread block of the launch grid, the end of the parameter range it
+  // reads and the rows it writes; launch_nblk >= 0 restricts a launch to blocks [P.blk_off, P.blk_off + launch_nblk)
+  std::vector<int> blk_pmax, blk_rmin, blk_rmax;
+  bool blk_rows_monotone = false;
+  int launch_nblk = -1;
+  cudaStream_t s_copy = nullptr, s_d2h = nullptr;
+  std::vector<cudaEvent_t> ev_pipe;
   int halo_base = INT_MAX;    // gather offsets >= halo_base address the halo buffer (multi-GPU packed halo)
   long long gather_len = 0;
   int wait_from = 0;          // first tile / slice that reads the halo
@@ -213,11 +220,12 @@ cudaError_t launch_row_pass_t(const nd_b200_engine* e, const KParams& P, cudaStr
 
 template <int VD, int ED, int EK, int PE>
 cudaError_t launch_shape(const nd_b200_engine* e, const KParams& P, cudaStream_t st) {
-  if (e->nblocks == 0) return cudaSuccess;
-  if (e->block == 256 && e->ept == 8) rhs_fused_kernel<VD, ED, EK, PE, 256, 8><<<e->nblocks, 256, 0, st>>>(P);
-  else if (e->block == 256 && e->ept == 4) rhs_fused_kernel<VD, ED, EK, PE, 256, 4><<<e->nblocks, 256, 0, st>>>(P);
-  else if (e->block == 128 && e->ept == 8) rhs_fused_kernel<VD, ED, EK, PE, 128, 8><<<e->nblocks, 128, 0, st>>>(P);
-  else if (e->block == 128 && e->ept == 4) rhs_fused_kernel<VD, ED, EK, PE, 128, 4><<<e->nblocks, 128, 0, st>>>(P);
+  const int grid = e->launch_nblk >= 0 ? e->launch_nblk : e->nblocks;
+  if (grid == 0) return cudaSuccess;
+  if (e->block == 256 && e->ept == 8) rhs_fused_kernel<VD, ED, EK, PE, 256, 8><<<grid, 256, 0, st>>>(P);
+  else if (e->block == 256 && e->ept == 4) rhs_fused_kernel<VD, ED, EK, PE, 256, 4><<<grid, 256, 0, st>>>(P);
+  else if (e->block == 128 && e->ept == 8) rhs_fused_kernel<VD, ED, EK, PE, 128, 8><<<grid, 128, 0, st>>>(P);
+  else if (e->block == 128 && e->ept == 4) rhs_fused_kernel<VD, ED, EK, PE, 128, 4><<<grid, 128, 0, st>>>(P);
   else return cudaErrorInvalidConfiguration;
   return cudaGetLastError();
 }
@@ -226,7 +234,7 @@ cudaError_t launch_shape(const nd_b200_engine* e, const KParams& P, cudaStream_t
 template <int VD, int ED, int EK, int PE, int U>
 cudaError_t launch_jag_u(const nd_b200_engine* e, const KParams& P, cudaStream_t st) {
   constexpr int BLOCK = 128;
-  const int grid = e->n_jag_blocks + e->n_jlong;
+  const int grid = e->launch_nblk >= 0 ? e->launch_nblk : e->n_jag_blocks + e->n_jlong;
   if (grid == 0) return cudaSuccess;
   const int wps = e->jag_wps > 0 ? e->jag_wps : jag_warps_per_sm_default(EK);
   if (wps >= 64) rhs_jag_kernel<VD, ED, EK, PE, BLOCK, U, 64><<<grid, BLOCK, 0, st>>>(P);
@@ -467,6 +475,16 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
     }
   }
   if (keep) e->h_rowptr.assign(cnt.begin(), cnt.end());
+  // end of the parameter range an entry / a row reads (host-buffer pipeline, nd_b200_rhs_host)
+  auto entry_pend = [&](long long j) -> int {
+    if (!any_epar) return 0;
+    const int pd = h_ebid.empty() ? e->heb[0].pdim : e->heb[h_ebid[(size_t)j]].pdim;
+    return pd > 0 ? h_epar[(size_t)j] + pd : 0;
+  };
+  auto row_pend = [&](long long r, size_t b) -> int {
+    const HostVB& h = e->hvb[b];
+    return h.pdim > 0 ? (int)(h.p0 + (r - h.row0 + 1) * h.pdim) : 0;
+  };
   // rows that read the halo ("boundary" rows); everything else can run while the halo is in flight
   std::vector<char> row_remote((size_t)nrows_owned, 0);
   if (d->gather_offset) {
@@ -561,6 +579,16 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
       };
       auto mid = std::stable_partition(tiles.begin(), tiles.end(), [&](const int4& t) { return !reads_halo(t); });
       e->wait_from = (int)(mid - tiles.begin());
+    }
+    e->blk_pmax.assign(tiles.size(), 0); e->blk_rmin.assign(tiles.size(), 0); e->blk_rmax.assign(tiles.size(), 0);
+    for (size_t k = 0; k < tiles.size(); ++k) {
+      const int4& t = tiles[k];
+      const bool lg = t.w < 0;
+      const int nr = lg ? 1 : ((t.w >> 16) & 0x1FF), ne = lg ? t.z : (t.w & 0xFFFF);
+      const size_t b = (size_t)((t.w >> 25) & 0x3F);
+      int pm = row_pend(t.x + nr - 1, b);
+      for (long long j = t.y; j < (long long)t.y + ne; ++j) pm = std::max(pm, entry_pend(j));
+      e->blk_pmax[k] = pm; e->blk_rmin[k] = t.x; e->blk_rmax[k] = t.x + nr - 1;
     }
   }
   std::vector<EBDev> deb;
@@ -671,6 +699,31 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
     }
     e->host_only = (d->flags & ND_B200_FLAG_HOST_ONLY) != 0;
     if (e->host_only) { e->h_jslices = jslices; e->h_jlong = jlong; e->h_jlanes = jlanes; e->h_jorder = order; }
+    {
+      const size_t nb = (jslices.size() + 3) / 4;
+      e->blk_pmax.assign(nb + jlong.size(), 0); e->blk_rmin.assign(nb + jlong.size(), INT_MAX); e->blk_rmax.assign(nb + jlong.size(), -1);
+      for (size_t sidx = 0; sidx < jslices.size(); ++sidx) {
+        const size_t k = sidx / 4;
+        const int4& S = jslices[sidx];
+        const long long eend = sidx + 1 < jslices.size() ? jslices[sidx + 1].x : (jlong.empty() ? (long long)order.size() : jlong[0].x);
+        int pm = e->blk_pmax[k];
+        for (long long q = S.x; q < eend; ++q) pm = std::max(pm, entry_pend(order[(size_t)q]));
+        for (int l = 0; l < 32; ++l) {
+          const uint16_t v = jlanes[sidx * 32 + (size_t)l];
+          if (!((v >> 12) & 1)) break;
+          const int r = S.y + ((v >> 6) & 31);
+          e->blk_rmin[k] = std::min(e->blk_rmin[k], r); e->blk_rmax[k] = std::max(e->blk_rmax[k], r);
+          pm = std::max(pm, row_pend(r, (size_t)S.z));
+        }
+        e->blk_pmax[k] = pm;
+      }
+      for (size_t q = 0; q < jlong.size(); ++q) {
+        const int4& Lr = jlong[q];
+        int pm = row_pend(Lr.y, (size_t)Lr.w);
+        for (long long j = Lr.x; j < (long long)Lr.x + Lr.z; ++j) pm = std::max(pm, entry_pend(order[(size_t)j]));
+        e->blk_pmax[nb + q] = pm; e->blk_rmin[nb + q] = Lr.y; e->blk_rmax[nb + q] = Lr.y;
+      }
+    }
     e->wait_from = jag_wait_from;
     e->nslices = (int)jslices.size();
     e->n_jag_blocks = (e->nslices + 3) / 4;   // BLOCK = 128: four slices per thread block
@@ -679,6 +732,9 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
     e->n_long = e->n_jlong;
   }
 
+  e->blk_rows_monotone = true;
+  for (size_t k = 0; k + 1 < e->blk_rmin.size(); ++k)
+    if (e->blk_rmin[k + 1] <= e->blk_rmax[k]) { e->blk_rows_monotone = false; break; }
   if (d->flags & ND_B200_FLAG_HOST_ONLY) { e->host_only = true; return ND_B200_OK; }
   CUDA_TRY(e, cudaSetDevice(e->device));
   if (e->jag) {
@@ -813,6 +869,9 @@ void nd_b200_destroy(nd_b200_engine* e) {
   cudaFree(e->d_tmpA); cudaFree(e->d_tmpB); cudaFree(e->d_ksum);
   cudaFree(e->d_hu); cudaFree(e->d_hp); cudaFree(e->d_hdu);
   if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
+  if (e->s_copy) cudaStreamDestroy(e->s_copy);
+  if (e->s_d2h) cudaStreamDestroy(e->s_d2h);
+  for (cudaEvent_t ev : e->ev_pipe) cudaEventDestroy(ev);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
   for (cudaEvent_t ev : e->ev) cudaEventDestroy(ev);
   for (cudaEvent_t ev : e->ev_pre) cudaEventDestroy(ev);
@@ -826,8 +885,18 @@ int nd_b200_rhs(nd_b200_engine* e, double* du, const double* u, const double* p,
   return rhs_impl(e, du, u, p, t, (cudaStream_t)stream, MODE_DU, nullptr);
 }
 
+// state ranges [start, len) written by rows [r0, r1] (inclusive), one per vertex batch the rows intersect
+static void rows_to_state_ranges(const nd_b200_engine* e, long long r0, long long r1, std::vector<std::pair<long long, long long>>& out) {
+  out.clear();
+  for (const HostVB& h : e->hvb) {
+    const long long lo = std::max<long long>(r0, h.row0), hi = std::min<long long>(r1 + 1, h.row0 + h.count);
+    if (lo < hi && h.dim > 0) out.push_back({h.state0 + (lo - h.row0) * h.dim, (hi - lo) * h.dim});
+  }
+}
+
 int nd_b200_rhs_host(nd_b200_engine* e, double* du_host, const double* u_host, const double* p_host, double t) {
   if (int rc = check_call(e, du_host, u_host, p_host)) return rc;
+  if (e->halo_base != INT_MAX) return fail(e, ND_B200_EUNSUPPORTED, "nd_b200_rhs_host on a halo engine");
   CUDA_TRY(e, cudaSetDevice(e->device));
   if (!e->own_stream) CUDA_TRY(e, cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
   const size_t nb = sizeof(double) * (size_t)e->lastidx_dynamic, pb = sizeof(double) * (size_t)e->lastidx_p;
@@ -837,11 +906,74 @@ int nd_b200_rhs_host(nd_b200_engine* e, double* du_host, const double* u_host, c
     CUDA_TRY(e, cudaMalloc((void**)&e->d_hp, std::max<size_t>(pb, 8)));
   }
   cudaStream_t st = e->own_stream;
-  CUDA_TRY(e, cudaMemcpyAsync(e->d_hu, u_host, nb, cudaMemcpyHostToDevice, st));
-  if (pb) CUDA_TRY(e, cudaMemcpyAsync(e->d_hp, p_host, pb, cudaMemcpyHostToDevice, st));
-  if (int rc = rhs_impl(e, e->d_hdu, e->d_hu, pb ? e->d_hp : nullptr, t, st, MODE_DU, nullptr)) return rc;
-  // only the states of owned rows are defined; for a partitioned engine copy the whole vector anyway
-  CUDA_TRY(e, cudaMemcpyAsync(du_host, e->d_hdu, nb, cudaMemcpyDeviceToHost, st));
+  // ---- pipelined form: the H2D copy of p is cut into pieces, a group of thread blocks starts as soon as the last
+  // parameter it reads has landed (blk_pmax; with edges(g) sorted by source the rows of group c read pieces <= c), and
+  // the D2H copy of a group's du rows overlaps the next group's kernel and the remaining H2D traffic.
+  int K = 8;
+  if (const char* s = getenv("ND_B200_HOST_CHUNKS")) K = std::max(1, std::min(32, atoi(s)));
+  const int nblk = (int)e->blk_pmax.size();
+  const bool pipelined = K > 1 && e->gather_from_u && !e->split && pb >= (size_t)K * 65536 && nblk >= 64 * K &&
+                         nblk == e->nblocks && (e->row_end - e->row_begin == e->nrows_total);
+  if (!pipelined) {
+    CUDA_TRY(e, cudaMemcpyAsync(e->d_hu, u_host, nb, cudaMemcpyHostToDevice, st));
+    if (pb) CUDA_TRY(e, cudaMemcpyAsync(e->d_hp, p_host, pb, cudaMemcpyHostToDevice, st));
+    if (int rc = rhs_impl(e, e->d_hdu, e->d_hu, pb ? e->d_hp : nullptr, t, st, MODE_DU, nullptr)) return rc;
+    CUDA_TRY(e, cudaMemcpyAsync(du_host, e->d_hdu, nb, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(e, cudaStreamSynchronize(st));
+    return ND_B200_OK;
+  }
+  if (!e->s_copy) CUDA_TRY(e, cudaStreamCreateWithFlags(&e->s_copy, cudaStreamNonBlocking));
+  if (!e->s_d2h) CUDA_TRY(e, cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking));
+  while ((int)e->ev_pipe.size() < 2 * K + 1) {
+    cudaEvent_t ev;
+    CUDA_TRY(e, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    e->ev_pipe.push_back(ev);
+  }
+  cudaEvent_t ev_u = e->ev_pipe[0];
+  cudaEvent_t* ev_p = &e->ev_pipe[1];
+  cudaEvent_t* ev_k = &e->ev_pipe[1 + K];
+  // H2D: u, then p piece by piece
+  CUDA_TRY(e, cudaMemcpyAsync(e->d_hu, u_host, nb, cudaMemcpyHostToDevice, e->s_copy));
+  CUDA_TRY(e, cudaEventRecord(ev_u, e->s_copy));
+  std::vector<long long> pend((size_t)K);
+  for (int k = 0; k < K; ++k) {
+    const long long a = e->lastidx_p * k / K, z = e->lastidx_p * (k + 1) / K;
+    pend[(size_t)k] = z;
+    CUDA_TRY(e, cudaMemcpyAsync(e->d_hp + a, p_host + a, sizeof(double) * (size_t)(z - a), cudaMemcpyHostToDevice, e->s_copy));
+    CUDA_TRY(e, cudaEventRecord(ev_p[k], e->s_copy));
+  }
+  // compute: group c = blocks [nblk*c/K, nblk*(c+1)/K)
+  KParams P;
+  fill_params(e, P);
+  P.u = e->d_hu; P.gsrc = e->d_hu; P.p = e->d_hp; P.du = e->d_hdu; P.mode = MODE_DU; P.t = t;
+  CUDA_TRY(e, cudaStreamWaitEvent(st, ev_u, 0));
+  std::vector<std::pair<long long, long long>> ranges;
+  int waited = -1;
+  for (int c = 0; c < K; ++c) {
+    const int b0 = (int)((long long)nblk * c / K), b1 = (int)((long long)nblk * (c + 1) / K);
+    int pm = 0, rmin = INT_MAX, rmax = -1;
+    for (int q = b0; q < b1; ++q) { pm = std::max(pm, e->blk_pmax[(size_t)q]); rmin = std::min(rmin, e->blk_rmin[(size_t)q]); rmax = std::max(rmax, e->blk_rmax[(size_t)q]); }
+    int need = -1;
+    if (pm > 0) { need = 0; while (need < K - 1 && pend[(size_t)need] < pm) ++need; }
+    if (need > waited) { CUDA_TRY(e, cudaStreamWaitEvent(st, ev_p[need], 0)); waited = need; }   // s_copy is in order: piece `need` implies all earlier ones
+    P.blk_off = b0;
+    e->launch_nblk = b1 - b0;
+    cudaError_t ce = launch_fused(e, P, st);
+    e->launch_nblk = -1;
+    CUDA_TRY(e, ce);
+    CUDA_TRY(e, cudaEventRecord(ev_k[c], st));
+    if (e->blk_rows_monotone && rmax >= rmin) {
+      CUDA_TRY(e, cudaStreamWaitEvent(e->s_d2h, ev_k[c], 0));
+      rows_to_state_ranges(e, rmin, rmax, ranges);
+      for (const auto& rg : ranges)
+        CUDA_TRY(e, cudaMemcpyAsync(du_host + rg.first, e->d_hdu + rg.first, sizeof(double) * (size_t)rg.second, cudaMemcpyDeviceToHost, e->s_d2h));
+    }
+  }
+  if (!e->blk_rows_monotone) {
+    CUDA_TRY(e, cudaStreamWaitEvent(e->s_d2h, ev_k[K - 1], 0));
+    CUDA_TRY(e, cudaMemcpyAsync(du_host, e->d_hdu, nb, cudaMemcpyDeviceToHost, e->s_d2h));
+  }
+  CUDA_TRY(e, cudaStreamSynchronize(e->s_d2h));
   CUDA_TRY(e, cudaStreamSynchronize(st));
   return ND_B200_OK;
 }

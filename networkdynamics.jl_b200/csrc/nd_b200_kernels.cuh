@@ -84,6 +84,7 @@ struct KParams {
   const double* halo;
   int halo_base;
   int wait_from;                       // first slice (jagged) / tile (tile kernel) that reads the halo
+  int blk_off;                         // this launch covers thread blocks [blk_off, blk_off + gridDim.x) of the full grid
 };
 
 // parameters of the edge pass (split mode)
@@ -372,14 +373,15 @@ __global__ void __launch_bounds__(BLOCK, (fused_warps_per_sm(EK) * 32) / BLOCK) 
 
   const int tid = threadIdx.x;
   // one 16-byte descriptor per thread block: {row0, e0, ne (long rows), ne | nrows<<16 | batch<<25 | long<<31}
-  const int4 d = __ldg(&P.tiles[blockIdx.x]);
+  const int bid = blockIdx.x + P.blk_off;
+  const int4 d = __ldg(&P.tiles[bid]);
   const int r0 = d.x, e0 = d.y;
   const bool is_long = d.w < 0;
   const int nrows = (d.w >> 16) & 0x1FF;
   const int ne = is_long ? d.z : (d.w & 0xFFFF);
   const VBDev B = P.vb[(d.w >> 25) & 0x3F];
   const int coupling0 = P.n_eb > 0 ? P.eb[0].coupling : 0;
-  if ((int)blockIdx.x >= P.wait_from) halo_wait(P);   // multi-GPU only: this tile reads the halo (block-uniform)
+  if (bid >= P.wait_from) halo_wait(P);   // multi-GPU only: this tile reads the halo (block-uniform)
 
   // ---------------- long row: whole block reduces one row with a fixed-shape tree -----------------
   if (is_long) {
@@ -804,13 +806,14 @@ __device__ __forceinline__ void long_row_block(const KParams& P, const int4 d, d
 template <int VD, int ED, int EK, int PE, int BLOCK, int U, int WPS>
 __global__ void __launch_bounds__(BLOCK, (WPS * 32) / BLOCK) rhs_jag_kernel(const __grid_constant__ KParams P) {
   __shared__ double s_val[BLOCK * ED];   // long rows only
-  if ((int)blockIdx.x >= P.n_jag_blocks) {
+  const int bid = blockIdx.x + P.blk_off;
+  if (bid >= P.n_jag_blocks) {
     halo_wait(P);   // multi-GPU only
-    long_row_block<VD, ED, EK, PE, BLOCK>(P, __ldg(&P.jlong[blockIdx.x - P.n_jag_blocks]), s_val);
+    long_row_block<VD, ED, EK, PE, BLOCK>(P, __ldg(&P.jlong[bid - P.n_jag_blocks]), s_val);
     return;
   }
   const int lane = threadIdx.x & 31;
-  const int sl = blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5);
+  const int sl = bid * (BLOCK / 32) + (threadIdx.x >> 5);
   if (sl >= P.nslices) return;           // warp-uniform
   if (sl >= P.wait_from) halo_wait_warp(P);   // multi-GPU only: this slice reads the halo
   const int4 S = __ldg(&P.jslices[sl]);

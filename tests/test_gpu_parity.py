@@ -226,6 +226,30 @@ def test_host_buffer_path_and_errors(nd, cuda):
     assert torch.count_nonzero(du_d).item() == 0
 
 
+@pytest.mark.parametrize("chunks", ["8", "3", "1"])
+def test_host_buffer_pipeline(nd, cuda, kernel_mode, monkeypatch, chunks):
+    """nd_b200_rhs_host on graphs large enough for the pipelined form (H2D of p in pieces, row groups start when their
+    parameters have landed, D2H of finished rows overlaps): identical to the device-resident call, bit for bit."""
+    torch = cuda
+    monkeypatch.setenv("ND_B200_HOST_CHUNKS", chunks)
+    L = nd.Lib
+    n = 200_000
+    half = np.array([0] * (n // 2) + [1] * (n // 2))
+    cases = [(nd.erdos_renyi(n, 4 * n, seed=3), L.diffusion_vertex(), L.diffusion_edge()),
+             (nd.barabasi_albert(n, 4, seed=3), ([L.kuramoto_first(), L.kuramoto_second()], np.random.default_rng(1).permutation(half)), L.kuramoto_edge()),
+             (nd.watts_strogatz(n, 6, 0.2, seed=3, directed=True), L.kuramoto_first(), nd.EdgeModel(g=nd.Directed(L.kuramoto_edge_f), outdim=1, pdim=1, name="dir_kura"))]
+    for g, vm, em in cases:
+        nw = nd.Network(g, vm, em, aggregator=nd.B200Aggregator("+", keep_tables=False))
+        u, p = rand_inputs(nw.dim(), nw.pdim(), layout=lambda q: condition_params(nw, q))
+        ref = _run_gpu(torch, nw, u, p)
+        hu, hp, hdu = nd.pinned_empty(u.size), nd.pinned_empty(p.size), nd.pinned_empty(u.size)
+        hu[:], hp[:] = u, p
+        for _ in range(3):
+            hdu[:] = np.nan
+            nw(hdu, hu, hp, 0.0)
+            assert np.array_equal(hdu, ref)
+
+
 @pytest.mark.parametrize("name", ["cfg4_powergrid_grid", "cfg1_kuramoto_ws", "cfg3_mixed_kuramoto_ba"])
 def test_rk4_trajectory(nd, cuda, kernel_mode, name):
     """north_star: trajectories agree within 1e-9 after 1000 fixed-step RK4 steps (dt = 1e-3)."""
