@@ -35,6 +35,20 @@ def algorithmic_bytes(nw, nentries):
     return 16 * nw.dim() + 8 * nw.pdim() + 4 * (nw.im.nv + 1) + 4 * nentries
 
 
+def profiled_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel on this workload, from the committed
+    `ncu --set full` capture (profiles/traffic.json: written by hand from profiles/*_ncu_summary.txt, per launch)"""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        t = json.load(open(path))
+        for k, v in t.items():
+            if kernel.startswith(k):
+                return v["dram_bytes"], v["source"]
+    except Exception:
+        pass
+    return None, None
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -251,10 +265,26 @@ def main():
     sync_all()
     warm_ms = a.elapsed_time(b)
     clocks = sampler.stop() if rank == 0 else None
+    local_ms = 0.0
+    if pnw is not None and pnw.exchange_kind == "p2p":
+        # compute-only time of the same rows (halo content reused, no publish, no wait): step - this = exposed halo time
+        evl = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        sync_all()
+        for a, b in evl:
+            flush.zero_()
+            a.record()
+            pnw.rhs_local(du, u, p, 0.0)
+            b.record()
+        sync_all()
+        local_ms = float(sum(a.elapsed_time(b) for a, b in evl))
     if dist is not None:
-        t = torch.tensor([total_ms, warm_ms], dtype=torch.float64, device="cuda")
+        t = torch.tensor([total_ms, warm_ms, local_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, warm_ms = t.tolist()
+        total_ms, warm_ms, local_ms = t.tolist()
+        hs = pnw.halo_stats() or {"recv_outputs": 0, "sent_outputs": 0, "owned_states": 0}
+        h = torch.tensor([hs["recv_outputs"], hs["sent_outputs"], hs["owned_states"]], dtype=torch.float64, device="cuda")
+        dist.all_reduce(h, op=dist.ReduceOp.MAX)
+        halo_max = h.tolist()
 
     # ---- end-to-end through the public call with HOST buffers (pinned), H2D + RHS + D2H every step ----------
     e2e = None
@@ -270,8 +300,9 @@ def main():
         e2e_s = time.perf_counter() - te
         e2e = {"value": g.ne * args.steps / e2e_s, "unit": "edge-evals/s", "h2d_bytes_per_step": 8 * (nw.dim() + nw.pdim()),
                "d2h_bytes_per_step": 8 * nw.dim(), "ms_per_step": 1e3 * e2e_s / args.steps,
-               "how": "nw(du,u,p,t) with pinned host vectors -> nd_b200_rhs_host: cudaMemcpyAsync H2D (u,p), fused RHS, "
-                      "cudaMemcpyAsync D2H (du), stream sync; wall clock around the calls"}
+               "how": "nw(du,u,p,t) with pinned host vectors -> nd_b200_rhs_host: H2D of u, H2D of p in 8 pieces, each row group's "
+                      "kernel starts when the last parameter it reads has landed, D2H of finished du rows overlaps the rest; "
+                      "stream sync before returning; wall clock around the calls"}
         assert np.array_equal(hdu, du.cpu().numpy()), "host-buffer path and device path disagree"
 
     if pnw is not None:
@@ -289,8 +320,10 @@ def main():
     roofline = None
     if world == 1 and fused_ms > 0:
         achieved = b_alg / (fused_ms * 1e-3) / 1e9
+        traffic, traffic_src = profiled_traffic(nw.kernel_name())
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "kernel": nw.kernel_name() + "<1,1,E_DIFFUSION>", "kernel_ms_avg": fused_ms,
+                    "traffic": traffic, "traffic_source": traffic_src,
+                    "kernel": nw.kernel_name() + "<1,1,E_DIFFUSION>", "kernel_ms_avg": fused_ms,
                     "algorithmic_bytes_per_launch": b_alg, "peak_source": peak_src,
                     "frac_of_nominal_8000": achieved / 8000.0,
                     "note": "kernel time from CUDA events recorded by the engine on the launch stream around the fused "
@@ -310,6 +343,16 @@ def main():
         "gpu_launches": int(launches), "clocks": clocks,
         "setup_s": {"graph": round(t_graph, 2), "network+csr": round(t_build, 2)},
     }
+    if world > 1:
+        line["exchange"] = {"kind": pnw.exchange_kind}
+        if pnw.exchange_kind == "p2p":
+            line["exchange"].update({
+                "recv_bytes_per_rank_per_step_max": int(8 * halo_max[0]), "sent_bytes_per_rank_per_step_max": int(8 * halo_max[1]),
+                "full_replication_bytes_per_rank": int(8 * (nw.dim() - halo_max[2])),
+                "compute_only_ms_per_step": local_ms / args.steps,
+                "exposed_halo_ms_per_step": max(0.0, (total_ms - local_ms) / args.steps),
+                "how": "compute_only = the same owned rows on the resident halo (no publish kernel, no flag wait), CUDA events, "
+                       "max over ranks; exposed = step - compute_only"})
     if e2e is not None:
         line["e2e"] = e2e
     if roofline is not None:

@@ -181,6 +181,10 @@ int nd_b200_comm_set_send(nd_b200_comm*, int32_t peer, const int64_t* state_offs
 /* replaces `(nw::Network)(du,u,p,t)` for a row-partitioned engine: only the owned states of u need to be valid */
 int nd_b200_rhs_exchange(nd_b200_engine*, nd_b200_comm*, double* du, const double* u, const double* p, double t,
                          void* stream);
+/* timing aid (exposed halo time = exchange call - this): the owned rows evaluated on whatever the halo buffer
+ * currently holds; no publish, no wait */
+int nd_b200_rhs_local(nd_b200_engine*, nd_b200_comm*, double* du, const double* u, const double* p, double t,
+                      void* stream);
 /* *timed_out = 1 if some RHS kernel gave up waiting for a peer (~2 s spin budget; results are then invalid) */
 int nd_b200_comm_status(nd_b200_comm*, int32_t* timed_out);
 const char* nd_b200_comm_last_error(const nd_b200_comm*);

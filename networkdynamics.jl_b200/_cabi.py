@@ -56,7 +56,7 @@ EXPORTED_SYMBOLS = [
     "nd_b200_create", "nd_b200_destroy", "nd_b200_last_error", "nd_b200_abi_version", "nd_b200_rhs",
     "nd_b200_rhs_host", "nd_b200_get_buffers", "nd_b200_rk4", "nd_b200_export_sizes", "nd_b200_export_tables",
     "nd_b200_launch_count", "nd_b200_set_timing", "nd_b200_timings", "nd_b200_host_alloc", "nd_b200_host_free",
-    "nd_b200_comm_create", "nd_b200_comm_export", "nd_b200_comm_open_peer", "nd_b200_comm_set_send", "nd_b200_rhs_exchange", "nd_b200_comm_status",
+    "nd_b200_comm_create", "nd_b200_comm_export", "nd_b200_comm_open_peer", "nd_b200_comm_set_send", "nd_b200_rhs_local", "nd_b200_rhs_exchange", "nd_b200_comm_status",
     "nd_b200_comm_last_error", "nd_b200_comm_destroy", "nd_b200_export_jag_sizes", "nd_b200_export_jag",
 ]
 IPC_HANDLE_BYTES = 64
@@ -143,6 +143,8 @@ def lib():
     L.nd_b200_comm_open_peer.argtypes = [C.c_void_p, C.c_int32, C.c_char_p]
     L.nd_b200_rhs_exchange.restype = C.c_int
     L.nd_b200_rhs_exchange.argtypes = [C.c_void_p, C.c_void_p, dp, dp, dp, C.c_double, C.c_void_p]
+    L.nd_b200_rhs_local.restype = C.c_int
+    L.nd_b200_rhs_local.argtypes = [C.c_void_p, C.c_void_p, dp, dp, dp, C.c_double, C.c_void_p]
     L.nd_b200_comm_status.restype = C.c_int
     L.nd_b200_comm_status.argtypes = [C.c_void_p, i32p]
     L.nd_b200_comm_last_error.restype = C.c_char_p

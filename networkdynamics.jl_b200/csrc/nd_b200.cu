@@ -1295,4 +1295,12 @@ int nd_b200_rhs_exchange(nd_b200_engine* e, nd_b200_comm* c, double* du, const d
   return rhs_impl(e, du, u, p, t, st, MODE_DU, nullptr, &w);
 }
 
+/* timing aid: the owned rows evaluated on whatever the halo buffer currently holds -- no publish, no wait */
+int nd_b200_rhs_local(nd_b200_engine* e, nd_b200_comm* c, double* du, const double* u, const double* p, double t, void* stream) {
+  if (int rc = check_call(e, du, u, p)) return rc;
+  if (!c || e->halo_base == INT_MAX) return fail(e, ND_B200_EINVAL, "nd_b200_rhs_local needs a halo engine and its comm");
+  WaitSpec w{c->halo(c->rank, (int)(c->seq & 1ull)), nullptr, 0, 0, nullptr};
+  return rhs_impl(e, du, u, p, t, (cudaStream_t)stream, MODE_DU, nullptr, &w);
+}
+
 }  // extern "C"

@@ -278,6 +278,25 @@ class PartitionedNetwork:
     def exchange(self, u):
         exchange_states(u, self.segments, self.group)
 
+    def rhs_local(self, du, u, p, t, *, stream=None):
+        """timing aid: the owned rows on the current halo content, no exchange (p2p engines only)"""
+        from .network import _addr, _stream_handle
+        from . import _cabi
+        a_du, _, _ = _addr(du)
+        a_u, _, _ = _addr(u)
+        a_p, _, _ = _addr(p)
+        rc = _cabi.lib().nd_b200_rhs_local(self.nw.handle, self.comm, a_du, a_u, a_p, float(t), _stream_handle(stream))
+        if rc:
+            self.nw._fail(rc)
+
+    def halo_stats(self):
+        """outputs received / sent per exchange by this rank and the share of its rows that read no remote output"""
+        if self.plan is None:
+            return None
+        sent = int(sum(o.size for o, _ in self.plan["sends"].values()))
+        return {"recv_outputs": int(self.plan["halo_lens"][self.rank]), "sent_outputs": sent,
+                "owned_states": int(sum(b - a for a, b in self.owned_segments))}
+
     def rhs(self, du, u, p, t, *, exchange: bool = True, stream=None):
         """`nw(du,u,p,t)` for the owned rows; only the owned states of `u` need to be valid on entry"""
         if exchange and self.comm is not None:
