@@ -24,9 +24,15 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (vertices per GPU, edges per GPU)
-    "cfg2_diffusion_er_1e6": (1_000_000, 4_000_000),
-    "cfg2_small": (100_000, 400_000),
+    # name: (vertices, edges, model family, scaling).  "weak": sizes are PER GPU (rank r owns one such slice of a
+    # world-times larger graph); "strong": sizes are the WHOLE graph, split over the ranks.
+    "cfg2_diffusion_er_1e6": (1_000_000, 4_000_000, "diffusion", "weak"),
+    "cfg2_small": (100_000, 400_000, "diffusion", "weak"),
+    # BASELINE.json configs[4] family (first-order Kuramoto on Erdos-Renyi, mean degree 16), strong scaling; the full
+    # 5e7 / 4e8 graph takes minutes of host-side generation per rank, the scaled ones keep its shape
+    "cfg5_kuramoto_er_5e7": (50_000_000, 400_000_000, "kuramoto", "strong"),
+    "cfg5_kuramoto_er_1e7": (10_000_000, 80_000_000, "kuramoto", "strong"),
+    "cfg5_kuramoto_er_5e6": (5_000_000, 40_000_000, "kuramoto", "strong"),
 }
 
 
@@ -102,11 +108,26 @@ class ClockSampler:
 
 
 def build_workload(nd, name, world):
-    nvp, nep = WORKLOADS[name]
+    nv, ne, family, scaling = WORKLOADS[name]
     t0 = time.time()
-    g = nd.erdos_renyi(nvp * world, nep * world, seed=1)
+    mult = world if scaling == "weak" else 1
+    g = nd.erdos_renyi(nv * mult, ne * mult, seed=1)
     L = nd.Lib
-    return g, L.diffusion_vertex(), L.diffusion_edge(), time.time() - t0
+    if family == "diffusion":
+        return g, L.diffusion_vertex(), L.diffusion_edge(), time.time() - t0
+    return g, L.kuramoto_first(), L.kuramoto_edge(), time.time() - t0
+
+
+def model_names(name):
+    return {"diffusion": ("diffusion_vertex", "diffusion_edge(pdim=1)", "E_DIFFUSION"),
+            "kuramoto": ("kuramoto_first", "kuramoto_edge(pdim=1)", "E_KURAMOTO")}[WORKLOADS[name][2]]
+
+
+def oracle_network(O, g, vm, em):
+    """the oracle's network for one vertex model + one edge model (same specs as tests/helpers.py)"""
+    vs = O.VSpec(vm.kernel_kind(), vm.dim, vm.pdim, vm.outdim)
+    es = O.ESpec(em.kernel_kind(), em.coupling, em.dim, em.pdim, em.outdim_src, em.outdim_dst)
+    return O.OracleNetwork(g.nv, g.src, g.dst, [vs], np.zeros(g.nv, np.int32), [es], np.zeros(g.ne, np.int32))
 
 
 def run_reference(args):
@@ -118,8 +139,7 @@ def run_reference(args):
     import ndb200 as nd
     from oracle import oracle as O
     g, vm, em, _ = build_workload(nd, args.workload, 1)
-    onw = O.OracleNetwork(g.nv, g.src, g.dst, [O.VSPECS["diffusion_vertex"]], np.zeros(g.nv, np.int32),
-                          [O.ESPECS["diffusion_edge"]], np.zeros(g.ne, np.int32))
+    onw = oracle_network(O, g, vm, em)
     u = np.random.default_rng(1).random(onw.lastidx_dynamic)
     p = np.random.default_rng(2).random(onw.lastidx_p)
     du = np.empty_like(u)
@@ -133,10 +153,10 @@ def run_reference(args):
     val = g.ne * args.steps / dt
     line = {"impl": "reference", "metric": "edge_evals_per_sec", "value": val, "unit": "edge-evals/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": WORKLOADS[args.workload][3], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "rhs_per_sec": args.steps / dt,
-            "config": {"workload": args.workload, "graph": f"erdos_renyi(N={g.nv}, E={g.ne})", "vertex": "diffusion_vertex",
-                       "edge": "diffusion_edge(pdim=1)"},
+            "config": {"workload": args.workload, "graph": f"erdos_renyi(N={g.nv}, E={g.ne})", "vertex": model_names(args.workload)[0],
+                       "edge": model_names(args.workload)[1]},
             "cpu_baseline": {"value": val, "unit": "edge-evals/s", "cores": threads, "kind": "port",
                              "sample": f"{args.steps} full RHS evaluations of the same workload; C/OpenMP restatement of "
                                        "ThreadedExecution{true}+ThreadedAggregator, not Julia"},
@@ -144,10 +164,9 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def cpu_baseline_leg(nd, g, budget_s=12.0):
+def cpu_baseline_leg(nd, g, vm, em, budget_s=12.0):
     from oracle import oracle as O
-    onw = O.OracleNetwork(g.nv, g.src, g.dst, [O.VSPECS["diffusion_vertex"]], np.zeros(g.nv, np.int32),
-                          [O.ESPECS["diffusion_edge"]], np.zeros(g.ne, np.int32))
+    onw = oracle_network(O, g, vm, em)
     u = np.random.default_rng(1).random(onw.lastidx_dynamic)
     p = np.random.default_rng(2).random(onw.lastidx_p)
     du = np.empty_like(u)
@@ -323,7 +342,7 @@ def main():
         traffic, traffic_src = profiled_traffic(nw.kernel_name())
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "traffic_source": traffic_src,
-                    "kernel": nw.kernel_name() + "<1,1,E_DIFFUSION>", "kernel_ms_avg": fused_ms,
+                    "kernel": nw.kernel_name() + f"<1,1,{model_names(args.workload)[2]}>", "kernel_ms_avg": fused_ms,
                     "algorithmic_bytes_per_launch": b_alg, "peak_source": peak_src,
                     "frac_of_nominal_8000": achieved / 8000.0,
                     "note": "kernel time from CUDA events recorded by the engine on the launch stream around the fused "
@@ -331,11 +350,11 @@ def main():
     line = {
         "metric": "edge_evals_per_sec", "value": g.ne * args.steps / (total_ms * 1e-3), "unit": "edge-evals/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": WORKLOADS[args.workload][3], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "rhs_per_sec": args.steps / (total_ms * 1e-3),
         "value_l2_warm": g.ne * args.steps / (warm_ms * 1e-3), "ms_per_step_l2_warm": warm_ms / args.steps,
-        "config": {"workload": args.workload, "graph": f"erdos_renyi(N={g.nv}, E={g.ne}), seed 1", "vertex": "diffusion_vertex",
-                   "edge": "diffusion_edge(pdim=1)", "directed_entries": n_entries_all,
+        "config": {"workload": args.workload, "graph": f"erdos_renyi(N={g.nv}, E={g.ne}), seed 1", "vertex": model_names(args.workload)[0],
+                   "edge": model_names(args.workload)[1], "directed_entries": n_entries_all,
                    "l2": "flushed between timed steps by a 256 MiB write outside the event brackets; value_l2_warm = back-to-back",
                    "partition": "none" if world == 1 else f"{world} contiguous vertex ranges, vertex outputs exchanged every step "
                                 f"({pnw.exchange_kind}: " + ("NVLink peer stores + arrival flags, wait fused into the RHS kernel)" if pnw.exchange_kind == "p2p" else "torch.distributed all-gather)"),
@@ -358,7 +377,7 @@ def main():
     if roofline is not None:
         line["roofline"] = roofline
     if world == 1 and not args.no_cpu_baseline:
-        cb, du_cpu, _, _ = cpu_baseline_leg(nd, g)
+        cb, du_cpu, _, _ = cpu_baseline_leg(nd, g, vm, em)
         line["cpu_baseline"] = cb
         ref = du_cpu
         got = du.cpu().numpy()

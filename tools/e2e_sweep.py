@@ -12,7 +12,7 @@ nw = nd.Network(g, nd.Lib.diffusion_vertex(), nd.Lib.diffusion_edge(), aggregato
 hu, hp, hdu = nd.pinned_empty(nw.dim()), nd.pinned_empty(nw.pdim()), nd.pinned_empty(nw.dim())
 hu[:] = np.random.default_rng(1).random(nw.dim()); hp[:] = np.random.default_rng(2).random(nw.pdim())
 ref = None
-for chunks in sys.argv[1:] or ["1", "2", "4", "8", "16", "32"]:
+for chunks in sys.argv[1:] or ["1", "2", "3", "4", "5", "6", "8"]:
     os.environ["ND_B200_HOST_CHUNKS"] = chunks
     for _ in range(5):
         nw(hdu, hu, hp, 0.0)
