@@ -221,7 +221,7 @@ cudaError_t launch_row_pass_t(const nd_b200_engine* e, const KParams& P, cudaStr
 
 template <int VD, int ED, int EK, int PE>
 cudaError_t launch_shape(const nd_b200_engine* e, const KParams& P, cudaStream_t st) {
-  const int grid = e->launch_nblk >= 0 ? e->launch_nblk : e->nblocks;
+  const int grid = (e->launch_nblk >= 0 ? e->launch_nblk : e->nblocks) + P.n_pub;
   if (grid == 0) return cudaSuccess;
   if (e->block == 256 && e->ept == 8) rhs_fused_kernel<VD, ED, EK, PE, 256, 8><<<grid, 256, 0, st>>>(P);
   else if (e->block == 256 && e->ept == 4) rhs_fused_kernel<VD, ED, EK, PE, 256, 4><<<grid, 256, 0, st>>>(P);
@@ -235,7 +235,7 @@ cudaError_t launch_shape(const nd_b200_engine* e, const KParams& P, cudaStream_t
 template <int VD, int ED, int EK, int PE, int U>
 cudaError_t launch_jag_u(const nd_b200_engine* e, const KParams& P, cudaStream_t st) {
   constexpr int BLOCK = 128;
-  const int grid = e->launch_nblk >= 0 ? e->launch_nblk : e->n_jag_blocks + e->n_jlong;
+  const int grid = (e->launch_nblk >= 0 ? e->launch_nblk : e->n_jag_blocks + e->n_jlong) + P.n_pub;
   if (grid == 0) return cudaSuccess;
   const int wps = e->jag_wps > 0 ? e->jag_wps : jag_warps_per_sm_default(EK);
   if (wps >= 64) rhs_jag_kernel<VD, ED, EK, PE, BLOCK, U, 64><<<grid, BLOCK, 0, st>>>(P);
@@ -777,7 +777,7 @@ int check_call(nd_b200_engine* e, const void* du, const void* u, const void* p) 
   return 0;
 }
 
-struct WaitSpec { const double* halo; const unsigned long long* flags; unsigned long long seq; int world; int* timeout; };
+struct WaitSpec { const double* halo; const unsigned long long* flags; unsigned long long seq; int world; int* timeout; const HaloParams* pub; int n_pub; };
 
 int rhs_impl(nd_b200_engine* e, double* du, const double* u, const double* p, double t, cudaStream_t st, int mode,
              double* aggbuf, const WaitSpec* w = nullptr) {
@@ -786,7 +786,10 @@ int rhs_impl(nd_b200_engine* e, double* du, const double* u, const double* p, do
   fill_params(e, P);
   P.u = u; P.p = p; P.du = du; P.mode = mode; P.aggbuf = aggbuf; P.t = t;
   P.gsrc = u;
-  if (w) { P.halo = w->halo; P.wait_flags = w->flags; P.wait_seq = w->seq; P.wait_world = w->world; P.wait_timeout = w->timeout; }
+  if (w) {
+    P.halo = w->halo; P.wait_flags = w->flags; P.wait_seq = w->seq; P.wait_world = w->world; P.wait_timeout = w->timeout;
+    if (w->pub) { P.H = *w->pub; P.n_pub = w->n_pub; }
+  }
   if (e->timing) {
     if (ensure_events(e, e->ev, e->ev_used + 2) || ensure_events(e, e->ev_pre, e->ev_pre_used + 2)) return ND_B200_ECUDA;
   }
@@ -1295,11 +1298,9 @@ int nd_b200_rhs_exchange(nd_b200_engine* e, nd_b200_comm* c, double* du, const d
     total += c->send_n[r];
   }
   H.world = c->world; H.rank = c->rank; H.seq = seq; H.src = u; H.done_counter = c->d_done;
-  const int grid = (int)std::max<long long>(1, std::min<long long>(148 * 2, (total + 1023) / 1024));
-  halo_publish_kernel<<<grid, 256, 0, st>>>(H);
-  CUDA_TRY(e, cudaGetLastError());
-  e->launches++;
-  WaitSpec w{c->halo(c->rank, parity), c->flags(c->rank), seq, c->world, c->d_timeout};
+  // publishing blocks: 128 threads each, ~8 outputs per thread, at least one (it raises the flags even when nothing is sent)
+  const int n_pub = (int)std::max<long long>(1, std::min<long long>(148 * 16, (total + 1023) / 1024));
+  WaitSpec w{c->halo(c->rank, parity), c->flags(c->rank), seq, c->world, c->d_timeout, &H, n_pub};
   return rhs_impl(e, du, u, p, t, st, MODE_DU, nullptr, &w);
 }
 
@@ -1307,7 +1308,7 @@ int nd_b200_rhs_exchange(nd_b200_engine* e, nd_b200_comm* c, double* du, const d
 int nd_b200_rhs_local(nd_b200_engine* e, nd_b200_comm* c, double* du, const double* u, const double* p, double t, void* stream) {
   if (int rc = check_call(e, du, u, p)) return rc;
   if (!c || e->halo_base == INT_MAX) return fail(e, ND_B200_EINVAL, "nd_b200_rhs_local needs a halo engine and its comm");
-  WaitSpec w{c->halo(c->rank, (int)(c->seq & 1ull)), nullptr, 0, 0, nullptr};
+  WaitSpec w{c->halo(c->rank, (int)(c->seq & 1ull)), nullptr, 0, 0, nullptr, nullptr, 0};
   return rhs_impl(e, du, u, p, t, (cudaStream_t)stream, MODE_DU, nullptr, &w);
 }
 

@@ -32,6 +32,19 @@ struct EBDev {          // one edge ComponentBatch
 enum { MODE_DU = 0, MODE_AGG = 1, MODE_RK = 2 };
 constexpr int EK_GENERIC = -1;   // several edge batches: per-entry batch id lookup
 
+constexpr int HALO_MAX_WORLD = 8;
+struct HaloParams {
+  double* halo[HALO_MAX_WORLD];                    // [peer] -> that rank's halo buffer (this sequence's parity), peer-mapped
+  unsigned long long* flags[HALO_MAX_WORLD];       // [peer] -> that rank's arrival-flag array
+  const int* send_idx[HALO_MAX_WORLD];             // [peer] -> offsets (into src) of the outputs that peer reads, ascending
+  long long send_n[HALO_MAX_WORLD];                //          how many
+  long long dst_off[HALO_MAX_WORLD];               //          where this rank's block starts inside the peer's halo buffer
+  int world, rank;
+  unsigned long long seq;
+  const double* src;                                // the owner's state vector (full layout, owned ranges valid)
+  unsigned int* done_counter;                       // local: blocks finished (reset by the last block)
+};
+
 struct KParams {
   const int* __restrict__ rowptr;      // [nrows_owned+1], entries of owned rows, relative to row_base
   const int* __restrict__ nbr;         // per entry: offset of the neighbour's output in gsrc; ~offset when this row is the edge's src
@@ -85,6 +98,10 @@ struct KParams {
   int halo_base;
   int wait_from;                       // first slice (jagged) / tile (tile kernel) that reads the halo
   int blk_off;                         // this launch covers thread blocks [blk_off, blk_off + gridDim.x) of the full grid
+  // multi-GPU: the first n_pub thread blocks of the grid pack this rank's boundary outputs into the peers' halo buffers
+  // (NVLink stores) and raise the arrival flags; interior tiles follow, tiles that read the halo come last
+  int n_pub;
+  HaloParams H;
 };
 
 // parameters of the edge pass (split mode)
@@ -269,19 +286,6 @@ __device__ __forceinline__ void load_vertex_state(const KParams& P, const VBDev&
 // by sequence parity, which is enough: a rank can only publish sequence s+2 after it has consumed every peer's s+1,
 // which those peers published after finishing their own reads of s.
 // ------------------------------------------------------------------------------------------------
-constexpr int HALO_MAX_WORLD = 8;
-struct HaloParams {
-  double* halo[HALO_MAX_WORLD];                    // [peer] -> that rank's halo buffer (this sequence's parity), peer-mapped
-  unsigned long long* flags[HALO_MAX_WORLD];       // [peer] -> that rank's arrival-flag array
-  const int* send_idx[HALO_MAX_WORLD];             // [peer] -> offsets (into src) of the outputs that peer reads, ascending
-  long long send_n[HALO_MAX_WORLD];                //          how many
-  long long dst_off[HALO_MAX_WORLD];               //          where this rank's block starts inside the peer's halo buffer
-  int world, rank;
-  unsigned long long seq;
-  const double* src;                                // the owner's state vector (full layout, owned ranges valid)
-  unsigned int* done_counter;                       // local: blocks finished (reset by the last block)
-};
-
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
   unsigned long long v;
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -291,25 +295,33 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// pack + publish: for every peer, gather the outputs it needs from the owner's state vector (ascending offsets: the
-// reads are nearly coalesced) and store them contiguously into the peer's halo buffer (coalesced NVLink stores); the
-// last block to finish raises this rank's arrival flag on every rank.
-__global__ void __launch_bounds__(256) halo_publish_kernel(const __grid_constant__ HaloParams H) {
-  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long nthreads = (long long)gridDim.x * blockDim.x;
+// pack + publish, executed by the first n_pub thread blocks of the RHS grid: for every peer, gather the outputs it
+// needs from the owner's state vector (ascending offsets: the reads are nearly coalesced) and store them contiguously
+// into the peer's halo buffer (coalesced NVLink stores).  The last publishing block to finish raises this rank's arrival
+// flag on every rank.  Publishing blocks never wait on anything and are scheduled before every tile of the same grid,
+// so tiles that spin on the peers' flags cannot starve them.
+__device__ __forceinline__ void publish_block(const HaloParams& H, int bid, int nblocks) {
+  const long long tid = (long long)bid * blockDim.x + threadIdx.x;
+  const long long nthreads = (long long)nblocks * blockDim.x;
   for (int r = 0; r < H.world; ++r) {
     if (r == H.rank) continue;
     const long long n = H.send_n[r];
     const int* __restrict__ idx = H.send_idx[r];
     double* __restrict__ dst = H.halo[r] + H.dst_off[r];
-    for (long long i = tid; i < n; i += nthreads) dst[i] = H.src[idx[i]];
+    long long i = tid;
+    for (; i + 3 * nthreads < n; i += 4 * nthreads) {   // four independent gathers in flight per thread
+      const int i0 = idx[i], i1 = idx[i + nthreads], i2 = idx[i + 2 * nthreads], i3 = idx[i + 3 * nthreads];
+      const double v0 = H.src[i0], v1 = H.src[i1], v2 = H.src[i2], v3 = H.src[i3];
+      dst[i] = v0; dst[i + nthreads] = v1; dst[i + 2 * nthreads] = v2; dst[i + 3 * nthreads] = v3;
+    }
+    for (; i < n; i += nthreads) dst[i] = H.src[idx[i]];
   }
   // make this block's peer stores visible system-wide, then count the block as done
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned int prev = atomicAdd(H.done_counter, 1u);
-    if (prev == gridDim.x - 1) {
+    if (prev == (unsigned int)nblocks - 1u) {
       *H.done_counter = 0;
       __threadfence_system();
       for (int r = 0; r < H.world; ++r) st_release_sys(H.flags[r] + H.rank, H.seq);
@@ -372,8 +384,9 @@ __global__ void __launch_bounds__(BLOCK, (fused_warps_per_sm(EK) * 32) / BLOCK) 
   __shared__ uint8_t s_rowid[TILE];
 
   const int tid = threadIdx.x;
+  if ((int)blockIdx.x < P.n_pub) { publish_block(P.H, blockIdx.x, P.n_pub); return; }   // multi-GPU only
   // one 16-byte descriptor per thread block: {row0, e0, ne (long rows), ne | nrows<<16 | batch<<25 | long<<31}
-  const int bid = blockIdx.x + P.blk_off;
+  const int bid = (int)blockIdx.x - P.n_pub + P.blk_off;
   const int4 d = __ldg(&P.tiles[bid]);
   const int r0 = d.x, e0 = d.y;
   const bool is_long = d.w < 0;
@@ -806,7 +819,8 @@ __device__ __forceinline__ void long_row_block(const KParams& P, const int4 d, d
 template <int VD, int ED, int EK, int PE, int BLOCK, int U, int WPS>
 __global__ void __launch_bounds__(BLOCK, (WPS * 32) / BLOCK) rhs_jag_kernel(const __grid_constant__ KParams P) {
   __shared__ double s_val[BLOCK * ED];   // long rows only
-  const int bid = blockIdx.x + P.blk_off;
+  if ((int)blockIdx.x < P.n_pub) { publish_block(P.H, blockIdx.x, P.n_pub); return; }   // multi-GPU only
+  const int bid = (int)blockIdx.x - P.n_pub + P.blk_off;
   if (bid >= P.n_jag_blocks) {
     halo_wait(P);   // multi-GPU only
     long_row_block<VD, ED, EK, PE, BLOCK>(P, __ldg(&P.jlong[bid - P.n_jag_blocks]), s_val);
