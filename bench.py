@@ -33,6 +33,9 @@ WORKLOADS = {
     "cfg5_kuramoto_er_5e7": (50_000_000, 400_000_000, "kuramoto", "strong"),
     "cfg5_kuramoto_er_1e7": (10_000_000, 80_000_000, "kuramoto", "strong"),
     "cfg5_kuramoto_er_5e6": (5_000_000, 40_000_000, "kuramoto", "strong"),
+    # a graph WITH locality (1000 x 1000*world lattice, contiguous ranges = strips): the halo is one lattice row per
+    # neighbour and nearly every tile is interior -- what the packed halo + interior-first order are built for
+    "grid_kuramoto_1e6": (1_000_000, 1_998_000, "kuramoto", "weak"),
 }
 
 
@@ -111,7 +114,10 @@ def build_workload(nd, name, world):
     nv, ne, family, scaling = WORKLOADS[name]
     t0 = time.time()
     mult = world if scaling == "weak" else 1
-    g = nd.erdos_renyi(nv * mult, ne * mult, seed=1)
+    if name.startswith("grid"):
+        g = nd.grid_graph(1000, 1000 * mult)
+    else:
+        g = nd.erdos_renyi(nv * mult, ne * mult, seed=1)
     L = nd.Lib
     if family == "diffusion":
         return g, L.diffusion_vertex(), L.diffusion_edge(), time.time() - t0
@@ -155,7 +161,7 @@ def run_reference(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
             "scaling": WORKLOADS[args.workload][3], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "rhs_per_sec": args.steps / dt,
-            "config": {"workload": args.workload, "graph": f"erdos_renyi(N={g.nv}, E={g.ne})", "vertex": model_names(args.workload)[0],
+            "config": {"workload": args.workload, "graph": (f"grid_graph(1000, {g.nv // 1000})" if args.workload.startswith("grid") else f"erdos_renyi(N={g.nv}, E={g.ne})"), "vertex": model_names(args.workload)[0],
                        "edge": model_names(args.workload)[1]},
             "cpu_baseline": {"value": val, "unit": "edge-evals/s", "cores": threads, "kind": "port",
                              "sample": f"{args.steps} full RHS evaluations of the same workload; C/OpenMP restatement of "
@@ -353,7 +359,7 @@ def main():
         "higher_is_better": True, "scaling": WORKLOADS[args.workload][3], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "rhs_per_sec": args.steps / (total_ms * 1e-3),
         "value_l2_warm": g.ne * args.steps / (warm_ms * 1e-3), "ms_per_step_l2_warm": warm_ms / args.steps,
-        "config": {"workload": args.workload, "graph": f"erdos_renyi(N={g.nv}, E={g.ne}), seed 1", "vertex": model_names(args.workload)[0],
+        "config": {"workload": args.workload, "graph": (f"grid_graph(1000, {g.nv // 1000})" if args.workload.startswith("grid") else f"erdos_renyi(N={g.nv}, E={g.ne}), seed 1"), "vertex": model_names(args.workload)[0],
                    "edge": model_names(args.workload)[1], "directed_entries": n_entries_all,
                    "l2": "flushed between timed steps by a 256 MiB write outside the event brackets; value_l2_warm = back-to-back",
                    "partition": "none" if world == 1 else f"{world} contiguous vertex ranges, vertex outputs exchanged every step "

@@ -47,7 +47,8 @@ enum {
   ND_B200_E_LINE_DQ = 3                /* test/ComponentLibrary.jl:212-245, p=(R,X,active)         */
 };
 /* edge output wrappers, src/component_functions.jl:117-203 */
-enum { ND_B200_ANTISYMMETRIC = 0, ND_B200_SYMMETRIC = 1, ND_B200_DIRECTED = 2 };
+enum { ND_B200_ANTISYMMETRIC = 0, ND_B200_SYMMETRIC = 1, ND_B200_DIRECTED = 2,
+       ND_B200_FIDUCIAL = 3 /* the edge's own two-sided g(osrc, odst, ...); user-supplied kinds only */ };
 
 /* One `ComponentBatch` of vertices (src/network_structure.jl:176-222 + register_vertices! :224-239).
  * `*_first` are the `first` fields of the batch's BatchStrides (1-based); widths are the strides. */

@@ -282,7 +282,7 @@ cudaError_t launch_vout(nd_b200_engine* e, const double* u, const double* p, dou
   const int nb = (int)((e->nrows_total + T - 1) / T);
   if (nb == 0) return cudaSuccess;
   e->launches++;
-  vertex_out_kernel<<<nb, T, 0, st>>>(e->d_vb, (int)e->hvb.size(), e->vdepth, u, p, vout, (int)e->nrows_total);
+  vertex_out_kernel<<<nb, T, 0, st>>>(e->d_vb, (int)e->hvb.size(), e->vdepth, u, p, vout, (int)e->nrows_total, 0.0);
   return cudaGetLastError();
 }
 
@@ -1015,9 +1015,9 @@ int nd_b200_get_buffers(nd_b200_engine* e, double* o, double* aggbuf, const doub
       const int nb = (int)((h.count + T - 1) / T);
       e->launches++;
       if (e->vdepth == 2)
-        edge_out_kernel<2, 2><<<nb, T, 0, st>>>(h.kind, h.coupling, h.pdim, h.osrc, h.count, e->d_esrc_off[b], e->d_edst_off[b], h.p0, h.out0, gsrc, p, o);
+        edge_out_kernel<2, 2><<<nb, T, 0, st>>>(h.kind, h.coupling, h.pdim, h.osrc, h.count, e->d_esrc_off[b], e->d_edst_off[b], h.p0, h.out0, gsrc, p, o, t);
       else
-        edge_out_kernel<1, 1><<<nb, T, 0, st>>>(h.kind, h.coupling, h.pdim, h.osrc, h.count, e->d_esrc_off[b], e->d_edst_off[b], h.p0, h.out0, gsrc, p, o);
+        edge_out_kernel<1, 1><<<nb, T, 0, st>>>(h.kind, h.coupling, h.pdim, h.osrc, h.count, e->d_esrc_off[b], e->d_edst_off[b], h.p0, h.out0, gsrc, p, o, t);
       CUDA_TRY(e, cudaGetLastError());
     }
   }

@@ -13,9 +13,29 @@
 //
 // Compiled with -fmad=false: the reference (Julia) never contracts a*b+c, so neither do we.
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "nd_b200.h"
+#endif
+// When this file is compiled at run time (NVRTC, networks with user-supplied component kinds -- see custom_source() in
+// nd_b200.cu) the generator has already emitted: the integer typedefs, the registry enums of nd_b200.h, the user's
+// component functions in namespace ndb_user, and the macros below that splice them into the model switches.
+#ifndef ND_MAX_VDIM
+#define ND_MAX_VDIM 2            // largest vertex state dimension of the network (registry models: 2)
+#endif
+#ifndef ND_CUSTOM_EDGE_CASES
+#define ND_CUSTOM_EDGE_CASES     // case <kind>: ndb_user::edge_g_<kind>(odst, vs, vd, pe, t); break;
+#endif
+#ifndef ND_CUSTOM_EDGE_FID_CASES
+#define ND_CUSTOM_EDGE_FID_CASES // case <kind>: ndb_user::edge_g_<kind>(osrc, odst, vs, vd, pe, t); break;   (Fiducial)
+#endif
+#ifndef ND_CUSTOM_VERTEX_F_CASES
+#define ND_CUSTOM_VERTEX_F_CASES // case <kind>: ndb_user::vertex_f_<kind>(dv, v, acc, pv, t); break;
+#endif
+#ifndef ND_CUSTOM_VERTEX_G_CASES
+#define ND_CUSTOM_VERTEX_G_CASES // case <kind>: ndb_user::vertex_g_<kind>(out, v, pv, t); break;
+#endif
 
 namespace ndb {
 
@@ -127,39 +147,56 @@ struct EParams {
 // inner edge function: writes the DST output, g(odst, vsrc, vdst, p, t)
 template <int VD, int ED>
 __device__ __forceinline__ void edge_g_dst(int kind, double* odst, const double* vs, const double* vd,
-                                           const double* __restrict__ pe) {
-  if constexpr (VD == 1 && ED == 1) {
-    switch (kind) {
-      case ND_B200_E_DIFFUSION:      // test/ComponentLibrary.jl:8-10
-        odst[0] = pe[0] * (vs[0] - vd[0]);
-        break;
-      case ND_B200_E_DIFFUSION_NOP:  // benchmark/benchmark_models.jl:5-8
-        odst[0] = vs[0] - vd[0];
-        break;
-      case ND_B200_E_KURAMOTO:       // test/ComponentLibrary.jl:51-53
-        odst[0] = pe[0] * sin(vs[0] - vd[0]);
-        break;
-      default: odst[0] = 0.0;
-    }
-  } else if constexpr (VD == 2 && ED == 2) {
-    // ND_B200_E_LINE_DQ, test/ComponentLibrary.jl:212-245: idst = active*1/Z*(Vsrc-Vdst), Z = R+jX
-    double R = pe[0], X = pe[1], active = pe[2];
-    double dr = vs[0] - vd[0];
-    double di = vs[1] - vd[1];
-    double den = R * R + X * X;
-    odst[0] = active * ((R * dr + X * di) / den);
-    odst[1] = active * ((R * di - X * dr) / den);
+                                           const double* __restrict__ pe, double t) {
+  (void)t;
+  switch (kind) {
+    case ND_B200_E_DIFFUSION:      // test/ComponentLibrary.jl:8-10
+      if constexpr (VD == 1 && ED == 1) odst[0] = pe[0] * (vs[0] - vd[0]);
+      break;
+    case ND_B200_E_DIFFUSION_NOP:  // benchmark/benchmark_models.jl:5-8
+      if constexpr (VD == 1 && ED == 1) odst[0] = vs[0] - vd[0];
+      break;
+    case ND_B200_E_KURAMOTO:       // test/ComponentLibrary.jl:51-53
+      if constexpr (VD == 1 && ED == 1) odst[0] = pe[0] * sin(vs[0] - vd[0]);
+      break;
+    case ND_B200_E_LINE_DQ:        // test/ComponentLibrary.jl:212-245: idst = active*1/Z*(Vsrc-Vdst), Z = R+jX
+      if constexpr (VD == 2 && ED == 2) {
+        double R = pe[0], X = pe[1], active = pe[2];
+        double dr = vs[0] - vd[0];
+        double di = vs[1] - vd[1];
+        double den = R * R + X * X;
+        odst[0] = active * ((R * dr + X * di) / den);
+        odst[1] = active * ((R * di - X * dr) / den);
+      }
+      break;
+    ND_CUSTOM_EDGE_CASES
+    default:
+#pragma unroll
+      for (int d = 0; d < ED; ++d) odst[d] = 0.0;
   }
 }
 
 // value an entry contributes to ITS row: the dst output if the row is the edge's dst, else the src
-// output produced by the wrapper (AntiSymmetric: -odst, Symmetric: odst; src/component_functions.jl:117-152)
+// output produced by the wrapper (AntiSymmetric: -odst, Symmetric: odst; src/component_functions.jl:117-152;
+// Fiducial: the edge's own two-sided g(osrc, odst, ...), :189-203 -- user-supplied kinds only)
 template <int VD, int ED>
 __device__ __forceinline__ void entry_value(int kind, int coupling, int side, const double* self,
-                                            const double* xn, const double* __restrict__ pe, double* val) {
+                                            const double* xn, const double* __restrict__ pe, double t, double* val) {
   const double* vs = side ? self : xn;
   const double* vd = side ? xn : self;
-  edge_g_dst<VD, ED>(kind, val, vs, vd, pe);
+  if (coupling == ND_B200_FIDUCIAL) {
+    double osrc[ED], odst[ED];
+#pragma unroll
+    for (int d = 0; d < ED; ++d) { osrc[d] = 0.0; odst[d] = 0.0; }
+    switch (kind) {
+      ND_CUSTOM_EDGE_FID_CASES
+      default: break;
+    }
+#pragma unroll
+    for (int d = 0; d < ED; ++d) val[d] = side ? osrc[d] : odst[d];
+    return;
+  }
+  edge_g_dst<VD, ED>(kind, val, vs, vd, pe, t);
   if (side && coupling == ND_B200_ANTISYMMETRIC) {
 #pragma unroll
     for (int d = 0; d < ED; ++d) val[d] = -val[d];
@@ -168,13 +205,17 @@ __device__ __forceinline__ void entry_value(int kind, int coupling, int side, co
 
 // vertex g for non-StateMask models: NoFeedForward g(out,u,p,t)
 __device__ __forceinline__ void vertex_g(int kind, int outdim, double* out, const double* v,
-                                         const double* __restrict__ pv) {
-  if (kind == ND_B200_V_SWING_DQ) {   // test/ComponentLibrary.jl:158-159
-    double V = pv[3];
-    out[0] = V * cos(v[0]);
-    out[1] = V * sin(v[0]);
-  } else {                            // StateMask(1:outdim), src/component_functions.jl:81-99
-    for (int k = 0; k < outdim; ++k) out[k] = v[k];
+                                         const double* __restrict__ pv, double t) {
+  (void)t;
+  switch (kind) {
+    case ND_B200_V_SWING_DQ: {          // test/ComponentLibrary.jl:158-159
+      double V = pv[3];
+      out[0] = V * cos(v[0]);
+      out[1] = V * sin(v[0]);
+    } break;
+    ND_CUSTOM_VERTEX_G_CASES
+    default:                            // StateMask(1:outdim), src/component_functions.jl:81-99
+      for (int k = 0; k < outdim; ++k) out[k] = v[k];
   }
 }
 
@@ -182,7 +223,8 @@ __device__ __forceinline__ void vertex_g(int kind, int outdim, double* out, cons
 // recomputes u_r,u_i with the same expressions as its g).
 template <int VD, int ED>
 __device__ __forceinline__ void vertex_f(int kind, double* dv, const double* v, const double* acc,
-                                         const double* __restrict__ pv, const double* selfout) {
+                                         const double* __restrict__ pv, const double* selfout, double t) {
+  (void)t; (void)selfout;
   switch (kind) {
     case ND_B200_V_DIFFUSION:            // test/ComponentLibrary.jl:42-45
       dv[0] = acc[0];
@@ -210,6 +252,8 @@ __device__ __forceinline__ void vertex_f(int kind, double* dv, const double* v, 
         dv[1] = 1.0 / M * (Pmech + Pdamping + Pel);
       }
     } break;
+    ND_CUSTOM_VERTEX_F_CASES
+    default: break;
   }
 }
 
@@ -225,25 +269,28 @@ __device__ __forceinline__ void vertex_phase(const KParams& P, const VBDev& B, i
   }
   const long long i = row - B.row0;
   const long long s = B.state0 + i * B.dim;
-  const bool two = B.dim == 2;          // registry: dim is 1 or 2
-  const double v[2] = {vin[0], two ? vin[1] : 0.0};
-  double dv[2] = {0.0, 0.0};
-  vertex_f<VD, ED>(B.kind, dv, v, acc, pv, selfout);
+  const int dim = B.dim;                // <= ND_MAX_VDIM
+  double v[ND_MAX_VDIM], dv[ND_MAX_VDIM];
+#pragma unroll
+  for (int c = 0; c < ND_MAX_VDIM; ++c) { v[c] = c < dim ? vin[c] : 0.0; dv[c] = 0.0; }
+  vertex_f<VD, ED>(B.kind, dv, v, acc, pv, selfout, P.t);
   if (P.mode == MODE_DU) {
-    if (two && ((s & 1) == 0)) {
-      *reinterpret_cast<double2*>(P.du + s) = make_double2(dv[0], dv[1]);
+    if (ND_MAX_VDIM == 2 && dim == 2 && ((s & 1) == 0)) {
+      *reinterpret_cast<double2*>(P.du + s) = make_double2(dv[0], dv[ND_MAX_VDIM > 1 ? 1 : 0]);
     } else {
-      P.du[s] = dv[0];
-      if (two) P.du[s + 1] = dv[1];
+#pragma unroll
+      for (int c = 0; c < ND_MAX_VDIM; ++c)
+        if (c < dim) P.du[s + c] = dv[c];
     }
     return;
   }
   // MODE_RK: classical RK4, operation order of the CPU restatement's rk4:
   //   u <- u + (dt/6)*(((k1 + 2k2) + 2k3) + k4)
-  double un[2] = {0.0, 0.0};
+  double un[ND_MAX_VDIM];
 #pragma unroll
-  for (int c = 0; c < 2; ++c) {
-    if (c == 1 && !two) break;
+  for (int c = 0; c < ND_MAX_VDIM; ++c) {
+    un[c] = 0.0;
+    if (c >= dim) continue;
     const long long idx = s + c;
     if (P.stage == 1) {
       P.ksum[idx] = dv[c];
@@ -258,17 +305,17 @@ __device__ __forceinline__ void vertex_phase(const KParams& P, const VBDev& B, i
   }
   if (!P.gather_from_u) {
     double out[VD];
-    vertex_g(B.kind, VD, out, un, pv);
+    vertex_g(B.kind, VD, out, un, pv, P.t);
 #pragma unroll
     for (int k = 0; k < VD; ++k) P.vout_next[(long long)row * VD + k] = out[k];
   }
 }
 
-// loads the (<= 2) states of a row from global memory
+// loads the (<= ND_MAX_VDIM) states of a row from global memory
 __device__ __forceinline__ void load_vertex_state(const KParams& P, const VBDev& B, int row, double* v) {
   const long long s = B.state0 + (long long)(row - B.row0) * B.dim;
-  v[0] = P.u[s];
-  v[1] = (B.dim == 2) ? P.u[s + 1] : 0.0;
+#pragma unroll
+  for (int c = 0; c < ND_MAX_VDIM; ++c) v[c] = c < B.dim ? P.u[s + c] : 0.0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -300,7 +347,7 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
 // into the peer's halo buffer (coalesced NVLink stores).  The last publishing block to finish raises this rank's arrival
 // flag on every rank.  Publishing blocks never wait on anything and are scheduled before every tile of the same grid,
 // so tiles that spin on the peers' flags cannot starve them.
-__device__ __forceinline__ void publish_block(const HaloParams& H, int bid, int nblocks) {
+__device__ __noinline__ void publish_block(const HaloParams& H, int bid, int nblocks) {
   const long long tid = (long long)bid * blockDim.x + threadIdx.x;
   const long long nthreads = (long long)nblocks * blockDim.x;
   for (int r = 0; r < H.world; ++r) {
@@ -421,7 +468,7 @@ __global__ void __launch_bounds__(BLOCK, (fused_warps_per_sm(EK) * 32) / BLOCK) 
         kind = E.kind; coupling = E.coupling;
       }
       double val[ED];
-      entry_value<VD, ED>(kind, coupling, side, self, xn, pe, val);
+      entry_value<VD, ED>(kind, coupling, side, self, xn, pe, P.t, val);
 #pragma unroll
       for (int q = 0; q < ED; ++q) part[q] = part[q] + val[q];
     }
@@ -436,7 +483,7 @@ __global__ void __launch_bounds__(BLOCK, (fused_warps_per_sm(EK) * 32) / BLOCK) 
       __syncthreads();
     }
     if (tid == 0) {
-      double acc[ED], v[2];
+      double acc[ED], v[ND_MAX_VDIM];
 #pragma unroll
       for (int q = 0; q < ED; ++q) acc[q] = s_val[q];
       load_vertex_state(P, B, r0, v);
@@ -509,7 +556,7 @@ __global__ void __launch_bounds__(BLOCK, (fused_warps_per_sm(EK) * 32) / BLOCK) 
         kind = E.kind; coupling = E.coupling;
       }
       double val[ED];
-      entry_value<VD, ED>(kind, coupling, side, self, xn[k], P.p + ep[k], val);
+      entry_value<VD, ED>(kind, coupling, side, self, xn[k], P.p + ep[k], P.t, val);
 #pragma unroll
       for (int q = 0; q < ED; ++q) s_val[jj * ED + q] = val[q];
     }
@@ -525,7 +572,7 @@ __global__ void __launch_bounds__(BLOCK, (fused_warps_per_sm(EK) * 32) / BLOCK) 
 #pragma unroll
       for (int q = 0; q < ED; ++q) acc[q] = acc[q] + s_val[jj * ED + q];
     }
-    double self[VD], v[2];
+    double self[VD], v[ND_MAX_VDIM];
 #pragma unroll
     for (int q = 0; q < VD; ++q) self[q] = s_self[tid * VD + q];
     load_vertex_state(P, B, r0 + tid, v);
@@ -534,8 +581,11 @@ __global__ void __launch_bounds__(BLOCK, (fused_warps_per_sm(EK) * 32) / BLOCK) 
 }
 
 // PASS 1 for networks whose vertex outputs are not plain state copies: vout[row*VD + k] = g_v(u, p)
+#ifndef ND_MAX_VOUT
+#define ND_MAX_VOUT 2            // largest vertex output dimension (vdepth)
+#endif
 __global__ void vertex_out_kernel(const VBDev* __restrict__ vb, int n_vb, int vd, const double* __restrict__ u,
-                                  const double* __restrict__ p, double* __restrict__ vout, int nrows_total) {
+                                  const double* __restrict__ p, double* __restrict__ vout, int nrows_total, double t) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= nrows_total) return;
   int b = 0;
@@ -543,9 +593,10 @@ __global__ void vertex_out_kernel(const VBDev* __restrict__ vb, int n_vb, int vd
     if (row >= vb[i].row0) b = i;
   const VBDev B = vb[b];
   const long long i = row - B.row0;
-  double v[2] = {0.0, 0.0}, out[2] = {0.0, 0.0};
-  for (int c = 0; c < B.dim && c < 2; ++c) v[c] = u[B.state0 + i * B.dim + c];
-  vertex_g(B.kind, vd, out, v, p + B.p0 + i * B.pdim);
+  double v[ND_MAX_VDIM], out[ND_MAX_VOUT];
+  for (int c = 0; c < ND_MAX_VDIM; ++c) v[c] = c < B.dim ? u[B.state0 + i * B.dim + c] : 0.0;
+  for (int k = 0; k < ND_MAX_VOUT; ++k) out[k] = 0.0;
+  vertex_g(B.kind, vd, out, v, p + B.p0 + i * B.pdim, t);
   for (int k = 0; k < vd; ++k) vout[(long long)row * vd + k] = out[k];
 }
 
@@ -554,14 +605,22 @@ template <int VD, int ED>
 __global__ void edge_out_kernel(int kind, int coupling, int pdim, int osrc, long long count,
                                 const int* __restrict__ esrc_off, const int* __restrict__ edst_off,
                                 long long p0, long long out0, const double* __restrict__ gsrc,
-                                const double* __restrict__ p, double* __restrict__ o) {
+                                const double* __restrict__ p, double* __restrict__ o, double t) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
   double vs[VD], vd[VD], val[ED];
 #pragma unroll
   for (int k = 0; k < VD; ++k) { vs[k] = gsrc[(long long)esrc_off[i] + k]; vd[k] = gsrc[(long long)edst_off[i] + k]; }
-  edge_g_dst<VD, ED>(kind, val, vs, vd, p + p0 + i * pdim);
   double* oo = o + out0 + i * (osrc + ED);
+  if (coupling == ND_B200_FIDUCIAL) {     // the edge's own two-sided g: both outputs through entry_value
+    double sv[ED];
+    entry_value<VD, ED>(kind, coupling, 1, vs, vd, p + p0 + i * pdim, t, sv);    // side 1: self = src, neighbour = dst
+    entry_value<VD, ED>(kind, coupling, 0, vd, vs, p + p0 + i * pdim, t, val);   // side 0: self = dst, neighbour = src
+#pragma unroll
+    for (int d = 0; d < ED; ++d) { oo[d] = sv[d]; oo[osrc + d] = val[d]; }
+    return;
+  }
+  edge_g_dst<VD, ED>(kind, val, vs, vd, p + p0 + i * pdim, t);
   if (osrc) {
 #pragma unroll
     for (int d = 0; d < ED; ++d) oo[d] = (coupling == ND_B200_ANTISYMMETRIC) ? -val[d] : val[d];
@@ -629,7 +688,7 @@ __global__ void __launch_bounds__(BLOCK) edge_pass_kernel(const __grid_constant_
       ooff = e * (coupling == ND_B200_DIRECTED ? ED : 2 * ED);
     }
     double val[ED];
-    edge_g_dst<VD, ED>(kind, val, vs[k], vd[k], pe);
+    edge_g_dst<VD, ED>(kind, val, vs[k], vd[k], pe, 0.0);
     double* oo = Q.oedge + ooff;
     if (coupling == ND_B200_DIRECTED) {
 #pragma unroll
@@ -685,7 +744,7 @@ __global__ void __launch_bounds__(BLOCK, 2048 / BLOCK) row_pass_kernel(const __g
       __syncthreads();
     }
     if (tid == 0) {
-      double acc[ED], v[2], self[VD];
+      double acc[ED], v[ND_MAX_VDIM], self[VD];
 #pragma unroll
       for (int q = 0; q < ED; ++q) acc[q] = s_val[q];
 #pragma unroll
@@ -726,7 +785,7 @@ __global__ void __launch_bounds__(BLOCK, 2048 / BLOCK) row_pass_kernel(const __g
 #pragma unroll
       for (int q = 0; q < ED; ++q) acc[q] = acc[q] + s_val[jj * ED + q];
     }
-    double self[VD], v[2];
+    double self[VD], v[ND_MAX_VDIM];
 #pragma unroll
     for (int q = 0; q < VD; ++q) self[q] = P.gather_from_u ? 0.0 : P.gsrc[(long long)(r0 + tid) * VD + q];
     load_vertex_state(P, B, r0 + tid, v);
@@ -793,7 +852,7 @@ __device__ __forceinline__ void long_row_block(const KParams& P, const int4 d, d
       }
     }
     double val[ED];
-    entry_value<VD, ED>(kind, coupling, side, self, xn, pl, val);
+    entry_value<VD, ED>(kind, coupling, side, self, xn, pl, P.t, val);
 #pragma unroll
     for (int q = 0; q < ED; ++q) part[q] = part[q] + val[q];
   }
@@ -808,7 +867,7 @@ __device__ __forceinline__ void long_row_block(const KParams& P, const int4 d, d
     __syncthreads();
   }
   if (tid == 0) {
-    double acc[ED], v[2];
+    double acc[ED], v[ND_MAX_VDIM];
 #pragma unroll
     for (int q = 0; q < ED; ++q) acc[q] = s_val[q];
     load_vertex_state(P, B, r0, v);
@@ -911,7 +970,7 @@ __global__ void __launch_bounds__(BLOCK, (WPS * 32) / BLOCK) rhs_jag_kernel(cons
     for (int q = 0; q < U; ++q) {
       if (act[q]) {
         double val[ED];
-        entry_value<VD, ED>(kind[q], coupling[q], nb[q] < 0, self, xn[q], pl[q], val);
+        entry_value<VD, ED>(kind[q], coupling[q], nb[q] < 0, self, xn[q], pl[q], P.t, val);
 #pragma unroll
         for (int d = 0; d < ED; ++d) acc[d] = acc[d] + val[d];
       }
@@ -935,7 +994,7 @@ __global__ void __launch_bounds__(BLOCK, (WPS * 32) / BLOCK) rhs_jag_kernel(cons
   }
   // (6) vertex model
   if (head) {
-    double v[2];
+    double v[ND_MAX_VDIM];
     load_vertex_state(P, B, row, v);
     vertex_phase<VD, ED>(P, B, row, acc, self, v, P.p + B.p0 + (long long)(row - B.row0) * B.pdim);
   }
