@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define ND_B200_ABI_VERSION 2
+#define ND_B200_ABI_VERSION 3
 
 /* status codes (Julia glue rethrows: EINVAL -> ArgumentError, others -> ErrorException) */
 enum {
@@ -73,6 +73,30 @@ typedef struct nd_b200_ebatch {
   int64_t state_first, p_first, out_first, gbuf_first;
 } nd_b200_ebatch;
 
+/* ---- user-supplied component kinds (runtime-compiled, NVRTC) ---------------------------------------------------------
+ * Lifts the fixed registry: a component function the caller can state as CUDA C++ -- hand-written, or
+ * printed from a symbolic model (ModelingToolkit / Symbolics `build_function(...; target=CTarget())`, the path
+ * ext/NetworkDynamicsMTKExt.jl:497-518 takes to a RuntimeGeneratedFunction) -- is spliced into the same fused kernels
+ * and compiled for sm_100a when the engine is created.  Bodies see exactly the arguments of the reference's
+ * component functions (src/component_functions.jl:251-329,532-567), as plain double pointers:
+ *   vertex f : void f(double* dv, const double* v, const double* esum, const double* p, double t)
+ *   vertex g : void g(double* out, const double* v, const double* p, double t)        (NULL = StateMask(1:outdim))
+ *   edge g   : void g(double* e_dst, const double* v_src, const double* v_dst, const double* p, double t)
+ *              wrapped by AntiSymmetric / Symmetric / Directed (ebatch.coupling), or, with two_sided = 1 and
+ *              coupling = ND_B200_FIDUCIAL, the reference's own two-sided form
+ *              void g(double* e_src, double* e_dst, const double* v_src, const double* v_dst, const double* p, double t)
+ * Compiled with --fmad=false like the registry kernels.  A body that does not compile fails nd_b200_create with
+ * ND_B200_EINVAL and the NVRTC log in nd_b200_last_error. */
+#define ND_B200_CUSTOM_KIND_BASE 1000
+typedef struct nd_b200_custom_kind {
+  int32_t kind;            /* >= ND_B200_CUSTOM_KIND_BASE; referenced by vbatch.kind / ebatch.kind */
+  int32_t role;            /* 0 = vertex, 1 = edge                                                */
+  int32_t dim, pdim, outdim;  /* vertex: states, parameters, outputs; edge: 0, parameters, outdim.dst */
+  int32_t two_sided;       /* edge only: body has the Fiducial signature                         */
+  const char* f_body;      /* vertex: body of f; edge: body of g                                  */
+  const char* g_body;      /* vertex: body of g, or NULL for StateMask(1:outdim); edge: NULL      */
+} nd_b200_custom_kind;
+
 typedef struct nd_b200_desc {
   int32_t abi_version;     /* ND_B200_ABI_VERSION                            */
   int32_t device;          /* CUDA device ordinal                            */
@@ -100,6 +124,9 @@ typedef struct nd_b200_desc {
    * the peers fill through nd_b200_rhs_exchange.  Vertices this engine never reads may hold any valid value. */
   const int64_t* gather_offset;
   int64_t gather_len;
+  int32_t n_custom;        /* user-supplied component kinds referenced by the batches */
+  int32_t reserved;
+  const nd_b200_custom_kind* custom;
 } nd_b200_desc;
 
 #define ND_B200_FLAG_NO_EXPORT 1  /* do not keep host copies of the CSR for nd_b200_export_tables */
@@ -152,6 +179,9 @@ int nd_b200_export_tables(const nd_b200_engine*, int64_t* rowptr, int64_t* nbr_v
  * nd_b200_export_tables) stored at jagged position k. */
 int nd_b200_export_jag_sizes(const nd_b200_engine*, int64_t sizes[6]);
 int nd_b200_export_jag(const nd_b200_engine*, int32_t* slices, uint16_t* lanes, int32_t* longs, int32_t* order);
+
+/* the CUDA source generated for an engine with user-supplied kinds (NULL otherwise); owned by the engine */
+const char* nd_b200_custom_source(const nd_b200_engine*);
 
 /* kernel launches issued by this engine since creation (bench.py's gpu_launches) */
 int64_t nd_b200_launch_count(const nd_b200_engine*);

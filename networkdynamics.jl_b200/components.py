@@ -32,6 +32,34 @@ class RegisteredFunction:
 
 
 @dataclass(frozen=True)
+class CudaFunction:
+    """A user-supplied component function stated as the BODY of a CUDA C++ device function; it is spliced into the fused
+    kernels and compiled for sm_100a (NVRTC) when the network is built -- the engine-side counterpart of the reference
+    accepting arbitrary Julia functions (and of MTK models printed with Symbolics' C target,
+    ext/NetworkDynamicsMTKExt.jl:497-518).  Arguments visible to the body, by role (include/nd_b200.h):
+      vertex_f : double* dv, const double* v, const double* esum, const double* p, double t
+      vertex_g : double* out, const double* v, const double* p, double t
+      edge_g   : double* e_dst, const double* v_src, const double* v_dst, const double* p, double t
+      edge_g2  : double* e_src, double* e_dst, const double* v_src, const double* v_dst, const double* p, double t
+                 (the two-sided form; use it unwrapped or as Fiducial(...))
+    `py` is an optional host restatement (same arguments as numpy arrays, returning the outputs) used by tests only."""
+    name: str
+    role: str
+    body: str
+    py: Optional[object] = field(default=None, compare=False, hash=False)
+
+    def __call__(self, *a, **k):  # pragma: no cover
+        raise RuntimeError(f"{self.name} is device code; evaluate it through Network(...)")
+
+
+@dataclass(frozen=True)
+class Fiducial:
+    """the edge's own two-sided g(osrc, odst, ...), src/component_functions.jl:189-203 (user-supplied kinds only)"""
+    g: object
+    coupling = _cabi.FIDUCIAL
+
+
+@dataclass(frozen=True)
 class StateMask:
     """`StateMask(idxs)`: output k is state idxs[k] (1-based), src/component_functions.jl:81-99."""
     idxs: Tuple[int, ...]
@@ -85,6 +113,18 @@ class VertexModel:
         """What batches are formed on: src/construction.jl:245-256 (name/metadata are not part of it)."""
         return ("V", self.f, self.g, self.dim, self.outdim, self.pdim)
 
+    def custom_spec(self):
+        """(role, dim, pdim, outdim, two_sided, f_body, g_body) when f is user-supplied CUDA code, else None"""
+        if not isinstance(self.f, CudaFunction) or self.f.role != "vertex_f":
+            return None
+        if isinstance(self.g, CudaFunction) and self.g.role == "vertex_g":
+            g_body = self.g.body
+        elif isinstance(self.g, StateMask) and self.g.idxs == tuple(range(1, self.outdim + 1)):
+            g_body = None
+        else:
+            return None
+        return (0, self.dim, self.pdim, self.outdim, 0, self.f.body, g_body)
+
     def kernel_kind(self) -> Optional[int]:
         f = self.f
         if not isinstance(f, RegisteredFunction) or f.role != "vertex_f":
@@ -109,6 +149,8 @@ class EdgeModel:
 
     @property
     def coupling(self) -> Optional[int]:
+        if isinstance(self.g, CudaFunction) and self.g.role == "edge_g2":
+            return _cabi.FIDUCIAL
         return getattr(self.g, "coupling", None)
 
     @property
@@ -121,6 +163,18 @@ class EdgeModel:
 
     def component_hash(self):
         return ("E", self.f, self.g, self.dim, self.outdim_src, self.outdim_dst, self.pdim)
+
+    def custom_spec(self):
+        if self.f is not None or self.dim != 0:
+            return None
+        if isinstance(self.g, CudaFunction) and self.g.role == "edge_g2":       # unwrapped two-sided g
+            return (1, 0, self.pdim, self.outdim, 1, self.g.body, None)
+        inner = getattr(self.g, "g", None)
+        if isinstance(inner, CudaFunction):
+            if isinstance(self.g, Fiducial):
+                return (1, 0, self.pdim, self.outdim, 1, inner.body, None) if inner.role == "edge_g2" else None
+            return (1, 0, self.pdim, self.outdim, 0, inner.body, None) if inner.role == "edge_g" else None
+        return None
 
     def kernel_kind(self) -> Optional[int]:
         inner = getattr(self.g, "g", None)

@@ -7,6 +7,8 @@
 // Evaluation: see nd_b200_kernels.cuh.
 #include "nd_b200_kernels.cuh"
 
+#include <nvrtc.h>
+
 #include <algorithm>
 #include <climits>
 #include <cmath>
@@ -82,6 +84,14 @@ struct nd_b200_engine {
   int halo_base = INT_MAX;    // gather offsets >= halo_base address the halo buffer (multi-GPU packed halo)
   long long gather_len = 0;
   int wait_from = 0;          // first tile / slice that reads the halo
+  // user-supplied component kinds: the kernels are compiled at creation time (NVRTC) from the same header
+  struct CustomKind { int kind, role, dim, pdim, outdim, two_sided; std::string f_body, g_body; };
+  std::vector<CustomKind> customs;
+  bool custom = false;
+  int c_pe = 0, c_maxdim = 1;          // template PE (largest edge pdim) and ND_MAX_VDIM of the generated kernels
+  std::string custom_src;
+  cudaLibrary_t c_lib = nullptr;
+  cudaKernel_t c_fused = nullptr, c_jag = nullptr, c_vout = nullptr, c_eout = nullptr;
   bool host_only = false;     // ND_B200_FLAG_HOST_ONLY: tables built, nothing uploaded (layout tests without a GPU)
   std::vector<int4> h_jslices, h_jlong;
   std::vector<uint16_t> h_jlanes;
@@ -139,6 +149,25 @@ int upload(nd_b200_engine* e, T** dst, const std::vector<T>& src) {
 }
 
 // registry: the (dim, pdim, outdim) each kernel was written for
+bool vertex_kind_ok(const nd_b200_vbatch& b, std::string& why);
+bool edge_kind_ok(const nd_b200_ebatch& b, int vdepth, std::string& why);
+const nd_b200_engine::CustomKind* find_custom(const nd_b200_engine* e, int kind, int role) {
+  for (const auto& c : e->customs)
+    if (c.kind == kind && c.role == role) return &c;
+  return nullptr;
+}
+
+bool vertex_kind_ok(const nd_b200_engine* e, const nd_b200_vbatch& b, std::string& why) {
+  if (b.kind >= ND_B200_CUSTOM_KIND_BASE) {
+    const auto* c = find_custom(e, b.kind, 0);
+    if (!c) { why = "vertex kind " + std::to_string(b.kind) + " is not among the descriptor's custom kinds"; return false; }
+    if (c->dim != b.dim || c->pdim != b.pdim || c->outdim != b.outdim) { why = "custom vertex kind " + std::to_string(b.kind) + " declared with other (dim,pdim,outdim)"; return false; }
+    if (c->g_body.empty() && b.outdim > b.dim) { why = "custom vertex kind " + std::to_string(b.kind) + ": StateMask(1:outdim) needs outdim <= dim"; return false; }
+    return true;
+  }
+  return vertex_kind_ok(b, why);
+}
+
 bool vertex_kind_ok(const nd_b200_vbatch& b, std::string& why) {
   struct R { int kind, dim, pdim, outdim; };
   static const R reg[] = {{ND_B200_V_DIFFUSION, 1, 0, 1}, {ND_B200_V_KURAMOTO_FIRST, 1, 1, 1},
@@ -156,6 +185,18 @@ bool vertex_kind_ok(const nd_b200_vbatch& b, std::string& why) {
   why = "vertex kind " + std::to_string(b.kind) + " is not in the B200 kernel registry";
   return false;
 }
+bool edge_kind_ok(const nd_b200_engine* e, const nd_b200_ebatch& b, int vdepth, std::string& why) {
+  if (b.kind >= ND_B200_CUSTOM_KIND_BASE) {
+    const auto* c = find_custom(e, b.kind, 1);
+    if (!c) { why = "edge kind " + std::to_string(b.kind) + " is not among the descriptor's custom kinds"; return false; }
+    if (c->pdim != b.pdim || c->outdim != b.outdim_dst) { why = "custom edge kind " + std::to_string(b.kind) + " declared with other (pdim,outdim)"; return false; }
+    if ((b.coupling == ND_B200_FIDUCIAL) != (c->two_sided != 0)) { why = "custom edge kind " + std::to_string(b.kind) + ": the Fiducial wrapper and a two-sided body go together"; return false; }
+    return true;
+  }
+  if (b.coupling == ND_B200_FIDUCIAL) { why = "Fiducial edges need a user-supplied (custom) kind"; return false; }
+  return edge_kind_ok(b, vdepth, why);
+}
+
 bool edge_kind_ok(const nd_b200_ebatch& b, int vdepth, std::string& why) {
   struct R { int kind, pdim, odst, vdepth; };
   static const R reg[] = {{ND_B200_E_DIFFUSION, 1, 1, 1}, {ND_B200_E_DIFFUSION_NOP, 0, 1, 1},
@@ -223,10 +264,14 @@ template <int VD, int ED, int EK, int PE>
 cudaError_t launch_shape(const nd_b200_engine* e, const KParams& P, cudaStream_t st) {
   const int grid = (e->launch_nblk >= 0 ? e->launch_nblk : e->nblocks) + P.n_pub;
   if (grid == 0) return cudaSuccess;
-  if (e->block == 256 && e->ept == 8) rhs_fused_kernel<VD, ED, EK, PE, 256, 8><<<grid, 256, 0, st>>>(P);
-  else if (e->block == 256 && e->ept == 4) rhs_fused_kernel<VD, ED, EK, PE, 256, 4><<<grid, 256, 0, st>>>(P);
-  else if (e->block == 128 && e->ept == 8) rhs_fused_kernel<VD, ED, EK, PE, 128, 8><<<grid, 128, 0, st>>>(P);
-  else if (e->block == 128 && e->ept == 4) rhs_fused_kernel<VD, ED, EK, PE, 128, 4><<<grid, 128, 0, st>>>(P);
+  if (e->halo_base != INT_MAX) {   // multi-GPU variant, default launch shape only
+    if (e->block != 128 || e->ept != 4) return cudaErrorInvalidConfiguration;
+    rhs_fused_kernel<VD, ED, EK, PE, 128, 4, true><<<grid, 128, 0, st>>>(P);
+  }
+  else if (e->block == 256 && e->ept == 8) rhs_fused_kernel<VD, ED, EK, PE, 256, 8, false><<<grid, 256, 0, st>>>(P);
+  else if (e->block == 256 && e->ept == 4) rhs_fused_kernel<VD, ED, EK, PE, 256, 4, false><<<grid, 256, 0, st>>>(P);
+  else if (e->block == 128 && e->ept == 8) rhs_fused_kernel<VD, ED, EK, PE, 128, 8, false><<<grid, 128, 0, st>>>(P);
+  else if (e->block == 128 && e->ept == 4) rhs_fused_kernel<VD, ED, EK, PE, 128, 4, false><<<grid, 128, 0, st>>>(P);
   else return cudaErrorInvalidConfiguration;
   return cudaGetLastError();
 }
@@ -238,9 +283,13 @@ cudaError_t launch_jag_u(const nd_b200_engine* e, const KParams& P, cudaStream_t
   const int grid = (e->launch_nblk >= 0 ? e->launch_nblk : e->n_jag_blocks + e->n_jlong) + P.n_pub;
   if (grid == 0) return cudaSuccess;
   const int wps = e->jag_wps > 0 ? e->jag_wps : jag_warps_per_sm_default(EK);
-  if (wps >= 64) rhs_jag_kernel<VD, ED, EK, PE, BLOCK, U, 64><<<grid, BLOCK, 0, st>>>(P);
-  else if (wps >= 48) rhs_jag_kernel<VD, ED, EK, PE, BLOCK, U, 48><<<grid, BLOCK, 0, st>>>(P);
-  else rhs_jag_kernel<VD, ED, EK, PE, BLOCK, U, 32><<<grid, BLOCK, 0, st>>>(P);
+  if (e->halo_base != INT_MAX) {   // multi-GPU variant: one occupancy setting
+    if (wps >= 48) rhs_jag_kernel<VD, ED, EK, PE, BLOCK, U, 48, true><<<grid, BLOCK, 0, st>>>(P);
+    else rhs_jag_kernel<VD, ED, EK, PE, BLOCK, U, 32, true><<<grid, BLOCK, 0, st>>>(P);
+  }
+  else if (wps >= 64) rhs_jag_kernel<VD, ED, EK, PE, BLOCK, U, 64, false><<<grid, BLOCK, 0, st>>>(P);
+  else if (wps >= 48) rhs_jag_kernel<VD, ED, EK, PE, BLOCK, U, 48, false><<<grid, BLOCK, 0, st>>>(P);
+  else rhs_jag_kernel<VD, ED, EK, PE, BLOCK, U, 32, false><<<grid, BLOCK, 0, st>>>(P);
   return cudaGetLastError();
 }
 template <int VD, int ED, int EK, int PE>
@@ -258,7 +307,17 @@ cudaError_t launch_jag(nd_b200_engine* e, const KParams& P, cudaStream_t st) {
   }
 }
 
+cudaError_t launch_custom(nd_b200_engine* e, const KParams& P, cudaStream_t st) {
+  const int nb = e->jag ? e->n_jag_blocks + e->n_jlong : e->nblocks;
+  const int grid = (e->launch_nblk >= 0 ? e->launch_nblk : nb) + P.n_pub;
+  if (grid == 0) return cudaSuccess;
+  e->launches++;
+  void* args[] = {const_cast<KParams*>(&P)};
+  return cudaLaunchKernel((const void*)(e->jag ? e->c_jag : e->c_fused), dim3((unsigned)grid), dim3(128), args, 0, st);
+}
+
 cudaError_t launch_fused(nd_b200_engine* e, const KParams& P, cudaStream_t st) {
+  if (e->custom) return launch_custom(e, P, st);
   if (e->jag) return launch_jag(e, P, st);
   if (e->split) {
     // edge pass (PASS 5) then row pass (aggregate + PASS 6); P.gsrc is the gather source of this evaluation
@@ -282,6 +341,11 @@ cudaError_t launch_vout(nd_b200_engine* e, const double* u, const double* p, dou
   const int nb = (int)((e->nrows_total + T - 1) / T);
   if (nb == 0) return cudaSuccess;
   e->launches++;
+  if (e->custom) {
+    const VBDev* vb = e->d_vb; int nvb = (int)e->hvb.size(), vd = e->vdepth, nr = (int)e->nrows_total; double t0 = 0.0;
+    void* args[] = {&vb, &nvb, &vd, &u, &p, &vout, &nr, &t0};
+    return cudaLaunchKernel((const void*)e->c_vout, dim3((unsigned)nb), dim3(T), args, 0, st);
+  }
   vertex_out_kernel<<<nb, T, 0, st>>>(e->d_vb, (int)e->hvb.size(), e->vdepth, u, p, vout, (int)e->nrows_total, 0.0);
   return cudaGetLastError();
 }
@@ -295,6 +359,104 @@ int ensure_events(nd_b200_engine* e, std::vector<cudaEvent_t>& v, size_t need) {
   return 0;
 }
 
+// ---- user-supplied kinds: source generation + NVRTC ------------------------------------------------------------------
+// nd_b200_kernels.cuh as text (generated next to this file by the build, see _cabi.build): the run-time compiled kernels
+// are the SAME templates as the precompiled ones, with the user's functions spliced into the model switches.
+static const char* const kKernelHeaderText[] = {
+#include "nd_b200_kernels_embed.inc"
+};
+
+std::string custom_source(const nd_b200_engine* e, int vdepth) {
+  std::string src;
+  char buf[512];
+  src += "// generated by libnd_b200 (user-supplied component kinds)\n";
+  src += "typedef unsigned char uint8_t;\ntypedef unsigned short uint16_t;\ntypedef int int32_t;\ntypedef long long int64_t;\n";
+  snprintf(buf, sizeof buf,
+           "enum { ND_B200_V_DIFFUSION = %d, ND_B200_V_KURAMOTO_FIRST = %d, ND_B200_V_KURAMOTO_SECOND = %d, ND_B200_V_KURAMOTO_SECOND_BENCH = %d, ND_B200_V_SWING_DQ = %d };\n",
+           ND_B200_V_DIFFUSION, ND_B200_V_KURAMOTO_FIRST, ND_B200_V_KURAMOTO_SECOND, ND_B200_V_KURAMOTO_SECOND_BENCH, ND_B200_V_SWING_DQ);
+  src += buf;
+  snprintf(buf, sizeof buf, "enum { ND_B200_E_DIFFUSION = %d, ND_B200_E_DIFFUSION_NOP = %d, ND_B200_E_KURAMOTO = %d, ND_B200_E_LINE_DQ = %d };\n",
+           ND_B200_E_DIFFUSION, ND_B200_E_DIFFUSION_NOP, ND_B200_E_KURAMOTO, ND_B200_E_LINE_DQ);
+  src += buf;
+  snprintf(buf, sizeof buf, "enum { ND_B200_ANTISYMMETRIC = %d, ND_B200_SYMMETRIC = %d, ND_B200_DIRECTED = %d, ND_B200_FIDUCIAL = %d };\n",
+           ND_B200_ANTISYMMETRIC, ND_B200_SYMMETRIC, ND_B200_DIRECTED, ND_B200_FIDUCIAL);
+  src += buf;
+  snprintf(buf, sizeof buf, "#define ND_MAX_VDIM %d\n#define ND_MAX_VOUT %d\n", std::max(e->c_maxdim, 1), std::max(vdepth, 1));
+  src += buf;
+  std::string edge_cases, fid_cases, vf_cases, vg_cases;
+  src += "namespace ndb_user {\n";
+  for (const auto& c : e->customs) {
+    const std::string id = std::to_string(c.kind);
+    if (c.role == 0) {
+      src += "__device__ __forceinline__ void vertex_f_" + id + "(double* __restrict__ dv, const double* __restrict__ v, const double* __restrict__ esum, const double* __restrict__ p, double t) {\n" + c.f_body + "\n}\n";
+      vf_cases += " case " + id + ": ndb_user::vertex_f_" + id + "(dv, v, acc, pv, t); break;";
+      if (!c.g_body.empty()) {
+        src += "__device__ __forceinline__ void vertex_g_" + id + "(double* __restrict__ out, const double* __restrict__ v, const double* __restrict__ p, double t) {\n" + c.g_body + "\n}\n";
+        vg_cases += " case " + id + ": ndb_user::vertex_g_" + id + "(out, v, pv, t); break;";
+      }
+    } else if (c.two_sided) {
+      src += "__device__ __forceinline__ void edge_g_" + id + "(double* __restrict__ e_src, double* __restrict__ e_dst, const double* __restrict__ v_src, const double* __restrict__ v_dst, const double* __restrict__ p, double t) {\n" + c.f_body + "\n}\n";
+      fid_cases += " case " + id + ": ndb_user::edge_g_" + id + "(osrc, odst, vs, vd, pe, t); break;";
+    } else {
+      src += "__device__ __forceinline__ void edge_g_" + id + "(double* __restrict__ e_dst, const double* __restrict__ v_src, const double* __restrict__ v_dst, const double* __restrict__ p, double t) {\n" + c.f_body + "\n}\n";
+      edge_cases += " case " + id + ": ndb_user::edge_g_" + id + "(odst, vs, vd, pe, t); break;";
+    }
+  }
+  src += "}  // namespace ndb_user\n";
+  src += "#define ND_CUSTOM_EDGE_CASES" + edge_cases + "\n";
+  src += "#define ND_CUSTOM_EDGE_FID_CASES" + fid_cases + "\n";
+  src += "#define ND_CUSTOM_VERTEX_F_CASES" + vf_cases + "\n";
+  src += "#define ND_CUSTOM_VERTEX_G_CASES" + vg_cases + "\n";
+  for (const char* part : kKernelHeaderText) src += part;
+  return src;
+}
+
+// compile the generated source for sm_100a; on success load it (unless host_only) and fetch the kernels
+int compile_custom(nd_b200_engine* e, int vdepth, int edepth) {
+  e->custom_src = custom_source(e, vdepth);
+  nvrtcProgram prog = nullptr;
+  if (nvrtcCreateProgram(&prog, e->custom_src.c_str(), "nd_b200_custom.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS)
+    return fail(e, ND_B200_ECUDA, "nvrtcCreateProgram failed");
+  char nm[4][160];
+  const int ek = e->ek, pe = e->c_pe;
+  const char* halo = e->halo_base != INT_MAX ? "true" : "false";
+  snprintf(nm[0], sizeof nm[0], "ndb::rhs_fused_kernel<%d, %d, %d, %d, 128, 4, %s>", vdepth, edepth, ek, pe, halo);
+  snprintf(nm[1], sizeof nm[1], "ndb::rhs_jag_kernel<%d, %d, %d, %d, 128, 2, 48, %s>", vdepth, edepth, ek, pe, halo);
+  snprintf(nm[2], sizeof nm[2], "ndb::vertex_out_kernel");
+  snprintf(nm[3], sizeof nm[3], "ndb::edge_out_kernel<%d, %d>", vdepth, edepth);
+  for (int k = 0; k < 4; ++k) nvrtcAddNameExpression(prog, nm[k]);
+  const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "--fmad=false", "-lineinfo", "-default-device"};
+  const nvrtcResult rc = nvrtcCompileProgram(prog, 5, opts);
+  if (rc != NVRTC_SUCCESS) {
+    size_t n = 0;
+    nvrtcGetProgramLogSize(prog, &n);
+    std::string log(n, '\0');
+    if (n) nvrtcGetProgramLog(prog, &log[0]);
+    nvrtcDestroyProgram(&prog);
+    if (log.size() > 400) log.resize(400);
+    return fail(e, ND_B200_EINVAL, "user-supplied component code does not compile: %s", log.c_str());
+  }
+  if (e->host_only) { nvrtcDestroyProgram(&prog); return ND_B200_OK; }
+  size_t nbin = 0;
+  nvrtcGetCUBINSize(prog, &nbin);
+  std::vector<char> cubin(nbin);
+  nvrtcGetCUBIN(prog, cubin.data());
+  std::string lowered[4];
+  for (int k = 0; k < 4; ++k) {
+    const char* ln = nullptr;
+    if (nvrtcGetLoweredName(prog, nm[k], &ln) != NVRTC_SUCCESS || !ln) { nvrtcDestroyProgram(&prog); return fail(e, ND_B200_ECUDA, "no lowered name for %s", nm[k]); }
+    lowered[k] = ln;
+  }
+  nvrtcDestroyProgram(&prog);
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  CUDA_TRY(e, cudaLibraryLoadData(&e->c_lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+  CUDA_TRY(e, cudaLibraryGetKernel(&e->c_fused, e->c_lib, lowered[0].c_str()));
+  CUDA_TRY(e, cudaLibraryGetKernel(&e->c_jag, e->c_lib, lowered[1].c_str()));
+  CUDA_TRY(e, cudaLibraryGetKernel(&e->c_vout, e->c_lib, lowered[2].c_str()));
+  CUDA_TRY(e, cudaLibraryGetKernel(&e->c_eout, e->c_lib, lowered[3].c_str()));
+  return ND_B200_OK;
+}
+
 int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
   if (d->abi_version != ND_B200_ABI_VERSION) return fail(e, ND_B200_EINVAL, "descriptor abi_version %d != %d", d->abi_version, ND_B200_ABI_VERSION);
   if (d->nv <= 0) return fail(e, ND_B200_EINVAL, "network needs at least one vertex");
@@ -305,8 +467,19 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
   e->nv = d->nv; e->ne = d->ne; e->vdepth = d->vdepth; e->edepth = d->ne > 0 ? d->edepth : d->vdepth;
   e->lastidx_dynamic = d->lastidx_dynamic; e->lastidx_p = d->lastidx_p;
   e->lastidx_out = d->lastidx_out; e->lastidx_aggr = d->lastidx_aggr;
-  if (!((d->vdepth == 1 && (d->ne == 0 || d->edepth == 1)) || (d->vdepth == 2 && d->edepth == 2)))
-    return fail(e, ND_B200_EUNSUPPORTED, "no kernel for (vdepth,edepth)=(%d,%d); available: (1,1),(2,2)", d->vdepth, d->edepth);
+  if (d->n_custom < 0 || (d->n_custom > 0 && !d->custom)) return fail(e, ND_B200_EINVAL, "bad custom kind table");
+  for (int k = 0; k < d->n_custom; ++k) {
+    const nd_b200_custom_kind& c = d->custom[k];
+    if (c.kind < ND_B200_CUSTOM_KIND_BASE || (c.role != 0 && c.role != 1) || !c.f_body) return fail(e, ND_B200_EINVAL, "custom kind %d: id must be >= %d, role 0|1, f_body non-NULL", c.kind, ND_B200_CUSTOM_KIND_BASE);
+    if (c.dim < 0 || c.dim > 16 || c.pdim < 0 || c.pdim > 64 || c.outdim < 1 || c.outdim > 8) return fail(e, ND_B200_EUNSUPPORTED, "custom kind %d: dims outside dim<=16, pdim<=64, 1<=outdim<=8", c.kind);
+    e->customs.push_back(nd_b200_engine::CustomKind{c.kind, c.role, c.dim, c.pdim, c.outdim, c.two_sided, c.f_body, c.g_body ? c.g_body : ""});
+  }
+  for (int b = 0; b < d->n_vbatches; ++b) e->custom = e->custom || d->vbatches[b].kind >= ND_B200_CUSTOM_KIND_BASE;
+  for (int b = 0; b < d->n_ebatches; ++b) e->custom = e->custom || d->ebatches[b].kind >= ND_B200_CUSTOM_KIND_BASE;
+  if (!e->custom && !((d->vdepth == 1 && (d->ne == 0 || d->edepth == 1)) || (d->vdepth == 2 && d->edepth == 2)))
+    return fail(e, ND_B200_EUNSUPPORTED, "no precompiled kernel for (vdepth,edepth)=(%d,%d); available: (1,1),(2,2) -- other shapes need user-supplied kinds", d->vdepth, d->edepth);
+  if (e->custom && (d->vdepth < 1 || d->vdepth > 8 || (d->ne > 0 && (d->edepth < 1 || d->edepth > 8))))
+    return fail(e, ND_B200_EUNSUPPORTED, "(vdepth,edepth)=(%d,%d) outside 1..8", d->vdepth, d->edepth);
   if (d->lastidx_dynamic >= INT_MAX || d->lastidx_p >= INT_MAX || d->lastidx_out >= (long long)INT_MAX * 2)
     return fail(e, ND_B200_EUNSUPPORTED, "network too large for 32-bit offsets");
   e->long_thr = d->long_row_threshold > 0 ? d->long_row_threshold : 128;
@@ -319,7 +492,7 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
   for (int b = 0; b < d->n_vbatches; ++b) {
     const nd_b200_vbatch& vb = d->vbatches[b];
     std::string why;
-    if (!vertex_kind_ok(vb, why)) return fail(e, ND_B200_EUNSUPPORTED, "%s (no CPU fallback)", why.c_str());
+    if (!vertex_kind_ok(e, vb, why)) return fail(e, ND_B200_EUNSUPPORTED, "%s (no CPU fallback)", why.c_str());
     if (vb.outdim != d->vdepth) return fail(e, ND_B200_EINVAL, "vertex batch %d outdim %d != vdepth %d", b + 1, vb.outdim, d->vdepth);
     if (vb.count <= 0 || !vb.indices) return fail(e, ND_B200_EINVAL, "vertex batch %d is empty", b + 1);
     if (vb.state_first != state_expect) return fail(e, ND_B200_EINVAL, "vertex batch %d: statestride.first %lld, expected %lld", b + 1, (long long)vb.state_first, state_expect);
@@ -334,6 +507,9 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
     }
     row += vb.count; state_expect += vb.count * vb.dim; out_expect += vb.count * vb.outdim;
     if (vb.kind == ND_B200_V_SWING_DQ) all_statemask1 = false;
+    if (vb.kind >= ND_B200_CUSTOM_KIND_BASE && !find_custom(e, vb.kind, 0)->g_body.empty()) all_statemask1 = false;
+    if (vb.dim > (e->custom ? 16 : 2)) return fail(e, ND_B200_EUNSUPPORTED, "vertex batch %d: dim %d", b + 1, vb.dim);
+    e->c_maxdim = std::max(e->c_maxdim, vb.dim);
   }
   if (row != d->nv) return fail(e, ND_B200_EINVAL, "vertex batches cover %lld of %lld vertices", row, (long long)d->nv);
   e->nrows_total = row;
@@ -377,9 +553,11 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
   for (int b = 0; b < d->n_ebatches; ++b) {
     const nd_b200_ebatch& eb = d->ebatches[b];
     std::string why;
-    if (!edge_kind_ok(eb, d->vdepth, why)) return fail(e, ND_B200_EUNSUPPORTED, "%s (no CPU fallback)", why.c_str());
+    if (!edge_kind_ok(e, eb, d->vdepth, why)) return fail(e, ND_B200_EUNSUPPORTED, "%s (no CPU fallback)", why.c_str());
+    if (eb.outdim_dst != d->edepth) return fail(e, ND_B200_EINVAL, "edge batch %d: outdim.dst %d != edepth %d", b + 1, eb.outdim_dst, d->edepth);
+    e->c_pe = std::max(e->c_pe, eb.pdim);
     if (eb.dim != 0) return fail(e, ND_B200_EUNSUPPORTED, "edge batch %d has dynamic states (ODE edges are not supported by the B200 engine)", b + 1);
-    if (eb.coupling != ND_B200_ANTISYMMETRIC && eb.coupling != ND_B200_SYMMETRIC && eb.coupling != ND_B200_DIRECTED)
+    if (eb.coupling != ND_B200_ANTISYMMETRIC && eb.coupling != ND_B200_SYMMETRIC && eb.coupling != ND_B200_DIRECTED && eb.coupling != ND_B200_FIDUCIAL)
       return fail(e, ND_B200_EUNSUPPORTED, "edge batch %d: unsupported output wrapper %d", b + 1, eb.coupling);
     const int osrc_expect = eb.coupling == ND_B200_DIRECTED ? 0 : eb.outdim_dst;
     if (eb.outdim_src != osrc_expect) return fail(e, ND_B200_EINVAL, "edge batch %d: outdim.src %d inconsistent with wrapper", b + 1, eb.outdim_src);
@@ -398,7 +576,7 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
   if (eout_expect - 1 != d->lastidx_out) return fail(e, ND_B200_EINVAL, "lastidx_out %lld inconsistent with batches (%lld)", (long long)d->lastidx_out, eout_expect - 1);
   if (state_expect - 1 != d->lastidx_dynamic) return fail(e, ND_B200_EINVAL, "lastidx_dynamic %lld inconsistent with vertex batches (%lld)", (long long)d->lastidx_dynamic, state_expect - 1);
   e->ek = (d->n_ebatches == 1) ? d->ebatches[0].kind : EK_GENERIC;
-  if (d->vdepth == 2 && d->n_ebatches > 1) {
+  if (!e->custom && d->vdepth == 2 && d->n_ebatches > 1) {
     // all (2,2) batches must be LINE_DQ with one coupling (single templated kernel)
     for (int b = 1; b < d->n_ebatches; ++b)
       if (d->ebatches[b].coupling != d->ebatches[0].coupling) return fail(e, ND_B200_EUNSUPPORTED, "mixed wrappers for dq lines");
@@ -427,15 +605,15 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
   std::vector<int> h_nbr((size_t)std::max<long long>(e->nentries, 1)), h_epar;
   std::vector<uint8_t> h_ebid;
   if (any_epar) h_epar.assign((size_t)std::max<long long>(e->nentries, 1), 0);
-  if (e->ek == EK_GENERIC && d->vdepth == 1) h_ebid.assign((size_t)std::max<long long>(e->nentries, 1), 0);
+  if (e->ek == EK_GENERIC && (d->vdepth == 1 || e->custom)) h_ebid.assign((size_t)std::max<long long>(e->nentries, 1), 0);
   if (keep) { e->h_nbr_vid.resize((size_t)e->nentries); e->h_eid.resize((size_t)e->nentries); e->h_side.resize((size_t)e->nentries); }
   // split mode tables: per entry its position in the edge part of `o`; per edge (in `o` order) the gather offsets
-  const bool generic_edges = (e->ek == EK_GENERIC && d->vdepth == 1);
+  const bool generic_edges = (e->ek == EK_GENERIC && (d->vdepth == 1 || e->custom));
   e->oedge_base = d->nv * (long long)d->vdepth;
   e->oedge_len = d->lastidx_out - e->oedge_base;
   e->ne_all = d->ne;
   bool want_split = false;
-  if (const char* s = getenv("ND_B200_KERNEL")) want_split = !strcmp(s, "split") && nrows_owned == e->nrows_total && !(d->vdepth == 2 && d->n_ebatches > 1);
+  if (const char* s = getenv("ND_B200_KERNEL")) want_split = !strcmp(s, "split") && nrows_owned == e->nrows_total && !(d->vdepth == 2 && d->n_ebatches > 1) && !e->custom;
   if (want_split && e->oedge_len >= INT_MAX) return fail(e, ND_B200_EUNSUPPORTED, "edge output buffer exceeds 2^31 scalars on one device");
   std::vector<int> h_oidx(want_split ? (size_t)std::max<long long>(e->nentries, 1) : 1), h_es(want_split ? (size_t)std::max<long long>(d->ne, 1) : 1), h_et(want_split ? (size_t)std::max<long long>(d->ne, 1) : 1);
   std::vector<int> h_eepar, h_eooff;
@@ -625,7 +803,7 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
   std::vector<int> jnbr;
   std::vector<int2> jent;
   std::vector<uint8_t> jebid;
-  const bool jag_pe = any_epar || generic_edges;   // kernels instantiated with PE > 0 read {nbr, epar} pairs
+  const bool jag_pe = any_epar || (generic_edges && !e->custom);   // kernels instantiated with PE > 0 read {nbr, epar} pairs
   if (e->jag) {
     e->jsplit = 32;
     if (const char* s = getenv("ND_B200_JAG_SPLIT")) e->jsplit = std::min(63, std::max(1, atoi(s)));
@@ -736,7 +914,12 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
   e->blk_rows_monotone = true;
   for (size_t k = 0; k + 1 < e->blk_rmin.size(); ++k)
     if (e->blk_rmin[k + 1] <= e->blk_rmax[k]) { e->blk_rows_monotone = false; break; }
-  if (d->flags & ND_B200_FLAG_HOST_ONLY) { e->host_only = true; return ND_B200_OK; }
+  if (d->flags & ND_B200_FLAG_HOST_ONLY) e->host_only = true;
+  if (e->custom) {
+    if (e->jag) { e->jag_wps = 48; e->jag_u = 2; }   // the one jagged instantiation that is compiled for user-supplied kinds
+    if (int rc = compile_custom(e, d->vdepth, e->edepth)) return rc;
+  }
+  if (e->host_only) return ND_B200_OK;
   CUDA_TRY(e, cudaSetDevice(e->device));
   if (e->jag) {
     if (upload(e, &e->d_vb, dvb) || upload(e, &e->d_eb, deb) || upload(e, &e->d_jslices, jslices) || upload(e, &e->d_jlanes, jlanes) ||
@@ -753,7 +936,7 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
       upload(e, &e->d_vb, dvb) || upload(e, &e->d_eb, deb))
     return ND_B200_ECUDA;
   if (any_epar && upload(e, &e->d_epar, h_epar)) return ND_B200_ECUDA;
-  if (e->ek == EK_GENERIC && d->vdepth == 1 && upload(e, &e->d_ebid, h_ebid)) return ND_B200_ECUDA;
+  if (!h_ebid.empty() && upload(e, &e->d_ebid, h_ebid)) return ND_B200_ECUDA;
   if (!e->gather_from_u) {
     for (int k = 0; k < 2; ++k) CUDA_TRY(e, cudaMalloc((void**)&e->d_vout[k], sizeof(double) * (size_t)(e->nrows_total * e->vdepth)));
   }
@@ -867,6 +1050,7 @@ void nd_b200_destroy(nd_b200_engine* e) {
   cudaFree(e->d_vb); cudaFree(e->d_eb); cudaFree(e->d_vout[0]); cudaFree(e->d_vout[1]);
   cudaFree(e->d_tiles); cudaFree(e->d_oidx); cudaFree(e->d_es); cudaFree(e->d_et); cudaFree(e->d_eepar); cudaFree(e->d_eooff);
   cudaFree(e->d_eebid); cudaFree(e->d_oedge);
+  if (e->c_lib) cudaLibraryUnload(e->c_lib);
   cudaFree(e->d_jslices); cudaFree(e->d_jlanes); cudaFree(e->d_jnbr); cudaFree(e->d_jent); cudaFree(e->d_jebid); cudaFree(e->d_jlong);
   for (int* q : e->d_esrc_off) cudaFree(q);
   for (int* q : e->d_edst_off) cudaFree(q);
@@ -1014,7 +1198,13 @@ int nd_b200_get_buffers(nd_b200_engine* e, double* o, double* aggbuf, const doub
       const int T = 256;
       const int nb = (int)((h.count + T - 1) / T);
       e->launches++;
-      if (e->vdepth == 2)
+      if (e->custom) {
+        int kind = h.kind, coupling = h.coupling, pdim = h.pdim, osrc = h.osrc;
+        long long count = h.count, p0 = h.p0, out0 = h.out0;
+        const int *es = e->d_esrc_off[b], *et = e->d_edst_off[b];
+        void* args[] = {&kind, &coupling, &pdim, &osrc, &count, &es, &et, &p0, &out0, &gsrc, &p, &o, &t};
+        CUDA_TRY(e, cudaLaunchKernel((const void*)e->c_eout, dim3((unsigned)nb), dim3(T), args, 0, st));
+      } else if (e->vdepth == 2)
         edge_out_kernel<2, 2><<<nb, T, 0, st>>>(h.kind, h.coupling, h.pdim, h.osrc, h.count, e->d_esrc_off[b], e->d_edst_off[b], h.p0, h.out0, gsrc, p, o, t);
       else
         edge_out_kernel<1, 1><<<nb, T, 0, st>>>(h.kind, h.coupling, h.pdim, h.osrc, h.count, e->d_esrc_off[b], e->d_edst_off[b], h.p0, h.out0, gsrc, p, o, t);
@@ -1043,7 +1233,13 @@ int nd_b200_rk4(nd_b200_engine* e, double* u, const double* p, double t0, double
     CUDA_TRY(e, cudaMalloc((void**)&e->d_ksum, nb));
   }
   if (!e->gather_from_u) CUDA_TRY(e, launch_vout(e, u, p, e->d_vout[0], st));
-  // The registry models are autonomous, so one captured step can be replayed for every t.
+  // The registry models are autonomous, so one captured step can be replayed for every t.  User-supplied kinds may read
+  // t: their steps are enqueued one by one with the right stage times.
+  if (e->custom) {
+    for (int64_t k = 0; k < nsteps; ++k)
+      if (int rc = rk4_step_enqueue(e, u, p, t0 + (double)k * dt, dt, st)) return rc;
+    return ND_B200_OK;
+  }
   const int UNROLL = 8;
   const int per_graph = (int)std::min<int64_t>(UNROLL, nsteps);
   if (!e->graph_exec || e->graph_u != u || e->graph_p != p || e->graph_dt != dt || e->graph_steps != per_graph) {
@@ -1105,6 +1301,8 @@ int nd_b200_export_jag(const nd_b200_engine* e, int32_t* slices, uint16_t* lanes
   for (size_t k = 0; k < e->h_jorder.size(); ++k) order[k] = e->h_jorder[k];
   return ND_B200_OK;
 }
+
+const char* nd_b200_custom_source(const nd_b200_engine* e) { return (e && e->custom) ? e->custom_src.c_str() : nullptr; }
 
 int64_t nd_b200_launch_count(const nd_b200_engine* e) { return e ? e->launches : 0; }
 

@@ -347,7 +347,7 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
 // into the peer's halo buffer (coalesced NVLink stores).  The last publishing block to finish raises this rank's arrival
 // flag on every rank.  Publishing blocks never wait on anything and are scheduled before every tile of the same grid,
 // so tiles that spin on the peers' flags cannot starve them.
-__device__ __noinline__ void publish_block(const HaloParams& H, int bid, int nblocks) {
+__device__ __forceinline__ void publish_block(const HaloParams& H, int bid, int nblocks) {
   const long long tid = (long long)bid * blockDim.x + threadIdx.x;
   const long long nthreads = (long long)nblocks * blockDim.x;
   for (int r = 0; r < H.world; ++r) {
@@ -410,18 +410,22 @@ __device__ __forceinline__ void halo_wait_warp(const KParams& P) {
 }
 
 // gather source of an offset: the state vector (or materialised vertex outputs) below halo_base, the halo buffer above
+template <bool HALO>
 __device__ __forceinline__ const double* gather_ptr(const KParams& P, int off) {
-  return (off >= P.halo_base ? P.halo - P.halo_base : P.gsrc) + off;
+  if constexpr (HALO) return (off >= P.halo_base ? P.halo - P.halo_base : P.gsrc) + off;
+  else return P.gsrc + off;
 }
 
 // Occupancy is the lever for this kernel (it is bound by the L2 sector bandwidth of the random gathers and hides
 // latency with many independent blocks), so registers are capped through the min-blocks launch bound.
 // Measured on B200 (profiles/r01_tuning.md): 64 resident warps/SM (32 registers) is best for the arithmetic-free
 // diffusion kernels, 48 warps/SM (40 registers) for the kernels that evaluate sin / complex division.
-constexpr int fused_warps_per_sm(int ek) {
+__host__ __device__ constexpr int fused_warps_per_sm(int ek) {
   return (ek == ND_B200_E_DIFFUSION || ek == ND_B200_E_DIFFUSION_NOP) ? 64 : 48;
 }
-template <int VD, int ED, int EK, int PE, int BLOCK, int EPT>
+// HALO = true: the multi-GPU variant (publishing blocks, flag waits, gathers from [u | halo]); the single-GPU variant
+// carries none of it (the 32-register diffusion kernels lose 9-19 % when that code shares their register allocation).
+template <int VD, int ED, int EK, int PE, int BLOCK, int EPT, bool HALO>
 __global__ void __launch_bounds__(BLOCK, (fused_warps_per_sm(EK) * 32) / BLOCK) rhs_fused_kernel(const __grid_constant__ KParams P) {
   constexpr int TILE = BLOCK * EPT;
   static_assert(BLOCK <= 256, "row ids are stored as uint8");
@@ -431,9 +435,11 @@ __global__ void __launch_bounds__(BLOCK, (fused_warps_per_sm(EK) * 32) / BLOCK) 
   __shared__ uint8_t s_rowid[TILE];
 
   const int tid = threadIdx.x;
-  if ((int)blockIdx.x < P.n_pub) { publish_block(P.H, blockIdx.x, P.n_pub); return; }   // multi-GPU only
+  if constexpr (HALO) {
+    if ((int)blockIdx.x < P.n_pub) { publish_block(P.H, blockIdx.x, P.n_pub); return; }
+  }
   // one 16-byte descriptor per thread block: {row0, e0, ne (long rows), ne | nrows<<16 | batch<<25 | long<<31}
-  const int bid = (int)blockIdx.x - P.n_pub + P.blk_off;
+  const int bid = (int)blockIdx.x - (HALO ? P.n_pub : 0) + P.blk_off;
   const int4 d = __ldg(&P.tiles[bid]);
   const int r0 = d.x, e0 = d.y;
   const bool is_long = d.w < 0;
@@ -441,7 +447,9 @@ __global__ void __launch_bounds__(BLOCK, (fused_warps_per_sm(EK) * 32) / BLOCK) 
   const int ne = is_long ? d.z : (d.w & 0xFFFF);
   const VBDev B = P.vb[(d.w >> 25) & 0x3F];
   const int coupling0 = P.n_eb > 0 ? P.eb[0].coupling : 0;
-  if (bid >= P.wait_from) halo_wait(P);   // multi-GPU only: this tile reads the halo (block-uniform)
+  if constexpr (HALO) {
+    if (bid >= P.wait_from) halo_wait(P);   // this tile reads the halo (block-uniform)
+  }
 
   // ---------------- long row: whole block reduces one row with a fixed-shape tree -----------------
   if (is_long) {
@@ -457,7 +465,7 @@ __global__ void __launch_bounds__(BLOCK, (fused_warps_per_sm(EK) * 32) / BLOCK) 
       const int side = nb < 0;
       nb = side ? ~nb : nb;
       double xn[VD];
-      const double* gp = gather_ptr(P, nb);
+      const double* gp = gather_ptr<HALO>(P, nb);
 #pragma unroll
       for (int k = 0; k < VD; ++k) xn[k] = gp[k];
       const double* pe = P.p;
@@ -530,7 +538,7 @@ __global__ void __launch_bounds__(BLOCK, (fused_warps_per_sm(EK) * 32) / BLOCK) 
 #pragma unroll
     for (int q = 0; q < VD; ++q) xn[k][q] = 0.0;
     if (jj < ne) {
-      const double* gp = gather_ptr(P, off);
+      const double* gp = gather_ptr<HALO>(P, off);
       if constexpr (VD == 2) {
         const double2 t2 = *reinterpret_cast<const double2*>(gp);
         xn[k][0] = t2.x; xn[k][1] = t2.y;
@@ -811,11 +819,11 @@ __global__ void __launch_bounds__(BLOCK, 2048 / BLOCK) row_pass_kernel(const __g
 // differs from the sequential sum only in association, like the block tree of the long rows).  Rows that would need
 // more than 32 lanes go to the whole-block path (same code as rhs_fused_kernel's long rows).
 // ------------------------------------------------------------------------------------------------
-constexpr int jag_warps_per_sm_default(int ek) {
+__host__ __device__ constexpr int jag_warps_per_sm_default(int ek) {
   return (ek == ND_B200_E_DIFFUSION || ek == ND_B200_E_DIFFUSION_NOP) ? 64 : 48;
 }
 
-template <int VD, int ED, int EK, int PE, int BLOCK>
+template <int VD, int ED, int EK, int PE, int BLOCK, bool HALO>
 __device__ __forceinline__ void long_row_block(const KParams& P, const int4 d, double* s_val) {
   const int tid = threadIdx.x;
   const int e0 = d.x, r0 = d.y, ne = d.z;
@@ -835,7 +843,7 @@ __device__ __forceinline__ void long_row_block(const KParams& P, const int4 d, d
     const int side = nb < 0;
     nb = side ? ~nb : nb;
     double xn[VD];
-    const double* gp = gather_ptr(P, nb);
+    const double* gp = gather_ptr<HALO>(P, nb);
 #pragma unroll
     for (int k = 0; k < VD; ++k) xn[k] = gp[k];
     int kind = EK, coupling = coupling0, pd = PE;
@@ -846,10 +854,8 @@ __device__ __forceinline__ void long_row_block(const KParams& P, const int4 d, d
     double pl[PE > 0 ? PE : 1];
     pl[0] = 0.0;
     if constexpr (PE > 0) {
-      if (pd > 0) {
 #pragma unroll
-        for (int k = 0; k < PE; ++k) pl[k] = P.p[(long long)ep + k];
-      }
+      for (int k = 0; k < PE; ++k) pl[k] = k < pd ? P.p[(long long)ep + k] : 0.0;
     }
     double val[ED];
     entry_value<VD, ED>(kind, coupling, side, self, xn, pl, P.t, val);
@@ -875,20 +881,24 @@ __device__ __forceinline__ void long_row_block(const KParams& P, const int4 d, d
   }
 }
 
-template <int VD, int ED, int EK, int PE, int BLOCK, int U, int WPS>
+template <int VD, int ED, int EK, int PE, int BLOCK, int U, int WPS, bool HALO>
 __global__ void __launch_bounds__(BLOCK, (WPS * 32) / BLOCK) rhs_jag_kernel(const __grid_constant__ KParams P) {
   __shared__ double s_val[BLOCK * ED];   // long rows only
-  if ((int)blockIdx.x < P.n_pub) { publish_block(P.H, blockIdx.x, P.n_pub); return; }   // multi-GPU only
-  const int bid = (int)blockIdx.x - P.n_pub + P.blk_off;
+  if constexpr (HALO) {
+    if ((int)blockIdx.x < P.n_pub) { publish_block(P.H, blockIdx.x, P.n_pub); return; }
+  }
+  const int bid = (int)blockIdx.x - (HALO ? P.n_pub : 0) + P.blk_off;
   if (bid >= P.n_jag_blocks) {
-    halo_wait(P);   // multi-GPU only
-    long_row_block<VD, ED, EK, PE, BLOCK>(P, __ldg(&P.jlong[bid - P.n_jag_blocks]), s_val);
+    if constexpr (HALO) halo_wait(P);
+    long_row_block<VD, ED, EK, PE, BLOCK, HALO>(P, __ldg(&P.jlong[bid - P.n_jag_blocks]), s_val);
     return;
   }
   const int lane = threadIdx.x & 31;
   const int sl = bid * (BLOCK / 32) + (threadIdx.x >> 5);
   if (sl >= P.nslices) return;           // warp-uniform
-  if (sl >= P.wait_from) halo_wait_warp(P);   // multi-GPU only: this slice reads the halo
+  if constexpr (HALO) {
+    if (sl >= P.wait_from) halo_wait_warp(P);   // this slice reads the halo
+  }
   const int4 S = __ldg(&P.jslices[sl]);
   const unsigned desc = __ldg(&P.jlanes[(long long)sl * 32 + lane]);
   const int len = desc & 63;
@@ -945,7 +955,7 @@ __global__ void __launch_bounds__(BLOCK, (WPS * 32) / BLOCK) rhs_jag_kernel(cons
       pl[q][0] = 0.0;
       kind[q] = EK; coupling[q] = coupling0;
       if (act[q]) {
-        const double* gp = gather_ptr(P, off);
+        const double* gp = gather_ptr<HALO>(P, off);
         if constexpr (VD == 2) {
           const double2 t2 = *reinterpret_cast<const double2*>(gp);
           xn[q][0] = t2.x; xn[q][1] = t2.y;
@@ -958,10 +968,8 @@ __global__ void __launch_bounds__(BLOCK, (WPS * 32) / BLOCK) rhs_jag_kernel(cons
           kind[q] = E.kind; coupling[q] = E.coupling; pd = E.pdim;
         }
         if constexpr (PE > 0) {
-          if (pd > 0) {
 #pragma unroll
-            for (int k = 0; k < PE; ++k) pl[q][k] = P.p[(long long)ep[q] + k];
-          }
+          for (int k = 0; k < PE; ++k) pl[q][k] = k < pd ? P.p[(long long)ep[q] + k] : 0.0;
         }
       }
     }

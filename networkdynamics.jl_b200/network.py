@@ -202,8 +202,20 @@ class B200Aggregator:
         L = _cabi.lib()
         vb = (_cabi.VBatch * len(vertexbatches))()
         keep = []
+        customs = {}     # custom_spec -> kind id: user-supplied CUDA component functions (compiled by the engine, NVRTC)
+
+        def custom_kind(model):
+            spec = model.custom_spec()
+            if spec is None:
+                return None
+            if spec not in customs:
+                customs[spec] = _cabi.CUSTOM_KIND_BASE + len(customs)
+            return customs[spec]
+
         for k, b in enumerate(vertexbatches):
             kind = b.model.kernel_kind()
+            if kind is None:
+                kind = custom_kind(b.model)
             if kind is None:
                 raise ArgumentError(f"vertex model {b.model.name!r} has no kernel in the B200 registry "
                                     "(unsupported components raise instead of falling back to the CPU)")
@@ -214,6 +226,8 @@ class B200Aggregator:
         eb = (_cabi.EBatch * max(1, len(edgebatches)))()
         for k, b in enumerate(edgebatches):
             kind = b.model.kernel_kind()
+            if kind is None:
+                kind = custom_kind(b.model)
             if kind is None:
                 raise ArgumentError(f"edge model {b.model.name!r} has no kernel in the B200 registry "
                                     "(unsupported components raise instead of falling back to the CPU)")
@@ -235,6 +249,16 @@ class B200Aggregator:
                           (0 if self._opts["keep_tables"] else _cabi.FLAG_NO_EXPORT)
                           | (_cabi.FLAG_HOST_ONLY if self._opts["host_only"] else 0),
                           None, 0)
+        if customs:
+            ck = (_cabi.CustomKind * len(customs))()
+            for i, (spec, kid) in enumerate(customs.items()):
+                role, dim, pdim, outdim, two_sided, f_body, g_body = spec
+                fb, gb = f_body.encode(), (g_body.encode() if g_body is not None else None)
+                keep += [fb, gb]
+                ck[i] = _cabi.CustomKind(kid, role, dim, pdim, outdim, two_sided, fb, gb)
+            keep.append(ck)
+            desc.n_custom = len(customs)
+            desc.custom = ck
         if self._opts["gather_offset"] is not None:
             go = np.ascontiguousarray(self._opts["gather_offset"], dtype=np.int64)
             if go.size != im.nv:
@@ -443,6 +467,11 @@ class Network:
         if sz[0] >= 0:
             return "rhs_jag_kernel"
         return "edge_pass_kernel+row_pass_kernel" if os.environ.get("ND_B200_KERNEL") == "split" else "rhs_fused_kernel"
+
+    def custom_source(self) -> Optional[str]:
+        """the CUDA source the engine generated for user-supplied component kinds (None for registry-only networks)"""
+        src = self._L.nd_b200_custom_source(self.handle)
+        return src.decode() if src else None
 
     def export_jag(self):
         """the jagged device layout of the default kernel (host_only engines): slices[n,4], lanes[n,32], longs[m,4],

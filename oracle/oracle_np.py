@@ -104,13 +104,26 @@ class IndexManager:
         return int(nz[0]) + 1, m[nz[0]:nz[-1] + 1]
 
 
-def _vertex_g(kind, u, p):
+class PyKind:
+    """A component kind given as host callables (tests of user-supplied CUDA kinds): for vertices f(v, esum, p, t) -> dv
+    and optionally g(v, p, t) -> out (None = StateMask(1:outdim)); for edges g(v_src, v_dst, p, t) -> e_dst, or with the
+    Fiducial wrapper -> (e_src, e_dst) (src/component_functions.jl:189-203)."""
+
+    def __init__(self, f=None, g=None):
+        self.f, self.g = f, g
+
+
+def _vertex_g(kind, u, p, t=0.0):
+    if isinstance(kind, PyKind):
+        return None if kind.g is None else [float(x) for x in kind.g(u, p, t)]
     if kind == O.V_SWING_DQ:
         return [p[3] * math.cos(u[0]), p[3] * math.sin(u[0])]
     return None  # StateMask handled by caller
 
 
-def _edge_g(kind, vs, vd, p):
+def _edge_g(kind, vs, vd, p, t=0.0):
+    if isinstance(kind, PyKind):
+        return kind.g(vs, vd, p, t)
     if kind == O.E_DIFFUSION:
         return [p[0] * (vs[0] - vd[0])]
     if kind == O.E_DIFFUSION_NOP:
@@ -125,7 +138,9 @@ def _edge_g(kind, vs, vd, p):
     raise ValueError(kind)
 
 
-def _vertex_f(kind, v, acc, p):
+def _vertex_f(kind, v, acc, p, t=0.0):
+    if isinstance(kind, PyKind):
+        return [float(x) for x in kind.f(v, acc, p, t)]
     if kind == O.V_DIFFUSION:
         return [acc[0]]
     if kind == O.V_KURAMOTO_FIRST:
@@ -156,7 +171,7 @@ def rhs(im: IndexManager, u, p, t=0.0):
     for spec, idxs in im.vbatches:  # PASS 1
         s = im.vspecs[spec]
         for i in idxs:
-            out = _vertex_g(s.kind, sl(u, im.v_data[i]), sl(p, im.v_para[i]))
+            out = _vertex_g(s.kind, sl(u, im.v_data[i]), sl(p, im.v_para[i]), t)
             if out is None:
                 out = sl(u, im.v_data[i])[:s.outdim]
             o[im.v_out[i].first - 1:im.v_out[i].last] = out
@@ -166,7 +181,11 @@ def rhs(im: IndexManager, u, p, t=0.0):
         s = im.especs[spec]
         for i in idxs:
             vs, vd = sl(gbuf, im.e_gbufr[i][0]), sl(gbuf, im.e_gbufr[i][1])
-            odst = _edge_g(s.kind, vs, vd, sl(p, im.e_para[i]))
+            odst = _edge_g(s.kind, vs, vd, sl(p, im.e_para[i]), t)
+            if s.coupling == O.FIDUCIAL:                       # two-sided g writes both outputs itself
+                osrc, odst = odst
+                o[im.e_out[i][0].first - 1:im.e_out[i][0].last] = [float(x) for x in osrc]
+            odst = [float(x) for x in odst]
             o[im.e_out[i][1].first - 1:im.e_out[i][1].last] = odst
             if s.coupling == O.ANTISYMMETRIC:
                 o[im.e_out[i][0].first - 1:im.e_out[i][0].last] = [-x for x in odst]
@@ -179,6 +198,6 @@ def rhs(im: IndexManager, u, p, t=0.0):
     for spec, idxs in im.vbatches:  # PASS 6
         s = im.vspecs[spec]
         for i in idxs:
-            dv = _vertex_f(s.kind, sl(u, im.v_data[i]), sl(aggbuf, im.v_aggr[i]), sl(p, im.v_para[i]))
+            dv = _vertex_f(s.kind, sl(u, im.v_data[i]), sl(aggbuf, im.v_aggr[i]), sl(p, im.v_para[i]), t)
             du[im.v_data[i].first - 1:im.v_data[i].last] = dv
     return np.array(du), np.array(o), np.array(aggbuf)
