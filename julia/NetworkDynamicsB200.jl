@@ -18,7 +18,7 @@ using CUDA: CuArray, CuPtr, stream
 import NetworkDynamics: aggregate!, get_aggr_constructor, iscudacompatible, aggfun
 
 const libnd_b200 = get(ENV, "ND_B200_LIB", "libnd_b200.so")
-const ABI_VERSION = Cint(1)
+const ABI_VERSION = Cint(3)
 
 # ---- tags ---------------------------------------------------------------------------------------------------------
 "`ExecutionStyle` tag (field-less: only its type is stored in `Network{EX,...}`, src/network_structure.jl:83,116)."
@@ -39,7 +39,23 @@ const E_DIFFUSION, E_DIFFUSION_NOP, E_KURAMOTO, E_LINE_DQ = Cint.(0:3)
 coupling_of(::AntiSymmetric) = Cint(0)
 coupling_of(::Symmetric) = Cint(1)
 coupling_of(::Directed) = Cint(2)
+coupling_of(::Fiducial) = Cint(3)          # user-supplied two-sided kinds only (see cuda_source)
 coupling_of(x) = throw(ArgumentError("B200 engine: edge output wrapper $(typeof(x)) is not supported (no CPU fallback)"))
+
+# ---- user-supplied kinds (run-time compiled by the engine, NVRTC; include/nd_b200.h: nd_b200_custom_kind) -----------
+# A component function that has no hand-written kernel can still run on the engine if it can be stated as the BODY of a
+# CUDA C++ device function with the reference's own argument list (dv, v, esum, p, t / out, v, p, t /
+# e_dst, v_src, v_dst, p, t / e_src, e_dst, v_src, v_dst, p, t), e.g.
+#   NetworkDynamicsB200.cuda_source(::typeof(myedge!)) = "e_dst[0] = p[0] * sin(v_src[0] - v_dst[0]);"
+# For ModelingToolkit components the body is what Symbolics prints for the generated function:
+#   cuda_source(f::RuntimeGeneratedFunction) = Symbolics.build_function(rhs_exprs, args...; target = Symbolics.CTarget())
+# (ext/NetworkDynamicsMTKExt.jl:497-518 builds the same expressions into a RuntimeGeneratedFunction).
+cuda_source(f) = nothing
+const CUSTOM_KIND_BASE = Cint(1000)
+struct CCustomKind
+    kind::Cint; role::Cint; dim::Cint; pdim::Cint; outdim::Cint; two_sided::Cint
+    f_body::Cstring; g_body::Cstring
+end
 
 # ---- C structs (mirror include/nd_b200.h) ---------------------------------------------------------------------------
 struct CVBatch
@@ -61,6 +77,8 @@ struct CDesc
     lastidx_dynamic::Int64; lastidx_p::Int64; lastidx_out::Int64; lastidx_aggr::Int64
     row_begin::Int64; row_end::Int64
     long_row_threshold::Cint; flags::Cint
+    gather_offset::Ptr{Int64}; gather_len::Int64        # multi-GPU packed halo (C_NULL, 0: single GPU)
+    n_custom::Cint; reserved::Cint; custom::Ptr{CCustomKind}
 end
 
 # ---- the aggregator owns the engine ---------------------------------------------------------------------------------
@@ -88,10 +106,21 @@ function B200Aggregator(im::IndexManager, edgebatches, f)
     # populated when the aggregator closure runs (src/construction.jl:198)
     vidxs = _find_identical_components(im.vertexm)
     keep = Any[]
+    customs = CCustomKind[]                  # user-supplied kinds referenced by the batches
+    function custom_kind!(role, d, pd, od, two_sided, fsrc, gsrc)
+        fb = Base.unsafe_convert(Cstring, Base.cconvert(Cstring, fsrc)); push!(keep, fsrc)
+        gb = isnothing(gsrc) ? Cstring(C_NULL) : (push!(keep, gsrc); Base.unsafe_convert(Cstring, Base.cconvert(Cstring, gsrc)))
+        push!(customs, CCustomKind(CUSTOM_KIND_BASE + length(customs), role, d, pd, od, two_sided, fb, gb))
+        customs[end].kind
+    end
     vb = map(vidxs) do idxs
         m = im.vertexm[first(idxs)]
         kind = vertex_kernel(compf(m), compg(m))
-        isnothing(kind) && throw(ArgumentError("vertex model $(m.name) has no kernel in the B200 registry (no CPU fallback)"))
+        if isnothing(kind) && !isnothing(cuda_source(compf(m)))      # user-supplied kind
+            gs = compg(m) isa StateMask ? nothing : cuda_source(compg(m))
+            kind = custom_kind!(0, dim(m), pdim(m), outdim(m), 0, cuda_source(compf(m)), gs)
+        end
+        isnothing(kind) && throw(ArgumentError("vertex model $(m.name) has neither a registry kernel nor a cuda_source (no CPU fallback)"))
         ix = Vector{Int64}(idxs); push!(keep, ix)
         i1 = first(idxs)
         CVBatch(kind, dim(m), pdim(m), outdim(m), length(ix), pointer(ix),
@@ -99,9 +128,14 @@ function B200Aggregator(im::IndexManager, edgebatches, f)
     end
     eb = map(collect(edgebatches)) do b
         g = compg(b)
-        kind = edge_kernel(g.g)
+        inner = g isa NetworkDynamics.SingleSidedOutputWrapper && !(g isa Fiducial) ? g.g : g
+        kind = edge_kernel(inner)
+        if isnothing(kind) && !isnothing(cuda_source(inner))         # user-supplied kind (two-sided body: Fiducial / unwrapped)
+            two = (g isa Fiducial || !(g isa NetworkDynamics.SingleSidedOutputWrapper)) ? 1 : 0
+            kind = custom_kind!(1, 0, pdim(b), outdim(b).dst, two, cuda_source(inner), nothing)
+        end
         (isnothing(kind) || !isnothing(compf(b))) &&
-            throw(ArgumentError("edge batch $(typeof(g)) has no kernel in the B200 registry (no CPU fallback)"))
+            throw(ArgumentError("edge batch $(typeof(g)) has neither a registry kernel nor a cuda_source, or is an ODE edge (no CPU fallback)"))
         ix = Vector{Int64}(b.indices); push!(keep, ix)
         od = outdim(b)
         CEBatch(kind, coupling_of(g), dim(b), pdim(b), od.src, od.dst, length(ix), pointer(ix),
@@ -109,11 +143,12 @@ function B200Aggregator(im::IndexManager, edgebatches, f)
     end
     esrc = Int64[e.src for e in im.edgevec]; edst = Int64[e.dst for e in im.edgevec]
     handle = Ref{Ptr{Cvoid}}(C_NULL)
-    GC.@preserve keep vb eb esrc edst begin
+    GC.@preserve keep vb eb esrc edst customs begin
         desc = CDesc(ABI_VERSION, Cint(CUDA.deviceid()), length(im.vertexm), length(im.edgevec),
                      pointer(esrc), pointer(edst), im.vdepth, im.edepth, length(vb), length(eb),
                      pointer(vb), pointer(eb), im.lastidx_dynamic, im.lastidx_p, im.lastidx_out, im.lastidx_aggr,
-                     0, 0, Cint(0), Cint(0))
+                     0, 0, Cint(0), Cint(0), Ptr{Int64}(C_NULL), 0,
+                     Cint(length(customs)), Cint(0), isempty(customs) ? Ptr{CCustomKind}(C_NULL) : pointer(customs))
         rc = ccall((:nd_b200_create, libnd_b200), Cint, (Ref{CDesc}, Ref{Ptr{Cvoid}}), desc, handle)
         _check(rc, C_NULL)
     end
