@@ -253,10 +253,17 @@ def main():
         flush.zero_()
         step()
     sync_all()
-    # keep the device busy ~0.3 s more so SM clocks have ramped from idle before the timed region
-    t_pre = time.perf_counter()
-    while time.perf_counter() - t_pre < 0.3:
-        for _ in range(20):
+    # keep the device busy ~0.3 s more so SM clocks have ramped from idle before the timed region.  Multi-rank: the
+    # exchange is collective, so every rank must make the SAME number of calls -- a wall-clock loop would let ranks
+    # disagree by one batch and leave the others spinning on flags that never come.
+    if world == 1:
+        t_pre = time.perf_counter()
+        while time.perf_counter() - t_pre < 0.3:
+            for _ in range(20):
+                step()
+            torch.cuda.synchronize()
+    else:
+        for _ in range(400):
             step()
         torch.cuda.synchronize()
     sync_all()

@@ -382,7 +382,9 @@ __device__ __forceinline__ void halo_wait(const KParams& P) {
   if (threadIdx.x < P.wait_world) {
     const long long t0 = clock64();
     while (ld_acquire_sys(P.wait_flags + threadIdx.x) < P.wait_seq) {
-      if (clock64() - t0 > 4000000000LL) {   // ~2 s: a peer died; do not hang the GPU
+      // ~2 s: a peer died or the ranks' call sequences diverged; do not hang the GPU.  The mark is sticky: once set,
+      // later tiles and calls give up at once (results are invalid anyway, nd_b200_comm_status reports it).
+      if (*(volatile int*)P.wait_timeout || clock64() - t0 > 4000000000LL) {
         *P.wait_timeout = 1;
         break;
       }
@@ -399,7 +401,7 @@ __device__ __forceinline__ void halo_wait_warp(const KParams& P) {
   if (lane < P.wait_world) {
     const long long t0 = clock64();
     while (ld_acquire_sys(P.wait_flags + lane) < P.wait_seq) {
-      if (clock64() - t0 > 4000000000LL) {
+      if (*(volatile int*)P.wait_timeout || clock64() - t0 > 4000000000LL) {
         *P.wait_timeout = 1;
         break;
       }
