@@ -494,14 +494,14 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
     std::string why;
     if (!vertex_kind_ok(e, vb, why)) return fail(e, ND_B200_EUNSUPPORTED, "%s (no CPU fallback)", why.c_str());
     if (vb.outdim != d->vdepth) return fail(e, ND_B200_EINVAL, "vertex batch %d outdim %d != vdepth %d", b + 1, vb.outdim, d->vdepth);
-    if (vb.count <= 0 || !vb.indices) return fail(e, ND_B200_EINVAL, "vertex batch %d is empty", b + 1);
+    if (vb.count <= 0 || (!vb.indices && d->n_vbatches != 1)) return fail(e, ND_B200_EINVAL, "vertex batch %d is empty", b + 1);
     if (vb.state_first != state_expect) return fail(e, ND_B200_EINVAL, "vertex batch %d: statestride.first %lld, expected %lld", b + 1, (long long)vb.state_first, state_expect);
     if (vb.out_first != out_expect) return fail(e, ND_B200_EINVAL, "vertex batch %d: outbufstride.first %lld, expected %lld", b + 1, (long long)vb.out_first, out_expect);
     if (ed > 0 && vb.aggr_first != row * ed + 1) return fail(e, ND_B200_EINVAL, "vertex batch %d: inbufstride.first %lld, expected %lld", b + 1, (long long)vb.aggr_first, row * ed + 1);
     HostVB h{vb.kind, vb.dim, vb.pdim, vb.outdim, vb.count, vb.state_first - 1, vb.p_first - 1, vb.out_first - 1, row};
     e->hvb.push_back(h);
     for (long long i = 0; i < vb.count; ++i) {
-      long long vid = vb.indices[i];
+      long long vid = vb.indices ? vb.indices[i] : i + 1;
       if (vid < 1 || vid > d->nv || row_of_vertex[(size_t)vid - 1] >= 0) return fail(e, ND_B200_EINVAL, "vertex batch %d: bad or duplicate vertex id %lld", b + 1, vid);
       row_of_vertex[(size_t)vid - 1] = (int)(row + i);
     }
@@ -527,7 +527,7 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
   for (int b = 0; b < d->n_vbatches; ++b) {
     const HostVB& h = e->hvb[b];
     for (long long i = 0; i < h.count; ++i) {
-      long long vid = d->vbatches[b].indices[i];
+      long long vid = d->vbatches[b].indices ? d->vbatches[b].indices[i] : i + 1;
       goff[(size_t)vid - 1] = e->gather_from_u ? (int)(h.state0 + i * h.dim) : (int)((h.row0 + i) * d->vdepth);
     }
   }
@@ -562,13 +562,13 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
     const int osrc_expect = eb.coupling == ND_B200_DIRECTED ? 0 : eb.outdim_dst;
     if (eb.outdim_src != osrc_expect) return fail(e, ND_B200_EINVAL, "edge batch %d: outdim.src %d inconsistent with wrapper", b + 1, eb.outdim_src);
     if (eb.out_first != eout_expect) return fail(e, ND_B200_EINVAL, "edge batch %d: outbufstride.first %lld, expected %lld", b + 1, (long long)eb.out_first, eout_expect);
-    if (eb.count <= 0 || !eb.indices) return fail(e, ND_B200_EINVAL, "edge batch %d is empty", b + 1);
+    if (eb.count <= 0 || (!eb.indices && d->n_ebatches != 1)) return fail(e, ND_B200_EINVAL, "edge batch %d is empty", b + 1);
     HostEB h{eb.kind, eb.coupling, eb.dim, eb.pdim, eb.outdim_src, eb.outdim_dst, eb.count, eb.p_first - 1, eb.out_first - 1};
     e->heb.push_back(h);
     eout_expect += eb.count * (eb.outdim_src + eb.outdim_dst);
     if (eb.pdim > 0) any_epar = true;
     for (long long i = 0; i < eb.count; ++i) {
-      long long eid = eb.indices[i];
+      long long eid = eb.indices ? eb.indices[i] : i + 1;
       if (eid < 1 || eid > d->ne || edge_seen[(size_t)eid - 1]) return fail(e, ND_B200_EINVAL, "edge batch %d: bad or duplicate edge id %lld", b + 1, eid);
       edge_seen[(size_t)eid - 1] = 1;
     }
@@ -588,7 +588,7 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
   for (int b = 0; b < d->n_ebatches; ++b) {
     const nd_b200_ebatch& eb = d->ebatches[b];
     for (long long i = 0; i < eb.count; ++i) {
-      const long long eid = eb.indices[i] - 1;
+      const long long eid = eb.indices ? eb.indices[i] - 1 : i;
       const long long s = d->edge_src[eid], t = d->edge_dst[eid];
       if (s < 1 || s > d->nv || t < 1 || t > d->nv) return fail(e, ND_B200_EINVAL, "edge %lld endpoint out of range", eid + 1);
       const int rs = row_of_vertex[(size_t)s - 1], rt = row_of_vertex[(size_t)t - 1];
@@ -625,7 +625,7 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
     for (int b = 0; b < d->n_ebatches; ++b) {
       const nd_b200_ebatch& eb = d->ebatches[b];
       for (long long i = 0; i < eb.count; ++i) {
-        const long long eid = eb.indices[i] - 1;
+        const long long eid = eb.indices ? eb.indices[i] - 1 : i;
         const long long s = d->edge_src[eid], t = d->edge_dst[eid];
         const int rs = row_of_vertex[(size_t)s - 1], rt = row_of_vertex[(size_t)t - 1];
         const int ep = eb.pdim > 0 ? (int)(eb.p_first - 1 + i * eb.pdim) : 0;
@@ -681,7 +681,7 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
       const nd_b200_ebatch& eb = d->ebatches[b];
       e->h_esrc_off[(size_t)b].resize((size_t)eb.count); e->h_edst_off[(size_t)b].resize((size_t)eb.count);
       for (long long i = 0; i < eb.count; ++i) {
-        const long long eid = eb.indices[i] - 1;
+        const long long eid = eb.indices ? eb.indices[i] - 1 : i;
         e->h_esrc_off[(size_t)b][(size_t)i] = goff[(size_t)d->edge_src[eid] - 1];
         e->h_edst_off[(size_t)b][(size_t)i] = goff[(size_t)d->edge_dst[eid] - 1];
       }
@@ -1039,6 +1039,48 @@ int nd_b200_create(const nd_b200_desc* desc, nd_b200_engine** out) {
   }
   *out = e;
   return ND_B200_OK;
+}
+
+/* Homogeneous network straight from an edge list (the config-5 path): one vertex kind, one edge kind, the
+ * flat layout the reference's constructor would produce for it (register_vertices!/register_edges!,
+ * src/network_structure.jl:224-258) -- without the caller materialising per-component tables. */
+int nd_b200_create_from_edgelist(int32_t device, int64_t nv, int64_t ne, const int64_t* edge_src, const int64_t* edge_dst,
+                                 int32_t vertex_kind, int32_t edge_kind, int32_t coupling, int64_t row_begin,
+                                 int64_t row_end, int32_t flags, nd_b200_engine** out) {
+  struct VR { int kind, dim, pdim, outdim; };
+  static const VR vreg[] = {{ND_B200_V_DIFFUSION, 1, 0, 1}, {ND_B200_V_KURAMOTO_FIRST, 1, 1, 1}, {ND_B200_V_KURAMOTO_SECOND, 2, 3, 1},
+                            {ND_B200_V_KURAMOTO_SECOND_BENCH, 2, 1, 1}, {ND_B200_V_SWING_DQ, 2, 4, 2}};
+  struct ER { int kind, pdim, odst; };
+  static const ER ereg[] = {{ND_B200_E_DIFFUSION, 1, 1}, {ND_B200_E_DIFFUSION_NOP, 0, 1}, {ND_B200_E_KURAMOTO, 1, 1}, {ND_B200_E_LINE_DQ, 3, 2}};
+  const VR* v = nullptr;
+  const ER* g = nullptr;
+  for (const VR& r : vreg) if (r.kind == vertex_kind) v = &r;
+  for (const ER& r : ereg) if (r.kind == edge_kind) g = &r;
+  if (!out || !v || (ne > 0 && !g) || nv <= 0 || ne < 0 || (ne > 0 && (!edge_src || !edge_dst)))
+    return fail(nullptr, ND_B200_EINVAL, "nd_b200_create_from_edgelist: bad arguments or kinds outside the registry");
+  if (coupling != ND_B200_ANTISYMMETRIC && coupling != ND_B200_SYMMETRIC && coupling != ND_B200_DIRECTED)
+    return fail(nullptr, ND_B200_EINVAL, "nd_b200_create_from_edgelist: unsupported wrapper %d", coupling);
+  nd_b200_vbatch vb;
+  memset(&vb, 0, sizeof vb);
+  vb.kind = v->kind; vb.dim = v->dim; vb.pdim = v->pdim; vb.outdim = v->outdim; vb.count = nv; vb.indices = nullptr;
+  vb.state_first = 1; vb.p_first = 1; vb.out_first = 1; vb.aggr_first = 1;
+  nd_b200_ebatch eb;
+  memset(&eb, 0, sizeof eb);
+  const int osrc = (ne > 0 && coupling != ND_B200_DIRECTED) ? g->odst : 0;
+  if (ne > 0) {
+    eb.kind = g->kind; eb.coupling = coupling; eb.dim = 0; eb.pdim = g->pdim; eb.outdim_src = osrc; eb.outdim_dst = g->odst;
+    eb.count = ne; eb.indices = nullptr;
+    eb.state_first = nv * v->dim + 1; eb.p_first = nv * v->pdim + 1; eb.out_first = nv * v->outdim + 1; eb.gbuf_first = 1;
+  }
+  nd_b200_desc d;
+  memset(&d, 0, sizeof d);
+  d.abi_version = ND_B200_ABI_VERSION; d.device = device; d.nv = nv; d.ne = ne; d.edge_src = edge_src; d.edge_dst = edge_dst;
+  d.vdepth = v->outdim; d.edepth = ne > 0 ? g->odst : v->outdim;
+  d.n_vbatches = 1; d.n_ebatches = ne > 0 ? 1 : 0; d.vbatches = &vb; d.ebatches = &eb;
+  d.lastidx_dynamic = nv * v->dim; d.lastidx_p = nv * v->pdim + (ne > 0 ? ne * g->pdim : 0);
+  d.lastidx_out = nv * v->outdim + (ne > 0 ? ne * (osrc + g->odst) : 0); d.lastidx_aggr = nv * d.edepth;
+  d.row_begin = row_begin; d.row_end = row_end; d.flags = flags;
+  return nd_b200_create(&d, out);
 }
 
 void nd_b200_destroy(nd_b200_engine* e) {

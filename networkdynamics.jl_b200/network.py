@@ -370,6 +370,42 @@ class Network:
         self.execution = execution
         self._L = _cabi.lib()
 
+    @classmethod
+    def from_edgelist(cls, g, vertexm: VertexModel, edgem: EdgeModel, *, device: Optional[int] = None, row_range=None,
+                      keep_tables: bool = False, host_only: bool = False):
+        """Homogeneous network straight from the edge list (`nd_b200_create_from_edgelist`): one registry
+        vertex model, one registry edge model.  Same flat `u` / `p` layout and same engine as `Network(g, vertexm, edgem)`,
+        without the per-component host tables (BASELINE config 5 has 4e8 edges: six Int64 tables would be 19 GB)."""
+        from types import SimpleNamespace
+        vk, ek = vertexm.kernel_kind(), edgem.kernel_kind()
+        if vk is None or ek is None:
+            raise ArgumentError("from_edgelist needs registry models (no CPU fallback)")
+        self = cls.__new__(cls)
+        self._L = L = _cabi.lib()
+        nv, ne = g.nv, g.ne
+        src = np.ascontiguousarray(g.src, dtype=np.int64)
+        dst = np.ascontiguousarray(g.dst, dtype=np.int64)
+        osrc = edgem.outdim_src if ne else 0
+        edepth = edgem.outdim_dst if ne else vertexm.outdim
+        self.im = SimpleNamespace(nv=nv, ne=ne, vdepth=vertexm.outdim, edepth=edepth,
+                                  lastidx_dynamic=nv * vertexm.dim, lastidx_p=nv * vertexm.pdim + ne * edgem.pdim,
+                                  lastidx_out=nv * vertexm.outdim + ne * (osrc + edgem.outdim_dst), lastidx_aggr=nv * edepth)
+        dev = _current_device() if device is None else device
+        rr = row_range or (0, 0)
+        flags = (0 if keep_tables else _cabi.FLAG_NO_EXPORT) | (_cabi.FLAG_HOST_ONLY if host_only else 0)
+        h = C.c_void_p()
+        rc = L.nd_b200_create_from_edgelist(int(dev), nv, ne, src.ctypes.data_as(_cabi.i64p), dst.ctypes.data_as(_cabi.i64p),
+                                            vk, ek, edgem.coupling, int(rr[0]), int(rr[1]), flags, C.byref(h))
+        if rc != _cabi.OK:
+            msg = L.nd_b200_last_error(None).decode()
+            raise (ArgumentError if rc in (_cabi.EINVAL, _cabi.EUNSUPPORTED) else RuntimeError)(msg)
+        agg = B200Aggregator("+", device=dev, row_range=row_range, keep_tables=keep_tables, host_only=host_only)
+        agg.handle, agg.device = h, int(dev)
+        self.vertexbatches = []
+        self.layer = NetworkLayer(g, [], agg, edepth, vertexm.outdim)
+        self.execution = B200Execution()
+        return self
+
     # -- sizes (src/network_structure.jl:118-131) ---------------------------------------------------
     def dim(self):
         return self.im.lastidx_dynamic

@@ -77,3 +77,32 @@ def test_unregistered_component_is_rejected_before_any_device_work(nd):
     masked = nd.VertexModel(f=L.kuramoto_inertia, g=nd.StateMask(2), dim=2, pdim=3, name="mask2")
     with pytest.raises(nd.ArgumentError):
         nd.Network(g, masked, L.kuramoto_edge())
+
+
+def test_create_from_edgelist_builds_the_same_engine(nd, monkeypatch):
+    """nd_b200_create_from_edgelist (homogeneous network from a bare edge list) against the table-driven
+    constructor: same sizes, same CSR (rowptr, neighbour, edge id, side), same jagged layout -- on host-only engines."""
+    L = nd.Lib
+    cases = [(nd.erdos_renyi(3000, 12000, seed=2), L.kuramoto_first(), L.kuramoto_edge()),
+             (nd.barabasi_albert(2000, 4, seed=2), L.kuramoto_second(), L.kuramoto_edge()),
+             (nd.grid_graph(31, 17), L.swing_dq(), L.line_dq()),
+             (nd.watts_strogatz(1500, 6, 0.2, seed=1, directed=True), L.diffusion_vertex(),
+              nd.EdgeModel(g=nd.Directed(L.diffusionedge_nop), outdim=1, pdim=0, name="dir_diff")),
+             (nd.SimpleGraph(7, [], []), L.kuramoto_first(), L.kuramoto_edge())]
+    for mode in ("fused", "jag"):
+        monkeypatch.setenv("ND_B200_KERNEL", mode)
+        for g, vm, em in cases:
+            for rr in (None, (g.nv // 3, g.nv - 2)):
+                a = nd.Network(g, vm, em, aggregator=nd.B200Aggregator("+", host_only=True, row_range=rr))
+                b = nd.Network.from_edgelist(g, vm, em, host_only=True, keep_tables=True, row_range=rr)
+                assert (a.dim(), a.pdim(), a.im.lastidx_out, a.im.lastidx_aggr) == (b.dim(), b.pdim(), b.im.lastidx_out, b.im.lastidx_aggr)
+                assert a.engine_sizes() == b.engine_sizes()
+                for x, y in zip(a.export_tables(), b.export_tables()):
+                    assert np.array_equal(x, y)
+                if mode == "jag":
+                    ja, jb = a.export_jag(), b.export_jag()
+                    for k in ("slices", "lanes", "longs", "order"):
+                        assert np.array_equal(ja[k], jb[k]), k
+    with pytest.raises(nd.ArgumentError):      # user-supplied kinds go through the table-driven constructor
+        nd.Network.from_edgelist(cases[0][0], nd.VertexModel(f=nd.CudaFunction("f", "vertex_f", "dv[0]=0;"), g=nd.StateMask((1,)), dim=1),
+                                 L.kuramoto_edge(), host_only=True)
