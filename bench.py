@@ -332,7 +332,7 @@ def main():
         e2e_s = time.perf_counter() - te
         e2e = {"value": g.ne * args.steps / e2e_s, "unit": "edge-evals/s", "h2d_bytes_per_step": 8 * (nw.dim() + nw.pdim()),
                "d2h_bytes_per_step": 8 * nw.dim(), "ms_per_step": 1e3 * e2e_s / args.steps,
-               "how": "nw(du,u,p,t) with pinned host vectors -> nd_b200_rhs_host: H2D of u, H2D of p in 8 pieces, each row group's "
+               "how": "nw(du,u,p,t) with pinned host vectors -> nd_b200_rhs_host: H2D of u, H2D of p in 3 pieces (1/2, 1/4, 1/4), each row group's "
                       "kernel starts when the last parameter it reads has landed, D2H of finished du rows overlaps the rest; "
                       "stream sync before returning; wall clock around the calls"}
         assert np.array_equal(hdu, du.cpu().numpy()), "host-buffer path and device path disagree"

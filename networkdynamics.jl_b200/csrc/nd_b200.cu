@@ -1141,9 +1141,9 @@ int nd_b200_rhs_host(nd_b200_engine* e, double* du_host, const double* u_host, c
   // the D2H copy of a group's du rows overlaps the next group's kernel and the remaining H2D traffic.
   // piece k covers the fraction 1/2, 1/4, ... of p and of the thread blocks (the last two pieces are equal): what stays
   // exposed after the H2D stream is the LAST group's kernel + D2H, so late pieces are small while early ones keep the
-  // per-copy overhead low.  Measured on B200 (cfg2, 48 MB over PCIe per call): 0.96 ms unpipelined, 0.87 ms with 4..8
-  // equal pieces.
-  int K = 5;
+  // per-copy overhead low.  Measured on B200 (cfg2, 48 MB over PCIe per call, profiles/r01_tuning.md section 7): 0.96 ms
+  // unpipelined; 0.870 ms with K=3 (1/2, 1/4, 1/4), 0.896 with K=5; the H2D stream alone is ~0.76 ms.
+  int K = 3;
   if (const char* s = getenv("ND_B200_HOST_CHUNKS")) K = std::max(1, std::min(10, atoi(s)));
   std::vector<double> cum((size_t)K + 1, 0.0);
   for (int k = 0; k < K; ++k) cum[(size_t)k + 1] = (k == K - 1) ? 1.0 : 1.0 - std::ldexp(1.0, -(k + 1));
