@@ -21,6 +21,17 @@
 
 using namespace ndb;
 
+// Kernel launch.  The kernel name comes last so that template argument lists (they contain commas) survive the macro.
+// ND_CUSIM: tests/cusim/ compiles this very file with g++ against an emulation of the CUDA runtime that executes the kernel
+// sources thread by thread on the CPU (fibers, warp collectives, block barriers) so that the CPU test suite exercises the
+// real kernels and launch logic.  That build is a test double: it is never part of libnd_b200.so and the package never loads it.
+#ifdef ND_CUSIM
+#define ND_LAUNCH(grid, block, stream, args, ...) \
+  cusim::launch(dim3((unsigned)(grid)), dim3((unsigned)(block)), (stream), [=]() { __VA_ARGS__ args; })
+#else
+#define ND_LAUNCH(grid, block, stream, args, ...) __VA_ARGS__<<<(grid), (block), 0, (stream)>>> args
+#endif
+
 namespace {
 
 thread_local std::string g_create_error;
@@ -232,7 +243,7 @@ cudaError_t launch_edge_pass_t(const nd_b200_engine* e, const EParams& Q, cudaSt
   const long long per = BLOCK * EPT;
   const int grid = (int)((e->ne_all + per - 1) / per);
   if (grid == 0) return cudaSuccess;
-  edge_pass_kernel<VD, ED, EK, PE, BLOCK, EPT><<<grid, BLOCK, 0, st>>>(Q);
+  ND_LAUNCH(grid, BLOCK, st, (Q), edge_pass_kernel<VD, ED, EK, PE, BLOCK, EPT>);
   return cudaGetLastError();
 }
 cudaError_t launch_edge_pass(nd_b200_engine* e, const double* gsrc, const double* p, cudaStream_t st) {
@@ -252,10 +263,10 @@ cudaError_t launch_edge_pass(nd_b200_engine* e, const double* gsrc, const double
 }
 template <int VD, int ED>
 cudaError_t launch_row_pass_t(const nd_b200_engine* e, const KParams& P, cudaStream_t st) {
-  if (e->block == 256 && e->ept == 8) row_pass_kernel<VD, ED, 256, 8><<<e->nblocks, 256, 0, st>>>(P);
-  else if (e->block == 256 && e->ept == 4) row_pass_kernel<VD, ED, 256, 4><<<e->nblocks, 256, 0, st>>>(P);
-  else if (e->block == 128 && e->ept == 8) row_pass_kernel<VD, ED, 128, 8><<<e->nblocks, 128, 0, st>>>(P);
-  else if (e->block == 128 && e->ept == 4) row_pass_kernel<VD, ED, 128, 4><<<e->nblocks, 128, 0, st>>>(P);
+  if (e->block == 256 && e->ept == 8) ND_LAUNCH(e->nblocks, 256, st, (P), row_pass_kernel<VD, ED, 256, 8>);
+  else if (e->block == 256 && e->ept == 4) ND_LAUNCH(e->nblocks, 256, st, (P), row_pass_kernel<VD, ED, 256, 4>);
+  else if (e->block == 128 && e->ept == 8) ND_LAUNCH(e->nblocks, 128, st, (P), row_pass_kernel<VD, ED, 128, 8>);
+  else if (e->block == 128 && e->ept == 4) ND_LAUNCH(e->nblocks, 128, st, (P), row_pass_kernel<VD, ED, 128, 4>);
   else return cudaErrorInvalidConfiguration;
   return cudaGetLastError();
 }
@@ -266,12 +277,12 @@ cudaError_t launch_shape(const nd_b200_engine* e, const KParams& P, cudaStream_t
   if (grid == 0) return cudaSuccess;
   if (e->halo_base != INT_MAX) {   // multi-GPU variant, default launch shape only
     if (e->block != 128 || e->ept != 4) return cudaErrorInvalidConfiguration;
-    rhs_fused_kernel<VD, ED, EK, PE, 128, 4, true><<<grid, 128, 0, st>>>(P);
+    ND_LAUNCH(grid, 128, st, (P), rhs_fused_kernel<VD, ED, EK, PE, 128, 4, true>);
   }
-  else if (e->block == 256 && e->ept == 8) rhs_fused_kernel<VD, ED, EK, PE, 256, 8, false><<<grid, 256, 0, st>>>(P);
-  else if (e->block == 256 && e->ept == 4) rhs_fused_kernel<VD, ED, EK, PE, 256, 4, false><<<grid, 256, 0, st>>>(P);
-  else if (e->block == 128 && e->ept == 8) rhs_fused_kernel<VD, ED, EK, PE, 128, 8, false><<<grid, 128, 0, st>>>(P);
-  else if (e->block == 128 && e->ept == 4) rhs_fused_kernel<VD, ED, EK, PE, 128, 4, false><<<grid, 128, 0, st>>>(P);
+  else if (e->block == 256 && e->ept == 8) ND_LAUNCH(grid, 256, st, (P), rhs_fused_kernel<VD, ED, EK, PE, 256, 8, false>);
+  else if (e->block == 256 && e->ept == 4) ND_LAUNCH(grid, 256, st, (P), rhs_fused_kernel<VD, ED, EK, PE, 256, 4, false>);
+  else if (e->block == 128 && e->ept == 8) ND_LAUNCH(grid, 128, st, (P), rhs_fused_kernel<VD, ED, EK, PE, 128, 8, false>);
+  else if (e->block == 128 && e->ept == 4) ND_LAUNCH(grid, 128, st, (P), rhs_fused_kernel<VD, ED, EK, PE, 128, 4, false>);
   else return cudaErrorInvalidConfiguration;
   return cudaGetLastError();
 }
@@ -284,12 +295,12 @@ cudaError_t launch_jag_u(const nd_b200_engine* e, const KParams& P, cudaStream_t
   if (grid == 0) return cudaSuccess;
   const int wps = e->jag_wps > 0 ? e->jag_wps : jag_warps_per_sm_default(EK);
   if (e->halo_base != INT_MAX) {   // multi-GPU variant: one occupancy setting
-    if (wps >= 48) rhs_jag_kernel<VD, ED, EK, PE, BLOCK, U, 48, true><<<grid, BLOCK, 0, st>>>(P);
-    else rhs_jag_kernel<VD, ED, EK, PE, BLOCK, U, 32, true><<<grid, BLOCK, 0, st>>>(P);
+    if (wps >= 48) ND_LAUNCH(grid, BLOCK, st, (P), rhs_jag_kernel<VD, ED, EK, PE, BLOCK, U, 48, true>);
+    else ND_LAUNCH(grid, BLOCK, st, (P), rhs_jag_kernel<VD, ED, EK, PE, BLOCK, U, 32, true>);
   }
-  else if (wps >= 64) rhs_jag_kernel<VD, ED, EK, PE, BLOCK, U, 64, false><<<grid, BLOCK, 0, st>>>(P);
-  else if (wps >= 48) rhs_jag_kernel<VD, ED, EK, PE, BLOCK, U, 48, false><<<grid, BLOCK, 0, st>>>(P);
-  else rhs_jag_kernel<VD, ED, EK, PE, BLOCK, U, 32, false><<<grid, BLOCK, 0, st>>>(P);
+  else if (wps >= 64) ND_LAUNCH(grid, BLOCK, st, (P), rhs_jag_kernel<VD, ED, EK, PE, BLOCK, U, 64, false>);
+  else if (wps >= 48) ND_LAUNCH(grid, BLOCK, st, (P), rhs_jag_kernel<VD, ED, EK, PE, BLOCK, U, 48, false>);
+  else ND_LAUNCH(grid, BLOCK, st, (P), rhs_jag_kernel<VD, ED, EK, PE, BLOCK, U, 32, false>);
   return cudaGetLastError();
 }
 template <int VD, int ED, int EK, int PE>
@@ -346,7 +357,7 @@ cudaError_t launch_vout(nd_b200_engine* e, const double* u, const double* p, dou
     void* args[] = {&vb, &nvb, &vd, &u, &p, &vout, &nr, &t0};
     return cudaLaunchKernel((const void*)e->c_vout, dim3((unsigned)nb), dim3(T), args, 0, st);
   }
-  vertex_out_kernel<<<nb, T, 0, st>>>(e->d_vb, (int)e->hvb.size(), e->vdepth, u, p, vout, (int)e->nrows_total, 0.0);
+  ND_LAUNCH(nb, T, st, (e->d_vb, (int)e->hvb.size(), e->vdepth, u, p, vout, (int)e->nrows_total, 0.0), vertex_out_kernel);
   return cudaGetLastError();
 }
 
@@ -1247,9 +1258,9 @@ int nd_b200_get_buffers(nd_b200_engine* e, double* o, double* aggbuf, const doub
         void* args[] = {&kind, &coupling, &pdim, &osrc, &count, &es, &et, &p0, &out0, &gsrc, &p, &o, &t};
         CUDA_TRY(e, cudaLaunchKernel((const void*)e->c_eout, dim3((unsigned)nb), dim3(T), args, 0, st));
       } else if (e->vdepth == 2)
-        edge_out_kernel<2, 2><<<nb, T, 0, st>>>(h.kind, h.coupling, h.pdim, h.osrc, h.count, e->d_esrc_off[b], e->d_edst_off[b], h.p0, h.out0, gsrc, p, o, t);
+        ND_LAUNCH(nb, T, st, (h.kind, h.coupling, h.pdim, h.osrc, h.count, e->d_esrc_off[b], e->d_edst_off[b], h.p0, h.out0, gsrc, p, o, t), edge_out_kernel<2, 2>);
       else
-        edge_out_kernel<1, 1><<<nb, T, 0, st>>>(h.kind, h.coupling, h.pdim, h.osrc, h.count, e->d_esrc_off[b], e->d_edst_off[b], h.p0, h.out0, gsrc, p, o, t);
+        ND_LAUNCH(nb, T, st, (h.kind, h.coupling, h.pdim, h.osrc, h.count, e->d_esrc_off[b], e->d_edst_off[b], h.p0, h.out0, gsrc, p, o, t), edge_out_kernel<1, 1>);
       CUDA_TRY(e, cudaGetLastError());
     }
   }

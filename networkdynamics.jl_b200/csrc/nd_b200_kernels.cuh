@@ -333,6 +333,10 @@ __device__ __forceinline__ void load_vertex_state(const KParams& P, const VBDev&
 // by sequence parity, which is enough: a rank can only publish sequence s+2 after it has consumed every peer's s+1,
 // which those peers published after finishing their own reads of s.
 // ------------------------------------------------------------------------------------------------
+#ifdef ND_CUSIM   // tests/cusim (CPU emulation of these kernels for the CPU test suite; never part of the product build)
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+#else
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
   unsigned long long v;
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -341,6 +345,7 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+#endif
 
 // pack + publish, executed by the first n_pub thread blocks of the RHS grid: for every peer, gather the outputs it
 // needs from the owner's state vector (ascending offsets: the reads are nearly coalesced) and store them contiguously

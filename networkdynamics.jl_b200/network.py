@@ -199,7 +199,7 @@ class B200Aggregator:
         return agg
 
     def _build(self, im, vertexbatches, edgebatches):
-        L = _cabi.lib()
+        L = self._L = _cabi.lib()           # the library that owns the handle (also the one that destroys it)
         vb = (_cabi.VBatch * len(vertexbatches))()
         keep = []
         customs = {}     # custom_spec -> kind id: user-supplied CUDA component functions (compiled by the engine, NVRTC)
@@ -278,7 +278,7 @@ class B200Aggregator:
         h, self.handle = getattr(self, "handle", None), None
         if h:
             try:
-                _cabi.lib().nd_b200_destroy(h)
+                (getattr(self, "_L", None) or _cabi.lib()).nd_b200_destroy(h)
             except Exception:
                 pass
 
@@ -400,7 +400,7 @@ class Network:
             msg = L.nd_b200_last_error(None).decode()
             raise (ArgumentError if rc in (_cabi.EINVAL, _cabi.EUNSUPPORTED) else RuntimeError)(msg)
         agg = B200Aggregator("+", device=dev, row_range=row_range, keep_tables=keep_tables, host_only=host_only)
-        agg.handle, agg.device = h, int(dev)
+        agg.handle, agg.device, agg._L = h, int(dev), L
         self.vertexbatches = []
         self.layer = NetworkLayer(g, [], agg, edepth, vertexm.outdim)
         self.execution = B200Execution()

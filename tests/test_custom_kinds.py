@@ -2,8 +2,9 @@
 fused kernels and compiled for sm_100a when the network is built (NVRTC), lifting the fixed registry.
 
 CPU tests: the generated source compiles (host-only engines compile but do not load), errors surface as ArgumentError
-with the compiler log.  GPU tests: `du`, `get_buffers` and RK4 against the pure-Python oracle twin evaluating the SAME
-models from host callables (oracle/oracle_np.py: PyKind), on small graphs the twin finishes in seconds.
+with the compiler log.  Parity tests (`backend` fixture: the B200, and the CPU emulation of the same generated source in
+tests/cusim): `du`, `get_buffers` and RK4 against the pure-Python oracle twin evaluating the SAME models from host
+callables (oracle/oracle_np.py: PyKind), on small graphs the twin finishes in seconds.
 """
 import math
 
@@ -105,10 +106,9 @@ def test_custom_kinds_compile_and_report_errors(nd):
         assert nw.custom_source() is not None, name
 
 
-@pytest.mark.gpu
 @pytest.mark.parametrize("mode", ["fused", "jag"])
-def test_custom_kinds_match_python_twin(nd, cuda, monkeypatch, mode):
-    torch = cuda
+def test_custom_kinds_match_python_twin(nd, backend, monkeypatch, mode):
+    B = backend
     monkeypatch.setenv("ND_B200_KERNEL", mode)
     for name, g, vms, vt, ems, et in _cases(nd):
         nw = nd.Network(g, (vms, vt), (ems, et))
@@ -118,22 +118,18 @@ def test_custom_kinds_match_python_twin(nd, cuda, monkeypatch, mode):
         u, p = rng.random(nw.dim()), 0.25 + rng.random(nw.pdim())
         for t in (0.0, 0.7):
             ref_du, ref_o, ref_agg = ONP.rhs(im, u, p, t)
-            du = torch.full((nw.dim(),), float("nan"), dtype=torch.float64, device="cuda")
-            nw(du, torch.from_numpy(u).cuda(), torch.from_numpy(p).cuda(), t)
-            torch.cuda.synchronize()
-            assert floored_rel_err(du.cpu().numpy(), ref_du) <= 1e-12, (name, mode, t)
-        o = torch.full((nw.im.lastidx_out,), float("nan"), dtype=torch.float64, device="cuda")
-        agg = torch.full((nw.im.lastidx_aggr,), float("nan"), dtype=torch.float64, device="cuda")
-        nw.get_buffers(o, agg, torch.from_numpy(u).cuda(), torch.from_numpy(p).cuda(), 0.7)
-        torch.cuda.synchronize()
-        assert floored_rel_err(o.cpu().numpy(), ref_o) <= 1e-12, name
-        assert floored_rel_err(agg.cpu().numpy(), ref_agg) <= 1e-12, name
+            du = B.nan(nw.dim())
+            nw(du, B.dev(u), B.dev(p), t)
+            assert floored_rel_err(B.host(du), ref_du) <= 1e-12, (name, mode, t)
+        o, agg = B.nan(nw.im.lastidx_out), B.nan(nw.im.lastidx_aggr)
+        nw.get_buffers(o, agg, B.dev(u), B.dev(p), 0.7)
+        assert floored_rel_err(B.host(o), ref_o) <= 1e-12, name
+        assert floored_rel_err(B.host(agg), ref_agg) <= 1e-12, name
 
 
-@pytest.mark.gpu
-def test_custom_kinds_rk4_and_host_buffers(nd, cuda):
+def test_custom_kinds_rk4_and_host_buffers(nd, backend):
     """fused-stage RK4 and the host-buffer call work for user-supplied kinds (autonomous models: RK4 replays one graph)"""
-    torch = cuda
+    B = backend
     M = _models(nd)
     g = nd.erdos_renyi(400, 1600, seed=4)
     nw = nd.Network(g, M["fhn"], M["wsin"])
@@ -147,10 +143,9 @@ def test_custom_kinds_rk4_and_host_buffers(nd, cuda):
         k3 = ONP.rhs(im, x + 0.5 * dt * k2, p)[0]
         k4 = ONP.rhs(im, x + dt * k3, p)[0]
         x = x + (dt / 6.0) * (((k1 + 2.0 * k2) + 2.0 * k3) + k4)
-    ud = torch.from_numpy(u).cuda()
-    nw.rk4(ud, torch.from_numpy(p).cuda(), 0.0, dt, 5)
-    torch.cuda.synchronize()
-    assert floored_rel_err(ud.cpu().numpy(), x) <= 1e-11
+    ud = B.dev(u)
+    nw.rk4(ud, B.dev(p), 0.0, dt, 5)
+    assert floored_rel_err(B.host(ud), x) <= 1e-11
     hdu = np.empty_like(u)
     nw(hdu, u, p, 0.0)
     assert floored_rel_err(hdu, ONP.rhs(im, u, p)[0]) <= 1e-12

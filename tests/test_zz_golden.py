@@ -1,5 +1,5 @@
 """Committed fixtures (tests/golden/*.npz, written by tests/golden/make_golden.py): the C oracle reproduces them bit for
-bit, the independent pure-Python twin agrees, the graph generators are stable, and -- on a GPU -- the CUDA path matches
+bit, the independent pure-Python twin agrees, the graph generators are stable, and -- on a GPU -- the CUDA path (and, in the CPU suite, its emulation in tests/cusim) matches
 the stored numbers within the north_star tolerances (du 1e-12 per RHS; these 50-step trajectories 1e-11)."""
 import importlib.util
 import os
@@ -39,24 +39,22 @@ def test_oracle_reproduces_committed_fixtures(nd, name):
     assert np.array_equal(du2, z["du"]) and np.array_equal(agg2, z["aggbuf"])
 
 
-@pytest.mark.gpu
 @pytest.mark.parametrize("name", NAMES)
-def test_cuda_path_matches_committed_fixtures(nd, cuda, name):
-    torch = cuda
+def test_cuda_path_matches_committed_fixtures(nd, backend, name):
+    B = backend
     g, vm, em = make_golden.cases(nd)[name]
     z = np.load(os.path.join(HERE, name + ".npz"))
     nw = nd.Network(g, vm, em)
-    u, p = torch.from_numpy(z["u"]).cuda(), torch.from_numpy(z["p"]).cuda()
-    du = torch.full_like(u, float("nan"))
+    u, p = B.dev(z["u"]), B.dev(z["p"])
+    du = B.nan(nw.dim())
     nw(du, u, p, 0.0)
-    o = torch.full((nw.im.lastidx_out,), float("nan"), dtype=torch.float64, device="cuda")
-    agg = torch.full((nw.im.lastidx_aggr,), float("nan"), dtype=torch.float64, device="cuda")
+    o, agg = B.nan(nw.im.lastidx_out), B.nan(nw.im.lastidx_aggr)
     nw.get_buffers(o, agg, u, p, 0.0)
-    ur = u.clone()
+    ur = B.dev(z["u"])
     nw.rk4(ur, p, 0.0, 1e-3, 50)
-    torch.cuda.synchronize()
-    assert floored_rel_err(du.cpu().numpy(), z["du"]) <= 1e-12
-    assert floored_rel_err(o.cpu().numpy(), z["o"]) <= 1e-12 and floored_rel_err(agg.cpu().numpy(), z["aggbuf"]) <= 1e-12
-    assert floored_rel_err(ur.cpu().numpy(), z["rk4_50"]) <= 1e-11
+    du, o, agg, ur = B.host(du), B.host(o), B.host(agg), B.host(ur)
+    assert floored_rel_err(du, z["du"]) <= 1e-12
+    assert floored_rel_err(o, z["o"]) <= 1e-12 and floored_rel_err(agg, z["aggbuf"]) <= 1e-12
+    assert floored_rel_err(ur, z["rk4_50"]) <= 1e-11
     if name == "cfg2_diffusion_er":          # no transcendental, reference order: bit-identical
-        assert np.array_equal(du.cpu().numpy(), z["du"])
+        assert np.array_equal(du, z["du"])
