@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define ND_B200_ABI_VERSION 3
+#define ND_B200_ABI_VERSION 4
 
 /* status codes (Julia glue rethrows: EINVAL -> ArgumentError, others -> ErrorException) */
 enum {
@@ -44,11 +44,16 @@ enum {
   ND_B200_E_DIFFUSION = 0,             /* test/ComponentLibrary.jl:8-13,  e = p*(vs-vd)            */
   ND_B200_E_DIFFUSION_NOP = 1,         /* benchmark/benchmark_models.jl:5-9, e = vs-vd             */
   ND_B200_E_KURAMOTO = 2,              /* test/ComponentLibrary.jl:51-57, e = K*sin(ths-thd)       */
-  ND_B200_E_LINE_DQ = 3                /* test/ComponentLibrary.jl:212-245, p=(R,X,active)         */
+  ND_B200_E_LINE_DQ = 3,               /* test/ComponentLibrary.jl:212-245, p=(R,X,active)         */
+  /* edges WITH states (dim > 0): f(de,e,vsrc,vdst,p,t) registered here, outputs are StateMasks (ebatch.mask_*) */
+  ND_B200_E_DIFFUSION_ODE = 4,         /* test/ComponentLibrary.jl:30-40, dim 2, p=(tau,)          */
+  ND_B200_E_RELAX_ODE = 5,             /* test/diffusion_test.jl:96-101, dim 2, no parameters      */
+  ND_B200_E_DIFFUSION_FID = 6          /* test/ComponentLibrary.jl:22-28, static two-sided g (coupling = ND_B200_FIDUCIAL) */
 };
 /* edge output wrappers, src/component_functions.jl:117-203 */
 enum { ND_B200_ANTISYMMETRIC = 0, ND_B200_SYMMETRIC = 1, ND_B200_DIRECTED = 2,
-       ND_B200_FIDUCIAL = 3 /* the edge's own two-sided g(osrc, odst, ...); user-supplied kinds only */ };
+       ND_B200_FIDUCIAL = 3 /* static edges: the edge's own two-sided g(osrc, odst, ...) (ND_B200_E_DIFFUSION_FID or a
+                               user-supplied kind); edges with states: Fiducial(src=mask, dst=mask) */ };
 
 /* One `ComponentBatch` of vertices (src/network_structure.jl:176-222 + register_vertices! :224-239).
  * `*_first` are the `first` fields of the batch's BatchStrides (1-based); widths are the strides. */
@@ -71,6 +76,11 @@ typedef struct nd_b200_ebatch {
   int64_t count;
   const int64_t* indices;  /* batch.indices: 1-based edge ids                */
   int64_t state_first, p_first, out_first, gbuf_first;
+  /* edges with states (dim > 0; "ODE edges", src/coreloop.jl:41,76): the output function must be a StateMask
+   * (src/component_functions.jl:81-99) over a contiguous index range -- dst output k = state mask_dst_first + k
+   * (1-based), wrapped by AntiSymmetric / Symmetric / Directed, or Fiducial(src=..., dst=...) with its own
+   * mask_src_first.  0 when dim == 0. */
+  int32_t mask_src_first, mask_dst_first;
 } nd_b200_ebatch;
 
 /* ---- user-supplied component kinds (runtime-compiled, NVRTC) ---------------------------------------------------------
@@ -85,15 +95,17 @@ typedef struct nd_b200_ebatch {
  *              wrapped by AntiSymmetric / Symmetric / Directed (ebatch.coupling), or, with two_sided = 1 and
  *              coupling = ND_B200_FIDUCIAL, the reference's own two-sided form
  *              void g(double* e_src, double* e_dst, const double* v_src, const double* v_dst, const double* p, double t)
+ *   edge f   : void f(double* de, const double* e, const double* v_src, const double* v_dst, const double* p, double t)
+ *              for edges with states (custom_kind.dim > 0); their outputs are the StateMasks of ebatch.mask_*
  * Compiled with --fmad=false like the registry kernels.  A body that does not compile fails nd_b200_create with
  * ND_B200_EINVAL and the NVRTC log in nd_b200_last_error. */
 #define ND_B200_CUSTOM_KIND_BASE 1000
 typedef struct nd_b200_custom_kind {
   int32_t kind;            /* >= ND_B200_CUSTOM_KIND_BASE; referenced by vbatch.kind / ebatch.kind */
   int32_t role;            /* 0 = vertex, 1 = edge                                                */
-  int32_t dim, pdim, outdim;  /* vertex: states, parameters, outputs; edge: 0, parameters, outdim.dst */
+  int32_t dim, pdim, outdim;  /* vertex: states, parameters, outputs; edge: states (0 = static), parameters, outdim.dst */
   int32_t two_sided;       /* edge only: body has the Fiducial signature                         */
-  const char* f_body;      /* vertex: body of f; edge: body of g                                  */
+  const char* f_body;      /* vertex: body of f; static edge: body of g; edge with states: body of f */
   const char* g_body;      /* vertex: body of g, or NULL for StateMask(1:outdim); edge: NULL      */
 } nd_b200_custom_kind;
 

@@ -18,7 +18,7 @@ using CUDA: CuArray, CuPtr, stream
 import NetworkDynamics: aggregate!, get_aggr_constructor, iscudacompatible, aggfun
 
 const libnd_b200 = get(ENV, "ND_B200_LIB", "libnd_b200.so")
-const ABI_VERSION = Cint(3)
+const ABI_VERSION = Cint(4)
 
 # ---- tags ---------------------------------------------------------------------------------------------------------
 "`ExecutionStyle` tag (field-less: only its type is stored in `Network{EX,...}`, src/network_structure.jl:83,116)."
@@ -30,16 +30,23 @@ iscudacompatible(::Type{<:B200Execution}) = true
 # Users opt a component function into a hand-written kernel by adding a method; anything else raises ArgumentError.
 vertex_kernel(f, g) = nothing
 edge_kernel(g) = nothing
+edge_f_kernel(f) = nothing             # f of an edge WITH states ("ODE edge"); its g must be StateMasks
 const V_DIFFUSION, V_KURAMOTO_FIRST, V_KURAMOTO_SECOND, V_KURAMOTO_SECOND_BENCH, V_SWING_DQ = Cint.(0:4)
-const E_DIFFUSION, E_DIFFUSION_NOP, E_KURAMOTO, E_LINE_DQ = Cint.(0:3)
+const E_DIFFUSION, E_DIFFUSION_NOP, E_KURAMOTO, E_LINE_DQ, E_DIFFUSION_ODE, E_RELAX_ODE, E_DIFFUSION_FID = Cint.(0:6)
 # e.g. (test/ComponentLibrary.jl):
 #   NetworkDynamicsB200.edge_kernel(::typeof(Lib.kuramoto_edge!))       = NetworkDynamicsB200.E_KURAMOTO
 #   NetworkDynamicsB200.vertex_kernel(::typeof(Lib.kuramoto_vertex!), ::StateMask) = NetworkDynamicsB200.V_KURAMOTO_FIRST
+#   NetworkDynamicsB200.edge_kernel(::typeof(Lib.diffusionedge_fid!))    = NetworkDynamicsB200.E_DIFFUSION_FID   # two-sided, unwrapped
+#   NetworkDynamicsB200.edge_f_kernel(::typeof(Lib.diffusion_dedge!))    = NetworkDynamicsB200.E_DIFFUSION_ODE   # g = Fiducial(dst=1:1, src=2:2)
+
+# contiguous StateMask -> its first index (1-based); anything else is not an engine-readable output of a stateful edge
+_mask_first(m::StateMask) = (ix = collect(m.idxs); ix == collect(first(ix):first(ix)+length(ix)-1) ? Cint(first(ix)) : nothing)
+_mask_first(_) = nothing
 
 coupling_of(::AntiSymmetric) = Cint(0)
 coupling_of(::Symmetric) = Cint(1)
 coupling_of(::Directed) = Cint(2)
-coupling_of(::Fiducial) = Cint(3)          # user-supplied two-sided kinds only (see cuda_source)
+coupling_of(::Fiducial) = Cint(3)          # static: two-sided kinds; with states: Fiducial(src=mask, dst=mask)
 coupling_of(x) = throw(ArgumentError("B200 engine: edge output wrapper $(typeof(x)) is not supported (no CPU fallback)"))
 
 # ---- user-supplied kinds (run-time compiled by the engine, NVRTC; include/nd_b200.h: nd_b200_custom_kind) -----------
@@ -67,6 +74,7 @@ struct CEBatch
     kind::Cint; coupling::Cint; dim::Cint; pdim::Cint; outdim_src::Cint; outdim_dst::Cint
     count::Int64; indices::Ptr{Int64}
     state_first::Int64; p_first::Int64; out_first::Int64; gbuf_first::Int64
+    mask_src_first::Cint; mask_dst_first::Cint      # edges with states: StateMask outputs (0 for static edges)
 end
 struct CDesc
     abi_version::Cint; device::Cint
@@ -128,18 +136,34 @@ function B200Aggregator(im::IndexManager, edgebatches, f)
     end
     eb = map(collect(edgebatches)) do b
         g = compg(b)
-        inner = g isa NetworkDynamics.SingleSidedOutputWrapper && !(g isa Fiducial) ? g.g : g
-        kind = edge_kernel(inner)
-        if isnothing(kind) && !isnothing(cuda_source(inner))         # user-supplied kind (two-sided body: Fiducial / unwrapped)
-            two = (g isa Fiducial || !(g isa NetworkDynamics.SingleSidedOutputWrapper)) ? 1 : 0
-            kind = custom_kind!(1, 0, pdim(b), outdim(b).dst, two, cuda_source(inner), nothing)
-        end
-        (isnothing(kind) || !isnothing(compf(b))) &&
-            throw(ArgumentError("edge batch $(typeof(g)) has neither a registry kernel nor a cuda_source, or is an ODE edge (no CPU fallback)"))
-        ix = Vector{Int64}(b.indices); push!(keep, ix)
         od = outdim(b)
-        CEBatch(kind, coupling_of(g), dim(b), pdim(b), od.src, od.dst, length(ix), pointer(ix),
-                b.statestride.first, b.pstride.first, b.outbufstride.first, b.inbufstride.first)
+        msrc, mdst = Cint(0), Cint(0)
+        if dim(b) > 0
+            # edge with states (src/coreloop.jl:41,76): f is a registry kernel or a cuda_source body, the outputs must be
+            # contiguous StateMasks -- AntiSymmetric(1), Symmetric(1:2), Directed(1), Fiducial(dst=1:1, src=2:2), ...
+            g isa NetworkDynamics.SingleSidedOutputWrapper || throw(ArgumentError("B200 engine: an edge with states needs StateMask outputs (no CPU fallback)"))
+            md = _mask_first(g isa Fiducial ? g.dst : g.g)
+            ms = g isa Fiducial ? _mask_first(g.src) : Cint(0)
+            (isnothing(md) || isnothing(ms)) && throw(ArgumentError("B200 engine: edge outputs must be contiguous StateMasks of the edge's states"))
+            msrc, mdst = ms, md
+            kind = edge_f_kernel(compf(b))
+            if isnothing(kind) && !isnothing(cuda_source(compf(b)))
+                kind = custom_kind!(1, dim(b), pdim(b), od.dst, 0, cuda_source(compf(b)), nothing)
+            end
+        else
+            inner = g isa NetworkDynamics.SingleSidedOutputWrapper && !(g isa Fiducial) ? g.g : g
+            kind = edge_kernel(inner)
+            if isnothing(kind) && !isnothing(cuda_source(inner))     # user-supplied kind (two-sided body: Fiducial / unwrapped)
+                two = (g isa Fiducial || !(g isa NetworkDynamics.SingleSidedOutputWrapper)) ? 1 : 0
+                kind = custom_kind!(1, 0, pdim(b), od.dst, two, cuda_source(inner), nothing)
+            end
+        end
+        isnothing(kind) &&
+            throw(ArgumentError("edge batch $(typeof(g)) has neither a registry kernel nor a cuda_source (no CPU fallback)"))
+        ix = Vector{Int64}(b.indices); push!(keep, ix)
+        coupling = g isa NetworkDynamics.SingleSidedOutputWrapper ? coupling_of(g) : Cint(3)   # unwrapped two-sided g
+        CEBatch(kind, coupling, dim(b), pdim(b), od.src, od.dst, length(ix), pointer(ix),
+                b.statestride.first, b.pstride.first, b.outbufstride.first, b.inbufstride.first, msrc, mdst)
     end
     esrc = Int64[e.src for e in im.edgevec]; edst = Int64[e.dst for e in im.edgevec]
     handle = Ref{Ptr{Cvoid}}(C_NULL)

@@ -24,7 +24,7 @@ class RegisteredFunction:
     """A component function with a hand-written sm_100a kernel.  `ref` cites the Julia source it restates."""
     name: str
     kind: int
-    role: str  # "vertex_f" | "vertex_g" | "edge_g"
+    role: str  # "vertex_f" | "vertex_g" | "edge_g" | "edge_g2" (two-sided static g) | "edge_f" (f of an edge with states)
     ref: str = ""
 
     def __call__(self, *a, **k):  # pragma: no cover - these are device kernels, not host callables
@@ -42,6 +42,8 @@ class CudaFunction:
       edge_g   : double* e_dst, const double* v_src, const double* v_dst, const double* p, double t
       edge_g2  : double* e_src, double* e_dst, const double* v_src, const double* v_dst, const double* p, double t
                  (the two-sided form; use it unwrapped or as Fiducial(...))
+      edge_f   : double* de, const double* e, const double* v_src, const double* v_dst, const double* p, double t
+                 (f of an edge with states; its g must be StateMasks: AntiSymmetric(1), Fiducial(dst=1, src=2), ...)
     `py` is an optional host restatement (same arguments as numpy arrays, returning the outputs) used by tests only."""
     name: str
     role: str
@@ -52,11 +54,36 @@ class CudaFunction:
         raise RuntimeError(f"{self.name} is device code; evaluate it through Network(...)")
 
 
-@dataclass(frozen=True)
 class Fiducial:
-    """the edge's own two-sided g(osrc, odst, ...), src/component_functions.jl:189-203 (user-supplied kinds only)"""
-    g: object
+    """`Fiducial(src, dst)` / `Fiducial(src=..., dst=...)` (src/component_functions.jl:177-203): two single-sided output
+    functions.  For edges with states both are StateMasks (ints / index tuples are wrapped like in the reference,
+    :191-194).  For static edges the engine takes the pair as ONE two-sided function `Fiducial(g)` with
+    g(osrc, odst, vsrc, vdst, p, t) -- the form the reference itself evaluates (src/coreloop.jl:208)."""
     coupling = _cabi.FIDUCIAL
+
+    def __init__(self, *args, src=None, dst=None, g=None):
+        if len(args) == 1 and src is None and dst is None and g is None:
+            g = args[0]
+        elif len(args) == 2 and src is None and dst is None:
+            src, dst = args
+        elif args:
+            raise ArgumentError("Fiducial(g), Fiducial(src, dst) or Fiducial(src=..., dst=...)")
+        wrap = lambda m: m if (m is None or isinstance(m, StateMask) or callable(m)) else StateMask(m)
+        self.g, self.src, self.dst = g, wrap(src), wrap(dst)
+        if (self.g is None) == (self.src is None or self.dst is None):
+            raise ArgumentError("Fiducial needs either one two-sided function or both src and dst")
+
+    def _key(self):
+        return (self.g, self.src, self.dst)
+
+    def __eq__(self, o):
+        return isinstance(o, Fiducial) and self._key() == o._key()
+
+    def __hash__(self):
+        return hash(("Fiducial",) + self._key())
+
+    def __repr__(self):
+        return f"Fiducial({self.g!r})" if self.g is not None else f"Fiducial(src={self.src!r}, dst={self.dst!r})"
 
 
 @dataclass(frozen=True)
@@ -69,26 +96,43 @@ class StateMask:
             idxs = (idxs,)
         object.__setattr__(self, "idxs", tuple(int(i) for i in idxs))
 
+    def contiguous_first(self):
+        """first index when the mask is a contiguous ascending range (what the engine's StateMask reads need), else None"""
+        i = self.idxs
+        return i[0] if i and i == tuple(range(i[0], i[0] + len(i))) else None
+
 
 @dataclass(frozen=True)
 class AntiSymmetric:
-    """osrc = -odst, src/component_functions.jl:117-127"""
+    """osrc = -odst, src/component_functions.jl:117-127; a number / index tuple wraps the StateMask like in the reference"""
     g: object
     coupling = _cabi.ANTISYMMETRIC
+
+    def __post_init__(self):
+        if isinstance(self.g, (int, tuple, list, range)):
+            object.__setattr__(self, "g", StateMask(self.g))
 
 
 @dataclass(frozen=True)
 class Symmetric:
-    """osrc = odst, src/component_functions.jl:142-152"""
+    """osrc = odst, src/component_functions.jl:142-152; a number / index tuple wraps the StateMask like in the reference"""
     g: object
     coupling = _cabi.SYMMETRIC
+
+    def __post_init__(self):
+        if isinstance(self.g, (int, tuple, list, range)):
+            object.__setattr__(self, "g", StateMask(self.g))
 
 
 @dataclass(frozen=True)
 class Directed:
-    """no src output (outdim.src = 0), src/component_functions.jl:167-175"""
+    """no src output (outdim.src = 0), src/component_functions.jl:167-175; a number / index tuple wraps the StateMask like in the reference"""
     g: object
     coupling = _cabi.DIRECTED
+
+    def __post_init__(self):
+        if isinstance(self.g, (int, tuple, list, range)):
+            object.__setattr__(self, "g", StateMask(self.g))
 
 
 @dataclass(frozen=True)
@@ -139,7 +183,8 @@ class VertexModel:
 
 @dataclass(frozen=True)
 class EdgeModel:
-    g: object                      # AntiSymmetric / Symmetric / Directed wrapping a RegisteredFunction
+    g: object                      # AntiSymmetric / Symmetric / Directed / Fiducial wrapping a function or, for edges with
+                                   # states (f given, dim > 0), StateMasks
     outdim: int = 1
     pdim: int = 0
     dim: int = 0
@@ -164,8 +209,29 @@ class EdgeModel:
     def component_hash(self):
         return ("E", self.f, self.g, self.dim, self.outdim_src, self.outdim_dst, self.pdim)
 
+    def state_masks(self):
+        """(mask_src_first, mask_dst_first), 1-based, for an edge with states whose outputs are contiguous StateMasks of
+        the right width; None otherwise (src/component_functions.jl:81-99,117-203)"""
+        if self.dim <= 0 or self.f is None:
+            return None
+        if isinstance(self.g, Fiducial):
+            ms, md = self.g.src, self.g.dst
+            if not (isinstance(ms, StateMask) and isinstance(md, StateMask)) or len(ms.idxs) != self.outdim or len(md.idxs) != self.outdim:
+                return None
+            a, b = ms.contiguous_first(), md.contiguous_first()
+            return None if a is None or b is None or max(a, b) + self.outdim - 1 > self.dim else (a, b)
+        md = getattr(self.g, "g", None)
+        if not isinstance(md, StateMask) or len(md.idxs) != self.outdim:
+            return None
+        b = md.contiguous_first()
+        return None if b is None or b + self.outdim - 1 > self.dim else (0, b)
+
     def custom_spec(self):
-        if self.f is not None or self.dim != 0:
+        if self.dim > 0:              # edge with states: user-supplied f, StateMask outputs
+            if isinstance(self.f, CudaFunction) and self.f.role == "edge_f" and self.state_masks() is not None:
+                return (1, self.dim, self.pdim, self.outdim, 0, self.f.body, None)
+            return None
+        if self.f is not None:
             return None
         if isinstance(self.g, CudaFunction) and self.g.role == "edge_g2":       # unwrapped two-sided g
             return (1, 0, self.pdim, self.outdim, 1, self.g.body, None)
@@ -178,9 +244,15 @@ class EdgeModel:
 
     def kernel_kind(self) -> Optional[int]:
         inner = getattr(self.g, "g", None)
-        if self.f is not None or self.dim != 0 or self.coupling is None:
+        if self.coupling is None:
             return None
-        if isinstance(inner, RegisteredFunction) and inner.role == "edge_g":
+        if self.dim > 0:              # edge with states: registered f, StateMask outputs
+            if isinstance(self.f, RegisteredFunction) and self.f.role == "edge_f" and self.state_masks() is not None:
+                return self.f.kind
+            return None
+        if self.f is not None:
+            return None
+        if isinstance(inner, RegisteredFunction) and inner.role == ("edge_g2" if isinstance(self.g, Fiducial) else "edge_g"):
             return inner.kind
         return None
 
@@ -192,6 +264,9 @@ class Lib:
     diffusionedge_nop = RegisteredFunction("diffusionedge!", _cabi.E_DIFFUSION_NOP, "edge_g", "benchmark/benchmark_models.jl:5-8")
     kuramoto_edge_f = RegisteredFunction("kuramoto_edge!", _cabi.E_KURAMOTO, "edge_g", "test/ComponentLibrary.jl:51-53")
     line_dq_f = RegisteredFunction("StaticPowerLineDQ", _cabi.E_LINE_DQ, "edge_g", "test/ComponentLibrary.jl:212-245")
+    diffusionedge_fid = RegisteredFunction("diffusionedge_fid!", _cabi.E_DIFFUSION_FID, "edge_g2", "test/ComponentLibrary.jl:22-25")
+    diffusion_dedge = RegisteredFunction("diffusion_dedge!", _cabi.E_DIFFUSION_ODE, "edge_f", "test/ComponentLibrary.jl:30-34")
+    real_ode_edge = RegisteredFunction("real_ode_edge!", _cabi.E_RELAX_ODE, "edge_f", "test/diffusion_test.jl:96-100")
     diffusionvertex = RegisteredFunction("diffusionvertex!", _cabi.V_DIFFUSION, "vertex_f", "test/ComponentLibrary.jl:42-45")
     kuramoto_vertex = RegisteredFunction("kuramoto_vertex!", _cabi.V_KURAMOTO_FIRST, "vertex_f", "test/ComponentLibrary.jl:69-71")
     kuramoto_inertia = RegisteredFunction("kuramoto_inertia!", _cabi.V_KURAMOTO_SECOND, "vertex_f", "test/ComponentLibrary.jl:59-63")
@@ -207,6 +282,22 @@ class Lib:
     def diffusion_edge_nop():
         """benchmark variant without a parameter (benchmark/benchmark_models.jl:9)"""
         return EdgeModel(g=AntiSymmetric(Lib.diffusionedge_nop), outdim=1, pdim=0, name="diff_edge")
+
+    @staticmethod
+    def diffusion_edge_fid():
+        """test/ComponentLibrary.jl:26-28: two-sided static g, no wrapper"""
+        return EdgeModel(g=Fiducial(Lib.diffusionedge_fid), outdim=1, pdim=1, name="diff_edge_fid")
+
+    @staticmethod
+    def diffusion_odeedge():
+        """test/ComponentLibrary.jl:35-40: edge with two states, outputs Fiducial(dst=1:1, src=2:2)"""
+        return EdgeModel(f=Lib.diffusion_dedge, dim=2, pdim=1, psym=("τ",), g=Fiducial(dst=(1,), src=(2,)), outdim=1,
+                         name="diff_edge_ode")
+
+    @staticmethod
+    def relax_odeedge():
+        """test/diffusion_test.jl:101: EdgeModel(; f=real_ode_edge!, dim=2, g=Fiducial(2,1))"""
+        return EdgeModel(f=Lib.real_ode_edge, dim=2, pdim=0, g=Fiducial(2, 1), outdim=1, name="real_ode_edge")
 
     @staticmethod
     def diffusion_vertex():

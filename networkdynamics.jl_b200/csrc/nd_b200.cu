@@ -40,7 +40,7 @@ constexpr int MAX_VB = 64;
 constexpr int MAX_EB = 255;   // edge batch id is stored per entry as uint8
 
 struct HostVB { int kind, dim, pdim, outdim; long long count, state0, p0, out0, row0; };
-struct HostEB { int kind, coupling, dim, pdim, osrc, odst; long long count, p0, out0; };
+struct HostEB { int kind, coupling, dim, pdim, osrc, odst; long long count, p0, out0; long long state0; int mask_src, mask_dst; };   // masks 0-based
 
 }  // namespace
 
@@ -102,7 +102,12 @@ struct nd_b200_engine {
   int c_pe = 0, c_maxdim = 1;          // template PE (largest edge pdim) and ND_MAX_VDIM of the generated kernels
   std::string custom_src;
   cudaLibrary_t c_lib = nullptr;
-  cudaKernel_t c_fused = nullptr, c_jag = nullptr, c_vout = nullptr, c_eout = nullptr;
+  cudaKernel_t c_fused = nullptr, c_jag = nullptr, c_vout = nullptr, c_eout = nullptr, c_ef = nullptr;
+  // edge batches with states ("ODE edges"): their f runs in edge_f_kernel after the row kernel; per edge of the batch the
+  // gather offsets of its two vertex outputs
+  struct OdeBatch { int b; int* d_es; int* d_et; };
+  std::vector<OdeBatch> ode;
+  int c_maxedim = 1;                   // ND_MAX_EDIM of the generated kernels
   bool host_only = false;     // ND_B200_FLAG_HOST_ONLY: tables built, nothing uploaded (layout tests without a GPU)
   std::vector<int4> h_jslices, h_jlong;
   std::vector<uint16_t> h_jlanes;
@@ -200,22 +205,27 @@ bool edge_kind_ok(const nd_b200_engine* e, const nd_b200_ebatch& b, int vdepth, 
   if (b.kind >= ND_B200_CUSTOM_KIND_BASE) {
     const auto* c = find_custom(e, b.kind, 1);
     if (!c) { why = "edge kind " + std::to_string(b.kind) + " is not among the descriptor's custom kinds"; return false; }
-    if (c->pdim != b.pdim || c->outdim != b.outdim_dst) { why = "custom edge kind " + std::to_string(b.kind) + " declared with other (pdim,outdim)"; return false; }
+    if (c->pdim != b.pdim || c->outdim != b.outdim_dst || c->dim != b.dim) { why = "custom edge kind " + std::to_string(b.kind) + " declared with other (dim,pdim,outdim)"; return false; }
+    if (b.dim > 0) {
+      if (c->two_sided) { why = "custom edge kind " + std::to_string(b.kind) + ": an edge with states supplies f; its outputs are StateMasks"; return false; }
+      return true;
+    }
     if ((b.coupling == ND_B200_FIDUCIAL) != (c->two_sided != 0)) { why = "custom edge kind " + std::to_string(b.kind) + ": the Fiducial wrapper and a two-sided body go together"; return false; }
     return true;
   }
-  if (b.coupling == ND_B200_FIDUCIAL) { why = "Fiducial edges need a user-supplied (custom) kind"; return false; }
+  if (b.dim == 0 && (b.coupling == ND_B200_FIDUCIAL) != (b.kind == ND_B200_E_DIFFUSION_FID)) { why = "a static Fiducial edge needs a two-sided kind (ND_B200_E_DIFFUSION_FID or a user-supplied one)"; return false; }
   return edge_kind_ok(b, vdepth, why);
 }
 
 bool edge_kind_ok(const nd_b200_ebatch& b, int vdepth, std::string& why) {
-  struct R { int kind, pdim, odst, vdepth; };
-  static const R reg[] = {{ND_B200_E_DIFFUSION, 1, 1, 1}, {ND_B200_E_DIFFUSION_NOP, 0, 1, 1},
-                          {ND_B200_E_KURAMOTO, 1, 1, 1}, {ND_B200_E_LINE_DQ, 3, 2, 2}};
+  struct R { int kind, pdim, odst, vdepth, dim; };
+  static const R reg[] = {{ND_B200_E_DIFFUSION, 1, 1, 1, 0}, {ND_B200_E_DIFFUSION_NOP, 0, 1, 1, 0},
+                          {ND_B200_E_KURAMOTO, 1, 1, 1, 0}, {ND_B200_E_LINE_DQ, 3, 2, 2, 0},
+                          {ND_B200_E_DIFFUSION_ODE, 1, 1, 1, 2}, {ND_B200_E_RELAX_ODE, 0, 1, 1, 2}, {ND_B200_E_DIFFUSION_FID, 1, 1, 1, 0}};
   for (const R& r : reg)
     if (r.kind == b.kind) {
-      if (r.pdim != b.pdim || r.odst != b.outdim_dst || r.vdepth != vdepth) {
-        why = "edge kind " + std::to_string(b.kind) + " registered with (pdim,outdim,vdepth)=(" + std::to_string(r.pdim) + "," +
+      if (r.pdim != b.pdim || r.odst != b.outdim_dst || r.vdepth != vdepth || r.dim != b.dim) {
+        why = "edge kind " + std::to_string(b.kind) + " registered with (dim,pdim,outdim,vdepth)=(" + std::to_string(r.dim) + "," + std::to_string(r.pdim) + "," +
               std::to_string(r.odst) + "," + std::to_string(r.vdepth) + ")";
         return false;
       }
@@ -230,6 +240,7 @@ void fill_params(const nd_b200_engine* e, KParams& P) {
   P.rowptr = e->d_rowptr; P.nbr = e->d_nbr; P.epar = e->d_epar; P.ebid = e->d_ebid; P.blk_row = e->d_blk_row;
   P.vb = e->d_vb; P.eb = e->d_eb; P.n_vb = (int)e->hvb.size(); P.n_eb = (int)e->heb.size();
   P.row_base = (int)e->row_begin; P.long_thr = e->long_thr; P.gather_from_u = e->gather_from_u;
+  P.state_edges = e->ode.empty() ? 0 : 1;
   P.tiles = e->d_tiles; P.ntiles = e->ntiles; P.oidx = e->d_oidx; P.oedge = e->d_oedge;
   P.jslices = e->d_jslices; P.jlanes = e->d_jlanes; P.jnbr = e->d_jnbr; P.jent = e->d_jent; P.jebid = e->d_jebid;
   P.jlong = e->d_jlong; P.nslices = e->nslices; P.n_jag_blocks = e->n_jag_blocks;
@@ -361,6 +372,35 @@ cudaError_t launch_vout(nd_b200_engine* e, const double* u, const double* p, dou
   return cudaGetLastError();
 }
 
+// PASS 4 for edge batches with states: du_e = f(u_e, v_src, v_dst, p, t), with the epilogue of the evaluation P describes
+cudaError_t launch_edge_f(nd_b200_engine* e, const KParams& P, cudaStream_t st) {
+  for (const auto& ob : e->ode) {
+    const HostEB& h = e->heb[(size_t)ob.b];
+    EFParams Q;
+    memset(&Q, 0, sizeof Q);
+    Q.kind = h.kind; Q.dim = h.dim; Q.pdim = h.pdim; Q.count = h.count; Q.state0 = h.state0; Q.p0 = h.p0;
+    Q.esrc_off = ob.d_es; Q.edst_off = ob.d_et;
+    Q.u = P.u; Q.gsrc = P.gsrc; Q.p = P.p; Q.du = P.du; Q.mode = P.mode; Q.stage = P.stage; Q.u0 = P.u0; Q.unext = P.unext;
+    Q.ksum = P.ksum; Q.hs = P.hs; Q.h6 = P.h6; Q.t = P.t;
+    const int T = 256;
+    const int nb = (int)((h.count + T - 1) / T);
+    if (nb == 0) continue;
+    e->launches++;
+    if (e->custom) {
+      void* args[] = {&Q};
+      cudaError_t c = cudaLaunchKernel((const void*)e->c_ef, dim3((unsigned)nb), dim3(T), args, 0, st);
+      if (c != cudaSuccess) return c;
+    } else if (e->vdepth == 2) {
+      ND_LAUNCH(nb, T, st, (Q), edge_f_kernel<2>);
+    } else {
+      ND_LAUNCH(nb, T, st, (Q), edge_f_kernel<1>);
+    }
+    cudaError_t c = cudaGetLastError();
+    if (c != cudaSuccess) return c;
+  }
+  return cudaSuccess;
+}
+
 int ensure_events(nd_b200_engine* e, std::vector<cudaEvent_t>& v, size_t need) {
   while (v.size() < need) {
     cudaEvent_t ev;
@@ -386,15 +426,15 @@ std::string custom_source(const nd_b200_engine* e, int vdepth) {
            "enum { ND_B200_V_DIFFUSION = %d, ND_B200_V_KURAMOTO_FIRST = %d, ND_B200_V_KURAMOTO_SECOND = %d, ND_B200_V_KURAMOTO_SECOND_BENCH = %d, ND_B200_V_SWING_DQ = %d };\n",
            ND_B200_V_DIFFUSION, ND_B200_V_KURAMOTO_FIRST, ND_B200_V_KURAMOTO_SECOND, ND_B200_V_KURAMOTO_SECOND_BENCH, ND_B200_V_SWING_DQ);
   src += buf;
-  snprintf(buf, sizeof buf, "enum { ND_B200_E_DIFFUSION = %d, ND_B200_E_DIFFUSION_NOP = %d, ND_B200_E_KURAMOTO = %d, ND_B200_E_LINE_DQ = %d };\n",
-           ND_B200_E_DIFFUSION, ND_B200_E_DIFFUSION_NOP, ND_B200_E_KURAMOTO, ND_B200_E_LINE_DQ);
+  snprintf(buf, sizeof buf, "enum { ND_B200_E_DIFFUSION = %d, ND_B200_E_DIFFUSION_NOP = %d, ND_B200_E_KURAMOTO = %d, ND_B200_E_LINE_DQ = %d, ND_B200_E_DIFFUSION_ODE = %d, ND_B200_E_RELAX_ODE = %d, ND_B200_E_DIFFUSION_FID = %d };\n",
+           ND_B200_E_DIFFUSION, ND_B200_E_DIFFUSION_NOP, ND_B200_E_KURAMOTO, ND_B200_E_LINE_DQ, ND_B200_E_DIFFUSION_ODE, ND_B200_E_RELAX_ODE, ND_B200_E_DIFFUSION_FID);
   src += buf;
   snprintf(buf, sizeof buf, "enum { ND_B200_ANTISYMMETRIC = %d, ND_B200_SYMMETRIC = %d, ND_B200_DIRECTED = %d, ND_B200_FIDUCIAL = %d };\n",
            ND_B200_ANTISYMMETRIC, ND_B200_SYMMETRIC, ND_B200_DIRECTED, ND_B200_FIDUCIAL);
   src += buf;
-  snprintf(buf, sizeof buf, "#define ND_MAX_VDIM %d\n#define ND_MAX_VOUT %d\n", std::max(e->c_maxdim, 1), std::max(vdepth, 1));
+  snprintf(buf, sizeof buf, "#define ND_MAX_VDIM %d\n#define ND_MAX_VOUT %d\n#define ND_MAX_EDIM %d\n", std::max(e->c_maxdim, 1), std::max(vdepth, 1), std::max(e->c_maxedim, 2));
   src += buf;
-  std::string edge_cases, fid_cases, vf_cases, vg_cases;
+  std::string edge_cases, fid_cases, vf_cases, vg_cases, ef_cases;
   src += "namespace ndb_user {\n";
   for (const auto& c : e->customs) {
     const std::string id = std::to_string(c.kind);
@@ -405,6 +445,9 @@ std::string custom_source(const nd_b200_engine* e, int vdepth) {
         src += "__device__ __forceinline__ void vertex_g_" + id + "(double* __restrict__ out, const double* __restrict__ v, const double* __restrict__ p, double t) {\n" + c.g_body + "\n}\n";
         vg_cases += " case " + id + ": ndb_user::vertex_g_" + id + "(out, v, pv, t); break;";
       }
+    } else if (c.dim > 0) {   // edge with states: the body is f; outputs are StateMasks
+      src += "__device__ __forceinline__ void edge_f_" + id + "(double* __restrict__ de, const double* __restrict__ e, const double* __restrict__ v_src, const double* __restrict__ v_dst, const double* __restrict__ p, double t) {\n" + c.f_body + "\n}\n";
+      ef_cases += " case " + id + ": ndb_user::edge_f_" + id + "(de, ue, vs, vd, pe, t); break;";
     } else if (c.two_sided) {
       src += "__device__ __forceinline__ void edge_g_" + id + "(double* __restrict__ e_src, double* __restrict__ e_dst, const double* __restrict__ v_src, const double* __restrict__ v_dst, const double* __restrict__ p, double t) {\n" + c.f_body + "\n}\n";
       fid_cases += " case " + id + ": ndb_user::edge_g_" + id + "(osrc, odst, vs, vd, pe, t); break;";
@@ -416,6 +459,7 @@ std::string custom_source(const nd_b200_engine* e, int vdepth) {
   src += "}  // namespace ndb_user\n";
   src += "#define ND_CUSTOM_EDGE_CASES" + edge_cases + "\n";
   src += "#define ND_CUSTOM_EDGE_FID_CASES" + fid_cases + "\n";
+  src += "#define ND_CUSTOM_EDGE_F_CASES" + ef_cases + "\n";
   src += "#define ND_CUSTOM_VERTEX_F_CASES" + vf_cases + "\n";
   src += "#define ND_CUSTOM_VERTEX_G_CASES" + vg_cases + "\n";
   for (const char* part : kKernelHeaderText) src += part;
@@ -428,14 +472,15 @@ int compile_custom(nd_b200_engine* e, int vdepth, int edepth) {
   nvrtcProgram prog = nullptr;
   if (nvrtcCreateProgram(&prog, e->custom_src.c_str(), "nd_b200_custom.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS)
     return fail(e, ND_B200_ECUDA, "nvrtcCreateProgram failed");
-  char nm[4][160];
+  char nm[5][160];
   const int ek = e->ek, pe = e->c_pe;
   const char* halo = e->halo_base != INT_MAX ? "true" : "false";
   snprintf(nm[0], sizeof nm[0], "ndb::rhs_fused_kernel<%d, %d, %d, %d, 128, 4, %s>", vdepth, edepth, ek, pe, halo);
   snprintf(nm[1], sizeof nm[1], "ndb::rhs_jag_kernel<%d, %d, %d, %d, 128, 2, 48, %s>", vdepth, edepth, ek, pe, halo);
   snprintf(nm[2], sizeof nm[2], "ndb::vertex_out_kernel");
   snprintf(nm[3], sizeof nm[3], "ndb::edge_out_kernel<%d, %d>", vdepth, edepth);
-  for (int k = 0; k < 4; ++k) nvrtcAddNameExpression(prog, nm[k]);
+  snprintf(nm[4], sizeof nm[4], "ndb::edge_f_kernel<%d>", vdepth);
+  for (int k = 0; k < 5; ++k) nvrtcAddNameExpression(prog, nm[k]);
   const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "--fmad=false", "-lineinfo", "-default-device"};
   const nvrtcResult rc = nvrtcCompileProgram(prog, 5, opts);
   if (rc != NVRTC_SUCCESS) {
@@ -452,8 +497,8 @@ int compile_custom(nd_b200_engine* e, int vdepth, int edepth) {
   nvrtcGetCUBINSize(prog, &nbin);
   std::vector<char> cubin(nbin);
   nvrtcGetCUBIN(prog, cubin.data());
-  std::string lowered[4];
-  for (int k = 0; k < 4; ++k) {
+  std::string lowered[5];
+  for (int k = 0; k < 5; ++k) {
     const char* ln = nullptr;
     if (nvrtcGetLoweredName(prog, nm[k], &ln) != NVRTC_SUCCESS || !ln) { nvrtcDestroyProgram(&prog); return fail(e, ND_B200_ECUDA, "no lowered name for %s", nm[k]); }
     lowered[k] = ln;
@@ -465,6 +510,7 @@ int compile_custom(nd_b200_engine* e, int vdepth, int edepth) {
   CUDA_TRY(e, cudaLibraryGetKernel(&e->c_jag, e->c_lib, lowered[1].c_str()));
   CUDA_TRY(e, cudaLibraryGetKernel(&e->c_vout, e->c_lib, lowered[2].c_str()));
   CUDA_TRY(e, cudaLibraryGetKernel(&e->c_eout, e->c_lib, lowered[3].c_str()));
+  CUDA_TRY(e, cudaLibraryGetKernel(&e->c_ef, e->c_lib, lowered[4].c_str()));
   return ND_B200_OK;
 }
 
@@ -483,6 +529,7 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
     const nd_b200_custom_kind& c = d->custom[k];
     if (c.kind < ND_B200_CUSTOM_KIND_BASE || (c.role != 0 && c.role != 1) || !c.f_body) return fail(e, ND_B200_EINVAL, "custom kind %d: id must be >= %d, role 0|1, f_body non-NULL", c.kind, ND_B200_CUSTOM_KIND_BASE);
     if (c.dim < 0 || c.dim > 16 || c.pdim < 0 || c.pdim > 64 || c.outdim < 1 || c.outdim > 8) return fail(e, ND_B200_EUNSUPPORTED, "custom kind %d: dims outside dim<=16, pdim<=64, 1<=outdim<=8", c.kind);
+    if (c.role == 1) e->c_maxedim = std::max(e->c_maxedim, c.dim);
     e->customs.push_back(nd_b200_engine::CustomKind{c.kind, c.role, c.dim, c.pdim, c.outdim, c.two_sided, c.f_body, c.g_body ? c.g_body : ""});
   }
   for (int b = 0; b < d->n_vbatches; ++b) e->custom = e->custom || d->vbatches[b].kind >= ND_B200_CUSTOM_KIND_BASE;
@@ -558,7 +605,7 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
   }
 
   // ---- edge batches --------------------------------------------------------------------------
-  bool any_epar = false;
+  bool any_epar = false, any_ode = false;
   long long eout_expect = out_expect;
   std::vector<char> edge_seen((size_t)std::max<long long>(d->ne, 1), 0);
   for (int b = 0; b < d->n_ebatches; ++b) {
@@ -567,14 +614,25 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
     if (!edge_kind_ok(e, eb, d->vdepth, why)) return fail(e, ND_B200_EUNSUPPORTED, "%s (no CPU fallback)", why.c_str());
     if (eb.outdim_dst != d->edepth) return fail(e, ND_B200_EINVAL, "edge batch %d: outdim.dst %d != edepth %d", b + 1, eb.outdim_dst, d->edepth);
     e->c_pe = std::max(e->c_pe, eb.pdim);
-    if (eb.dim != 0) return fail(e, ND_B200_EUNSUPPORTED, "edge batch %d has dynamic states (ODE edges are not supported by the B200 engine)", b + 1);
+    if (eb.dim < 0 || eb.dim > (e->custom ? 16 : 2)) return fail(e, ND_B200_EUNSUPPORTED, "edge batch %d: dim %d", b + 1, eb.dim);
+    if (eb.dim > 0) {
+      // edges with states: outputs are StateMasks over a contiguous range of the edge's own states
+      if (d->row_end > 0 && (d->row_begin != 0 || d->row_end != e->nrows_total)) return fail(e, ND_B200_EUNSUPPORTED, "edges with states on a row-partitioned engine");
+      if (d->gather_offset) return fail(e, ND_B200_EUNSUPPORTED, "edges with states on a halo engine");
+      if (eb.state_first != state_expect) return fail(e, ND_B200_EINVAL, "edge batch %d: statestride.first %lld, expected %lld", b + 1, (long long)eb.state_first, state_expect);
+      if (eb.mask_dst_first < 1 || eb.mask_dst_first + eb.outdim_dst - 1 > eb.dim) return fail(e, ND_B200_EINVAL, "edge batch %d: dst StateMask outside 1..dim", b + 1);
+      if (eb.coupling == ND_B200_FIDUCIAL && (eb.mask_src_first < 1 || eb.mask_src_first + eb.outdim_src - 1 > eb.dim)) return fail(e, ND_B200_EINVAL, "edge batch %d: src StateMask outside 1..dim", b + 1);
+      state_expect += eb.count * eb.dim;
+      any_ode = true;
+    }
     if (eb.coupling != ND_B200_ANTISYMMETRIC && eb.coupling != ND_B200_SYMMETRIC && eb.coupling != ND_B200_DIRECTED && eb.coupling != ND_B200_FIDUCIAL)
       return fail(e, ND_B200_EUNSUPPORTED, "edge batch %d: unsupported output wrapper %d", b + 1, eb.coupling);
     const int osrc_expect = eb.coupling == ND_B200_DIRECTED ? 0 : eb.outdim_dst;
     if (eb.outdim_src != osrc_expect) return fail(e, ND_B200_EINVAL, "edge batch %d: outdim.src %d inconsistent with wrapper", b + 1, eb.outdim_src);
     if (eb.out_first != eout_expect) return fail(e, ND_B200_EINVAL, "edge batch %d: outbufstride.first %lld, expected %lld", b + 1, (long long)eb.out_first, eout_expect);
     if (eb.count <= 0 || (!eb.indices && d->n_ebatches != 1)) return fail(e, ND_B200_EINVAL, "edge batch %d is empty", b + 1);
-    HostEB h{eb.kind, eb.coupling, eb.dim, eb.pdim, eb.outdim_src, eb.outdim_dst, eb.count, eb.p_first - 1, eb.out_first - 1};
+    HostEB h{eb.kind, eb.coupling, eb.dim, eb.pdim, eb.outdim_src, eb.outdim_dst, eb.count, eb.p_first - 1, eb.out_first - 1,
+             eb.state_first - 1, eb.dim > 0 ? eb.mask_src_first - 1 : 0, eb.dim > 0 ? eb.mask_dst_first - 1 : 0};
     e->heb.push_back(h);
     eout_expect += eb.count * (eb.outdim_src + eb.outdim_dst);
     if (eb.pdim > 0) any_epar = true;
@@ -585,8 +643,11 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
     }
   }
   if (eout_expect - 1 != d->lastidx_out) return fail(e, ND_B200_EINVAL, "lastidx_out %lld inconsistent with batches (%lld)", (long long)d->lastidx_out, eout_expect - 1);
-  if (state_expect - 1 != d->lastidx_dynamic) return fail(e, ND_B200_EINVAL, "lastidx_dynamic %lld inconsistent with vertex batches (%lld)", (long long)d->lastidx_dynamic, state_expect - 1);
-  e->ek = (d->n_ebatches == 1) ? d->ebatches[0].kind : EK_GENERIC;
+  if (state_expect - 1 != d->lastidx_dynamic) return fail(e, ND_B200_EINVAL, "lastidx_dynamic %lld inconsistent with the batches (%lld)", (long long)d->lastidx_dynamic, state_expect - 1);
+  e->ek = (d->n_ebatches == 1 && !any_ode) ? d->ebatches[0].kind : EK_GENERIC;   // entries of edges with states: generic kernels only
+  if (any_ode && (d->lastidx_dynamic >= ND_STATE_ENTRY_BIT || d->nv * (long long)d->vdepth >= ND_STATE_ENTRY_BIT))
+    return fail(e, ND_B200_EUNSUPPORTED, "networks with edge states need offsets below 2^30");
+  if (any_ode && !e->custom && d->vdepth != 1) return fail(e, ND_B200_EUNSUPPORTED, "edges with states and vdepth %d need user-supplied kinds", d->vdepth);
   if (!e->custom && d->vdepth == 2 && d->n_ebatches > 1) {
     // all (2,2) batches must be LINE_DQ with one coupling (single templated kernel)
     for (int b = 1; b < d->n_ebatches; ++b)
@@ -615,6 +676,9 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
   const bool keep = !(d->flags & ND_B200_FLAG_NO_EXPORT);
   std::vector<int> h_nbr((size_t)std::max<long long>(e->nentries, 1)), h_epar;
   std::vector<uint8_t> h_ebid;
+  // the precompiled generic kernels are instantiated with PE = 1 and read the parameter-offset stream even when no edge
+  // batch of this network has parameters
+  if (e->ek == EK_GENERIC && d->vdepth == 1 && !e->custom) any_epar = true;
   if (any_epar) h_epar.assign((size_t)std::max<long long>(e->nentries, 1), 0);
   if (e->ek == EK_GENERIC && (d->vdepth == 1 || e->custom)) h_ebid.assign((size_t)std::max<long long>(e->nentries, 1), 0);
   if (keep) { e->h_nbr_vid.resize((size_t)e->nentries); e->h_eid.resize((size_t)e->nentries); e->h_side.resize((size_t)e->nentries); }
@@ -624,7 +688,7 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
   e->oedge_len = d->lastidx_out - e->oedge_base;
   e->ne_all = d->ne;
   bool want_split = false;
-  if (const char* s = getenv("ND_B200_KERNEL")) want_split = !strcmp(s, "split") && nrows_owned == e->nrows_total && !(d->vdepth == 2 && d->n_ebatches > 1) && !e->custom;
+  if (const char* s = getenv("ND_B200_KERNEL")) want_split = !strcmp(s, "split") && nrows_owned == e->nrows_total && !(d->vdepth == 2 && d->n_ebatches > 1) && !e->custom && !any_ode;
   if (want_split && e->oedge_len >= INT_MAX) return fail(e, ND_B200_EUNSUPPORTED, "edge output buffer exceeds 2^31 scalars on one device");
   std::vector<int> h_oidx(want_split ? (size_t)std::max<long long>(e->nentries, 1) : 1), h_es(want_split ? (size_t)std::max<long long>(d->ne, 1) : 1), h_et(want_split ? (size_t)std::max<long long>(d->ne, 1) : 1);
   std::vector<int> h_eepar, h_eooff;
@@ -645,10 +709,14 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
         if (generic_edges && want_split) { h_eepar[(size_t)kedge] = ep; h_eooff[(size_t)kedge] = (int)oo; h_eebid[(size_t)kedge] = (uint8_t)b; }
         ++kedge;
         // src output precedes dst output in `o` (register_edges!, src/network_structure.jl:244-245)
+        // edges with states contribute a StateMask read of their own states: the offset of the output state inside u,
+        // flagged with ND_STATE_ENTRY_BIT (state_entry_value in the kernels)
+        const int so_src = eb.dim > 0 ? (int)((eb.state_first - 1) + i * eb.dim + (eb.coupling == ND_B200_FIDUCIAL ? eb.mask_src_first - 1 : eb.mask_dst_first - 1)) | ND_STATE_ENTRY_BIT : 0;
+        const int so_dst = eb.dim > 0 ? (int)((eb.state_first - 1) + i * eb.dim + (eb.mask_dst_first - 1)) | ND_STATE_ENTRY_BIT : 0;
         if (eb.outdim_src > 0 && owned(rs)) {
           const long long j = cur[(size_t)(rs - e->row_begin)]++;
           if (want_split) h_oidx[(size_t)j] = (int)oo;
-          h_nbr[(size_t)j] = ~goff[(size_t)t - 1];
+          h_nbr[(size_t)j] = eb.dim > 0 ? ~so_src : ~goff[(size_t)t - 1];
           if (any_epar) h_epar[(size_t)j] = ep;
           if (!h_ebid.empty()) h_ebid[(size_t)j] = (uint8_t)b;
           if (keep) { e->h_nbr_vid[(size_t)j] = (int)t; e->h_eid[(size_t)j] = (int)(eid + 1); e->h_side[(size_t)j] = 1; }
@@ -656,7 +724,7 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
         if (owned(rt)) {
           const long long j = cur[(size_t)(rt - e->row_begin)]++;
           if (want_split) h_oidx[(size_t)j] = (int)(oo + eb.outdim_src);
-          h_nbr[(size_t)j] = goff[(size_t)s - 1];
+          h_nbr[(size_t)j] = eb.dim > 0 ? so_dst : goff[(size_t)s - 1];
           if (any_epar) h_epar[(size_t)j] = ep;
           if (!h_ebid.empty()) h_ebid[(size_t)j] = (uint8_t)b;
           if (keep) { e->h_nbr_vid[(size_t)j] = (int)s; e->h_eid[(size_t)j] = (int)(eid + 1); e->h_side[(size_t)j] = 0; }
@@ -782,7 +850,7 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
     }
   }
   std::vector<EBDev> deb;
-  for (const HostEB& h : e->heb) deb.push_back(EBDev{h.kind, h.coupling, h.pdim});
+  for (const HostEB& h : e->heb) deb.push_back(EBDev{h.kind, h.coupling, h.pdim, h.dim});
 
   // ---- jagged layout: 32-lane slices, column-major compacted entries (rhs_jag_kernel) ------------------------
   // ND_B200_KERNEL=jag|fused|split overrides the automatic choice.  A strictly sequential long_row_threshold beyond
@@ -932,6 +1000,19 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
   }
   if (e->host_only) return ND_B200_OK;
   CUDA_TRY(e, cudaSetDevice(e->device));
+  for (int b = 0; b < d->n_ebatches; ++b) {
+    const nd_b200_ebatch& eb = d->ebatches[b];
+    if (eb.dim == 0) continue;
+    std::vector<int> es((size_t)eb.count), et((size_t)eb.count);
+    for (long long i = 0; i < eb.count; ++i) {
+      const long long eid = eb.indices ? eb.indices[i] - 1 : i;
+      es[(size_t)i] = goff[(size_t)d->edge_src[eid] - 1];
+      et[(size_t)i] = goff[(size_t)d->edge_dst[eid] - 1];
+    }
+    nd_b200_engine::OdeBatch ob{b, nullptr, nullptr};
+    if (upload(e, &ob.d_es, es) || upload(e, &ob.d_et, et)) return ND_B200_ECUDA;
+    e->ode.push_back(ob);
+  }
   if (e->jag) {
     if (upload(e, &e->d_vb, dvb) || upload(e, &e->d_eb, deb) || upload(e, &e->d_jslices, jslices) || upload(e, &e->d_jlanes, jlanes) ||
         upload(e, &e->d_jlong, jlong))
@@ -996,6 +1077,7 @@ int rhs_impl(nd_b200_engine* e, double* du, const double* u, const double* p, do
   if (e->timing) CUDA_TRY(e, cudaEventRecord(e->ev[e->ev_used], st));
   CUDA_TRY(e, launch_fused(e, P, st));
   if (e->timing) { CUDA_TRY(e, cudaEventRecord(e->ev[e->ev_used + 1], st)); e->ev_used += 2; }
+  if (!e->ode.empty() && mode == MODE_DU) CUDA_TRY(e, launch_edge_f(e, P, st));
   return ND_B200_OK;
 }
 
@@ -1020,6 +1102,7 @@ int rk4_step_enqueue(nd_b200_engine* e, double* u, const double* p, double t, do
     if (e->gather_from_u) { P.gsrc = in[s]; P.vout_next = nullptr; }
     else { P.gsrc = e->d_vout[s & 1]; P.vout_next = e->d_vout[(s + 1) & 1]; }   // stage 4 leaves outputs of the new u in d_vout[0]
     CUDA_TRY(e, launch_fused(e, P, st));
+    if (!e->ode.empty()) CUDA_TRY(e, launch_edge_f(e, P, st));
   }
   return ND_B200_OK;
 }
@@ -1105,6 +1188,7 @@ void nd_b200_destroy(nd_b200_engine* e) {
   cudaFree(e->d_eebid); cudaFree(e->d_oedge);
   if (e->c_lib) cudaLibraryUnload(e->c_lib);
   cudaFree(e->d_jslices); cudaFree(e->d_jlanes); cudaFree(e->d_jnbr); cudaFree(e->d_jent); cudaFree(e->d_jebid); cudaFree(e->d_jlong);
+  for (auto& ob : e->ode) { cudaFree(ob.d_es); cudaFree(ob.d_et); }
   for (int* q : e->d_esrc_off) cudaFree(q);
   for (int* q : e->d_edst_off) cudaFree(q);
   cudaFree(e->d_tmpA); cudaFree(e->d_tmpB); cudaFree(e->d_ksum);
@@ -1160,7 +1244,7 @@ int nd_b200_rhs_host(nd_b200_engine* e, double* du_host, const double* u_host, c
   for (int k = 0; k < K; ++k) cum[(size_t)k + 1] = (k == K - 1) ? 1.0 : 1.0 - std::ldexp(1.0, -(k + 1));
   const int nblk = (int)e->blk_pmax.size();
   const double last = std::ldexp(1.0, -(K - 1));   // fraction of the smallest piece
-  const bool pipelined = K > 1 && e->gather_from_u && !e->split && (double)pb * last >= 16384.0 && (double)nblk * last >= 8.0 &&
+  const bool pipelined = K > 1 && e->gather_from_u && !e->split && e->ode.empty() && (double)pb * last >= 16384.0 && (double)nblk * last >= 8.0 &&
                          nblk == e->nblocks && (e->row_end - e->row_begin == e->nrows_total);
   if (!pipelined) {
     CUDA_TRY(e, cudaMemcpyAsync(e->d_hu, u_host, nb, cudaMemcpyHostToDevice, st));
@@ -1251,7 +1335,9 @@ int nd_b200_get_buffers(nd_b200_engine* e, double* o, double* aggbuf, const doub
       const int T = 256;
       const int nb = (int)((h.count + T - 1) / T);
       e->launches++;
-      if (e->custom) {
+      if (h.dim > 0) {   // edges with states: outputs are StateMask reads
+        ND_LAUNCH(nb, T, st, (h.coupling, h.dim, h.osrc, h.odst, h.mask_src, h.mask_dst, h.count, h.state0, h.out0, u, o), edge_mask_out_kernel);
+      } else if (e->custom) {
         int kind = h.kind, coupling = h.coupling, pdim = h.pdim, osrc = h.osrc;
         long long count = h.count, p0 = h.p0, out0 = h.out0;
         const int *es = e->d_esrc_off[b], *et = e->d_edst_off[b];
@@ -1309,7 +1395,7 @@ int nd_b200_rk4(nd_b200_engine* e, double* u, const double* p, double t0, double
     CUDA_TRY(e, cudaGraphInstantiate(&e->graph_exec, e->graph, 0));
     e->graph_u = u; e->graph_p = p; e->graph_dt = dt; e->graph_steps = per_graph;
   }
-  const long long per_step = 4;
+  const long long per_step = 4 * (1 + (long long)e->ode.size());
   int64_t done = 0;
   while (nsteps - done >= per_graph) {
     CUDA_TRY(e, cudaGraphLaunch(e->graph_exec, st));
@@ -1324,7 +1410,7 @@ int nd_b200_rk4(nd_b200_engine* e, double* u, const double* p, double t0, double
 int nd_b200_export_sizes(const nd_b200_engine* e, int64_t sizes[8]) {
   if (!e || !sizes) return ND_B200_EINVAL;
   sizes[0] = e->row_end - e->row_begin; sizes[1] = e->nentries; sizes[2] = e->nblocks; sizes[3] = e->n_long;
-  sizes[4] = e->gather_from_u; sizes[5] = (e->gather_from_u ? 0 : 1) + (e->split ? 2 : 1); sizes[6] = e->row_begin; sizes[7] = e->row_end;
+  sizes[4] = e->gather_from_u; sizes[5] = (e->gather_from_u ? 0 : 1) + (e->split ? 2 : 1) + (long long)e->ode.size(); sizes[6] = e->row_begin; sizes[7] = e->row_end;
   return ND_B200_OK;
 }
 

@@ -30,6 +30,12 @@
 #ifndef ND_CUSTOM_EDGE_FID_CASES
 #define ND_CUSTOM_EDGE_FID_CASES // case <kind>: ndb_user::edge_g_<kind>(osrc, odst, vs, vd, pe, t); break;   (Fiducial)
 #endif
+#ifndef ND_CUSTOM_EDGE_F_CASES
+#define ND_CUSTOM_EDGE_F_CASES   // case <kind>: ndb_user::edge_f_<kind>(de, ue, vs, vd, pe, t); break;   (edges with states)
+#endif
+#ifndef ND_MAX_EDIM
+#define ND_MAX_EDIM 2            // largest edge state dimension of the network (registry models: 2)
+#endif
 #ifndef ND_CUSTOM_VERTEX_F_CASES
 #define ND_CUSTOM_VERTEX_F_CASES // case <kind>: ndb_user::vertex_f_<kind>(dv, v, acc, pv, t); break;
 #endif
@@ -47,7 +53,11 @@ struct VBDev {          // one vertex ComponentBatch, 0-based offsets
 };
 struct EBDev {          // one edge ComponentBatch
   int kind, coupling, pdim;
+  int dim;              // > 0: edge with states; its outputs are StateMasks of those states (no g arithmetic)
 };
+// entries of edges with states carry this bit in their offset: the offset then addresses the edge's own output state in u
+// instead of a neighbour's output in the gather source (generic kernels only; such networks keep offsets below 2^30)
+constexpr int ND_STATE_ENTRY_BIT = 1 << 30;
 
 enum { MODE_DU = 0, MODE_AGG = 1, MODE_RK = 2 };
 constexpr int EK_GENERIC = -1;   // several edge batches: per-entry batch id lookup
@@ -77,6 +87,7 @@ struct KParams {
   int row_base;                        // first owned row
   int long_thr;                        // rows with more entries are reduced by the whole block
   int gather_from_u;                   // 1: vertex outputs are read straight from u (all StateMask, vdepth 1)
+  int state_edges;                     // 1: some edge batch has states (entries flagged with ND_STATE_ENTRY_BIT exist)
   int mode;
   const double* __restrict__ u;        // state vector the vertex models read
   const double* __restrict__ gsrc;     // gather source: u (gather_from_u) or the materialised vertex outputs
@@ -189,6 +200,9 @@ __device__ __forceinline__ void entry_value(int kind, int coupling, int side, co
 #pragma unroll
     for (int d = 0; d < ED; ++d) { osrc[d] = 0.0; odst[d] = 0.0; }
     switch (kind) {
+      case ND_B200_E_DIFFUSION_FID:   // test/ComponentLibrary.jl:22-25
+        if constexpr (VD == 1 && ED == 1) { odst[0] = pe[0] * (vs[0] - vd[0]); osrc[0] = -odst[0]; }
+        break;
       ND_CUSTOM_EDGE_FID_CASES
       default: break;
     }
@@ -200,6 +214,43 @@ __device__ __forceinline__ void entry_value(int kind, int coupling, int side, co
   if (side && coupling == ND_B200_ANTISYMMETRIC) {
 #pragma unroll
     for (int d = 0; d < ED; ++d) val[d] = -val[d];
+  }
+}
+
+// entries of edges WITH states: the contribution is a StateMask read of the edge's own states (PASS 2, src/coreloop.jl:41;
+// apply_compg(::PureStateMap), :230-233; wrappers src/component_functions.jl:117-203).  `off` addresses, inside u, the first
+// state of the output this side of the edge shows (Fiducial(src=..., dst=...): two different masks; the other wrappers
+// read the dst mask on both sides).
+template <int ED>
+__device__ __forceinline__ void state_entry_value(const double* __restrict__ u, int coupling, int side, int off, double* val) {
+#pragma unroll
+  for (int d = 0; d < ED; ++d) {
+    const double x = u[off + d];
+    val[d] = (side && coupling == ND_B200_ANTISYMMETRIC) ? -x : x;
+  }
+}
+
+// edge f (PASS 4, edges with states): f(de, e, vsrc, vdst, p, t), src/coreloop.jl:76,194-218
+template <int VD>
+__device__ __forceinline__ void edge_f(int kind, double* de, const double* ue, const double* vs, const double* vd,
+                                       const double* __restrict__ pe, double t) {
+  (void)t;
+  switch (kind) {
+    case ND_B200_E_DIFFUSION_ODE:   // test/ComponentLibrary.jl:30-34
+      if constexpr (VD == 1) {
+        const double tau = pe[0];
+        de[0] = 1.0 / tau * (sin(vs[0] - vd[0]) - ue[0]);
+        de[1] = 1.0 / tau * (sin(vd[0] - vs[0]) - ue[1]);
+      }
+      break;
+    case ND_B200_E_RELAX_ODE:       // test/diffusion_test.jl:96-100
+      if constexpr (VD == 1) {
+        de[0] = vs[0] - vd[0] - ue[0];
+        de[1] = vd[0] - vs[0] - ue[1];
+      }
+      break;
+    ND_CUSTOM_EDGE_F_CASES
+    default: break;
   }
 }
 
@@ -471,10 +522,16 @@ __global__ void __launch_bounds__(BLOCK, (fused_warps_per_sm(EK) * 32) / BLOCK) 
       int nb = P.nbr[e0 + jj];
       const int side = nb < 0;
       nb = side ? ~nb : nb;
+      bool st = false;
+      if constexpr (EK == EK_GENERIC) { st = P.state_edges && (nb & ND_STATE_ENTRY_BIT); nb &= ~ND_STATE_ENTRY_BIT; }
       double xn[VD];
-      const double* gp = gather_ptr<HALO>(P, nb);
 #pragma unroll
-      for (int k = 0; k < VD; ++k) xn[k] = gp[k];
+      for (int k = 0; k < VD; ++k) xn[k] = 0.0;
+      if (!st) {
+        const double* gp = gather_ptr<HALO>(P, nb);
+#pragma unroll
+        for (int k = 0; k < VD; ++k) xn[k] = gp[k];
+      }
       const double* pe = P.p;
       if constexpr (PE > 0) pe = P.p + P.epar[e0 + jj];
       int kind = EK, coupling = coupling0;
@@ -483,7 +540,8 @@ __global__ void __launch_bounds__(BLOCK, (fused_warps_per_sm(EK) * 32) / BLOCK) 
         kind = E.kind; coupling = E.coupling;
       }
       double val[ED];
-      entry_value<VD, ED>(kind, coupling, side, self, xn, pe, P.t, val);
+      if (st) state_entry_value<ED>(P.u, coupling, side, nb, val);
+      else entry_value<VD, ED>(kind, coupling, side, self, xn, pe, P.t, val);
 #pragma unroll
       for (int q = 0; q < ED; ++q) part[q] = part[q] + val[q];
     }
@@ -544,7 +602,9 @@ __global__ void __launch_bounds__(BLOCK, (fused_warps_per_sm(EK) * 32) / BLOCK) 
     const int off = nb[k] < 0 ? ~nb[k] : nb[k];
 #pragma unroll
     for (int q = 0; q < VD; ++q) xn[k][q] = 0.0;
-    if (jj < ne) {
+    bool st = false;   // entry of an edge with states: read in step (5) from u
+    if constexpr (EK == EK_GENERIC) st = P.state_edges && (off & ND_STATE_ENTRY_BIT);
+    if (jj < ne && !st) {
       const double* gp = gather_ptr<HALO>(P, off);
       if constexpr (VD == 2) {
         const double2 t2 = *reinterpret_cast<const double2*>(gp);
@@ -566,12 +626,17 @@ __global__ void __launch_bounds__(BLOCK, (fused_warps_per_sm(EK) * 32) / BLOCK) 
 #pragma unroll
       for (int q = 0; q < VD; ++q) self[q] = s_self[r * VD + q];
       int kind = EK, coupling = coupling0;
+      bool st = false;
+      int off = side ? ~nb[k] : nb[k];
       if constexpr (EK == EK_GENERIC) {
         const EBDev E = P.eb[P.ebid[e0 + jj]];
         kind = E.kind; coupling = E.coupling;
+        st = P.state_edges && (off & ND_STATE_ENTRY_BIT);
+        off &= ~ND_STATE_ENTRY_BIT;
       }
       double val[ED];
-      entry_value<VD, ED>(kind, coupling, side, self, xn[k], P.p + ep[k], P.t, val);
+      if (st) state_entry_value<ED>(P.u, coupling, side, off, val);
+      else entry_value<VD, ED>(kind, coupling, side, self, xn[k], P.p + ep[k], P.t, val);
 #pragma unroll
       for (int q = 0; q < ED; ++q) s_val[jj * ED + q] = val[q];
     }
@@ -644,6 +709,71 @@ __global__ void edge_out_kernel(int kind, int coupling, int pdim, int osrc, long
   for (int d = 0; d < ED; ++d) oo[osrc + d] = val[d];
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// edges with states ("ODE edges", src/coreloop.jl:41,76): their outputs are StateMasks of their own states -- the row
+// kernels read them straight from u (state_entry_value) -- and their f runs here, one thread per edge of a batch:
+//   du_e = f(u_e, v_src, v_dst, p_e, t)     with the same epilogues as the vertex phase (du / fused RK4 stage)
+// States and parameters of a batch are contiguous (coalesced), the two vertex outputs are gathered.
+// ------------------------------------------------------------------------------------------------
+struct EFParams {
+  int kind, dim, pdim;
+  long long count, state0, p0;
+  const int* __restrict__ esrc_off;    // per edge of the batch: gather offset of the src / dst vertex output
+  const int* __restrict__ edst_off;
+  const double* __restrict__ u;        // state vector (stage input)
+  const double* __restrict__ gsrc;     // gather source of vertex outputs
+  const double* __restrict__ p;
+  double* __restrict__ du;
+  int mode, stage;
+  const double* __restrict__ u0;
+  double* __restrict__ unext;
+  double* __restrict__ ksum;
+  double hs, h6, t;
+};
+
+template <int VD>
+__global__ void __launch_bounds__(256) edge_f_kernel(const __grid_constant__ EFParams Q) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Q.count) return;
+  double vs[VD], vd[VD], ue[ND_MAX_EDIM], de[ND_MAX_EDIM];
+#pragma unroll
+  for (int k = 0; k < VD; ++k) { vs[k] = Q.gsrc[(long long)Q.esrc_off[i] + k]; vd[k] = Q.gsrc[(long long)Q.edst_off[i] + k]; }
+  const long long s = Q.state0 + i * Q.dim;
+#pragma unroll
+  for (int c = 0; c < ND_MAX_EDIM; ++c) { ue[c] = c < Q.dim ? Q.u[s + c] : 0.0; de[c] = 0.0; }
+  edge_f<VD>(Q.kind, de, ue, vs, vd, Q.p + Q.p0 + i * Q.pdim, Q.t);
+#pragma unroll
+  for (int c = 0; c < ND_MAX_EDIM; ++c) {
+    if (c >= Q.dim) continue;
+    const long long idx = s + c;
+    if (Q.mode == MODE_DU) { Q.du[idx] = de[c]; continue; }
+    // MODE_RK: same stage algebra as vertex_phase
+    double un;
+    if (Q.stage == 1) {
+      Q.ksum[idx] = de[c];
+      un = ue[c] + Q.hs * de[c];
+    } else if (Q.stage < 4) {
+      Q.ksum[idx] = Q.ksum[idx] + 2.0 * de[c];
+      un = Q.u0[idx] + Q.hs * de[c];
+    } else {
+      un = Q.u0[idx] + Q.h6 * (Q.ksum[idx] + de[c]);
+    }
+    Q.unext[idx] = un;
+  }
+}
+
+// get_buffers support: outputs of a batch of edges with states in the reference's `o` layout (src range, dst range)
+__global__ void edge_mask_out_kernel(int coupling, int dim, int osrc, int odst, int mask_src, int mask_dst, long long count,
+                                     long long state0, long long out0, const double* __restrict__ u, double* __restrict__ o) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const double* ue = u + state0 + i * dim;
+  double* oo = o + out0 + i * (osrc + odst);
+  for (int d = 0; d < odst; ++d) oo[osrc + d] = ue[mask_dst + d];
+  for (int d = 0; d < osrc; ++d)
+    oo[d] = coupling == ND_B200_FIDUCIAL ? ue[mask_src + d] : (coupling == ND_B200_ANTISYMMETRIC ? -ue[mask_dst + d] : ue[mask_dst + d]);
+}
 
 // ------------------------------------------------------------------------------------------------
 // split mode ("edge once"): PASS 5 and the aggregation as two kernels around the reference's own
@@ -849,10 +979,16 @@ __device__ __forceinline__ void long_row_block(const KParams& P, const int4 d, d
     else nb = P.jnbr[e0 + jj];
     const int side = nb < 0;
     nb = side ? ~nb : nb;
+    bool st = false;
+    if constexpr (EK == EK_GENERIC) { st = P.state_edges && (nb & ND_STATE_ENTRY_BIT); nb &= ~ND_STATE_ENTRY_BIT; }
     double xn[VD];
-    const double* gp = gather_ptr<HALO>(P, nb);
 #pragma unroll
-    for (int k = 0; k < VD; ++k) xn[k] = gp[k];
+    for (int k = 0; k < VD; ++k) xn[k] = 0.0;
+    if (!st) {
+      const double* gp = gather_ptr<HALO>(P, nb);
+#pragma unroll
+      for (int k = 0; k < VD; ++k) xn[k] = gp[k];
+    }
     int kind = EK, coupling = coupling0, pd = PE;
     if constexpr (EK == EK_GENERIC) {
       const EBDev E = P.eb[P.jebid[e0 + jj]];
@@ -865,7 +1001,8 @@ __device__ __forceinline__ void long_row_block(const KParams& P, const int4 d, d
       for (int k = 0; k < PE; ++k) pl[k] = k < pd ? P.p[(long long)ep + k] : 0.0;
     }
     double val[ED];
-    entry_value<VD, ED>(kind, coupling, side, self, xn, pl, P.t, val);
+    if (st) state_entry_value<ED>(P.u, coupling, side, nb, val);
+    else entry_value<VD, ED>(kind, coupling, side, self, xn, pl, P.t, val);
 #pragma unroll
     for (int q = 0; q < ED; ++q) part[q] = part[q] + val[q];
   }
@@ -961,13 +1098,17 @@ __global__ void __launch_bounds__(BLOCK, (WPS * 32) / BLOCK) rhs_jag_kernel(cons
       for (int k = 0; k < VD; ++k) xn[q][k] = 0.0;
       pl[q][0] = 0.0;
       kind[q] = EK; coupling[q] = coupling0;
+      bool st = false;   // entry of an edge with states: read in step (4) from u
+      if constexpr (EK == EK_GENERIC) st = P.state_edges && (off & ND_STATE_ENTRY_BIT);
       if (act[q]) {
-        const double* gp = gather_ptr<HALO>(P, off);
-        if constexpr (VD == 2) {
-          const double2 t2 = *reinterpret_cast<const double2*>(gp);
-          xn[q][0] = t2.x; xn[q][1] = t2.y;
-        } else {
-          xn[q][0] = gp[0];
+        if (!st) {
+          const double* gp = gather_ptr<HALO>(P, off);
+          if constexpr (VD == 2) {
+            const double2 t2 = *reinterpret_cast<const double2*>(gp);
+            xn[q][0] = t2.x; xn[q][1] = t2.y;
+          } else {
+            xn[q][0] = gp[0];
+          }
         }
         int pd = PE;
         if constexpr (EK == EK_GENERIC) {
@@ -985,7 +1126,11 @@ __global__ void __launch_bounds__(BLOCK, (WPS * 32) / BLOCK) rhs_jag_kernel(cons
     for (int q = 0; q < U; ++q) {
       if (act[q]) {
         double val[ED];
-        entry_value<VD, ED>(kind[q], coupling[q], nb[q] < 0, self, xn[q], pl[q], P.t, val);
+        bool st = false;
+        int off = nb[q] < 0 ? ~nb[q] : nb[q];
+        if constexpr (EK == EK_GENERIC) { st = P.state_edges && (off & ND_STATE_ENTRY_BIT); off &= ~ND_STATE_ENTRY_BIT; }
+        if (st) state_entry_value<ED>(P.u, coupling[q], nb[q] < 0, off, val);
+        else entry_value<VD, ED>(kind[q], coupling[q], nb[q] < 0, self, xn[q], pl[q], P.t, val);
 #pragma unroll
         for (int d = 0; d < ED; ++d) acc[d] = acc[d] + val[d];
       }

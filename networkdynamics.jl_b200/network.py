@@ -233,9 +233,10 @@ class B200Aggregator:
                                     "(unsupported components raise instead of falling back to the CPU)")
             idx = np.ascontiguousarray(b.indices, dtype=np.int64)
             keep.append(idx)
+            masks = b.model.state_masks() or (0, 0)
             eb[k] = _cabi.EBatch(kind, b.model.coupling, b.model.dim, b.model.pdim, b.model.outdim_src,
                                  b.model.outdim_dst, idx.size, idx.ctypes.data_as(_cabi.i64p), b.state_first,
-                                 b.p_first, b.out_first, b.in_first)
+                                 b.p_first, b.out_first, b.in_first, masks[0], masks[1])
         dev = self._opts["device"]
         if dev is None:
             dev = _current_device()

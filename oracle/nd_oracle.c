@@ -289,6 +289,32 @@ static inline void edge_g_dst(int kind, double* odst, const double* vs, const do
   }
 }
 
+/* two-sided static g (no wrapper): g(osrc, odst, vsrc, vdst, p, t), src/coreloop.jl:208,220-222 */
+static inline void edge_g_two_sided(int kind, double* osrc, double* odst, const double* vs, const double* vd, const double* p) {
+  switch (kind) {
+    case NDO_E_DIFFUSION_FID:  /* test/ComponentLibrary.jl:22-25 : e_d[1] = p*(v_s[1] .- v_d[1]); e_s[1] = -e_d[1] */
+      odst[0] = p[0] * (vs[0] - vd[0]);
+      osrc[0] = -odst[0];
+      break;
+  }
+}
+
+/* edge f (PASS 4, edges with states): f(de, e, vsrc, vdst, p, t), src/coreloop.jl:194-211,213-218 */
+static inline void edge_f(int kind, double* de, const double* e, const double* vs, const double* vd, const double* p) {
+  switch (kind) {
+    case NDO_E_DIFFUSION_ODE: { /* test/ComponentLibrary.jl:30-34 : de[1] = 1/tau*(sin(v_s[1]-v_d[1]) - e[1]) ... */
+      double tau = p[0];
+      de[0] = 1.0 / tau * (sin(vs[0] - vd[0]) - e[0]);
+      de[1] = 1.0 / tau * (sin(vd[0] - vs[0]) - e[1]);
+    } break;
+    case NDO_E_RELAX_ODE:       /* test/diffusion_test.jl:96-100 : de[1] = v_s[1]-v_d[1]-e[1]; de[2] = v_d[1]-v_s[1]-e[2] */
+      de[0] = vs[0] - vd[0] - e[0];
+      de[1] = vd[0] - vs[0] - e[1];
+      break;
+  }
+}
+static inline int edge_kind_has_states(int kind) { return kind == NDO_E_DIFFUSION_ODE || kind == NDO_E_RELAX_ODE; }
+
 /* vertex f (PASS 6): f(du, u, agg, p, t), src/coreloop.jl:176-192,213-218 */
 static inline void vertex_f(int kind, double* dv, const double* v, const double* acc, const double* p) {
   switch (kind) {
@@ -330,9 +356,12 @@ static int check_supported(const ndo_network* nw) {
   }
   for (int32_t b = 0; b < nw->n_eb; ++b) {
     const ndo_espec* s = &nw->especs[nw->eb[b].spec];
-    if (s->kind < 0 || s->kind > NDO_E_LINE_DQ) FAIL("edge kind %d has no RHS in the oracle", s->kind);
-    if (s->dim != 0) FAIL("ODE edges are not restated");
-    if (s->coupling == NDO_FIDUCIAL) FAIL("Fiducial edges are not restated");
+    if (s->kind < 0 || s->kind > NDO_E_DIFFUSION_FID) FAIL("edge kind %d has no RHS in the oracle", s->kind);
+    if ((s->dim != 0) != edge_kind_has_states(s->kind)) FAIL("edge kind %d: dim %d does not fit the model", s->kind, s->dim);
+    if (s->dim != 0) {   /* outputs are StateMasks over the edge's own states */
+      if (s->mask_dst < 1 || s->mask_dst + s->outdim_dst - 1 > s->dim) FAIL("edge StateMask (dst) outside the states");
+      if (s->coupling == NDO_FIDUCIAL && (s->mask_src < 1 || s->mask_src + s->outdim_src - 1 > s->dim)) FAIL("edge StateMask (src) outside the states");
+    } else if ((s->coupling == NDO_FIDUCIAL) != (s->kind == NDO_E_DIFFUSION_FID)) FAIL("two-sided g and the Fiducial coupling go together");
   }
   return 0;
 }
@@ -345,6 +374,25 @@ static inline void vb_g(ndo_network* nw, const ndo_batch* B, const ndo_vspec* s,
   double* out = nw->o + (B->out_first - 1) + k * s->outdim;
   vertex_g(s->kind, s->outdim, out, uu, pp);
 }
+/* PASS 2: g of edges WITHOUT feed forward = edges whose outputs are StateMasks of their own states
+ * (apply_compg(::PureStateMap), src/coreloop.jl:230-233; wrappers src/component_functions.jl:117-203) */
+static inline void eb_g_state(ndo_network* nw, const ndo_batch* B, const ndo_espec* s, int64_t k, const double* u) {
+  const double* ue = u + (B->state_first - 1) + k * s->dim;
+  double* osrc = nw->o + (B->out_first - 1) + k * (s->outdim_src + s->outdim_dst);
+  double* odst = osrc + s->outdim_src;
+  for (int d = 0; d < s->outdim_dst; ++d) odst[d] = ue[s->mask_dst - 1 + d];
+  if (s->coupling == NDO_ANTISYMMETRIC) for (int d = 0; d < s->outdim_src; ++d) osrc[d] = -odst[d];
+  else if (s->coupling == NDO_SYMMETRIC) for (int d = 0; d < s->outdim_src; ++d) osrc[d] = odst[d];
+  else if (s->coupling == NDO_FIDUCIAL) for (int d = 0; d < s->outdim_src; ++d) osrc[d] = ue[s->mask_src - 1 + d];
+}
+/* PASS 4: f of edges without feed forward, src/coreloop.jl:76 */
+static inline void eb_f(ndo_network* nw, const ndo_batch* B, const ndo_espec* s, int64_t k, double* du, const double* u, const double* p) {
+  int vd = nw->vdepth;
+  const double* vsrc = nw->gbuf + (B->in_first - 1) + k * 2 * vd;
+  const double* vdst = vsrc + vd;
+  const double* pp = p ? p + (B->p_first - 1) + k * s->pdim : NULL;
+  edge_f(s->kind, du + (B->state_first - 1) + k * s->dim, u + (B->state_first - 1) + k * s->dim, vsrc, vdst, pp);
+}
 static inline void eb_g(ndo_network* nw, const ndo_batch* B, const ndo_espec* s, int64_t k, const double* p) {
   int vd = nw->vdepth;
   const double* vsrc = nw->gbuf + (B->in_first - 1) + k * 2 * vd;      /* get_src_dst, src/gbufs.jl:27-31 */
@@ -352,6 +400,7 @@ static inline void eb_g(ndo_network* nw, const ndo_batch* B, const ndo_espec* s,
   const double* pp = p ? p + (B->p_first - 1) + k * s->pdim : NULL;
   double* osrc = nw->o + (B->out_first - 1) + k * (s->outdim_src + s->outdim_dst);
   double* odst = osrc + s->outdim_src;
+  if (s->coupling == NDO_FIDUCIAL) { edge_g_two_sided(s->kind, osrc, odst, vsrc, vdst, pp); return; }
   edge_g_dst(s->kind, odst, vsrc, vdst, pp);
   if (s->coupling == NDO_ANTISYMMETRIC)      /* src/component_functions.jl:117-127 */
     for (int d = 0; d < s->outdim_src; ++d) osrc[d] = -odst[d];
@@ -380,12 +429,25 @@ int ndo_rhs_sequential(ndo_network* nw, double* du, const double* u, const doubl
     const ndo_batch* B = &nw->vb[b]; const ndo_vspec* s = &nw->vspecs[B->spec];
     for (int64_t k = 0; k < B->len; ++k) vb_g(nw, B, s, k, u, p);
   }
-  /* PASS 2 (ODE-edge g), loopback, PASS 3 (ff vertices), externals: empty for the restated models */
-  /* gather!, coreloop.jl:67 + gbufs.jl:25 */
-  for (int64_t k = 0; k < nw->lastidx_gbuf; ++k) nw->gbuf[k] = nw->o[nw->gbufmap[k] - 1];
-  /* PASS 4 empty; PASS 5: fg of ff edges, coreloop.jl:78 */
+  /* PASS 2: g of edges without ff (edges with states), coreloop.jl:41 */
   for (int32_t b = 0; b < nw->n_eb; ++b) {
     const ndo_batch* B = &nw->eb[b]; const ndo_espec* s = &nw->especs[B->spec];
+    if (s->dim == 0) continue;
+    for (int64_t k = 0; k < B->len; ++k) eb_g_state(nw, B, s, k, u);
+  }
+  /* loopback, PASS 3 (ff vertices), externals: empty for the restated models */
+  /* gather!, coreloop.jl:67 + gbufs.jl:25 */
+  for (int64_t k = 0; k < nw->lastidx_gbuf; ++k) nw->gbuf[k] = nw->o[nw->gbufmap[k] - 1];
+  /* PASS 4: f of edges without ff, coreloop.jl:76 */
+  for (int32_t b = 0; b < nw->n_eb; ++b) {
+    const ndo_batch* B = &nw->eb[b]; const ndo_espec* s = &nw->especs[B->spec];
+    if (s->dim == 0) continue;
+    for (int64_t k = 0; k < B->len; ++k) eb_f(nw, B, s, k, du, u, p);
+  }
+  /* PASS 5: fg of ff edges (static edges: g only), coreloop.jl:78 */
+  for (int32_t b = 0; b < nw->n_eb; ++b) {
+    const ndo_batch* B = &nw->eb[b]; const ndo_espec* s = &nw->especs[B->spec];
+    if (s->dim != 0) continue;
     for (int64_t k = 0; k < B->len; ++k) eb_g(nw, B, s, k, p);
   }
   /* aggregate!, aggregators.jl:140-151 : single ascending sweep */
@@ -460,11 +522,24 @@ int ndo_rhs_threaded(ndo_network* nw, double* du, const double* u, const double*
 #pragma omp parallel for schedule(static) num_threads(nthreads)
     for (int64_t k = 0; k < B->len; ++k) vb_g(nw, B, s, k, u, p);
   }
+  for (int32_t b = 0; b < nw->n_eb; ++b) {
+    const ndo_batch* B = &nw->eb[b]; const ndo_espec* s = &nw->especs[B->spec];
+    if (s->dim == 0) continue;
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+    for (int64_t k = 0; k < B->len; ++k) eb_g_state(nw, B, s, k, u);
+  }
   /* NNlib.gather! on Vectors is multithreaded over the destination */
 #pragma omp parallel for schedule(static) num_threads(nthreads)
   for (int64_t k = 0; k < nw->lastidx_gbuf; ++k) nw->gbuf[k] = nw->o[nw->gbufmap[k] - 1];
   for (int32_t b = 0; b < nw->n_eb; ++b) {
     const ndo_batch* B = &nw->eb[b]; const ndo_espec* s = &nw->especs[B->spec];
+    if (s->dim == 0) continue;
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+    for (int64_t k = 0; k < B->len; ++k) eb_f(nw, B, s, k, du, u, p);
+  }
+  for (int32_t b = 0; b < nw->n_eb; ++b) {
+    const ndo_batch* B = &nw->eb[b]; const ndo_espec* s = &nw->especs[B->spec];
+    if (s->dim != 0) continue;
 #pragma omp parallel for schedule(static) num_threads(nthreads)
     for (int64_t k = 0; k < B->len; ++k) eb_g(nw, B, s, k, p);
   }

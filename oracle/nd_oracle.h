@@ -44,6 +44,9 @@ enum {
   NDO_E_DIFFUSION_NOP = 1,      /* e = vs - vd                                */
   NDO_E_KURAMOTO = 2,           /* e = K*sin(ths - thd)                       */
   NDO_E_LINE_DQ = 3,            /* static dq line, p=(R,X,active)             */
+  NDO_E_DIFFUSION_ODE = 4,      /* ODE edge, dim 2, p=(tau,): de = 1/tau*(sin(..)-e); outputs are states  */
+  NDO_E_RELAX_ODE = 5,          /* ODE edge, dim 2, no p: de1 = vs-vd-e1, de2 = vd-vs-e2                 */
+  NDO_E_DIFFUSION_FID = 6,      /* static two-sided g: e_d = p*(vs-vd); e_s = -e_d                       */
   NDO_E_OPAQUE = 100
 };
 /* edge output wrappers, src/component_functions.jl:117-203 */
@@ -58,6 +61,9 @@ typedef struct {
   int32_t kind;
   int32_t coupling;
   int32_t dim, pdim, outdim_src, outdim_dst;
+  /* edges with states (dim > 0): the outputs are StateMasks (src/component_functions.jl:81-99) -- dst output k is state
+   * mask_dst + k, and for Fiducial(src=..., dst=...) src output k is state mask_src + k (1-based firsts; 0 = unused) */
+  int32_t mask_src, mask_dst;
 } ndo_espec;
 
 typedef struct ndo_network ndo_network;

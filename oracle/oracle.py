@@ -21,7 +21,7 @@ _LIB = os.path.join(_HERE, "libnd_oracle.so")
 # kind ids (mirror nd_oracle.h)
 V_DIFFUSION, V_KURAMOTO_FIRST, V_KURAMOTO_SECOND, V_KURAMOTO_SECOND_BENCH, V_SWING_DQ = range(5)
 V_OPAQUE = 100
-E_DIFFUSION, E_DIFFUSION_NOP, E_KURAMOTO, E_LINE_DQ = range(4)
+E_DIFFUSION, E_DIFFUSION_NOP, E_KURAMOTO, E_LINE_DQ, E_DIFFUSION_ODE, E_RELAX_ODE, E_DIFFUSION_FID = range(7)
 E_OPAQUE = 100
 ANTISYMMETRIC, SYMMETRIC, DIRECTED, FIDUCIAL = range(4)
 
@@ -32,7 +32,7 @@ class _VSpec(C.Structure):
 
 class _ESpec(C.Structure):
     _fields_ = [("kind", C.c_int32), ("coupling", C.c_int32), ("dim", C.c_int32), ("pdim", C.c_int32),
-                ("outdim_src", C.c_int32), ("outdim_dst", C.c_int32)]
+                ("outdim_src", C.c_int32), ("outdim_dst", C.c_int32), ("mask_src", C.c_int32), ("mask_dst", C.c_int32)]
 
 
 @dataclass(frozen=True)
@@ -51,6 +51,8 @@ class ESpec:
     pdim: int
     outdim_src: int
     outdim_dst: int
+    mask_src: int = 0      # edges with states: 1-based first state of the src / dst output StateMask
+    mask_dst: int = 0
 
 
 # the model zoo of test/ComponentLibrary.jl and benchmark/benchmark_models.jl (dims as declared there)
@@ -66,6 +68,12 @@ ESPECS = {
     "diffusion_edge_nop": ESpec(E_DIFFUSION_NOP, ANTISYMMETRIC, 0, 0, 1, 1),
     "kuramoto_edge": ESpec(E_KURAMOTO, ANTISYMMETRIC, 0, 1, 1, 1),
     "line_dq": ESpec(E_LINE_DQ, ANTISYMMETRIC, 0, 3, 2, 2),
+    # test/ComponentLibrary.jl:30-40: f=diffusion_dedge!, dim=2, g=Fiducial(dst=1:1, src=2:2)
+    "diffusion_odeedge": ESpec(E_DIFFUSION_ODE, FIDUCIAL, 2, 1, 1, 1, 2, 1),
+    # test/diffusion_test.jl:96-101: f=real_ode_edge!, dim=2, g=Fiducial(2,1) = Fiducial(src=2, dst=1)
+    "relax_odeedge": ESpec(E_RELAX_ODE, FIDUCIAL, 2, 0, 1, 1, 2, 1),
+    # test/ComponentLibrary.jl:22-28: two-sided static g
+    "diffusion_edge_fid": ESpec(E_DIFFUSION_FID, FIDUCIAL, 0, 1, 1, 1),
 }
 
 
@@ -133,7 +141,8 @@ class OracleNetwork:
         et = np.ascontiguousarray(etype, dtype=np.int32)
         assert vt.size == self.nv and et.size == self.ne
         vs = (_VSpec * max(1, len(self.vspecs)))(*[_VSpec(s.kind, s.dim, s.pdim, s.outdim) for s in self.vspecs])
-        es = (_ESpec * max(1, len(self.especs)))(*[_ESpec(s.kind, s.coupling, s.dim, s.pdim, s.outdim_src, s.outdim_dst)
+        es = (_ESpec * max(1, len(self.especs)))(*[_ESpec(s.kind, s.coupling, s.dim, s.pdim, s.outdim_src, s.outdim_dst,
+                                                          getattr(s, "mask_src", 0), getattr(s, "mask_dst", 0))
                                                    for s in self.especs])
         i64p = C.POINTER(C.c_int64)
         i32p = C.POINTER(C.c_int32)

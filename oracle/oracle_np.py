@@ -107,7 +107,8 @@ class IndexManager:
 class PyKind:
     """A component kind given as host callables (tests of user-supplied CUDA kinds): for vertices f(v, esum, p, t) -> dv
     and optionally g(v, p, t) -> out (None = StateMask(1:outdim)); for edges g(v_src, v_dst, p, t) -> e_dst, or with the
-    Fiducial wrapper -> (e_src, e_dst) (src/component_functions.jl:189-203)."""
+    Fiducial wrapper -> (e_src, e_dst) (src/component_functions.jl:189-203); for edges with states
+    f(e, v_src, v_dst, p, t) -> de (their outputs are StateMasks, ESpec.mask_src / mask_dst)."""
 
     def __init__(self, f=None, g=None):
         self.f, self.g = f, g
@@ -130,11 +131,26 @@ def _edge_g(kind, vs, vd, p, t=0.0):
         return [vs[0] - vd[0]]
     if kind == O.E_KURAMOTO:
         return [p[0] * math.sin(vs[0] - vd[0])]
+    if kind == O.E_DIFFUSION_FID:                          # two-sided: (e_src, e_dst)
+        ed = p[0] * (vs[0] - vd[0])
+        return [-ed], [ed]
     if kind == O.E_LINE_DQ:
         R, X, active = p
         dr, di = vs[0] - vd[0], vs[1] - vd[1]
         den = R * R + X * X
         return [active * ((R * dr + X * di) / den), active * ((R * di - X * dr) / den)]
+    raise ValueError(kind)
+
+
+def _edge_f(kind, e, vs, vd, p, t=0.0):
+    """f of edges with states: test/ComponentLibrary.jl:30-34, test/diffusion_test.jl:96-100"""
+    if isinstance(kind, PyKind):
+        return [float(x) for x in kind.f(e, vs, vd, p, t)]
+    if kind == O.E_DIFFUSION_ODE:
+        tau = p[0]
+        return [1.0 / tau * (math.sin(vs[0] - vd[0]) - e[0]), 1.0 / tau * (math.sin(vd[0] - vs[0]) - e[1])]
+    if kind == O.E_RELAX_ODE:
+        return [vs[0] - vd[0] - e[0], vd[0] - vs[0] - e[1]]
     raise ValueError(kind)
 
 
@@ -175,10 +191,33 @@ def rhs(im: IndexManager, u, p, t=0.0):
             if out is None:
                 out = sl(u, im.v_data[i])[:s.outdim]
             o[im.v_out[i].first - 1:im.v_out[i].last] = out
+    for spec, idxs in im.ebatches:  # PASS 2: g of edges without ff = StateMasks of the edge's own states
+        s = im.especs[spec]
+        if s.dim == 0:
+            continue
+        for i in idxs:
+            ue = sl(u, im.e_data[i])
+            odst = ue[s.mask_dst - 1:s.mask_dst - 1 + s.outdim_dst]
+            o[im.e_out[i][1].first - 1:im.e_out[i][1].last] = odst
+            if s.coupling == O.ANTISYMMETRIC:
+                o[im.e_out[i][0].first - 1:im.e_out[i][0].last] = [-x for x in odst]
+            elif s.coupling == O.SYMMETRIC:
+                o[im.e_out[i][0].first - 1:im.e_out[i][0].last] = list(odst)
+            elif s.coupling == O.FIDUCIAL:
+                o[im.e_out[i][0].first - 1:im.e_out[i][0].last] = ue[s.mask_src - 1:s.mask_src - 1 + s.outdim_src]
     gmap = im.gbuf_map()
     gbuf = [o[k - 1] for k in gmap]  # gather!
+    for spec, idxs in im.ebatches:  # PASS 4: f of edges without ff
+        s = im.especs[spec]
+        if s.dim == 0:
+            continue
+        for i in idxs:
+            vs, vd = sl(gbuf, im.e_gbufr[i][0]), sl(gbuf, im.e_gbufr[i][1])
+            du[im.e_data[i].first - 1:im.e_data[i].last] = _edge_f(s.kind, sl(u, im.e_data[i]), vs, vd, sl(p, im.e_para[i]), t)
     for spec, idxs in im.ebatches:  # PASS 5
         s = im.especs[spec]
+        if s.dim != 0:
+            continue
         for i in idxs:
             vs, vd = sl(gbuf, im.e_gbufr[i][0]), sl(gbuf, im.e_gbufr[i][1])
             odst = _edge_g(s.kind, vs, vd, sl(p, im.e_para[i]), t)

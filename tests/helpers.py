@@ -13,7 +13,8 @@ def vspec_of(m):
 def espec_of(m):
     kind = m.kernel_kind()
     coupling = m.coupling if m.coupling is not None else O.FIDUCIAL
-    return O.ESpec(O.E_OPAQUE if kind is None else kind, coupling, m.dim, m.pdim, m.outdim_src, m.outdim_dst)
+    masks = m.state_masks() or (0, 0)
+    return O.ESpec(O.E_OPAQUE if kind is None else kind, coupling, m.dim, m.pdim, m.outdim_src, m.outdim_dst, masks[0], masks[1])
 
 
 def model_types(models, n):

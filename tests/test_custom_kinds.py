@@ -47,7 +47,15 @@ def _models(nd):
     line2 = nd.EdgeModel(g=nd.AntiSymmetric(C("line2", "edge_g", "e_dst[0] = p[0]*(v_src[0]-v_dst[0]) - p[1]*(v_src[1]-v_dst[1]); e_dst[1] = p[1]*(v_src[0]-v_dst[0]) + p[0]*(v_src[1]-v_dst[1]);",
                                               py=lambda vs, vd, p, t: [p[0] * (vs[0] - vd[0]) - p[1] * (vs[1] - vd[1]), p[1] * (vs[0] - vd[0]) + p[0] * (vs[1] - vd[1])])),
                          outdim=2, pdim=2, name="line2")
-    return dict(fhn=fhn, relax3=relax3, wsin=wsin, cubic=cubic, fid=fid, osc=osc, line2=line2)
+    # edges WITH states (user-supplied f, StateMask outputs): an RL line between the 2-dim outputs of `osc` (states = the
+    # two current components, output AntiSymmetric(1:2)), and a 3-state edge whose two sides show different states
+    dynline = nd.EdgeModel(f=C("dynline_f", "edge_f", "de[0] = (v_src[0] - v_dst[0] - p[0]*e[0] + p[1]*e[1]) / p[1]; de[1] = (v_src[1] - v_dst[1] - p[0]*e[1] - p[1]*e[0]) / p[1];",
+                                py=lambda e, vs, vd, p, t: [(vs[0] - vd[0] - p[0] * e[0] + p[1] * e[1]) / p[1], (vs[1] - vd[1] - p[0] * e[1] - p[1] * e[0]) / p[1]]),
+                           g=nd.AntiSymmetric((1, 2)), dim=2, pdim=2, outdim=2, name="dynline")
+    lag3 = nd.EdgeModel(f=C("lag3_f", "edge_f", "de[0] = sin(t) - e[0]; de[1] = p[0]*(v_src[0] - v_dst[0]) - e[1]; de[2] = -e[1] - e[2]*e[0];",
+                             py=lambda e, vs, vd, p, t: [math.sin(t) - e[0], p[0] * (vs[0] - vd[0]) - e[1], -e[1] - e[2] * e[0]]),
+                        g=nd.Fiducial(dst=2, src=3), dim=3, pdim=1, outdim=1, name="lag3")
+    return dict(fhn=fhn, relax3=relax3, wsin=wsin, cubic=cubic, fid=fid, osc=osc, line2=line2, dynline=dynline, lag3=lag3)
 
 
 def _py_kind(m):
@@ -56,14 +64,16 @@ def _py_kind(m):
     if kk is not None:
         return kk
     is_cuda = lambda x: x.__class__.__name__ == "CudaFunction"
-    if hasattr(m, "outdim_dst"):     # edge: wrapper(CudaFunction) or an unwrapped two-sided CudaFunction
+    if hasattr(m, "outdim_dst"):     # edge: wrapper(CudaFunction) or an unwrapped two-sided CudaFunction; with states: f
+        if m.dim > 0:
+            return ONP.PyKind(f=m.f.py)
         return ONP.PyKind(g=(m.g if is_cuda(m.g) else m.g.g).py)
     return ONP.PyKind(f=m.f.py, g=(m.g.py if is_cuda(m.g) else None))
 
 
 def _twin(g, vms, vtypes, ems, etypes):
     vs = [O.VSpec(_py_kind(m), m.dim, m.pdim, m.outdim) for m in vms]
-    es = [O.ESpec(_py_kind(m), m.coupling, m.dim, m.pdim, m.outdim_src, m.outdim_dst) for m in ems]
+    es = [O.ESpec(_py_kind(m), m.coupling, m.dim, m.pdim, m.outdim_src, m.outdim_dst, *(m.state_masks() or (0, 0))) for m in ems]
     return ONP.IndexManager(g.nv, g.src, g.dst, vs, list(vtypes), es, list(etypes))
 
 
@@ -82,6 +92,12 @@ def _cases(nd):
     g4 = nd.watts_strogatz(400, 4, 0.3, seed=1, directed=True)
     dirw = nd.EdgeModel(g=nd.Directed(M["wsin"].g.g), outdim=1, pdim=2, name="dir_wsin")
     yield "directed", g4, [M["relax3"]], np.zeros(g4.nv, int), [dirw, M["fid"]], rng.integers(0, 2, g4.ne)
+    # edges with states: all edges dynamic lines on computed 2-dim vertex outputs; static + stateful + registry stateful mixed
+    g5 = nd.grid_graph(12, 10)
+    yield "osc+dynline", g5, [M["osc"]], np.zeros(g5.nv, int), [M["dynline"], M["line2"]], rng.integers(0, 2, g5.ne)
+    g6 = nd.barabasi_albert(300, 3, seed=5)
+    yield ("stateful_mix", g6, [M["fhn"], L.kuramoto_first()], rng.integers(0, 2, g6.nv),
+           [M["lag3"], M["wsin"], L.diffusion_odeedge(), L.diffusion_edge_fid()], rng.integers(0, 4, g6.ne))
 
 
 def test_custom_kinds_compile_and_report_errors(nd):
@@ -128,24 +144,30 @@ def test_custom_kinds_match_python_twin(nd, backend, monkeypatch, mode):
 
 
 def test_custom_kinds_rk4_and_host_buffers(nd, backend):
-    """fused-stage RK4 and the host-buffer call work for user-supplied kinds (autonomous models: RK4 replays one graph)"""
+    """fused-stage RK4 (vertex and edge states; user-supplied kinds may read t, so their steps are enqueued one by one
+    with the stage times) and the host-buffer call work for user-supplied kinds"""
     B = backend
     M = _models(nd)
+    L = nd.Lib
     g = nd.erdos_renyi(400, 1600, seed=4)
-    nw = nd.Network(g, M["fhn"], M["wsin"])
-    im = _twin(g, [M["fhn"]], np.zeros(g.nv, int), [M["wsin"]], np.zeros(g.ne, int))
     rng = np.random.default_rng(1)
-    u, p = rng.random(nw.dim()), 0.25 + rng.random(nw.pdim())
-    dt, x = 1e-2, u.copy()
-    for _ in range(5):
-        k1 = ONP.rhs(im, x, p)[0]
-        k2 = ONP.rhs(im, x + 0.5 * dt * k1, p)[0]
-        k3 = ONP.rhs(im, x + 0.5 * dt * k2, p)[0]
-        k4 = ONP.rhs(im, x + dt * k3, p)[0]
-        x = x + (dt / 6.0) * (((k1 + 2.0 * k2) + 2.0 * k3) + k4)
-    ud = B.dev(u)
-    nw.rk4(ud, B.dev(p), 0.0, dt, 5)
-    assert floored_rel_err(B.host(ud), x) <= 1e-11
-    hdu = np.empty_like(u)
-    nw(hdu, u, p, 0.0)
-    assert floored_rel_err(hdu, ONP.rhs(im, u, p)[0]) <= 1e-12
+    nets = [([M["fhn"]], np.zeros(g.nv, int), [M["wsin"]], np.zeros(g.ne, int)),
+            ([M["fhn"], L.kuramoto_first()], rng.integers(0, 2, g.nv), [M["lag3"], M["wsin"], L.diffusion_odeedge()], rng.integers(0, 3, g.ne))]
+    for vms, vt, ems, et in nets:
+        nw = nd.Network(g, (vms, vt), (ems, et))
+        im = _twin(g, vms, vt, ems, et)
+        u, p = rng.random(nw.dim()), 0.25 + rng.random(nw.pdim())
+        dt, x, t0 = 1e-2, u.copy(), 0.3
+        for s in range(5):
+            t = t0 + s * dt
+            k1 = ONP.rhs(im, x, p, t)[0]
+            k2 = ONP.rhs(im, x + 0.5 * dt * k1, p, t + 0.5 * dt)[0]
+            k3 = ONP.rhs(im, x + 0.5 * dt * k2, p, t + 0.5 * dt)[0]
+            k4 = ONP.rhs(im, x + dt * k3, p, t + dt)[0]
+            x = x + (dt / 6.0) * (((k1 + 2.0 * k2) + 2.0 * k3) + k4)
+        ud = B.dev(u)
+        nw.rk4(ud, B.dev(p), t0, dt, 5)
+        assert floored_rel_err(B.host(ud), x) <= 1e-11
+        hdu = np.empty_like(u)
+        nw(hdu, u, p, 0.0)
+        assert floored_rel_err(hdu, ONP.rhs(im, u, p)[0]) <= 1e-12

@@ -112,16 +112,83 @@ def test_mixed_edge_batches_directed_graph(nd, backend, kernel_mode):
 
 
 def test_reference_gpu_test_network(nd, backend, kernel_mode):
-    """test/GPU_test.jl:12-69 restated for the registry models: complete_graph(4), two vertex types, several edge types."""
+    """test/GPU_test.jl:12-69 verbatim: complete_graph(4), vertices [kuramoto_second, diffusion_vertex, ...], edges
+    [diffusion_odeedge, kuramoto_edge, kuramoto_edge, diffusion_edge_fid, diffusion_odeedge, diffusion_edge_fid] -- an
+    edge batch WITH states (StateMask outputs Fiducial(dst=1:1, src=2:2)), a static AntiSymmetric batch and a static
+    two-sided (Fiducial) batch in one network; `du`, `get_buffers` and RK4."""
+    B = backend
     L = nd.Lib
     g = nd.complete_graph(4)
     vm = [L.kuramoto_second(), L.diffusion_vertex(), L.kuramoto_second(), L.diffusion_vertex()]
-    em = [L.diffusion_edge(), L.kuramoto_edge(), L.kuramoto_edge(), L.diffusion_edge(), L.kuramoto_edge(), L.diffusion_edge()]
+    em = [L.diffusion_odeedge(), L.kuramoto_edge(), L.kuramoto_edge(), L.diffusion_edge_fid(), L.diffusion_odeedge(), L.diffusion_edge_fid()]
     nw = nd.Network(g, vm, em)
     onw = oracle_network(g, vm, em)
-    u, p = rand_inputs(nw.dim(), nw.pdim(), layout=lambda q: condition_params(nw, q))
-    du = _run_gpu(backend, nw, u, p)
+    assert nw.dim() == 10 and nw.pdim() == 12          # 2*2 + 2*1 vertex states + 2*2 edge states; 2*3 + 6 parameters
+    u, p = rand_inputs(nw.dim(), nw.pdim(), layout=lambda q: 0.5 + condition_params(nw, q))
+    du = _run_gpu(B, nw, u, p)
     assert floored_rel_err(du, onw.rhs(u, p)) <= TOL_DU
+    o, agg = B.nan(nw.im.lastidx_out), B.nan(nw.im.lastidx_aggr)
+    nw.get_buffers(o, agg, B.dev(u), B.dev(p), 0.0)
+    _, o_ref, agg_ref = onw.rhs(u, p, return_bufs=True)
+    assert floored_rel_err(B.host(o), o_ref) <= TOL_DU and floored_rel_err(B.host(agg), agg_ref) <= TOL_DU
+    ud = B.dev(u)
+    nw.rk4(ud, B.dev(p), 0.0, 1e-3, 100)
+    assert floored_rel_err(B.host(ud), onw.rk4(u, p, 0.0, 1e-3, 100)) <= TOL_TRAJ
+
+
+def test_edges_with_states(nd, backend, kernel_mode):
+    """Edges with states ("ODE edges", src/coreloop.jl:41,76): PASS 2 reads their StateMask outputs, PASS 4 evaluates
+    their f.  Known answer (test/diffusion_test.jl:96-129, the relaxation edge de = (vs - vd) - e): with every edge state
+    on its constraint the vertex part of du is -L*x and the edge part is exactly 0.  Then random states against the
+    oracle, a mixed static / stateful network on a power-law graph, and 1000 (emulator: 100) RK4 steps."""
+    B = backend
+    L = nd.Lib
+    g = nd.erdos_renyi(int(20_000 * B.scale), int(80_000 * B.scale), seed=3)
+    nw = nd.Network(g, L.diffusion_vertex(), L.relax_odeedge())
+    assert nw.dim() == g.nv + 2 * g.ne and nw.pdim() == 0
+    x = np.random.default_rng(0).standard_normal(g.nv)
+    e = np.stack([x[g.src - 1] - x[g.dst - 1], x[g.dst - 1] - x[g.src - 1]], axis=1).ravel()
+    du = _run_gpu(B, nw, np.concatenate([x, e]), None)
+    s, d = g.src - 1, g.dst - 1
+    Lx = np.zeros(g.nv)
+    np.add.at(Lx, s, x[s] - x[d])
+    np.add.at(Lx, d, x[d] - x[s])
+    assert np.allclose(du[:g.nv], -Lx, rtol=1e-12, atol=1e-12) and np.all(du[g.nv:] == 0.0)
+    onw = oracle_network(g, L.diffusion_vertex(), L.relax_odeedge())
+    u, _ = rand_inputs(nw.dim(), 0)
+    assert np.array_equal(_run_gpu(B, nw, u, None), onw.rhs(u, None))          # no transcendental: bit-identical
+    # mixed: two vertex batches, stateful + static + two-sided static edge batches, hubs
+    rng = np.random.default_rng(5)
+    n = int(20_000 * B.scale)
+    g = nd.barabasi_albert(n, 4, seed=4)
+    vm = ([L.kuramoto_first(), L.kuramoto_second(), L.diffusion_vertex()], rng.integers(0, 3, g.nv))
+    em = ([L.diffusion_odeedge(), L.kuramoto_edge(), L.relax_odeedge(), L.diffusion_edge_fid(), L.diffusion_edge_nop()], rng.integers(0, 5, g.ne))
+    nw = nd.Network(g, vm, em)
+    onw = oracle_network(g, vm, em)
+    u, p = rand_inputs(nw.dim(), nw.pdim(), layout=lambda q: 0.5 + condition_params(nw, q))
+    assert floored_rel_err(_run_gpu(B, nw, u, p), onw.rhs(u, p)) <= TOL_DU
+    assert nw.engine_sizes()["launches_per_rhs"] == 3                            # row kernel + one f kernel per stateful batch
+    hdu = np.empty_like(u)
+    nw(hdu, u, p, 0.0)                                                           # host-buffer path (unpipelined form)
+    assert floored_rel_err(hdu, onw.rhs(u, p)) <= TOL_DU
+    ud = B.dev(u)
+    nw.rk4(ud, B.dev(p), 0.0, 1e-3, B.rk4_steps)
+    assert floored_rel_err(B.host(ud), onw.rk4(u, p, 0.0, 1e-3, B.rk4_steps, threads=4)) <= TOL_TRAJ
+    # row-partitioned engines reject them (an edge's states would need an owner rank)
+    with pytest.raises(nd.ArgumentError):
+        nd.Network(g, vm, em, aggregator=nd.B200Aggregator("+", row_range=(0, n // 2)))
+
+
+def test_parameter_free_multi_batch_network(nd, backend, kernel_mode):
+    """several edge batches, none with parameters: the generic kernels still read their parameter-offset stream"""
+    L = nd.Lib
+    g = nd.watts_strogatz(int(5000 * backend.scale) + 100, 4, 0.5, seed=2, directed=True)
+    em = ([L.diffusion_edge_nop(), nd.EdgeModel(g=nd.Directed(L.diffusionedge_nop), outdim=1, pdim=0, name="dir_diff"),
+           nd.EdgeModel(g=nd.Symmetric(L.diffusionedge_nop), outdim=1, pdim=0, name="sym_diff")], np.random.default_rng(1).integers(0, 3, g.ne))
+    nw = nd.Network(g, L.diffusion_vertex(), em)
+    onw = oracle_network(g, L.diffusion_vertex(), em)
+    u, _ = rand_inputs(nw.dim(), 0)
+    assert np.array_equal(_run_gpu(backend, nw, u, None), onw.rhs(u, None))
 
 
 def test_edge_cases(nd, backend, kernel_mode):

@@ -184,3 +184,43 @@ def test_size_checks_raise(nd):
         onw.rhs(np.zeros(4), np.zeros(6))
     with pytest.raises(ValueError):
         onw.rhs(np.zeros(3), np.zeros(5))
+
+
+def test_edges_with_states_known_answers(nd):
+    """Edges with states (src/coreloop.jl:41,76).  Layout: test/GPU_test.jl:12-22's network has dim 10 = 2*2 + 2*1 vertex
+    states followed by 2*2 edge states, pdim 12.  Known answer (test/diffusion_test.jl:96-129, real_ode_edge! with
+    g=Fiducial(2,1)): with every edge state on its constraint e = (vs-vd, vd-vs) the vertex part of du is -L*x and the
+    edge part is exactly 0; off the constraint the edge part is the residual.  C oracle == Python twin bit for bit."""
+    L = nd.Lib
+    g = nd.complete_graph(4)
+    vm = [L.kuramoto_second(), L.diffusion_vertex(), L.kuramoto_second(), L.diffusion_vertex()]
+    em = [L.diffusion_odeedge(), L.kuramoto_edge(), L.kuramoto_edge(), L.diffusion_edge_fid(), L.diffusion_odeedge(), L.diffusion_edge_fid()]
+    onw = oracle_network(g, vm, em)
+    assert (onw.lastidx_dynamic, onw.lastidx_p, onw.lastidx_out) == (10, 12, 4 + 2 * 6)
+    assert [list(i) for _, i in onw.batches("edge")] == [[1, 5], [2, 3], [4, 6]]
+    assert list(onw.table("e_data")) == [7, 11, 11, 11, 9, 11]          # stateful batch first: 7:8, 9:10; empty ranges after
+    from helpers import model_types
+    ems, et = model_types(em, g.ne)
+    vms, vt = model_types(vm, g.nv)
+    im = _np_im(g, vms, vt, ems, et)
+    rng = np.random.default_rng(3)
+    u, p = rng.random(10), 0.5 + rng.random(12)
+    du, o, agg = onw.rhs(u, p, return_bufs=True)
+    du2, o2, agg2 = ONP.rhs(im, u, p)
+    assert np.array_equal(du, du2) and np.array_equal(o, o2) and np.array_equal(agg, agg2)
+    assert np.array_equal(onw.rhs(u, p, threads=3), du)
+    # edge 1 = (1,2) is stateful: its dst output is its first state, its src output the second (Fiducial(dst=1:1, src=2:2))
+    assert o[onw.table("e_out_dst")[0] - 1] == u[6] and o[onw.table("e_out_src")[0] - 1] == u[7]
+    tau = p[onw.table("e_para")[0] - 1]
+    th1, x2 = u[0], u[4]                                                  # vertex 1 = kuramoto_second (state 1), vertex 2 = diffusion
+    assert du[6] == 1.0 / tau * (np.sin(th1 - x2) - u[6]) and du[7] == 1.0 / tau * (np.sin(x2 - th1) - u[7])
+
+    g = nd.erdos_renyi(200, 800, seed=3)
+    onw = oracle_network(g, L.diffusion_vertex(), L.relax_odeedge())
+    x = rng.standard_normal(g.nv)
+    e = np.stack([x[g.src - 1] - x[g.dst - 1], x[g.dst - 1] - x[g.src - 1]], axis=1).ravel()
+    du = onw.rhs(np.concatenate([x, e]), None)
+    assert np.allclose(du[:g.nv], -g.laplacian() @ x, rtol=1e-12, atol=1e-12) and np.all(du[g.nv:] == 0.0)
+    e2 = e + 0.25
+    du = onw.rhs(np.concatenate([x, e2]), None)
+    assert np.allclose(du[g.nv:], e - e2, rtol=0, atol=1e-15)
