@@ -193,8 +193,8 @@ int nd_b200_export_tables(const nd_b200_engine*, int64_t* rowptr, int64_t* nbr_v
 /* The jagged device layout of the default kernel (rhs_jag_kernel), ND_B200_FLAG_HOST_ONLY engines only.
  * sizes[0]=slices (-1: engine uses a tile kernel) [1]=rows reduced by a whole block [2]=row split width [3]=entries
  * [4]=first slice (tile, for the tile kernel) that reads the halo [5]=outputs in the halo (-1: no halo layout).
- * slices[4*s..] = {entry base, first row, vertex batch, max parts}; lanes[32*s+l] = len | rowrel<<6 | head<<11 |
- * valid<<12; longs[4*k..] = {entry base, row, entries, vertex batch}; order[k] = CSR entry (as exported by
+ * slices[4*s..] = {entry base, first row, vertex batch, max parts}; lanes[32*s+l] = len | rowrel<<6 (7 bits) | head<<13 |
+ * valid<<14; longs[4*k..] = {entry base, row, entries, vertex batch}; order[k] = CSR entry (as exported by
  * nd_b200_export_tables) stored at jagged position k. */
 int nd_b200_export_jag_sizes(const nd_b200_engine*, int64_t sizes[6]);
 int nd_b200_export_jag(const nd_b200_engine*, int32_t* slices, uint16_t* lanes, int32_t* longs, int32_t* order);

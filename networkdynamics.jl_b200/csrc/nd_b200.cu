@@ -888,6 +888,8 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
     if (const char* s = getenv("ND_B200_JAG_SPLIT")) e->jsplit = std::min(63, std::max(1, atoi(s)));
     if (const char* s = getenv("ND_B200_JAG_U")) e->jag_u = atoi(s);
     if (const char* s = getenv("ND_B200_JAG_WPS")) e->jag_wps = atoi(s);
+    int jwindow = 32;
+    if (const char* s = getenv("ND_B200_JAG_WINDOW")) { const int w = atoi(s); if (w == 64 || w == 128) jwindow = w; }
     // rows longer than this are reduced by a whole block: explicit threshold if the caller gave one, else what a
     // slice can hold
     const long long block_thr = d->long_row_threshold > 0 ? std::min<long long>(d->long_row_threshold, 32LL * e->jsplit) : 32LL * e->jsplit;
@@ -916,11 +918,43 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
         jslices.push_back(make_int4(e0, (int)row0, (int)b, maxparts));
         for (int l = 0; l < 32; ++l) {
           uint16_t v = 0;
-          if (l < (int)lanes.size()) v = (uint16_t)(lanes[(size_t)l].len | (lanes[(size_t)l].rowrel << 6) | (lanes[(size_t)l].head << 11) | (1 << 12));
+          if (l < (int)lanes.size()) v = (uint16_t)(lanes[(size_t)l].len | (lanes[(size_t)l].rowrel << 6) | (lanes[(size_t)l].head << 13) | (1 << 14));
           jlanes.push_back(v);
         }
         lanes.clear(); row0 = -1; maxparts = 1;
       };
+      if (jwindow > 32) {
+        // degree-bucketed slices (ND_B200_JAG_WINDOW = 64 | 128): the rows of a window of consecutive rows are dealt to
+        // the lanes in order of decreasing degree, so the 32 rows that share a slice have (nearly) equal length and the
+        // lane walk wastes no iterations on short rows next to long ones; lanes address their row relative to the window
+        // start (7 bits).  The row's own u / du / vertex parameters stay within the window (<= 1 KB of each vector).
+        std::vector<long long> wrows;
+        for (long long w0 = lo; w0 < hi; w0 += jwindow) {
+          wrows.clear();
+          for (long long r = w0; r < std::min<long long>(w0 + jwindow, hi); ++r) {
+            if (nclasses == 2 && row_remote[(size_t)(r - e->row_begin)] != cls) continue;
+            const long long deg = cnt[(size_t)(r - e->row_begin) + 1] - cnt[(size_t)(r - e->row_begin)];
+            const int nparts = (int)std::max<long long>(1, (deg + e->jsplit - 1) / e->jsplit);
+            if (deg > block_thr || nparts > 32) { long_rows.push_back({r, (int)b}); continue; }
+            wrows.push_back(r);
+          }
+          std::stable_sort(wrows.begin(), wrows.end(), [&](long long x, long long y) {
+            return cnt[(size_t)(x - e->row_begin) + 1] - cnt[(size_t)(x - e->row_begin)] > cnt[(size_t)(y - e->row_begin) + 1] - cnt[(size_t)(y - e->row_begin)];
+          });
+          for (long long r : wrows) {
+            const long long a = cnt[(size_t)(r - e->row_begin)], deg = cnt[(size_t)(r - e->row_begin) + 1] - a;
+            const int nparts = (int)std::max<long long>(1, (deg + e->jsplit - 1) / e->jsplit);
+            if ((int)lanes.size() + nparts > 32) flush();
+            if (lanes.empty()) row0 = w0;
+            for (int k = 0; k < nparts; ++k) {
+              const long long len = std::min<long long>(e->jsplit, deg - (long long)k * e->jsplit);
+              lanes.push_back(Lane{(int)(r - w0), (int)std::max<long long>(len, 0), k == 0, a + (long long)k * e->jsplit});
+            }
+            maxparts = std::max(maxparts, nparts);
+          }
+          flush();
+        }
+      } else {
       for (long long r = lo; r < hi; ++r) {
         if (nclasses == 2 && row_remote[(size_t)(r - e->row_begin)] != cls) continue;
         const long long a = cnt[(size_t)(r - e->row_begin)], deg = cnt[(size_t)(r - e->row_begin) + 1] - a;
@@ -935,6 +969,7 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
         maxparts = std::max(maxparts, nparts);
       }
       flush();
+      }
     }
     }
     if (nclasses == 1) jag_wait_from = 0;
@@ -968,8 +1003,8 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
         for (long long q = S.x; q < eend; ++q) pm = std::max(pm, entry_pend(order[(size_t)q]));
         for (int l = 0; l < 32; ++l) {
           const uint16_t v = jlanes[sidx * 32 + (size_t)l];
-          if (!((v >> 12) & 1)) break;
-          const int r = S.y + ((v >> 6) & 31);
+          if (!((v >> 14) & 1)) break;
+          const int r = S.y + ((v >> 6) & 127);
           e->blk_rmin[k] = std::min(e->blk_rmin[k], r); e->blk_rmax[k] = std::max(e->blk_rmax[k], r);
           pm = std::max(pm, row_pend(r, (size_t)S.z));
         }

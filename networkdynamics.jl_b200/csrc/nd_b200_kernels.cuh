@@ -116,7 +116,7 @@ struct KParams {
   int* wait_timeout;                   // set to 1 if a flag did not arrive within the spin budget
   // jagged ("warp-sliced") layout, see rhs_jag_kernel
   const int4* __restrict__ jslices;    // per 32-lane slice {entry base, first row, vertex batch, max parts of a split row}
-  const uint16_t* __restrict__ jlanes; // per lane: len | rowrel<<6 | head<<11 | valid<<12
+  const uint16_t* __restrict__ jlanes; // per lane: len | rowrel<<6 (7 bits) | head<<13 | valid<<14
   const int* __restrict__ jnbr;        // per entry, slice-local column-major compacted order (PE == 0 kernels)
   const int2* __restrict__ jent;       // per entry {nbr, epar} (PE > 0 kernels)
   const uint8_t* __restrict__ jebid;   // per entry edge batch id (EK_GENERIC)
@@ -1046,8 +1046,8 @@ __global__ void __launch_bounds__(BLOCK, (WPS * 32) / BLOCK) rhs_jag_kernel(cons
   const int4 S = __ldg(&P.jslices[sl]);
   const unsigned desc = __ldg(&P.jlanes[(long long)sl * 32 + lane]);
   const int len = desc & 63;
-  const int row = S.y + ((desc >> 6) & 31);
-  const bool head = (desc >> 11) & 1, valid = (desc >> 12) & 1;
+  const int row = S.y + ((desc >> 6) & 127);
+  const bool head = (desc >> 13) & 1, valid = (desc >> 14) & 1;
   const VBDev B = P.vb[S.z];
   const int coupling0 = P.n_eb > 0 ? P.eb[0].coupling : 0;
   const unsigned lt = (1u << lane) - 1u;

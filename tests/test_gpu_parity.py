@@ -371,6 +371,13 @@ def test_launch_shapes_agree(nd, backend, monkeypatch):
         nw = nd.Network(g, vm, em)
         u, p = rand_inputs(nw.dim(), nw.pdim(), layout=lambda q: condition_params(nw, q))
         assert floored_rel_err(_run_gpu(backend, nw, u, p), onw.rhs(u, p)) <= TOL_DU, (unroll, wps, split)
+    # degree-bucketed slices: rows of a 64 / 128-row window dealt to the lanes by decreasing degree
+    for window, split in ((64, 32), (128, 32), (128, 7)):
+        monkeypatch.setenv("ND_B200_JAG_WINDOW", str(window))
+        monkeypatch.setenv("ND_B200_JAG_SPLIT", str(split))
+        nw = nd.Network(g, vm, em)
+        u, p = rand_inputs(nw.dim(), nw.pdim(), layout=lambda q: condition_params(nw, q))
+        assert floored_rel_err(_run_gpu(backend, nw, u, p), onw.rhs(u, p)) <= TOL_DU, (window, split)
 
 
 @pytest.mark.gpu

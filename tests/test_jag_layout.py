@@ -11,16 +11,16 @@ import pytest
 from helpers import oracle_network
 
 
-def _walk(jag, nentries):
+def _walk(jag, nentries, window=32):
     """replay the kernel's slot computation; returns {row: [csr entries in the order the kernel accumulates them]}"""
     rows, seen = {}, np.zeros(nentries, dtype=np.int64)
     order = jag["order"]
     for s, (e0, row0, _batch, maxparts) in enumerate(jag["slices"]):
         d = jag["lanes"][s].astype(np.int64)
-        ln, rowrel, head, valid = d & 63, (d >> 6) & 31, (d >> 11) & 1, (d >> 12) & 1
+        ln, rowrel, head, valid = d & 63, (d >> 6) & 127, (d >> 13) & 1, (d >> 14) & 1
         assert np.all(ln[valid == 0] == 0) and np.all(head[valid == 0] == 0)
         assert np.all(np.diff(valid) <= 0), "valid lanes are a prefix"
-        assert head[0] == 1 and rowrel[0] == 0
+        assert head[0] == 1 and (rowrel[0] == 0 or window > 32) and np.all(rowrel[valid == 1] < window)
         base, j, per_lane = int(e0), 0, [[] for _ in range(32)]
         while True:
             act = ln > j
@@ -74,8 +74,18 @@ def _cases(nd):
     yield "partition", nd.erdos_renyi(3000, 12000, seed=4), L.diffusion_vertex(), L.diffusion_edge(), {"rows": (1000, 2100)}
 
 
-def test_jagged_layout_replays_the_csr_in_order(nd, monkeypatch):
+def _lane_utilisation(jag):
+    """entries / (32 * sum over slices of the longest lane): the share of lane-iterations of the walk that do work"""
+    ln = (jag["lanes"].astype(np.int64) & 63)
+    return float(ln.sum()) / max(1.0, 32.0 * float(ln.max(axis=1).sum()))
+
+
+@pytest.mark.parametrize("window", [32, 64, 128])
+def test_jagged_layout_replays_the_csr_in_order(nd, monkeypatch, window):
+    """window > 32 (ND_B200_JAG_WINDOW): degree-bucketed slices -- the rows of a window are dealt to the lanes by
+    decreasing degree; same entries, same per-row order, fewer wasted lane iterations"""
     monkeypatch.setenv("ND_B200_KERNEL", "jag")
+    monkeypatch.setenv("ND_B200_JAG_WINDOW", str(window))
     for name, g, vm, em, opt in _cases(nd):
         for k, v in opt.items():
             if k.startswith("ND_"):
@@ -85,7 +95,10 @@ def test_jagged_layout_replays_the_csr_in_order(nd, monkeypatch):
         rowptr, _nbr, _eid, _side = nw.export_tables()
         jag = nw.export_jag()
         sz = nw.engine_sizes()
-        rows = _walk(jag, sz["nentries"])
+        rows = _walk(jag, sz["nentries"], window)
+        if name == "er":
+            util = _lane_utilisation(jag)
+            assert util > {32: 0.45, 64: 0.6, 128: 0.7}[window], (window, util)
         r0 = sz["row_begin"]
         assert sorted(rows) == list(range(r0, r0 + sz["nrows"])), name
         for r, ents in rows.items():
@@ -180,7 +193,7 @@ def test_halo_plan_and_interior_first_order(nd, monkeypatch):
             remote_row[np.unique(rows_of_entries[is_remote])] = True
             for s, (e0, row0, _b, _mp) in enumerate(jag["slices"]):
                 d = jag["lanes"][s].astype(np.int64)
-                rows = row0 + ((d >> 6) & 31)[((d >> 12) & 1) == 1]
+                rows = row0 + ((d >> 6) & 127)[((d >> 14) & 1) == 1]
                 assert np.all(remote_row[rows] == (s >= jag["wait_from"])), (s, jag["wait_from"])
             _walk(jag, nbr.size)
             assert 0 < jag["wait_from"] < len(jag["slices"]) or g.nv != 3000 or True
