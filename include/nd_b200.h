@@ -171,6 +171,16 @@ int nd_b200_rhs(nd_b200_engine*, double* du, const double* u, const double* p, d
  * then a stream synchronise.  This is the end-to-end form a CPU-resident caller would use. */
 int nd_b200_rhs_host(nd_b200_engine*, double* du_host, const double* u_host, const double* p_host, double t);
 
+/* Optional contract with the caller (no reference counterpart): copy the edge parameters into the engine's own per-entry
+ * array, in the entry order of its device layout, and evaluate every following RHS / RK4 / get_buffers call from that
+ * copy -- the kernels then read parameters coalesced with the index stream instead of through one scattered 8-byte read
+ * per entry.  The caller guarantees that the EDGE parameters in p do not change until the next nd_b200_pack_params;
+ * vertex parameters are still read from p on every call.  p == NULL returns to reading p on every call (the default, the
+ * reference's semantics: callbacks may mutate p between calls).  Available for networks with ONE registry edge batch
+ * that has parameters, default launch shape; ND_B200_EUNSUPPORTED otherwise.  nd_b200_rk4 can do this by itself for the
+ * duration of a call (p is constant there): environment ND_B200_RK4_PACK=1. */
+int nd_b200_pack_params(nd_b200_engine*, const double* p, void* stream);
+
 /* Replaces `get_buffers(nw,u,p,t)` = RET=Val(:buf_init) (src/coreloop.jl:33-36,92-94,103-109):
  * materialises the output buffer o (lastidx_out) and the aggregation buffer (lastidx_aggr). */
 int nd_b200_get_buffers(nd_b200_engine*, double* o, double* aggbuf, const double* u, const double* p,

@@ -212,5 +212,19 @@ function rk4!(nw::Network{<:B200Execution}, u::CuArray{Float64}, p, t0, dt, nste
     u
 end
 
-export B200Execution, B200Aggregator, rk4!
+"""
+    pack_params!(nw, p)          # p::CuArray{Float64}, or `nothing` to undo
+
+Optional contract (no reference counterpart; `nd_b200_pack_params`): the engine copies the edge parameters into its own
+per-entry array and reads them coalesced until the next call.  The caller promises not to change edge parameters in `p`
+in between (e.g. call it again from the `affect!` of a callback that mutates `p`).  Default: `p` is re-read on every call.
+"""
+function pack_params!(nw::Network{<:B200Execution}, p)
+    h = nw.layer.aggregator.handle
+    pp = isnothing(p) ? CuPtr{Float64}(0) : pointer(p::CuArray{Float64})
+    _check(ccall((:nd_b200_pack_params, libnd_b200), Cint, (Ptr{Cvoid}, CuPtr{Float64}, Ptr{Cvoid}), h, pp, stream().handle), h)
+    nothing
+end
+
+export B200Execution, B200Aggregator, rk4!, pack_params!
 end # module

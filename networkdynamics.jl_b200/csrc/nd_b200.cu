@@ -108,6 +108,11 @@ struct nd_b200_engine {
   struct OdeBatch { int b; int* d_es; int* d_et; };
   std::vector<OdeBatch> ode;
   int c_maxedim = 1;                   // ND_MAX_EDIM of the generated kernels
+  // packed edge parameters (nd_b200_pack_params): per entry, in the entry order of the layout in use
+  double* d_ppack = nullptr;
+  bool pack_on = false;
+  int pack_pe = 0;                     // edge pdim of the single edge batch (0: packing unavailable)
+  bool graph_packed = false;           // the captured RK4 graph was built with pack_on
   bool host_only = false;     // ND_B200_FLAG_HOST_ONLY: tables built, nothing uploaded (layout tests without a GPU)
   std::vector<int4> h_jslices, h_jlong;
   std::vector<uint16_t> h_jlanes;
@@ -245,6 +250,7 @@ void fill_params(const nd_b200_engine* e, KParams& P) {
   P.jslices = e->d_jslices; P.jlanes = e->d_jlanes; P.jnbr = e->d_jnbr; P.jent = e->d_jent; P.jebid = e->d_jebid;
   P.jlong = e->d_jlong; P.nslices = e->nslices; P.n_jag_blocks = e->n_jag_blocks;
   P.halo = nullptr; P.halo_base = e->halo_base; P.wait_from = e->wait_from;
+  P.ppack = e->pack_on ? e->d_ppack : nullptr;
 }
 
 // ---- split mode launches --------------------------------------------------------------------------------
@@ -286,6 +292,13 @@ template <int VD, int ED, int EK, int PE>
 cudaError_t launch_shape(const nd_b200_engine* e, const KParams& P, cudaStream_t st) {
   const int grid = (e->launch_nblk >= 0 ? e->launch_nblk : e->nblocks) + P.n_pub;
   if (grid == 0) return cudaSuccess;
+  if constexpr (PE > 0 && EK != EK_GENERIC) {
+    if (e->pack_on) {   // packed edge parameters: default launch shape only (checked by nd_b200_pack_params)
+      if (e->halo_base != INT_MAX) ND_LAUNCH(grid, 128, st, (P), rhs_fused_kernel<VD, ED, EK, PE, 128, 4, true, true>);
+      else ND_LAUNCH(grid, 128, st, (P), rhs_fused_kernel<VD, ED, EK, PE, 128, 4, false, true>);
+      return cudaGetLastError();
+    }
+  }
   if (e->halo_base != INT_MAX) {   // multi-GPU variant, default launch shape only
     if (e->block != 128 || e->ept != 4) return cudaErrorInvalidConfiguration;
     ND_LAUNCH(grid, 128, st, (P), rhs_fused_kernel<VD, ED, EK, PE, 128, 4, true>);
@@ -305,6 +318,16 @@ cudaError_t launch_jag_u(const nd_b200_engine* e, const KParams& P, cudaStream_t
   const int grid = (e->launch_nblk >= 0 ? e->launch_nblk : e->n_jag_blocks + e->n_jlong) + P.n_pub;
   if (grid == 0) return cudaSuccess;
   const int wps = e->jag_wps > 0 ? e->jag_wps : jag_warps_per_sm_default(EK);
+  if constexpr (PE > 0 && EK != EK_GENERIC && U == 2) {
+    if (e->pack_on) {   // packed edge parameters: U = 2 only (checked by nd_b200_pack_params)
+      if (e->halo_base != INT_MAX) {
+        if (wps >= 48) ND_LAUNCH(grid, BLOCK, st, (P), rhs_jag_kernel<VD, ED, EK, PE, BLOCK, U, 48, true, true>);
+        else ND_LAUNCH(grid, BLOCK, st, (P), rhs_jag_kernel<VD, ED, EK, PE, BLOCK, U, 32, true, true>);
+      } else if (wps >= 48) ND_LAUNCH(grid, BLOCK, st, (P), rhs_jag_kernel<VD, ED, EK, PE, BLOCK, U, 48, false, true>);
+      else ND_LAUNCH(grid, BLOCK, st, (P), rhs_jag_kernel<VD, ED, EK, PE, BLOCK, U, 32, false, true>);
+      return cudaGetLastError();
+    }
+  }
   if (e->halo_base != INT_MAX) {   // multi-GPU variant: one occupancy setting
     if (wps >= 48) ND_LAUNCH(grid, BLOCK, st, (P), rhs_jag_kernel<VD, ED, EK, PE, BLOCK, U, 48, true>);
     else ND_LAUNCH(grid, BLOCK, st, (P), rhs_jag_kernel<VD, ED, EK, PE, BLOCK, U, 32, true>);
@@ -648,6 +671,7 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
   if (any_ode && (d->lastidx_dynamic >= ND_STATE_ENTRY_BIT || d->nv * (long long)d->vdepth >= ND_STATE_ENTRY_BIT))
     return fail(e, ND_B200_EUNSUPPORTED, "networks with edge states need offsets below 2^30");
   if (any_ode && !e->custom && d->vdepth != 1) return fail(e, ND_B200_EUNSUPPORTED, "edges with states and vdepth %d need user-supplied kinds", d->vdepth);
+  e->pack_pe = (!e->custom && e->ek != EK_GENERIC && d->n_ebatches == 1) ? d->ebatches[0].pdim : 0;
   if (!e->custom && d->vdepth == 2 && d->n_ebatches > 1) {
     // all (2,2) batches must be LINE_DQ with one coupling (single templated kernel)
     for (int b = 1; b < d->n_ebatches; ++b)
@@ -1224,6 +1248,7 @@ void nd_b200_destroy(nd_b200_engine* e) {
   if (e->c_lib) cudaLibraryUnload(e->c_lib);
   cudaFree(e->d_jslices); cudaFree(e->d_jlanes); cudaFree(e->d_jnbr); cudaFree(e->d_jent); cudaFree(e->d_jebid); cudaFree(e->d_jlong);
   for (auto& ob : e->ode) { cudaFree(ob.d_es); cudaFree(ob.d_et); }
+  cudaFree(e->d_ppack);
   for (int* q : e->d_esrc_off) cudaFree(q);
   for (int* q : e->d_edst_off) cudaFree(q);
   cudaFree(e->d_tmpA); cudaFree(e->d_tmpB); cudaFree(e->d_ksum);
@@ -1345,6 +1370,35 @@ int nd_b200_rhs_host(nd_b200_engine* e, double* du_host, const double* u_host, c
   return ND_B200_OK;
 }
 
+int nd_b200_pack_params(nd_b200_engine* e, const double* p, void* stream) {
+  if (!e) return ND_B200_EINVAL;
+  if (e->host_only) return fail(e, ND_B200_EUNSUPPORTED, "host-only engine");
+  if (!p) { e->pack_on = false; return ND_B200_OK; }
+  if (e->pack_pe <= 0 || e->split) return fail(e, ND_B200_EUNSUPPORTED, "packed edge parameters need ONE registry edge batch with parameters and a fused kernel");
+  if (e->jag ? e->jag_u != 2 : (e->block != 128 || e->ept != 4)) return fail(e, ND_B200_EUNSUPPORTED, "packed edge parameters are compiled for the default launch shape only");
+  if (e->nentries == 0) return ND_B200_OK;
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!e->d_ppack) CUDA_TRY(e, cudaMalloc((void**)&e->d_ppack, sizeof(double) * (size_t)e->nentries * (size_t)e->pack_pe));
+  const int T = 256;
+  const int nb = (int)((e->nentries + T - 1) / T);
+  if (e->jag) {
+    if (!e->d_jnbr) {   // the PK kernels read a plain neighbour stream: extract it once from the {nbr, epar} pairs
+      CUDA_TRY(e, cudaMalloc((void**)&e->d_jnbr, sizeof(int) * (size_t)e->nentries));
+      ND_LAUNCH(nb, T, st, ((const int*)e->d_jent, e->nentries, e->d_jnbr), extract_nbr_kernel);
+      CUDA_TRY(e, cudaGetLastError());
+      e->launches++;
+    }
+    ND_LAUNCH(nb, T, st, ((const int*)e->d_jent, 2, 1, e->nentries, e->pack_pe, p, e->d_ppack), pack_params_kernel);
+  } else {
+    ND_LAUNCH(nb, T, st, (e->d_epar, 1, 0, e->nentries, e->pack_pe, p, e->d_ppack), pack_params_kernel);
+  }
+  CUDA_TRY(e, cudaGetLastError());
+  e->launches++;
+  e->pack_on = true;
+  return ND_B200_OK;
+}
+
 int nd_b200_get_buffers(nd_b200_engine* e, double* o, double* aggbuf, const double* u, const double* p, double t,
                         void* stream) {
   if (!e) return ND_B200_EINVAL;
@@ -1406,6 +1460,13 @@ int nd_b200_rk4(nd_b200_engine* e, double* u, const double* p, double t0, double
     CUDA_TRY(e, cudaMalloc((void**)&e->d_tmpB, nb));
     CUDA_TRY(e, cudaMalloc((void**)&e->d_ksum, nb));
   }
+  // p is constant for the whole call: with ND_B200_RK4_PACK=1 the edge parameters are packed once into entry order and
+  // every stage reads them coalesced (contract-free; off by default until measured on every config)
+  struct Unpack { nd_b200_engine* e; bool on; ~Unpack() { if (on) e->pack_on = false; } } unpack{e, false};
+  if (!e->pack_on && e->pack_pe > 0) {
+    const char* s = getenv("ND_B200_RK4_PACK");
+    if (s && atoi(s) > 0 && nd_b200_pack_params(e, p, stream) == ND_B200_OK) unpack.on = true;
+  }
   if (!e->gather_from_u) CUDA_TRY(e, launch_vout(e, u, p, e->d_vout[0], st));
   // The registry models are autonomous, so one captured step can be replayed for every t.  User-supplied kinds may read
   // t: their steps are enqueued one by one with the right stage times.
@@ -1416,7 +1477,7 @@ int nd_b200_rk4(nd_b200_engine* e, double* u, const double* p, double t0, double
   }
   const int UNROLL = 8;
   const int per_graph = (int)std::min<int64_t>(UNROLL, nsteps);
-  if (!e->graph_exec || e->graph_u != u || e->graph_p != p || e->graph_dt != dt || e->graph_steps != per_graph) {
+  if (!e->graph_exec || e->graph_u != u || e->graph_p != p || e->graph_dt != dt || e->graph_steps != per_graph || e->graph_packed != e->pack_on) {
     destroy_graph(e);
     if (!e->cap_stream) CUDA_TRY(e, cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
     CUDA_TRY(e, cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal));
@@ -1428,7 +1489,7 @@ int nd_b200_rk4(nd_b200_engine* e, double* u, const double* p, double t0, double
     if (rc != ND_B200_OK) return rc;
     CUDA_TRY(e, ce);
     CUDA_TRY(e, cudaGraphInstantiate(&e->graph_exec, e->graph, 0));
-    e->graph_u = u; e->graph_p = p; e->graph_dt = dt; e->graph_steps = per_graph;
+    e->graph_u = u; e->graph_p = p; e->graph_dt = dt; e->graph_steps = per_graph; e->graph_packed = e->pack_on;
   }
   const long long per_step = 4 * (1 + (long long)e->ode.size());
   int64_t done = 0;

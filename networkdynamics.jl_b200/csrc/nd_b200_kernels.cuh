@@ -79,6 +79,8 @@ struct KParams {
   const int* __restrict__ rowptr;      // [nrows_owned+1], entries of owned rows, relative to row_base
   const int* __restrict__ nbr;         // per entry: offset of the neighbour's output in gsrc; ~offset when this row is the edge's src
   const int* __restrict__ epar;        // per entry: offset of the edge's parameter block in p (nullptr when no edge has parameters)
+  const double* __restrict__ ppack;    // PK kernels: the edge parameters of entry j at ppack[j*PE ..], in the entry order of the
+                                       // layout in use (filled by pack_params_kernel; nd_b200_pack_params)
   const uint8_t* __restrict__ ebid;    // per entry: edge batch id (EK_GENERIC only)
   const int* __restrict__ blk_row;     // [nblocks+1] first (global) row of each thread block
   const VBDev* __restrict__ vb;
@@ -483,7 +485,9 @@ __host__ __device__ constexpr int fused_warps_per_sm(int ek) {
 }
 // HALO = true: the multi-GPU variant (publishing blocks, flag waits, gathers from [u | halo]); the single-GPU variant
 // carries none of it (the 32-register diffusion kernels lose 9-19 % when that code shares their register allocation).
-template <int VD, int ED, int EK, int PE, int BLOCK, int EPT, bool HALO>
+// PK = true: edge parameters come from the engine's packed per-entry copy (coalesced with the index stream; no parameter
+// offsets are read) -- valid while the caller guarantees p is unchanged since nd_b200_pack_params (nd_b200_rk4 packs per call).
+template <int VD, int ED, int EK, int PE, int BLOCK, int EPT, bool HALO, bool PK = false>
 __global__ void __launch_bounds__(BLOCK, (fused_warps_per_sm(EK) * 32) / BLOCK) rhs_fused_kernel(const __grid_constant__ KParams P) {
   constexpr int TILE = BLOCK * EPT;
   static_assert(BLOCK <= 256, "row ids are stored as uint8");
@@ -533,7 +537,7 @@ __global__ void __launch_bounds__(BLOCK, (fused_warps_per_sm(EK) * 32) / BLOCK) 
         for (int k = 0; k < VD; ++k) xn[k] = gp[k];
       }
       const double* pe = P.p;
-      if constexpr (PE > 0) pe = P.p + P.epar[e0 + jj];
+      if constexpr (PE > 0) pe = PK ? P.ppack + (long long)(e0 + jj) * PE : P.p + P.epar[e0 + jj];
       int kind = EK, coupling = coupling0;
       if constexpr (EK == EK_GENERIC) {
         const EBDev E = P.eb[P.ebid[e0 + jj]];
@@ -576,7 +580,7 @@ __global__ void __launch_bounds__(BLOCK, (fused_warps_per_sm(EK) * 32) / BLOCK) 
     nb[k] = 0; ep[k] = 0;
     if (jj < ne) {
       nb[k] = P.nbr[e0 + jj];
-      if constexpr (PE > 0) ep[k] = P.epar[e0 + jj];
+      if constexpr (PE > 0 && !PK) ep[k] = P.epar[e0 + jj];
     }
   }
   // (2) row pointers + own outputs of the block's rows
@@ -636,7 +640,7 @@ __global__ void __launch_bounds__(BLOCK, (fused_warps_per_sm(EK) * 32) / BLOCK) 
       }
       double val[ED];
       if (st) state_entry_value<ED>(P.u, coupling, side, off, val);
-      else entry_value<VD, ED>(kind, coupling, side, self, xn[k], P.p + ep[k], P.t, val);
+      else entry_value<VD, ED>(kind, coupling, side, self, xn[k], PK ? P.ppack + (long long)(e0 + jj) * PE : P.p + ep[k], P.t, val);
 #pragma unroll
       for (int q = 0; q < ED; ++q) s_val[jj * ED + q] = val[q];
     }
@@ -658,6 +662,21 @@ __global__ void __launch_bounds__(BLOCK, (fused_warps_per_sm(EK) * 32) / BLOCK) 
     load_vertex_state(P, B, r0 + tid, v);
     vertex_phase<VD, ED>(P, B, r0 + tid, acc, self, v, P.p + B.p0 + (long long)(r0 + tid - B.row0) * B.pdim);
   }
+}
+
+// ppack[j*pe + k] = p[off_j + k]: the edge parameters in the entry order of the layout in use.  `offs` is the layout's own
+// per-entry offset stream (tile layout: epar, stride 1; jagged layout: the .y of the {nbr, epar} pairs, stride 2).
+__global__ void pack_params_kernel(const int* __restrict__ offs, int stride, int first, long long n, int pe,
+                                   const double* __restrict__ p, double* __restrict__ ppack) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const long long o = offs[j * stride + first];
+  for (int k = 0; k < pe; ++k) ppack[j * pe + k] = p[o + k];
+}
+
+__global__ void extract_nbr_kernel(const int* __restrict__ pairs, long long n, int* __restrict__ nbr) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) nbr[j] = pairs[2 * j];
 }
 
 // PASS 1 for networks whose vertex outputs are not plain state copies: vout[row*VD + k] = g_v(u, p)
@@ -960,7 +979,7 @@ __host__ __device__ constexpr int jag_warps_per_sm_default(int ek) {
   return (ek == ND_B200_E_DIFFUSION || ek == ND_B200_E_DIFFUSION_NOP) ? 64 : 48;
 }
 
-template <int VD, int ED, int EK, int PE, int BLOCK, bool HALO>
+template <int VD, int ED, int EK, int PE, int BLOCK, bool HALO, bool PK>
 __device__ __forceinline__ void long_row_block(const KParams& P, const int4 d, double* s_val) {
   const int tid = threadIdx.x;
   const int e0 = d.x, r0 = d.y, ne = d.z;
@@ -975,7 +994,7 @@ __device__ __forceinline__ void long_row_block(const KParams& P, const int4 d, d
   for (int q = 0; q < ED; ++q) part[q] = 0.0;
   for (int jj = tid; jj < ne; jj += BLOCK) {
     int nb, ep = 0;
-    if constexpr (PE > 0) { const int2 t2 = P.jent[e0 + jj]; nb = t2.x; ep = t2.y; }
+    if constexpr (PE > 0 && !PK) { const int2 t2 = P.jent[e0 + jj]; nb = t2.x; ep = t2.y; }
     else nb = P.jnbr[e0 + jj];
     const int side = nb < 0;
     nb = side ? ~nb : nb;
@@ -998,7 +1017,7 @@ __device__ __forceinline__ void long_row_block(const KParams& P, const int4 d, d
     pl[0] = 0.0;
     if constexpr (PE > 0) {
 #pragma unroll
-      for (int k = 0; k < PE; ++k) pl[k] = k < pd ? P.p[(long long)ep + k] : 0.0;
+      for (int k = 0; k < PE; ++k) pl[k] = PK ? P.ppack[(long long)(e0 + jj) * PE + k] : (k < pd ? P.p[(long long)ep + k] : 0.0);
     }
     double val[ED];
     if (st) state_entry_value<ED>(P.u, coupling, side, nb, val);
@@ -1025,7 +1044,7 @@ __device__ __forceinline__ void long_row_block(const KParams& P, const int4 d, d
   }
 }
 
-template <int VD, int ED, int EK, int PE, int BLOCK, int U, int WPS, bool HALO>
+template <int VD, int ED, int EK, int PE, int BLOCK, int U, int WPS, bool HALO, bool PK = false>
 __global__ void __launch_bounds__(BLOCK, (WPS * 32) / BLOCK) rhs_jag_kernel(const __grid_constant__ KParams P) {
   __shared__ double s_val[BLOCK * ED];   // long rows only
   if constexpr (HALO) {
@@ -1034,7 +1053,7 @@ __global__ void __launch_bounds__(BLOCK, (WPS * 32) / BLOCK) rhs_jag_kernel(cons
   const int bid = (int)blockIdx.x - (HALO ? P.n_pub : 0) + P.blk_off;
   if (bid >= P.n_jag_blocks) {
     if constexpr (HALO) halo_wait(P);
-    long_row_block<VD, ED, EK, PE, BLOCK, HALO>(P, __ldg(&P.jlong[bid - P.n_jag_blocks]), s_val);
+    long_row_block<VD, ED, EK, PE, BLOCK, HALO, PK>(P, __ldg(&P.jlong[bid - P.n_jag_blocks]), s_val);
     return;
   }
   const int lane = threadIdx.x & 31;
@@ -1084,7 +1103,7 @@ __global__ void __launch_bounds__(BLOCK, (WPS * 32) / BLOCK) rhs_jag_kernel(cons
     for (int q = 0; q < U; ++q) {
       nb[q] = 0; ep[q] = 0;
       if (act[q]) {
-        if constexpr (PE > 0) { const int2 t2 = __ldcs(&P.jent[pos[q]]); nb[q] = t2.x; ep[q] = t2.y; }
+        if constexpr (PE > 0 && !PK) { const int2 t2 = __ldcs(&P.jent[pos[q]]); nb[q] = t2.x; ep[q] = t2.y; }
         else nb[q] = __ldcs(&P.jnbr[pos[q]]);
       }
     }
@@ -1117,7 +1136,7 @@ __global__ void __launch_bounds__(BLOCK, (WPS * 32) / BLOCK) rhs_jag_kernel(cons
         }
         if constexpr (PE > 0) {
 #pragma unroll
-          for (int k = 0; k < PE; ++k) pl[q][k] = k < pd ? P.p[(long long)ep[q] + k] : 0.0;
+          for (int k = 0; k < PE; ++k) pl[q][k] = PK ? __ldcs(&P.ppack[(long long)pos[q] * PE + k]) : (k < pd ? P.p[(long long)ep[q] + k] : 0.0);
         }
       }
     }

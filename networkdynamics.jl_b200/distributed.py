@@ -244,6 +244,12 @@ class PartitionedNetwork:
         self.comm = h
         dist.barrier(group=self.group)
 
+    def pack_params(self, p, *, stream=None):
+        """Per-rank packed copy of the edge parameters this rank's rows read (nd_b200_pack_params): removes the isolated
+        8-byte reads of cut-edge parameters scattered over the whole `p` vector.  Contract: edge parameters in `p` stay
+        unchanged until the next call; `pack_params(None)` goes back to re-reading `p` on every RHS.  Local (no collective)."""
+        self.nw.pack_params(p, stream=stream)
+
     def comm_timed_out(self) -> bool:
         import ctypes as C
         from . import _cabi

@@ -474,6 +474,17 @@ class Network:
         if rc:
             self._fail(rc)
 
+    def pack_params(self, p, *, stream=None):
+        """Optional contract (nd_b200_pack_params): copy the edge parameters of device vector `p` into the engine's
+        per-entry array; until the next call the kernels read edge parameters from that copy (coalesced) and the caller
+        must not change them in `p`.  `pack_params(None)` returns to re-reading `p` on every call (the default)."""
+        a_p, dev, n_p = _addr(p)
+        if p is not None and (not dev or n_p != self.im.lastidx_p):
+            raise ArgumentError(f"pack_params needs a device vector of size {self.im.lastidx_p}")
+        rc = self._L.nd_b200_pack_params(self.handle, a_p, _stream_handle(stream))
+        if rc:
+            self._fail(rc)
+
     # -- introspection -----------------------------------------------------------------------------
     def engine_sizes(self):
         s = (C.c_int64 * 8)()

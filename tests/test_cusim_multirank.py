@@ -22,7 +22,7 @@ def _ptr(a):
     return a.ctypes.data if a is not None else None
 
 
-def _run_world(nd, g, vm, em, world, ncalls, h=0.01):
+def _run_world(nd, g, vm, em, world, ncalls, h=0.01, pack=False):
     import cusim
     from networkdynamics_jl_b200 import distributed as D
     with cusim.use() as L:
@@ -57,6 +57,9 @@ def _run_world(nd, g, vm, em, world, ncalls, h=0.01):
                 u[a:b] = u0[a:b]
             us.append(u)
         errors = []
+        if pack:     # per-rank packed copy of the edge parameters (HALO + PK kernel variants)
+            for r in range(world):
+                assert L.nd_b200_pack_params(nws[r].handle, _ptr(p), None) == 0, L.nd_b200_last_error(nws[r].handle).decode()
 
         def rank_main(r):
             try:
@@ -127,3 +130,14 @@ def test_emulated_ranks_match_sequential_oracle(nd, monkeypatch, name, world, ke
     # the plan is what the survey asks for: only boundary outputs travel
     if name == "grid_kuramoto":
         assert max(max(pl["halo_lens"]) for pl in plans) <= 2 * 40
+
+
+@pytest.mark.parametrize("kernel", ["fused", "jag"])
+@pytest.mark.parametrize("name", ["er_diffusion", "grid_kuramoto"])
+def test_emulated_ranks_with_packed_edge_parameters(nd, monkeypatch, name, kernel):
+    """the same protocol with every rank evaluating from its packed per-entry copy of the edge parameters
+    (nd_b200_pack_params on a halo engine)"""
+    monkeypatch.setenv("ND_B200_KERNEL", kernel)
+    g, vm, em = _cases(nd)[name]
+    out, ref, _plans, _sizes, _k = _run_world(nd, g, vm, em, 3, ncalls=6, pack=True)
+    assert np.array_equal(out, ref)

@@ -405,3 +405,67 @@ def test_full_size_properties_cfg2(nd, gpu_backend):
         for _, val in sorted(terms, key=lambda t: t[0]):
             acc = acc + val
         assert fx[v - 1] == acc
+
+
+@pytest.mark.parametrize("mode", ["fused", "jag"])
+def test_packed_edge_parameters(nd, backend, monkeypatch, mode):
+    """nd_b200_pack_params: the engine's per-entry copy of the edge parameters (coalesced reads instead of one scattered
+    read per entry).  Packed evaluation is bit-identical to the default one; the contract is visible -- edge parameters
+    changed behind the engine's back are NOT seen until the next pack, vertex parameters always are; nd_b200_rk4 with
+    ND_B200_RK4_PACK=1 packs per call and gives the same trajectory bit for bit."""
+    B = backend
+    L = nd.Lib
+    monkeypatch.setenv("ND_B200_KERNEL", mode)
+    n = int(20_000 * B.scale)
+    half = np.array([0] * (n // 2) + [1] * (n // 2))
+    cases = [(nd.erdos_renyi(n, 4 * n, seed=3), L.diffusion_vertex(), L.diffusion_edge()),
+             (nd.barabasi_albert(n, 4, seed=3), ([L.kuramoto_first(), L.kuramoto_second()], np.random.default_rng(1).permutation(half)), L.kuramoto_edge()),
+             (nd.grid_graph(30, 40), L.swing_dq(), L.line_dq())]
+    for g, vm, em in cases:
+        nw = nd.Network(g, vm, em)
+        onw = oracle_network(g, vm, em)
+        u, p = rand_inputs(nw.dim(), nw.pdim(), layout=lambda q: condition_params(nw, q))
+        ref = _run_gpu(B, nw, u, p)
+        p_d = B.dev(p)
+        nw.pack_params(p_d)
+        du = B.nan(nw.dim())
+        nw(du, B.dev(u), p_d, 0.0)
+        assert np.array_equal(B.host(du), ref)
+        assert floored_rel_err(ref, onw.rhs(u, p)) <= TOL_DU
+        # edge parameters changed without a new pack: not seen (that is the contract); vertex parameters: seen
+        eb = nw.layer.edgebatches[0]
+        p2 = p.copy()
+        p2[eb.p_first - 1:] *= 1.5
+        nw(du, B.dev(u), B.dev(p2), 0.0)
+        assert np.array_equal(B.host(du), ref)
+        if eb.p_first > 1:
+            p3 = p.copy()
+            p3[:eb.p_first - 1] *= 1.25
+            nw(du, B.dev(u), B.dev(p3), 0.0)
+            assert floored_rel_err(B.host(du), onw.rhs(u, p3)) <= TOL_DU
+        nw.pack_params(B.dev(p2))
+        nw(du, B.dev(u), B.dev(p2), 0.0)
+        assert floored_rel_err(B.host(du), onw.rhs(u, p2)) <= TOL_DU
+        o, agg = B.nan(nw.im.lastidx_out), B.nan(nw.im.lastidx_aggr)
+        nw.get_buffers(o, agg, B.dev(u), B.dev(p2), 0.0)
+        assert floored_rel_err(B.host(agg), onw.rhs(u, p2, return_bufs=True)[2]) <= TOL_DU
+        nw.pack_params(None)                                   # back to the reference's semantics
+        nw(du, B.dev(u), p_d, 0.0)
+        assert np.array_equal(B.host(du), ref)
+        # RK4: per-call packing
+        ua, ub = B.dev(u), B.dev(u)
+        nw.rk4(ua, p_d, 0.0, 1e-3, 12)
+        monkeypatch.setenv("ND_B200_RK4_PACK", "1")
+        nw.rk4(ub, p_d, 0.0, 1e-3, 12)
+        monkeypatch.delenv("ND_B200_RK4_PACK")
+        assert np.array_equal(B.host(ua), B.host(ub))
+        nw(du, B.dev(u), B.dev(p2), 0.0)                       # ... and the engine is unpacked again afterwards
+        assert floored_rel_err(B.host(du), onw.rhs(u, p2)) <= TOL_DU
+    # several edge batches / no edge parameters: no packed kernels, the request is refused, nothing falls back silently
+    g = nd.erdos_renyi(500, 2000, seed=1)
+    em = ([L.diffusion_edge(), L.kuramoto_edge()], np.random.default_rng(2).integers(0, 2, g.ne))
+    nw = nd.Network(g, L.kuramoto_first(), em)
+    with pytest.raises(nd.ArgumentError):
+        nw.pack_params(B.dev(np.ones(nw.pdim())))
+    with pytest.raises(nd.ArgumentError):
+        nd.Network(g, L.diffusion_vertex(), L.diffusion_edge_nop()).pack_params(B.dev(np.ones(1)))

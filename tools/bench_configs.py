@@ -57,6 +57,12 @@ def main():
             p_h = condition_params(nw, np.random.default_rng(2).random(nw.pdim()))
             u, p = torch.from_numpy(u_h).cuda(), torch.from_numpy(p_h).cuda()
             du = torch.empty_like(u)
+            if os.environ.get("ND_B200_PACK_P") == "1":     # tool-level switch: evaluate from the engine's packed edge parameters
+                try:
+                    nw.pack_params(p)
+                except nd.ArgumentError as ex:
+                    print(json.dumps({"config": name, "mode": mode, "skipped": str(ex)}), flush=True)
+                    continue
             for _ in range(5 if quick else 50): nw(du, u, p, 0.0)
             torch.cuda.synchronize()
             K = 5 if quick else 100

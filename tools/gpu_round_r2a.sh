@@ -8,7 +8,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gp
 ( time timeout 1500 python -m pytest tests -m gpu -x -q ) > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 tail -8 gpurun_out/pytest_gpu.log
-MODES="default:;fused:ND_B200_KERNEL=fused;jag32:ND_B200_KERNEL=jag;jag64:ND_B200_KERNEL=jag,ND_B200_JAG_WINDOW=64;jag128:ND_B200_KERNEL=jag,ND_B200_JAG_WINDOW=128;jag128_u4:ND_B200_KERNEL=jag,ND_B200_JAG_WINDOW=128,ND_B200_JAG_U=4;jag128_w64:ND_B200_KERNEL=jag,ND_B200_JAG_WINDOW=128,ND_B200_JAG_WPS=64"
+MODES="default:;fused:ND_B200_KERNEL=fused;jag32:ND_B200_KERNEL=jag;jag64:ND_B200_KERNEL=jag,ND_B200_JAG_WINDOW=64;jag128:ND_B200_KERNEL=jag,ND_B200_JAG_WINDOW=128;jag128_u4:ND_B200_KERNEL=jag,ND_B200_JAG_WINDOW=128,ND_B200_JAG_U=4;jag128_w64:ND_B200_KERNEL=jag,ND_B200_JAG_WINDOW=128,ND_B200_JAG_WPS=64;packed:ND_B200_PACK_P=1;fused_packed:ND_B200_KERNEL=fused,ND_B200_PACK_P=1;jag128_packed:ND_B200_KERNEL=jag,ND_B200_JAG_WINDOW=128,ND_B200_PACK_P=1;rk4pack:ND_B200_RK4_PACK=1"
 timeout 1200 python tools/bench_configs.py cfg1 cfg2 cfg2nop cfg2kura cfg3 cfg4 cfg5s --check "--modes=$MODES" > gpurun_out/r02a_sweep_window.jsonl 2> gpurun_out/r02a_sweep_window.err
 python tools/fmt_bench.py < gpurun_out/r02a_sweep_window.jsonl
 timeout 600 python bench.py --steps 200 --warmup 5 > gpurun_out/r02a_bench_cfg2.json 2> gpurun_out/r02a_bench_cfg2.err
