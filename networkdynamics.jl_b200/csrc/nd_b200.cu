@@ -290,7 +290,7 @@ cudaError_t launch_row_pass_t(const nd_b200_engine* e, const KParams& P, cudaStr
 
 template <int VD, int ED, int EK, int PE>
 cudaError_t launch_shape(const nd_b200_engine* e, const KParams& P, cudaStream_t st) {
-  const int grid = (e->launch_nblk >= 0 ? e->launch_nblk : e->nblocks) + P.n_pub;
+  const int grid = (e->launch_nblk >= 0 ? e->launch_nblk : e->nblocks) + P.n_pub + P.fence;
   if (grid == 0) return cudaSuccess;
   if constexpr (PE > 0 && EK != EK_GENERIC) {
     if (e->pack_on) {   // packed edge parameters: default launch shape only (checked by nd_b200_pack_params)
@@ -315,7 +315,7 @@ cudaError_t launch_shape(const nd_b200_engine* e, const KParams& P, cudaStream_t
 template <int VD, int ED, int EK, int PE, int U>
 cudaError_t launch_jag_u(const nd_b200_engine* e, const KParams& P, cudaStream_t st) {
   constexpr int BLOCK = 128;
-  const int grid = (e->launch_nblk >= 0 ? e->launch_nblk : e->n_jag_blocks + e->n_jlong) + P.n_pub;
+  const int grid = (e->launch_nblk >= 0 ? e->launch_nblk : e->n_jag_blocks + e->n_jlong) + P.n_pub + P.fence;
   if (grid == 0) return cudaSuccess;
   const int wps = e->jag_wps > 0 ? e->jag_wps : jag_warps_per_sm_default(EK);
   if constexpr (PE > 0 && EK != EK_GENERIC && U == 2) {
@@ -354,7 +354,7 @@ cudaError_t launch_jag(nd_b200_engine* e, const KParams& P, cudaStream_t st) {
 
 cudaError_t launch_custom(nd_b200_engine* e, const KParams& P, cudaStream_t st) {
   const int nb = e->jag ? e->n_jag_blocks + e->n_jlong : e->nblocks;
-  const int grid = (e->launch_nblk >= 0 ? e->launch_nblk : nb) + P.n_pub;
+  const int grid = (e->launch_nblk >= 0 ? e->launch_nblk : nb) + P.n_pub + P.fence;
   if (grid == 0) return cudaSuccess;
   e->launches++;
   void* args[] = {const_cast<KParams*>(&P)};
@@ -668,6 +668,10 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
   if (eout_expect - 1 != d->lastidx_out) return fail(e, ND_B200_EINVAL, "lastidx_out %lld inconsistent with batches (%lld)", (long long)d->lastidx_out, eout_expect - 1);
   if (state_expect - 1 != d->lastidx_dynamic) return fail(e, ND_B200_EINVAL, "lastidx_dynamic %lld inconsistent with the batches (%lld)", (long long)d->lastidx_dynamic, state_expect - 1);
   e->ek = (d->n_ebatches == 1 && !any_ode) ? d->ebatches[0].kind : EK_GENERIC;   // entries of edges with states: generic kernels only
+  // precompiled specialisations exist for the benchmark edge kinds; every other registry kind runs in the generic kernels
+  if (!e->custom && d->vdepth == 1 && e->ek != ND_B200_E_DIFFUSION && e->ek != ND_B200_E_DIFFUSION_NOP && e->ek != ND_B200_E_KURAMOTO) e->ek = EK_GENERIC;
+  bool any_fiducial = false;
+  for (int b = 0; b < d->n_ebatches; ++b) any_fiducial = any_fiducial || d->ebatches[b].coupling == ND_B200_FIDUCIAL;
   if (any_ode && (d->lastidx_dynamic >= ND_STATE_ENTRY_BIT || d->nv * (long long)d->vdepth >= ND_STATE_ENTRY_BIT))
     return fail(e, ND_B200_EUNSUPPORTED, "networks with edge states need offsets below 2^30");
   if (any_ode && !e->custom && d->vdepth != 1) return fail(e, ND_B200_EUNSUPPORTED, "edges with states and vdepth %d need user-supplied kinds", d->vdepth);
@@ -712,7 +716,7 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
   e->oedge_len = d->lastidx_out - e->oedge_base;
   e->ne_all = d->ne;
   bool want_split = false;
-  if (const char* s = getenv("ND_B200_KERNEL")) want_split = !strcmp(s, "split") && nrows_owned == e->nrows_total && !(d->vdepth == 2 && d->n_ebatches > 1) && !e->custom && !any_ode;
+  if (const char* s = getenv("ND_B200_KERNEL")) want_split = !strcmp(s, "split") && nrows_owned == e->nrows_total && !(d->vdepth == 2 && d->n_ebatches > 1) && !e->custom && !any_ode && !any_fiducial;
   if (want_split && e->oedge_len >= INT_MAX) return fail(e, ND_B200_EUNSUPPORTED, "edge output buffer exceeds 2^31 scalars on one device");
   std::vector<int> h_oidx(want_split ? (size_t)std::max<long long>(e->nentries, 1) : 1), h_es(want_split ? (size_t)std::max<long long>(d->ne, 1) : 1), h_et(want_split ? (size_t)std::max<long long>(d->ne, 1) : 1);
   std::vector<int> h_eepar, h_eooff;
@@ -1122,7 +1126,12 @@ int rhs_impl(nd_b200_engine* e, double* du, const double* u, const double* p, do
   P.gsrc = u;
   if (w) {
     P.halo = w->halo; P.wait_flags = w->flags; P.wait_seq = w->seq; P.wait_world = w->world; P.wait_timeout = w->timeout;
-    if (w->pub) { P.H = *w->pub; P.n_pub = w->n_pub; }
+    if (w->pub) {
+      P.H = *w->pub; P.n_pub = w->n_pub;
+      // no block of this launch would wait for the peers (no row reads the halo, or no rows at all): add the fence block
+      const bool waits = e->jag ? (e->wait_from < e->nslices || e->n_jlong > 0) : (e->wait_from < e->nblocks);
+      P.fence = waits ? 0 : 1;
+    }
   }
   if (e->timing) {
     if (ensure_events(e, e->ev, e->ev_used + 2) || ensure_events(e, e->ev_pre, e->ev_pre_used + 2)) return ND_B200_ECUDA;

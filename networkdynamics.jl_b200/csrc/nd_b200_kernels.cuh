@@ -134,6 +134,11 @@ struct KParams {
   // multi-GPU: the first n_pub thread blocks of the grid pack this rank's boundary outputs into the peers' halo buffers
   // (NVLink stores) and raise the arrival flags; interior tiles follow, tiles that read the halo come last
   int n_pub;
+  // 1: this rank has no tile / slice that waits for the peers' flags.  The double buffering of the halo relies on every
+  // rank's call s+1 not COMPLETING before all peers have started theirs (a peer that races two calls ahead would overwrite
+  // the buffer parity a slower reader is still gathering from), so such a launch carries one extra, last block that only
+  // waits for the arrival flags.
+  int fence;
   HaloParams H;
 };
 
@@ -499,6 +504,7 @@ __global__ void __launch_bounds__(BLOCK, (fused_warps_per_sm(EK) * 32) / BLOCK) 
   const int tid = threadIdx.x;
   if constexpr (HALO) {
     if ((int)blockIdx.x < P.n_pub) { publish_block(P.H, blockIdx.x, P.n_pub); return; }
+    if (P.fence && blockIdx.x == gridDim.x - 1) { halo_wait(P); return; }
   }
   // one 16-byte descriptor per thread block: {row0, e0, ne (long rows), ne | nrows<<16 | batch<<25 | long<<31}
   const int bid = (int)blockIdx.x - (HALO ? P.n_pub : 0) + P.blk_off;
@@ -1049,6 +1055,7 @@ __global__ void __launch_bounds__(BLOCK, (WPS * 32) / BLOCK) rhs_jag_kernel(cons
   __shared__ double s_val[BLOCK * ED];   // long rows only
   if constexpr (HALO) {
     if ((int)blockIdx.x < P.n_pub) { publish_block(P.H, blockIdx.x, P.n_pub); return; }
+    if (P.fence && blockIdx.x == gridDim.x - 1) { halo_wait(P); return; }
   }
   const int bid = (int)blockIdx.x - (HALO ? P.n_pub : 0) + P.blk_off;
   if (bid >= P.n_jag_blocks) {

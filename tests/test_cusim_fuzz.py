@@ -1,0 +1,170 @@
+"""Seeded fuzzing of the engine on the CPU emulation of its kernels (tests/cusim): random small graphs (directed and
+undirected, isolated vertices, hubs), random mixes of vertex / edge batch types (all wrappers, the two-sided static edge,
+edges with states), random kernel family and launch / layout switches (row split width, degree-bucket window, unroll,
+block shape, long-row threshold) -- `du`, `get_buffers`, a few RK4 steps and the host-buffer call against the sequential
+oracle.  The B200 runs the same engine code on the fixed parity cases (`-m gpu`); this widens the CPU suite's coverage of
+corner cases (empty rows and batches, rows cut into lane parts, single-row tiles, hub rows reduced by a block)."""
+import numpy as np
+import pytest
+
+from helpers import condition_params, floored_rel_err, oracle_network
+
+
+def _random_graph(nd, rng):
+    n = int(rng.integers(1, 260))
+    kind = rng.integers(0, 5)
+    directed = bool(rng.integers(0, 2))
+    if n < 3 or kind == 0:                       # sparse random pairs, possibly none
+        m = int(rng.integers(0, 3 * n + 1))
+        s, d = rng.integers(1, n + 1, m), rng.integers(1, n + 1, m)
+    elif kind == 1:                              # a hub (or two) + random edges: rows far above the split width
+        hubs = rng.integers(1, n + 1, int(rng.integers(1, 3)))
+        s = np.concatenate([np.repeat(hubs, n), rng.integers(1, n + 1, n)])
+        d = np.concatenate([np.tile(np.arange(1, n + 1), hubs.size), rng.integers(1, n + 1, n)])
+    elif kind == 2:                              # dense: every row long
+        m = int(rng.integers(n, min(40 * n, n * n) + 1))
+        s, d = rng.integers(1, n + 1, m), rng.integers(1, n + 1, m)
+    elif kind == 3:                              # ring + chords
+        s = np.concatenate([np.arange(1, n + 1), rng.integers(1, n + 1, n // 2)])
+        d = np.concatenate([np.roll(np.arange(1, n + 1), -1), rng.integers(1, n + 1, n // 2)])
+    else:                                        # many isolated vertices
+        m = int(rng.integers(0, max(2, n // 4)))
+        s, d = rng.integers(1, n // 2 + 2, m), rng.integers(1, n // 2 + 2, m)
+        s, d = np.minimum(s, n), np.minimum(d, n)
+    return (nd.SimpleDiGraph if directed else nd.SimpleGraph)(n, s, d)
+
+
+def _random_models(nd, rng, g):
+    L = nd.Lib
+    vpool = [L.kuramoto_first(), L.kuramoto_second(), L.kuramoto_second_bench(), L.diffusion_vertex()]
+    epool = [L.diffusion_edge(), L.diffusion_edge_nop(), L.kuramoto_edge(), L.diffusion_edge_fid(), L.diffusion_odeedge(), L.relax_odeedge(),
+             nd.EdgeModel(g=nd.Symmetric(L.diffusionedge), outdim=1, pdim=1, name="sym_diff"),
+             nd.EdgeModel(g=nd.Symmetric(L.kuramoto_edge_f), outdim=1, pdim=1, name="sym_kura"),
+             nd.EdgeModel(g=nd.Directed(L.kuramoto_edge_f), outdim=1, pdim=1, name="dir_kura"),
+             nd.EdgeModel(g=nd.Directed(L.diffusionedge_nop), outdim=1, pdim=0, name="dir_diff")]
+    nvt, net = int(rng.integers(1, 4)), int(rng.integers(1, 5))
+    vsel = [vpool[i] for i in rng.choice(len(vpool), nvt, replace=False)]
+    esel = [epool[i] for i in rng.choice(len(epool), net, replace=False)]
+    vm = vsel[0] if nvt == 1 and rng.integers(0, 2) else (vsel, rng.integers(0, nvt, g.nv))
+    em = esel[0] if net == 1 and rng.integers(0, 2) else (esel, rng.integers(0, net, g.ne))
+    return vm, em
+
+
+def _random_switches(rng):
+    env = {"ND_B200_KERNEL": ["fused", "jag", "jag", "split"][int(rng.integers(0, 4))]}
+    if env["ND_B200_KERNEL"] == "jag":
+        env["ND_B200_JAG_SPLIT"] = str([1, 3, 7, 32, 63][int(rng.integers(0, 5))])
+        env["ND_B200_JAG_WINDOW"] = str([32, 64, 128][int(rng.integers(0, 3))])
+        env["ND_B200_JAG_U"] = str([2, 4][int(rng.integers(0, 2))])
+        env["ND_B200_JAG_WPS"] = str([32, 48, 64][int(rng.integers(0, 3))])
+    else:
+        env["ND_B200_BLOCK"] = str([128, 256][int(rng.integers(0, 2))])
+        env["ND_B200_EPT"] = str([4, 8][int(rng.integers(0, 2))])
+    thr = [0, 0, 2, 5, 40][int(rng.integers(0, 5))]
+    return env, thr
+
+
+@pytest.mark.parametrize("seed", range(48))
+def test_fuzz_registry_networks_on_the_emulator(nd, monkeypatch, seed):
+    import cusim
+    rng = np.random.default_rng(1000 + seed)
+    g = _random_graph(nd, rng)
+    vm, em = _random_models(nd, rng, g)
+    env, thr = _random_switches(rng)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    with cusim.use():
+        try:
+            nw = nd.Network(g, vm, em, aggregator=nd.B200Aggregator("+", long_row_threshold=thr))
+        except nd.ArgumentError as ex:           # the one legitimate refusal: a short row that no tile can hold
+            assert "long rows disabled" in str(ex) or "exceeds" in str(ex), (seed, str(ex))
+            return
+        onw = oracle_network(g, vm, em)
+        assert (nw.dim(), nw.pdim()) == (onw.lastidx_dynamic, onw.lastidx_p)
+        u = rng.standard_normal(nw.dim())
+        p = 0.5 + condition_params(nw, rng.random(nw.pdim()))
+        pd = cusim.dev(p) if p.size else None
+        ref, o_ref, agg_ref = onw.rhs(u, p, return_bufs=True)
+        du = cusim.empty(nw.dim())
+        nw(du, cusim.dev(u), pd, 0.0)
+        assert not np.isnan(du.numpy()).any(), (seed, env)
+        assert floored_rel_err(du.numpy(), ref) <= 1e-12, (seed, env, thr)
+        o, agg = cusim.empty(nw.im.lastidx_out), cusim.empty(nw.im.lastidx_aggr)
+        nw.get_buffers(o, agg, cusim.dev(u), pd, 0.0)
+        assert floored_rel_err(agg.numpy(), agg_ref) <= 1e-12, (seed, env, thr)
+        assert floored_rel_err(o.numpy(), o_ref) <= 1e-12 and np.array_equal(np.isnan(o.numpy()), np.isnan(o_ref)), (seed, env)
+        ud = cusim.dev(u)
+        nw.rk4(ud, pd, 0.0, 1e-3, 3)
+        assert floored_rel_err(ud.numpy(), onw.rk4(u, p, 0.0, 1e-3, 3)) <= 1e-11, (seed, env, thr)
+        hdu = np.full(nw.dim(), np.nan)
+        nw(hdu, u, p if p.size else None, 0.0)
+        assert np.array_equal(hdu, du.numpy()), (seed, env)
+        try:
+            nw.pack_params(pd)
+        except nd.ArgumentError:
+            pass
+        else:
+            du2 = cusim.empty(nw.dim())
+            nw(du2, cusim.dev(u), pd, 0.0)
+            assert np.array_equal(du2.numpy(), du.numpy()), (seed, env)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_fuzz_dq_networks_on_the_emulator(nd, monkeypatch, seed):
+    """vdepth = edepth = 2 family (computed vertex outputs, vertex_out pre-pass, ping-pong outputs in RK4)"""
+    import cusim
+    rng = np.random.default_rng(5000 + seed)
+    g = _random_graph(nd, rng)
+    if g.directed:
+        g = nd.SimpleGraph(g.nv, g.src, g.dst)
+    env, thr = _random_switches(rng)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    L = nd.Lib
+    with cusim.use():
+        try:
+            nw = nd.Network(g, L.swing_dq(), L.line_dq(), aggregator=nd.B200Aggregator("+", long_row_threshold=thr))
+        except nd.ArgumentError as ex:
+            assert "long rows disabled" in str(ex) or "exceeds" in str(ex), (seed, str(ex))
+            return
+        onw = oracle_network(g, L.swing_dq(), L.line_dq())
+        u = rng.standard_normal(nw.dim())
+        p = condition_params(nw, rng.random(nw.pdim()))
+        ref, o_ref, agg_ref = onw.rhs(u, p, return_bufs=True)
+        du = cusim.empty(nw.dim())
+        nw(du, cusim.dev(u), cusim.dev(p), 0.0)
+        assert floored_rel_err(du.numpy(), ref) <= 1e-12, (seed, env, thr)
+        o, agg = cusim.empty(nw.im.lastidx_out), cusim.empty(nw.im.lastidx_aggr)
+        nw.get_buffers(o, agg, cusim.dev(u), cusim.dev(p), 0.0)
+        assert floored_rel_err(agg.numpy(), agg_ref) <= 1e-12 and floored_rel_err(o.numpy(), o_ref) <= 1e-12, (seed, env)
+        ud = cusim.dev(u)
+        nw.rk4(ud, cusim.dev(p), 0.0, 1e-3, 3)
+        assert floored_rel_err(ud.numpy(), onw.rk4(u, p, 0.0, 1e-3, 3)) <= 1e-11, (seed, env, thr)
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_fuzz_emulated_ranks(nd, monkeypatch, seed):
+    """random graphs / model mixes / layout switches on 2..5 emulated ranks (threads): row partition, packed halo plan,
+    interior-first order, publish / wait protocol; states after a few exchanging Euler steps against the oracle"""
+    from test_cusim_multirank import _run_world
+    rng = np.random.default_rng(9000 + seed)
+    g = _random_graph(nd, rng)
+    L = nd.Lib
+    vpool = [L.kuramoto_first(), L.kuramoto_second(), L.kuramoto_second_bench(), L.diffusion_vertex()]
+    epool = [L.diffusion_edge(), L.diffusion_edge_nop(), L.kuramoto_edge(), L.diffusion_edge_fid(),
+             nd.EdgeModel(g=nd.Symmetric(L.kuramoto_edge_f), outdim=1, pdim=1, name="sym_kura"),
+             nd.EdgeModel(g=nd.Directed(L.kuramoto_edge_f), outdim=1, pdim=1, name="dir_kura")]
+    nvt, net = int(rng.integers(1, 4)), int(rng.integers(1, 4))
+    vm = ([vpool[i] for i in rng.choice(len(vpool), nvt, replace=False)], rng.integers(0, nvt, g.nv))
+    em = ([epool[i] for i in rng.choice(len(epool), net, replace=False)], rng.integers(0, net, g.ne))
+    env, _thr = _random_switches(rng)
+    if env["ND_B200_KERNEL"] == "split":
+        env = {"ND_B200_KERNEL": "fused"}           # halo engines: default tile shape only
+    elif env["ND_B200_KERNEL"] == "fused":
+        env = {"ND_B200_KERNEL": "fused"}
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    world = int(rng.integers(2, 6))
+    out, ref, _plans, _sizes, _k = _run_world(nd, g, vm, em, world, ncalls=4, h=0.01)
+    assert not np.isnan(out).any(), (seed, env, world)
+    assert floored_rel_err(out, ref) <= 1e-12, (seed, env, world)
