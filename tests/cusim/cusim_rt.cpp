@@ -17,8 +17,10 @@
 #include <unistd.h>
 
 #include <atomic>
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <deque>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -28,8 +30,16 @@ struct cusimGraph {
   struct Op { dim3 grid, block; std::function<void()> body; };
   std::vector<Op> ops;
 };
-struct cusimStream { cusimGraph* cap = nullptr; };
-struct cusimEvent { long long ns = 0; };
+// Streams are DEFERRED: work submitted to a non-null stream is queued and drained as late as legality allows -- when the
+// stream (or an event recorded behind the work) is synchronised or waited on.  A missing event dependency between two
+// streams therefore shows up as a wrong result (the consumer runs before the producer's queue was drained) instead of
+// being hidden by lucky timing.  The null stream executes immediately.
+struct cusimStream {
+  cusimGraph* cap = nullptr;
+  std::deque<std::function<void()>> q;
+  unsigned long long enq = 0, done = 0;   // operations submitted / executed
+};
+struct cusimEvent { long long ns = 0; cusimStream* st = nullptr; unsigned long long seq = 0; };
 struct cusimLibrary { void* dl = nullptr; };
 
 namespace cusim {
@@ -214,9 +224,31 @@ long long clock_ns() {
   return (long long)ts.tv_sec * 1000000000LL + ts.tv_nsec;
 }
 
+namespace {
+thread_local std::vector<cusimStream*> g_streams;   // streams created by this host thread
+
+void drain_until(cusimStream* st, unsigned long long seq) {
+  while (st && st->done < seq && !st->q.empty()) {
+    std::function<void()> op = std::move(st->q.front());
+    st->q.pop_front();
+    st->done++;
+    op();
+  }
+}
+void drain(cusimStream* st) { if (st) drain_until(st, st->enq); }
+void drain_all() {
+  for (size_t i = 0; i < g_streams.size(); ++i) drain(g_streams[i]);
+}
+void submit(cusimStream* st, std::function<void()> op) {
+  if (!st) { op(); return; }
+  st->q.push_back(std::move(op));
+  st->enq++;
+}
+}  // namespace
+
 void launch(dim3 grid, dim3 block, cudaStream_t st, std::function<void()> body) {
   if (st && st->cap) { st->cap->ops.push_back(cusimGraph::Op{grid, block, std::move(body)}); return; }
-  run_grid(grid, block, body);
+  submit(st, [grid, block, body]() { run_grid(grid, block, body); });
 }
 
 }  // namespace cusim
@@ -236,7 +268,7 @@ cudaError_t cudaGetLastError() {
   return cudaSuccess;
 }
 cudaError_t cudaSetDevice(int) { return cudaSuccess; }
-cudaError_t cudaDeviceSynchronize() { return cusim::g_failed.load() ? cudaErrorLaunchFailure : cudaSuccess; }
+cudaError_t cudaDeviceSynchronize() { cusim::drain_all(); return cusim::g_failed.load() ? cudaErrorLaunchFailure : cudaSuccess; }
 cudaError_t cudaMalloc(void** p, size_t bytes) {
   void* q = nullptr;
   if (posix_memalign(&q, 256, bytes ? bytes : 8)) return cudaErrorMemoryAllocation;
@@ -244,16 +276,34 @@ cudaError_t cudaMalloc(void** p, size_t bytes) {
   *p = q;
   return cudaSuccess;
 }
-cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+cudaError_t cudaFree(void* p) { if (p) cusim::drain_all(); free(p); return cudaSuccess; }   // cudaFree synchronises the device
 cudaError_t cudaHostAlloc(void** p, size_t bytes, unsigned) { return cudaMalloc(p, bytes); }
-cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
+cudaError_t cudaFreeHost(void* p) { if (p) cusim::drain_all(); free(p); return cudaSuccess; }
+// synchronous copies run on the legacy default stream: they do not wait for non-blocking streams
 cudaError_t cudaMemcpy(void* dst, const void* src, size_t n, cudaMemcpyKind) { memmove(dst, src, n); return cudaSuccess; }
-cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t n, cudaMemcpyKind, cudaStream_t) { memmove(dst, src, n); return cudaSuccess; }
+cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t n, cudaMemcpyKind, cudaStream_t st) {
+  if (st && st->cap) return cudaErrorInvalidValue;
+  cusim::submit(st, [dst, src, n]() { memmove(dst, src, n); });
+  return cudaSuccess;
+}
 cudaError_t cudaMemset(void* p, int v, size_t n) { memset(p, v, n); return cudaSuccess; }
-cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = new cusimStream(); return cudaSuccess; }
-cudaError_t cudaStreamDestroy(cudaStream_t s) { delete s; return cudaSuccess; }
-cudaError_t cudaStreamSynchronize(cudaStream_t) { return cusim::g_failed.load() ? cudaErrorLaunchFailure : cudaSuccess; }
-cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = new cusimStream(); cusim::g_streams.push_back(*s); return cudaSuccess; }
+cudaError_t cudaStreamDestroy(cudaStream_t s) {
+  if (!s) return cudaSuccess;
+  cusim::drain(s);
+  auto& v = cusim::g_streams;
+  v.erase(std::remove(v.begin(), v.end(), s), v.end());
+  delete s;
+  return cudaSuccess;
+}
+cudaError_t cudaStreamSynchronize(cudaStream_t st) { cusim::drain(st); return cusim::g_failed.load() ? cudaErrorLaunchFailure : cudaSuccess; }
+cudaError_t cudaStreamWaitEvent(cudaStream_t st, cudaEvent_t ev, unsigned) {
+  cusimStream* src = ev->st;            // the event's state at the time of THIS call is what is waited for
+  const unsigned long long seq = ev->seq;
+  if (!src || src == st) return cudaSuccess;
+  cusim::submit(st, [src, seq]() { cusim::drain_until(src, seq); });
+  return cudaSuccess;
+}
 cudaError_t cudaStreamBeginCapture(cudaStream_t s, cudaStreamCaptureMode) {
   if (!s || s->cap) return cudaErrorInvalidValue;
   s->cap = new cusimGraph();
@@ -267,7 +317,7 @@ cudaError_t cudaStreamEndCapture(cudaStream_t s, cudaGraph_t* g) {
 }
 cudaError_t cudaGraphInstantiate(cudaGraphExec_t* x, cudaGraph_t g, unsigned long long) { *x = new cusimGraph(*g); return cudaSuccess; }
 cudaError_t cudaGraphLaunch(cudaGraphExec_t x, cudaStream_t st) {
-  for (const auto& op : x->ops) cusim::launch(op.grid, op.block, st, op.body);
+  for (const auto& op : x->ops) cusim::launch(op.grid, op.block, st, op.body);   // bodies are held by value
   return cusim::g_failed.load() ? cudaErrorLaunchFailure : cudaSuccess;
 }
 cudaError_t cudaGraphDestroy(cudaGraph_t g) { delete g; return cudaSuccess; }
@@ -275,8 +325,19 @@ cudaError_t cudaGraphExecDestroy(cudaGraphExec_t g) { delete g; return cudaSucce
 cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new cusimEvent(); return cudaSuccess; }
 cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = new cusimEvent(); return cudaSuccess; }
 cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
-cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { e->ns = cusim::clock_ns(); return cudaSuccess; }
-cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) { *ms = (float)((b->ns - a->ns) * 1e-6); return cudaSuccess; }
+cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t st) {
+  if (st && st->cap) return cudaErrorInvalidValue;
+  cusim::submit(st, [e]() { e->ns = cusim::clock_ns(); });
+  e->st = st;
+  e->seq = st ? st->enq : 0;
+  return cudaSuccess;
+}
+cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) {
+  cusim::drain_until(a->st, a->seq);
+  cusim::drain_until(b->st, b->seq);
+  *ms = (float)((b->ns - a->ns) * 1e-6);
+  return cudaSuccess;
+}
 cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) { memset(h, 0, sizeof *h); memcpy(h->reserved, &p, sizeof p); return cudaSuccess; }
 cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) { memcpy(p, h.reserved, sizeof *p); return cudaSuccess; }
 cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
@@ -300,7 +361,8 @@ cudaError_t cudaLibraryGetKernel(cudaKernel_t* k, cudaLibrary_t lib, const char*
 cudaError_t cudaLaunchKernel(const void* func, dim3 grid, dim3 block, void** args, size_t, cudaStream_t st) {
   if (st && st->cap) return cudaErrorInvalidValue;   // argument pointers do not outlive the call
   auto f = (void (*)(void**))func;
-  cusim::launch(grid, block, st, [=]() { f(args); });
+  cusim::drain(st);                                   // ... so this launch cannot be deferred: keep stream order, run now
+  cusim::launch(grid, block, nullptr, [=]() { f(args); });
   return cudaSuccess;
 }
 
