@@ -168,3 +168,44 @@ def test_fuzz_emulated_ranks(nd, monkeypatch, seed):
     out, ref, _plans, _sizes, _k = _run_world(nd, g, vm, em, world, ncalls=4, h=0.01)
     assert not np.isnan(out).any(), (seed, env, world)
     assert floored_rel_err(out, ref) <= 1e-12, (seed, env, world)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_fuzz_host_buffer_pipeline(nd, monkeypatch, seed):
+    """nd_b200_rhs_host's pipelined form (parameter vector uploaded in 2..10 pieces, row groups released as their
+    parameters land, D2H of finished rows overlapped) on mid-size random networks.  The emulator's streams are deferred,
+    so a row group launched before the last parameter it reads has been copied reads poisoned memory."""
+    import cusim
+    rng = np.random.default_rng(7000 + seed)
+    L = nd.Lib
+    n = int(rng.integers(6000, 20000))
+    kind = int(rng.integers(0, 4))
+    if kind == 0:
+        g = nd.erdos_renyi(n, int(rng.integers(2, 6)) * n, seed=seed)
+    elif kind == 1:
+        g = nd.barabasi_albert(n, int(rng.integers(2, 5)), seed=seed)
+    elif kind == 2:
+        g = nd.watts_strogatz(n, 6, 0.3, seed=seed, directed=True)
+    else:
+        g = nd.grid_graph(100, n // 100)
+    vpool = [L.kuramoto_first(), L.kuramoto_second(), L.kuramoto_second_bench(), L.diffusion_vertex()]
+    nvt = int(rng.integers(1, 4))
+    vm = ([vpool[i] for i in rng.choice(len(vpool), nvt, replace=False)], rng.integers(0, nvt, g.nv))
+    if g.directed:
+        em = nd.EdgeModel(g=nd.Directed(L.kuramoto_edge_f), outdim=1, pdim=1, name="dir_kura")
+    else:
+        em = [L.diffusion_edge(), L.kuramoto_edge(), ([L.diffusion_edge(), L.kuramoto_edge()], rng.integers(0, 2, g.ne))][int(rng.integers(0, 3))]
+    monkeypatch.setenv("ND_B200_KERNEL", ["fused", "jag"][int(rng.integers(0, 2))])
+    if rng.integers(0, 2):
+        monkeypatch.setenv("ND_B200_JAG_WINDOW", "128")
+    monkeypatch.setenv("ND_B200_HOST_CHUNKS", str(int(rng.integers(2, 11))))
+    with cusim.use():
+        nw = nd.Network(g, vm, em, aggregator=nd.B200Aggregator("+", keep_tables=False))
+        onw = oracle_network(g, vm, em)
+        u = rng.standard_normal(nw.dim())
+        p = 0.5 + condition_params(nw, rng.random(nw.pdim()))
+        ref = onw.rhs(u, p)
+        for _ in range(2):
+            hdu = np.full(nw.dim(), np.nan)
+            nw(hdu, u, p, 0.0)
+            assert floored_rel_err(hdu, ref) <= 1e-12, seed
