@@ -620,7 +620,8 @@ __global__ void __launch_bounds__(BLOCK, (fused_warps_per_sm(EK) * 32) / BLOCK) 
         const double2 t2 = *reinterpret_cast<const double2*>(gp);
         xn[k][0] = t2.x; xn[k][1] = t2.y;
       } else {
-        xn[k][0] = gp[0];
+#pragma unroll
+        for (int q = 0; q < VD; ++q) xn[k][q] = gp[q];
       }
     }
   }
@@ -1133,7 +1134,8 @@ __global__ void __launch_bounds__(BLOCK, (WPS * 32) / BLOCK) rhs_jag_kernel(cons
             const double2 t2 = *reinterpret_cast<const double2*>(gp);
             xn[q][0] = t2.x; xn[q][1] = t2.y;
           } else {
-            xn[q][0] = gp[0];
+#pragma unroll
+            for (int k = 0; k < VD; ++k) xn[q][k] = gp[k];
           }
         }
         int pd = PE;

@@ -209,3 +209,104 @@ def test_fuzz_host_buffer_pipeline(nd, monkeypatch, seed):
             hdu = np.full(nw.dim(), np.nan)
             nw(hdu, u, p, 0.0)
             assert floored_rel_err(hdu, ref) <= 1e-12, seed
+
+
+def _expr(rng, terms):
+    """a random expression over the given operand strings, valid (and evaluated in the same order) in C and Python"""
+    k = int(rng.integers(1, 4))
+    parts = []
+    for _ in range(k):
+        a, b = terms[int(rng.integers(0, len(terms)))], terms[int(rng.integers(0, len(terms)))]
+        c = round(float(rng.uniform(-1.5, 1.5)), 3)
+        parts.append([f"{c}*{a}", f"{a}*{b}", f"sin({a} - {b})", f"({a} + {c})*{b}"][int(rng.integers(0, 4))])
+    return " + ".join(parts)
+
+
+def _pyfun(args, outs):
+    import math
+    src = f"lambda {args}: [" + ", ".join(outs) + "]"
+    return eval(src, {"sin": math.sin})
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_fuzz_user_supplied_kinds(nd, monkeypatch, seed):
+    """run-time compiled kinds with random dimensions (vdepth != edepth, up to 5 states, 0..3 parameters), random
+    bodies generated as the same expression text for CUDA and for the Python twin, computed or StateMask vertex outputs,
+    all wrappers, two-sided static edges, edges with states and per-side masks -- on the emulator ("NVRTC" = g++)"""
+    import cusim
+    from oracle import oracle as O
+    from oracle import oracle_np as ONP
+    rng = np.random.default_rng(11000 + seed)
+    C = nd.CudaFunction
+    vdepth, edepth = int(rng.integers(1, 4)), int(rng.integers(1, 4))
+    g = _random_graph(nd, rng)
+    if g.nv < 3:
+        g = nd.complete_graph(4)
+
+    def vertex(k):
+        dim, pdim = int(rng.integers(vdepth, 6)), int(rng.integers(0, 4))
+        ops = [f"v[{i}]" for i in range(dim)] + [f"esum[{i}]" for i in range(edepth)] + [f"p[{i}]" for i in range(pdim)] + ["t"]
+        fo = [_expr(rng, ops) for _ in range(dim)]
+        f = C(f"vf{k}", "vertex_f", " ".join(f"dv[{i}] = {e};" for i, e in enumerate(fo)), py=_pyfun("v, esum, p, t", fo))
+        if rng.integers(0, 2):
+            gops = [f"v[{i}]" for i in range(dim)] + [f"p[{i}]" for i in range(pdim)]
+            go = [_expr(rng, gops) for _ in range(vdepth)]
+            gfun = C(f"vg{k}", "vertex_g", " ".join(f"out[{i}] = {e};" for i, e in enumerate(go)), py=_pyfun("v, p, t", go))
+        else:
+            gfun = nd.StateMask(tuple(range(1, vdepth + 1)))
+        return nd.VertexModel(f=f, g=gfun, dim=dim, pdim=pdim, outdim=vdepth, name=f"v{k}")
+
+    def edge(k):
+        pdim = int(rng.integers(0, 4))
+        ops = [f"v_src[{i}]" for i in range(vdepth)] + [f"v_dst[{i}]" for i in range(vdepth)] + [f"p[{i}]" for i in range(pdim)]
+        style = int(rng.integers(0, 3))
+        if style == 0:      # one-sided g under a wrapper
+            eo = [_expr(rng, ops) for _ in range(edepth)]
+            body = C(f"eg{k}", "edge_g", " ".join(f"e_dst[{i}] = {e};" for i, e in enumerate(eo)), py=_pyfun("v_src, v_dst, p, t", eo))
+            w = [nd.AntiSymmetric, nd.Symmetric, nd.Directed][int(rng.integers(0, 3))]
+            return nd.EdgeModel(g=w(body), outdim=edepth, pdim=pdim, name=f"e{k}")
+        if style == 1:      # two-sided static g
+            es, ed = [_expr(rng, ops) for _ in range(edepth)], [_expr(rng, ops) for _ in range(edepth)]
+            txt = " ".join(f"e_src[{i}] = {e};" for i, e in enumerate(es)) + " " + " ".join(f"e_dst[{i}] = {e};" for i, e in enumerate(ed))
+            py_s, py_d = _pyfun("v_src, v_dst, p, t", es), _pyfun("v_src, v_dst, p, t", ed)
+            body = C(f"eg2{k}", "edge_g2", txt, py=lambda vs, vd, p, t, a=py_s, b=py_d: (a(vs, vd, p, t), b(vs, vd, p, t)))
+            return nd.EdgeModel(g=nd.Fiducial(body), outdim=edepth, pdim=pdim, name=f"e{k}")
+        dim = int(rng.integers(edepth, 2 * edepth + 2))      # edge with states
+        fops = ops + [f"e[{i}]" for i in range(dim)] + ["t"]
+        fo = [_expr(rng, fops) for _ in range(dim)]
+        f = C(f"ef{k}", "edge_f", " ".join(f"de[{i}] = {e};" for i, e in enumerate(fo)), py=_pyfun("e, v_src, v_dst, p, t", fo))
+        md = int(rng.integers(1, dim - edepth + 2))
+        ms = int(rng.integers(1, dim - edepth + 2))
+        mask = lambda a: tuple(range(a, a + edepth))
+        w = [nd.AntiSymmetric(mask(md)), nd.Symmetric(mask(md)), nd.Directed(mask(md)), nd.Fiducial(src=mask(ms), dst=mask(md))][int(rng.integers(0, 4))]
+        return nd.EdgeModel(f=f, g=w, dim=dim, pdim=pdim, outdim=edepth, name=f"e{k}")
+
+    vms = [vertex(k) for k in range(int(rng.integers(1, 3)))]
+    ems = [edge(k) for k in range(int(rng.integers(1, 4)))]
+    vt, et = rng.integers(0, len(vms), g.nv), rng.integers(0, len(ems), g.ne)
+    monkeypatch.setenv("ND_B200_KERNEL", ["fused", "jag"][int(rng.integers(0, 2))])
+    monkeypatch.setenv("ND_B200_JAG_SPLIT", str([3, 32][int(rng.integers(0, 2))]))
+
+    def kind(m):
+        if hasattr(m, "outdim_dst"):
+            if m.dim > 0:
+                return ONP.PyKind(f=m.f.py)
+            inner = m.g.g
+            return ONP.PyKind(g=inner.py)
+        return ONP.PyKind(f=m.f.py, g=(m.g.py if isinstance(m.g, C) else None))
+    vs = [O.VSpec(kind(m), m.dim, m.pdim, m.outdim) for m in vms]
+    es = [O.ESpec(kind(m), m.coupling, m.dim, m.pdim, m.outdim_src, m.outdim_dst, *(m.state_masks() or (0, 0))) for m in ems]
+    im = ONP.IndexManager(g.nv, g.src, g.dst, vs, list(vt), es, list(et))
+    with cusim.use():
+        nw = nd.Network(g, (vms, vt), (ems, et), aggregator=nd.B200Aggregator("+", long_row_threshold=[0, 4][int(rng.integers(0, 2))]))
+        assert (nw.dim(), nw.pdim()) == (im.last["dynamic"], im.last["p"])
+        u, p = rng.uniform(-1, 1, nw.dim()), rng.uniform(0.2, 1.2, nw.pdim())
+        pd = cusim.dev(p) if p.size else None
+        for t in (0.0, 0.4):
+            ref, o_ref, agg_ref = ONP.rhs(im, u, p, t)
+            du = cusim.empty(nw.dim())
+            nw(du, cusim.dev(u), pd, t)
+            assert floored_rel_err(du.numpy(), ref) <= 1e-12, (seed, t)
+        o, agg = cusim.empty(nw.im.lastidx_out), cusim.empty(nw.im.lastidx_aggr)
+        nw.get_buffers(o, agg, cusim.dev(u), pd, 0.4)
+        assert floored_rel_err(agg.numpy(), agg_ref) <= 1e-12 and floored_rel_err(o.numpy(), o_ref) <= 1e-12, seed
