@@ -107,6 +107,32 @@ def test_fuzz_registry_networks_on_the_emulator(nd, monkeypatch, seed):
             du2 = cusim.empty(nw.dim())
             nw(du2, cusim.dev(u), pd, 0.0)
             assert np.array_equal(du2.numpy(), du.numpy()), (seed, env)
+            nw.pack_params(None)
+        # RK4 step counts around the 8-step graph unroll (whole graphs + remainder steps)
+        nsteps = int(rng.integers(1, 20))
+        ud = cusim.dev(u)
+        nw.rk4(ud, pd, 0.0, 1e-3, nsteps)
+        assert floored_rel_err(ud.numpy(), onw.rk4(u, p, 0.0, 1e-3, nsteps)) <= 1e-11, (seed, env, nsteps)
+        # row-partitioned engines without a halo layout (the all-gather exchange path): every rank evaluates its own row
+        # range from a complete state vector; the ranges tile du
+        has_states = any(getattr(m, "dim", 0) > 0 for m in (em[0] if isinstance(em, tuple) else [em]))
+        if not has_states and g.nv >= 2:
+            cuts = sorted(set([0, g.nv] + [int(c) for c in rng.integers(0, g.nv + 1, int(rng.integers(1, 4)))]))
+            out = np.full(nw.dim(), np.nan)
+            for a, b in zip(cuts[:-1], cuts[1:]):
+                part = nd.Network(g, vm, em, aggregator=nd.B200Aggregator("+", long_row_threshold=thr, row_range=(a, b), keep_tables=False))
+                dp = cusim.empty(nw.dim())
+                part(dp, cusim.dev(u), pd, 0.0)
+                w = ~np.isnan(dp.numpy())
+                assert not np.any(w & ~np.isnan(out)), "two row ranges wrote the same state"
+                out[w] = dp.numpy()[w]
+            assert np.array_equal(out, du.numpy()), (seed, env, cuts)
+        # homogeneous registry networks: the engine built straight from the edge list is the same engine
+        if not isinstance(vm, tuple) and not isinstance(em, tuple) and not has_states and em.coupling != 3 and g.ne > 0:
+            el = nd.Network.from_edgelist(g, vm, em)
+            d3 = cusim.empty(nw.dim())
+            el(d3, cusim.dev(u), pd, 0.0)
+            assert floored_rel_err(d3.numpy(), ref) <= 1e-12, (seed, env)
 
 
 @pytest.mark.parametrize("seed", range(8))
