@@ -15,6 +15,9 @@ run() {  # name, extra args
   echo "== $name rc=$?"; tail -c 1800 gpurun_out/bench_n${N}_${name}.json; tail -3 gpurun_out/bench_n${N}_${name}.err
 }
 run cfg2_p2p --exchange p2p
+run cfg2_p2p_pack --exchange p2p --pack
 run cfg2_nccl --exchange nccl
 run cfg5s_p2p --exchange p2p --workload cfg5_kuramoto_er_5e6
+run cfg5s_p2p_pack --exchange p2p --workload cfg5_kuramoto_er_5e6 --pack
+run grid_p2p --exchange p2p --workload grid_kuramoto_1e6
 ls -la gpurun_out | head -40
