@@ -13,8 +13,8 @@ from . import _cabi
 from ._cabi import build
 from .components import (AntiSymmetric, ArgumentError, CudaFunction, Directed, EdgeModel, Fiducial, Lib,
                          RegisteredFunction, StateMask, Symmetric, VertexModel)
-from .graphs import (SimpleDiGraph, SimpleGraph, barabasi_albert, complete_graph, erdos_renyi, grid_graph, ne, nv,
-                     path_graph, watts_strogatz)
+from .graphs import (SimpleDiGraph, SimpleGraph, barabasi_albert, complete_graph, erdos_renyi, grid_graph, locality_order, ne,
+                     nv, path_graph, permute_graph, watts_strogatz)
 from .network import (B200Aggregator, B200Execution, ComponentBatch, ExecutionStyle, IndexManager, Network, dim,
                       find_identical, get_aggr_constructor, iscudacompatible, pdim, pinned_empty, usebuffer)
 

@@ -145,3 +145,41 @@ def barabasi_albert(n: int, m: int, seed: int = 1) -> SimpleGraph:
     src = 1 + i // m
     dst = np.where(ptr == 0, 0, 1 + ((ptr - 1) // 2) // m)
     return SimpleGraph(n, src + 1, dst + 1)
+
+
+# ---------------------------------------------------------------------------------------------------
+# locality ordering for the multi-GPU vertex partition ("contiguous ranges of a locality-ordered graph")
+# ---------------------------------------------------------------------------------------------------
+def locality_order(g, method: str = "rcm") -> np.ndarray:
+    """A vertex ordering under which neighbours get nearby ids, so that contiguous id ranges (what PartitionedNetwork
+    gives every rank) cut few edges: reverse Cuthill-McKee on the symmetrised adjacency structure.
+    Returns `order` (0-based): order[k] = the OLD vertex (0-based) that becomes new vertex k."""
+    if method != "rcm":
+        raise ValueError("locality_order: only 'rcm' is implemented")
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import reverse_cuthill_mckee
+    n = g.nv
+    s, d = np.asarray(g.src) - 1, np.asarray(g.dst) - 1
+    a = coo_matrix((np.ones(2 * s.size, dtype=np.int8), (np.concatenate([s, d]), np.concatenate([d, s]))), shape=(n, n)).tocsr()
+    return np.asarray(reverse_cuthill_mckee(a, symmetric_mode=True), dtype=np.int64)
+
+
+def permute_graph(g, order: np.ndarray):
+    """Relabel the vertices of `g` (new vertex k = old vertex order[k]) and return (g2, edge_order): g2 in the reference's
+    canonical edge order, edge_order[j] = the OLD edge index (0-based) that is edge j of g2 -- what a caller needs to carry
+    per-vertex data (`x_new = x_old[order]`) and per-edge data (`y_new = y_old[edge_order]`) over to the relabelled network.
+    The sequential accumulation order is then defined on the new ids."""
+    order = np.asarray(order, dtype=np.int64)
+    n = g.nv
+    if order.size != n or not np.array_equal(np.sort(order), np.arange(n)):
+        raise ValueError("order must be a permutation of 0..nv-1")
+    new_of_old = np.empty(n, dtype=np.int64)
+    new_of_old[order] = np.arange(n)
+    s, d = new_of_old[np.asarray(g.src) - 1], new_of_old[np.asarray(g.dst) - 1]
+    if not g.directed:
+        s, d = np.minimum(s, d), np.maximum(s, d)
+    edge_order = np.argsort(s * n + d, kind="stable")
+    cls = SimpleDiGraph if g.directed else SimpleGraph
+    g2 = cls(n, s[edge_order] + 1, d[edge_order] + 1)
+    assert g2.ne == g.ne
+    return g2, edge_order
