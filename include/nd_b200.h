@@ -241,6 +241,11 @@ int nd_b200_comm_set_send(nd_b200_comm*, int32_t peer, const int64_t* state_offs
 /* replaces `(nw::Network)(du,u,p,t)` for a row-partitioned engine: only the owned states of u need to be valid */
 int nd_b200_rhs_exchange(nd_b200_engine*, nd_b200_comm*, double* du, const double* u, const double* p, double t,
                          void* stream);
+/* replaces `solve(ODEProblem(nw,...), RK4(); dt, adaptive=false)` for a row-partitioned engine: classical RK4 with four
+ * exchanging launches per step (every stage packs the boundary outputs of its own input for the peers and applies the fused
+ * stage update to the owned states).  Collective like nd_b200_rhs_exchange; only the owned states of u are read / advanced. */
+int nd_b200_rk4_exchange(nd_b200_engine*, nd_b200_comm*, double* u, const double* p, double t0, double dt, int64_t nsteps,
+                         void* stream);
 /* timing aid (exposed halo time = exchange call - this): the owned rows evaluated on whatever the halo buffer
  * currently holds; no publish, no wait */
 int nd_b200_rhs_local(nd_b200_engine*, nd_b200_comm*, double* du, const double* u, const double* p, double t,

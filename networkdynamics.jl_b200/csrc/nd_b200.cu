@@ -1719,19 +1719,23 @@ void nd_b200_comm_destroy(nd_b200_comm* c) {
   delete c;
 }
 
-int nd_b200_rhs_exchange(nd_b200_engine* e, nd_b200_comm* c, double* du, const double* u, const double* p, double t,
-                         void* stream) {
-  if (int rc = check_call(e, du, u, p)) return rc;
-  if (!c) return fail(e, ND_B200_EINVAL, "nd_b200_rhs_exchange: comm is NULL");
-  if (!e->gather_from_u || e->split) return fail(e, ND_B200_EUNSUPPORTED, "nd_b200_rhs_exchange needs StateMask vertices and a fused kernel");
+}  // extern "C"
+
+namespace {
+int check_exchange(nd_b200_engine* e, nd_b200_comm* c, const char* who) {
+  if (!c) return fail(e, ND_B200_EINVAL, "%s: comm is NULL", who);
+  if (!e->gather_from_u || e->split) return fail(e, ND_B200_EUNSUPPORTED, "%s needs StateMask vertices and a fused kernel", who);
   if (e->halo_base == INT_MAX) return fail(e, ND_B200_EINVAL, "the engine was created without gather_offset (no halo layout)");
   if (e->gather_len - e->lastidx_dynamic != c->halo_len) return fail(e, ND_B200_EINVAL, "comm halo holds %lld outputs, the engine expects %lld", c->halo_len, e->gather_len - e->lastidx_dynamic);
   for (int r = 0; r < c->world; ++r)
     if (!c->base[r]) return fail(e, ND_B200_EINVAL, "peer %d has not been opened", r);
-  cudaStream_t st = (cudaStream_t)stream;
+  return ND_B200_OK;
+}
+// one exchange = the next sequence number: what the publishing blocks of this launch send (outputs packed from `src`) and
+// what its halo-reading tiles wait for
+WaitSpec next_exchange(nd_b200_comm* c, const double* src, HaloParams& H) {
   const unsigned long long seq = ++c->seq;
   const int parity = (int)(seq & 1ull);
-  HaloParams H;
   memset(&H, 0, sizeof H);
   long long total = 0;
   for (int r = 0; r < c->world; ++r) {
@@ -1739,11 +1743,62 @@ int nd_b200_rhs_exchange(nd_b200_engine* e, nd_b200_comm* c, double* du, const d
     H.send_idx[r] = c->d_send_idx[r]; H.send_n[r] = c->send_n[r]; H.dst_off[r] = c->dst_off[r];
     total += c->send_n[r];
   }
-  H.world = c->world; H.rank = c->rank; H.seq = seq; H.src = u; H.done_counter = c->d_done;
+  H.world = c->world; H.rank = c->rank; H.seq = seq; H.src = src; H.done_counter = c->d_done;
   // publishing blocks: 128 threads each, ~8 outputs per thread, at least one (it raises the flags even when nothing is sent)
   const int n_pub = (int)std::max<long long>(1, std::min<long long>(148 * 16, (total + 1023) / 1024));
-  WaitSpec w{c->halo(c->rank, parity), c->flags(c->rank), seq, c->world, c->d_timeout, &H, n_pub};
-  return rhs_impl(e, du, u, p, t, st, MODE_DU, nullptr, &w);
+  return WaitSpec{c->halo(c->rank, parity), c->flags(c->rank), seq, c->world, c->d_timeout, &H, n_pub};
+}
+}  // namespace
+
+extern "C" {
+
+int nd_b200_rhs_exchange(nd_b200_engine* e, nd_b200_comm* c, double* du, const double* u, const double* p, double t,
+                         void* stream) {
+  if (int rc = check_call(e, du, u, p)) return rc;
+  if (int rc = check_exchange(e, c, "nd_b200_rhs_exchange")) return rc;
+  HaloParams H;
+  const WaitSpec w = next_exchange(c, u, H);
+  return rhs_impl(e, du, u, p, t, (cudaStream_t)stream, MODE_DU, nullptr, &w);
+}
+
+/* Classical RK4 on a row-partitioned engine: four exchanging launches per step and nothing else -- every stage packs the
+ * boundary outputs of ITS input vector for the peers, evaluates the owned rows and applies the fused stage update to the
+ * owned states (same operation order as nd_b200_rk4 / the oracle).  Only the owned states of u are read and advanced. */
+int nd_b200_rk4_exchange(nd_b200_engine* e, nd_b200_comm* c, double* u, const double* p, double t0, double dt, int64_t nsteps,
+                         void* stream) {
+  if (int rc = check_call(e, u, u, p)) return rc;
+  if (int rc = check_exchange(e, c, "nd_b200_rk4_exchange")) return rc;
+  if (nsteps <= 0) return ND_B200_OK;
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t nb = sizeof(double) * (size_t)e->lastidx_dynamic;
+  if (!e->d_tmpA) {
+    CUDA_TRY(e, cudaMalloc((void**)&e->d_tmpA, nb));
+    CUDA_TRY(e, cudaMalloc((void**)&e->d_tmpB, nb));
+    CUDA_TRY(e, cudaMalloc((void**)&e->d_ksum, nb));
+  }
+  const double h2 = 0.5 * dt;
+  const double* in[4] = {u, e->d_tmpA, e->d_tmpB, e->d_tmpA};
+  double* out[4] = {e->d_tmpA, e->d_tmpB, e->d_tmpA, u};
+  const double hs[4] = {h2, h2, dt, 0.0};
+  for (int64_t k = 0; k < nsteps; ++k) {
+    const double t = t0 + (double)k * dt;
+    const double ts[4] = {t, t + h2, t + h2, t + dt};
+    for (int s = 0; s < 4; ++s) {
+      HaloParams H;
+      const WaitSpec w = next_exchange(c, in[s], H);
+      KParams P;
+      fill_params(e, P);
+      P.p = p; P.mode = MODE_RK; P.u0 = u; P.ksum = e->d_ksum; P.h6 = dt / 6.0;
+      P.stage = s + 1; P.u = in[s]; P.gsrc = in[s]; P.unext = out[s]; P.hs = hs[s]; P.t = ts[s]; P.vout_next = nullptr;
+      P.halo = w.halo; P.wait_flags = w.flags; P.wait_seq = w.seq; P.wait_world = w.world; P.wait_timeout = w.timeout;
+      P.H = H; P.n_pub = w.n_pub;
+      const bool waits = e->jag ? (e->wait_from < e->nslices || e->n_jlong > 0) : (e->wait_from < e->nblocks);
+      P.fence = waits ? 0 : 1;
+      CUDA_TRY(e, launch_fused(e, P, st));
+    }
+  }
+  return ND_B200_OK;
 }
 
 /* timing aid: the owned rows evaluated on whatever the halo buffer currently holds -- no publish, no wait */

@@ -320,6 +320,24 @@ class PartitionedNetwork:
             self.exchange(u)
         self.nw(du, u, p, t)
 
+    def rk4(self, u, p, t0, dt, nsteps, *, stream=None, work=None):
+        """`nsteps` classical RK4 steps on the owned states of `u` (in place).  With the NVLink exchange this is
+        nd_b200_rk4_exchange: four exchanging kernel launches per step per rank and nothing else (stage updates fused into
+        the kernels' epilogues); with the all-gather exchange the stages are driven from the host (`rk4_step`)."""
+        if self.comm is not None:
+            from .network import _addr, _stream_handle
+            from . import _cabi
+            a_u, _, n_u = _addr(u)
+            a_p, _, n_p = _addr(p)
+            self.nw._check_sizes(n_u, n_u, n_p, p is not None)
+            rc = _cabi.lib().nd_b200_rk4_exchange(self.nw.handle, self.comm, a_u, a_p, float(t0), float(dt), int(nsteps), _stream_handle(stream))
+            if rc:
+                self.nw._fail(rc)
+            return
+        work = {} if work is None else work
+        for k in range(int(nsteps)):
+            self.rk4_step(u, p, t0 + k * dt, dt, work)
+
     def rk4_step(self, u, p, t, dt, work):
         """one classical RK4 step on the owned states (same operation order as the single-GPU engine); `work` is a
         dict of scratch tensors reused across steps"""

@@ -194,6 +194,8 @@ def test_fuzz_emulated_ranks(nd, monkeypatch, seed):
     out, ref, _plans, _sizes, _k = _run_world(nd, g, vm, em, world, ncalls=4, h=0.01)
     assert not np.isnan(out).any(), (seed, env, world)
     assert floored_rel_err(out, ref) <= 1e-12, (seed, env, world)
+    out, ref, _plans, _sizes, _k = _run_world(nd, g, vm, em, world, ncalls=3, rk4=1e-2)     # nd_b200_rk4_exchange
+    assert not np.isnan(out).any() and floored_rel_err(out, ref) <= 1e-11, (seed, env, world)
 
 
 @pytest.mark.parametrize("seed", range(10))

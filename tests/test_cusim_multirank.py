@@ -22,7 +22,7 @@ def _ptr(a):
     return a.ctypes.data if a is not None else None
 
 
-def _run_world(nd, g, vm, em, world, ncalls, h=0.01, pack=False):
+def _run_world(nd, g, vm, em, world, ncalls, h=0.01, pack=False, rk4=None):
     import cusim
     from networkdynamics_jl_b200 import distributed as D
     with cusim.use() as L:
@@ -63,6 +63,11 @@ def _run_world(nd, g, vm, em, world, ncalls, h=0.01, pack=False):
 
         def rank_main(r):
             try:
+                if rk4 is not None:        # fused multi-rank RK4: four exchanging launches per step, nothing else
+                    rc = L.nd_b200_rk4_exchange(nws[r].handle, comms[r], _ptr(us[r]), _ptr(p) if p.size else None, 0.0, rk4, ncalls, None)
+                    if rc:
+                        raise RuntimeError(L.nd_b200_last_error(nws[r].handle).decode())
+                    return
                 du = np.full(n, np.nan)
                 for k in range(ncalls):
                     rc = L.nd_b200_rhs_exchange(nws[r].handle, comms[r], _ptr(du), _ptr(us[r]), _ptr(p) if p.size else None, 0.0, None)
@@ -93,6 +98,8 @@ def _run_world(nd, g, vm, em, world, ncalls, h=0.01, pack=False):
             L.nd_b200_comm_destroy(c)
         del nws
     onw = oracle_network(g, vm, em)
+    if rk4 is not None:
+        return out, onw.rk4(u0, p, 0.0, rk4, ncalls), plans, sizes, kernel
     ref = u0.copy()
     for _ in range(ncalls):
         ref = ref + h * onw.rhs(ref, p)
@@ -182,3 +189,18 @@ def test_locality_ordering_shrinks_the_halo(nd, monkeypatch):
     out, ref2, plans, _sizes, _k = _run_world(nd, g2, L.kuramoto_first(), L.kuramoto_edge(), world, ncalls=3)
     assert np.array_equal(out, ref2)
     assert max(plans[0]["halo_lens"]) == h_ordered
+
+
+@pytest.mark.parametrize("kernel", ["fused", "jag"])
+@pytest.mark.parametrize("name,world", [("er_diffusion", 4), ("grid_kuramoto", 3), ("ba_mixed", 2)])
+def test_emulated_ranks_fused_rk4(nd, monkeypatch, name, world, kernel):
+    """nd_b200_rk4_exchange: classical RK4 on a row-partitioned network with the stage updates fused into the exchanging
+    kernels (each stage publishes the boundary outputs of its own input vector); 10 steps against the oracle's RK4"""
+    monkeypatch.setenv("ND_B200_KERNEL", kernel)
+    g, vm, em = _cases(nd)[name]
+    out, ref, _plans, _sizes, _k = _run_world(nd, g, vm, em, world, ncalls=10, rk4=1e-2)
+    assert not np.isnan(out).any()
+    if name == "ba_mixed":
+        assert np.max(np.abs(out - ref)) <= 1e-12 * np.max(np.abs(ref))
+    else:
+        assert np.array_equal(out, ref)
