@@ -110,14 +110,40 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def build_workload(nd, name, world):
+def shared_graph(nd, make, tag, rank, world, barrier):
+    """one rank generates the (seeded, identical everywhere) graph, the others map its edge arrays from shared memory:
+    8 ranks generating a 4e8-edge graph each would need ~20 GB and minutes of host time apiece"""
+    if world == 1:
+        return make()
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else __import__("tempfile").gettempdir()
+    path = os.path.join(base, f"ndb200_{tag}_{os.environ.get('MASTER_PORT', '0')}")
+    if rank == 0:
+        g = make()
+        np.save(path + "_src.npy", g.src)
+        np.save(path + "_dst.npy", g.dst)
+        np.save(path + "_nv.npy", np.array([g.nv], dtype=np.int64))
+    barrier()
+    if rank != 0:
+        n = int(np.load(path + "_nv.npy")[0])
+        g = nd.SimpleGraph(n, np.load(path + "_src.npy", mmap_mode="r"), np.load(path + "_dst.npy", mmap_mode="r"), _canonical=True)
+    barrier()
+    if rank == 0:      # the mappings of the other ranks keep the pages alive
+        for suffix in ("_src.npy", "_dst.npy", "_nv.npy"):
+            try:
+                os.remove(path + suffix)
+            except OSError:
+                pass
+    return g
+
+
+def build_workload(nd, name, world, rank=0, barrier=None):
     nv, ne, family, scaling = WORKLOADS[name]
     t0 = time.time()
     mult = world if scaling == "weak" else 1
     if name.startswith("grid"):
         g = nd.grid_graph(1000, 1000 * mult)
     else:
-        g = nd.erdos_renyi(nv * mult, ne * mult, seed=1)
+        g = shared_graph(nd, lambda: nd.erdos_renyi(nv * mult, ne * mult, seed=1), f"{name}_{mult}", rank, world if barrier else 1, barrier)
     L = nd.Lib
     if family == "diffusion":
         return g, L.diffusion_vertex(), L.diffusion_edge(), time.time() - t0
@@ -222,14 +248,18 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    g, vm, em, t_graph = build_workload(nd, args.workload, world)
+    g, vm, em, t_graph = build_workload(nd, args.workload, world, rank, (dist.barrier if dist is not None else None))
     t0 = time.time()
     if world == 1:
-        nw = nd.Network(g, vm, em, execution=nd.B200Execution(), aggregator=nd.B200Aggregator("+", keep_tables=False))
+        if g.nv >= 10_000_000:     # config-5 scale: engine straight from the edge list, no per-component host tables
+            nw = nd.Network.from_edgelist(g, vm, em)
+        else:
+            nw = nd.Network(g, vm, em, execution=nd.B200Execution(), aggregator=nd.B200Aggregator("+", keep_tables=False))
         pnw = None
     else:
         from networkdynamics_jl_b200.distributed import PartitionedNetwork
-        pnw = PartitionedNetwork(g, vm, em, rank=rank, world=world, group=dist.group.WORLD, exchange=args.exchange)
+        # homogeneous workloads: partition, halo plan and engines from the bare edge list
+        pnw = PartitionedNetwork(g, vm, em, rank=rank, world=world, group=dist.group.WORLD, exchange=args.exchange, from_edgelist=True)
         nw = pnw.nw
     t_build = time.time() - t0
     sizes = nw.engine_sizes()

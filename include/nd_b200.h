@@ -153,10 +153,12 @@ int nd_b200_create(const nd_b200_desc* desc, nd_b200_engine** out);
 /* The same for a HOMOGENEOUS network given as a bare edge list (BASELINE config 5: 5e7 vertices, 4e8 edges): one registry
  * vertex kind, one registry edge kind + wrapper; the flat u / p layout is the one the reference's constructor produces
  * for such a network (vertex states, then nothing; vertex parameters, then edge parameters in edges(g) order).
- * edge_src / edge_dst: 1-based, edges(g) order.  Saves the caller the per-component tables of nd_b200_desc. */
+ * edge_src / edge_dst: 1-based, edges(g) order.  Saves the caller the per-component tables of nd_b200_desc.
+ * gather_offset / gather_len: as in nd_b200_desc (row-partitioned engine with a packed halo). */
 int nd_b200_create_from_edgelist(int32_t device, int64_t nv, int64_t ne, const int64_t* edge_src, const int64_t* edge_dst,
                                  int32_t vertex_kind, int32_t edge_kind, int32_t coupling, int64_t row_begin,
-                                 int64_t row_end, int32_t flags, nd_b200_engine** out);
+                                 int64_t row_end, int32_t flags, const int64_t* gather_offset /* NULL: no halo layout */,
+                                 int64_t gather_len, nd_b200_engine** out);
 void nd_b200_destroy(nd_b200_engine*);
 /* message of the last failing call on this engine (engine == NULL: last failing create on this thread) */
 const char* nd_b200_last_error(const nd_b200_engine*);

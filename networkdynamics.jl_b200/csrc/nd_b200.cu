@@ -1208,7 +1208,8 @@ int nd_b200_create(const nd_b200_desc* desc, nd_b200_engine** out) {
  * src/network_structure.jl:224-258) -- without the caller materialising per-component tables. */
 int nd_b200_create_from_edgelist(int32_t device, int64_t nv, int64_t ne, const int64_t* edge_src, const int64_t* edge_dst,
                                  int32_t vertex_kind, int32_t edge_kind, int32_t coupling, int64_t row_begin,
-                                 int64_t row_end, int32_t flags, nd_b200_engine** out) {
+                                 int64_t row_end, int32_t flags, const int64_t* gather_offset, int64_t gather_len,
+                                 nd_b200_engine** out) {
   struct VR { int kind, dim, pdim, outdim; };
   static const VR vreg[] = {{ND_B200_V_DIFFUSION, 1, 0, 1}, {ND_B200_V_KURAMOTO_FIRST, 1, 1, 1}, {ND_B200_V_KURAMOTO_SECOND, 2, 3, 1},
                             {ND_B200_V_KURAMOTO_SECOND_BENCH, 2, 1, 1}, {ND_B200_V_SWING_DQ, 2, 4, 2}};
@@ -1242,6 +1243,7 @@ int nd_b200_create_from_edgelist(int32_t device, int64_t nv, int64_t ne, const i
   d.lastidx_dynamic = nv * v->dim; d.lastidx_p = nv * v->pdim + (ne > 0 ? ne * g->pdim : 0);
   d.lastidx_out = nv * v->outdim + (ne > 0 ? ne * (osrc + g->odst) : 0); d.lastidx_aggr = nv * d.edepth;
   d.row_begin = row_begin; d.row_end = row_end; d.flags = flags;
+  d.gather_offset = gather_offset; d.gather_len = gather_len;
   return nd_b200_create(&d, out);
 }
 

@@ -23,6 +23,8 @@ from .network import B200Aggregator, B200Execution, ComponentBatch, IndexManager
 
 def row_of_vertex(im: IndexManager) -> np.ndarray:
     """aggregation-slot row (0-based) of every vertex: (v_aggr.first - 1) / edepth; rows follow batch order."""
+    if getattr(im, "homogeneous", False):        # one vertex batch 1:nv (Network.from_edgelist): row = vertex
+        return np.arange(im.nv, dtype=np.int64)
     if im.edepth > 0:
         return (im.v_aggr - 1) // im.edepth
     row = np.empty(im.nv, dtype=np.int64)
@@ -38,7 +40,7 @@ def row_entry_counts(im: IndexManager, edgebatches: Sequence[ComponentBatch]) ->
     rov = row_of_vertex(im)
     cnt = np.zeros(im.nv, dtype=np.int64)
     for b in edgebatches:
-        e = b.indices - 1
+        e = slice(None) if b.indices is None else b.indices - 1
         cnt += np.bincount(rov[im.edge_dst[e] - 1], minlength=im.nv)
         if b.model.outdim_src > 0:
             cnt += np.bincount(rov[im.edge_src[e] - 1], minlength=im.nv)
@@ -97,10 +99,13 @@ def halo_plan(im: IndexManager, edgebatches: Sequence[ComponentBatch], row_range
     world = len(row_ranges)
     nv = im.nv
     vowner = owner_of_rows(row_of_vertex(im), row_ranges)
-    goff = np.asarray(im.v_data, dtype=np.int64) - 1
+    if getattr(im, "homogeneous", False):
+        goff = np.arange(nv, dtype=np.int64) * int(im.vdim)
+    else:
+        goff = np.asarray(im.v_data, dtype=np.int64) - 1
     needed = np.zeros((world, nv), dtype=bool)
     for b in edgebatches:
-        e = np.asarray(b.indices, dtype=np.int64) - 1
+        e = slice(None) if b.indices is None else np.asarray(b.indices, dtype=np.int64) - 1
         s, t = np.asarray(im.edge_src)[e] - 1, np.asarray(im.edge_dst)[e] - 1
         needed[vowner[t], s] = True                   # the dst row reads the src vertex's output
         if b.model.outdim_src > 0:
@@ -168,13 +173,18 @@ class PartitionedNetwork:
     evaluate the owned rows into `du` (only the owned entries of `du` are written)."""
 
     def __init__(self, g, vertexm, edgem, *, rank: int, world: int, group=None, device=None,
-                 long_row_threshold: int = 0, exchange: str = "auto"):
+                 long_row_threshold: int = 0, exchange: str = "auto", from_edgelist: bool = False):
         """exchange: "p2p"  -- states are pushed into every rank's replica with NVLink peer stores by the engine's
         publish kernel and the RHS kernel waits on arrival flags (nd_b200_rhs_exchange; no NCCL on the data path);
         "nccl" -- torch.distributed collectives on the caller's `u`; "auto" -- p2p when the network allows it
         (all vertices StateMask) and CUDA IPC works, else nccl."""
-        # host tables first (no device work) to compute the partition
-        probe = Network(g, vertexm, edgem, execution=B200Execution(), aggregator=lambda im, eb: None)
+        # host tables first (no device work) to compute the partition.  from_edgelist (one registry vertex model, one
+        # registry edge model): nothing per component is materialised -- the partition, the halo plan and the engine are
+        # built from the bare edge list (BASELINE config 5: 5e7 vertices, 4e8 edges per graph, 8 ranks on one host)
+        if from_edgelist:
+            probe = Network.from_edgelist(g, vertexm, edgem, layout_only=True)
+        else:
+            probe = Network(g, vertexm, edgem, execution=B200Execution(), aggregator=lambda im, eb: None)
         self.rank, self.world, self.group = rank, world, group
         self.entry_counts = row_entry_counts(probe.im, probe.layer.edgebatches)
         self.row_ranges = partition_rows(self.entry_counts, world)
@@ -184,6 +194,10 @@ class PartitionedNetwork:
         self.plan = None
 
         def engine(plan):
+            if from_edgelist:
+                return Network.from_edgelist(g, vertexm, edgem, device=device, row_range=self.row_ranges[rank], keep_tables=False,
+                                             gather_offset=None if plan is None else plan["gather_offset"],
+                                             gather_len=0 if plan is None else plan["gather_len"])
             return Network(g, vertexm, edgem, execution=B200Execution(),
                            aggregator=B200Aggregator("+", device=device, row_range=self.row_ranges[rank],
                                                      long_row_threshold=long_row_threshold, keep_tables=False,

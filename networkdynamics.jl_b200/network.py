@@ -61,8 +61,10 @@ class ComponentBatch:
     in_first: int             # aggbuf (vertices) / gbuf (edges)
     out_first: int
 
+    count: int = -1           # batches described without an index array (indices=None: components 1:count)
+
     def __len__(self):
-        return int(self.indices.size)
+        return int(self.indices.size) if self.indices is not None else int(self.count)
 
 
 class IndexManager:
@@ -373,7 +375,8 @@ class Network:
 
     @classmethod
     def from_edgelist(cls, g, vertexm: VertexModel, edgem: EdgeModel, *, device: Optional[int] = None, row_range=None,
-                      keep_tables: bool = False, host_only: bool = False):
+                      keep_tables: bool = False, host_only: bool = False, gather_offset=None, gather_len: int = 0,
+                      layout_only: bool = False):
         """Homogeneous network straight from the edge list (`nd_b200_create_from_edgelist`): one registry
         vertex model, one registry edge model.  Same flat `u` / `p` layout and same engine as `Network(g, vertexm, edgem)`,
         without the per-component host tables (BASELINE config 5 has 4e8 edges: six Int64 tables would be 19 GB)."""
@@ -382,28 +385,43 @@ class Network:
         if vk is None or ek is None:
             raise ArgumentError("from_edgelist needs registry models (no CPU fallback)")
         self = cls.__new__(cls)
-        self._L = L = _cabi.lib()
+        self._L = L = None if layout_only else _cabi.lib()
         nv, ne = g.nv, g.ne
         src = np.ascontiguousarray(g.src, dtype=np.int64)
         dst = np.ascontiguousarray(g.dst, dtype=np.int64)
         osrc = edgem.outdim_src if ne else 0
         edepth = edgem.outdim_dst if ne else vertexm.outdim
-        self.im = SimpleNamespace(nv=nv, ne=ne, vdepth=vertexm.outdim, edepth=edepth,
+        self.im = SimpleNamespace(nv=nv, ne=ne, vdepth=vertexm.outdim, edepth=edepth, homogeneous=True, edge_src=src, edge_dst=dst,
+                                  vdim=vertexm.dim,
                                   lastidx_dynamic=nv * vertexm.dim, lastidx_p=nv * vertexm.pdim + ne * edgem.pdim,
                                   lastidx_out=nv * vertexm.outdim + ne * (osrc + edgem.outdim_dst), lastidx_aggr=nv * edepth)
         dev = _current_device() if device is None else device
         rr = row_range or (0, 0)
         flags = (0 if keep_tables else _cabi.FLAG_NO_EXPORT) | (_cabi.FLAG_HOST_ONLY if host_only else 0)
         h = C.c_void_p()
-        rc = L.nd_b200_create_from_edgelist(int(dev), nv, ne, src.ctypes.data_as(_cabi.i64p), dst.ctypes.data_as(_cabi.i64p),
-                                            vk, ek, edgem.coupling, int(rr[0]), int(rr[1]), flags, C.byref(h))
-        if rc != _cabi.OK:
-            msg = L.nd_b200_last_error(None).decode()
-            raise (ArgumentError if rc in (_cabi.EINVAL, _cabi.EUNSUPPORTED) else RuntimeError)(msg)
-        agg = B200Aggregator("+", device=dev, row_range=row_range, keep_tables=keep_tables, host_only=host_only)
-        agg.handle, agg.device, agg._L = h, int(dev), L
-        self.vertexbatches = []
-        self.layer = NetworkLayer(g, [], agg, edepth, vertexm.outdim)
+        go = None
+        if gather_offset is not None:           # row-partitioned engine with a packed halo (distributed.py)
+            go = np.ascontiguousarray(gather_offset, dtype=np.int64)
+            if go.size != nv:
+                raise ArgumentError("gather_offset needs one entry per vertex")
+        agg = None
+        if not layout_only:     # layout_only: sizes and batches only, no engine (what distributed.py plans the partition on)
+            rc = L.nd_b200_create_from_edgelist(int(dev), nv, ne, src.ctypes.data_as(_cabi.i64p), dst.ctypes.data_as(_cabi.i64p),
+                                                vk, ek, edgem.coupling, int(rr[0]), int(rr[1]), flags,
+                                                go.ctypes.data_as(_cabi.i64p) if go is not None else None, int(gather_len), C.byref(h))
+            if rc != _cabi.OK:
+                msg = L.nd_b200_last_error(None).decode()
+                raise (ArgumentError if rc in (_cabi.EINVAL, _cabi.EUNSUPPORTED) else RuntimeError)(msg)
+            agg = B200Aggregator("+", device=dev, row_range=row_range, keep_tables=keep_tables, host_only=host_only)
+            agg.handle, agg.device, agg._L = h, int(dev), L
+        # the one vertex batch / edge batch of the layout (what register_vertices! / register_edges! would return), without
+        # per-component index arrays: indices=None stands for 1:n
+        self.vertexbatches = [ComponentBatch("vertex", vertexm, None, 1, 1, 1, 1)]
+        ebatches = [ComponentBatch("edge", edgem, None, nv * vertexm.dim + 1, nv * vertexm.pdim + 1, 1, nv * vertexm.outdim + 1)] if ne else []
+        self.vertexbatches[0].count = nv
+        for b in ebatches:
+            b.count = ne
+        self.layer = NetworkLayer(g, ebatches, agg, edepth, vertexm.outdim)
         self.execution = B200Execution()
         return self
 
@@ -416,7 +434,8 @@ class Network:
 
     @property
     def handle(self):
-        return self.layer.aggregator.handle
+        agg = self.layer.aggregator
+        return None if agg is None else agg.handle
 
     def _fail(self, rc):
         msg = self._L.nd_b200_last_error(self.handle).decode()

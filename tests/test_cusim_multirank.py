@@ -22,17 +22,21 @@ def _ptr(a):
     return a.ctypes.data if a is not None else None
 
 
-def _run_world(nd, g, vm, em, world, ncalls, h=0.01, pack=False, rk4=None):
+def _run_world(nd, g, vm, em, world, ncalls, h=0.01, pack=False, rk4=None, edgelist=False):
     import cusim
     from networkdynamics_jl_b200 import distributed as D
     with cusim.use() as L:
-        probe = nd.Network(g, vm, em, aggregator=null_aggregator)
+        probe = nd.Network.from_edgelist(g, vm, em, layout_only=True) if edgelist else nd.Network(g, vm, em, aggregator=null_aggregator)
         rr = D.partition_rows(D.row_entry_counts(probe.im, probe.layer.edgebatches), world)
         segs = [D.state_segments(probe.vertexbatches, a, b) for a, b in rr]
         plans = [D.halo_plan(probe.im, probe.layer.edgebatches, rr, r) for r in range(world)]
-        nws = [nd.Network(g, vm, em, aggregator=nd.B200Aggregator(
-            "+", device=r, row_range=rr[r], keep_tables=False, gather_offset=plans[r]["gather_offset"],
-            gather_len=plans[r]["gather_len"])) for r in range(world)]
+        if edgelist:     # partition, halo plan and engines straight from the bare edge list (no per-component tables)
+            nws = [nd.Network.from_edgelist(g, vm, em, device=r, row_range=rr[r], gather_offset=plans[r]["gather_offset"],
+                                            gather_len=plans[r]["gather_len"]) for r in range(world)]
+        else:
+            nws = [nd.Network(g, vm, em, aggregator=nd.B200Aggregator(
+                "+", device=r, row_range=rr[r], keep_tables=False, gather_offset=plans[r]["gather_offset"],
+                gather_len=plans[r]["gather_len"])) for r in range(world)]
         comms, handles = [], []
         for r in range(world):
             c = C.c_void_p()
@@ -204,3 +208,35 @@ def test_emulated_ranks_fused_rk4(nd, monkeypatch, name, world, kernel):
         assert np.max(np.abs(out - ref)) <= 1e-12 * np.max(np.abs(ref))
     else:
         assert np.array_equal(out, ref)
+
+
+def test_partition_from_the_bare_edge_list(nd, monkeypatch):
+    """BASELINE config 5 path (5e7 vertices, 4e8 edges, 8 ranks on one host): partition, halo plan and engines built from
+    the bare edge list (`Network.from_edgelist(layout_only=True)`, `PartitionedNetwork(from_edgelist=True)`) without any
+    per-component table -- the same plan as the table-driven construction, and the same states on emulated ranks."""
+    from networkdynamics_jl_b200 import distributed as D
+    L = nd.Lib
+    dirk = nd.EdgeModel(g=nd.Directed(L.kuramoto_edge_f), outdim=1, pdim=1, name="dir_kura")
+    cases = [(nd.erdos_renyi(3000, 12000, seed=2), L.kuramoto_first(), L.kuramoto_edge()),
+             (nd.barabasi_albert(2000, 3, seed=2), L.kuramoto_second(), L.kuramoto_edge()),       # dim 2: output = first state
+             (nd.watts_strogatz(2000, 4, 0.3, seed=1, directed=True), L.diffusion_vertex(), dirk)]
+    for g, vm, em in cases:
+        a = nd.Network(g, vm, em, aggregator=null_aggregator)
+        b = nd.Network.from_edgelist(g, vm, em, layout_only=True)
+        assert (a.dim(), a.pdim()) == (b.dim(), b.pdim()) and b.handle is None
+        ca, cb = D.row_entry_counts(a.im, a.layer.edgebatches), D.row_entry_counts(b.im, b.layer.edgebatches)
+        assert np.array_equal(ca, cb)
+        for world in (2, 5):
+            rr = D.partition_rows(ca, world)
+            assert [D.state_segments(a.vertexbatches, *r) for r in rr] == [D.state_segments(b.vertexbatches, *r) for r in rr]
+            for r in range(world):
+                pa, pb = D.halo_plan(a.im, a.layer.edgebatches, rr, r), D.halo_plan(b.im, b.layer.edgebatches, rr, r)
+                assert np.array_equal(pa["gather_offset"], pb["gather_offset"]) and pa["halo_lens"] == pb["halo_lens"]
+                assert pa["sends"].keys() == pb["sends"].keys()
+                for q in pa["sends"]:
+                    assert np.array_equal(pa["sends"][q][0], pb["sends"][q][0]) and pa["sends"][q][1] == pb["sends"][q][1]
+    for kernel in ("fused", "jag"):
+        monkeypatch.setenv("ND_B200_KERNEL", kernel)
+        for g, vm, em in cases[:2]:
+            out, ref, _p, _s, _k = _run_world(nd, g, vm, em, 3, ncalls=4, edgelist=True)
+            assert np.max(np.abs(out - ref)) <= 1e-13 * np.max(np.abs(ref))

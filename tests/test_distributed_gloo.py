@@ -151,3 +151,36 @@ def _worker_uniform(rank, world, port, out_dir):
 def test_three_rank_gloo_allgather_exchange(nd, tmp_path):
     import torch.multiprocessing as mp
     mp.spawn(_worker_uniform, args=(3, _free_port(), str(tmp_path)), nprocs=3, join=True)
+
+
+def _worker_shared_graph(rank, world, port, out_dir):
+    """bench.py's shared graph generation: rank 0 generates, the others map the edge arrays from shared memory; the
+    edge-list based partition planning runs on the mapped arrays"""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    import ndb200 as nd
+    import bench
+    from networkdynamics_jl_b200 import distributed as D
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    calls = []
+
+    def make():
+        calls.append(1)
+        return nd.erdos_renyi(4000, 16000, seed=1)
+    g = bench.shared_graph(nd, make, "gloo_test", rank, world, dist.barrier)
+    ref = nd.erdos_renyi(4000, 16000, seed=1)
+    assert g.nv == ref.nv and np.array_equal(g.src, ref.src) and np.array_equal(g.dst, ref.dst)
+    assert len(calls) == (1 if rank == 0 else 0)
+    probe = nd.Network.from_edgelist(g, nd.Lib.kuramoto_first(), nd.Lib.kuramoto_edge(), layout_only=True)
+    rr = D.partition_rows(D.row_entry_counts(probe.im, probe.layer.edgebatches), world)
+    plan = D.halo_plan(probe.im, probe.layer.edgebatches, rr, rank)
+    assert plan["halo_lens"][rank] > 0 and plan["gather_len"] == probe.dim() + plan["halo_lens"][rank]
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_shared_graph_generation(nd, tmp_path):
+    import torch.multiprocessing as mp
+    mp.spawn(_worker_shared_graph, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    assert not [f for f in os.listdir("/dev/shm") if f.startswith("ndb200_gloo_test")] if os.path.isdir("/dev/shm") else True
