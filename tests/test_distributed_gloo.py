@@ -184,3 +184,51 @@ def test_two_rank_shared_graph_generation(nd, tmp_path):
     import torch.multiprocessing as mp
     mp.spawn(_worker_shared_graph, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
     assert not [f for f in os.listdir("/dev/shm") if f.startswith("ndb200_gloo_test")] if os.path.isdir("/dev/shm") else True
+
+
+def _worker_partitioned_class(rank, world, port, out_dir):
+    """the real PartitionedNetwork class (all-gather exchange over gloo) with every rank's engine running on the CPU
+    emulation of the kernels (tests/cusim): table-driven and edge-list construction, rhs, host-driven RK4"""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch
+    import torch.distributed as dist
+    import cusim
+    import ndb200 as nd
+    from networkdynamics_jl_b200.distributed import PartitionedNetwork
+    from helpers import oracle_network
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    L = nd.Lib
+    g = nd.erdos_renyi(1500, 6000, seed=5)
+    vm, em = L.kuramoto_second(), L.kuramoto_edge()
+    onw = oracle_network(g, vm, em)
+    u0 = np.random.default_rng(1).random(onw.lastidx_dynamic)
+    p = 0.5 + np.random.default_rng(2).random(onw.lastidx_p)
+    with cusim.use():
+        for from_edgelist in (False, True):
+            pn = PartitionedNetwork(g, vm, em, rank=rank, world=world, exchange="nccl", from_edgelist=from_edgelist)
+            assert pn.exchange_kind == "nccl" and pn.comm is None and (pn.dim(), pn.pdim()) == (u0.size, p.size)
+            u = torch.full((pn.dim(),), float("nan"), dtype=torch.float64)
+            for a, b in pn.owned_segments:
+                u[a:b] = torch.from_numpy(u0[a:b])
+            pt = torch.from_numpy(p)
+            du = torch.full_like(u, float("nan"))
+            pn.rhs(du, u, pt, 0.0)
+            ref = onw.rhs(u0, p)
+            for a, b in pn.owned_segments:
+                assert np.array_equal(du[a:b].numpy(), ref[a:b]), from_edgelist
+            pn.rk4(u, pt, 0.0, 1e-3, 3)
+            pn.exchange(u)
+            assert np.max(np.abs(u.numpy() - onw.rk4(u0, p, 0.0, 1e-3, 3))) <= 1e-14
+            assert not pn.comm_timed_out()
+            pn.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_partitioned_network_class_on_the_emulator(nd, tmp_path):
+    import torch.multiprocessing as mp
+    import cusim
+    cusim.build()                      # once, before the ranks race to build it
+    mp.spawn(_worker_partitioned_class, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
