@@ -378,8 +378,11 @@ def main():
     if pnw is not None:
         # N > 1: every rank keeps its inputs in pinned HOST memory; per step H2D of the rank's owned states and of the
         # parameter vector, the exchanging RHS, D2H of the owned rows of du, stream sync.  Wall clock, max over ranks.
+        assert not pnw.comm_timed_out(), "a rank timed out waiting for a peer's states"      # the timed region above is void then
+        e2e_s, owned = float("inf"), 0
         try:
             segs = pnw.owned_segments
+            owned = int(sum(b_ - a_ for a_, b_ in segs))
             hu, hp, hdu = nd.pinned_empty(nw.dim()), nd.pinned_empty(nw.pdim()), nd.pinned_empty(nw.dim())
             hu[:], hp[:] = u_h, p_h
             hu_t, hp_t, hdu_t = torch.from_numpy(hu), torch.from_numpy(hp), torch.from_numpy(hdu)
@@ -394,25 +397,28 @@ def main():
                 torch.cuda.synchronize()
             for _ in range(3):
                 e2e_step()
-            sync_all()
+            torch.cuda.synchronize()
             te = time.perf_counter()
             for _ in range(args.steps):
                 e2e_step()
             e2e_s = time.perf_counter() - te
-            tt = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            e2e_s = float(tt.item())
-            owned = int(sum(b_ - a_ for a_, b_ in segs))
+            for a_, b_ in segs[:1]:
+                assert np.array_equal(hdu[a_:b_], du[a_:b_].cpu().numpy()), "host-buffer path and device path disagree"
+            assert not pnw.comm_timed_out(), "a rank timed out waiting for a peer's states during the end-to-end leg"
+        except Exception as ex:  # the device-resident numbers above stay valid; say why the end-to-end leg is missing
+            e2e_error = repr(ex)
+        # every rank reaches this collective exactly once, whatever happened above
+        tt = torch.tensor([e2e_s if e2e_error is None else 0.0, 0.0 if e2e_error is None else 1.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        if tt[1].item() > 0:
+            e2e_error = e2e_error or "another rank failed in the end-to-end leg"
+        else:
+            e2e_s = float(tt[0].item())
             e2e = {"value": g.ne * args.steps / e2e_s, "unit": "edge-evals/s", "h2d_bytes_per_step": 8 * (owned + nw.pdim()),
                    "d2h_bytes_per_step": 8 * owned, "ms_per_step": 1e3 * e2e_s / args.steps,
                    "how": "per rank: pinned host vectors -> H2D of the rank's owned states and of p, exchanging RHS "
                           "(nd_b200_rhs_exchange / all-gather), D2H of the owned rows of du, stream sync; wall clock around "
                           "the calls, max over ranks; bytes are per rank"}
-            for a_, b_ in segs[:1]:
-                assert np.array_equal(hdu[a_:b_], du[a_:b_].cpu().numpy()), "host-buffer path and device path disagree"
-        except Exception as ex:  # the device-resident numbers above stay valid; say why the end-to-end leg is missing
-            e2e, e2e_error = None, repr(ex)
-        assert not pnw.comm_timed_out(), "a rank timed out waiting for a peer's states"
         pnw.close()
     if rank != 0:
         if dist is not None:
