@@ -115,14 +115,22 @@ def shared_graph(nd, make, tag, rank, world, barrier):
     8 ranks generating a 4e8-edge graph each would need ~20 GB and minutes of host time apiece"""
     if world == 1:
         return make()
-    base = "/dev/shm" if os.path.isdir("/dev/shm") else __import__("tempfile").gettempdir()
-    path = os.path.join(base, f"ndb200_{tag}_{os.environ.get('MASTER_PORT', '0')}")
+    import shutil
+    import tempfile
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
     if rank == 0:
         g = make()
+        if shutil.disk_usage(base).free < 2 * (g.src.nbytes + g.dst.nbytes):      # containers often cap /dev/shm at 64 MB
+            base = tempfile.gettempdir()
+    path = os.path.join(base, f"ndb200_{tag}_{os.environ.get('MASTER_PORT', '0')}")
+    alt = os.path.join(tempfile.gettempdir(), f"ndb200_{tag}_{os.environ.get('MASTER_PORT', '0')}")
+    if rank == 0:
         np.save(path + "_src.npy", g.src)
         np.save(path + "_dst.npy", g.dst)
         np.save(path + "_nv.npy", np.array([g.nv], dtype=np.int64))
     barrier()
+    if rank != 0 and not os.path.exists(path + "_nv.npy"):
+        path = alt
     if rank != 0:
         n = int(np.load(path + "_nv.npy")[0])
         g = nd.SimpleGraph(n, np.load(path + "_src.npy", mmap_mode="r"), np.load(path + "_dst.npy", mmap_mode="r"), _canonical=True)
@@ -143,7 +151,9 @@ def build_workload(nd, name, world, rank=0, barrier=None):
     if name.startswith("grid"):
         g = nd.grid_graph(1000, 1000 * mult)
     else:
-        g = shared_graph(nd, lambda: nd.erdos_renyi(nv * mult, ne * mult, seed=1), f"{name}_{mult}", rank, world if barrier else 1, barrier)
+        make = lambda: nd.erdos_renyi(nv * mult, ne * mult, seed=1)
+        # config-5 scale: generate once, map into the other ranks; smaller graphs are generated by every rank (seconds)
+        g = shared_graph(nd, make, f"{name}_{mult}", rank, world, barrier) if (barrier and nv * mult >= 10_000_000) else make()
     L = nd.Lib
     if family == "diffusion":
         return g, L.diffusion_vertex(), L.diffusion_edge(), time.time() - t0
@@ -258,8 +268,9 @@ def main():
         pnw = None
     else:
         from networkdynamics_jl_b200.distributed import PartitionedNetwork
-        # homogeneous workloads: partition, halo plan and engines from the bare edge list
-        pnw = PartitionedNetwork(g, vm, em, rank=rank, world=world, group=dist.group.WORLD, exchange=args.exchange, from_edgelist=True)
+        # config-5 scale: partition, halo plan and engines from the bare edge list (no per-component host tables)
+        pnw = PartitionedNetwork(g, vm, em, rank=rank, world=world, group=dist.group.WORLD, exchange=args.exchange,
+                                 from_edgelist=g.nv >= 10_000_000)
         nw = pnw.nw
     t_build = time.time() - t0
     sizes = nw.engine_sizes()
