@@ -66,11 +66,44 @@ def use():
         cabi._lib = prev
 
 
+class _Owner:
+    """frees a guarded allocation of the emulated library when the last view of it goes away"""
+
+    def __init__(self, L, ptr):
+        self.L, self.ptr = L, ptr
+
+    def __del__(self):
+        try:
+            self.L.nd_b200_host_free(self.ptr)
+        except Exception:
+            pass
+
+
+class _Arr(np.ndarray):
+    pass
+
+
+def _guarded(n: int) -> np.ndarray:
+    """float64 vector inside one of the emulator's guarded allocations (it ends at an inaccessible page), so that a kernel
+    reading or writing past the end of u / du / p faults at the access"""
+    L = lib()
+    n = int(n)
+    ptr = L.nd_b200_host_alloc(max(n, 1) * 8)
+    if not ptr:
+        raise MemoryError("emulated allocation failed")
+    buf = (C.c_double * max(n, 1)).from_address(ptr)
+    arr = np.frombuffer(buf, dtype=np.float64, count=max(n, 1))[:n].view(_Arr)
+    arr._owner = _Owner(L, ptr)
+    return arr
+
+
 class DeviceArray:
-    """a numpy vector presented as device memory (`__cuda_array_interface__`) to the emulated engine"""
+    """a float64 vector presented as device memory (`__cuda_array_interface__`) to the emulated engine"""
 
     def __init__(self, a):
-        self.a = np.ascontiguousarray(a, dtype=np.float64)
+        a = np.asarray(a, dtype=np.float64).ravel()
+        self.a = _guarded(a.size)
+        self.a[:] = a
 
     @property
     def __cuda_array_interface__(self):
@@ -81,7 +114,7 @@ class DeviceArray:
 
 
 def dev(a) -> DeviceArray:
-    return DeviceArray(np.array(a, dtype=np.float64, copy=True))
+    return DeviceArray(a)
 
 
 def empty(n) -> DeviceArray:

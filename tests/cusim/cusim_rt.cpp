@@ -269,16 +269,49 @@ cudaError_t cudaGetLastError() {
 }
 cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 cudaError_t cudaDeviceSynchronize() { cusim::drain_all(); return cusim::g_failed.load() ? cudaErrorLaunchFailure : cudaSuccess; }
+// Device allocations end at an inaccessible guard page (and start right after one), so a kernel that reads or writes past
+// the end of a table -- or before its start -- faults at the offending access instead of silently touching a neighbour
+// allocation (the emulator's memcheck).  The start keeps the 16-byte alignment vector loads need.
+namespace {
+struct GuardedBlock { void* base; size_t total; };
+std::mutex g_alloc_mutex;
+std::vector<std::pair<void*, GuardedBlock>> g_allocs;
+const size_t kPage = (size_t)sysconf(_SC_PAGESIZE);
+}  // namespace
 cudaError_t cudaMalloc(void** p, size_t bytes) {
-  void* q = nullptr;
-  if (posix_memalign(&q, 256, bytes ? bytes : 8)) return cudaErrorMemoryAllocation;
-  memset(q, 0xCD, bytes ? bytes : 8);   // device memory is not zero-initialised: make reads of unwritten memory visible
+  if (bytes == 0) bytes = 8;
+  const size_t payload = (bytes + 15) / 16 * 16;
+  const size_t body = (payload + kPage - 1) / kPage * kPage;
+  const size_t total = body + 2 * kPage;
+  char* base = (char*)mmap(nullptr, total, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+  if (base == (char*)MAP_FAILED) return cudaErrorMemoryAllocation;
+  mprotect(base, kPage, PROT_NONE);
+  mprotect(base + kPage + body, kPage, PROT_NONE);
+  char* q = base + kPage + body - payload;     // the payload ends exactly at the trailing guard page
+  memset(q, 0xCD, payload);                    // device memory is not zero-initialised: make reads of unwritten memory visible
+  {
+    std::lock_guard<std::mutex> lk(g_alloc_mutex);
+    g_allocs.push_back({q, GuardedBlock{base, total}});
+  }
   *p = q;
   return cudaSuccess;
 }
-cudaError_t cudaFree(void* p) { if (p) cusim::drain_all(); free(p); return cudaSuccess; }   // cudaFree synchronises the device
+cudaError_t cudaFree(void* p) {      // cudaFree synchronises the device
+  if (!p) return cudaSuccess;
+  cusim::drain_all();
+  std::lock_guard<std::mutex> lk(g_alloc_mutex);
+  for (size_t i = 0; i < g_allocs.size(); ++i)
+    if (g_allocs[i].first == p) {
+      munmap(g_allocs[i].second.base, g_allocs[i].second.total);
+      g_allocs[i] = g_allocs.back();
+      g_allocs.pop_back();
+      return cudaSuccess;
+    }
+  cusim::set_error("cudaFree of a pointer that cudaMalloc did not return");
+  return cudaErrorInvalidValue;
+}
 cudaError_t cudaHostAlloc(void** p, size_t bytes, unsigned) { return cudaMalloc(p, bytes); }
-cudaError_t cudaFreeHost(void* p) { if (p) cusim::drain_all(); free(p); return cudaSuccess; }
+cudaError_t cudaFreeHost(void* p) { return cudaFree(p); }
 // synchronous copies run on the legacy default stream: they do not wait for non-blocking streams
 cudaError_t cudaMemcpy(void* dst, const void* src, size_t n, cudaMemcpyKind) { memmove(dst, src, n); return cudaSuccess; }
 cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t n, cudaMemcpyKind, cudaStream_t st) {
