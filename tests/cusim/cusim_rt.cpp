@@ -112,7 +112,15 @@ bool run_block(int n) {
   P.in_kernel = true;
   char msg[256];
   for (;;) {
-    for (int t = 0; t < n; ++t) {
+    // Between two scheduling points the threads of a block run one after the other; the ORDER is a free choice on real
+    // hardware, so results must not depend on it.  CUSIM_ORDER=reverse|shuffle runs them in another order: a missing
+    // __syncthreads / __syncwarp between a shared-memory (or global) write and a read by another thread then changes
+    // the result (the emulator's racecheck).
+    static const int order_mode = [] { const char* s = getenv("CUSIM_ORDER"); return !s ? 0 : (!strcmp(s, "reverse") ? 1 : (!strcmp(s, "shuffle") ? 2 : 0)); }();
+    static thread_local unsigned long long lcg = 0x9E3779B97F4A7C15ull;
+    const int rot = order_mode == 2 ? (int)((lcg = lcg * 6364136223846793005ull + 1442695040888963407ull) >> 33) % n : 0;
+    for (int i = 0; i < n; ++i) {
+      const int t = order_mode == 1 ? n - 1 - i : (order_mode == 2 ? (int)(((long long)i * 61 + rot) % n) : i);   // 61 is coprime to every block size used
       if (P.f[(size_t)t].state != ST_READY) continue;
       P.cur = t;
       ctx.tid = dim3((unsigned)t);

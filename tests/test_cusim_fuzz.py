@@ -338,3 +338,22 @@ def test_fuzz_user_supplied_kinds(nd, monkeypatch, seed):
         o, agg = cusim.empty(nw.im.lastidx_out), cusim.empty(nw.im.lastidx_aggr)
         nw.get_buffers(o, agg, cusim.dev(u), pd, 0.4)
         assert floored_rel_err(agg.numpy(), agg_ref) <= 1e-12 and floored_rel_err(o.numpy(), o_ref) <= 1e-12, seed
+
+
+@pytest.mark.parametrize("order,select", [("reverse", "dq_networks or registry_networks"),
+                                          ("shuffle", "rhs_matches_sequential_oracle or edge_cases")])
+def test_results_do_not_depend_on_thread_order(order, select):
+    """the emulator's racecheck: between two barriers / warp collectives the threads of a block may run in any order on real
+    hardware.  Re-run the single-engine fuzz (reverse order) and the fixed tile / jagged / split parity cases (shuffled order)
+    in a fresh process -- a missing __syncthreads between a shared-memory write and another thread's read would change a
+    result.  (The whole suite has been run once in both orders.)"""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, CUSIM_ORDER=order)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "pytest", "-x", "-q", "-m", "not gpu", "-p", "no:cacheprovider",
+           os.path.join(root, "tests", "test_cusim_fuzz.py"), os.path.join(root, "tests", "test_gpu_parity.py"),
+           "-k", f"({select}) and not thread_order"]
+    r = subprocess.run(cmd, env=env, cwd=root, capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
