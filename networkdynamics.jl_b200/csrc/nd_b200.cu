@@ -543,6 +543,9 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
   if (d->n_vbatches <= 0 || d->n_vbatches > MAX_VB) return fail(e, ND_B200_EUNSUPPORTED, "number of vertex batches %d outside 1..%d", d->n_vbatches, MAX_VB);
   if (d->n_ebatches < 0 || d->n_ebatches > MAX_EB) return fail(e, ND_B200_EUNSUPPORTED, "number of edge batches %d outside 0..%d", d->n_ebatches, MAX_EB);
   if (d->ne > 0 && d->n_ebatches == 0) return fail(e, ND_B200_EINVAL, "edges without edge batches");
+  if (d->ne < 0 || !d->vbatches || (d->n_ebatches > 0 && !d->ebatches) || (d->ne > 0 && (!d->edge_src || !d->edge_dst)))
+    return fail(e, ND_B200_EINVAL, "descriptor with missing tables");
+  if (d->vdepth < 1 || (d->ne > 0 && d->edepth < 1)) return fail(e, ND_B200_EINVAL, "vdepth / edepth must be positive");
   e->device = d->device;
   e->nv = d->nv; e->ne = d->ne; e->vdepth = d->vdepth; e->edepth = d->ne > 0 ? d->edepth : d->vdepth;
   e->lastidx_dynamic = d->lastidx_dynamic; e->lastidx_p = d->lastidx_p;
@@ -567,7 +570,7 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
 
   // ---- vertex batches: registry check, contiguity of rows/states (register_vertices!) ----------
   std::vector<int> row_of_vertex((size_t)d->nv, -1);
-  long long row = 0, state_expect = 1, out_expect = 1;
+  long long row = 0, state_expect = 1, out_expect = 1, p_expect = 1;
   const int ed = d->ne > 0 ? d->edepth : 0;
   bool all_statemask1 = true;
   for (int b = 0; b < d->n_vbatches; ++b) {
@@ -575,9 +578,11 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
     std::string why;
     if (!vertex_kind_ok(e, vb, why)) return fail(e, ND_B200_EUNSUPPORTED, "%s (no CPU fallback)", why.c_str());
     if (vb.outdim != d->vdepth) return fail(e, ND_B200_EINVAL, "vertex batch %d outdim %d != vdepth %d", b + 1, vb.outdim, d->vdepth);
-    if (vb.count <= 0 || (!vb.indices && d->n_vbatches != 1)) return fail(e, ND_B200_EINVAL, "vertex batch %d is empty", b + 1);
+    if (vb.count <= 0 || vb.count > d->nv || (!vb.indices && d->n_vbatches != 1)) return fail(e, ND_B200_EINVAL, "vertex batch %d is empty or larger than the graph", b + 1);
     if (vb.state_first != state_expect) return fail(e, ND_B200_EINVAL, "vertex batch %d: statestride.first %lld, expected %lld", b + 1, (long long)vb.state_first, state_expect);
     if (vb.out_first != out_expect) return fail(e, ND_B200_EINVAL, "vertex batch %d: outbufstride.first %lld, expected %lld", b + 1, (long long)vb.out_first, out_expect);
+    if (vb.dim < 0 || vb.pdim < 0) return fail(e, ND_B200_EINVAL, "vertex batch %d: negative dimension", b + 1);
+    if (vb.pdim > 0 && vb.p_first != p_expect) return fail(e, ND_B200_EINVAL, "vertex batch %d: pstride.first %lld, expected %lld", b + 1, (long long)vb.p_first, p_expect);
     if (ed > 0 && vb.aggr_first != row * ed + 1) return fail(e, ND_B200_EINVAL, "vertex batch %d: inbufstride.first %lld, expected %lld", b + 1, (long long)vb.aggr_first, row * ed + 1);
     HostVB h{vb.kind, vb.dim, vb.pdim, vb.outdim, vb.count, vb.state_first - 1, vb.p_first - 1, vb.out_first - 1, row};
     e->hvb.push_back(h);
@@ -586,7 +591,7 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
       if (vid < 1 || vid > d->nv || row_of_vertex[(size_t)vid - 1] >= 0) return fail(e, ND_B200_EINVAL, "vertex batch %d: bad or duplicate vertex id %lld", b + 1, vid);
       row_of_vertex[(size_t)vid - 1] = (int)(row + i);
     }
-    row += vb.count; state_expect += vb.count * vb.dim; out_expect += vb.count * vb.outdim;
+    row += vb.count; state_expect += vb.count * vb.dim; out_expect += vb.count * vb.outdim; p_expect += vb.count * vb.pdim;
     if (vb.kind == ND_B200_V_SWING_DQ) all_statemask1 = false;
     if (vb.kind >= ND_B200_CUSTOM_KIND_BASE && !find_custom(e, vb.kind, 0)->g_body.empty()) all_statemask1 = false;
     if (vb.dim > (e->custom ? 16 : 2)) return fail(e, ND_B200_EUNSUPPORTED, "vertex batch %d: dim %d", b + 1, vb.dim);
@@ -653,7 +658,10 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
     const int osrc_expect = eb.coupling == ND_B200_DIRECTED ? 0 : eb.outdim_dst;
     if (eb.outdim_src != osrc_expect) return fail(e, ND_B200_EINVAL, "edge batch %d: outdim.src %d inconsistent with wrapper", b + 1, eb.outdim_src);
     if (eb.out_first != eout_expect) return fail(e, ND_B200_EINVAL, "edge batch %d: outbufstride.first %lld, expected %lld", b + 1, (long long)eb.out_first, eout_expect);
-    if (eb.count <= 0 || (!eb.indices && d->n_ebatches != 1)) return fail(e, ND_B200_EINVAL, "edge batch %d is empty", b + 1);
+    if (eb.pdim < 0 || eb.pdim > 64) return fail(e, ND_B200_EINVAL, "edge batch %d: pdim %d", b + 1, eb.pdim);
+    if (eb.pdim > 0 && eb.p_first != p_expect) return fail(e, ND_B200_EINVAL, "edge batch %d: pstride.first %lld, expected %lld", b + 1, (long long)eb.p_first, p_expect);
+    p_expect += eb.count * eb.pdim;
+    if (eb.count <= 0 || eb.count > d->ne || (!eb.indices && d->n_ebatches != 1)) return fail(e, ND_B200_EINVAL, "edge batch %d is empty or larger than the graph", b + 1);
     HostEB h{eb.kind, eb.coupling, eb.dim, eb.pdim, eb.outdim_src, eb.outdim_dst, eb.count, eb.p_first - 1, eb.out_first - 1,
              eb.state_first - 1, eb.dim > 0 ? eb.mask_src_first - 1 : 0, eb.dim > 0 ? eb.mask_dst_first - 1 : 0};
     e->heb.push_back(h);
@@ -667,6 +675,7 @@ int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
   }
   if (eout_expect - 1 != d->lastidx_out) return fail(e, ND_B200_EINVAL, "lastidx_out %lld inconsistent with batches (%lld)", (long long)d->lastidx_out, eout_expect - 1);
   if (state_expect - 1 != d->lastidx_dynamic) return fail(e, ND_B200_EINVAL, "lastidx_dynamic %lld inconsistent with the batches (%lld)", (long long)d->lastidx_dynamic, state_expect - 1);
+  if (p_expect - 1 != d->lastidx_p) return fail(e, ND_B200_EINVAL, "lastidx_p %lld inconsistent with the batches (%lld)", (long long)d->lastidx_p, p_expect - 1);
   e->ek = (d->n_ebatches == 1 && !any_ode) ? d->ebatches[0].kind : EK_GENERIC;   // entries of edges with states: generic kernels only
   // precompiled specialisations exist for the benchmark edge kinds; every other registry kind runs in the generic kernels
   if (!e->custom && d->vdepth == 1 && e->ek != ND_B200_E_DIFFUSION && e->ek != ND_B200_E_DIFFUSION_NOP && e->ek != ND_B200_E_KURAMOTO) e->ek = EK_GENERIC;

@@ -269,6 +269,8 @@ class B200Aggregator:
             keep.append(go)
             desc.gather_offset = go.ctypes.data_as(_cabi.i64p)
             desc.gather_len = int(self._opts["gather_len"])
+        keep += [vb, eb, src, dst]
+        self._desc, self._keep = desc, keep          # kept alive with the engine (tests mutate copies of it)
         h = C.c_void_p()
         rc = L.nd_b200_create(C.byref(desc), C.byref(h))
         if rc != _cabi.OK:

@@ -106,3 +106,95 @@ def test_create_from_edgelist_builds_the_same_engine(nd, monkeypatch):
     with pytest.raises(nd.ArgumentError):      # user-supplied kinds go through the table-driven constructor
         nd.Network.from_edgelist(cases[0][0], nd.VertexModel(f=nd.CudaFunction("f", "vertex_f", "dv[0]=0;"), g=nd.StateMask((1,)), dim=1),
                                  L.kuramoto_edge(), host_only=True)
+
+
+def test_create_rejects_inconsistent_descriptors(nd):
+    """nd_b200_create validates that the descriptor describes the layout register_vertices! / register_edges! produce
+    (src/network_structure.jl:224-258); every single-field corruption of a valid descriptor is refused with a status code
+    and a message -- no crash, no engine (host-only build of the real library: no GPU needed)."""
+    import copy
+    import ctypes as C
+    cabi = nd._cabi
+    L = nd.Lib
+    rng = np.random.default_rng(5)
+    g = nd.barabasi_albert(300, 3, seed=1)
+    vm = ([L.kuramoto_first(), L.kuramoto_second()], rng.integers(0, 2, g.nv))
+    em = ([L.kuramoto_edge(), L.diffusion_edge_nop(), L.diffusion_odeedge()], rng.integers(0, 3, g.ne))
+    nw = nd.Network(g, vm, em, aggregator=nd.B200Aggregator("+", host_only=True))
+    agg = nw.layer.aggregator
+    lib = cabi.lib()
+
+    def create(desc):
+        h = C.c_void_p()
+        rc = lib.nd_b200_create(C.byref(desc), C.byref(h))
+        if rc == cabi.OK:
+            lib.nd_b200_destroy(h)
+        else:
+            assert not h.value and lib.nd_b200_last_error(None), "a refusal carries a message and no engine"
+        return rc
+
+    def clone():
+        d = cabi.Desc.from_buffer_copy(agg._desc)
+        vb = (cabi.VBatch * d.n_vbatches).from_buffer_copy((cabi.VBatch * d.n_vbatches).from_address(C.addressof(d.vbatches.contents)))
+        eb = (cabi.EBatch * d.n_ebatches).from_buffer_copy((cabi.EBatch * d.n_ebatches).from_address(C.addressof(d.ebatches.contents)))
+        d.vbatches, d.ebatches = vb, eb
+        return d, vb, eb
+
+    d, _, _ = clone()
+    assert create(d) == cabi.OK                                 # the untouched copy is fine
+    top = ["abi_version", "nv", "ne", "vdepth", "edepth", "n_vbatches", "n_ebatches", "lastidx_dynamic", "lastidx_p", "lastidx_out"]
+    refused = 0
+    for name in top:
+        for delta in (1, -1, 1000):
+            d, _, _ = clone()
+            setattr(d, name, getattr(d, name) + delta)
+            if name in ("n_vbatches", "n_ebatches", "nv", "ne") and delta > 0:
+                continue                                        # would make the engine read past the caller's arrays
+            assert create(d) in (cabi.EINVAL, cabi.EUNSUPPORTED), (name, delta)
+            refused += 1
+    for k in range(2):
+        for name in ("kind", "dim", "pdim", "outdim", "count", "state_first", "p_first", "out_first", "aggr_first"):
+            d, vb, _ = clone()
+            delta = -1 if name == "count" else 1
+            setattr(vb[k], name, getattr(vb[k], name) + delta)
+            if name == "kind" and k == 0:
+                setattr(vb[k], name, 77)
+            rc = create(d)
+            if name == "p_first" and vb[k].pdim == 0:
+                continue
+            assert rc in (cabi.EINVAL, cabi.EUNSUPPORTED), ("vbatch", k, name)
+            refused += 1
+    for k in range(3):
+        for name in ("kind", "coupling", "dim", "pdim", "outdim_src", "outdim_dst", "count", "state_first", "p_first", "out_first",
+                     "mask_src_first", "mask_dst_first"):
+            d, _, eb = clone()
+            old = getattr(eb[k], name)
+            setattr(eb[k], name, old - 1 if name == "count" else (9 if name == "coupling" else old + (5 if name.startswith("mask") else 1)))
+            rc = create(d)
+            irrelevant = (name == "p_first" and eb[k].pdim == 0) or (name == "state_first" and eb[k].dim == 0) or \
+                         (name.startswith("mask") and eb[k].dim == 0) or (name == "mask_src_first" and eb[k].coupling != cabi.FIDUCIAL)
+            if irrelevant:
+                continue
+            assert rc in (cabi.EINVAL, cabi.EUNSUPPORTED), ("ebatch", k, name)
+            refused += 1
+    # null tables, duplicated / out-of-range component ids, edges with bad endpoints
+    for field in ("vbatches", "ebatches", "edge_src", "edge_dst"):
+        d, _, _ = clone()
+        setattr(d, field, None)
+        assert create(d) == cabi.EINVAL, field
+    d, vb, _ = clone()
+    idx = np.ctypeslib.as_array(vb[0].indices, shape=(vb[0].count,)).copy()
+    idx[1] = idx[0]
+    vb[0].indices = idx.ctypes.data_as(cabi.i64p)
+    assert create(d) == cabi.EINVAL
+    d, _, eb = clone()
+    idx = np.ctypeslib.as_array(eb[0].indices, shape=(eb[0].count,)).copy()
+    idx[-1] = g.ne + 5
+    eb[0].indices = idx.ctypes.data_as(cabi.i64p)
+    assert create(d) == cabi.EINVAL
+    d, _, _ = clone()
+    bad = np.ascontiguousarray(g.src).copy()
+    bad[3] = g.nv + 1
+    d.edge_src = bad.ctypes.data_as(cabi.i64p)
+    assert create(d) == cabi.EINVAL
+    assert refused > 60
