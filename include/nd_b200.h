@@ -179,8 +179,9 @@ int nd_b200_rhs_host(nd_b200_engine*, double* du_host, const double* u_host, con
  * per entry.  The caller guarantees that the EDGE parameters in p do not change until the next nd_b200_pack_params;
  * vertex parameters are still read from p on every call.  p == NULL returns to reading p on every call (the default, the
  * reference's semantics: callbacks may mutate p between calls).  Available for networks with ONE registry edge batch
- * that has parameters, default launch shape; ND_B200_EUNSUPPORTED otherwise.  nd_b200_rk4 can do this by itself for the
- * duration of a call (p is constant there): environment ND_B200_RK4_PACK=1. */
+ * that has parameters, default launch shape; ND_B200_EUNSUPPORTED otherwise.  nd_b200_rk4 does this by itself for the
+ * duration of a call (p is constant there) when p exceeds 256 MB and the call takes >= 4 steps; environment
+ * ND_B200_RK4_PACK=1 / 0 forces / forbids it. */
 int nd_b200_pack_params(nd_b200_engine*, const double* p, void* stream);
 
 /* Replaces `get_buffers(nw,u,p,t)` = RET=Val(:buf_init) (src/coreloop.jl:33-36,92-94,103-109):

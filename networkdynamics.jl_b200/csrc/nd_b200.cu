@@ -1480,12 +1480,15 @@ int nd_b200_rk4(nd_b200_engine* e, double* u, const double* p, double t0, double
     CUDA_TRY(e, cudaMalloc((void**)&e->d_tmpB, nb));
     CUDA_TRY(e, cudaMalloc((void**)&e->d_ksum, nb));
   }
-  // p is constant for the whole call: with ND_B200_RK4_PACK=1 the edge parameters are packed once into entry order and
-  // every stage reads them coalesced (contract-free; off by default until measured on every config)
+  // p is constant for the whole call: the edge parameters can be packed once into entry order so that every stage reads
+  // them coalesced (contract-free).  ND_B200_RK4_PACK=1 / 0 forces / forbids it.
   struct Unpack { nd_b200_engine* e; bool on; ~Unpack() { if (on) e->pack_on = false; } } unpack{e, false};
   if (!e->pack_on && e->pack_pe > 0) {
+    // default: only where the gain does not depend on a measurement -- a parameter vector far beyond the 126 MB L2, whose
+    // per-entry reads are isolated DRAM sectors, and enough stages to amortise the one packing pass
     const char* s = getenv("ND_B200_RK4_PACK");
-    if (s && atoi(s) > 0 && nd_b200_pack_params(e, p, stream) == ND_B200_OK) unpack.on = true;
+    const bool want = s ? atoi(s) > 0 : (sizeof(double) * (size_t)e->lastidx_p >= ((size_t)256 << 20) && nsteps >= 4);
+    if (want && nd_b200_pack_params(e, p, stream) == ND_B200_OK) unpack.on = true;
   }
   if (!e->gather_from_u) CUDA_TRY(e, launch_vout(e, u, p, e->d_vout[0], st));
   // The registry models are autonomous, so one captured step can be replayed for every t.  User-supplied kinds may read
