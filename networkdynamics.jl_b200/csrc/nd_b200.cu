@@ -537,584 +537,647 @@ int compile_custom(nd_b200_engine* e, int vdepth, int edepth) {
   return ND_B200_OK;
 }
 
-int build_engine(nd_b200_engine* e, const nd_b200_desc* d) {
-  if (d->abi_version != ND_B200_ABI_VERSION) return fail(e, ND_B200_EINVAL, "descriptor abi_version %d != %d", d->abi_version, ND_B200_ABI_VERSION);
-  if (d->nv <= 0) return fail(e, ND_B200_EINVAL, "network needs at least one vertex");
-  if (d->n_vbatches <= 0 || d->n_vbatches > MAX_VB) return fail(e, ND_B200_EUNSUPPORTED, "number of vertex batches %d outside 1..%d", d->n_vbatches, MAX_VB);
-  if (d->n_ebatches < 0 || d->n_ebatches > MAX_EB) return fail(e, ND_B200_EUNSUPPORTED, "number of edge batches %d outside 0..%d", d->n_ebatches, MAX_EB);
-  if (d->ne > 0 && d->n_ebatches == 0) return fail(e, ND_B200_EINVAL, "edges without edge batches");
-  if (d->ne < 0 || !d->vbatches || (d->n_ebatches > 0 && !d->ebatches) || (d->ne > 0 && (!d->edge_src || !d->edge_dst)))
-    return fail(e, ND_B200_EINVAL, "descriptor with missing tables");
-  if (d->vdepth < 1 || (d->ne > 0 && d->edepth < 1)) return fail(e, ND_B200_EINVAL, "vdepth / edepth must be positive");
-  e->device = d->device;
-  e->nv = d->nv; e->ne = d->ne; e->vdepth = d->vdepth; e->edepth = d->ne > 0 ? d->edepth : d->vdepth;
-  e->lastidx_dynamic = d->lastidx_dynamic; e->lastidx_p = d->lastidx_p;
-  e->lastidx_out = d->lastidx_out; e->lastidx_aggr = d->lastidx_aggr;
-  if (d->n_custom < 0 || (d->n_custom > 0 && !d->custom)) return fail(e, ND_B200_EINVAL, "bad custom kind table");
-  for (int k = 0; k < d->n_custom; ++k) {
-    const nd_b200_custom_kind& c = d->custom[k];
-    if (c.kind < ND_B200_CUSTOM_KIND_BASE || (c.role != 0 && c.role != 1) || !c.f_body) return fail(e, ND_B200_EINVAL, "custom kind %d: id must be >= %d, role 0|1, f_body non-NULL", c.kind, ND_B200_CUSTOM_KIND_BASE);
-    if (c.dim < 0 || c.dim > 16 || c.pdim < 0 || c.pdim > 64 || c.outdim < 1 || c.outdim > 8) return fail(e, ND_B200_EUNSUPPORTED, "custom kind %d: dims outside dim<=16, pdim<=64, 1<=outdim<=8", c.kind);
-    if (c.role == 1) e->c_maxedim = std::max(e->c_maxedim, c.dim);
-    e->customs.push_back(nd_b200_engine::CustomKind{c.kind, c.role, c.dim, c.pdim, c.outdim, c.two_sided, c.f_body, c.g_body ? c.g_body : ""});
-  }
-  for (int b = 0; b < d->n_vbatches; ++b) e->custom = e->custom || d->vbatches[b].kind >= ND_B200_CUSTOM_KIND_BASE;
-  for (int b = 0; b < d->n_ebatches; ++b) e->custom = e->custom || d->ebatches[b].kind >= ND_B200_CUSTOM_KIND_BASE;
-  if (!e->custom && !((d->vdepth == 1 && (d->ne == 0 || d->edepth == 1)) || (d->vdepth == 2 && d->edepth == 2)))
-    return fail(e, ND_B200_EUNSUPPORTED, "no precompiled kernel for (vdepth,edepth)=(%d,%d); available: (1,1),(2,2) -- other shapes need user-supplied kinds", d->vdepth, d->edepth);
-  if (e->custom && (d->vdepth < 1 || d->vdepth > 8 || (d->ne > 0 && (d->edepth < 1 || d->edepth > 8))))
-    return fail(e, ND_B200_EUNSUPPORTED, "(vdepth,edepth)=(%d,%d) outside 1..8", d->vdepth, d->edepth);
-  if (d->lastidx_dynamic >= INT_MAX || d->lastidx_p >= INT_MAX || d->lastidx_out >= (long long)INT_MAX * 2)
-    return fail(e, ND_B200_EUNSUPPORTED, "network too large for 32-bit offsets");
-  e->long_thr = d->long_row_threshold > 0 ? d->long_row_threshold : 128;
-
-  // ---- vertex batches: registry check, contiguity of rows/states (register_vertices!) ----------
-  std::vector<int> row_of_vertex((size_t)d->nv, -1);
-  long long row = 0, state_expect = 1, out_expect = 1, p_expect = 1;
-  const int ed = d->ne > 0 ? d->edepth : 0;
-  bool all_statemask1 = true;
-  for (int b = 0; b < d->n_vbatches; ++b) {
-    const nd_b200_vbatch& vb = d->vbatches[b];
-    std::string why;
-    if (!vertex_kind_ok(e, vb, why)) return fail(e, ND_B200_EUNSUPPORTED, "%s (no CPU fallback)", why.c_str());
-    if (vb.outdim != d->vdepth) return fail(e, ND_B200_EINVAL, "vertex batch %d outdim %d != vdepth %d", b + 1, vb.outdim, d->vdepth);
-    if (vb.count <= 0 || vb.count > d->nv || (!vb.indices && d->n_vbatches != 1)) return fail(e, ND_B200_EINVAL, "vertex batch %d is empty or larger than the graph", b + 1);
-    if (vb.state_first != state_expect) return fail(e, ND_B200_EINVAL, "vertex batch %d: statestride.first %lld, expected %lld", b + 1, (long long)vb.state_first, state_expect);
-    if (vb.out_first != out_expect) return fail(e, ND_B200_EINVAL, "vertex batch %d: outbufstride.first %lld, expected %lld", b + 1, (long long)vb.out_first, out_expect);
-    if (vb.dim < 0 || vb.pdim < 0) return fail(e, ND_B200_EINVAL, "vertex batch %d: negative dimension", b + 1);
-    if (vb.pdim > 0 && vb.p_first != p_expect) return fail(e, ND_B200_EINVAL, "vertex batch %d: pstride.first %lld, expected %lld", b + 1, (long long)vb.p_first, p_expect);
-    if (ed > 0 && vb.aggr_first != row * ed + 1) return fail(e, ND_B200_EINVAL, "vertex batch %d: inbufstride.first %lld, expected %lld", b + 1, (long long)vb.aggr_first, row * ed + 1);
-    HostVB h{vb.kind, vb.dim, vb.pdim, vb.outdim, vb.count, vb.state_first - 1, vb.p_first - 1, vb.out_first - 1, row};
-    e->hvb.push_back(h);
-    for (long long i = 0; i < vb.count; ++i) {
-      long long vid = vb.indices ? vb.indices[i] : i + 1;
-      if (vid < 1 || vid > d->nv || row_of_vertex[(size_t)vid - 1] >= 0) return fail(e, ND_B200_EINVAL, "vertex batch %d: bad or duplicate vertex id %lld", b + 1, vid);
-      row_of_vertex[(size_t)vid - 1] = (int)(row + i);
-    }
-    row += vb.count; state_expect += vb.count * vb.dim; out_expect += vb.count * vb.outdim; p_expect += vb.count * vb.pdim;
-    if (vb.kind == ND_B200_V_SWING_DQ) all_statemask1 = false;
-    if (vb.kind >= ND_B200_CUSTOM_KIND_BASE && !find_custom(e, vb.kind, 0)->g_body.empty()) all_statemask1 = false;
-    if (vb.dim > (e->custom ? 16 : 2)) return fail(e, ND_B200_EUNSUPPORTED, "vertex batch %d: dim %d", b + 1, vb.dim);
-    e->c_maxdim = std::max(e->c_maxdim, vb.dim);
-  }
-  if (row != d->nv) return fail(e, ND_B200_EINVAL, "vertex batches cover %lld of %lld vertices", row, (long long)d->nv);
-  e->nrows_total = row;
-  e->gather_from_u = (all_statemask1 && d->vdepth == 1) ? 1 : 0;
-
-  e->row_begin = 0; e->row_end = e->nrows_total;
-  if (d->row_end > 0) {
-    if (d->row_begin < 0 || d->row_begin > d->row_end || d->row_end > e->nrows_total) return fail(e, ND_B200_EINVAL, "row partition [%lld,%lld) outside 0..%lld", (long long)d->row_begin, (long long)d->row_end, e->nrows_total);
-    e->row_begin = d->row_begin; e->row_end = d->row_end;
-  }
-  const long long nrows_owned = e->row_end - e->row_begin;
-
-  // gather offset of a vertex's output inside the gather source
-  std::vector<int> goff((size_t)d->nv);
-  for (int b = 0; b < d->n_vbatches; ++b) {
-    const HostVB& h = e->hvb[b];
-    for (long long i = 0; i < h.count; ++i) {
-      long long vid = d->vbatches[b].indices ? d->vbatches[b].indices[i] : i + 1;
-      goff[(size_t)vid - 1] = e->gather_from_u ? (int)(h.state0 + i * h.dim) : (int)((h.row0 + i) * d->vdepth);
-    }
-  }
-  if (d->gather_offset) {
-    // multi-GPU packed halo: remote vertices are read from the halo buffer appended (logically) to the state vector
-    if (!e->gather_from_u) return fail(e, ND_B200_EUNSUPPORTED, "gather_offset needs StateMask vertices with one output");
-    if (d->gather_len < d->lastidx_dynamic || d->gather_len >= INT_MAX) return fail(e, ND_B200_EINVAL, "gather_len %lld outside [lastidx_dynamic, 2^31)", (long long)d->gather_len);
-    for (long long v = 0; v < d->nv; ++v) {
-      const long long o = d->gather_offset[v];
-      if (o < 0 || o >= d->gather_len) return fail(e, ND_B200_EINVAL, "gather_offset[%lld] = %lld outside [0, %lld)", v + 1, o, (long long)d->gather_len);
-      const int r = row_of_vertex[(size_t)v];
-      if (r >= e->row_begin && r < e->row_end && o != goff[(size_t)v]) return fail(e, ND_B200_EINVAL, "gather_offset of vertex %lld (an owned row) must be its own state offset", v + 1);
-      goff[(size_t)v] = (int)o;
-    }
-    e->halo_base = (int)d->lastidx_dynamic;
-    e->gather_len = d->gather_len;
-  }
-
-  // ---- edge batches --------------------------------------------------------------------------
-  bool any_epar = false, any_ode = false;
-  long long eout_expect = out_expect;
-  std::vector<char> edge_seen((size_t)std::max<long long>(d->ne, 1), 0);
-  for (int b = 0; b < d->n_ebatches; ++b) {
-    const nd_b200_ebatch& eb = d->ebatches[b];
-    std::string why;
-    if (!edge_kind_ok(e, eb, d->vdepth, why)) return fail(e, ND_B200_EUNSUPPORTED, "%s (no CPU fallback)", why.c_str());
-    if (eb.outdim_dst != d->edepth) return fail(e, ND_B200_EINVAL, "edge batch %d: outdim.dst %d != edepth %d", b + 1, eb.outdim_dst, d->edepth);
-    e->c_pe = std::max(e->c_pe, eb.pdim);
-    if (eb.dim < 0 || eb.dim > (e->custom ? 16 : 2)) return fail(e, ND_B200_EUNSUPPORTED, "edge batch %d: dim %d", b + 1, eb.dim);
-    if (eb.dim > 0) {
-      // edges with states: outputs are StateMasks over a contiguous range of the edge's own states
-      if (d->row_end > 0 && (d->row_begin != 0 || d->row_end != e->nrows_total)) return fail(e, ND_B200_EUNSUPPORTED, "edges with states on a row-partitioned engine");
-      if (d->gather_offset) return fail(e, ND_B200_EUNSUPPORTED, "edges with states on a halo engine");
-      if (eb.state_first != state_expect) return fail(e, ND_B200_EINVAL, "edge batch %d: statestride.first %lld, expected %lld", b + 1, (long long)eb.state_first, state_expect);
-      if (eb.mask_dst_first < 1 || eb.mask_dst_first + eb.outdim_dst - 1 > eb.dim) return fail(e, ND_B200_EINVAL, "edge batch %d: dst StateMask outside 1..dim", b + 1);
-      if (eb.coupling == ND_B200_FIDUCIAL && (eb.mask_src_first < 1 || eb.mask_src_first + eb.outdim_src - 1 > eb.dim)) return fail(e, ND_B200_EINVAL, "edge batch %d: src StateMask outside 1..dim", b + 1);
-      state_expect += eb.count * eb.dim;
-      any_ode = true;
-    }
-    if (eb.coupling != ND_B200_ANTISYMMETRIC && eb.coupling != ND_B200_SYMMETRIC && eb.coupling != ND_B200_DIRECTED && eb.coupling != ND_B200_FIDUCIAL)
-      return fail(e, ND_B200_EUNSUPPORTED, "edge batch %d: unsupported output wrapper %d", b + 1, eb.coupling);
-    const int osrc_expect = eb.coupling == ND_B200_DIRECTED ? 0 : eb.outdim_dst;
-    if (eb.outdim_src != osrc_expect) return fail(e, ND_B200_EINVAL, "edge batch %d: outdim.src %d inconsistent with wrapper", b + 1, eb.outdim_src);
-    if (eb.out_first != eout_expect) return fail(e, ND_B200_EINVAL, "edge batch %d: outbufstride.first %lld, expected %lld", b + 1, (long long)eb.out_first, eout_expect);
-    if (eb.pdim < 0 || eb.pdim > 64) return fail(e, ND_B200_EINVAL, "edge batch %d: pdim %d", b + 1, eb.pdim);
-    if (eb.pdim > 0 && eb.p_first != p_expect) return fail(e, ND_B200_EINVAL, "edge batch %d: pstride.first %lld, expected %lld", b + 1, (long long)eb.p_first, p_expect);
-    p_expect += eb.count * eb.pdim;
-    if (eb.count <= 0 || eb.count > d->ne || (!eb.indices && d->n_ebatches != 1)) return fail(e, ND_B200_EINVAL, "edge batch %d is empty or larger than the graph", b + 1);
-    HostEB h{eb.kind, eb.coupling, eb.dim, eb.pdim, eb.outdim_src, eb.outdim_dst, eb.count, eb.p_first - 1, eb.out_first - 1,
-             eb.state_first - 1, eb.dim > 0 ? eb.mask_src_first - 1 : 0, eb.dim > 0 ? eb.mask_dst_first - 1 : 0};
-    e->heb.push_back(h);
-    eout_expect += eb.count * (eb.outdim_src + eb.outdim_dst);
-    if (eb.pdim > 0) any_epar = true;
-    for (long long i = 0; i < eb.count; ++i) {
-      long long eid = eb.indices ? eb.indices[i] : i + 1;
-      if (eid < 1 || eid > d->ne || edge_seen[(size_t)eid - 1]) return fail(e, ND_B200_EINVAL, "edge batch %d: bad or duplicate edge id %lld", b + 1, eid);
-      edge_seen[(size_t)eid - 1] = 1;
-    }
-  }
-  if (eout_expect - 1 != d->lastidx_out) return fail(e, ND_B200_EINVAL, "lastidx_out %lld inconsistent with batches (%lld)", (long long)d->lastidx_out, eout_expect - 1);
-  if (state_expect - 1 != d->lastidx_dynamic) return fail(e, ND_B200_EINVAL, "lastidx_dynamic %lld inconsistent with the batches (%lld)", (long long)d->lastidx_dynamic, state_expect - 1);
-  if (p_expect - 1 != d->lastidx_p) return fail(e, ND_B200_EINVAL, "lastidx_p %lld inconsistent with the batches (%lld)", (long long)d->lastidx_p, p_expect - 1);
-  e->ek = (d->n_ebatches == 1 && !any_ode) ? d->ebatches[0].kind : EK_GENERIC;   // entries of edges with states: generic kernels only
-  // precompiled specialisations exist for the benchmark edge kinds; every other registry kind runs in the generic kernels
-  if (!e->custom && d->vdepth == 1 && e->ek != ND_B200_E_DIFFUSION && e->ek != ND_B200_E_DIFFUSION_NOP && e->ek != ND_B200_E_KURAMOTO) e->ek = EK_GENERIC;
-  bool any_fiducial = false;
-  for (int b = 0; b < d->n_ebatches; ++b) any_fiducial = any_fiducial || d->ebatches[b].coupling == ND_B200_FIDUCIAL;
-  if (any_ode && (d->lastidx_dynamic >= ND_STATE_ENTRY_BIT || d->nv * (long long)d->vdepth >= ND_STATE_ENTRY_BIT))
-    return fail(e, ND_B200_EUNSUPPORTED, "networks with edge states need offsets below 2^30");
-  if (any_ode && !e->custom && d->vdepth != 1) return fail(e, ND_B200_EUNSUPPORTED, "edges with states and vdepth %d need user-supplied kinds", d->vdepth);
-  e->pack_pe = (!e->custom && e->ek != EK_GENERIC && d->n_ebatches == 1) ? d->ebatches[0].pdim : 0;
-  if (!e->custom && d->vdepth == 2 && d->n_ebatches > 1) {
-    // all (2,2) batches must be LINE_DQ with one coupling (single templated kernel)
-    for (int b = 1; b < d->n_ebatches; ++b)
-      if (d->ebatches[b].coupling != d->ebatches[0].coupling) return fail(e, ND_B200_EUNSUPPORTED, "mixed wrappers for dq lines");
-  }
-
-  // ---- destination-sorted CSR over owned rows: count, then stable placement ---------------------
-  std::vector<long long> cnt((size_t)nrows_owned + 1, 0);
-  auto owned = [&](int r) { return r >= e->row_begin && r < e->row_end; };
-  for (int b = 0; b < d->n_ebatches; ++b) {
-    const nd_b200_ebatch& eb = d->ebatches[b];
-    for (long long i = 0; i < eb.count; ++i) {
-      const long long eid = eb.indices ? eb.indices[i] - 1 : i;
-      const long long s = d->edge_src[eid], t = d->edge_dst[eid];
-      if (s < 1 || s > d->nv || t < 1 || t > d->nv) return fail(e, ND_B200_EINVAL, "edge %lld endpoint out of range", eid + 1);
-      const int rs = row_of_vertex[(size_t)s - 1], rt = row_of_vertex[(size_t)t - 1];
-      if (eb.outdim_src > 0 && owned(rs)) cnt[(size_t)(rs - e->row_begin) + 1]++;
-      if (owned(rt)) cnt[(size_t)(rt - e->row_begin) + 1]++;
-    }
-  }
-  for (long long r = 0; r < nrows_owned; ++r) cnt[(size_t)r + 1] += cnt[(size_t)r];
-  e->nentries = cnt[(size_t)nrows_owned];
-  if (e->nentries >= INT_MAX) return fail(e, ND_B200_EUNSUPPORTED, "more than 2^31 directed entries on one device");
-  std::vector<int> h_rowptr((size_t)nrows_owned + 1);
-  for (size_t r = 0; r < h_rowptr.size(); ++r) h_rowptr[r] = (int)cnt[r];
-  const bool keep = !(d->flags & ND_B200_FLAG_NO_EXPORT);
-  std::vector<int> h_nbr((size_t)std::max<long long>(e->nentries, 1)), h_epar;
+// Construction of an engine from a descriptor, stage by stage (host side; see the comments of each stage).  The members are
+// the tables the stages hand to each other; what the engine keeps is copied / uploaded by the last stage.
+struct EngineBuilder {
+  nd_b200_engine* e;
+  const nd_b200_desc* d;
+  // vertices
+  std::vector<int> row_of_vertex;            // vertex id - 1 -> aggregation-slot row
+  std::vector<int> goff;                     // vertex id - 1 -> offset of its output in the gather source
+  long long state_expect = 1, out_expect = 1, p_expect = 1, nrows_owned = 0;
+  // edges
+  bool any_epar = false, any_ode = false, any_fiducial = false;
+  // CSR over the owned rows, entries in accumulation order
+  std::vector<long long> cnt;
+  std::vector<int> h_rowptr, h_nbr, h_epar;
   std::vector<uint8_t> h_ebid;
-  // the precompiled generic kernels are instantiated with PE = 1 and read the parameter-offset stream even when no edge
-  // batch of this network has parameters
-  if (e->ek == EK_GENERIC && d->vdepth == 1 && !e->custom) any_epar = true;
-  if (any_epar) h_epar.assign((size_t)std::max<long long>(e->nentries, 1), 0);
-  if (e->ek == EK_GENERIC && (d->vdepth == 1 || e->custom)) h_ebid.assign((size_t)std::max<long long>(e->nentries, 1), 0);
-  if (keep) { e->h_nbr_vid.resize((size_t)e->nentries); e->h_eid.resize((size_t)e->nentries); e->h_side.resize((size_t)e->nentries); }
-  // split mode tables: per entry its position in the edge part of `o`; per edge (in `o` order) the gather offsets
-  const bool generic_edges = (e->ek == EK_GENERIC && (d->vdepth == 1 || e->custom));
-  e->oedge_base = d->nv * (long long)d->vdepth;
-  e->oedge_len = d->lastidx_out - e->oedge_base;
-  e->ne_all = d->ne;
-  bool want_split = false;
-  if (const char* s = getenv("ND_B200_KERNEL")) want_split = !strcmp(s, "split") && nrows_owned == e->nrows_total && !(d->vdepth == 2 && d->n_ebatches > 1) && !e->custom && !any_ode && !any_fiducial;
-  if (want_split && e->oedge_len >= INT_MAX) return fail(e, ND_B200_EUNSUPPORTED, "edge output buffer exceeds 2^31 scalars on one device");
-  std::vector<int> h_oidx(want_split ? (size_t)std::max<long long>(e->nentries, 1) : 1), h_es(want_split ? (size_t)std::max<long long>(d->ne, 1) : 1), h_et(want_split ? (size_t)std::max<long long>(d->ne, 1) : 1);
-  std::vector<int> h_eepar, h_eooff;
+  bool keep = false, generic_edges = false, want_split = false;
+  std::vector<int> h_oidx, h_es, h_et, h_eepar, h_eooff;   // split mode
   std::vector<uint8_t> h_eebid;
-  if (generic_edges && want_split) { h_eepar.assign((size_t)std::max<long long>(d->ne, 1), 0); h_eooff.assign((size_t)std::max<long long>(d->ne, 1), 0); h_eebid.assign((size_t)std::max<long long>(d->ne, 1), 0); }
-  {
-    long long kedge = 0;
-    std::vector<long long> cur(cnt.begin(), cnt.end() - 1);
-    for (int b = 0; b < d->n_ebatches; ++b) {
-      const nd_b200_ebatch& eb = d->ebatches[b];
-      for (long long i = 0; i < eb.count; ++i) {
-        const long long eid = eb.indices ? eb.indices[i] - 1 : i;
-        const long long s = d->edge_src[eid], t = d->edge_dst[eid];
-        const int rs = row_of_vertex[(size_t)s - 1], rt = row_of_vertex[(size_t)t - 1];
-        const int ep = eb.pdim > 0 ? (int)(eb.p_first - 1 + i * eb.pdim) : 0;
-        const long long oo = (eb.out_first - 1) + i * (eb.outdim_src + eb.outdim_dst) - e->oedge_base;   // this edge's block in the edge part of o
-        if (want_split) { h_es[(size_t)kedge] = goff[(size_t)s - 1]; h_et[(size_t)kedge] = goff[(size_t)t - 1]; }
-        if (generic_edges && want_split) { h_eepar[(size_t)kedge] = ep; h_eooff[(size_t)kedge] = (int)oo; h_eebid[(size_t)kedge] = (uint8_t)b; }
-        ++kedge;
-        // src output precedes dst output in `o` (register_edges!, src/network_structure.jl:244-245)
-        // edges with states contribute a StateMask read of their own states: the offset of the output state inside u,
-        // flagged with ND_STATE_ENTRY_BIT (state_entry_value in the kernels)
-        const int so_src = eb.dim > 0 ? (int)((eb.state_first - 1) + i * eb.dim + (eb.coupling == ND_B200_FIDUCIAL ? eb.mask_src_first - 1 : eb.mask_dst_first - 1)) | ND_STATE_ENTRY_BIT : 0;
-        const int so_dst = eb.dim > 0 ? (int)((eb.state_first - 1) + i * eb.dim + (eb.mask_dst_first - 1)) | ND_STATE_ENTRY_BIT : 0;
-        if (eb.outdim_src > 0 && owned(rs)) {
-          const long long j = cur[(size_t)(rs - e->row_begin)]++;
-          if (want_split) h_oidx[(size_t)j] = (int)oo;
-          h_nbr[(size_t)j] = eb.dim > 0 ? ~so_src : ~goff[(size_t)t - 1];
-          if (any_epar) h_epar[(size_t)j] = ep;
-          if (!h_ebid.empty()) h_ebid[(size_t)j] = (uint8_t)b;
-          if (keep) { e->h_nbr_vid[(size_t)j] = (int)t; e->h_eid[(size_t)j] = (int)(eid + 1); e->h_side[(size_t)j] = 1; }
-        }
-        if (owned(rt)) {
-          const long long j = cur[(size_t)(rt - e->row_begin)]++;
-          if (want_split) h_oidx[(size_t)j] = (int)(oo + eb.outdim_src);
-          h_nbr[(size_t)j] = eb.dim > 0 ? so_dst : goff[(size_t)s - 1];
-          if (any_epar) h_epar[(size_t)j] = ep;
-          if (!h_ebid.empty()) h_ebid[(size_t)j] = (uint8_t)b;
-          if (keep) { e->h_nbr_vid[(size_t)j] = (int)s; e->h_eid[(size_t)j] = (int)(eid + 1); e->h_side[(size_t)j] = 0; }
-        }
-      }
-    }
-  }
-  if (keep) e->h_rowptr.assign(cnt.begin(), cnt.end());
-  // end of the parameter range an entry / a row reads (host-buffer pipeline, nd_b200_rhs_host)
-  auto entry_pend = [&](long long j) -> int {
-    if (!any_epar) return 0;
-    const int pd = h_ebid.empty() ? e->heb[0].pdim : e->heb[h_ebid[(size_t)j]].pdim;
-    return pd > 0 ? h_epar[(size_t)j] + pd : 0;
-  };
-  auto row_pend = [&](long long r, size_t b) -> int {
-    const HostVB& h = e->hvb[b];
-    return h.pdim > 0 ? (int)(h.p0 + (r - h.row0 + 1) * h.pdim) : 0;
-  };
-  // rows that read the halo ("boundary" rows); everything else can run while the halo is in flight
-  std::vector<char> row_remote((size_t)nrows_owned, 0);
-  if (d->gather_offset) {
-    for (long long r = 0; r < nrows_owned; ++r)
-      for (long long j = cnt[(size_t)r]; j < cnt[(size_t)r + 1]; ++j) {
-        const int o = h_nbr[(size_t)j] < 0 ? ~h_nbr[(size_t)j] : h_nbr[(size_t)j];
-        if (o >= e->halo_base) { row_remote[(size_t)r] = 1; break; }
-      }
-  }
-
-  // get_buffers tables: gather offsets per edge in batch order
-  if (keep) {
-    e->h_esrc_off.resize((size_t)d->n_ebatches); e->h_edst_off.resize((size_t)d->n_ebatches);
-    for (int b = 0; b < d->n_ebatches; ++b) {
-      const nd_b200_ebatch& eb = d->ebatches[b];
-      e->h_esrc_off[(size_t)b].resize((size_t)eb.count); e->h_edst_off[(size_t)b].resize((size_t)eb.count);
-      for (long long i = 0; i < eb.count; ++i) {
-        const long long eid = eb.indices ? eb.indices[i] - 1 : i;
-        e->h_esrc_off[(size_t)b][(size_t)i] = goff[(size_t)d->edge_src[eid] - 1];
-        e->h_edst_off[(size_t)b][(size_t)i] = goff[(size_t)d->edge_dst[eid] - 1];
-      }
-    }
-  }
-
-  // ---- launch shape + thread-block row ranges ----------------------------------------------------
-  e->block = 128; e->ept = 4;   // measured best on B200 for every registry family (profiles/r01_tuning.md)
-  if (const char* s = getenv("ND_B200_BLOCK")) e->block = atoi(s);
-  if (const char* s = getenv("ND_B200_EPT")) e->ept = atoi(s);
-  if (!((e->block == 256 || e->block == 128) && (e->ept == 8 || e->ept == 4))) return fail(e, ND_B200_EINVAL, "ND_B200_BLOCK/ND_B200_EPT must be 128|256 / 4|8");
-  const int tile = e->block * e->ept;
+  std::vector<char> row_remote;              // owned row reads the halo
+  // tile layout
   std::vector<int> blk_row;
   std::vector<VBDev> dvb;
-  e->n_long = 0;
-  for (size_t b = 0; b < e->hvb.size(); ++b) {
-    const HostVB& h = e->hvb[b];
-    VBDev v{h.kind, h.dim, h.pdim, (int)h.row0, (int)h.count, (int)blk_row.size(), h.state0, h.p0};
-    long long r = std::max<long long>(h.row0, e->row_begin);
-    const long long rend = std::min<long long>(h.row0 + h.count, e->row_end);
-    while (r < rend) {
-      blk_row.push_back((int)r);
-      const long long deg0 = cnt[(size_t)(r - e->row_begin) + 1] - cnt[(size_t)(r - e->row_begin)];
-      if (deg0 > e->long_thr) { e->n_long++; r++; continue; }
-      long long rr = r, ents = 0;
-      while (rr < rend && rr - r < e->block) {
-        const long long deg = cnt[(size_t)(rr - e->row_begin) + 1] - cnt[(size_t)(rr - e->row_begin)];
-        if (deg > e->long_thr || ents + deg > tile) break;
-        ents += deg; rr++;
-      }
-      if (rr == r) {   // a single short row that does not fit a tile: only when long_thr >= tile
-        return fail(e, ND_B200_EUNSUPPORTED, "row with %lld entries exceeds the %d-entry tile with long rows disabled", deg0, tile);
-      }
-      r = rr;
-    }
-    dvb.push_back(v);
-  }
-  e->nblocks = (int)blk_row.size();
-  blk_row.push_back((int)e->row_end);
-
-  // owned state ranges: one per vertex batch the row range intersects
-  for (const HostVB& h : e->hvb) {
-    const long long lo = std::max<long long>(e->row_begin, h.row0), hi = std::min<long long>(e->row_end, h.row0 + h.count);
-    if (lo < hi && h.dim > 0) e->own_segs.push_back({h.state0 + (lo - h.row0) * h.dim, (hi - lo) * h.dim});
-  }
-  // ---- one 16-byte descriptor per thread block -----------------------------------------------------------
-  e->split = 0;   // default: fused kernel (faster on B200 for every config whose state vector fits in L2)
-  if (want_split) e->split = 1;
-  std::vector<int4> tiles;
-  {
-    tiles.reserve((size_t)e->nblocks);
-    size_t bi = 0;
-    for (int k = 0; k < e->nblocks; ++k) {
-      const int r0 = blk_row[(size_t)k], r1 = blk_row[(size_t)k + 1];
-      while (bi + 1 < dvb.size() && k >= dvb[bi + 1].blk0) ++bi;
-      const long long a = cnt[(size_t)(r0 - e->row_begin)], z = cnt[(size_t)(r1 - e->row_begin)];
-      const long long ne = z - a;
-      const bool is_long = (r1 - r0 == 1) && ne > e->long_thr;
-      int4 t;
-      t.x = r0; t.y = (int)a;
-      if (is_long) { t.z = (int)ne; t.w = (int)(0x80000000u | ((unsigned)bi << 25) | (1u << 16)); }
-      else { t.z = 0; t.w = (int)((unsigned)ne | ((unsigned)(r1 - r0) << 16) | ((unsigned)bi << 25)); }
-      tiles.push_back(t);
-    }
-    e->ntiles = (int)tiles.size();
-    e->wait_from = 0;
-    if (d->gather_offset) {
-      // interior tiles first, tiles that read the halo last (each descriptor is self-contained)
-      auto reads_halo = [&](const int4& t) {
-        const int nr = (t.w < 0) ? 1 : ((t.w >> 16) & 0x1FF);
-        for (int r = 0; r < nr; ++r)
-          if (row_remote[(size_t)(t.x + r - e->row_begin)]) return true;
-        return false;
-      };
-      auto mid = std::stable_partition(tiles.begin(), tiles.end(), [&](const int4& t) { return !reads_halo(t); });
-      e->wait_from = (int)(mid - tiles.begin());
-    }
-    e->blk_pmax.assign(tiles.size(), 0); e->blk_rmin.assign(tiles.size(), 0); e->blk_rmax.assign(tiles.size(), 0);
-    for (size_t k = 0; k < tiles.size(); ++k) {
-      const int4& t = tiles[k];
-      const bool lg = t.w < 0;
-      const int nr = lg ? 1 : ((t.w >> 16) & 0x1FF), ne = lg ? t.z : (t.w & 0xFFFF);
-      const size_t b = (size_t)((t.w >> 25) & 0x3F);
-      int pm = row_pend(t.x + nr - 1, b);
-      for (long long j = t.y; j < (long long)t.y + ne; ++j) pm = std::max(pm, entry_pend(j));
-      e->blk_pmax[k] = pm; e->blk_rmin[k] = t.x; e->blk_rmax[k] = t.x + nr - 1;
-    }
-  }
   std::vector<EBDev> deb;
-  for (const HostEB& h : e->heb) deb.push_back(EBDev{h.kind, h.coupling, h.pdim, h.dim});
-
-  // ---- jagged layout: 32-lane slices, column-major compacted entries (rhs_jag_kernel) ------------------------
-  // ND_B200_KERNEL=jag|fused|split overrides the automatic choice.  A strictly sequential long_row_threshold beyond
-  // what one lane can hold (63 entries) needs the tile kernel.
-  // Kernel family (measured on B200, profiles/r01c_sweep_fused_vs_jag.jsonl): the tile kernel wins whenever degrees
-  // vary (idle lanes in the jagged walk: ER cfg2 72 vs 76 us, BA cfg3 91 vs 148 us) or the graph is small (latency of the
-  // per-lane walk: cfg1); the jagged kernel wins on large regular-degree graphs (cfg4 grid: RK4 step 45 vs 55 us).
-  // auto = jagged iff lane utilisation of the walk >= 0.8 and there are enough rows to fill the machine.
-  {
-    long long sum_max = 0;
-    for (long long r = 0; r < nrows_owned; r += 32) {
-      long long m = 0;
-      for (long long q = r; q < std::min<long long>(r + 32, nrows_owned); ++q) m = std::max(m, cnt[(size_t)q + 1] - cnt[(size_t)q]);
-      sum_max += m;
-    }
-    const double util = sum_max > 0 ? (double)e->nentries / (32.0 * (double)sum_max) : 0.0;
-    e->jag = (util >= 0.8 && nrows_owned >= 65536) ? 1 : 0;
-  }
-  if (const char* s = getenv("ND_B200_KERNEL")) {
-    if (!strcmp(s, "jag")) e->jag = 1;
-    else if (!strcmp(s, "fused") || !strcmp(s, "split") || !strcmp(s, "v1")) e->jag = 0;
-  }
-  if (e->split) e->jag = 0;
-  if (d->long_row_threshold > 63 * 32) e->jag = 0;
-  e->jag_u = 2;
-  e->jag_wps = d->vdepth == 2 ? 32 : 48;   // spill-free register budgets, best measured
+  std::vector<int4> tiles;
+  // jagged layout
   std::vector<int4> jslices, jlong;
   std::vector<uint16_t> jlanes;
   std::vector<int> jnbr;
   std::vector<int2> jent;
   std::vector<uint8_t> jebid;
-  const bool jag_pe = any_epar || (generic_edges && !e->custom);   // kernels instantiated with PE > 0 read {nbr, epar} pairs
-  if (e->jag) {
-    e->jsplit = 32;
-    if (const char* s = getenv("ND_B200_JAG_SPLIT")) e->jsplit = std::min(63, std::max(1, atoi(s)));
-    if (const char* s = getenv("ND_B200_JAG_U")) e->jag_u = atoi(s);
-    if (const char* s = getenv("ND_B200_JAG_WPS")) e->jag_wps = atoi(s);
-    int jwindow = 32;
-    if (const char* s = getenv("ND_B200_JAG_WINDOW")) { const int w = atoi(s); if (w == 64 || w == 128) jwindow = w; }
-    // rows longer than this are reduced by a whole block: explicit threshold if the caller gave one, else what a
-    // slice can hold
-    const long long block_thr = d->long_row_threshold > 0 ? std::min<long long>(d->long_row_threshold, 32LL * e->jsplit) : 32LL * e->jsplit;
-    std::vector<int> order;
-    order.reserve((size_t)e->nentries);
-    struct Lane { int rowrel, len, head; long long start; };
-    std::vector<Lane> lanes;
-    std::vector<std::pair<long long, int>> long_rows;   // (row, batch)
-    int jag_wait_from = 0;
-    const int nclasses = d->gather_offset ? 2 : 1;   // class 0: interior rows, class 1: rows that read the halo
-    for (int cls = 0; cls < nclasses; ++cls) {
-    if (cls == 1) jag_wait_from = (int)jslices.size();
-    for (size_t b = 0; b < e->hvb.size(); ++b) {
-      const HostVB& h = e->hvb[b];
-      const long long lo = std::max<long long>(h.row0, e->row_begin), hi = std::min<long long>(h.row0 + h.count, e->row_end);
-      long long row0 = -1;
-      int maxparts = 1;
-      auto flush = [&]() {
-        if (lanes.empty()) return;
-        int maxlen = 0;
-        for (const Lane& L : lanes) maxlen = std::max(maxlen, L.len);
-        const int e0 = (int)order.size();
-        for (int j = 0; j < maxlen; ++j)
-          for (const Lane& L : lanes)
-            if (L.len > j) order.push_back((int)(L.start + j));
-        jslices.push_back(make_int4(e0, (int)row0, (int)b, maxparts));
-        for (int l = 0; l < 32; ++l) {
-          uint16_t v = 0;
-          if (l < (int)lanes.size()) v = (uint16_t)(lanes[(size_t)l].len | (lanes[(size_t)l].rowrel << 6) | (lanes[(size_t)l].head << 13) | (1 << 14));
-          jlanes.push_back(v);
-        }
-        lanes.clear(); row0 = -1; maxparts = 1;
-      };
-      if (jwindow > 32) {
-        // degree-bucketed slices (ND_B200_JAG_WINDOW = 64 | 128): the rows of a window of consecutive rows are dealt to
-        // the lanes in order of decreasing degree, so the 32 rows that share a slice have (nearly) equal length and the
-        // lane walk wastes no iterations on short rows next to long ones; lanes address their row relative to the window
-        // start (7 bits).  The row's own u / du / vertex parameters stay within the window (<= 1 KB of each vector).
-        std::vector<long long> wrows;
-        for (long long w0 = lo; w0 < hi; w0 += jwindow) {
-          wrows.clear();
-          for (long long r = w0; r < std::min<long long>(w0 + jwindow, hi); ++r) {
-            if (nclasses == 2 && row_remote[(size_t)(r - e->row_begin)] != cls) continue;
-            const long long deg = cnt[(size_t)(r - e->row_begin) + 1] - cnt[(size_t)(r - e->row_begin)];
-            const int nparts = (int)std::max<long long>(1, (deg + e->jsplit - 1) / e->jsplit);
-            if (deg > block_thr || nparts > 32) { long_rows.push_back({r, (int)b}); continue; }
-            wrows.push_back(r);
-          }
-          std::stable_sort(wrows.begin(), wrows.end(), [&](long long x, long long y) {
-            return cnt[(size_t)(x - e->row_begin) + 1] - cnt[(size_t)(x - e->row_begin)] > cnt[(size_t)(y - e->row_begin) + 1] - cnt[(size_t)(y - e->row_begin)];
-          });
-          for (long long r : wrows) {
-            const long long a = cnt[(size_t)(r - e->row_begin)], deg = cnt[(size_t)(r - e->row_begin) + 1] - a;
-            const int nparts = (int)std::max<long long>(1, (deg + e->jsplit - 1) / e->jsplit);
-            if ((int)lanes.size() + nparts > 32) flush();
-            if (lanes.empty()) row0 = w0;
-            for (int k = 0; k < nparts; ++k) {
-              const long long len = std::min<long long>(e->jsplit, deg - (long long)k * e->jsplit);
-              lanes.push_back(Lane{(int)(r - w0), (int)std::max<long long>(len, 0), k == 0, a + (long long)k * e->jsplit});
-            }
-            maxparts = std::max(maxparts, nparts);
-          }
-          flush();
-        }
-      } else {
-      for (long long r = lo; r < hi; ++r) {
-        if (nclasses == 2 && row_remote[(size_t)(r - e->row_begin)] != cls) continue;
-        const long long a = cnt[(size_t)(r - e->row_begin)], deg = cnt[(size_t)(r - e->row_begin) + 1] - a;
-        const int nparts = (int)std::max<long long>(1, (deg + e->jsplit - 1) / e->jsplit);
-        if (deg > block_thr || nparts > 32) { long_rows.push_back({r, (int)b}); continue; }
-        if ((int)lanes.size() + nparts > 32 || (row0 >= 0 && r - row0 >= 32)) flush();
-        if (lanes.empty()) row0 = r;
-        for (int k = 0; k < nparts; ++k) {
-          const long long len = std::min<long long>(e->jsplit, deg - (long long)k * e->jsplit);
-          lanes.push_back(Lane{(int)(r - row0), (int)std::max<long long>(len, 0), k == 0, a + (long long)k * e->jsplit});
-        }
-        maxparts = std::max(maxparts, nparts);
-      }
-      flush();
-      }
-    }
-    }
-    if (nclasses == 1) jag_wait_from = 0;
-    for (const auto& lr : long_rows) {
-      const long long a = cnt[(size_t)(lr.first - e->row_begin)], deg = cnt[(size_t)(lr.first - e->row_begin) + 1] - a;
-      jlong.push_back(make_int4((int)order.size(), (int)lr.first, (int)deg, lr.second));
-      for (long long j = 0; j < deg; ++j) order.push_back((int)(a + j));
-    }
-    if ((long long)order.size() != e->nentries) return fail(e, ND_B200_EINVAL, "internal: jagged layout holds %lld of %lld entries", (long long)order.size(), e->nentries);
-    if (jag_pe) {
-      jent.resize(std::max<size_t>(order.size(), 1));
-      for (size_t k = 0; k < order.size(); ++k) jent[k] = make_int2(h_nbr[(size_t)order[k]], any_epar ? h_epar[(size_t)order[k]] : 0);
-    } else {
-      jnbr.resize(std::max<size_t>(order.size(), 1));
-      for (size_t k = 0; k < order.size(); ++k) jnbr[k] = h_nbr[(size_t)order[k]];
-    }
-    if (!h_ebid.empty()) {
-      jebid.resize(std::max<size_t>(order.size(), 1));
-      for (size_t k = 0; k < order.size(); ++k) jebid[k] = h_ebid[(size_t)order[k]];
-    }
-    e->host_only = (d->flags & ND_B200_FLAG_HOST_ONLY) != 0;
-    if (e->host_only) { e->h_jslices = jslices; e->h_jlong = jlong; e->h_jlanes = jlanes; e->h_jorder = order; }
-    {
-      const size_t nb = (jslices.size() + 3) / 4;
-      e->blk_pmax.assign(nb + jlong.size(), 0); e->blk_rmin.assign(nb + jlong.size(), INT_MAX); e->blk_rmax.assign(nb + jlong.size(), -1);
-      for (size_t sidx = 0; sidx < jslices.size(); ++sidx) {
-        const size_t k = sidx / 4;
-        const int4& S = jslices[sidx];
-        const long long eend = sidx + 1 < jslices.size() ? jslices[sidx + 1].x : (jlong.empty() ? (long long)order.size() : jlong[0].x);
-        int pm = e->blk_pmax[k];
-        for (long long q = S.x; q < eend; ++q) pm = std::max(pm, entry_pend(order[(size_t)q]));
-        for (int l = 0; l < 32; ++l) {
-          const uint16_t v = jlanes[sidx * 32 + (size_t)l];
-          if (!((v >> 14) & 1)) break;
-          const int r = S.y + ((v >> 6) & 127);
-          e->blk_rmin[k] = std::min(e->blk_rmin[k], r); e->blk_rmax[k] = std::max(e->blk_rmax[k], r);
-          pm = std::max(pm, row_pend(r, (size_t)S.z));
-        }
-        e->blk_pmax[k] = pm;
-      }
-      for (size_t q = 0; q < jlong.size(); ++q) {
-        const int4& Lr = jlong[q];
-        int pm = row_pend(Lr.y, (size_t)Lr.w);
-        for (long long j = Lr.x; j < (long long)Lr.x + Lr.z; ++j) pm = std::max(pm, entry_pend(order[(size_t)j]));
-        e->blk_pmax[nb + q] = pm; e->blk_rmin[nb + q] = Lr.y; e->blk_rmax[nb + q] = Lr.y;
-      }
-    }
-    e->wait_from = jag_wait_from;
-    e->nslices = (int)jslices.size();
-    e->n_jag_blocks = (e->nslices + 3) / 4;   // BLOCK = 128: four slices per thread block
-    e->n_jlong = (int)jlong.size();
-    e->nblocks = e->n_jag_blocks + e->n_jlong;
-    e->n_long = e->n_jlong;
+  bool jag_pe = false;
+
+  EngineBuilder(nd_b200_engine* e_, const nd_b200_desc* d_) : e(e_), d(d_) {}
+
+  bool owned(int r) const { return r >= e->row_begin && r < e->row_end; }
+  // end of the parameter range an entry / a row reads (host-buffer pipeline, nd_b200_rhs_host)
+  int entry_pend(long long j) const {
+    if (!any_epar) return 0;
+    const int pd = h_ebid.empty() ? e->heb[0].pdim : e->heb[h_ebid[(size_t)j]].pdim;
+    return pd > 0 ? h_epar[(size_t)j] + pd : 0;
+  }
+  int row_pend(long long r, size_t b) const {
+    const HostVB& h = e->hvb[b];
+    return h.pdim > 0 ? (int)(h.p0 + (r - h.row0 + 1) * h.pdim) : 0;
   }
 
-  e->blk_rows_monotone = true;
-  for (size_t k = 0; k + 1 < e->blk_rmin.size(); ++k)
-    if (e->blk_rmin[k + 1] <= e->blk_rmax[k]) { e->blk_rows_monotone = false; break; }
-  if (d->flags & ND_B200_FLAG_HOST_ONLY) e->host_only = true;
-  if (e->custom) {
-    if (e->jag) { e->jag_wps = 48; e->jag_u = 2; }   // the one jagged instantiation that is compiled for user-supplied kinds
-    if (int rc = compile_custom(e, d->vdepth, e->edepth)) return rc;
-  }
-  if (e->host_only) return ND_B200_OK;
-  CUDA_TRY(e, cudaSetDevice(e->device));
-  for (int b = 0; b < d->n_ebatches; ++b) {
-    const nd_b200_ebatch& eb = d->ebatches[b];
-    if (eb.dim == 0) continue;
-    std::vector<int> es((size_t)eb.count), et((size_t)eb.count);
-    for (long long i = 0; i < eb.count; ++i) {
-      const long long eid = eb.indices ? eb.indices[i] - 1 : i;
-      es[(size_t)i] = goff[(size_t)d->edge_src[eid] - 1];
-      et[(size_t)i] = goff[(size_t)d->edge_dst[eid] - 1];
+  // sizes, limits, user-supplied kinds
+  int check_descriptor() {
+    if (d->abi_version != ND_B200_ABI_VERSION) return fail(e, ND_B200_EINVAL, "descriptor abi_version %d != %d", d->abi_version, ND_B200_ABI_VERSION);
+    if (d->nv <= 0) return fail(e, ND_B200_EINVAL, "network needs at least one vertex");
+    if (d->n_vbatches <= 0 || d->n_vbatches > MAX_VB) return fail(e, ND_B200_EUNSUPPORTED, "number of vertex batches %d outside 1..%d", d->n_vbatches, MAX_VB);
+    if (d->n_ebatches < 0 || d->n_ebatches > MAX_EB) return fail(e, ND_B200_EUNSUPPORTED, "number of edge batches %d outside 0..%d", d->n_ebatches, MAX_EB);
+    if (d->ne > 0 && d->n_ebatches == 0) return fail(e, ND_B200_EINVAL, "edges without edge batches");
+    if (d->ne < 0 || !d->vbatches || (d->n_ebatches > 0 && !d->ebatches) || (d->ne > 0 && (!d->edge_src || !d->edge_dst)))
+      return fail(e, ND_B200_EINVAL, "descriptor with missing tables");
+    if (d->vdepth < 1 || (d->ne > 0 && d->edepth < 1)) return fail(e, ND_B200_EINVAL, "vdepth / edepth must be positive");
+    e->device = d->device;
+    e->nv = d->nv; e->ne = d->ne; e->vdepth = d->vdepth; e->edepth = d->ne > 0 ? d->edepth : d->vdepth;
+    e->lastidx_dynamic = d->lastidx_dynamic; e->lastidx_p = d->lastidx_p;
+    e->lastidx_out = d->lastidx_out; e->lastidx_aggr = d->lastidx_aggr;
+    if (d->n_custom < 0 || (d->n_custom > 0 && !d->custom)) return fail(e, ND_B200_EINVAL, "bad custom kind table");
+    for (int k = 0; k < d->n_custom; ++k) {
+      const nd_b200_custom_kind& c = d->custom[k];
+      if (c.kind < ND_B200_CUSTOM_KIND_BASE || (c.role != 0 && c.role != 1) || !c.f_body) return fail(e, ND_B200_EINVAL, "custom kind %d: id must be >= %d, role 0|1, f_body non-NULL", c.kind, ND_B200_CUSTOM_KIND_BASE);
+      if (c.dim < 0 || c.dim > 16 || c.pdim < 0 || c.pdim > 64 || c.outdim < 1 || c.outdim > 8) return fail(e, ND_B200_EUNSUPPORTED, "custom kind %d: dims outside dim<=16, pdim<=64, 1<=outdim<=8", c.kind);
+      if (c.role == 1) e->c_maxedim = std::max(e->c_maxedim, c.dim);
+      e->customs.push_back(nd_b200_engine::CustomKind{c.kind, c.role, c.dim, c.pdim, c.outdim, c.two_sided, c.f_body, c.g_body ? c.g_body : ""});
     }
-    nd_b200_engine::OdeBatch ob{b, nullptr, nullptr};
-    if (upload(e, &ob.d_es, es) || upload(e, &ob.d_et, et)) return ND_B200_ECUDA;
-    e->ode.push_back(ob);
+    for (int b = 0; b < d->n_vbatches; ++b) e->custom = e->custom || d->vbatches[b].kind >= ND_B200_CUSTOM_KIND_BASE;
+    for (int b = 0; b < d->n_ebatches; ++b) e->custom = e->custom || d->ebatches[b].kind >= ND_B200_CUSTOM_KIND_BASE;
+    if (!e->custom && !((d->vdepth == 1 && (d->ne == 0 || d->edepth == 1)) || (d->vdepth == 2 && d->edepth == 2)))
+      return fail(e, ND_B200_EUNSUPPORTED, "no precompiled kernel for (vdepth,edepth)=(%d,%d); available: (1,1),(2,2) -- other shapes need user-supplied kinds", d->vdepth, d->edepth);
+    if (e->custom && (d->vdepth < 1 || d->vdepth > 8 || (d->ne > 0 && (d->edepth < 1 || d->edepth > 8))))
+      return fail(e, ND_B200_EUNSUPPORTED, "(vdepth,edepth)=(%d,%d) outside 1..8", d->vdepth, d->edepth);
+    if (d->lastidx_dynamic >= INT_MAX || d->lastidx_p >= INT_MAX || d->lastidx_out >= (long long)INT_MAX * 2)
+      return fail(e, ND_B200_EUNSUPPORTED, "network too large for 32-bit offsets");
+    e->long_thr = d->long_row_threshold > 0 ? d->long_row_threshold : 128;
+    return ND_B200_OK;
   }
-  if (e->jag) {
-    if (upload(e, &e->d_vb, dvb) || upload(e, &e->d_eb, deb) || upload(e, &e->d_jslices, jslices) || upload(e, &e->d_jlanes, jlanes) ||
-        upload(e, &e->d_jlong, jlong))
-      return ND_B200_ECUDA;
-    if (jag_pe ? upload(e, &e->d_jent, jent) : upload(e, &e->d_jnbr, jnbr)) return ND_B200_ECUDA;
-    if (!jebid.empty() && upload(e, &e->d_jebid, jebid)) return ND_B200_ECUDA;
-    if (!e->gather_from_u) {
-      for (int k = 0; k < 2; ++k) CUDA_TRY(e, cudaMalloc((void**)&e->d_vout[k], sizeof(double) * (size_t)(e->nrows_total * e->vdepth)));
+
+  // vertex batches: registry check, contiguity of rows / states (register_vertices!), gather offsets, halo layout
+  int register_vertices() {
+    // ---- vertex batches: registry check, contiguity of rows/states (register_vertices!) ----------
+    row_of_vertex.assign((size_t)d->nv, -1);
+    long long row = 0;
+    const int ed = d->ne > 0 ? d->edepth : 0;
+    bool all_statemask1 = true;
+    for (int b = 0; b < d->n_vbatches; ++b) {
+      const nd_b200_vbatch& vb = d->vbatches[b];
+      std::string why;
+      if (!vertex_kind_ok(e, vb, why)) return fail(e, ND_B200_EUNSUPPORTED, "%s (no CPU fallback)", why.c_str());
+      if (vb.outdim != d->vdepth) return fail(e, ND_B200_EINVAL, "vertex batch %d outdim %d != vdepth %d", b + 1, vb.outdim, d->vdepth);
+      if (vb.count <= 0 || vb.count > d->nv || (!vb.indices && d->n_vbatches != 1)) return fail(e, ND_B200_EINVAL, "vertex batch %d is empty or larger than the graph", b + 1);
+      if (vb.state_first != state_expect) return fail(e, ND_B200_EINVAL, "vertex batch %d: statestride.first %lld, expected %lld", b + 1, (long long)vb.state_first, state_expect);
+      if (vb.out_first != out_expect) return fail(e, ND_B200_EINVAL, "vertex batch %d: outbufstride.first %lld, expected %lld", b + 1, (long long)vb.out_first, out_expect);
+      if (vb.dim < 0 || vb.pdim < 0) return fail(e, ND_B200_EINVAL, "vertex batch %d: negative dimension", b + 1);
+      if (vb.pdim > 0 && vb.p_first != p_expect) return fail(e, ND_B200_EINVAL, "vertex batch %d: pstride.first %lld, expected %lld", b + 1, (long long)vb.p_first, p_expect);
+      if (ed > 0 && vb.aggr_first != row * ed + 1) return fail(e, ND_B200_EINVAL, "vertex batch %d: inbufstride.first %lld, expected %lld", b + 1, (long long)vb.aggr_first, row * ed + 1);
+      HostVB h{vb.kind, vb.dim, vb.pdim, vb.outdim, vb.count, vb.state_first - 1, vb.p_first - 1, vb.out_first - 1, row};
+      e->hvb.push_back(h);
+      for (long long i = 0; i < vb.count; ++i) {
+        long long vid = vb.indices ? vb.indices[i] : i + 1;
+        if (vid < 1 || vid > d->nv || row_of_vertex[(size_t)vid - 1] >= 0) return fail(e, ND_B200_EINVAL, "vertex batch %d: bad or duplicate vertex id %lld", b + 1, vid);
+        row_of_vertex[(size_t)vid - 1] = (int)(row + i);
+      }
+      row += vb.count; state_expect += vb.count * vb.dim; out_expect += vb.count * vb.outdim; p_expect += vb.count * vb.pdim;
+      if (vb.kind == ND_B200_V_SWING_DQ) all_statemask1 = false;
+      if (vb.kind >= ND_B200_CUSTOM_KIND_BASE && !find_custom(e, vb.kind, 0)->g_body.empty()) all_statemask1 = false;
+      if (vb.dim > (e->custom ? 16 : 2)) return fail(e, ND_B200_EUNSUPPORTED, "vertex batch %d: dim %d", b + 1, vb.dim);
+      e->c_maxdim = std::max(e->c_maxdim, vb.dim);
+    }
+    if (row != d->nv) return fail(e, ND_B200_EINVAL, "vertex batches cover %lld of %lld vertices", row, (long long)d->nv);
+    e->nrows_total = row;
+    e->gather_from_u = (all_statemask1 && d->vdepth == 1) ? 1 : 0;
+
+    e->row_begin = 0; e->row_end = e->nrows_total;
+    if (d->row_end > 0) {
+      if (d->row_begin < 0 || d->row_begin > d->row_end || d->row_end > e->nrows_total) return fail(e, ND_B200_EINVAL, "row partition [%lld,%lld) outside 0..%lld", (long long)d->row_begin, (long long)d->row_end, e->nrows_total);
+      e->row_begin = d->row_begin; e->row_end = d->row_end;
+    }
+    nrows_owned = e->row_end - e->row_begin;
+
+    // gather offset of a vertex's output inside the gather source
+    goff.assign((size_t)d->nv, 0);
+    for (int b = 0; b < d->n_vbatches; ++b) {
+      const HostVB& h = e->hvb[b];
+      for (long long i = 0; i < h.count; ++i) {
+        long long vid = d->vbatches[b].indices ? d->vbatches[b].indices[i] : i + 1;
+        goff[(size_t)vid - 1] = e->gather_from_u ? (int)(h.state0 + i * h.dim) : (int)((h.row0 + i) * d->vdepth);
+      }
+    }
+    if (d->gather_offset) {
+      // multi-GPU packed halo: remote vertices are read from the halo buffer appended (logically) to the state vector
+      if (!e->gather_from_u) return fail(e, ND_B200_EUNSUPPORTED, "gather_offset needs StateMask vertices with one output");
+      if (d->gather_len < d->lastidx_dynamic || d->gather_len >= INT_MAX) return fail(e, ND_B200_EINVAL, "gather_len %lld outside [lastidx_dynamic, 2^31)", (long long)d->gather_len);
+      for (long long v = 0; v < d->nv; ++v) {
+        const long long o = d->gather_offset[v];
+        if (o < 0 || o >= d->gather_len) return fail(e, ND_B200_EINVAL, "gather_offset[%lld] = %lld outside [0, %lld)", v + 1, o, (long long)d->gather_len);
+        const int r = row_of_vertex[(size_t)v];
+        if (r >= e->row_begin && r < e->row_end && o != goff[(size_t)v]) return fail(e, ND_B200_EINVAL, "gather_offset of vertex %lld (an owned row) must be its own state offset", v + 1);
+        goff[(size_t)v] = (int)o;
+      }
+      e->halo_base = (int)d->lastidx_dynamic;
+      e->gather_len = d->gather_len;
     }
     return ND_B200_OK;
   }
-  if (upload(e, &e->d_rowptr, h_rowptr) || upload(e, &e->d_nbr, h_nbr) || upload(e, &e->d_blk_row, blk_row) ||
-      upload(e, &e->d_vb, dvb) || upload(e, &e->d_eb, deb))
-    return ND_B200_ECUDA;
-  if (any_epar && upload(e, &e->d_epar, h_epar)) return ND_B200_ECUDA;
-  if (!h_ebid.empty() && upload(e, &e->d_ebid, h_ebid)) return ND_B200_ECUDA;
-  if (!e->gather_from_u) {
-    for (int k = 0; k < 2; ++k) CUDA_TRY(e, cudaMalloc((void**)&e->d_vout[k], sizeof(double) * (size_t)(e->nrows_total * e->vdepth)));
+
+  // edge batches: registry check, wrappers, strides (register_edges!), kernel family of the network
+  int register_edges() {
+    // ---- edge batches --------------------------------------------------------------------------
+    long long eout_expect = out_expect;
+    std::vector<char> edge_seen((size_t)std::max<long long>(d->ne, 1), 0);
+    for (int b = 0; b < d->n_ebatches; ++b) {
+      const nd_b200_ebatch& eb = d->ebatches[b];
+      std::string why;
+      if (!edge_kind_ok(e, eb, d->vdepth, why)) return fail(e, ND_B200_EUNSUPPORTED, "%s (no CPU fallback)", why.c_str());
+      if (eb.outdim_dst != d->edepth) return fail(e, ND_B200_EINVAL, "edge batch %d: outdim.dst %d != edepth %d", b + 1, eb.outdim_dst, d->edepth);
+      e->c_pe = std::max(e->c_pe, eb.pdim);
+      if (eb.dim < 0 || eb.dim > (e->custom ? 16 : 2)) return fail(e, ND_B200_EUNSUPPORTED, "edge batch %d: dim %d", b + 1, eb.dim);
+      if (eb.dim > 0) {
+        // edges with states: outputs are StateMasks over a contiguous range of the edge's own states
+        if (d->row_end > 0 && (d->row_begin != 0 || d->row_end != e->nrows_total)) return fail(e, ND_B200_EUNSUPPORTED, "edges with states on a row-partitioned engine");
+        if (d->gather_offset) return fail(e, ND_B200_EUNSUPPORTED, "edges with states on a halo engine");
+        if (eb.state_first != state_expect) return fail(e, ND_B200_EINVAL, "edge batch %d: statestride.first %lld, expected %lld", b + 1, (long long)eb.state_first, state_expect);
+        if (eb.mask_dst_first < 1 || eb.mask_dst_first + eb.outdim_dst - 1 > eb.dim) return fail(e, ND_B200_EINVAL, "edge batch %d: dst StateMask outside 1..dim", b + 1);
+        if (eb.coupling == ND_B200_FIDUCIAL && (eb.mask_src_first < 1 || eb.mask_src_first + eb.outdim_src - 1 > eb.dim)) return fail(e, ND_B200_EINVAL, "edge batch %d: src StateMask outside 1..dim", b + 1);
+        state_expect += eb.count * eb.dim;
+        any_ode = true;
+      }
+      if (eb.coupling != ND_B200_ANTISYMMETRIC && eb.coupling != ND_B200_SYMMETRIC && eb.coupling != ND_B200_DIRECTED && eb.coupling != ND_B200_FIDUCIAL)
+        return fail(e, ND_B200_EUNSUPPORTED, "edge batch %d: unsupported output wrapper %d", b + 1, eb.coupling);
+      const int osrc_expect = eb.coupling == ND_B200_DIRECTED ? 0 : eb.outdim_dst;
+      if (eb.outdim_src != osrc_expect) return fail(e, ND_B200_EINVAL, "edge batch %d: outdim.src %d inconsistent with wrapper", b + 1, eb.outdim_src);
+      if (eb.out_first != eout_expect) return fail(e, ND_B200_EINVAL, "edge batch %d: outbufstride.first %lld, expected %lld", b + 1, (long long)eb.out_first, eout_expect);
+      if (eb.pdim < 0 || eb.pdim > 64) return fail(e, ND_B200_EINVAL, "edge batch %d: pdim %d", b + 1, eb.pdim);
+      if (eb.pdim > 0 && eb.p_first != p_expect) return fail(e, ND_B200_EINVAL, "edge batch %d: pstride.first %lld, expected %lld", b + 1, (long long)eb.p_first, p_expect);
+      p_expect += eb.count * eb.pdim;
+      if (eb.count <= 0 || eb.count > d->ne || (!eb.indices && d->n_ebatches != 1)) return fail(e, ND_B200_EINVAL, "edge batch %d is empty or larger than the graph", b + 1);
+      HostEB h{eb.kind, eb.coupling, eb.dim, eb.pdim, eb.outdim_src, eb.outdim_dst, eb.count, eb.p_first - 1, eb.out_first - 1,
+               eb.state_first - 1, eb.dim > 0 ? eb.mask_src_first - 1 : 0, eb.dim > 0 ? eb.mask_dst_first - 1 : 0};
+      e->heb.push_back(h);
+      eout_expect += eb.count * (eb.outdim_src + eb.outdim_dst);
+      if (eb.pdim > 0) any_epar = true;
+      for (long long i = 0; i < eb.count; ++i) {
+        long long eid = eb.indices ? eb.indices[i] : i + 1;
+        if (eid < 1 || eid > d->ne || edge_seen[(size_t)eid - 1]) return fail(e, ND_B200_EINVAL, "edge batch %d: bad or duplicate edge id %lld", b + 1, eid);
+        edge_seen[(size_t)eid - 1] = 1;
+      }
+    }
+    if (eout_expect - 1 != d->lastidx_out) return fail(e, ND_B200_EINVAL, "lastidx_out %lld inconsistent with batches (%lld)", (long long)d->lastidx_out, eout_expect - 1);
+    if (state_expect - 1 != d->lastidx_dynamic) return fail(e, ND_B200_EINVAL, "lastidx_dynamic %lld inconsistent with the batches (%lld)", (long long)d->lastidx_dynamic, state_expect - 1);
+    if (p_expect - 1 != d->lastidx_p) return fail(e, ND_B200_EINVAL, "lastidx_p %lld inconsistent with the batches (%lld)", (long long)d->lastidx_p, p_expect - 1);
+    e->ek = (d->n_ebatches == 1 && !any_ode) ? d->ebatches[0].kind : EK_GENERIC;   // entries of edges with states: generic kernels only
+    // precompiled specialisations exist for the benchmark edge kinds; every other registry kind runs in the generic kernels
+    if (!e->custom && d->vdepth == 1 && e->ek != ND_B200_E_DIFFUSION && e->ek != ND_B200_E_DIFFUSION_NOP && e->ek != ND_B200_E_KURAMOTO) e->ek = EK_GENERIC;
+    for (int b = 0; b < d->n_ebatches; ++b) any_fiducial = any_fiducial || d->ebatches[b].coupling == ND_B200_FIDUCIAL;
+    if (any_ode && (d->lastidx_dynamic >= ND_STATE_ENTRY_BIT || d->nv * (long long)d->vdepth >= ND_STATE_ENTRY_BIT))
+      return fail(e, ND_B200_EUNSUPPORTED, "networks with edge states need offsets below 2^30");
+    if (any_ode && !e->custom && d->vdepth != 1) return fail(e, ND_B200_EUNSUPPORTED, "edges with states and vdepth %d need user-supplied kinds", d->vdepth);
+    e->pack_pe = (!e->custom && e->ek != EK_GENERIC && d->n_ebatches == 1) ? d->ebatches[0].pdim : 0;
+    if (!e->custom && d->vdepth == 2 && d->n_ebatches > 1) {
+      // all (2,2) batches must be LINE_DQ with one coupling (single templated kernel)
+      for (int b = 1; b < d->n_ebatches; ++b)
+        if (d->ebatches[b].coupling != d->ebatches[0].coupling) return fail(e, ND_B200_EUNSUPPORTED, "mixed wrappers for dq lines");
+    }
+    return ND_B200_OK;
   }
-  if (upload(e, &e->d_tiles, tiles)) return ND_B200_ECUDA;
-  if (e->split) {
-    if (upload(e, &e->d_oidx, h_oidx) || upload(e, &e->d_es, h_es) || upload(e, &e->d_et, h_et)) return ND_B200_ECUDA;
-    if (generic_edges && (upload(e, &e->d_eepar, h_eepar) || upload(e, &e->d_eooff, h_eooff) || upload(e, &e->d_eebid, h_eebid))) return ND_B200_ECUDA;
-    CUDA_TRY(e, cudaMalloc((void**)&e->d_oedge, sizeof(double) * (size_t)std::max<long long>(e->oedge_len, 2)));
-    // the fused kernel's per-entry arrays are not needed
-    cudaFree(e->d_nbr); cudaFree(e->d_epar); cudaFree(e->d_ebid);
-    e->d_nbr = nullptr; e->d_epar = nullptr; e->d_ebid = nullptr;
+
+  // destination-sorted CSR over the owned rows in SequentialAggregator order (+ split-mode and get_buffers tables)
+  int build_csr() {
+    // ---- destination-sorted CSR over owned rows: count, then stable placement ---------------------
+    cnt.assign((size_t)nrows_owned + 1, 0);
+    for (int b = 0; b < d->n_ebatches; ++b) {
+      const nd_b200_ebatch& eb = d->ebatches[b];
+      for (long long i = 0; i < eb.count; ++i) {
+        const long long eid = eb.indices ? eb.indices[i] - 1 : i;
+        const long long s = d->edge_src[eid], t = d->edge_dst[eid];
+        if (s < 1 || s > d->nv || t < 1 || t > d->nv) return fail(e, ND_B200_EINVAL, "edge %lld endpoint out of range", eid + 1);
+        const int rs = row_of_vertex[(size_t)s - 1], rt = row_of_vertex[(size_t)t - 1];
+        if (eb.outdim_src > 0 && owned(rs)) cnt[(size_t)(rs - e->row_begin) + 1]++;
+        if (owned(rt)) cnt[(size_t)(rt - e->row_begin) + 1]++;
+      }
+    }
+    for (long long r = 0; r < nrows_owned; ++r) cnt[(size_t)r + 1] += cnt[(size_t)r];
+    e->nentries = cnt[(size_t)nrows_owned];
+    if (e->nentries >= INT_MAX) return fail(e, ND_B200_EUNSUPPORTED, "more than 2^31 directed entries on one device");
+    h_rowptr.assign((size_t)nrows_owned + 1, 0);
+    for (size_t r = 0; r < h_rowptr.size(); ++r) h_rowptr[r] = (int)cnt[r];
+    keep = !(d->flags & ND_B200_FLAG_NO_EXPORT);
+    h_nbr.assign((size_t)std::max<long long>(e->nentries, 1), 0);
+    // the precompiled generic kernels are instantiated with PE = 1 and read the parameter-offset stream even when no edge
+    // batch of this network has parameters
+    if (e->ek == EK_GENERIC && d->vdepth == 1 && !e->custom) any_epar = true;
+    if (any_epar) h_epar.assign((size_t)std::max<long long>(e->nentries, 1), 0);
+    if (e->ek == EK_GENERIC && (d->vdepth == 1 || e->custom)) h_ebid.assign((size_t)std::max<long long>(e->nentries, 1), 0);
+    if (keep) { e->h_nbr_vid.resize((size_t)e->nentries); e->h_eid.resize((size_t)e->nentries); e->h_side.resize((size_t)e->nentries); }
+    // split mode tables: per entry its position in the edge part of `o`; per edge (in `o` order) the gather offsets
+    generic_edges = (e->ek == EK_GENERIC && (d->vdepth == 1 || e->custom));
+    e->oedge_base = d->nv * (long long)d->vdepth;
+    e->oedge_len = d->lastidx_out - e->oedge_base;
+    e->ne_all = d->ne;
+    want_split = false;
+    if (const char* s = getenv("ND_B200_KERNEL")) want_split = !strcmp(s, "split") && nrows_owned == e->nrows_total && !(d->vdepth == 2 && d->n_ebatches > 1) && !e->custom && !any_ode && !any_fiducial;
+    if (want_split && e->oedge_len >= INT_MAX) return fail(e, ND_B200_EUNSUPPORTED, "edge output buffer exceeds 2^31 scalars on one device");
+    h_oidx.assign(want_split ? (size_t)std::max<long long>(e->nentries, 1) : 1, 0);
+    h_es.assign(want_split ? (size_t)std::max<long long>(d->ne, 1) : 1, 0);
+    h_et.assign(want_split ? (size_t)std::max<long long>(d->ne, 1) : 1, 0);
+    if (generic_edges && want_split) { h_eepar.assign((size_t)std::max<long long>(d->ne, 1), 0); h_eooff.assign((size_t)std::max<long long>(d->ne, 1), 0); h_eebid.assign((size_t)std::max<long long>(d->ne, 1), 0); }
+    {
+      long long kedge = 0;
+      std::vector<long long> cur(cnt.begin(), cnt.end() - 1);
+      for (int b = 0; b < d->n_ebatches; ++b) {
+        const nd_b200_ebatch& eb = d->ebatches[b];
+        for (long long i = 0; i < eb.count; ++i) {
+          const long long eid = eb.indices ? eb.indices[i] - 1 : i;
+          const long long s = d->edge_src[eid], t = d->edge_dst[eid];
+          const int rs = row_of_vertex[(size_t)s - 1], rt = row_of_vertex[(size_t)t - 1];
+          const int ep = eb.pdim > 0 ? (int)(eb.p_first - 1 + i * eb.pdim) : 0;
+          const long long oo = (eb.out_first - 1) + i * (eb.outdim_src + eb.outdim_dst) - e->oedge_base;   // this edge's block in the edge part of o
+          if (want_split) { h_es[(size_t)kedge] = goff[(size_t)s - 1]; h_et[(size_t)kedge] = goff[(size_t)t - 1]; }
+          if (generic_edges && want_split) { h_eepar[(size_t)kedge] = ep; h_eooff[(size_t)kedge] = (int)oo; h_eebid[(size_t)kedge] = (uint8_t)b; }
+          ++kedge;
+          // src output precedes dst output in `o` (register_edges!, src/network_structure.jl:244-245)
+          // edges with states contribute a StateMask read of their own states: the offset of the output state inside u,
+          // flagged with ND_STATE_ENTRY_BIT (state_entry_value in the kernels)
+          const int so_src = eb.dim > 0 ? (int)((eb.state_first - 1) + i * eb.dim + (eb.coupling == ND_B200_FIDUCIAL ? eb.mask_src_first - 1 : eb.mask_dst_first - 1)) | ND_STATE_ENTRY_BIT : 0;
+          const int so_dst = eb.dim > 0 ? (int)((eb.state_first - 1) + i * eb.dim + (eb.mask_dst_first - 1)) | ND_STATE_ENTRY_BIT : 0;
+          if (eb.outdim_src > 0 && owned(rs)) {
+            const long long j = cur[(size_t)(rs - e->row_begin)]++;
+            if (want_split) h_oidx[(size_t)j] = (int)oo;
+            h_nbr[(size_t)j] = eb.dim > 0 ? ~so_src : ~goff[(size_t)t - 1];
+            if (any_epar) h_epar[(size_t)j] = ep;
+            if (!h_ebid.empty()) h_ebid[(size_t)j] = (uint8_t)b;
+            if (keep) { e->h_nbr_vid[(size_t)j] = (int)t; e->h_eid[(size_t)j] = (int)(eid + 1); e->h_side[(size_t)j] = 1; }
+          }
+          if (owned(rt)) {
+            const long long j = cur[(size_t)(rt - e->row_begin)]++;
+            if (want_split) h_oidx[(size_t)j] = (int)(oo + eb.outdim_src);
+            h_nbr[(size_t)j] = eb.dim > 0 ? so_dst : goff[(size_t)s - 1];
+            if (any_epar) h_epar[(size_t)j] = ep;
+            if (!h_ebid.empty()) h_ebid[(size_t)j] = (uint8_t)b;
+            if (keep) { e->h_nbr_vid[(size_t)j] = (int)s; e->h_eid[(size_t)j] = (int)(eid + 1); e->h_side[(size_t)j] = 0; }
+          }
+        }
+      }
+    }
+    if (keep) e->h_rowptr.assign(cnt.begin(), cnt.end());
+    // rows that read the halo ("boundary" rows); everything else can run while the halo is in flight
+    row_remote.assign((size_t)nrows_owned, 0);
+    if (d->gather_offset) {
+      for (long long r = 0; r < nrows_owned; ++r)
+        for (long long j = cnt[(size_t)r]; j < cnt[(size_t)r + 1]; ++j) {
+          const int o = h_nbr[(size_t)j] < 0 ? ~h_nbr[(size_t)j] : h_nbr[(size_t)j];
+          if (o >= e->halo_base) { row_remote[(size_t)r] = 1; break; }
+        }
+    }
+
+    // get_buffers tables: gather offsets per edge in batch order
+    if (keep) {
+      e->h_esrc_off.resize((size_t)d->n_ebatches); e->h_edst_off.resize((size_t)d->n_ebatches);
+      for (int b = 0; b < d->n_ebatches; ++b) {
+        const nd_b200_ebatch& eb = d->ebatches[b];
+        e->h_esrc_off[(size_t)b].resize((size_t)eb.count); e->h_edst_off[(size_t)b].resize((size_t)eb.count);
+        for (long long i = 0; i < eb.count; ++i) {
+          const long long eid = eb.indices ? eb.indices[i] - 1 : i;
+          e->h_esrc_off[(size_t)b][(size_t)i] = goff[(size_t)d->edge_src[eid] - 1];
+          e->h_edst_off[(size_t)b][(size_t)i] = goff[(size_t)d->edge_dst[eid] - 1];
+        }
+      }
+    }
+    return ND_B200_OK;
   }
-  return ND_B200_OK;
-}
+
+  // launch shape, thread-block row ranges, one descriptor per thread block (tile kernel)
+  int plan_tiles() {
+    // ---- launch shape + thread-block row ranges ----------------------------------------------------
+    e->block = 128; e->ept = 4;   // measured best on B200 for every registry family (profiles/r01_tuning.md)
+    if (const char* s = getenv("ND_B200_BLOCK")) e->block = atoi(s);
+    if (const char* s = getenv("ND_B200_EPT")) e->ept = atoi(s);
+    if (!((e->block == 256 || e->block == 128) && (e->ept == 8 || e->ept == 4))) return fail(e, ND_B200_EINVAL, "ND_B200_BLOCK/ND_B200_EPT must be 128|256 / 4|8");
+    const int tile = e->block * e->ept;
+    e->n_long = 0;
+    for (size_t b = 0; b < e->hvb.size(); ++b) {
+      const HostVB& h = e->hvb[b];
+      VBDev v{h.kind, h.dim, h.pdim, (int)h.row0, (int)h.count, (int)blk_row.size(), h.state0, h.p0};
+      long long r = std::max<long long>(h.row0, e->row_begin);
+      const long long rend = std::min<long long>(h.row0 + h.count, e->row_end);
+      while (r < rend) {
+        blk_row.push_back((int)r);
+        const long long deg0 = cnt[(size_t)(r - e->row_begin) + 1] - cnt[(size_t)(r - e->row_begin)];
+        if (deg0 > e->long_thr) { e->n_long++; r++; continue; }
+        long long rr = r, ents = 0;
+        while (rr < rend && rr - r < e->block) {
+          const long long deg = cnt[(size_t)(rr - e->row_begin) + 1] - cnt[(size_t)(rr - e->row_begin)];
+          if (deg > e->long_thr || ents + deg > tile) break;
+          ents += deg; rr++;
+        }
+        if (rr == r) {   // a single short row that does not fit a tile: only when long_thr >= tile
+          return fail(e, ND_B200_EUNSUPPORTED, "row with %lld entries exceeds the %d-entry tile with long rows disabled", deg0, tile);
+        }
+        r = rr;
+      }
+      dvb.push_back(v);
+    }
+    e->nblocks = (int)blk_row.size();
+    blk_row.push_back((int)e->row_end);
+
+    // owned state ranges: one per vertex batch the row range intersects
+    for (const HostVB& h : e->hvb) {
+      const long long lo = std::max<long long>(e->row_begin, h.row0), hi = std::min<long long>(e->row_end, h.row0 + h.count);
+      if (lo < hi && h.dim > 0) e->own_segs.push_back({h.state0 + (lo - h.row0) * h.dim, (hi - lo) * h.dim});
+    }
+    // ---- one 16-byte descriptor per thread block -----------------------------------------------------------
+    e->split = 0;   // default: fused kernel (faster on B200 for every config whose state vector fits in L2)
+    if (want_split) e->split = 1;
+    {
+      tiles.reserve((size_t)e->nblocks);
+      size_t bi = 0;
+      for (int k = 0; k < e->nblocks; ++k) {
+        const int r0 = blk_row[(size_t)k], r1 = blk_row[(size_t)k + 1];
+        while (bi + 1 < dvb.size() && k >= dvb[bi + 1].blk0) ++bi;
+        const long long a = cnt[(size_t)(r0 - e->row_begin)], z = cnt[(size_t)(r1 - e->row_begin)];
+        const long long ne = z - a;
+        const bool is_long = (r1 - r0 == 1) && ne > e->long_thr;
+        int4 t;
+        t.x = r0; t.y = (int)a;
+        if (is_long) { t.z = (int)ne; t.w = (int)(0x80000000u | ((unsigned)bi << 25) | (1u << 16)); }
+        else { t.z = 0; t.w = (int)((unsigned)ne | ((unsigned)(r1 - r0) << 16) | ((unsigned)bi << 25)); }
+        tiles.push_back(t);
+      }
+      e->ntiles = (int)tiles.size();
+      e->wait_from = 0;
+      if (d->gather_offset) {
+        // interior tiles first, tiles that read the halo last (each descriptor is self-contained)
+        auto reads_halo = [&](const int4& t) {
+          const int nr = (t.w < 0) ? 1 : ((t.w >> 16) & 0x1FF);
+          for (int r = 0; r < nr; ++r)
+            if (row_remote[(size_t)(t.x + r - e->row_begin)]) return true;
+          return false;
+        };
+        auto mid = std::stable_partition(tiles.begin(), tiles.end(), [&](const int4& t) { return !reads_halo(t); });
+        e->wait_from = (int)(mid - tiles.begin());
+      }
+      e->blk_pmax.assign(tiles.size(), 0); e->blk_rmin.assign(tiles.size(), 0); e->blk_rmax.assign(tiles.size(), 0);
+      for (size_t k = 0; k < tiles.size(); ++k) {
+        const int4& t = tiles[k];
+        const bool lg = t.w < 0;
+        const int nr = lg ? 1 : ((t.w >> 16) & 0x1FF), ne = lg ? t.z : (t.w & 0xFFFF);
+        const size_t b = (size_t)((t.w >> 25) & 0x3F);
+        int pm = row_pend(t.x + nr - 1, b);
+        for (long long j = t.y; j < (long long)t.y + ne; ++j) pm = std::max(pm, entry_pend(j));
+        e->blk_pmax[k] = pm; e->blk_rmin[k] = t.x; e->blk_rmax[k] = t.x + nr - 1;
+      }
+    }
+    for (const HostEB& h : e->heb) deb.push_back(EBDev{h.kind, h.coupling, h.pdim, h.dim});
+    return ND_B200_OK;
+  }
+
+  // kernel family choice + the jagged (warp-slice) layout
+  int build_jagged() {
+    // ---- jagged layout: 32-lane slices, column-major compacted entries (rhs_jag_kernel) ------------------------
+    // ND_B200_KERNEL=jag|fused|split overrides the automatic choice.  A strictly sequential long_row_threshold beyond
+    // what one lane can hold (63 entries) needs the tile kernel.
+    // Kernel family (measured on B200, profiles/r01c_sweep_fused_vs_jag.jsonl): the tile kernel wins whenever degrees
+    // vary (idle lanes in the jagged walk: ER cfg2 72 vs 76 us, BA cfg3 91 vs 148 us) or the graph is small (latency of the
+    // per-lane walk: cfg1); the jagged kernel wins on large regular-degree graphs (cfg4 grid: RK4 step 45 vs 55 us).
+    // auto = jagged iff lane utilisation of the walk >= 0.8 and there are enough rows to fill the machine.
+    {
+      long long sum_max = 0;
+      for (long long r = 0; r < nrows_owned; r += 32) {
+        long long m = 0;
+        for (long long q = r; q < std::min<long long>(r + 32, nrows_owned); ++q) m = std::max(m, cnt[(size_t)q + 1] - cnt[(size_t)q]);
+        sum_max += m;
+      }
+      const double util = sum_max > 0 ? (double)e->nentries / (32.0 * (double)sum_max) : 0.0;
+      e->jag = (util >= 0.8 && nrows_owned >= 65536) ? 1 : 0;
+    }
+    if (const char* s = getenv("ND_B200_KERNEL")) {
+      if (!strcmp(s, "jag")) e->jag = 1;
+      else if (!strcmp(s, "fused") || !strcmp(s, "split") || !strcmp(s, "v1")) e->jag = 0;
+    }
+    if (e->split) e->jag = 0;
+    if (d->long_row_threshold > 63 * 32) e->jag = 0;
+    e->jag_u = 2;
+    e->jag_wps = d->vdepth == 2 ? 32 : 48;   // spill-free register budgets, best measured
+    jag_pe = any_epar || (generic_edges && !e->custom);   // kernels instantiated with PE > 0 read {nbr, epar} pairs
+    if (e->jag) {
+      e->jsplit = 32;
+      if (const char* s = getenv("ND_B200_JAG_SPLIT")) e->jsplit = std::min(63, std::max(1, atoi(s)));
+      if (const char* s = getenv("ND_B200_JAG_U")) e->jag_u = atoi(s);
+      if (const char* s = getenv("ND_B200_JAG_WPS")) e->jag_wps = atoi(s);
+      int jwindow = 32;
+      if (const char* s = getenv("ND_B200_JAG_WINDOW")) { const int w = atoi(s); if (w == 64 || w == 128) jwindow = w; }
+      // rows longer than this are reduced by a whole block: explicit threshold if the caller gave one, else what a
+      // slice can hold
+      const long long block_thr = d->long_row_threshold > 0 ? std::min<long long>(d->long_row_threshold, 32LL * e->jsplit) : 32LL * e->jsplit;
+      std::vector<int> order;
+      order.reserve((size_t)e->nentries);
+      struct Lane { int rowrel, len, head; long long start; };
+      std::vector<Lane> lanes;
+      std::vector<std::pair<long long, int>> long_rows;   // (row, batch)
+      int jag_wait_from = 0;
+      const int nclasses = d->gather_offset ? 2 : 1;   // class 0: interior rows, class 1: rows that read the halo
+      for (int cls = 0; cls < nclasses; ++cls) {
+      if (cls == 1) jag_wait_from = (int)jslices.size();
+      for (size_t b = 0; b < e->hvb.size(); ++b) {
+        const HostVB& h = e->hvb[b];
+        const long long lo = std::max<long long>(h.row0, e->row_begin), hi = std::min<long long>(h.row0 + h.count, e->row_end);
+        long long row0 = -1;
+        int maxparts = 1;
+        auto flush = [&]() {
+          if (lanes.empty()) return;
+          int maxlen = 0;
+          for (const Lane& L : lanes) maxlen = std::max(maxlen, L.len);
+          const int e0 = (int)order.size();
+          for (int j = 0; j < maxlen; ++j)
+            for (const Lane& L : lanes)
+              if (L.len > j) order.push_back((int)(L.start + j));
+          jslices.push_back(make_int4(e0, (int)row0, (int)b, maxparts));
+          for (int l = 0; l < 32; ++l) {
+            uint16_t v = 0;
+            if (l < (int)lanes.size()) v = (uint16_t)(lanes[(size_t)l].len | (lanes[(size_t)l].rowrel << 6) | (lanes[(size_t)l].head << 13) | (1 << 14));
+            jlanes.push_back(v);
+          }
+          lanes.clear(); row0 = -1; maxparts = 1;
+        };
+        if (jwindow > 32) {
+          // degree-bucketed slices (ND_B200_JAG_WINDOW = 64 | 128): the rows of a window of consecutive rows are dealt to
+          // the lanes in order of decreasing degree, so the 32 rows that share a slice have (nearly) equal length and the
+          // lane walk wastes no iterations on short rows next to long ones; lanes address their row relative to the window
+          // start (7 bits).  The row's own u / du / vertex parameters stay within the window (<= 1 KB of each vector).
+          std::vector<long long> wrows;
+          for (long long w0 = lo; w0 < hi; w0 += jwindow) {
+            wrows.clear();
+            for (long long r = w0; r < std::min<long long>(w0 + jwindow, hi); ++r) {
+              if (nclasses == 2 && row_remote[(size_t)(r - e->row_begin)] != cls) continue;
+              const long long deg = cnt[(size_t)(r - e->row_begin) + 1] - cnt[(size_t)(r - e->row_begin)];
+              const int nparts = (int)std::max<long long>(1, (deg + e->jsplit - 1) / e->jsplit);
+              if (deg > block_thr || nparts > 32) { long_rows.push_back({r, (int)b}); continue; }
+              wrows.push_back(r);
+            }
+            std::stable_sort(wrows.begin(), wrows.end(), [&](long long x, long long y) {
+              return cnt[(size_t)(x - e->row_begin) + 1] - cnt[(size_t)(x - e->row_begin)] > cnt[(size_t)(y - e->row_begin) + 1] - cnt[(size_t)(y - e->row_begin)];
+            });
+            for (long long r : wrows) {
+              const long long a = cnt[(size_t)(r - e->row_begin)], deg = cnt[(size_t)(r - e->row_begin) + 1] - a;
+              const int nparts = (int)std::max<long long>(1, (deg + e->jsplit - 1) / e->jsplit);
+              if ((int)lanes.size() + nparts > 32) flush();
+              if (lanes.empty()) row0 = w0;
+              for (int k = 0; k < nparts; ++k) {
+                const long long len = std::min<long long>(e->jsplit, deg - (long long)k * e->jsplit);
+                lanes.push_back(Lane{(int)(r - w0), (int)std::max<long long>(len, 0), k == 0, a + (long long)k * e->jsplit});
+              }
+              maxparts = std::max(maxparts, nparts);
+            }
+            flush();
+          }
+        } else {
+        for (long long r = lo; r < hi; ++r) {
+          if (nclasses == 2 && row_remote[(size_t)(r - e->row_begin)] != cls) continue;
+          const long long a = cnt[(size_t)(r - e->row_begin)], deg = cnt[(size_t)(r - e->row_begin) + 1] - a;
+          const int nparts = (int)std::max<long long>(1, (deg + e->jsplit - 1) / e->jsplit);
+          if (deg > block_thr || nparts > 32) { long_rows.push_back({r, (int)b}); continue; }
+          if ((int)lanes.size() + nparts > 32 || (row0 >= 0 && r - row0 >= 32)) flush();
+          if (lanes.empty()) row0 = r;
+          for (int k = 0; k < nparts; ++k) {
+            const long long len = std::min<long long>(e->jsplit, deg - (long long)k * e->jsplit);
+            lanes.push_back(Lane{(int)(r - row0), (int)std::max<long long>(len, 0), k == 0, a + (long long)k * e->jsplit});
+          }
+          maxparts = std::max(maxparts, nparts);
+        }
+        flush();
+        }
+      }
+      }
+      if (nclasses == 1) jag_wait_from = 0;
+      for (const auto& lr : long_rows) {
+        const long long a = cnt[(size_t)(lr.first - e->row_begin)], deg = cnt[(size_t)(lr.first - e->row_begin) + 1] - a;
+        jlong.push_back(make_int4((int)order.size(), (int)lr.first, (int)deg, lr.second));
+        for (long long j = 0; j < deg; ++j) order.push_back((int)(a + j));
+      }
+      if ((long long)order.size() != e->nentries) return fail(e, ND_B200_EINVAL, "internal: jagged layout holds %lld of %lld entries", (long long)order.size(), e->nentries);
+      if (jag_pe) {
+        jent.resize(std::max<size_t>(order.size(), 1));
+        for (size_t k = 0; k < order.size(); ++k) jent[k] = make_int2(h_nbr[(size_t)order[k]], any_epar ? h_epar[(size_t)order[k]] : 0);
+      } else {
+        jnbr.resize(std::max<size_t>(order.size(), 1));
+        for (size_t k = 0; k < order.size(); ++k) jnbr[k] = h_nbr[(size_t)order[k]];
+      }
+      if (!h_ebid.empty()) {
+        jebid.resize(std::max<size_t>(order.size(), 1));
+        for (size_t k = 0; k < order.size(); ++k) jebid[k] = h_ebid[(size_t)order[k]];
+      }
+      e->host_only = (d->flags & ND_B200_FLAG_HOST_ONLY) != 0;
+      if (e->host_only) { e->h_jslices = jslices; e->h_jlong = jlong; e->h_jlanes = jlanes; e->h_jorder = order; }
+      {
+        const size_t nb = (jslices.size() + 3) / 4;
+        e->blk_pmax.assign(nb + jlong.size(), 0); e->blk_rmin.assign(nb + jlong.size(), INT_MAX); e->blk_rmax.assign(nb + jlong.size(), -1);
+        for (size_t sidx = 0; sidx < jslices.size(); ++sidx) {
+          const size_t k = sidx / 4;
+          const int4& S = jslices[sidx];
+          const long long eend = sidx + 1 < jslices.size() ? jslices[sidx + 1].x : (jlong.empty() ? (long long)order.size() : jlong[0].x);
+          int pm = e->blk_pmax[k];
+          for (long long q = S.x; q < eend; ++q) pm = std::max(pm, entry_pend(order[(size_t)q]));
+          for (int l = 0; l < 32; ++l) {
+            const uint16_t v = jlanes[sidx * 32 + (size_t)l];
+            if (!((v >> 14) & 1)) break;
+            const int r = S.y + ((v >> 6) & 127);
+            e->blk_rmin[k] = std::min(e->blk_rmin[k], r); e->blk_rmax[k] = std::max(e->blk_rmax[k], r);
+            pm = std::max(pm, row_pend(r, (size_t)S.z));
+          }
+          e->blk_pmax[k] = pm;
+        }
+        for (size_t q = 0; q < jlong.size(); ++q) {
+          const int4& Lr = jlong[q];
+          int pm = row_pend(Lr.y, (size_t)Lr.w);
+          for (long long j = Lr.x; j < (long long)Lr.x + Lr.z; ++j) pm = std::max(pm, entry_pend(order[(size_t)j]));
+          e->blk_pmax[nb + q] = pm; e->blk_rmin[nb + q] = Lr.y; e->blk_rmax[nb + q] = Lr.y;
+        }
+      }
+      e->wait_from = jag_wait_from;
+      e->nslices = (int)jslices.size();
+      e->n_jag_blocks = (e->nslices + 3) / 4;   // BLOCK = 128: four slices per thread block
+      e->n_jlong = (int)jlong.size();
+      e->nblocks = e->n_jag_blocks + e->n_jlong;
+      e->n_long = e->n_jlong;
+    }
+
+    e->blk_rows_monotone = true;
+    for (size_t k = 0; k + 1 < e->blk_rmin.size(); ++k)
+      if (e->blk_rmin[k + 1] <= e->blk_rmax[k]) { e->blk_rows_monotone = false; break; }
+    return ND_B200_OK;
+  }
+
+  // run-time compilation of user-supplied kinds, uploads
+  int finish() {
+    if (d->flags & ND_B200_FLAG_HOST_ONLY) e->host_only = true;
+    if (e->custom) {
+      if (e->jag) { e->jag_wps = 48; e->jag_u = 2; }   // the one jagged instantiation that is compiled for user-supplied kinds
+      if (int rc = compile_custom(e, d->vdepth, e->edepth)) return rc;
+    }
+    if (e->host_only) return ND_B200_OK;
+    CUDA_TRY(e, cudaSetDevice(e->device));
+    for (int b = 0; b < d->n_ebatches; ++b) {
+      const nd_b200_ebatch& eb = d->ebatches[b];
+      if (eb.dim == 0) continue;
+      std::vector<int> es((size_t)eb.count), et((size_t)eb.count);
+      for (long long i = 0; i < eb.count; ++i) {
+        const long long eid = eb.indices ? eb.indices[i] - 1 : i;
+        es[(size_t)i] = goff[(size_t)d->edge_src[eid] - 1];
+        et[(size_t)i] = goff[(size_t)d->edge_dst[eid] - 1];
+      }
+      nd_b200_engine::OdeBatch ob{b, nullptr, nullptr};
+      if (upload(e, &ob.d_es, es) || upload(e, &ob.d_et, et)) return ND_B200_ECUDA;
+      e->ode.push_back(ob);
+    }
+    if (e->jag) {
+      if (upload(e, &e->d_vb, dvb) || upload(e, &e->d_eb, deb) || upload(e, &e->d_jslices, jslices) || upload(e, &e->d_jlanes, jlanes) ||
+          upload(e, &e->d_jlong, jlong))
+        return ND_B200_ECUDA;
+      if (jag_pe ? upload(e, &e->d_jent, jent) : upload(e, &e->d_jnbr, jnbr)) return ND_B200_ECUDA;
+      if (!jebid.empty() && upload(e, &e->d_jebid, jebid)) return ND_B200_ECUDA;
+      if (!e->gather_from_u) {
+        for (int k = 0; k < 2; ++k) CUDA_TRY(e, cudaMalloc((void**)&e->d_vout[k], sizeof(double) * (size_t)(e->nrows_total * e->vdepth)));
+      }
+      return ND_B200_OK;
+    }
+    if (upload(e, &e->d_rowptr, h_rowptr) || upload(e, &e->d_nbr, h_nbr) || upload(e, &e->d_blk_row, blk_row) ||
+        upload(e, &e->d_vb, dvb) || upload(e, &e->d_eb, deb))
+      return ND_B200_ECUDA;
+    if (any_epar && upload(e, &e->d_epar, h_epar)) return ND_B200_ECUDA;
+    if (!h_ebid.empty() && upload(e, &e->d_ebid, h_ebid)) return ND_B200_ECUDA;
+    if (!e->gather_from_u) {
+      for (int k = 0; k < 2; ++k) CUDA_TRY(e, cudaMalloc((void**)&e->d_vout[k], sizeof(double) * (size_t)(e->nrows_total * e->vdepth)));
+    }
+    if (upload(e, &e->d_tiles, tiles)) return ND_B200_ECUDA;
+    if (e->split) {
+      if (upload(e, &e->d_oidx, h_oidx) || upload(e, &e->d_es, h_es) || upload(e, &e->d_et, h_et)) return ND_B200_ECUDA;
+      if (generic_edges && (upload(e, &e->d_eepar, h_eepar) || upload(e, &e->d_eooff, h_eooff) || upload(e, &e->d_eebid, h_eebid))) return ND_B200_ECUDA;
+      CUDA_TRY(e, cudaMalloc((void**)&e->d_oedge, sizeof(double) * (size_t)std::max<long long>(e->oedge_len, 2)));
+      // the fused kernel's per-entry arrays are not needed
+      cudaFree(e->d_nbr); cudaFree(e->d_epar); cudaFree(e->d_ebid);
+      e->d_nbr = nullptr; e->d_epar = nullptr; e->d_ebid = nullptr;
+    }
+    return ND_B200_OK;
+    return ND_B200_OK;
+  }
+
+  int run() {
+    if (int rc = check_descriptor()) return rc;
+    if (int rc = register_vertices()) return rc;
+    if (int rc = register_edges()) return rc;
+    if (int rc = build_csr()) return rc;
+    if (int rc = plan_tiles()) return rc;
+    if (int rc = build_jagged()) return rc;
+    return finish();
+  }
+};
+
+int build_engine(nd_b200_engine* e, const nd_b200_desc* d) { return EngineBuilder(e, d).run(); }
 
 int check_call(nd_b200_engine* e, const void* du, const void* u, const void* p) {
   if (!e) return ND_B200_EINVAL;
