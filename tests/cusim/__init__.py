@@ -6,6 +6,11 @@ that points the package's ctypes binding at that library for the duration of a t
 real kernel code (tile kernel, jagged kernel, long rows, RK4 epilogues, get_buffers, run-time compiled kinds, the NVLink
 publish / wait protocol with emulated ranks as threads) against the oracle.
 
+What the emulated runtime checks beyond results (cusim_rt.cpp): warp collectives / barriers complete only with every named
+lane present (divergence is an error, not a hang); non-null streams are deferred, so a missing event dependency between
+streams gives a wrong result; device allocations end at a guard page (out-of-bounds accesses fault); CUSIM_ORDER=reverse|
+shuffle permutes the order in which a block's threads run between scheduling points (data races change results).
+
 The product never loads this library: `networkdynamics.jl_b200._cabi.lib()` only ever opens libnd_b200.so and fails
 loudly without it.  "Device" vectors of the emulated engine are numpy arrays wrapped in `DeviceArray`.
 """
