@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define ND_B200_ABI_VERSION 4
+#define ND_B200_ABI_VERSION 5
 
 /* status codes (Julia glue rethrows: EINVAL -> ArgumentError, others -> ErrorException) */
 enum {
@@ -66,6 +66,13 @@ typedef struct nd_b200_vbatch {
   int64_t p_first;         /* pstride.first                                  */
   int64_t out_first;       /* outbufstride.first                             */
   int64_t aggr_first;      /* inbufstride.first (aggbuf)                     */
+  /* external inputs (src/external_inputs.jl; user-supplied kinds only): extdim scalars per component, gathered before f
+   * like collect_externals! (src/coreloop.jl:61).  ext_src[i*extdim + k] is entry extbuf_range(batch,i)[k] of the
+   * reference's ExtMap: > 0 = StateBufIdx (1-based index into u), < 0 = -(OutBufIdx) (1-based index into o; must be an
+   * output of a vertex or of an edge with states -- outputs of feed-forward components are refused like in the
+   * reference, src/external_inputs.jl:42-44).  extdim = 0 / ext_src = NULL: none. */
+  int32_t extdim, reserved;
+  const int64_t* ext_src;
 } nd_b200_vbatch;
 
 /* One `ComponentBatch` of edges (register_edges!, src/network_structure.jl:240-258). */
@@ -81,6 +88,8 @@ typedef struct nd_b200_ebatch {
    * (1-based), wrapped by AntiSymmetric / Symmetric / Directed, or Fiducial(src=..., dst=...) with its own
    * mask_src_first.  0 when dim == 0. */
   int32_t mask_src_first, mask_dst_first;
+  int32_t extdim, reserved;      /* external inputs of edges with states, as in nd_b200_vbatch */
+  const int64_t* ext_src;
 } nd_b200_ebatch;
 
 /* ---- user-supplied component kinds (runtime-compiled, NVRTC) ---------------------------------------------------------
@@ -97,6 +106,8 @@ typedef struct nd_b200_ebatch {
  *              void g(double* e_src, double* e_dst, const double* v_src, const double* v_dst, const double* p, double t)
  *   edge f   : void f(double* de, const double* e, const double* v_src, const double* v_dst, const double* p, double t)
  *              for edges with states (custom_kind.dim > 0); their outputs are the StateMasks of ebatch.mask_*
+ *   with external inputs (custom_kind.extdim > 0) f takes them like in the reference, right after the inputs:
+ *              vertex f(dv, v, esum, ext, p, t);   edge f(de, e, v_src, v_dst, ext, p, t)
  * Compiled with --fmad=false like the registry kernels.  A body that does not compile fails nd_b200_create with
  * ND_B200_EINVAL and the NVRTC log in nd_b200_last_error. */
 #define ND_B200_CUSTOM_KIND_BASE 1000
@@ -107,6 +118,7 @@ typedef struct nd_b200_custom_kind {
   int32_t two_sided;       /* edge only: body has the Fiducial signature                         */
   const char* f_body;      /* vertex: body of f; static edge: body of g; edge with states: body of f */
   const char* g_body;      /* vertex: body of g, or NULL for StateMask(1:outdim); edge: NULL      */
+  int32_t extdim, reserved; /* number of external inputs f takes (0: none)                       */
 } nd_b200_custom_kind;
 
 typedef struct nd_b200_desc {

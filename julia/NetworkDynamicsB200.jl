@@ -18,7 +18,7 @@ using CUDA: CuArray, CuPtr, stream
 import NetworkDynamics: aggregate!, get_aggr_constructor, iscudacompatible, aggfun
 
 const libnd_b200 = get(ENV, "ND_B200_LIB", "libnd_b200.so")
-const ABI_VERSION = Cint(4)
+const ABI_VERSION = Cint(5)
 
 # ---- tags ---------------------------------------------------------------------------------------------------------
 "`ExecutionStyle` tag (field-less: only its type is stored in `Network{EX,...}`, src/network_structure.jl:83,116)."
@@ -62,6 +62,7 @@ const CUSTOM_KIND_BASE = Cint(1000)
 struct CCustomKind
     kind::Cint; role::Cint; dim::Cint; pdim::Cint; outdim::Cint; two_sided::Cint
     f_body::Cstring; g_body::Cstring
+    extdim::Cint; reserved::Cint
 end
 
 # ---- C structs (mirror include/nd_b200.h) ---------------------------------------------------------------------------
@@ -69,12 +70,14 @@ struct CVBatch
     kind::Cint; dim::Cint; pdim::Cint; outdim::Cint
     count::Int64; indices::Ptr{Int64}
     state_first::Int64; p_first::Int64; out_first::Int64; aggr_first::Int64
+    extdim::Cint; reserved::Cint; ext_src::Ptr{Int64}     # external inputs: ExtMap entries of the batch (see _ext_table)
 end
 struct CEBatch
     kind::Cint; coupling::Cint; dim::Cint; pdim::Cint; outdim_src::Cint; outdim_dst::Cint
     count::Int64; indices::Ptr{Int64}
     state_first::Int64; p_first::Int64; out_first::Int64; gbuf_first::Int64
     mask_src_first::Cint; mask_dst_first::Cint      # edges with states: StateMask outputs (0 for static edges)
+    extdim::Cint; reserved::Cint; ext_src::Ptr{Int64}
 end
 struct CDesc
     abi_version::Cint; device::Cint
@@ -115,10 +118,19 @@ function B200Aggregator(im::IndexManager, edgebatches, f)
     vidxs = _find_identical_components(im.vertexm)
     keep = Any[]
     customs = CCustomKind[]                  # user-supplied kinds referenced by the batches
-    function custom_kind!(role, d, pd, od, two_sided, fsrc, gsrc)
+    # external inputs (src/external_inputs.jl): the reference's own ExtMap, one signed index per slot of the external-input
+    # buffer -- StateBufIdx(i) -> +i (into u), OutBufIdx(i) -> -i (into o) -- laid out per batch as count x extdim
+    extmap = NetworkDynamics.has_external_input(im) ? NetworkDynamics.ExtMap(im).map : nothing
+    function _ext_table(ranges, idxs, xd)
+        xd == 0 && return Ptr{Int64}(C_NULL)
+        tab = Int64[(m = extmap[r[k]]; m isa NetworkDynamics.StateBufIdx ? m.idx : -m.idx) for i in idxs for r in (ranges[i],) for k in 1:xd]
+        push!(keep, tab)
+        pointer(tab)
+    end
+    function custom_kind!(role, d, pd, od, two_sided, fsrc, gsrc, xd=0)
         fb = Base.unsafe_convert(Cstring, Base.cconvert(Cstring, fsrc)); push!(keep, fsrc)
         gb = isnothing(gsrc) ? Cstring(C_NULL) : (push!(keep, gsrc); Base.unsafe_convert(Cstring, Base.cconvert(Cstring, gsrc)))
-        push!(customs, CCustomKind(CUSTOM_KIND_BASE + length(customs), role, d, pd, od, two_sided, fb, gb))
+        push!(customs, CCustomKind(CUSTOM_KIND_BASE + length(customs), role, d, pd, od, two_sided, fb, gb, xd, 0))
         customs[end].kind
     end
     vb = map(vidxs) do idxs
@@ -126,13 +138,16 @@ function B200Aggregator(im::IndexManager, edgebatches, f)
         kind = vertex_kernel(compf(m), compg(m))
         if isnothing(kind) && !isnothing(cuda_source(compf(m)))      # user-supplied kind
             gs = compg(m) isa StateMask ? nothing : cuda_source(compg(m))
-            kind = custom_kind!(0, dim(m), pdim(m), outdim(m), 0, cuda_source(compf(m)), gs)
+            kind = custom_kind!(0, dim(m), pdim(m), outdim(m), 0, cuda_source(compf(m)), gs, NetworkDynamics.extdim(m))
         end
+        xd = NetworkDynamics.extdim(m)
+        (xd > 0 && kind < CUSTOM_KIND_BASE) && throw(ArgumentError("B200 engine: external inputs need a cuda_source vertex function (no CPU fallback)"))
         isnothing(kind) && throw(ArgumentError("vertex model $(m.name) has neither a registry kernel nor a cuda_source (no CPU fallback)"))
         ix = Vector{Int64}(idxs); push!(keep, ix)
         i1 = first(idxs)
         CVBatch(kind, dim(m), pdim(m), outdim(m), length(ix), pointer(ix),
-                first(im.v_data[i1]), first(im.v_para[i1]), first(im.v_out[i1]), first(im.v_aggr[i1]))
+                first(im.v_data[i1]), first(im.v_para[i1]), first(im.v_out[i1]), first(im.v_aggr[i1]),
+                xd, 0, _ext_table(im.v_ext, idxs, xd))
     end
     eb = map(collect(edgebatches)) do b
         g = compg(b)
@@ -148,7 +163,7 @@ function B200Aggregator(im::IndexManager, edgebatches, f)
             msrc, mdst = ms, md
             kind = edge_f_kernel(compf(b))
             if isnothing(kind) && !isnothing(cuda_source(compf(b)))
-                kind = custom_kind!(1, dim(b), pdim(b), od.dst, 0, cuda_source(compf(b)), nothing)
+                kind = custom_kind!(1, dim(b), pdim(b), od.dst, 0, cuda_source(compf(b)), nothing, NetworkDynamics.extdim(b))
             end
         else
             inner = g isa NetworkDynamics.SingleSidedOutputWrapper && !(g isa Fiducial) ? g.g : g
@@ -162,8 +177,12 @@ function B200Aggregator(im::IndexManager, edgebatches, f)
             throw(ArgumentError("edge batch $(typeof(g)) has neither a registry kernel nor a cuda_source (no CPU fallback)"))
         ix = Vector{Int64}(b.indices); push!(keep, ix)
         coupling = g isa NetworkDynamics.SingleSidedOutputWrapper ? coupling_of(g) : Cint(3)   # unwrapped two-sided g
+        xd = NetworkDynamics.extdim(b)
+        (xd > 0 && (dim(b) == 0 || kind < CUSTOM_KIND_BASE)) &&
+            throw(ArgumentError("B200 engine: external inputs of an edge need an edge with states and a cuda_source f (no CPU fallback)"))
         CEBatch(kind, coupling, dim(b), pdim(b), od.src, od.dst, length(ix), pointer(ix),
-                b.statestride.first, b.pstride.first, b.outbufstride.first, b.inbufstride.first, msrc, mdst)
+                b.statestride.first, b.pstride.first, b.outbufstride.first, b.inbufstride.first, msrc, mdst,
+                xd, 0, _ext_table(im.e_ext, b.indices, xd))
     end
     esrc = Int64[e.src for e in im.edgevec]; edst = Int64[e.dst for e in im.edgevec]
     handle = Ref{Ptr{Cvoid}}(C_NULL)

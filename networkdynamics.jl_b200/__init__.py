@@ -11,8 +11,8 @@ Layout of this package (only what the path needs):
 """
 from . import _cabi
 from ._cabi import build
-from .components import (AntiSymmetric, ArgumentError, CudaFunction, Directed, EdgeModel, Fiducial, Lib,
-                         RegisteredFunction, StateMask, Symmetric, VertexModel)
+from .components import (AntiSymmetric, ArgumentError, CudaFunction, Directed, EdgeModel, EIndex, Fiducial, Lib,
+                         RegisteredFunction, StateMask, Symmetric, VertexModel, VIndex)
 from .graphs import (SimpleDiGraph, SimpleGraph, barabasi_albert, complete_graph, erdos_renyi, grid_graph, locality_order, ne,
                      nv, path_graph, permute_graph, watts_strogatz)
 from .network import (B200Aggregator, B200Execution, ComponentBatch, ExecutionStyle, IndexManager, Network, dim,

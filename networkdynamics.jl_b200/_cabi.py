@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("ND_B200_LIB") or os.path.join(_PKG, "libnd_b200.so") 
 SOURCES = [os.path.join(_PKG, "csrc", "nd_b200.cu")]
 HEADERS = [os.path.join(_PKG, "csrc", "nd_b200_kernels.cuh"), os.path.join(_ROOT, "include", "nd_b200.h")]
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 OK, EINVAL, EUNSUPPORTED, ECUDA, ENOMEM = range(5)
 
 # registry ids (include/nd_b200.h)
@@ -33,19 +33,22 @@ i32p = C.POINTER(C.c_int32)
 class VBatch(C.Structure):
     _fields_ = [("kind", C.c_int32), ("dim", C.c_int32), ("pdim", C.c_int32), ("outdim", C.c_int32),
                 ("count", C.c_int64), ("indices", i64p), ("state_first", C.c_int64), ("p_first", C.c_int64),
-                ("out_first", C.c_int64), ("aggr_first", C.c_int64)]
+                ("out_first", C.c_int64), ("aggr_first", C.c_int64), ("extdim", C.c_int32), ("reserved", C.c_int32),
+                ("ext_src", i64p)]
 
 
 class EBatch(C.Structure):
     _fields_ = [("kind", C.c_int32), ("coupling", C.c_int32), ("dim", C.c_int32), ("pdim", C.c_int32),
                 ("outdim_src", C.c_int32), ("outdim_dst", C.c_int32), ("count", C.c_int64), ("indices", i64p),
                 ("state_first", C.c_int64), ("p_first", C.c_int64), ("out_first", C.c_int64),
-                ("gbuf_first", C.c_int64), ("mask_src_first", C.c_int32), ("mask_dst_first", C.c_int32)]
+                ("gbuf_first", C.c_int64), ("mask_src_first", C.c_int32), ("mask_dst_first", C.c_int32),
+                ("extdim", C.c_int32), ("reserved", C.c_int32), ("ext_src", i64p)]
 
 
 class CustomKind(C.Structure):
     _fields_ = [("kind", C.c_int32), ("role", C.c_int32), ("dim", C.c_int32), ("pdim", C.c_int32), ("outdim", C.c_int32),
-                ("two_sided", C.c_int32), ("f_body", C.c_char_p), ("g_body", C.c_char_p)]
+                ("two_sided", C.c_int32), ("f_body", C.c_char_p), ("g_body", C.c_char_p), ("extdim", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class Desc(C.Structure):

@@ -136,6 +136,21 @@ class Directed:
 
 
 @dataclass(frozen=True)
+class VIndex:
+    """`VIndex(i, sub)`: state / output `sub` of vertex i (1-based) as an external input (src/external_inputs.jl:36-50):
+    `sub` = a state symbol of the model (`sym`), a 1-based state index, or ("out", k) for output k."""
+    comp: int
+    sub: object
+
+
+@dataclass(frozen=True)
+class EIndex:
+    """`EIndex(i, sub)`: the same for edge i; ("out", k) counts over the flat outputs (src outputs, then dst outputs)."""
+    comp: int
+    sub: object
+
+
+@dataclass(frozen=True)
 class VertexModel:
     f: Optional[object]
     g: object                      # StateMask or a RegisteredFunction (NoFeedForward g)
@@ -145,6 +160,11 @@ class VertexModel:
     sym: Tuple[str, ...] = ()
     psym: Tuple[str, ...] = ()
     name: str = "VertexModel"
+    extin: Tuple[object, ...] = ()   # external inputs: VIndex / EIndex refs; f then takes (dv, v, esum, ext, p, t)
+
+    @property
+    def extdim(self) -> int:
+        return len(self.extin)
 
     def __post_init__(self):
         if self.outdim is None:
@@ -155,10 +175,10 @@ class VertexModel:
 
     def component_hash(self):
         """What batches are formed on: src/construction.jl:245-256 (name/metadata are not part of it)."""
-        return ("V", self.f, self.g, self.dim, self.outdim, self.pdim)
+        return ("V", self.f, self.g, self.dim, self.outdim, self.pdim, self.extdim)
 
     def custom_spec(self):
-        """(role, dim, pdim, outdim, two_sided, f_body, g_body) when f is user-supplied CUDA code, else None"""
+        """(role, dim, pdim, outdim, two_sided, f_body, g_body, extdim) when f is user-supplied CUDA code, else None"""
         if not isinstance(self.f, CudaFunction) or self.f.role != "vertex_f":
             return None
         if isinstance(self.g, CudaFunction) and self.g.role == "vertex_g":
@@ -167,11 +187,11 @@ class VertexModel:
             g_body = None
         else:
             return None
-        return (0, self.dim, self.pdim, self.outdim, 0, self.f.body, g_body)
+        return (0, self.dim, self.pdim, self.outdim, 0, self.f.body, g_body, self.extdim)
 
     def kernel_kind(self) -> Optional[int]:
         f = self.f
-        if not isinstance(f, RegisteredFunction) or f.role != "vertex_f":
+        if not isinstance(f, RegisteredFunction) or f.role != "vertex_f" or self.extdim:
             return None
         if f.kind == _cabi.V_SWING_DQ:
             return f.kind if isinstance(self.g, RegisteredFunction) and self.g.kind == f.kind else None
@@ -191,6 +211,12 @@ class EdgeModel:
     f: Optional[object] = None
     psym: Tuple[str, ...] = ()
     name: str = "EdgeModel"
+    sym: Tuple[str, ...] = ()
+    extin: Tuple[object, ...] = ()   # external inputs (edges with states only): f takes (de, e, v_src, v_dst, ext, p, t)
+
+    @property
+    def extdim(self) -> int:
+        return len(self.extin)
 
     @property
     def coupling(self) -> Optional[int]:
@@ -207,7 +233,7 @@ class EdgeModel:
         return self.outdim
 
     def component_hash(self):
-        return ("E", self.f, self.g, self.dim, self.outdim_src, self.outdim_dst, self.pdim)
+        return ("E", self.f, self.g, self.dim, self.outdim_src, self.outdim_dst, self.pdim, self.extdim)
 
     def state_masks(self):
         """(mask_src_first, mask_dst_first), 1-based, for an edge with states whose outputs are contiguous StateMasks of
@@ -229,22 +255,22 @@ class EdgeModel:
     def custom_spec(self):
         if self.dim > 0:              # edge with states: user-supplied f, StateMask outputs
             if isinstance(self.f, CudaFunction) and self.f.role == "edge_f" and self.state_masks() is not None:
-                return (1, self.dim, self.pdim, self.outdim, 0, self.f.body, None)
+                return (1, self.dim, self.pdim, self.outdim, 0, self.f.body, None, self.extdim)
             return None
-        if self.f is not None:
+        if self.f is not None or self.extdim:
             return None
         if isinstance(self.g, CudaFunction) and self.g.role == "edge_g2":       # unwrapped two-sided g
-            return (1, 0, self.pdim, self.outdim, 1, self.g.body, None)
+            return (1, 0, self.pdim, self.outdim, 1, self.g.body, None, 0)
         inner = getattr(self.g, "g", None)
         if isinstance(inner, CudaFunction):
             if isinstance(self.g, Fiducial):
-                return (1, 0, self.pdim, self.outdim, 1, inner.body, None) if inner.role == "edge_g2" else None
-            return (1, 0, self.pdim, self.outdim, 0, inner.body, None) if inner.role == "edge_g" else None
+                return (1, 0, self.pdim, self.outdim, 1, inner.body, None, 0) if inner.role == "edge_g2" else None
+            return (1, 0, self.pdim, self.outdim, 0, inner.body, None, 0) if inner.role == "edge_g" else None
         return None
 
     def kernel_kind(self) -> Optional[int]:
         inner = getattr(self.g, "g", None)
-        if self.coupling is None:
+        if self.coupling is None or self.extdim:
             return None
         if self.dim > 0:              # edge with states: registered f, StateMask outputs
             if isinstance(self.f, RegisteredFunction) and self.f.role == "edge_f" and self.state_masks() is not None:

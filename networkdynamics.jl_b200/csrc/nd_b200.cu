@@ -96,7 +96,7 @@ struct nd_b200_engine {
   long long gather_len = 0;
   int wait_from = 0;          // first tile / slice that reads the halo
   // user-supplied component kinds: the kernels are compiled at creation time (NVRTC) from the same header
-  struct CustomKind { int kind, role, dim, pdim, outdim, two_sided; std::string f_body, g_body; };
+  struct CustomKind { int kind, role, dim, pdim, outdim, two_sided; std::string f_body, g_body; int extdim; };
   std::vector<CustomKind> customs;
   bool custom = false;
   int c_pe = 0, c_maxdim = 1;          // template PE (largest edge pdim) and ND_MAX_VDIM of the generated kernels
@@ -105,7 +105,9 @@ struct nd_b200_engine {
   cudaKernel_t c_fused = nullptr, c_jag = nullptr, c_vout = nullptr, c_eout = nullptr, c_ef = nullptr;
   // edge batches with states ("ODE edges"): their f runs in edge_f_kernel after the row kernel; per edge of the batch the
   // gather offsets of its two vertex outputs
-  struct OdeBatch { int b; int* d_es; int* d_et; };
+  struct OdeBatch { int b; int* d_es; int* d_et; int* d_ext; int extdim; };
+  std::vector<int*> d_vext;            // per vertex batch: external-input codes (nullptr: none)
+  int c_maxext = 0;                    // ND_MAX_EXT of the generated kernels
   std::vector<OdeBatch> ode;
   int c_maxedim = 1;                   // ND_MAX_EDIM of the generated kernels
   // packed edge parameters (nd_b200_pack_params): per entry, in the entry order of the layout in use
@@ -182,7 +184,7 @@ bool vertex_kind_ok(const nd_b200_engine* e, const nd_b200_vbatch& b, std::strin
   if (b.kind >= ND_B200_CUSTOM_KIND_BASE) {
     const auto* c = find_custom(e, b.kind, 0);
     if (!c) { why = "vertex kind " + std::to_string(b.kind) + " is not among the descriptor's custom kinds"; return false; }
-    if (c->dim != b.dim || c->pdim != b.pdim || c->outdim != b.outdim) { why = "custom vertex kind " + std::to_string(b.kind) + " declared with other (dim,pdim,outdim)"; return false; }
+    if (c->dim != b.dim || c->pdim != b.pdim || c->outdim != b.outdim || c->extdim != b.extdim) { why = "custom vertex kind " + std::to_string(b.kind) + " declared with other (dim,pdim,outdim,extdim)"; return false; }
     if (c->g_body.empty() && b.outdim > b.dim) { why = "custom vertex kind " + std::to_string(b.kind) + ": StateMask(1:outdim) needs outdim <= dim"; return false; }
     return true;
   }
@@ -190,6 +192,7 @@ bool vertex_kind_ok(const nd_b200_engine* e, const nd_b200_vbatch& b, std::strin
 }
 
 bool vertex_kind_ok(const nd_b200_vbatch& b, std::string& why) {
+  if (b.extdim != 0) { why = "external inputs need a user-supplied vertex kind"; return false; }
   struct R { int kind, dim, pdim, outdim; };
   static const R reg[] = {{ND_B200_V_DIFFUSION, 1, 0, 1}, {ND_B200_V_KURAMOTO_FIRST, 1, 1, 1},
                           {ND_B200_V_KURAMOTO_SECOND, 2, 3, 1}, {ND_B200_V_KURAMOTO_SECOND_BENCH, 2, 1, 1},
@@ -210,7 +213,8 @@ bool edge_kind_ok(const nd_b200_engine* e, const nd_b200_ebatch& b, int vdepth, 
   if (b.kind >= ND_B200_CUSTOM_KIND_BASE) {
     const auto* c = find_custom(e, b.kind, 1);
     if (!c) { why = "edge kind " + std::to_string(b.kind) + " is not among the descriptor's custom kinds"; return false; }
-    if (c->pdim != b.pdim || c->outdim != b.outdim_dst || c->dim != b.dim) { why = "custom edge kind " + std::to_string(b.kind) + " declared with other (dim,pdim,outdim)"; return false; }
+    if (c->pdim != b.pdim || c->outdim != b.outdim_dst || c->dim != b.dim || c->extdim != b.extdim) { why = "custom edge kind " + std::to_string(b.kind) + " declared with other (dim,pdim,outdim,extdim)"; return false; }
+    if (b.extdim > 0 && b.dim == 0) { why = "custom edge kind " + std::to_string(b.kind) + ": external inputs need an edge with states (static edges are feed-forward)"; return false; }
     if (b.dim > 0) {
       if (c->two_sided) { why = "custom edge kind " + std::to_string(b.kind) + ": an edge with states supplies f; its outputs are StateMasks"; return false; }
       return true;
@@ -223,6 +227,7 @@ bool edge_kind_ok(const nd_b200_engine* e, const nd_b200_ebatch& b, int vdepth, 
 }
 
 bool edge_kind_ok(const nd_b200_ebatch& b, int vdepth, std::string& why) {
+  if (b.extdim != 0) { why = "external inputs need a user-supplied edge kind"; return false; }
   struct R { int kind, pdim, odst, vdepth, dim; };
   static const R reg[] = {{ND_B200_E_DIFFUSION, 1, 1, 1, 0}, {ND_B200_E_DIFFUSION_NOP, 0, 1, 1, 0},
                           {ND_B200_E_KURAMOTO, 1, 1, 1, 0}, {ND_B200_E_LINE_DQ, 3, 2, 2, 0},
@@ -402,7 +407,7 @@ cudaError_t launch_edge_f(nd_b200_engine* e, const KParams& P, cudaStream_t st) 
     EFParams Q;
     memset(&Q, 0, sizeof Q);
     Q.kind = h.kind; Q.dim = h.dim; Q.pdim = h.pdim; Q.count = h.count; Q.state0 = h.state0; Q.p0 = h.p0;
-    Q.esrc_off = ob.d_es; Q.edst_off = ob.d_et;
+    Q.esrc_off = ob.d_es; Q.edst_off = ob.d_et; Q.ext = ob.d_ext; Q.extdim = ob.extdim;
     Q.u = P.u; Q.gsrc = P.gsrc; Q.p = P.p; Q.du = P.du; Q.mode = P.mode; Q.stage = P.stage; Q.u0 = P.u0; Q.unext = P.unext;
     Q.ksum = P.ksum; Q.hs = P.hs; Q.h6 = P.h6; Q.t = P.t;
     const int T = 256;
@@ -455,22 +460,24 @@ std::string custom_source(const nd_b200_engine* e, int vdepth) {
   snprintf(buf, sizeof buf, "enum { ND_B200_ANTISYMMETRIC = %d, ND_B200_SYMMETRIC = %d, ND_B200_DIRECTED = %d, ND_B200_FIDUCIAL = %d };\n",
            ND_B200_ANTISYMMETRIC, ND_B200_SYMMETRIC, ND_B200_DIRECTED, ND_B200_FIDUCIAL);
   src += buf;
-  snprintf(buf, sizeof buf, "#define ND_MAX_VDIM %d\n#define ND_MAX_VOUT %d\n#define ND_MAX_EDIM %d\n", std::max(e->c_maxdim, 1), std::max(vdepth, 1), std::max(e->c_maxedim, 2));
+  snprintf(buf, sizeof buf, "#define ND_MAX_VDIM %d\n#define ND_MAX_VOUT %d\n#define ND_MAX_EDIM %d\n#define ND_MAX_EXT %d\n", std::max(e->c_maxdim, 1), std::max(vdepth, 1), std::max(e->c_maxedim, 2), e->c_maxext);
   src += buf;
   std::string edge_cases, fid_cases, vf_cases, vg_cases, ef_cases;
   src += "namespace ndb_user {\n";
   for (const auto& c : e->customs) {
     const std::string id = std::to_string(c.kind);
     if (c.role == 0) {
-      src += "__device__ __forceinline__ void vertex_f_" + id + "(double* __restrict__ dv, const double* __restrict__ v, const double* __restrict__ esum, const double* __restrict__ p, double t) {\n" + c.f_body + "\n}\n";
-      vf_cases += " case " + id + ": ndb_user::vertex_f_" + id + "(dv, v, acc, pv, t); break;";
+      const std::string xa = c.extdim > 0 ? "const double* __restrict__ ext, " : "", xc = c.extdim > 0 ? "ext, " : "";
+      src += "__device__ __forceinline__ void vertex_f_" + id + "(double* __restrict__ dv, const double* __restrict__ v, const double* __restrict__ esum, " + xa + "const double* __restrict__ p, double t) {\n" + c.f_body + "\n}\n";
+      vf_cases += " case " + id + ": ndb_user::vertex_f_" + id + "(dv, v, acc, " + xc + "pv, t); break;";
       if (!c.g_body.empty()) {
         src += "__device__ __forceinline__ void vertex_g_" + id + "(double* __restrict__ out, const double* __restrict__ v, const double* __restrict__ p, double t) {\n" + c.g_body + "\n}\n";
         vg_cases += " case " + id + ": ndb_user::vertex_g_" + id + "(out, v, pv, t); break;";
       }
     } else if (c.dim > 0) {   // edge with states: the body is f; outputs are StateMasks
-      src += "__device__ __forceinline__ void edge_f_" + id + "(double* __restrict__ de, const double* __restrict__ e, const double* __restrict__ v_src, const double* __restrict__ v_dst, const double* __restrict__ p, double t) {\n" + c.f_body + "\n}\n";
-      ef_cases += " case " + id + ": ndb_user::edge_f_" + id + "(de, ue, vs, vd, pe, t); break;";
+      const std::string xa = c.extdim > 0 ? "const double* __restrict__ ext, " : "", xc = c.extdim > 0 ? "ext, " : "";
+      src += "__device__ __forceinline__ void edge_f_" + id + "(double* __restrict__ de, const double* __restrict__ e, const double* __restrict__ v_src, const double* __restrict__ v_dst, " + xa + "const double* __restrict__ p, double t) {\n" + c.f_body + "\n}\n";
+      ef_cases += " case " + id + ": ndb_user::edge_f_" + id + "(de, ue, vs, vd, " + xc + "pe, t); break;";
     } else if (c.two_sided) {
       src += "__device__ __forceinline__ void edge_g_" + id + "(double* __restrict__ e_src, double* __restrict__ e_dst, const double* __restrict__ v_src, const double* __restrict__ v_dst, const double* __restrict__ p, double t) {\n" + c.f_body + "\n}\n";
       fid_cases += " case " + id + ": ndb_user::edge_g_" + id + "(osrc, odst, vs, vd, pe, t); break;";
@@ -547,7 +554,8 @@ struct EngineBuilder {
   std::vector<int> goff;                     // vertex id - 1 -> offset of its output in the gather source
   long long state_expect = 1, out_expect = 1, p_expect = 1, nrows_owned = 0;
   // edges
-  bool any_epar = false, any_ode = false, any_fiducial = false;
+  bool any_epar = false, any_ode = false, any_fiducial = false, any_ext = false;
+  std::vector<std::vector<int>> vext_codes, eext_codes;   // per batch: resolved external-input sources (see VBDev::ext)
   // CSR over the owned rows, entries in accumulation order
   std::vector<long long> cnt;
   std::vector<int> h_rowptr, h_nbr, h_epar;
@@ -603,7 +611,9 @@ struct EngineBuilder {
       if (c.kind < ND_B200_CUSTOM_KIND_BASE || (c.role != 0 && c.role != 1) || !c.f_body) return fail(e, ND_B200_EINVAL, "custom kind %d: id must be >= %d, role 0|1, f_body non-NULL", c.kind, ND_B200_CUSTOM_KIND_BASE);
       if (c.dim < 0 || c.dim > 16 || c.pdim < 0 || c.pdim > 64 || c.outdim < 1 || c.outdim > 8) return fail(e, ND_B200_EUNSUPPORTED, "custom kind %d: dims outside dim<=16, pdim<=64, 1<=outdim<=8", c.kind);
       if (c.role == 1) e->c_maxedim = std::max(e->c_maxedim, c.dim);
-      e->customs.push_back(nd_b200_engine::CustomKind{c.kind, c.role, c.dim, c.pdim, c.outdim, c.two_sided, c.f_body, c.g_body ? c.g_body : ""});
+      if (c.extdim < 0 || c.extdim > 32) return fail(e, ND_B200_EUNSUPPORTED, "custom kind %d: extdim outside 0..32", c.kind);
+    e->c_maxext = std::max(e->c_maxext, c.extdim);
+    e->customs.push_back(nd_b200_engine::CustomKind{c.kind, c.role, c.dim, c.pdim, c.outdim, c.two_sided, c.f_body, c.g_body ? c.g_body : "", c.extdim});
     }
     for (int b = 0; b < d->n_vbatches; ++b) e->custom = e->custom || d->vbatches[b].kind >= ND_B200_CUSTOM_KIND_BASE;
     for (int b = 0; b < d->n_ebatches; ++b) e->custom = e->custom || d->ebatches[b].kind >= ND_B200_CUSTOM_KIND_BASE;
@@ -746,6 +756,69 @@ struct EngineBuilder {
     return ND_B200_OK;
   }
 
+  // One entry of the reference's ExtMap (src/external_inputs.jl:1-50) -> where the kernels read it: StateBufIdx = the
+  // state vector; OutBufIdx = an output of a component WITHOUT feed forward, i.e. a vertex output (a state for StateMask
+  // vertices, else the materialised output block) or a StateMask output of an edge with states (a state, negated on the src
+  // side of AntiSymmetric).
+  int resolve_ext_source(long long src, int& code) const {
+    if (src > 0) {
+      if (src > d->lastidx_dynamic) return fail(e, ND_B200_EINVAL, "external input: state index %lld outside 1..%lld", src, (long long)d->lastidx_dynamic);
+      code = (int)(src - 1);
+      return ND_B200_OK;
+    }
+    const long long o = -src - 1;     // 0-based position in the output buffer
+    if (src == 0 || o >= d->lastidx_out) return fail(e, ND_B200_EINVAL, "external input: output index %lld outside 1..%lld", -src, (long long)d->lastidx_out);
+    const long long nvout = d->nv * (long long)d->vdepth;
+    if (o < nvout) {
+      const long long row = o / d->vdepth, k = o % d->vdepth;
+      if (e->gather_from_u) {          // vertex outputs are states (StateMask(1:vdepth))
+        size_t b = 0;
+        while (b + 1 < e->hvb.size() && row >= e->hvb[b + 1].row0) ++b;
+        code = (int)(e->hvb[b].state0 + (row - e->hvb[b].row0) * e->hvb[b].dim + k);
+      } else {
+        code = (int)(row * d->vdepth + k) | ND_EXT_FROM_VOUT;
+      }
+      return ND_B200_OK;
+    }
+    for (const HostEB& h : e->heb) {
+      const long long w = h.osrc + h.odst, lo = h.out0, hi = h.out0 + h.count * w;
+      if (o < lo || o >= hi) continue;
+      if (h.dim == 0) return fail(e, ND_B200_EUNSUPPORTED, "external input: outputs of feed-forward components (static edges) are not allowed (src/external_inputs.jl:42-44)");
+      const long long i = (o - lo) / w, c = (o - lo) % w;
+      const bool src_side = c < h.osrc;
+      const long long comp = src_side ? c : c - h.osrc;
+      const long long st = h.state0 + i * h.dim + ((src_side && h.coupling == ND_B200_FIDUCIAL) ? h.mask_src : h.mask_dst) + comp;
+      code = (int)st;
+      if (src_side && h.coupling == ND_B200_ANTISYMMETRIC) code |= (int)0x80000000u;
+      return ND_B200_OK;
+    }
+    return fail(e, ND_B200_EINVAL, "external input: output index %lld belongs to no component", -src);
+  }
+
+  // external inputs of the batches (after both registrations: sources may be any vertex or edge)
+  int resolve_externals() {
+    vext_codes.assign((size_t)d->n_vbatches, {});
+    eext_codes.assign((size_t)std::max(d->n_ebatches, 0), {});
+    for (int b = 0; b < d->n_vbatches; ++b) any_ext = any_ext || d->vbatches[b].extdim > 0;
+    for (int b = 0; b < d->n_ebatches; ++b) any_ext = any_ext || d->ebatches[b].extdim > 0;
+    if (!any_ext) return ND_B200_OK;
+    if (nrows_owned != e->nrows_total || d->gather_offset) return fail(e, ND_B200_EUNSUPPORTED, "external inputs on a row-partitioned / halo engine");
+    if (d->lastidx_dynamic >= ND_EXT_FROM_VOUT || d->nv * (long long)d->vdepth >= ND_EXT_FROM_VOUT) return fail(e, ND_B200_EUNSUPPORTED, "networks with external inputs need offsets below 2^30");
+    auto one = [&](int extdim, long long count, const int64_t* src, std::vector<int>& out, const char* what, int b) -> int {
+      if (extdim <= 0) return ND_B200_OK;
+      if (!src) return fail(e, ND_B200_EINVAL, "%s batch %d: extdim %d without ext_src", what, b + 1, extdim);
+      out.resize((size_t)(count * extdim));
+      for (size_t k = 0; k < out.size(); ++k)
+        if (int rc = resolve_ext_source(src[k], out[k])) return rc;
+      return ND_B200_OK;
+    };
+    for (int b = 0; b < d->n_vbatches; ++b)
+      if (int rc = one(d->vbatches[b].extdim, d->vbatches[b].count, d->vbatches[b].ext_src, vext_codes[(size_t)b], "vertex", b)) return rc;
+    for (int b = 0; b < d->n_ebatches; ++b)
+      if (int rc = one(d->ebatches[b].extdim, d->ebatches[b].count, d->ebatches[b].ext_src, eext_codes[(size_t)b], "edge", b)) return rc;
+    return ND_B200_OK;
+  }
+
   // destination-sorted CSR over the owned rows in SequentialAggregator order (+ split-mode and get_buffers tables)
   int build_csr() {
     // ---- destination-sorted CSR over owned rows: count, then stable placement ---------------------
@@ -780,7 +853,7 @@ struct EngineBuilder {
     e->oedge_len = d->lastidx_out - e->oedge_base;
     e->ne_all = d->ne;
     want_split = false;
-    if (const char* s = getenv("ND_B200_KERNEL")) want_split = !strcmp(s, "split") && nrows_owned == e->nrows_total && !(d->vdepth == 2 && d->n_ebatches > 1) && !e->custom && !any_ode && !any_fiducial;
+    if (const char* s = getenv("ND_B200_KERNEL")) want_split = !strcmp(s, "split") && nrows_owned == e->nrows_total && !(d->vdepth == 2 && d->n_ebatches > 1) && !e->custom && !any_ode && !any_fiducial && !any_ext;
     if (want_split && e->oedge_len >= INT_MAX) return fail(e, ND_B200_EUNSUPPORTED, "edge output buffer exceeds 2^31 scalars on one device");
     h_oidx.assign(want_split ? (size_t)std::max<long long>(e->nentries, 1) : 1, 0);
     h_es.assign(want_split ? (size_t)std::max<long long>(d->ne, 1) : 1, 0);
@@ -862,7 +935,7 @@ struct EngineBuilder {
     e->n_long = 0;
     for (size_t b = 0; b < e->hvb.size(); ++b) {
       const HostVB& h = e->hvb[b];
-      VBDev v{h.kind, h.dim, h.pdim, (int)h.row0, (int)h.count, (int)blk_row.size(), h.state0, h.p0};
+      VBDev v{h.kind, h.dim, h.pdim, (int)h.row0, (int)h.count, (int)blk_row.size(), h.state0, h.p0, nullptr, d->vbatches[b].extdim, 0};
       long long r = std::max<long long>(h.row0, e->row_begin);
       const long long rend = std::min<long long>(h.row0 + h.count, e->row_end);
       while (r < rend) {
@@ -1121,6 +1194,12 @@ struct EngineBuilder {
     }
     if (e->host_only) return ND_B200_OK;
     CUDA_TRY(e, cudaSetDevice(e->device));
+    e->d_vext.assign((size_t)d->n_vbatches, nullptr);
+    for (int b = 0; b < d->n_vbatches; ++b) {
+      if (d->vbatches[b].extdim <= 0) continue;
+      if (upload(e, &e->d_vext[(size_t)b], vext_codes[(size_t)b])) return ND_B200_ECUDA;
+      dvb[(size_t)b].ext = e->d_vext[(size_t)b];
+    }
     for (int b = 0; b < d->n_ebatches; ++b) {
       const nd_b200_ebatch& eb = d->ebatches[b];
       if (eb.dim == 0) continue;
@@ -1130,8 +1209,9 @@ struct EngineBuilder {
         es[(size_t)i] = goff[(size_t)d->edge_src[eid] - 1];
         et[(size_t)i] = goff[(size_t)d->edge_dst[eid] - 1];
       }
-      nd_b200_engine::OdeBatch ob{b, nullptr, nullptr};
+      nd_b200_engine::OdeBatch ob{b, nullptr, nullptr, nullptr, eb.extdim};
       if (upload(e, &ob.d_es, es) || upload(e, &ob.d_et, et)) return ND_B200_ECUDA;
+      if (eb.extdim > 0 && upload(e, &ob.d_ext, eext_codes[(size_t)b])) return ND_B200_ECUDA;
       e->ode.push_back(ob);
     }
     if (e->jag) {
@@ -1170,6 +1250,7 @@ struct EngineBuilder {
     if (int rc = check_descriptor()) return rc;
     if (int rc = register_vertices()) return rc;
     if (int rc = register_edges()) return rc;
+    if (int rc = resolve_externals()) return rc;
     if (int rc = build_csr()) return rc;
     if (int rc = plan_tiles()) return rc;
     if (int rc = build_jagged()) return rc;
@@ -1330,7 +1411,8 @@ void nd_b200_destroy(nd_b200_engine* e) {
   cudaFree(e->d_eebid); cudaFree(e->d_oedge);
   if (e->c_lib) cudaLibraryUnload(e->c_lib);
   cudaFree(e->d_jslices); cudaFree(e->d_jlanes); cudaFree(e->d_jnbr); cudaFree(e->d_jent); cudaFree(e->d_jebid); cudaFree(e->d_jlong);
-  for (auto& ob : e->ode) { cudaFree(ob.d_es); cudaFree(ob.d_et); }
+  for (auto& ob : e->ode) { cudaFree(ob.d_es); cudaFree(ob.d_et); cudaFree(ob.d_ext); }
+  for (int* q : e->d_vext) cudaFree(q);
   cudaFree(e->d_ppack);
   for (int* q : e->d_esrc_off) cudaFree(q);
   for (int* q : e->d_edst_off) cudaFree(q);

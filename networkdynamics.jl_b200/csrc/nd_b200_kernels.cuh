@@ -36,6 +36,9 @@
 #ifndef ND_MAX_EDIM
 #define ND_MAX_EDIM 2            // largest edge state dimension of the network (registry models: 2)
 #endif
+#ifndef ND_MAX_EXT
+#define ND_MAX_EXT 0             // largest number of external inputs of a component (src/external_inputs.jl); 0: none
+#endif
 #ifndef ND_CUSTOM_VERTEX_F_CASES
 #define ND_CUSTOM_VERTEX_F_CASES // case <kind>: ndb_user::vertex_f_<kind>(dv, v, acc, pv, t); break;
 #endif
@@ -50,7 +53,29 @@ struct VBDev {          // one vertex ComponentBatch, 0-based offsets
   int row0, nrows;      // aggregation-slot rows [row0, row0+nrows) of this batch (global numbering)
   int blk0;             // first thread block working on this batch
   long long state0, p0; // offsets into u / p
+  // external inputs (src/external_inputs.jl): component i of the batch reads extdim scalars, ext[i*extdim + k] = where
+  // from: low 30 bits = offset, bit 30 = from the materialised vertex outputs instead of u, bit 31 = negated
+  const int* ext;
+  int extdim, pad_;
 };
+constexpr int ND_EXT_FROM_VOUT = 1 << 30;
+// collect_externals! for one component (src/coreloop.jl:61, src/external_inputs.jl:52-66)
+__device__ __forceinline__ void gather_ext(const int* __restrict__ codes, int n, const double* __restrict__ u,
+                                           const double* __restrict__ vout, double* ext) {
+#if ND_MAX_EXT > 0
+#pragma unroll
+  for (int k = 0; k < ND_MAX_EXT; ++k) {
+    ext[k] = 0.0;
+    if (k < n) {
+      const int c = codes[k];
+      const double x = ((c & ND_EXT_FROM_VOUT) ? vout : u)[c & (ND_EXT_FROM_VOUT - 1)];
+      ext[k] = c < 0 ? -x : x;
+    }
+  }
+#else
+  (void)codes; (void)n; (void)u; (void)vout; (void)ext;
+#endif
+}
 struct EBDev {          // one edge ComponentBatch
   int kind, coupling, pdim;
   int dim;              // > 0: edge with states; its outputs are StateMasks of those states (no g arithmetic)
@@ -240,8 +265,8 @@ __device__ __forceinline__ void state_entry_value(const double* __restrict__ u, 
 // edge f (PASS 4, edges with states): f(de, e, vsrc, vdst, p, t), src/coreloop.jl:76,194-218
 template <int VD>
 __device__ __forceinline__ void edge_f(int kind, double* de, const double* ue, const double* vs, const double* vd,
-                                       const double* __restrict__ pe, double t) {
-  (void)t;
+                                       const double* __restrict__ pe, double t, const double* ext = nullptr) {
+  (void)t; (void)ext;
   switch (kind) {
     case ND_B200_E_DIFFUSION_ODE:   // test/ComponentLibrary.jl:30-34
       if constexpr (VD == 1) {
@@ -281,8 +306,9 @@ __device__ __forceinline__ void vertex_g(int kind, int outdim, double* out, cons
 // recomputes u_r,u_i with the same expressions as its g).
 template <int VD, int ED>
 __device__ __forceinline__ void vertex_f(int kind, double* dv, const double* v, const double* acc,
-                                         const double* __restrict__ pv, const double* selfout, double t) {
-  (void)t; (void)selfout;
+                                         const double* __restrict__ pv, const double* selfout, double t,
+                                         const double* ext = nullptr) {
+  (void)t; (void)selfout; (void)ext;
   switch (kind) {
     case ND_B200_V_DIFFUSION:            // test/ComponentLibrary.jl:42-45
       dv[0] = acc[0];
@@ -331,7 +357,13 @@ __device__ __forceinline__ void vertex_phase(const KParams& P, const VBDev& B, i
   double v[ND_MAX_VDIM], dv[ND_MAX_VDIM];
 #pragma unroll
   for (int c = 0; c < ND_MAX_VDIM; ++c) { v[c] = c < dim ? vin[c] : 0.0; dv[c] = 0.0; }
+#if ND_MAX_EXT > 0
+  double ext[ND_MAX_EXT];
+  gather_ext(B.ext + i * B.extdim, B.extdim, P.u, P.gsrc, ext);
+  vertex_f<VD, ED>(B.kind, dv, v, acc, pv, selfout, P.t, ext);
+#else
   vertex_f<VD, ED>(B.kind, dv, v, acc, pv, selfout, P.t);
+#endif
   if (P.mode == MODE_DU) {
     if (ND_MAX_VDIM == 2 && dim == 2 && ((s & 1) == 0)) {
       *reinterpret_cast<double2*>(P.du + s) = make_double2(dv[0], dv[ND_MAX_VDIM > 1 ? 1 : 0]);
@@ -747,6 +779,8 @@ struct EFParams {
   long long count, state0, p0;
   const int* __restrict__ esrc_off;    // per edge of the batch: gather offset of the src / dst vertex output
   const int* __restrict__ edst_off;
+  const int* __restrict__ ext;         // external inputs of the batch (see VBDev), extdim codes per edge
+  int extdim;
   const double* __restrict__ u;        // state vector (stage input)
   const double* __restrict__ gsrc;     // gather source of vertex outputs
   const double* __restrict__ p;
@@ -768,7 +802,13 @@ __global__ void __launch_bounds__(256) edge_f_kernel(const __grid_constant__ EFP
   const long long s = Q.state0 + i * Q.dim;
 #pragma unroll
   for (int c = 0; c < ND_MAX_EDIM; ++c) { ue[c] = c < Q.dim ? Q.u[s + c] : 0.0; de[c] = 0.0; }
+#if ND_MAX_EXT > 0
+  double ext[ND_MAX_EXT];
+  gather_ext(Q.ext + i * Q.extdim, Q.extdim, Q.u, Q.gsrc, ext);
+  edge_f<VD>(Q.kind, de, ue, vs, vd, Q.p + Q.p0 + i * Q.pdim, Q.t, ext);
+#else
   edge_f<VD>(Q.kind, de, ue, vs, vd, Q.p + Q.p0 + i * Q.pdim, Q.t);
+#endif
 #pragma unroll
   for (int c = 0; c < ND_MAX_EDIM; ++c) {
     if (c >= Q.dim) continue;

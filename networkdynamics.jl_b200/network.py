@@ -86,11 +86,12 @@ class IndexManager:
         self.vdepth = vd.pop()
         self.edepth = ed.pop() if ed else 0
         self.lastidx_dynamic = self.lastidx_out = self.lastidx_p = 0
-        self.lastidx_aggr = self.lastidx_gbuf = 0
+        self.lastidx_aggr = self.lastidx_gbuf = self.lastidx_extbuf = 0
         z = lambda n: np.zeros(n, dtype=np.int64)
         self.v_data, self.v_out, self.v_para, self.v_aggr = z(self.nv), z(self.nv), z(self.nv), z(self.nv)
         self.e_data, self.e_out_src, self.e_out_dst = z(self.ne), z(self.ne), z(self.ne)
         self.e_para, self.e_gbuf_src, self.e_gbuf_dst = z(self.ne), z(self.ne), z(self.ne)
+        self.v_ext, self.e_ext = z(self.nv), z(self.ne)
 
     def _next(self, which: str, count: int, width: int) -> np.ndarray:
         last = getattr(self, which)
@@ -105,6 +106,7 @@ class IndexManager:
         self.v_out[i0] = self._next("lastidx_out", n, m.outdim)
         self.v_para[i0] = self._next("lastidx_p", n, m.pdim)
         self.v_aggr[i0] = self._next("lastidx_aggr", n, self.edepth)
+        self.v_ext[i0] = self._next("lastidx_extbuf", n, m.extdim)
         f = i0[0]
         return ComponentBatch("vertex", m, idxs, int(self.v_data[f]), int(self.v_para[f]), int(self.v_aggr[f]),
                               int(self.v_out[f]))
@@ -122,9 +124,36 @@ class IndexManager:
         gf = self._next("lastidx_gbuf", n, 2 * self.vdepth)
         self.e_gbuf_src[i0] = gf
         self.e_gbuf_dst[i0] = gf + self.vdepth
+        self.e_ext[i0] = self._next("lastidx_extbuf", n, m.extdim)
         f = i0[0]
         return ComponentBatch("edge", m, idxs, int(self.e_data[f]), int(self.e_para[f]), int(self.e_gbuf_src[f]),
                               int(self.e_out_src[f]))
+
+
+def resolve_extin(im: "IndexManager", ref) -> int:
+    """One external-input reference -> the ExtMap entry the C ABI takes (src/external_inputs.jl:36-50): > 0 = 1-based
+    index into u (a state), < 0 = -(1-based index into o) (an output)."""
+    from .components import EIndex, VIndex
+    if isinstance(ref, VIndex):
+        m, data, out = im.vertexm[im.vtype[ref.comp - 1]], im.v_data[ref.comp - 1], im.v_out[ref.comp - 1]
+        nout = m.outdim
+    elif isinstance(ref, EIndex):
+        m, data, out = im.edgem[im.etype[ref.comp - 1]], im.e_data[ref.comp - 1], im.e_out_src[ref.comp - 1]
+        nout = m.outdim_src + m.outdim_dst
+    else:
+        raise ArgumentError(f"external input {ref!r} is neither a VIndex nor an EIndex")
+    sub = ref.sub
+    if isinstance(sub, str):
+        if sub not in m.sym:
+            raise ArgumentError(f"Cannot resolve external input {ref!r}: {sub!r} is not a state symbol of {m.name}")
+        sub = m.sym.index(sub) + 1
+    if isinstance(sub, (int, np.integer)):
+        if not 1 <= sub <= m.dim:
+            raise ArgumentError(f"Cannot resolve external input {ref!r}: state index outside 1..{m.dim}")
+        return int(data + sub - 1)
+    if isinstance(sub, tuple) and len(sub) == 2 and sub[0] == "out" and 1 <= sub[1] <= nout:
+        return -int(out + sub[1] - 1)
+    raise ArgumentError(f"Cannot resolve external input {ref!r}")
 
 
 def find_identical(keys: np.ndarray) -> List[np.ndarray]:
@@ -147,7 +176,7 @@ def _expand_models(models, n, what):
         hashes, remap = {}, np.zeros(len(uniq), dtype=np.int64)
         merged = []
         for i, m in enumerate(uniq):
-            h = m.component_hash()
+            h = (m.component_hash(), m.extin)      # external-input references are per component, not part of the batch hash
             if h not in hashes:
                 hashes[h] = len(merged)
                 merged.append(m)
@@ -158,7 +187,7 @@ def _expand_models(models, n, what):
         raise ArgumentError(f"Number of {what} models does not match the graph")
     hashes, uniq, types = {}, [], np.empty(n, dtype=np.int64)
     for i, m in enumerate(models):
-        h = m.component_hash()
+        h = (m.component_hash(), m.extin)
         k = hashes.get(h)
         if k is None:
             k = hashes[h] = len(uniq)
@@ -214,6 +243,18 @@ class B200Aggregator:
                 customs[spec] = _cabi.CUSTOM_KIND_BASE + len(customs)
             return customs[spec]
 
+        def ext_table(cb, b, models, types):
+            """ExtMap entries of a batch: the components of a batch share f (and extdim) but each has its own references"""
+            if b.model.extdim == 0:
+                return
+            tab = np.empty((len(b), b.model.extdim), dtype=np.int64)
+            for r, comp in enumerate(b.indices):
+                refs = models[types[comp - 1]].extin
+                tab[r] = [resolve_extin(im, ref) for ref in refs]
+            keep.append(tab)
+            cb.extdim = b.model.extdim
+            cb.ext_src = tab.ctypes.data_as(_cabi.i64p)
+
         for k, b in enumerate(vertexbatches):
             kind = b.model.kernel_kind()
             if kind is None:
@@ -225,6 +266,7 @@ class B200Aggregator:
             keep.append(idx)
             vb[k] = _cabi.VBatch(kind, b.model.dim, b.model.pdim, b.model.outdim, idx.size,
                                  idx.ctypes.data_as(_cabi.i64p), b.state_first, b.p_first, b.out_first, b.in_first)
+            ext_table(vb[k], b, im.vertexm, im.vtype)
         eb = (_cabi.EBatch * max(1, len(edgebatches)))()
         for k, b in enumerate(edgebatches):
             kind = b.model.kernel_kind()
@@ -239,6 +281,7 @@ class B200Aggregator:
             eb[k] = _cabi.EBatch(kind, b.model.coupling, b.model.dim, b.model.pdim, b.model.outdim_src,
                                  b.model.outdim_dst, idx.size, idx.ctypes.data_as(_cabi.i64p), b.state_first,
                                  b.p_first, b.out_first, b.in_first, masks[0], masks[1])
+            ext_table(eb[k], b, im.edgem, im.etype)
         dev = self._opts["device"]
         if dev is None:
             dev = _current_device()
@@ -255,10 +298,10 @@ class B200Aggregator:
         if customs:
             ck = (_cabi.CustomKind * len(customs))()
             for i, (spec, kid) in enumerate(customs.items()):
-                role, dim, pdim, outdim, two_sided, f_body, g_body = spec
+                role, dim, pdim, outdim, two_sided, f_body, g_body, extdim = spec
                 fb, gb = f_body.encode(), (g_body.encode() if g_body is not None else None)
                 keep += [fb, gb]
-                ck[i] = _cabi.CustomKind(kid, role, dim, pdim, outdim, two_sided, fb, gb)
+                ck[i] = _cabi.CustomKind(kid, role, dim, pdim, outdim, two_sided, fb, gb, extdim, 0)
             keep.append(ck)
             desc.n_custom = len(customs)
             desc.custom = ck
@@ -364,8 +407,14 @@ class Network:
         im = IndexManager(g, vm, vtype, em, etype)
         self.im = im
         # batches: all vertex batches first, then all edge batches (src/construction.jl:171-195)
-        self.vertexbatches = [im.register_vertices(idxs, vm[vtype[idxs[0] - 1]]) for idxs in find_identical(vtype)]
-        edgebatches = [im.register_edges(idxs, em[etype[idxs[0] - 1]]) for idxs in find_identical(etype)] if g.ne else []
+        # batches are formed on the component hash (src/construction.jl:245-256); models that differ only in WHAT their
+        # external inputs refer to share a batch
+        def batch_keys(models, types):
+            ids = {}
+            per_model = np.array([ids.setdefault(m.component_hash(), len(ids)) for m in models], dtype=np.int64)
+            return per_model[types]
+        self.vertexbatches = [im.register_vertices(idxs, vm[vtype[idxs[0] - 1]]) for idxs in find_identical(batch_keys(vm, vtype))]
+        edgebatches = [im.register_edges(idxs, em[etype[idxs[0] - 1]]) for idxs in find_identical(batch_keys(em, etype))] if g.ne else []
         if verbose:
             for b in self.vertexbatches + edgebatches:
                 print(f" - {b.kind} batch {b.model.name}: {len(b)} components")

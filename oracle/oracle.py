@@ -41,6 +41,7 @@ class VSpec:
     dim: int
     pdim: int
     outdim: int
+    extdim: int = 0        # external inputs (Python twin only; the C restatement rejects them)
 
 
 @dataclass(frozen=True)
@@ -53,6 +54,7 @@ class ESpec:
     outdim_dst: int
     mask_src: int = 0      # edges with states: 1-based first state of the src / dst output StateMask
     mask_dst: int = 0
+    extdim: int = 0        # external inputs (Python twin only)
 
 
 # the model zoo of test/ComponentLibrary.jl and benchmark/benchmark_models.jl (dims as declared there)
@@ -140,6 +142,8 @@ class OracleNetwork:
         vt = np.ascontiguousarray(vtype, dtype=np.int32)
         et = np.ascontiguousarray(etype, dtype=np.int32)
         assert vt.size == self.nv and et.size == self.ne
+        if any(getattr(s, "extdim", 0) for s in self.vspecs + self.especs):
+            raise ValueError("external inputs are not restated in the C oracle (use the Python twin)")
         vs = (_VSpec * max(1, len(self.vspecs)))(*[_VSpec(s.kind, s.dim, s.pdim, s.outdim) for s in self.vspecs])
         es = (_ESpec * max(1, len(self.especs)))(*[_ESpec(s.kind, s.coupling, s.dim, s.pdim, s.outdim_src, s.outdim_dst,
                                                           getattr(s, "mask_src", 0), getattr(s, "mask_dst", 0))

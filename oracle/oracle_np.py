@@ -56,9 +56,9 @@ class IndexManager:
         self.vspecs, self.especs = vspecs, especs
         self.vdepth = vspecs[vtype[0]].outdim
         self.edepth = especs[etype[0]].outdim_dst if self.ne else 0
-        self.last = dict(dynamic=0, out=0, p=0, aggr=0, gbuf=0)
-        self.v_data, self.v_out, self.v_para, self.v_aggr = ({} for _ in range(4))
-        self.e_data, self.e_out, self.e_para, self.e_gbufr = ({} for _ in range(4))
+        self.last = dict(dynamic=0, out=0, p=0, aggr=0, gbuf=0, ext=0)
+        self.v_data, self.v_out, self.v_para, self.v_aggr, self.v_ext = ({} for _ in range(5))
+        self.e_data, self.e_out, self.e_para, self.e_gbufr, self.e_ext = ({} for _ in range(5))
         self.vbatches = [(vtype[idxs[0] - 1], idxs) for idxs in find_identical(list(vtype))]
         self.ebatches = [(etype[idxs[0] - 1], idxs) for idxs in find_identical(list(etype))]
         for spec, idxs in self.vbatches:
@@ -68,6 +68,7 @@ class IndexManager:
                 self.v_out[i] = self._next("out", s.outdim)
                 self.v_para[i] = self._next("p", s.pdim)
                 self.v_aggr[i] = self._next("aggr", self.edepth)
+                self.v_ext[i] = self._next("ext", getattr(s, "extdim", 0))       # src/network_structure.jl:230
         for spec, idxs in self.ebatches:
             s = especs[spec]
             for i in idxs:
@@ -75,6 +76,7 @@ class IndexManager:
                 self.e_out[i] = (self._next("out", s.outdim_src), self._next("out", s.outdim_dst))
                 self.e_para[i] = self._next("p", s.pdim)
                 self.e_gbufr[i] = (self._next("gbuf", self.vdepth), self._next("gbuf", self.vdepth))
+                self.e_ext[i] = self._next("ext", getattr(s, "extdim", 0))       # src/network_structure.jl:249
 
     def _next(self, which, n):
         last = self.last[which]
@@ -108,7 +110,8 @@ class PyKind:
     """A component kind given as host callables (tests of user-supplied CUDA kinds): for vertices f(v, esum, p, t) -> dv
     and optionally g(v, p, t) -> out (None = StateMask(1:outdim)); for edges g(v_src, v_dst, p, t) -> e_dst, or with the
     Fiducial wrapper -> (e_src, e_dst) (src/component_functions.jl:189-203); for edges with states
-    f(e, v_src, v_dst, p, t) -> de (their outputs are StateMasks, ESpec.mask_src / mask_dst)."""
+    f(e, v_src, v_dst, p, t) -> de (their outputs are StateMasks, ESpec.mask_src / mask_dst).  Components with external
+    inputs (spec.extdim > 0) take them right after the inputs: f(v, esum, ext, p, t) / f(e, v_src, v_dst, ext, p, t)."""
 
     def __init__(self, f=None, g=None):
         self.f, self.g = f, g
@@ -142,10 +145,10 @@ def _edge_g(kind, vs, vd, p, t=0.0):
     raise ValueError(kind)
 
 
-def _edge_f(kind, e, vs, vd, p, t=0.0):
+def _edge_f(kind, e, vs, vd, p, t=0.0, ext=None):
     """f of edges with states: test/ComponentLibrary.jl:30-34, test/diffusion_test.jl:96-100"""
     if isinstance(kind, PyKind):
-        return [float(x) for x in kind.f(e, vs, vd, p, t)]
+        return [float(x) for x in (kind.f(e, vs, vd, ext, p, t) if ext is not None else kind.f(e, vs, vd, p, t))]
     if kind == O.E_DIFFUSION_ODE:
         tau = p[0]
         return [1.0 / tau * (math.sin(vs[0] - vd[0]) - e[0]), 1.0 / tau * (math.sin(vd[0] - vs[0]) - e[1])]
@@ -154,9 +157,9 @@ def _edge_f(kind, e, vs, vd, p, t=0.0):
     raise ValueError(kind)
 
 
-def _vertex_f(kind, v, acc, p, t=0.0):
+def _vertex_f(kind, v, acc, p, t=0.0, ext=None):
     if isinstance(kind, PyKind):
-        return [float(x) for x in kind.f(v, acc, p, t)]
+        return [float(x) for x in (kind.f(v, acc, ext, p, t) if ext is not None else kind.f(v, acc, p, t))]
     if kind == O.V_DIFFUSION:
         return [acc[0]]
     if kind == O.V_KURAMOTO_FIRST:
@@ -176,8 +179,10 @@ def _vertex_f(kind, v, acc, p, t=0.0):
     raise ValueError(kind)
 
 
-def rhs(im: IndexManager, u, p, t=0.0):
-    """src/coreloop.jl:1-102 with SequentialExecution{true} + SequentialAggregator(+)."""
+def rhs(im: IndexManager, u, p, t=0.0, extmap=None):
+    """src/coreloop.jl:1-102 with SequentialExecution{true} + SequentialAggregator(+).  `extmap`: the ExtMap
+    (src/external_inputs.jl:1-34) as one signed index per slot of the external-input buffer: > 0 = StateBufIdx (1-based
+    index into u), < 0 = -(OutBufIdx) (1-based index into o)."""
     u = [float(x) for x in u]
     p = [float(x) for x in p] if p is not None else []
     du = [0.0] * im.last["dynamic"]
@@ -205,6 +210,11 @@ def rhs(im: IndexManager, u, p, t=0.0):
                 o[im.e_out[i][0].first - 1:im.e_out[i][0].last] = list(odst)
             elif s.coupling == O.FIDUCIAL:
                 o[im.e_out[i][0].first - 1:im.e_out[i][0].last] = ue[s.mask_src - 1:s.mask_src - 1 + s.outdim_src]
+    extbuf = [float("nan")] * im.last["ext"]        # collect_externals!, src/coreloop.jl:61 + src/external_inputs.jl:52-66
+    if im.last["ext"]:
+        assert extmap is not None and len(extmap) == im.last["ext"]
+        for k, src in enumerate(extmap):
+            extbuf[k] = u[src - 1] if src > 0 else o[-src - 1]
     gmap = im.gbuf_map()
     gbuf = [o[k - 1] for k in gmap]  # gather!
     for spec, idxs in im.ebatches:  # PASS 4: f of edges without ff
@@ -213,7 +223,8 @@ def rhs(im: IndexManager, u, p, t=0.0):
             continue
         for i in idxs:
             vs, vd = sl(gbuf, im.e_gbufr[i][0]), sl(gbuf, im.e_gbufr[i][1])
-            du[im.e_data[i].first - 1:im.e_data[i].last] = _edge_f(s.kind, sl(u, im.e_data[i]), vs, vd, sl(p, im.e_para[i]), t)
+            ext = sl(extbuf, im.e_ext[i]) if getattr(s, "extdim", 0) else None
+            du[im.e_data[i].first - 1:im.e_data[i].last] = _edge_f(s.kind, sl(u, im.e_data[i]), vs, vd, sl(p, im.e_para[i]), t, ext)
     for spec, idxs in im.ebatches:  # PASS 5
         s = im.especs[spec]
         if s.dim != 0:
@@ -237,6 +248,7 @@ def rhs(im: IndexManager, u, p, t=0.0):
     for spec, idxs in im.vbatches:  # PASS 6
         s = im.vspecs[spec]
         for i in idxs:
-            dv = _vertex_f(s.kind, sl(u, im.v_data[i]), sl(aggbuf, im.v_aggr[i]), sl(p, im.v_para[i]), t)
+            ext = sl(extbuf, im.v_ext[i]) if getattr(s, "extdim", 0) else None
+            dv = _vertex_f(s.kind, sl(u, im.v_data[i]), sl(aggbuf, im.v_aggr[i]), sl(p, im.v_para[i]), t, ext)
             du[im.v_data[i].first - 1:im.v_data[i].last] = dv
     return np.array(du), np.array(o), np.array(aggbuf)

@@ -22,15 +22,15 @@ def test_header_symbols_are_exported(nd):
     for s in declared:
         assert hasattr(L, s), f"{s} declared in include/nd_b200.h but not exported"
     assert sorted(nd._cabi.EXPORTED_SYMBOLS) == declared
-    assert L.nd_b200_abi_version() == nd._cabi.ABI_VERSION == 4
+    assert L.nd_b200_abi_version() == nd._cabi.ABI_VERSION == 5
 
 
 def test_ctypes_struct_sizes_match_header(nd):
     # field-by-field mirror of the header structs (LP64): catches drift between nd_b200.h and _cabi.py
-    assert ctypes.sizeof(nd._cabi.VBatch) == 4 * 4 + 8 + 8 + 4 * 8
-    assert ctypes.sizeof(nd._cabi.EBatch) == 6 * 4 + 8 + 8 + 4 * 8 + 2 * 4
+    assert ctypes.sizeof(nd._cabi.VBatch) == 4 * 4 + 8 + 8 + 4 * 8 + 2 * 4 + 8
+    assert ctypes.sizeof(nd._cabi.EBatch) == 6 * 4 + 8 + 8 + 4 * 8 + 2 * 4 + 2 * 4 + 8
     assert ctypes.sizeof(nd._cabi.Desc) == 8 + 16 + 16 + 8 + 8 + 16 + 32 + 16 + 8 + 16 + 16
-    assert ctypes.sizeof(nd._cabi.CustomKind) == 6 * 4 + 2 * 8
+    assert ctypes.sizeof(nd._cabi.CustomKind) == 6 * 4 + 2 * 8 + 2 * 4
 
 
 def test_missing_library_fails_loudly(nd, monkeypatch):

@@ -171,3 +171,113 @@ def test_custom_kinds_rk4_and_host_buffers(nd, backend):
         hdu = np.empty_like(u)
         nw(hdu, u, p, 0.0)
         assert floored_rel_err(hdu, ONP.rhs(im, u, p)[0]) <= 1e-12
+
+
+def test_external_inputs(nd, backend, monkeypatch):
+    """External inputs (src/external_inputs.jl, src/coreloop.jl:61): a component's f reads states / outputs of OTHER
+    components -- vertices (f(dv, v, esum, ext, p, t)) and edges with states (f(de, e, vs, vd, ext, p, t)).  Sources: a
+    state (by symbol or index), a StateMask vertex output, a computed vertex output, the output of an edge with states (both
+    sides, AntiSymmetric sign).  Components that differ only in WHAT they refer to share a batch.  Against the Python twin,
+    `du`, RK4, both kernel families; outputs of static (feed-forward) edges are refused like in the reference (:42-44)."""
+    B = backend
+    C = nd.CudaFunction
+    M = _models(nd)
+    rng = np.random.default_rng(8)
+
+    def ctrl(refs):       # a controller vertex: follows the average of two remote quantities, coupled through its first state
+        return nd.VertexModel(f=C("ctrl_f", "vertex_f", "dv[0] = p[0]*(0.5*(ext[0] + ext[1]) - v[0]) + esum[0]; dv[1] = ext[1]*t - v[1];",
+                                  py=lambda v, e, x, p, t: [p[0] * (0.5 * (x[0] + x[1]) - v[0]) + e[0], x[1] * t - v[1]]),
+                              g=nd.StateMask((1,)), dim=2, pdim=1, sym=("x", "y"), extin=tuple(refs), name="ctrl")
+
+    def obs_edge(refs):   # an edge with states that integrates a remote state
+        return nd.EdgeModel(f=C("obs_f", "edge_f", "de[0] = ext[0] - e[0] + p[0]*(v_src[0] - v_dst[0]);",
+                                py=lambda e, vs, vd, x, p, t: [x[0] - e[0] + p[0] * (vs[0] - vd[0])]),
+                            g=nd.AntiSymmetric(1), dim=1, pdim=1, outdim=1, sym=("q",), extin=tuple(refs), name="obs")
+    for mode in ("fused", "jag"):
+        monkeypatch.setenv("ND_B200_KERNEL", mode)
+        g = nd.barabasi_albert(60, 2, seed=3)
+        fhn = nd.VertexModel(f=M["fhn"].f, g=M["fhn"].g, dim=2, pdim=3, sym=("a", "b"), name="fhn")
+        vms = [fhn] * g.nv
+        # three controllers with different references: a state by symbol, a state by index, a vertex output, an edge output
+        vms[4] = ctrl([nd.VIndex(2, "b"), nd.VIndex(7, 1)])
+        vms[11] = ctrl([nd.VIndex(5, ("out", 1)), nd.EIndex(3, ("out", 1))])
+        vms[30] = ctrl([nd.EIndex(3, ("out", 2)), nd.EIndex(3, "q")])
+        ems = [M["wsin"]] * g.ne
+        ems[2] = obs_edge([nd.VIndex(9, "a")])           # edge 3 (1-based): referenced above through both of its outputs
+        ems[10] = obs_edge([nd.VIndex(12, 2)])
+        nw = nd.Network(g, vms, ems)
+        assert len(nw.vertexbatches) == 2 and len(nw.layer.edgebatches) == 2 and nw.im.lastidx_extbuf == 3 * 2 + 2
+        # twin: same batching (hash = model without the references), per-component ExtMap
+        vspec = {id(fhn): O.VSpec(ONP.PyKind(f=fhn.f.py), 2, 3, 1)}
+        vs, vt = [], []
+        for m in vms:
+            key = "ctrl" if m.extdim else "fhn"
+            if key not in [k for k, _ in vs]:
+                vs.append((key, O.VSpec(ONP.PyKind(f=m.f.py), m.dim, m.pdim, m.outdim, m.extdim)))
+            vt.append([k for k, _ in vs].index(key))
+        es, et = [], []
+        for m in ems:
+            key = "obs" if m.dim else "wsin"
+            if key not in [k for k, _ in es]:
+                kind = ONP.PyKind(f=m.f.py) if m.dim else ONP.PyKind(g=m.g.g.py)
+                es.append((key, O.ESpec(kind, m.coupling, m.dim, m.pdim, m.outdim_src, m.outdim_dst, *(m.state_masks() or (0, 0)), m.extdim)))
+            et.append([k for k, _ in es].index(key))
+        im = ONP.IndexManager(g.nv, g.src, g.dst, [s for _, s in vs], vt, [s for _, s in es], et)
+        assert (im.last["dynamic"], im.last["p"], im.last["ext"]) == (nw.dim(), nw.pdim(), nw.im.lastidx_extbuf)
+        from networkdynamics_jl_b200.network import resolve_extin
+        extmap = [0] * im.last["ext"]
+        for i, m in enumerate(vms, start=1):
+            for k, ref in enumerate(m.extin):
+                extmap[im.v_ext[i].first - 1 + k] = resolve_extin(nw.im, ref)
+        for i, m in enumerate(ems, start=1):
+            for k, ref in enumerate(m.extin):
+                extmap[im.e_ext[i].first - 1 + k] = resolve_extin(nw.im, ref)
+        u, p = rng.uniform(-1, 1, nw.dim()), 0.25 + rng.random(nw.pdim())
+        for t in (0.0, 0.6):
+            ref = ONP.rhs(im, u, p, t, extmap)[0]
+            du = B.nan(nw.dim())
+            nw(du, B.dev(u), B.dev(p), t)
+            assert floored_rel_err(B.host(du), ref) <= 1e-12, (mode, t)
+        dt, x, t0 = 1e-2, u.copy(), 0.1
+        for s in range(3):
+            t = t0 + s * dt
+            k1 = ONP.rhs(im, x, p, t, extmap)[0]
+            k2 = ONP.rhs(im, x + 0.5 * dt * k1, p, t + 0.5 * dt, extmap)[0]
+            k3 = ONP.rhs(im, x + 0.5 * dt * k2, p, t + 0.5 * dt, extmap)[0]
+            k4 = ONP.rhs(im, x + dt * k3, p, t + dt, extmap)[0]
+            x = x + (dt / 6.0) * (((k1 + 2.0 * k2) + 2.0 * k3) + k4)
+        ud = B.dev(u)
+        nw.rk4(ud, B.dev(p), t0, dt, 3)
+        assert floored_rel_err(B.host(ud), x) <= 1e-11, mode
+    # computed (non-StateMask) vertex outputs as sources: read from the materialised output block of the same stage
+    monkeypatch.setenv("ND_B200_KERNEL", "fused")
+    g = nd.grid_graph(6, 5)
+    osc = nd.VertexModel(f=M["osc"].f, g=M["osc"].g, dim=2, pdim=1, outdim=2, sym=("th", "r"), name="osc")
+    watcher = nd.VertexModel(f=C("watch_f", "vertex_f", "dv[0] = ext[0]*ext[1] - v[0] + esum[0]; dv[1] = ext[2] + esum[1] - v[1];",
+                                 py=lambda v, e, x, p, t: [x[0] * x[1] - v[0] + e[0], x[2] + e[1] - v[1]]),
+                             g=M["osc"].g, dim=2, pdim=1, outdim=2, sym=("th", "r"),
+                             extin=(nd.VIndex(3, ("out", 1)), nd.VIndex(3, ("out", 2)), nd.VIndex(8, "r")), name="watcher")
+    vms = [osc] * g.nv
+    vms[20] = watcher
+    nw = nd.Network(g, vms, M["line2"])
+    vs = [O.VSpec(ONP.PyKind(f=osc.f.py, g=osc.g.py), 2, 1, 2), O.VSpec(ONP.PyKind(f=watcher.f.py, g=watcher.g.py), 2, 1, 2, 3)]
+    vt = [1 if m.extdim else 0 for m in vms]
+    es = [O.ESpec(ONP.PyKind(g=M["line2"].g.g.py), M["line2"].coupling, 0, 2, 2, 2)]
+    im = ONP.IndexManager(g.nv, g.src, g.dst, vs, vt, es, [0] * g.ne)
+    from networkdynamics_jl_b200.network import resolve_extin
+    extmap = [resolve_extin(nw.im, ref) for ref in watcher.extin]
+    u, p = rng.uniform(-1, 1, nw.dim()), 0.25 + rng.random(nw.pdim())
+    du = B.nan(nw.dim())
+    nw(du, B.dev(u), B.dev(p), 0.3)
+    assert floored_rel_err(B.host(du), ONP.rhs(im, u, p, 0.3, extmap)[0]) <= 1e-12
+    # refusals: output of a static (feed-forward) edge; unknown symbol; registry kinds do not take external inputs
+    g = nd.complete_graph(4)
+    with pytest.raises(nd.ArgumentError, match="feed-forward"):
+        nd.Network(g, [ctrl([nd.EIndex(1, ("out", 1)), nd.VIndex(2, 1)])] + [fhn] * 3, M["wsin"])
+    with pytest.raises(nd.ArgumentError, match="not a state symbol"):
+        nd.Network(g, [ctrl([nd.VIndex(2, "nope"), nd.VIndex(2, 1)])] + [fhn] * 3, M["wsin"])
+    L = nd.Lib
+    kf = L.kuramoto_first()
+    bad = nd.VertexModel(f=kf.f, g=kf.g, dim=1, pdim=1, extin=(nd.VIndex(2, 1),), name="k_ext")
+    with pytest.raises(nd.ArgumentError):
+        nd.Network(g, [bad] + [kf] * 3, L.kuramoto_edge())
