@@ -48,7 +48,10 @@ enum {
   /* edges WITH states (dim > 0): f(de,e,vsrc,vdst,p,t) registered here, outputs are StateMasks (ebatch.mask_*) */
   ND_B200_E_DIFFUSION_ODE = 4,         /* test/ComponentLibrary.jl:30-40, dim 2, p=(tau,)          */
   ND_B200_E_RELAX_ODE = 5,             /* test/diffusion_test.jl:96-101, dim 2, no parameters      */
-  ND_B200_E_DIFFUSION_FID = 6          /* test/ComponentLibrary.jl:22-28, static two-sided g (coupling = ND_B200_FIDUCIAL) */
+  ND_B200_E_DIFFUSION_FID = 6,         /* test/ComponentLibrary.jl:22-28, static two-sided g (coupling = ND_B200_FIDUCIAL) */
+  /* LoopbackConnection (src/post_utils.jl:105-190): Directed(LOOPBACK_G), out_dst = -in_src, from an "injector" leaf to
+   * its hub; the injector's input is the hub's output (apply_loopback!, src/coreloop.jl:47).  vdepth == edepth. */
+  ND_B200_E_LOOPBACK = 7
 };
 /* edge output wrappers, src/component_functions.jl:117-203 */
 enum { ND_B200_ANTISYMMETRIC = 0, ND_B200_SYMMETRIC = 1, ND_B200_DIRECTED = 2,
@@ -118,7 +121,10 @@ typedef struct nd_b200_custom_kind {
   int32_t two_sided;       /* edge only: body has the Fiducial signature                         */
   const char* f_body;      /* vertex: body of f; static edge: body of g; edge with states: body of f */
   const char* g_body;      /* vertex: body of g, or NULL for StateMask(1:outdim); edge: NULL      */
-  int32_t extdim, reserved; /* number of external inputs f takes (0: none)                       */
+  int32_t extdim;          /* number of external inputs f takes (0: none)                         */
+  int32_t g_ff;            /* vertex only: g is feed forward -- void g(double* out, const double* v, const double* ins,
+                              const double* p, double t); allowed for leaves behind a LoopbackConnection
+                              (src/construction.jl:52-80); dim may be 0 (PureFeedForward)            */
 } nd_b200_custom_kind;
 
 typedef struct nd_b200_desc {

@@ -32,7 +32,8 @@ vertex_kernel(f, g) = nothing
 edge_kernel(g) = nothing
 edge_f_kernel(f) = nothing             # f of an edge WITH states ("ODE edge"); its g must be StateMasks
 const V_DIFFUSION, V_KURAMOTO_FIRST, V_KURAMOTO_SECOND, V_KURAMOTO_SECOND_BENCH, V_SWING_DQ = Cint.(0:4)
-const E_DIFFUSION, E_DIFFUSION_NOP, E_KURAMOTO, E_LINE_DQ, E_DIFFUSION_ODE, E_RELAX_ODE, E_DIFFUSION_FID = Cint.(0:6)
+const E_DIFFUSION, E_DIFFUSION_NOP, E_KURAMOTO, E_LINE_DQ, E_DIFFUSION_ODE, E_RELAX_ODE, E_DIFFUSION_FID, E_LOOPBACK = Cint.(0:7)
+edge_kernel(::typeof(NetworkDynamics.LOOPBACK_G)) = E_LOOPBACK      # LoopbackConnection (src/post_utils.jl:105-185)
 # e.g. (test/ComponentLibrary.jl):
 #   NetworkDynamicsB200.edge_kernel(::typeof(Lib.kuramoto_edge!))       = NetworkDynamicsB200.E_KURAMOTO
 #   NetworkDynamicsB200.vertex_kernel(::typeof(Lib.kuramoto_vertex!), ::StateMask) = NetworkDynamicsB200.V_KURAMOTO_FIRST
@@ -62,7 +63,7 @@ const CUSTOM_KIND_BASE = Cint(1000)
 struct CCustomKind
     kind::Cint; role::Cint; dim::Cint; pdim::Cint; outdim::Cint; two_sided::Cint
     f_body::Cstring; g_body::Cstring
-    extdim::Cint; reserved::Cint
+    extdim::Cint; g_ff::Cint          # g_ff: vertex g is feed forward, g(out, v, ins, p, t) (injector leaves only)
 end
 
 # ---- C structs (mirror include/nd_b200.h) ---------------------------------------------------------------------------
@@ -127,18 +128,22 @@ function B200Aggregator(im::IndexManager, edgebatches, f)
         push!(keep, tab)
         pointer(tab)
     end
-    function custom_kind!(role, d, pd, od, two_sided, fsrc, gsrc, xd=0)
+    function custom_kind!(role, d, pd, od, two_sided, fsrc, gsrc, xd=0, gff=0)
         fb = Base.unsafe_convert(Cstring, Base.cconvert(Cstring, fsrc)); push!(keep, fsrc)
         gb = isnothing(gsrc) ? Cstring(C_NULL) : (push!(keep, gsrc); Base.unsafe_convert(Cstring, Base.cconvert(Cstring, gsrc)))
-        push!(customs, CCustomKind(CUSTOM_KIND_BASE + length(customs), role, d, pd, od, two_sided, fb, gb, xd, 0))
+        push!(customs, CCustomKind(CUSTOM_KIND_BASE + length(customs), role, d, pd, od, two_sided, fb, gb, xd, gff))
         customs[end].kind
     end
     vb = map(vidxs) do idxs
         m = im.vertexm[first(idxs)]
         kind = vertex_kernel(compf(m), compg(m))
-        if isnothing(kind) && !isnothing(cuda_source(compf(m)))      # user-supplied kind
+        if isnothing(kind) && (!isnothing(cuda_source(compf(m))) || (isnothing(compf(m)) && !isnothing(cuda_source(compg(m)))))   # user-supplied kind
             gs = compg(m) isa StateMask ? nothing : cuda_source(compg(m))
-            kind = custom_kind!(0, dim(m), pdim(m), outdim(m), 0, cuda_source(compf(m)), gs, NetworkDynamics.extdim(m))
+            # feed-forward g (injector leaves behind a LoopbackConnection): the body takes `ins` after `v`; a vertex without
+            # states (PureFeedForward) has f === nothing: its body is empty
+            gff = NetworkDynamics.hasff(m) ? 1 : 0
+            fsrc = isnothing(compf(m)) ? "" : cuda_source(compf(m))
+            kind = custom_kind!(0, dim(m), pdim(m), outdim(m), 0, fsrc, gs, NetworkDynamics.extdim(m), gff)
         end
         xd = NetworkDynamics.extdim(m)
         (xd > 0 && kind < CUSTOM_KIND_BASE) && throw(ArgumentError("B200 engine: external inputs need a cuda_source vertex function (no CPU fallback)"))

@@ -20,7 +20,7 @@ OK, EINVAL, EUNSUPPORTED, ECUDA, ENOMEM = range(5)
 
 # registry ids (include/nd_b200.h)
 V_DIFFUSION, V_KURAMOTO_FIRST, V_KURAMOTO_SECOND, V_KURAMOTO_SECOND_BENCH, V_SWING_DQ = range(5)
-E_DIFFUSION, E_DIFFUSION_NOP, E_KURAMOTO, E_LINE_DQ, E_DIFFUSION_ODE, E_RELAX_ODE, E_DIFFUSION_FID = range(7)
+E_DIFFUSION, E_DIFFUSION_NOP, E_KURAMOTO, E_LINE_DQ, E_DIFFUSION_ODE, E_RELAX_ODE, E_DIFFUSION_FID, E_LOOPBACK = range(8)
 ANTISYMMETRIC, SYMMETRIC, DIRECTED, FIDUCIAL = range(4)
 CUSTOM_KIND_BASE = 1000
 FLAG_NO_EXPORT = 1
@@ -48,7 +48,7 @@ class EBatch(C.Structure):
 class CustomKind(C.Structure):
     _fields_ = [("kind", C.c_int32), ("role", C.c_int32), ("dim", C.c_int32), ("pdim", C.c_int32), ("outdim", C.c_int32),
                 ("two_sided", C.c_int32), ("f_body", C.c_char_p), ("g_body", C.c_char_p), ("extdim", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("g_ff", C.c_int32)]
 
 
 class Desc(C.Structure):

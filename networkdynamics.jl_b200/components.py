@@ -39,6 +39,8 @@ class CudaFunction:
     ext/NetworkDynamicsMTKExt.jl:497-518).  Arguments visible to the body, by role (include/nd_b200.h):
       vertex_f : double* dv, const double* v, const double* esum, const double* p, double t
       vertex_g : double* out, const double* v, const double* p, double t
+      vertex_gff : double* out, const double* v, const double* ins, const double* p, double t
+                 (feed-forward g of an "injector" leaf behind a LoopbackConnection: `ins` = the hub's output; dim may be 0)
       edge_g   : double* e_dst, const double* v_src, const double* v_dst, const double* p, double t
       edge_g2  : double* e_src, double* e_dst, const double* v_src, const double* v_dst, const double* p, double t
                  (the two-sided form; use it unwrapped or as Fiducial(...))
@@ -181,13 +183,18 @@ class VertexModel:
         """(role, dim, pdim, outdim, two_sided, f_body, g_body, extdim) when f is user-supplied CUDA code, else None"""
         if not isinstance(self.f, CudaFunction) or self.f.role != "vertex_f":
             return None
-        if isinstance(self.g, CudaFunction) and self.g.role == "vertex_g":
+        if isinstance(self.g, CudaFunction) and self.g.role in ("vertex_g", "vertex_gff"):
             g_body = self.g.body
         elif isinstance(self.g, StateMask) and self.g.idxs == tuple(range(1, self.outdim + 1)):
             g_body = None
         else:
             return None
-        return (0, self.dim, self.pdim, self.outdim, 0, self.f.body, g_body, self.extdim)
+        return (0, self.dim, self.pdim, self.outdim, 0, self.f.body, g_body, self.extdim, int(self.hasff))
+
+    @property
+    def hasff(self) -> bool:
+        """feed-forward output function (src/component_functions.jl:63): allowed for injector leaves only"""
+        return isinstance(self.g, CudaFunction) and self.g.role == "vertex_gff"
 
     def kernel_kind(self) -> Optional[int]:
         f = self.f
@@ -255,17 +262,17 @@ class EdgeModel:
     def custom_spec(self):
         if self.dim > 0:              # edge with states: user-supplied f, StateMask outputs
             if isinstance(self.f, CudaFunction) and self.f.role == "edge_f" and self.state_masks() is not None:
-                return (1, self.dim, self.pdim, self.outdim, 0, self.f.body, None, self.extdim)
+                return (1, self.dim, self.pdim, self.outdim, 0, self.f.body, None, self.extdim, 0)
             return None
         if self.f is not None or self.extdim:
             return None
         if isinstance(self.g, CudaFunction) and self.g.role == "edge_g2":       # unwrapped two-sided g
-            return (1, 0, self.pdim, self.outdim, 1, self.g.body, None, 0)
+            return (1, 0, self.pdim, self.outdim, 1, self.g.body, None, 0, 0)
         inner = getattr(self.g, "g", None)
         if isinstance(inner, CudaFunction):
             if isinstance(self.g, Fiducial):
-                return (1, 0, self.pdim, self.outdim, 1, inner.body, None, 0) if inner.role == "edge_g2" else None
-            return (1, 0, self.pdim, self.outdim, 0, inner.body, None, 0) if inner.role == "edge_g" else None
+                return (1, 0, self.pdim, self.outdim, 1, inner.body, None, 0, 0) if inner.role == "edge_g2" else None
+            return (1, 0, self.pdim, self.outdim, 0, inner.body, None, 0, 0) if inner.role == "edge_g" else None
         return None
 
     def kernel_kind(self) -> Optional[int]:
@@ -293,6 +300,7 @@ class Lib:
     diffusionedge_fid = RegisteredFunction("diffusionedge_fid!", _cabi.E_DIFFUSION_FID, "edge_g2", "test/ComponentLibrary.jl:22-25")
     diffusion_dedge = RegisteredFunction("diffusion_dedge!", _cabi.E_DIFFUSION_ODE, "edge_f", "test/ComponentLibrary.jl:30-34")
     real_ode_edge = RegisteredFunction("real_ode_edge!", _cabi.E_RELAX_ODE, "edge_f", "test/diffusion_test.jl:96-100")
+    loopback_g = RegisteredFunction("LOOPBACK_G", _cabi.E_LOOPBACK, "edge_g", "src/post_utils.jl:105-108")
     diffusionvertex = RegisteredFunction("diffusionvertex!", _cabi.V_DIFFUSION, "vertex_f", "test/ComponentLibrary.jl:42-45")
     kuramoto_vertex = RegisteredFunction("kuramoto_vertex!", _cabi.V_KURAMOTO_FIRST, "vertex_f", "test/ComponentLibrary.jl:69-71")
     kuramoto_inertia = RegisteredFunction("kuramoto_inertia!", _cabi.V_KURAMOTO_SECOND, "vertex_f", "test/ComponentLibrary.jl:59-63")
@@ -313,6 +321,12 @@ class Lib:
     def diffusion_edge_fid():
         """test/ComponentLibrary.jl:26-28: two-sided static g, no wrapper"""
         return EdgeModel(g=Fiducial(Lib.diffusionedge_fid), outdim=1, pdim=1, name="diff_edge_fid")
+
+    @staticmethod
+    def loopback(outdim: int = 1):
+        """`LoopbackConnection(; potential, flow)` (src/post_utils.jl:110-185): Directed(LOOPBACK_G) from an injector leaf to
+        its hub -- the hub receives minus the injector's output, the injector's input is the hub's output"""
+        return EdgeModel(g=Directed(Lib.loopback_g), outdim=outdim, pdim=0, name="loopback")
 
     @staticmethod
     def diffusion_odeedge():

@@ -39,7 +39,7 @@ thread_local std::string g_create_error;
 constexpr int MAX_VB = 64;
 constexpr int MAX_EB = 255;   // edge batch id is stored per entry as uint8
 
-struct HostVB { int kind, dim, pdim, outdim; long long count, state0, p0, out0, row0; };
+struct HostVB { int kind, dim, pdim, outdim; long long count, state0, p0, out0, row0; int ff; };
 struct HostEB { int kind, coupling, dim, pdim, osrc, odst; long long count, p0, out0; long long state0; int mask_src, mask_dst; };   // masks 0-based
 
 }  // namespace
@@ -96,7 +96,7 @@ struct nd_b200_engine {
   long long gather_len = 0;
   int wait_from = 0;          // first tile / slice that reads the halo
   // user-supplied component kinds: the kernels are compiled at creation time (NVRTC) from the same header
-  struct CustomKind { int kind, role, dim, pdim, outdim, two_sided; std::string f_body, g_body; int extdim; };
+  struct CustomKind { int kind, role, dim, pdim, outdim, two_sided; std::string f_body, g_body; int extdim, g_ff; };
   std::vector<CustomKind> customs;
   bool custom = false;
   int c_pe = 0, c_maxdim = 1;          // template PE (largest edge pdim) and ND_MAX_VDIM of the generated kernels
@@ -107,6 +107,8 @@ struct nd_b200_engine {
   // gather offsets of its two vertex outputs
   struct OdeBatch { int b; int* d_es; int* d_et; int* d_ext; int extdim; };
   std::vector<int*> d_vext;            // per vertex batch: external-input codes (nullptr: none)
+  std::vector<int*> d_ffin;            // per vertex batch: hub output offsets of feed-forward (injector) vertices
+  bool any_ff = false;
   int c_maxext = 0;                    // ND_MAX_EXT of the generated kernels
   std::vector<OdeBatch> ode;
   int c_maxedim = 1;                   // ND_MAX_EDIM of the generated kernels
@@ -228,6 +230,10 @@ bool edge_kind_ok(const nd_b200_engine* e, const nd_b200_ebatch& b, int vdepth, 
 
 bool edge_kind_ok(const nd_b200_ebatch& b, int vdepth, std::string& why) {
   if (b.extdim != 0) { why = "external inputs need a user-supplied edge kind"; return false; }
+  if (b.kind == ND_B200_E_LOOPBACK) {     // LoopbackConnection: Directed(LOOPBACK_G), any depth with vdepth == edepth
+    if (b.coupling != ND_B200_DIRECTED || b.pdim != 0 || b.dim != 0 || b.outdim_dst != vdepth) { why = "a loopback edge is Directed, without parameters or states, and forwards vdepth values"; return false; }
+    return true;
+  }
   struct R { int kind, pdim, odst, vdepth, dim; };
   static const R reg[] = {{ND_B200_E_DIFFUSION, 1, 1, 1, 0}, {ND_B200_E_DIFFUSION_NOP, 0, 1, 1, 0},
                           {ND_B200_E_KURAMOTO, 1, 1, 1, 0}, {ND_B200_E_LINE_DQ, 3, 2, 2, 0},
@@ -386,18 +392,25 @@ cudaError_t launch_fused(nd_b200_engine* e, const KParams& P, cudaStream_t st) {
   }
 }
 
-cudaError_t launch_vout(nd_b200_engine* e, const double* u, const double* p, double* vout, cudaStream_t st) {
+// PASS 1 (+ PASS 3 for feed-forward vertices, which read their hub's output written by the first launch)
+cudaError_t launch_vout(nd_b200_engine* e, const double* u, const double* p, double* vout, cudaStream_t st, double t = 0.0) {
   const int T = 256;
   const int nb = (int)((e->nrows_total + T - 1) / T);
   if (nb == 0) return cudaSuccess;
-  e->launches++;
-  if (e->custom) {
-    const VBDev* vb = e->d_vb; int nvb = (int)e->hvb.size(), vd = e->vdepth, nr = (int)e->nrows_total; double t0 = 0.0;
-    void* args[] = {&vb, &nvb, &vd, &u, &p, &vout, &nr, &t0};
-    return cudaLaunchKernel((const void*)e->c_vout, dim3((unsigned)nb), dim3(T), args, 0, st);
+  for (int phase = 0; phase < (e->any_ff ? 2 : 1); ++phase) {
+    e->launches++;
+    if (e->custom) {
+      const VBDev* vb = e->d_vb; int nvb = (int)e->hvb.size(), vd = e->vdepth, nr = (int)e->nrows_total; double t0 = t;
+      void* args[] = {&vb, &nvb, &vd, &u, &p, &vout, &nr, &t0, &phase};
+      cudaError_t c = cudaLaunchKernel((const void*)e->c_vout, dim3((unsigned)nb), dim3(T), args, 0, st);
+      if (c != cudaSuccess) return c;
+    } else {
+      ND_LAUNCH(nb, T, st, (e->d_vb, (int)e->hvb.size(), e->vdepth, u, p, vout, (int)e->nrows_total, t, phase), vertex_out_kernel);
+      cudaError_t c = cudaGetLastError();
+      if (c != cudaSuccess) return c;
+    }
   }
-  ND_LAUNCH(nb, T, st, (e->d_vb, (int)e->hvb.size(), e->vdepth, u, p, vout, (int)e->nrows_total, 0.0), vertex_out_kernel);
-  return cudaGetLastError();
+  return cudaSuccess;
 }
 
 // PASS 4 for edge batches with states: du_e = f(u_e, v_src, v_dst, p, t), with the epilogue of the evaluation P describes
@@ -454,8 +467,8 @@ std::string custom_source(const nd_b200_engine* e, int vdepth) {
            "enum { ND_B200_V_DIFFUSION = %d, ND_B200_V_KURAMOTO_FIRST = %d, ND_B200_V_KURAMOTO_SECOND = %d, ND_B200_V_KURAMOTO_SECOND_BENCH = %d, ND_B200_V_SWING_DQ = %d };\n",
            ND_B200_V_DIFFUSION, ND_B200_V_KURAMOTO_FIRST, ND_B200_V_KURAMOTO_SECOND, ND_B200_V_KURAMOTO_SECOND_BENCH, ND_B200_V_SWING_DQ);
   src += buf;
-  snprintf(buf, sizeof buf, "enum { ND_B200_E_DIFFUSION = %d, ND_B200_E_DIFFUSION_NOP = %d, ND_B200_E_KURAMOTO = %d, ND_B200_E_LINE_DQ = %d, ND_B200_E_DIFFUSION_ODE = %d, ND_B200_E_RELAX_ODE = %d, ND_B200_E_DIFFUSION_FID = %d };\n",
-           ND_B200_E_DIFFUSION, ND_B200_E_DIFFUSION_NOP, ND_B200_E_KURAMOTO, ND_B200_E_LINE_DQ, ND_B200_E_DIFFUSION_ODE, ND_B200_E_RELAX_ODE, ND_B200_E_DIFFUSION_FID);
+  snprintf(buf, sizeof buf, "enum { ND_B200_E_DIFFUSION = %d, ND_B200_E_DIFFUSION_NOP = %d, ND_B200_E_KURAMOTO = %d, ND_B200_E_LINE_DQ = %d, ND_B200_E_DIFFUSION_ODE = %d, ND_B200_E_RELAX_ODE = %d, ND_B200_E_DIFFUSION_FID = %d, ND_B200_E_LOOPBACK = %d };\n",
+           ND_B200_E_DIFFUSION, ND_B200_E_DIFFUSION_NOP, ND_B200_E_KURAMOTO, ND_B200_E_LINE_DQ, ND_B200_E_DIFFUSION_ODE, ND_B200_E_RELAX_ODE, ND_B200_E_DIFFUSION_FID, ND_B200_E_LOOPBACK);
   src += buf;
   snprintf(buf, sizeof buf, "enum { ND_B200_ANTISYMMETRIC = %d, ND_B200_SYMMETRIC = %d, ND_B200_DIRECTED = %d, ND_B200_FIDUCIAL = %d };\n",
            ND_B200_ANTISYMMETRIC, ND_B200_SYMMETRIC, ND_B200_DIRECTED, ND_B200_FIDUCIAL);
@@ -471,8 +484,9 @@ std::string custom_source(const nd_b200_engine* e, int vdepth) {
       src += "__device__ __forceinline__ void vertex_f_" + id + "(double* __restrict__ dv, const double* __restrict__ v, const double* __restrict__ esum, " + xa + "const double* __restrict__ p, double t) {\n" + c.f_body + "\n}\n";
       vf_cases += " case " + id + ": ndb_user::vertex_f_" + id + "(dv, v, acc, " + xc + "pv, t); break;";
       if (!c.g_body.empty()) {
-        src += "__device__ __forceinline__ void vertex_g_" + id + "(double* __restrict__ out, const double* __restrict__ v, const double* __restrict__ p, double t) {\n" + c.g_body + "\n}\n";
-        vg_cases += " case " + id + ": ndb_user::vertex_g_" + id + "(out, v, pv, t); break;";
+        const std::string ia = c.g_ff ? "const double* __restrict__ ins, " : "", ic = c.g_ff ? "ins, " : "";
+        src += "__device__ __forceinline__ void vertex_g_" + id + "(double* __restrict__ out, const double* __restrict__ v, " + ia + "const double* __restrict__ p, double t) {\n" + c.g_body + "\n}\n";
+        vg_cases += " case " + id + ": ndb_user::vertex_g_" + id + "(out, v, " + ic + "pv, t); break;";
       }
     } else if (c.dim > 0) {   // edge with states: the body is f; outputs are StateMasks
       const std::string xa = c.extdim > 0 ? "const double* __restrict__ ext, " : "", xc = c.extdim > 0 ? "ext, " : "";
@@ -554,7 +568,8 @@ struct EngineBuilder {
   std::vector<int> goff;                     // vertex id - 1 -> offset of its output in the gather source
   long long state_expect = 1, out_expect = 1, p_expect = 1, nrows_owned = 0;
   // edges
-  bool any_epar = false, any_ode = false, any_fiducial = false, any_ext = false;
+  bool any_epar = false, any_ode = false, any_fiducial = false, any_ext = false, any_loopback = false;
+  std::vector<int> hub_of_vertex;            // vertex id - 1 -> hub vertex id (1-based) of an injector, else 0
   std::vector<std::vector<int>> vext_codes, eext_codes;   // per batch: resolved external-input sources (see VBDev::ext)
   // CSR over the owned rows, entries in accumulation order
   std::vector<long long> cnt;
@@ -613,7 +628,8 @@ struct EngineBuilder {
       if (c.role == 1) e->c_maxedim = std::max(e->c_maxedim, c.dim);
       if (c.extdim < 0 || c.extdim > 32) return fail(e, ND_B200_EUNSUPPORTED, "custom kind %d: extdim outside 0..32", c.kind);
     e->c_maxext = std::max(e->c_maxext, c.extdim);
-    e->customs.push_back(nd_b200_engine::CustomKind{c.kind, c.role, c.dim, c.pdim, c.outdim, c.two_sided, c.f_body, c.g_body ? c.g_body : "", c.extdim});
+    if (c.g_ff && (c.role != 0 || !c.g_body)) return fail(e, ND_B200_EINVAL, "custom kind %d: g_ff needs a vertex kind with a g body", c.kind);
+    e->customs.push_back(nd_b200_engine::CustomKind{c.kind, c.role, c.dim, c.pdim, c.outdim, c.two_sided, c.f_body, c.g_body ? c.g_body : "", c.extdim, c.g_ff});
     }
     for (int b = 0; b < d->n_vbatches; ++b) e->custom = e->custom || d->vbatches[b].kind >= ND_B200_CUSTOM_KIND_BASE;
     for (int b = 0; b < d->n_ebatches; ++b) e->custom = e->custom || d->ebatches[b].kind >= ND_B200_CUSTOM_KIND_BASE;
@@ -645,7 +661,9 @@ struct EngineBuilder {
       if (vb.dim < 0 || vb.pdim < 0) return fail(e, ND_B200_EINVAL, "vertex batch %d: negative dimension", b + 1);
       if (vb.pdim > 0 && vb.p_first != p_expect) return fail(e, ND_B200_EINVAL, "vertex batch %d: pstride.first %lld, expected %lld", b + 1, (long long)vb.p_first, p_expect);
       if (ed > 0 && vb.aggr_first != row * ed + 1) return fail(e, ND_B200_EINVAL, "vertex batch %d: inbufstride.first %lld, expected %lld", b + 1, (long long)vb.aggr_first, row * ed + 1);
-      HostVB h{vb.kind, vb.dim, vb.pdim, vb.outdim, vb.count, vb.state_first - 1, vb.p_first - 1, vb.out_first - 1, row};
+      const bool ff = vb.kind >= ND_B200_CUSTOM_KIND_BASE && find_custom(e, vb.kind, 0)->g_ff;
+      e->any_ff = e->any_ff || ff;
+      HostVB h{vb.kind, vb.dim, vb.pdim, vb.outdim, vb.count, vb.state_first - 1, vb.p_first - 1, vb.out_first - 1, row, ff ? 1 : 0};
       e->hvb.push_back(h);
       for (long long i = 0; i < vb.count; ++i) {
         long long vid = vb.indices ? vb.indices[i] : i + 1;
@@ -744,6 +762,44 @@ struct EngineBuilder {
     // precompiled specialisations exist for the benchmark edge kinds; every other registry kind runs in the generic kernels
     if (!e->custom && d->vdepth == 1 && e->ek != ND_B200_E_DIFFUSION && e->ek != ND_B200_E_DIFFUSION_NOP && e->ek != ND_B200_E_KURAMOTO) e->ek = EK_GENERIC;
     for (int b = 0; b < d->n_ebatches; ++b) any_fiducial = any_fiducial || d->ebatches[b].coupling == ND_B200_FIDUCIAL;
+    for (int b = 0; b < d->n_ebatches; ++b) any_loopback = any_loopback || d->ebatches[b].kind == ND_B200_E_LOOPBACK;
+    if (any_loopback || e->any_ff) {
+      // LoopbackConnection topology (src/construction.jl:52-80): a loopback edge starts at a LEAF (its only edge) -- the
+      // injector -- and every feed-forward vertex is such an injector
+      if (d->vdepth != d->edepth) return fail(e, ND_B200_EINVAL, "loopback edges need vdepth == edepth");
+      if (nrows_owned != e->nrows_total || d->gather_offset) return fail(e, ND_B200_EUNSUPPORTED, "loopback edges on a row-partitioned / halo engine");
+      if (!e->custom && d->vdepth != 1) return fail(e, ND_B200_EUNSUPPORTED, "loopback edges with vdepth %d need user-supplied kinds", d->vdepth);
+      std::vector<int> deg((size_t)d->nv, 0);
+      for (long long k = 0; k < d->ne; ++k) {
+        const long long a = d->edge_src[k], z = d->edge_dst[k];
+        if (a < 1 || a > d->nv || z < 1 || z > d->nv) return fail(e, ND_B200_EINVAL, "edge %lld endpoint out of range", k + 1);
+        deg[(size_t)a - 1]++; deg[(size_t)z - 1]++;
+      }
+      hub_of_vertex.assign((size_t)d->nv, 0);
+      for (int b = 0; b < d->n_ebatches; ++b) {
+        const nd_b200_ebatch& eb = d->ebatches[b];
+        if (eb.kind != ND_B200_E_LOOPBACK) continue;
+        for (long long i = 0; i < eb.count; ++i) {
+          const long long eid = eb.indices ? eb.indices[i] - 1 : i;
+          const long long a = d->edge_src[eid], z = d->edge_dst[eid];
+          if (deg[(size_t)a - 1] != 1) return fail(e, ND_B200_EINVAL, "all LoopbackConnection edges must originate from leaf nodes (edge %lld)", eid + 1);
+          hub_of_vertex[(size_t)a - 1] = (int)z;
+        }
+      }
+      for (int b = 0; b < d->n_vbatches; ++b) {
+        if (!e->hvb[(size_t)b].ff) continue;
+        for (long long i = 0; i < d->vbatches[b].count; ++i) {
+          const long long vid = d->vbatches[b].indices ? d->vbatches[b].indices[i] : i + 1;
+          if (!hub_of_vertex[(size_t)vid - 1]) return fail(e, ND_B200_EINVAL, "feed-forward vertex %lld: feed forward vertex models are only allowed as leaf nodes with a single LoopbackConnection to their hub", vid);
+        }
+      }
+      for (long long v = 0; v < d->nv; ++v)      // a hub is not itself a feed-forward vertex: its output must exist after PASS 1
+        if (hub_of_vertex[(size_t)v] && e->hvb.size()) {
+          const int hr = row_of_vertex[(size_t)hub_of_vertex[(size_t)v] - 1];
+          for (const HostVB& h : e->hvb)
+            if (hr >= h.row0 && hr < h.row0 + h.count && h.ff) return fail(e, ND_B200_EINVAL, "the hub of injector %lld is a feed-forward vertex", v + 1);
+        }
+    }
     if (any_ode && (d->lastidx_dynamic >= ND_STATE_ENTRY_BIT || d->nv * (long long)d->vdepth >= ND_STATE_ENTRY_BIT))
       return fail(e, ND_B200_EUNSUPPORTED, "networks with edge states need offsets below 2^30");
     if (any_ode && !e->custom && d->vdepth != 1) return fail(e, ND_B200_EUNSUPPORTED, "edges with states and vdepth %d need user-supplied kinds", d->vdepth);
@@ -830,7 +886,7 @@ struct EngineBuilder {
         const long long s = d->edge_src[eid], t = d->edge_dst[eid];
         if (s < 1 || s > d->nv || t < 1 || t > d->nv) return fail(e, ND_B200_EINVAL, "edge %lld endpoint out of range", eid + 1);
         const int rs = row_of_vertex[(size_t)s - 1], rt = row_of_vertex[(size_t)t - 1];
-        if (eb.outdim_src > 0 && owned(rs)) cnt[(size_t)(rs - e->row_begin) + 1]++;
+        if ((eb.outdim_src > 0 || eb.kind == ND_B200_E_LOOPBACK) && owned(rs)) cnt[(size_t)(rs - e->row_begin) + 1]++;   // loopback: the injector's input entry
         if (owned(rt)) cnt[(size_t)(rt - e->row_begin) + 1]++;
       }
     }
@@ -853,7 +909,7 @@ struct EngineBuilder {
     e->oedge_len = d->lastidx_out - e->oedge_base;
     e->ne_all = d->ne;
     want_split = false;
-    if (const char* s = getenv("ND_B200_KERNEL")) want_split = !strcmp(s, "split") && nrows_owned == e->nrows_total && !(d->vdepth == 2 && d->n_ebatches > 1) && !e->custom && !any_ode && !any_fiducial && !any_ext;
+    if (const char* s = getenv("ND_B200_KERNEL")) want_split = !strcmp(s, "split") && nrows_owned == e->nrows_total && !(d->vdepth == 2 && d->n_ebatches > 1) && !e->custom && !any_ode && !any_fiducial && !any_ext && !any_loopback;
     if (want_split && e->oedge_len >= INT_MAX) return fail(e, ND_B200_EUNSUPPORTED, "edge output buffer exceeds 2^31 scalars on one device");
     h_oidx.assign(want_split ? (size_t)std::max<long long>(e->nentries, 1) : 1, 0);
     h_es.assign(want_split ? (size_t)std::max<long long>(d->ne, 1) : 1, 0);
@@ -878,7 +934,7 @@ struct EngineBuilder {
           // flagged with ND_STATE_ENTRY_BIT (state_entry_value in the kernels)
           const int so_src = eb.dim > 0 ? (int)((eb.state_first - 1) + i * eb.dim + (eb.coupling == ND_B200_FIDUCIAL ? eb.mask_src_first - 1 : eb.mask_dst_first - 1)) | ND_STATE_ENTRY_BIT : 0;
           const int so_dst = eb.dim > 0 ? (int)((eb.state_first - 1) + i * eb.dim + (eb.mask_dst_first - 1)) | ND_STATE_ENTRY_BIT : 0;
-          if (eb.outdim_src > 0 && owned(rs)) {
+          if ((eb.outdim_src > 0 || eb.kind == ND_B200_E_LOOPBACK) && owned(rs)) {
             const long long j = cur[(size_t)(rs - e->row_begin)]++;
             if (want_split) h_oidx[(size_t)j] = (int)oo;
             h_nbr[(size_t)j] = eb.dim > 0 ? ~so_src : ~goff[(size_t)t - 1];
@@ -935,7 +991,7 @@ struct EngineBuilder {
     e->n_long = 0;
     for (size_t b = 0; b < e->hvb.size(); ++b) {
       const HostVB& h = e->hvb[b];
-      VBDev v{h.kind, h.dim, h.pdim, (int)h.row0, (int)h.count, (int)blk_row.size(), h.state0, h.p0, nullptr, d->vbatches[b].extdim, 0};
+      VBDev v{h.kind, h.dim, h.pdim, (int)h.row0, (int)h.count, (int)blk_row.size(), h.state0, h.p0, nullptr, d->vbatches[b].extdim, h.ff, nullptr};
       long long r = std::max<long long>(h.row0, e->row_begin);
       const long long rend = std::min<long long>(h.row0 + h.count, e->row_end);
       while (r < rend) {
@@ -1194,6 +1250,17 @@ struct EngineBuilder {
     }
     if (e->host_only) return ND_B200_OK;
     CUDA_TRY(e, cudaSetDevice(e->device));
+    e->d_ffin.assign((size_t)d->n_vbatches, nullptr);
+    for (int b = 0; b < d->n_vbatches; ++b) {
+      if (!e->hvb[(size_t)b].ff) continue;
+      std::vector<int> ffin((size_t)d->vbatches[b].count);
+      for (long long i = 0; i < d->vbatches[b].count; ++i) {
+        const long long vid = d->vbatches[b].indices ? d->vbatches[b].indices[i] : i + 1;
+        ffin[(size_t)i] = goff[(size_t)hub_of_vertex[(size_t)vid - 1] - 1];     // offset of the hub's output in the vertex-output block
+      }
+      if (upload(e, &e->d_ffin[(size_t)b], ffin)) return ND_B200_ECUDA;
+      dvb[(size_t)b].ffin = e->d_ffin[(size_t)b];
+    }
     e->d_vext.assign((size_t)d->n_vbatches, nullptr);
     for (int b = 0; b < d->n_vbatches; ++b) {
       if (d->vbatches[b].extdim <= 0) continue;
@@ -1291,7 +1358,7 @@ int rhs_impl(nd_b200_engine* e, double* du, const double* u, const double* p, do
   }
   if (!e->gather_from_u) {
     if (e->timing) CUDA_TRY(e, cudaEventRecord(e->ev_pre[e->ev_pre_used], st));
-    CUDA_TRY(e, launch_vout(e, u, p, e->d_vout[0], st));
+    CUDA_TRY(e, launch_vout(e, u, p, e->d_vout[0], st, t));
     if (e->timing) { CUDA_TRY(e, cudaEventRecord(e->ev_pre[e->ev_pre_used + 1], st)); e->ev_pre_used += 2; }
     P.gsrc = e->d_vout[0];
   }
@@ -1321,6 +1388,12 @@ int rk4_step_enqueue(nd_b200_engine* e, double* u, const double* p, double t, do
   for (int s = 0; s < 4; ++s) {
     P.stage = s + 1; P.u = in[s]; P.unext = out[s]; P.hs = hs[s]; P.t = ts[s];
     if (e->gather_from_u) { P.gsrc = in[s]; P.vout_next = nullptr; }
+    else if (e->custom) {
+      // user-supplied output functions may read t or, for feed-forward vertices, another vertex's output: every stage runs
+      // the output pre-pass on its own input at its own time instead of taking the outputs from the previous epilogue
+      CUDA_TRY(e, launch_vout(e, in[s], p, e->d_vout[0], st, ts[s]));
+      P.gsrc = e->d_vout[0]; P.vout_next = nullptr;
+    }
     else { P.gsrc = e->d_vout[s & 1]; P.vout_next = e->d_vout[(s + 1) & 1]; }   // stage 4 leaves outputs of the new u in d_vout[0]
     CUDA_TRY(e, launch_fused(e, P, st));
     if (!e->ode.empty()) CUDA_TRY(e, launch_edge_f(e, P, st));
@@ -1413,6 +1486,7 @@ void nd_b200_destroy(nd_b200_engine* e) {
   cudaFree(e->d_jslices); cudaFree(e->d_jlanes); cudaFree(e->d_jnbr); cudaFree(e->d_jent); cudaFree(e->d_jebid); cudaFree(e->d_jlong);
   for (auto& ob : e->ode) { cudaFree(ob.d_es); cudaFree(ob.d_et); cudaFree(ob.d_ext); }
   for (int* q : e->d_vext) cudaFree(q);
+  for (int* q : e->d_ffin) cudaFree(q);
   cudaFree(e->d_ppack);
   for (int* q : e->d_esrc_off) cudaFree(q);
   for (int* q : e->d_edst_off) cudaFree(q);
@@ -1573,12 +1647,12 @@ int nd_b200_get_buffers(nd_b200_engine* e, double* o, double* aggbuf, const doub
   cudaStream_t st = (cudaStream_t)stream;
   const double* gsrc = u;
   if (!e->gather_from_u) {
-    CUDA_TRY(e, launch_vout(e, u, p, e->d_vout[0], st));
+    CUDA_TRY(e, launch_vout(e, u, p, e->d_vout[0], st, t));
     gsrc = e->d_vout[0];
   }
   if (o) {
     // vertex outputs occupy o[0 .. nv*vdepth) in row order (register_vertices!)
-    CUDA_TRY(e, launch_vout(e, u, p, o, st));
+    CUDA_TRY(e, launch_vout(e, u, p, o, st, t));
     if (e->d_esrc_off.empty()) {
       e->d_esrc_off.assign(e->heb.size(), nullptr); e->d_edst_off.assign(e->heb.size(), nullptr);
       for (size_t b = 0; b < e->heb.size(); ++b)
@@ -1635,7 +1709,7 @@ int nd_b200_rk4(nd_b200_engine* e, double* u, const double* p, double t0, double
     const bool want = s ? atoi(s) > 0 : (sizeof(double) * (size_t)e->lastidx_p >= ((size_t)256 << 20) && nsteps >= 4);
     if (want && nd_b200_pack_params(e, p, stream) == ND_B200_OK) unpack.on = true;
   }
-  if (!e->gather_from_u) CUDA_TRY(e, launch_vout(e, u, p, e->d_vout[0], st));
+  if (!e->gather_from_u && !e->custom) CUDA_TRY(e, launch_vout(e, u, p, e->d_vout[0], st, t0));
   // The registry models are autonomous, so one captured step can be replayed for every t.  User-supplied kinds may read
   // t: their steps are enqueued one by one with the right stage times.
   if (e->custom) {

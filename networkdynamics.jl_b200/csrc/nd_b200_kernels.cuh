@@ -44,6 +44,7 @@
 #endif
 #ifndef ND_CUSTOM_VERTEX_G_CASES
 #define ND_CUSTOM_VERTEX_G_CASES // case <kind>: ndb_user::vertex_g_<kind>(out, v, pv, t); break;
+                                 // feed-forward vertices (injectors): ndb_user::vertex_g_<kind>(out, v, ins, pv, t)
 #endif
 
 namespace ndb {
@@ -56,7 +57,11 @@ struct VBDev {          // one vertex ComponentBatch, 0-based offsets
   // external inputs (src/external_inputs.jl): component i of the batch reads extdim scalars, ext[i*extdim + k] = where
   // from: low 30 bits = offset, bit 30 = from the materialised vertex outputs instead of u, bit 31 = negated
   const int* ext;
-  int extdim, pad_;
+  int extdim;
+  // feed-forward vertices ("injector" leaves behind a LoopbackConnection, src/post_utils.jl:110-190): g also reads the
+  // vertex's input = the output of its hub; ffin[i] = offset of that hub's output in the materialised vertex outputs
+  int ff;
+  const int* ffin;
 };
 constexpr int ND_EXT_FROM_VOUT = 1 << 30;
 // collect_externals! for one component (src/coreloop.jl:61, src/external_inputs.jl:52-66)
@@ -212,6 +217,12 @@ __device__ __forceinline__ void edge_g_dst(int kind, double* odst, const double*
         odst[1] = active * ((R * di - X * dr) / den);
       }
       break;
+    case ND_B200_E_LOOPBACK:       // LOOPBACK_G, src/post_utils.jl:105-108: outdst .= -1 .* insrc
+      if constexpr (VD == ED) {
+#pragma unroll
+        for (int d = 0; d < ED; ++d) odst[d] = -1.0 * vs[d];
+      }
+      break;
     ND_CUSTOM_EDGE_CASES
     default:
 #pragma unroll
@@ -227,6 +238,15 @@ __device__ __forceinline__ void entry_value(int kind, int coupling, int side, co
                                             const double* xn, const double* __restrict__ pe, double t, double* val) {
   const double* vs = side ? self : xn;
   const double* vd = side ? xn : self;
+  if (kind == ND_B200_E_LOOPBACK && side) {
+    // apply_loopback! (src/coreloop.jl:47, src/post_utils.jl:213-234): the injector's input IS its hub's output.  The
+    // engine stores it as the one entry of the injector's row (the loopback edge has no src output in `o`).
+    if constexpr (VD == ED) {
+#pragma unroll
+      for (int d = 0; d < ED; ++d) val[d] = vd[d];
+    }
+    return;
+  }
   if (coupling == ND_B200_FIDUCIAL) {
     double osrc[ED], odst[ED];
 #pragma unroll
@@ -288,8 +308,8 @@ __device__ __forceinline__ void edge_f(int kind, double* de, const double* ue, c
 
 // vertex g for non-StateMask models: NoFeedForward g(out,u,p,t)
 __device__ __forceinline__ void vertex_g(int kind, int outdim, double* out, const double* v,
-                                         const double* __restrict__ pv, double t) {
-  (void)t;
+                                         const double* __restrict__ pv, double t, const double* ins = nullptr) {
+  (void)t; (void)ins;
   switch (kind) {
     case ND_B200_V_SWING_DQ: {          // test/ComponentLibrary.jl:158-159
       double V = pv[3];
@@ -393,7 +413,7 @@ __device__ __forceinline__ void vertex_phase(const KParams& P, const VBDev& B, i
     }
     P.unext[idx] = un[c];
   }
-  if (!P.gather_from_u) {
+  if (!P.gather_from_u && P.vout_next) {      // absent: the next stage runs the output pre-pass itself
     double out[VD];
     vertex_g(B.kind, VD, out, un, pv, P.t);
 #pragma unroll
@@ -722,19 +742,24 @@ __global__ void extract_nbr_kernel(const int* __restrict__ pairs, long long n, i
 #ifndef ND_MAX_VOUT
 #define ND_MAX_VOUT 2            // largest vertex output dimension (vdepth)
 #endif
+// phase 0: vertices without feed forward (src/coreloop.jl:39); phase 1: feed-forward vertices, after the loopback copy
+// (src/coreloop.jl:47,55) -- their g reads the hub's output that phase 0 wrote
 __global__ void vertex_out_kernel(const VBDev* __restrict__ vb, int n_vb, int vd, const double* __restrict__ u,
-                                  const double* __restrict__ p, double* __restrict__ vout, int nrows_total, double t) {
+                                  const double* __restrict__ p, double* __restrict__ vout, int nrows_total, double t, int phase) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= nrows_total) return;
   int b = 0;
   for (int i = 1; i < n_vb; ++i)
     if (row >= vb[i].row0) b = i;
   const VBDev B = vb[b];
+  if ((B.ff != 0) != (phase != 0)) return;
   const long long i = row - B.row0;
-  double v[ND_MAX_VDIM], out[ND_MAX_VOUT];
+  double v[ND_MAX_VDIM], out[ND_MAX_VOUT], ins[ND_MAX_VOUT];
   for (int c = 0; c < ND_MAX_VDIM; ++c) v[c] = c < B.dim ? u[B.state0 + i * B.dim + c] : 0.0;
-  for (int k = 0; k < ND_MAX_VOUT; ++k) out[k] = 0.0;
-  vertex_g(B.kind, vd, out, v, p + B.p0 + i * B.pdim, t);
+  for (int k = 0; k < ND_MAX_VOUT; ++k) { out[k] = 0.0; ins[k] = 0.0; }
+  if (B.ff)
+    for (int k = 0; k < vd; ++k) ins[k] = vout[(long long)B.ffin[i] + k];
+  vertex_g(B.kind, vd, out, v, p + B.p0 + i * B.pdim, t, ins);
   for (int k = 0; k < vd; ++k) vout[(long long)row * vd + k] = out[k];
 }
 

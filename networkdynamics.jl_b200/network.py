@@ -298,10 +298,10 @@ class B200Aggregator:
         if customs:
             ck = (_cabi.CustomKind * len(customs))()
             for i, (spec, kid) in enumerate(customs.items()):
-                role, dim, pdim, outdim, two_sided, f_body, g_body, extdim = spec
+                role, dim, pdim, outdim, two_sided, f_body, g_body, extdim, g_ff = spec
                 fb, gb = f_body.encode(), (g_body.encode() if g_body is not None else None)
                 keep += [fb, gb]
-                ck[i] = _cabi.CustomKind(kid, role, dim, pdim, outdim, two_sided, fb, gb, extdim, 0)
+                ck[i] = _cabi.CustomKind(kid, role, dim, pdim, outdim, two_sided, fb, gb, extdim, g_ff)
             keep.append(ck)
             desc.n_custom = len(customs)
             desc.custom = ck

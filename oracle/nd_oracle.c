@@ -276,6 +276,8 @@ static inline void edge_g_dst(int kind, double* odst, const double* vs, const do
     case NDO_E_KURAMOTO:       /* test/ComponentLibrary.jl:51-53, benchmark_models.jl:27-29 */
       odst[0] = p[0] * sin(vs[0] - vd[0]);
       break;
+    case NDO_E_LOOPBACK:       /* src/post_utils.jl:105-108 : outdst .= -1 .* insrc (caller passes the vertex depth) */
+      break;
     case NDO_E_LINE_DQ: {      /* test/ComponentLibrary.jl:212-245: idst = active*1/Z*(Vsrc-Vdst), Z=R+jX.
                                   Hand-written equivalent (MTK codegen order is not recoverable):
                                   1/Z = (R - jX)/(R^2+X^2). */
@@ -356,7 +358,8 @@ static int check_supported(const ndo_network* nw) {
   }
   for (int32_t b = 0; b < nw->n_eb; ++b) {
     const ndo_espec* s = &nw->especs[nw->eb[b].spec];
-    if (s->kind < 0 || s->kind > NDO_E_DIFFUSION_FID) FAIL("edge kind %d has no RHS in the oracle", s->kind);
+    if (s->kind < 0 || s->kind > NDO_E_LOOPBACK) FAIL("edge kind %d has no RHS in the oracle", s->kind);
+    if (s->kind == NDO_E_LOOPBACK && (s->coupling != NDO_DIRECTED || s->pdim != 0 || s->dim != 0 || nw->vdepth != nw->edepth)) FAIL("a loopback edge is Directed(LOOPBACK_G) with vdepth == edepth");
     if ((s->dim != 0) != edge_kind_has_states(s->kind)) FAIL("edge kind %d: dim %d does not fit the model", s->kind, s->dim);
     if (s->dim != 0) {   /* outputs are StateMasks over the edge's own states */
       if (s->mask_dst < 1 || s->mask_dst + s->outdim_dst - 1 > s->dim) FAIL("edge StateMask (dst) outside the states");
@@ -401,6 +404,7 @@ static inline void eb_g(ndo_network* nw, const ndo_batch* B, const ndo_espec* s,
   double* osrc = nw->o + (B->out_first - 1) + k * (s->outdim_src + s->outdim_dst);
   double* odst = osrc + s->outdim_src;
   if (s->coupling == NDO_FIDUCIAL) { edge_g_two_sided(s->kind, osrc, odst, vsrc, vdst, pp); return; }
+  if (s->kind == NDO_E_LOOPBACK) { for (int d = 0; d < s->outdim_dst; ++d) odst[d] = -1.0 * vsrc[d]; return; }
   edge_g_dst(s->kind, odst, vsrc, vdst, pp);
   if (s->coupling == NDO_ANTISYMMETRIC)      /* src/component_functions.jl:117-127 */
     for (int d = 0; d < s->outdim_src; ++d) osrc[d] = -odst[d];
@@ -414,6 +418,21 @@ static inline void vb_f(ndo_network* nw, const ndo_batch* B, const ndo_vspec* s,
   const double* pp = p ? p + (B->p_first - 1) + k * s->pdim : NULL;
   const double* acc = nw->aggbuf + (B->in_first - 1) + k * nw->edepth;
   vertex_f(s->kind, dd, uu, acc, pp);
+}
+
+/* gen_loopback_map + _apply_loopback!, src/post_utils.jl:213-234: for every loopback edge copy the dst (hub) vertex's
+ * output into the src (injector) vertex's aggregation slot */
+static void apply_loopback(ndo_network* nw) {
+  for (int32_t b = 0; b < nw->n_eb; ++b) {
+    const ndo_batch* B = &nw->eb[b];
+    if (nw->especs[B->spec].kind != NDO_E_LOOPBACK) continue;
+    for (int64_t k = 0; k < B->len; ++k) {
+      int64_t i = B->indices[k] - 1;
+      const double* ov = nw->o + nw->v_out[nw->edst[i] - 1] - 1;
+      double* av = nw->aggbuf + nw->v_aggr[nw->esrc[i] - 1] - 1;
+      for (int d = 0; d < nw->vdepth; ++d) av[d] = ov[d];
+    }
+  }
 }
 
 /* (nw::Network)(du,u,p,t), src/coreloop.jl:1-102, SequentialExecution{true} (:111-119),
@@ -435,7 +454,9 @@ int ndo_rhs_sequential(ndo_network* nw, double* du, const double* u, const doubl
     if (s->dim == 0) continue;
     for (int64_t k = 0; k < B->len; ++k) eb_g_state(nw, B, s, k, u);
   }
-  /* loopback, PASS 3 (ff vertices), externals: empty for the restated models */
+  /* apply_loopback!, coreloop.jl:47 + post_utils.jl:213-234 : injector input <- hub output */
+  apply_loopback(nw);
+  /* PASS 3 (ff vertices), externals: empty for the restated models */
   /* gather!, coreloop.jl:67 + gbufs.jl:25 */
   for (int64_t k = 0; k < nw->lastidx_gbuf; ++k) nw->gbuf[k] = nw->o[nw->gbufmap[k] - 1];
   /* PASS 4: f of edges without ff, coreloop.jl:76 */
@@ -528,6 +549,7 @@ int ndo_rhs_threaded(ndo_network* nw, double* du, const double* u, const double*
 #pragma omp parallel for schedule(static) num_threads(nthreads)
     for (int64_t k = 0; k < B->len; ++k) eb_g_state(nw, B, s, k, u);
   }
+  apply_loopback(nw);   /* serial in the reference (CPU version of _apply_loopback!) */
   /* NNlib.gather! on Vectors is multithreaded over the destination */
 #pragma omp parallel for schedule(static) num_threads(nthreads)
   for (int64_t k = 0; k < nw->lastidx_gbuf; ++k) nw->gbuf[k] = nw->o[nw->gbufmap[k] - 1];

@@ -47,6 +47,8 @@ enum {
   NDO_E_DIFFUSION_ODE = 4,      /* ODE edge, dim 2, p=(tau,): de = 1/tau*(sin(..)-e); outputs are states  */
   NDO_E_RELAX_ODE = 5,          /* ODE edge, dim 2, no p: de1 = vs-vd-e1, de2 = vd-vs-e2                 */
   NDO_E_DIFFUSION_FID = 6,      /* static two-sided g: e_d = p*(vs-vd); e_s = -e_d                       */
+  NDO_E_LOOPBACK = 7,           /* LoopbackConnection: Directed(LOOPBACK_G), out_dst = -in_src; the src vertex's
+                                   input is the dst vertex's output (apply_loopback!)                    */
   NDO_E_OPAQUE = 100
 };
 /* edge output wrappers, src/component_functions.jl:117-203 */

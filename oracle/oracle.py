@@ -21,7 +21,7 @@ _LIB = os.path.join(_HERE, "libnd_oracle.so")
 # kind ids (mirror nd_oracle.h)
 V_DIFFUSION, V_KURAMOTO_FIRST, V_KURAMOTO_SECOND, V_KURAMOTO_SECOND_BENCH, V_SWING_DQ = range(5)
 V_OPAQUE = 100
-E_DIFFUSION, E_DIFFUSION_NOP, E_KURAMOTO, E_LINE_DQ, E_DIFFUSION_ODE, E_RELAX_ODE, E_DIFFUSION_FID = range(7)
+E_DIFFUSION, E_DIFFUSION_NOP, E_KURAMOTO, E_LINE_DQ, E_DIFFUSION_ODE, E_RELAX_ODE, E_DIFFUSION_FID, E_LOOPBACK = range(8)
 E_OPAQUE = 100
 ANTISYMMETRIC, SYMMETRIC, DIRECTED, FIDUCIAL = range(4)
 
@@ -42,6 +42,7 @@ class VSpec:
     pdim: int
     outdim: int
     extdim: int = 0        # external inputs (Python twin only; the C restatement rejects them)
+    ff: bool = False       # feed-forward g(v, ins, p, t) of an injector leaf (Python twin only)
 
 
 @dataclass(frozen=True)
@@ -142,8 +143,8 @@ class OracleNetwork:
         vt = np.ascontiguousarray(vtype, dtype=np.int32)
         et = np.ascontiguousarray(etype, dtype=np.int32)
         assert vt.size == self.nv and et.size == self.ne
-        if any(getattr(s, "extdim", 0) for s in self.vspecs + self.especs):
-            raise ValueError("external inputs are not restated in the C oracle (use the Python twin)")
+        if any(getattr(s, "extdim", 0) or getattr(s, "ff", False) for s in self.vspecs + self.especs):
+            raise ValueError("external inputs / feed-forward vertices are not restated in the C oracle (use the Python twin)")
         vs = (_VSpec * max(1, len(self.vspecs)))(*[_VSpec(s.kind, s.dim, s.pdim, s.outdim) for s in self.vspecs])
         es = (_ESpec * max(1, len(self.especs)))(*[_ESpec(s.kind, s.coupling, s.dim, s.pdim, s.outdim_src, s.outdim_dst,
                                                           getattr(s, "mask_src", 0), getattr(s, "mask_dst", 0))

@@ -117,9 +117,11 @@ class PyKind:
         self.f, self.g = f, g
 
 
-def _vertex_g(kind, u, p, t=0.0):
+def _vertex_g(kind, u, p, t=0.0, ins=None):
     if isinstance(kind, PyKind):
-        return None if kind.g is None else [float(x) for x in kind.g(u, p, t)]
+        if kind.g is None:
+            return None
+        return [float(x) for x in (kind.g(u, ins, p, t) if ins is not None else kind.g(u, p, t))]
     if kind == O.V_SWING_DQ:
         return [p[3] * math.cos(u[0]), p[3] * math.sin(u[0])]
     return None  # StateMask handled by caller
@@ -134,6 +136,8 @@ def _edge_g(kind, vs, vd, p, t=0.0):
         return [vs[0] - vd[0]]
     if kind == O.E_KURAMOTO:
         return [p[0] * math.sin(vs[0] - vd[0])]
+    if kind == O.E_LOOPBACK:                               # src/post_utils.jl:105-108
+        return [-1.0 * x for x in vs]
     if kind == O.E_DIFFUSION_FID:                          # two-sided: (e_src, e_dst)
         ed = p[0] * (vs[0] - vd[0])
         return [-ed], [ed]
@@ -189,8 +193,10 @@ def rhs(im: IndexManager, u, p, t=0.0, extmap=None):
     o = [float("nan")] * im.last["out"]
     aggbuf = [0.0] * im.last["aggr"]
     sl = lambda a, r: a[r.first - 1:r.last]
-    for spec, idxs in im.vbatches:  # PASS 1
+    for spec, idxs in im.vbatches:  # PASS 1: g of vertices without feed forward
         s = im.vspecs[spec]
+        if getattr(s, "ff", False):
+            continue
         for i in idxs:
             out = _vertex_g(s.kind, sl(u, im.v_data[i]), sl(p, im.v_para[i]), t)
             if out is None:
@@ -210,6 +216,18 @@ def rhs(im: IndexManager, u, p, t=0.0, extmap=None):
                 o[im.e_out[i][0].first - 1:im.e_out[i][0].last] = list(odst)
             elif s.coupling == O.FIDUCIAL:
                 o[im.e_out[i][0].first - 1:im.e_out[i][0].last] = ue[s.mask_src - 1:s.mask_src - 1 + s.outdim_src]
+    for spec, idxs in im.ebatches:  # apply_loopback!, src/coreloop.jl:47 + src/post_utils.jl:213-234
+        if im.especs[spec].kind != O.E_LOOPBACK:
+            continue
+        for i in idxs:
+            src, dst = im.edgevec[i - 1]
+            aggbuf[im.v_aggr[src].first - 1:im.v_aggr[src].last] = sl(o, im.v_out[dst])
+    for spec, idxs in im.vbatches:  # PASS 3: g of feed-forward vertices (injectors), src/coreloop.jl:55
+        s = im.vspecs[spec]
+        if not getattr(s, "ff", False):
+            continue
+        for i in idxs:
+            o[im.v_out[i].first - 1:im.v_out[i].last] = _vertex_g(s.kind, sl(u, im.v_data[i]), sl(p, im.v_para[i]), t, sl(aggbuf, im.v_aggr[i]))
     extbuf = [float("nan")] * im.last["ext"]        # collect_externals!, src/coreloop.jl:61 + src/external_inputs.jl:52-66
     if im.last["ext"]:
         assert extmap is not None and len(extmap) == im.last["ext"]

@@ -281,3 +281,100 @@ def test_external_inputs(nd, backend, monkeypatch):
     bad = nd.VertexModel(f=kf.f, g=kf.g, dim=1, pdim=1, extin=(nd.VIndex(2, 1),), name="k_ext")
     with pytest.raises(nd.ArgumentError):
         nd.Network(g, [bad] + [kf] * 3, L.kuramoto_edge())
+
+
+def test_loopback_connections_and_feed_forward_injectors(nd, backend, monkeypatch):
+    """LoopbackConnection + injector vertices (src/post_utils.jl:105-234, src/coreloop.jl:47,55; test/loopback_test.jl part A:
+    a capacitor hub with a resistor injector (pure feed forward, no states), an inductor injector (state output) and a
+    voltage source behind a resistor edge).  The injector's input is its hub's output, the hub receives minus the injector's
+    output; feed-forward g runs after the loopback copy.  Closed form, Python twin, RK4, get_buffers; then a registry-only
+    network against the C oracle; then the reference's topology errors."""
+    B = backend
+    C = nd.CudaFunction
+    L = nd.Lib
+    hub = nd.VertexModel(f=C("cap_f", "vertex_f", "dv[0] = esum[0] / p[0];", py=lambda v, e, p, t: [e[0] / p[0]]),
+                         g=nd.StateMask((1,)), dim=1, pdim=1, sym=("v",), name="hub")
+    rinj = nd.VertexModel(f=C("rinj_f", "vertex_f", "", py=lambda v, e, p, t: []),
+                          g=C("rinj_g", "vertex_gff", "out[0] = ins[0] / p[0];", py=lambda v, ins, p, t: [ins[0] / p[0]]),
+                          dim=0, pdim=1, outdim=1, name="R_injector")
+    linj = nd.VertexModel(f=C("linj_f", "vertex_f", "dv[0] = esum[0] / p[0];", py=lambda v, e, p, t: [e[0] / p[0]]),
+                          g=nd.StateMask((1,)), dim=1, pdim=1, sym=("i",), name="L_injector")
+    vsrc = nd.VertexModel(f=C("vs_f", "vertex_f", "", py=lambda v, e, p, t: []),
+                          g=C("vs_g", "vertex_g", "out[0] = p[0];", py=lambda v, p, t: [p[0]]), dim=0, pdim=1, outdim=1, name="vs")
+    res = L.diffusion_edge()                                  # i_dst = (1/R) (v_src - v_dst), i_src = -i_dst
+    g = nd.SimpleDiGraph(4, [2, 3, 4], [1, 1, 1])             # R_injector -> hub, L_injector -> hub, vs -> hub
+    vms, ems = [hub, rinj, linj, vsrc], [L.loopback(), L.loopback(), res]
+    for mode in ("fused", "jag"):
+        monkeypatch.setenv("ND_B200_KERNEL", mode)
+        nw = nd.Network(g, vms, ems)
+        assert nw.dim() == 2 and nw.pdim() == 5
+        # layout: u = [v_hub, i_L]; p = [C, R, Lind, V, 1/R_edge]
+        v, iL = 0.3, -0.2
+        Cc, R, Lind, V, ginv = 2.0, 100.0, 0.1, 1.0, 0.5
+        u = np.zeros(2); p = np.zeros(5)
+        for b in nw.vertexbatches:
+            nm = b.model.name
+            if nm == "hub": u[b.state_first - 1] = v; p[b.p_first - 1] = Cc
+            if nm == "L_injector": u[b.state_first - 1] = iL; p[b.p_first - 1] = Lind
+            if nm == "R_injector": p[b.p_first - 1] = R
+            if nm == "vs": p[b.p_first - 1] = V
+        eb = [b for b in nw.layer.edgebatches if b.model.pdim][0]
+        p[eb.p_first - 1] = ginv
+        du = B.nan(2)
+        nw(du, B.dev(u), B.dev(p), 0.0)
+        du = B.host(du)
+        hub_b = [b for b in nw.vertexbatches if b.model.name == "hub"][0]
+        l_b = [b for b in nw.vertexbatches if b.model.name == "L_injector"][0]
+        want_hub = (ginv * (V - v) + -1.0 * (v / R) + -1.0 * iL) / Cc
+        assert abs(du[hub_b.state_first - 1] - want_hub) <= 1e-15 and du[l_b.state_first - 1] == v / Lind, mode
+        # twin (same batching / layout), get_buffers and RK4
+        from helpers import model_types
+        um, vt = model_types(vms, g.nv)
+        uem, et = model_types(ems, g.ne)
+
+        def vspec(m):
+            if m.custom_spec() is not None:
+                return O.VSpec(ONP.PyKind(f=m.f.py, g=(m.g.py if isinstance(m.g, C) else None)), m.dim, m.pdim, m.outdim, 0, m.hasff)
+            return O.VSpec(m.kernel_kind(), m.dim, m.pdim, m.outdim)
+        im = ONP.IndexManager(g.nv, g.src, g.dst, [vspec(m) for m in um], list(vt),
+                              [O.ESpec(m.kernel_kind(), m.coupling, m.dim, m.pdim, m.outdim_src, m.outdim_dst) for m in uem], list(et))
+        ref_du, ref_o, ref_agg = ONP.rhs(im, u, p, 0.0)
+        assert floored_rel_err(du, ref_du) <= 1e-14
+        o, agg = B.nan(nw.im.lastidx_out), B.nan(nw.im.lastidx_aggr)
+        nw.get_buffers(o, agg, B.dev(u), B.dev(p), 0.0)
+        assert floored_rel_err(B.host(o), ref_o) <= 1e-14 and floored_rel_err(B.host(agg), ref_agg) <= 1e-14
+        dt, x = 1e-3, u.copy()
+        for s in range(20):
+            k1 = ONP.rhs(im, x, p)[0]
+            k2 = ONP.rhs(im, x + 0.5 * dt * k1, p)[0]
+            k3 = ONP.rhs(im, x + 0.5 * dt * k2, p)[0]
+            k4 = ONP.rhs(im, x + dt * k3, p)[0]
+            x = x + (dt / 6.0) * (((k1 + 2.0 * k2) + 2.0 * k3) + k4)
+        ud = B.dev(u)
+        nw.rk4(ud, B.dev(p), 0.0, dt, 20)
+        assert floored_rel_err(B.host(ud), x) <= 1e-12, mode
+        # registry-only: a ring of Kuramoto hubs, each with an inertial injector leaf behind a loopback edge (C oracle)
+        n = 40
+        ring_s, ring_d = np.arange(1, n + 1), np.roll(np.arange(1, n + 1), -1)
+        gs = np.concatenate([ring_s, np.arange(n + 1, 2 * n + 1)])
+        gd = np.concatenate([ring_d, np.arange(1, n + 1)])
+        g2 = nd.SimpleDiGraph(2 * n, gs, gd)
+        vm2 = [L.kuramoto_first()] * n + [L.kuramoto_second()] * n
+        is_loop = g2.src > n
+        em2 = ([L.kuramoto_edge(), L.loopback()], is_loop.astype(np.int64))
+        nw2 = nd.Network(g2, vm2, em2)
+        from helpers import condition_params, oracle_network
+        onw = oracle_network(g2, vm2, em2)
+        u2 = np.random.default_rng(2).random(nw2.dim())
+        p2 = 0.5 + condition_params(nw2, np.random.default_rng(3).random(nw2.pdim()))
+        d2 = B.nan(nw2.dim())
+        nw2(d2, B.dev(u2), B.dev(p2), 0.0)
+        assert floored_rel_err(B.host(d2), onw.rhs(u2, p2)) <= 1e-12, mode
+        ud = B.dev(u2)
+        nw2.rk4(ud, B.dev(p2), 0.0, 1e-3, 17)
+        assert floored_rel_err(B.host(ud), onw.rk4(u2, p2, 0.0, 1e-3, 17)) <= 1e-11, mode
+    # the reference's topology rules (src/construction.jl:52-80)
+    with pytest.raises(nd.ArgumentError, match="leaf"):      # loopback from a non-leaf
+        nd.Network(nd.SimpleDiGraph(3, [1, 1, 2], [2, 3, 3]), [hub, hub, hub], [L.loopback(), res, res])
+    with pytest.raises(nd.ArgumentError, match="[Ff]eed.forward"):   # feed-forward vertex without a loopback edge
+        nd.Network(nd.SimpleDiGraph(2, [2], [1]), [hub, rinj], [res])
