@@ -71,6 +71,17 @@ def test_fuzz_registry_networks_on_the_emulator(nd, monkeypatch, seed):
     g = _random_graph(nd, rng)
     vm, em = _random_models(nd, rng, g)
     env, thr = _random_switches(rng)
+    if g.directed and rng.integers(0, 3) == 0:
+        # LoopbackConnections: a few injector leaves (new vertices, any registry vertex kind) behind loopback edges to
+        # random hubs; the new edges sort behind the old ones (their src ids are the largest)
+        L = nd.Lib
+        k = int(rng.integers(1, 6))
+        hubs = rng.integers(1, g.nv + 1, k)
+        vlist, vtypes = (list(vm[0]), np.asarray(vm[1])) if isinstance(vm, tuple) else ([vm], np.zeros(g.nv, dtype=np.int64))
+        elist, etypes = (list(em[0]), np.asarray(em[1])) if isinstance(em, tuple) else ([em], np.zeros(g.ne, dtype=np.int64))
+        vm = (vlist, np.concatenate([vtypes, rng.integers(0, len(vlist), k)]))
+        em = (elist + [L.loopback()], np.concatenate([etypes, np.full(k, len(elist))]))
+        g = nd.SimpleDiGraph(g.nv + k, np.concatenate([g.src, g.nv + 1 + np.arange(k)]), np.concatenate([g.dst, hubs]))
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     with cusim.use():
@@ -116,7 +127,8 @@ def test_fuzz_registry_networks_on_the_emulator(nd, monkeypatch, seed):
         # row-partitioned engines without a halo layout (the all-gather exchange path): every rank evaluates its own row
         # range from a complete state vector; the ranges tile du
         has_states = any(getattr(m, "dim", 0) > 0 for m in (em[0] if isinstance(em, tuple) else [em]))
-        if not has_states and g.nv >= 2:
+        has_loopback = any(m.name == "loopback" for m in (em[0] if isinstance(em, tuple) else [em]))
+        if not has_states and not has_loopback and g.nv >= 2:
             cuts = sorted(set([0, g.nv] + [int(c) for c in rng.integers(0, g.nv + 1, int(rng.integers(1, 4)))]))
             out = np.full(nw.dim(), np.nan)
             for a, b in zip(cuts[:-1], cuts[1:]):
