@@ -224,3 +224,38 @@ def test_edges_with_states_known_answers(nd):
     e2 = e + 0.25
     du = onw.rhs(np.concatenate([x, e2]), None)
     assert np.allclose(du[g.nv:], e - e2, rtol=0, atol=1e-15)
+
+
+def test_loopback_known_answers(nd):
+    """LoopbackConnection (src/post_utils.jl:105-234, src/coreloop.jl:47): after the RHS the aggregation slot of an injector
+    leaf holds its hub's output (apply_loopback!), the hub's slot holds the sum of its ordinary edges plus MINUS the injector's
+    output (LOOPBACK_G: outdst = -1 .* insrc), and the loopback edge has no src output.  C oracle == Python twin."""
+    L = nd.Lib
+    n = 6
+    ring_s, ring_d = np.arange(1, n + 1), np.roll(np.arange(1, n + 1), -1)
+    g = nd.SimpleDiGraph(2 * n, np.concatenate([ring_s, np.arange(n + 1, 2 * n + 1)]), np.concatenate([ring_d, np.arange(1, n + 1)]))
+    vm = [L.kuramoto_first()] * n + [L.kuramoto_second()] * n
+    em = ([L.kuramoto_edge(), L.loopback()], (g.src > n).astype(np.int64))
+    onw = oracle_network(g, vm, em)
+    rng = np.random.default_rng(4)
+    u, p = rng.random(onw.lastidx_dynamic), 0.5 + rng.random(onw.lastidx_p)
+    du, o, agg = onw.rhs(u, p, return_bufs=True)
+    assert onw.lastidx_out == 2 * n + 2 * n + n                   # vertex outputs, ring edges (src+dst), loopback edges (dst only)
+    v_out, v_aggr = onw.table("v_out"), onw.table("v_aggr")
+    e_dst_out = onw.table("e_out_dst")
+    for k in range(n):
+        hub, inj = k + 1, n + k + 1
+        assert agg[v_aggr[inj - 1] - 1] == o[v_out[hub - 1] - 1] == u[k]            # injector input = hub output = theta_hub
+        loop_edge = int(np.nonzero((g.src == inj) & (g.dst == hub))[0][0])
+        assert o[e_dst_out[loop_edge] - 1] == -1.0 * o[v_out[inj - 1] - 1]           # hub receives minus the injector's output
+    from helpers import model_types
+    um, vt = model_types(vm, g.nv)
+    uem, et = model_types(em, g.ne)
+    im = _np_im(g, um, vt, uem, et)
+    du2, o2, agg2 = ONP.rhs(im, u, p)
+    assert np.array_equal(du, du2) and np.array_equal(o, o2, equal_nan=True) and np.array_equal(agg, agg2)
+    assert np.array_equal(onw.rhs(u, p, threads=3), du)
+    # the inertial injector: dv2 = 1/M (Pm - D v2 + theta_hub)
+    inj_states = onw.table("v_data")[n] - 1
+    M, D, Pm = p[onw.table("v_para")[n] - 1: onw.table("v_para")[n] + 2]
+    assert du[inj_states + 1] == 1.0 / M * (Pm - D * u[inj_states + 1] + u[0])
