@@ -76,15 +76,3 @@ def test_two_gpu_partitioned_rhs(nd, cuda, tmp_path, exchange, kernel):
     p = condition_params(nw, np.random.default_rng(2).random(nw.pdim()))
     assert floored_rel_err(np.load(tmp_path / "du.npy"), onw.rhs(u0, p)) <= 1e-12
     assert floored_rel_err(np.load(tmp_path / "u.npy"), onw.rk4(u0, p, 0.0, 1e-3, 5)) <= 1e-12
-
-
-@pytest.mark.parametrize("kernel", ["fused", "jag"])
-def test_zz_two_gpu_fused_rk4(nd, cuda, tmp_path, kernel):
-    """nd_b200_rk4_exchange (written after the round's last GPU run; green on emulated ranks, tests/test_cusim_multirank.py):
-    five fused RK4 steps equal five host-driven ones on both GPUs"""
-    torch = cuda
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
-    import torch.multiprocessing as mp
-    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
-    mp.spawn(_worker, args=(2, port, str(tmp_path), "p2p", kernel, True), nprocs=2, join=True)

@@ -151,3 +151,18 @@ def test_packed_edge_parameters(nd, backend, monkeypatch, mode):
         nw.pack_params(B.dev(np.ones(nw.pdim())))
     with pytest.raises(nd.ArgumentError):
         nd.Network(g, L.diffusion_vertex(), L.diffusion_edge_nop()).pack_params(B.dev(np.ones(1)))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kernel", ["fused", "jag"])
+def test_two_gpu_fused_rk4(nd, cuda, tmp_path, kernel):
+    """nd_b200_rk4_exchange (written after the round's last GPU run; green on emulated ranks, tests/test_cusim_multirank.py):
+    five fused RK4 steps equal five host-driven ones on both GPUs"""
+    torch = cuda
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    from test_gpu_multi import _worker
+    mp.spawn(_worker, args=(2, port, str(tmp_path), "p2p", kernel, True), nprocs=2, join=True)
