@@ -285,16 +285,21 @@ def test_fuzz_user_supplied_kinds(nd, monkeypatch, seed):
 
     def vertex(k):
         dim, pdim = int(rng.integers(vdepth, 6)), int(rng.integers(0, 4))
-        ops = [f"v[{i}]" for i in range(dim)] + [f"esum[{i}]" for i in range(edepth)] + [f"p[{i}]" for i in range(pdim)] + ["t"]
+        # external inputs (src/external_inputs.jl): the first state / the first output of random vertices
+        extin = tuple(nd.VIndex(int(rng.integers(1, g.nv + 1)), [1, ("out", 1)][int(rng.integers(0, 2))])
+                      for _ in range(int(rng.integers(0, 3)) if rng.integers(0, 2) else 0))
+        ops = [f"v[{i}]" for i in range(dim)] + [f"esum[{i}]" for i in range(edepth)] + [f"p[{i}]" for i in range(pdim)] + ["t"] + \
+              [f"ext[{i}]" for i in range(len(extin))]
         fo = [_expr(rng, ops) for _ in range(dim)]
-        f = C(f"vf{k}", "vertex_f", " ".join(f"dv[{i}] = {e};" for i, e in enumerate(fo)), py=_pyfun("v, esum, p, t", fo))
+        f = C(f"vf{k}", "vertex_f", " ".join(f"dv[{i}] = {e};" for i, e in enumerate(fo)),
+              py=_pyfun("v, esum, ext, p, t" if extin else "v, esum, p, t", fo))
         if rng.integers(0, 2):
             gops = [f"v[{i}]" for i in range(dim)] + [f"p[{i}]" for i in range(pdim)]
             go = [_expr(rng, gops) for _ in range(vdepth)]
             gfun = C(f"vg{k}", "vertex_g", " ".join(f"out[{i}] = {e};" for i, e in enumerate(go)), py=_pyfun("v, p, t", go))
         else:
             gfun = nd.StateMask(tuple(range(1, vdepth + 1)))
-        return nd.VertexModel(f=f, g=gfun, dim=dim, pdim=pdim, outdim=vdepth, name=f"v{k}")
+        return nd.VertexModel(f=f, g=gfun, dim=dim, pdim=pdim, outdim=vdepth, name=f"v{k}", extin=extin)
 
     def edge(k):
         pdim = int(rng.integers(0, 4))
@@ -334,7 +339,7 @@ def test_fuzz_user_supplied_kinds(nd, monkeypatch, seed):
             inner = m.g.g
             return ONP.PyKind(g=inner.py)
         return ONP.PyKind(f=m.f.py, g=(m.g.py if isinstance(m.g, C) else None))
-    vs = [O.VSpec(kind(m), m.dim, m.pdim, m.outdim) for m in vms]
+    vs = [O.VSpec(kind(m), m.dim, m.pdim, m.outdim, m.extdim) for m in vms]
     es = [O.ESpec(kind(m), m.coupling, m.dim, m.pdim, m.outdim_src, m.outdim_dst, *(m.state_masks() or (0, 0))) for m in ems]
     im = ONP.IndexManager(g.nv, g.src, g.dst, vs, list(vt), es, list(et))
     with cusim.use():
@@ -342,8 +347,13 @@ def test_fuzz_user_supplied_kinds(nd, monkeypatch, seed):
         assert (nw.dim(), nw.pdim()) == (im.last["dynamic"], im.last["p"])
         u, p = rng.uniform(-1, 1, nw.dim()), rng.uniform(0.2, 1.2, nw.pdim())
         pd = cusim.dev(p) if p.size else None
+        from networkdynamics_jl_b200.network import resolve_extin
+        extmap = [0] * im.last["ext"]
+        for i in range(1, g.nv + 1):
+            for k, ref in enumerate(vms[vt[i - 1]].extin):
+                extmap[im.v_ext[i].first - 1 + k] = resolve_extin(nw.im, ref)
         for t in (0.0, 0.4):
-            ref, o_ref, agg_ref = ONP.rhs(im, u, p, t)
+            ref, o_ref, agg_ref = ONP.rhs(im, u, p, t, extmap)
             du = cusim.empty(nw.dim())
             nw(du, cusim.dev(u), pd, t)
             assert floored_rel_err(du.numpy(), ref) <= 1e-12, (seed, t)
