@@ -12,8 +12,9 @@ module NetworkDynamicsB200
 
 using NetworkDynamics
 using NetworkDynamics: ExecutionStyle, Aggregator, IndexManager, ComponentBatch, Network,
-                       AntiSymmetric, Symmetric, Directed, StateMask, _find_identical_components,
+                       AntiSymmetric, Symmetric, Directed, Fiducial, StateMask, _find_identical_components,
                        compf, compg, dim, pdim, outdim
+import CUDA
 using CUDA: CuArray, CuPtr, stream
 import NetworkDynamics: aggregate!, get_aggr_constructor, iscudacompatible, aggfun
 
@@ -145,9 +146,9 @@ function B200Aggregator(im::IndexManager, edgebatches, f)
             fsrc = isnothing(compf(m)) ? "" : cuda_source(compf(m))
             kind = custom_kind!(0, dim(m), pdim(m), outdim(m), 0, fsrc, gs, NetworkDynamics.extdim(m), gff)
         end
+        isnothing(kind) && throw(ArgumentError("vertex model $(m.name) has neither a registry kernel nor a cuda_source (no CPU fallback)"))
         xd = NetworkDynamics.extdim(m)
         (xd > 0 && kind < CUSTOM_KIND_BASE) && throw(ArgumentError("B200 engine: external inputs need a cuda_source vertex function (no CPU fallback)"))
-        isnothing(kind) && throw(ArgumentError("vertex model $(m.name) has neither a registry kernel nor a cuda_source (no CPU fallback)"))
         ix = Vector{Int64}(idxs); push!(keep, ix)
         i1 = first(idxs)
         CVBatch(kind, dim(m), pdim(m), outdim(m), length(ix), pointer(ix),
