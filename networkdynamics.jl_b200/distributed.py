@@ -40,11 +40,25 @@ def row_entry_counts(im: IndexManager, edgebatches: Sequence[ComponentBatch]) ->
     rov = row_of_vertex(im)
     cnt = np.zeros(im.nv, dtype=np.int64)
     for b in edgebatches:
-        e = slice(None) if b.indices is None else b.indices - 1
-        cnt += np.bincount(rov[im.edge_dst[e] - 1], minlength=im.nv)
-        if b.model.outdim_src > 0:
-            cnt += np.bincount(rov[im.edge_src[e] - 1], minlength=im.nv)
+        for e in _edge_chunks(b, im.ne):
+            cnt += np.bincount(rov[im.edge_dst[e] - 1], minlength=im.nv)
+            if b.model.outdim_src > 0:
+                cnt += np.bincount(rov[im.edge_src[e] - 1], minlength=im.nv)
     return cnt
+
+
+_CHUNK = 1 << 25      # edges per pass: bounds the temporaries of the planning functions at config-5 scale (4e8 edges)
+
+
+def _edge_chunks(b: ComponentBatch, ne: int):
+    """index objects (slices, or pieces of the batch's index array, 0-based) covering the edges of a batch"""
+    if b.indices is None:
+        for a in range(0, ne, _CHUNK):
+            yield slice(a, min(a + _CHUNK, ne))
+    else:
+        idx = np.asarray(b.indices, dtype=np.int64) - 1
+        for a in range(0, idx.size, _CHUNK):
+            yield idx[a:a + _CHUNK]
 
 
 def partition_rows(entry_counts: np.ndarray, world: int, prefer_equal_rows: float = 0.05) -> List[Tuple[int, int]]:
@@ -105,11 +119,11 @@ def halo_plan(im: IndexManager, edgebatches: Sequence[ComponentBatch], row_range
         goff = np.asarray(im.v_data, dtype=np.int64) - 1
     needed = np.zeros((world, nv), dtype=bool)
     for b in edgebatches:
-        e = slice(None) if b.indices is None else np.asarray(b.indices, dtype=np.int64) - 1
-        s, t = np.asarray(im.edge_src)[e] - 1, np.asarray(im.edge_dst)[e] - 1
-        needed[vowner[t], s] = True                   # the dst row reads the src vertex's output
-        if b.model.outdim_src > 0:
-            needed[vowner[s], t] = True               # ... and the src row (wrapper output) reads the dst vertex's
+        for e in _edge_chunks(b, int(np.asarray(im.edge_src).size)):
+            s, t = np.asarray(im.edge_src)[e] - 1, np.asarray(im.edge_dst)[e] - 1
+            needed[vowner[t], s] = True               # the dst row reads the src vertex's output
+            if b.model.outdim_src > 0:
+                needed[vowner[s], t] = True           # ... and the src row (wrapper output) reads the dst vertex's
     needed[vowner, np.arange(nv)] = False             # own vertices are read from u
     vorder = np.lexsort((goff, vowner))
     need = [vorder[needed[r][vorder]] for r in range(world)]

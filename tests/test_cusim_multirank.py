@@ -240,3 +240,23 @@ def test_partition_from_the_bare_edge_list(nd, monkeypatch):
         for g, vm, em in cases[:2]:
             out, ref, _p, _s, _k = _run_world(nd, g, vm, em, 3, ncalls=4, edgelist=True)
             assert np.max(np.abs(out - ref)) <= 1e-13 * np.max(np.abs(ref))
+
+
+def test_planning_in_chunks(nd, monkeypatch):
+    """the partition / halo planning walks the edges in bounded chunks (config-5 scale: 4e8 edges); same plan for any chunk size"""
+    from networkdynamics_jl_b200 import distributed as D
+    L = nd.Lib
+    g = nd.barabasi_albert(3000, 4, seed=7)
+    em = ([L.kuramoto_edge(), nd.EdgeModel(g=nd.Directed(L.kuramoto_edge_f), outdim=1, pdim=1, name="dir_kura")], np.random.default_rng(1).integers(0, 2, g.ne))
+    probes = [nd.Network(g, L.kuramoto_first(), em, aggregator=null_aggregator), nd.Network.from_edgelist(g, L.kuramoto_first(), L.kuramoto_edge(), layout_only=True)]
+    for probe in probes:
+        ref_cnt = D.row_entry_counts(probe.im, probe.layer.edgebatches)
+        rr = D.partition_rows(ref_cnt, 4)
+        ref = [D.halo_plan(probe.im, probe.layer.edgebatches, rr, r) for r in range(4)]
+        monkeypatch.setattr(D, "_CHUNK", 777)
+        assert np.array_equal(D.row_entry_counts(probe.im, probe.layer.edgebatches), ref_cnt)
+        for r in range(4):
+            pl = D.halo_plan(probe.im, probe.layer.edgebatches, rr, r)
+            assert np.array_equal(pl["gather_offset"], ref[r]["gather_offset"]) and pl["halo_lens"] == ref[r]["halo_lens"]
+            assert all(np.array_equal(pl["sends"][q][0], ref[r]["sends"][q][0]) for q in pl["sends"])
+        monkeypatch.undo()
