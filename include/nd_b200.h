@@ -207,6 +207,14 @@ int nd_b200_pack_params(nd_b200_engine*, const double* p, void* stream);
 int nd_b200_get_buffers(nd_b200_engine*, double* o, double* aggbuf, const double* u, const double* p,
                         double t, void* stream);
 
+/* Replaces `aggregate!(aggregator, aggbuf, o)` (src/aggregators.jl:140-151, the SequentialAggregator sweep; call site
+ * src/coreloop.jl:90): adds the edge-output block of a materialised output buffer o (lastidx_out, device) into aggbuf
+ * (lastidx_aggr, device) -- per slot in ascending `o` order, ON TOP of aggbuf's present content, which is what
+ * test/aggregators_test.jl:69-79 requires of every Aggregator.  The RHS itself never materialises o (the sums live in
+ * registers); this entry point exists so that the Aggregator plug-in is complete on its own.  Full (unpartitioned)
+ * engines created without ND_B200_FLAG_NO_EXPORT. */
+int nd_b200_aggregate(nd_b200_engine*, double* aggbuf, const double* o, void* stream);
+
 /* Classical fixed-step RK4 on device-resident u (in place), stage updates fused into the RHS
  * kernels, step captured in a CUDA graph.  Replaces `solve(ODEProblem(nw,...), RK4(); dt, adaptive=false)`
  * around src/post_utils.jl:43-100 for the registry models. */

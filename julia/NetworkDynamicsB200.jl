@@ -15,7 +15,7 @@ using NetworkDynamics: ExecutionStyle, Aggregator, IndexManager, ComponentBatch,
                        AntiSymmetric, Symmetric, Directed, Fiducial, StateMask, _find_identical_components,
                        compf, compg, dim, pdim, outdim
 import CUDA
-using CUDA: CuArray, CuPtr, stream
+using CUDA: CuArray, CuVector, CuPtr, stream
 import NetworkDynamics: aggregate!, get_aggr_constructor, iscudacompatible, aggfun
 
 const libnd_b200 = get(ENV, "ND_B200_LIB", "libnd_b200.so")
@@ -105,8 +105,17 @@ function B200Aggregator(f)
     (im, batches) -> B200Aggregator(im, batches, f)
 end
 get_aggr_constructor(a::B200Aggregator) = B200Aggregator(a.f)
-iscudacompatible(::Type{<:B200Aggregator}) = true
-Base.show(io::IO, a::B200Aggregator) = print(io, "B200Aggregator(", a.f, ")")
+
+"""
+`aggregate!(a, aggbuf, o)` (src/aggregators.jl:140-151) on device vectors: adds the edge-output block of `o` into `aggbuf`,
+per slot in ascending `o` order, on top of its content (test/aggregators_test.jl:69-79).  The RHS method below does not
+use it -- the engine's row kernel keeps the sums in registers.
+"""
+function aggregate!(a::B200Aggregator, aggbuf::CuVector{Float64}, o::CuVector{Float64})
+    _check(ccall((:nd_b200_aggregate, libnd_b200), Cint, (Ptr{Cvoid}, CuPtr{Float64}, CuPtr{Float64}, Ptr{Cvoid}),
+                 a.handle, pointer(aggbuf), pointer(o), stream().handle), a.handle)
+    nothing
+end
 
 function _check(rc, handle)
     rc == 0 && return

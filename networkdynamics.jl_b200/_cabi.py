@@ -64,7 +64,7 @@ class Desc(C.Structure):
 
 EXPORTED_SYMBOLS = [
     "nd_b200_create", "nd_b200_destroy", "nd_b200_last_error", "nd_b200_abi_version", "nd_b200_rhs",
-    "nd_b200_rhs_host", "nd_b200_get_buffers", "nd_b200_rk4", "nd_b200_export_sizes", "nd_b200_export_tables",
+    "nd_b200_rhs_host", "nd_b200_get_buffers", "nd_b200_aggregate", "nd_b200_rk4", "nd_b200_export_sizes", "nd_b200_export_tables",
     "nd_b200_launch_count", "nd_b200_set_timing", "nd_b200_timings", "nd_b200_host_alloc", "nd_b200_host_free",
     "nd_b200_comm_create", "nd_b200_comm_export", "nd_b200_comm_open_peer", "nd_b200_comm_set_send", "nd_b200_rhs_local", "nd_b200_custom_source", "nd_b200_create_from_edgelist", "nd_b200_rhs_exchange", "nd_b200_comm_status",
     "nd_b200_comm_last_error", "nd_b200_comm_destroy", "nd_b200_export_jag_sizes", "nd_b200_export_jag", "nd_b200_pack_params", "nd_b200_rk4_exchange",
@@ -157,6 +157,8 @@ def bind(L):
     L.nd_b200_rhs.argtypes = [C.c_void_p, dp, dp, dp, C.c_double, C.c_void_p]
     L.nd_b200_rhs_host.restype = C.c_int
     L.nd_b200_rhs_host.argtypes = [C.c_void_p, dp, dp, dp, C.c_double]
+    L.nd_b200_aggregate.restype = C.c_int
+    L.nd_b200_aggregate.argtypes = [C.c_void_p, dp, dp, C.c_void_p]
     L.nd_b200_get_buffers.restype = C.c_int
     L.nd_b200_get_buffers.argtypes = [C.c_void_p, dp, dp, dp, dp, C.c_double, C.c_void_p]
     L.nd_b200_pack_params.restype = C.c_int

@@ -124,6 +124,11 @@ struct nd_b200_engine {
   // get_buffers support (lazy)
   std::vector<std::vector<int>> h_esrc_off, h_edst_off;   // per edge batch, gather offsets
   std::vector<int*> d_esrc_off, d_edst_off;
+  // nd_b200_aggregate support (lazy): per CSR entry the 0-based index of its output block in `o` (-1: the entry has no
+  // slot in `o` -- the hub -> injector entry of a loopback edge)
+  std::vector<long long> h_aggidx;
+  long long* d_aggidx = nullptr;
+  int* d_aggrow = nullptr;
   // host copies for export
   std::vector<long long> h_rowptr;
   std::vector<int> h_nbr_vid, h_eid;
@@ -902,7 +907,7 @@ struct EngineBuilder {
     if (e->ek == EK_GENERIC && d->vdepth == 1 && !e->custom) any_epar = true;
     if (any_epar) h_epar.assign((size_t)std::max<long long>(e->nentries, 1), 0);
     if (e->ek == EK_GENERIC && (d->vdepth == 1 || e->custom)) h_ebid.assign((size_t)std::max<long long>(e->nentries, 1), 0);
-    if (keep) { e->h_nbr_vid.resize((size_t)e->nentries); e->h_eid.resize((size_t)e->nentries); e->h_side.resize((size_t)e->nentries); }
+    if (keep) { e->h_nbr_vid.resize((size_t)e->nentries); e->h_eid.resize((size_t)e->nentries); e->h_side.resize((size_t)e->nentries); e->h_aggidx.resize((size_t)e->nentries); }
     // split mode tables: per entry its position in the edge part of `o`; per edge (in `o` order) the gather offsets
     generic_edges = (e->ek == EK_GENERIC && (d->vdepth == 1 || e->custom));
     e->oedge_base = d->nv * (long long)d->vdepth;
@@ -940,7 +945,7 @@ struct EngineBuilder {
             h_nbr[(size_t)j] = eb.dim > 0 ? ~so_src : ~goff[(size_t)t - 1];
             if (any_epar) h_epar[(size_t)j] = ep;
             if (!h_ebid.empty()) h_ebid[(size_t)j] = (uint8_t)b;
-            if (keep) { e->h_nbr_vid[(size_t)j] = (int)t; e->h_eid[(size_t)j] = (int)(eid + 1); e->h_side[(size_t)j] = 1; }
+            if (keep) { e->h_nbr_vid[(size_t)j] = (int)t; e->h_eid[(size_t)j] = (int)(eid + 1); e->h_side[(size_t)j] = 1; e->h_aggidx[(size_t)j] = eb.outdim_src > 0 ? oo + e->oedge_base : -1; }
           }
           if (owned(rt)) {
             const long long j = cur[(size_t)(rt - e->row_begin)]++;
@@ -948,7 +953,7 @@ struct EngineBuilder {
             h_nbr[(size_t)j] = eb.dim > 0 ? so_dst : goff[(size_t)s - 1];
             if (any_epar) h_epar[(size_t)j] = ep;
             if (!h_ebid.empty()) h_ebid[(size_t)j] = (uint8_t)b;
-            if (keep) { e->h_nbr_vid[(size_t)j] = (int)s; e->h_eid[(size_t)j] = (int)(eid + 1); e->h_side[(size_t)j] = 0; }
+            if (keep) { e->h_nbr_vid[(size_t)j] = (int)s; e->h_eid[(size_t)j] = (int)(eid + 1); e->h_side[(size_t)j] = 0; e->h_aggidx[(size_t)j] = oo + e->oedge_base + eb.outdim_src; }
           }
         }
       }
@@ -1490,6 +1495,7 @@ void nd_b200_destroy(nd_b200_engine* e) {
   cudaFree(e->d_ppack);
   for (int* q : e->d_esrc_off) cudaFree(q);
   for (int* q : e->d_edst_off) cudaFree(q);
+  cudaFree(e->d_aggrow); cudaFree(e->d_aggidx);
   cudaFree(e->d_tmpA); cudaFree(e->d_tmpB); cudaFree(e->d_ksum);
   cudaFree(e->d_hu); cudaFree(e->d_hp); cudaFree(e->d_hdu);
   if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
@@ -1684,6 +1690,28 @@ int nd_b200_get_buffers(nd_b200_engine* e, double* o, double* aggbuf, const doub
     P.u = u; P.p = p; P.gsrc = gsrc; P.mode = MODE_AGG; P.aggbuf = aggbuf; P.t = t;
     CUDA_TRY(e, launch_fused(e, P, st));
   }
+  return ND_B200_OK;
+}
+
+int nd_b200_aggregate(nd_b200_engine* e, double* aggbuf, const double* o, void* stream) {
+  if (!e) return ND_B200_EINVAL;
+  if (!aggbuf || !o) return fail(e, ND_B200_EINVAL, "aggbuf or o is NULL");
+  if (e->host_only || e->halo_base != INT_MAX || e->row_end - e->row_begin != e->nrows_total)
+    return fail(e, ND_B200_EUNSUPPORTED, "nd_b200_aggregate on a partitioned / host-only engine");
+  if (e->h_rowptr.size() != (size_t)e->nrows_total + 1) return fail(e, ND_B200_EUNSUPPORTED, "engine was created with ND_B200_FLAG_NO_EXPORT");
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  if (!e->d_aggrow) {
+    std::vector<int> rp(e->h_rowptr.begin(), e->h_rowptr.end());
+    std::vector<long long> oi(e->h_aggidx);
+    if (oi.empty()) oi.push_back(-1);
+    if (upload(e, &e->d_aggrow, rp) || upload(e, &e->d_aggidx, oi)) return ND_B200_ECUDA;
+  }
+  const long long n = (long long)e->nrows_total * e->edepth;
+  if (n == 0) return ND_B200_OK;
+  const int T = 256;
+  e->launches++;
+  ND_LAUNCH((unsigned)((n + T - 1) / T), T, (cudaStream_t)stream, (e->d_aggrow, e->d_aggidx, e->edepth, (long long)e->nrows_total, o, aggbuf), aggregate_kernel);
+  CUDA_TRY(e, cudaGetLastError());
   return ND_B200_OK;
 }
 

@@ -733,6 +733,23 @@ __global__ void pack_params_kernel(const int* __restrict__ offs, int stride, int
   for (int k = 0; k < pe; ++k) ppack[j * pe + k] = p[o + k];
 }
 
+// Standalone aggregate!(aggregator, aggbuf, o) (src/aggregators.jl:140-151): every aggregation slot adds its entries of the
+// edge-output block of `o` in ascending `o` order, starting from the slot's present content (additive, test/
+// aggregators_test.jl:69-79).  One thread per (row, component): the left-to-right order of the sequential sweep.
+__global__ void aggregate_kernel(const int* __restrict__ rowptr, const long long* __restrict__ oidx, int ed, long long nrows,
+                                 const double* __restrict__ o, double* __restrict__ aggbuf) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nrows * ed) return;
+  const long long row = i / ed;
+  const int q = (int)(i - row * ed);
+  double acc = aggbuf[i];
+  for (int j = rowptr[row]; j < rowptr[row + 1]; ++j) {
+    const long long oi = oidx[j];
+    if (oi >= 0) acc = acc + o[oi + q];
+  }
+  aggbuf[i] = acc;
+}
+
 __global__ void extract_nbr_kernel(const int* __restrict__ pairs, long long n, int* __restrict__ nbr) {
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (j < n) nbr[j] = pairs[2 * j];

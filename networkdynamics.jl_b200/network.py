@@ -321,6 +321,21 @@ class B200Aggregator:
             raise (ArgumentError if rc in (_cabi.EINVAL, _cabi.EUNSUPPORTED) else RuntimeError)(msg)
         self.handle = h
         self.device = int(dev)
+        self._sizes = (im.lastidx_out, im.lastidx_aggr)
+
+    def aggregate(self, aggbuf, o, *, stream=None):
+        """`aggregate!(aggregator, aggbuf, o)` (src/aggregators.jl:140-151): add the edge-output block of the device
+        vector `o` into the device vector `aggbuf`, per slot in ascending `o` order, on top of its present content."""
+        a_a, dev_a, n_a = _addr(aggbuf)
+        a_o, dev_o, n_o = _addr(o)
+        if not (dev_a and dev_o):
+            raise ArgumentError("aggregate needs device-resident aggbuf and o")
+        if (n_a, n_o) != (self._sizes[1], self._sizes[0]):
+            raise ArgumentError(f"aggregate: aggbuf / o have {n_a} / {n_o} entries, expected {self._sizes[1]} / {self._sizes[0]}")
+        rc = self._L.nd_b200_aggregate(self.handle, a_a, a_o, _stream_handle(stream))
+        if rc:
+            msg = self._L.nd_b200_last_error(self.handle).decode()
+            raise (ArgumentError if rc in (_cabi.EINVAL, _cabi.EUNSUPPORTED) else RuntimeError)(msg)
 
     def __del__(self):
         h, self.handle = getattr(self, "handle", None), None
@@ -465,6 +480,7 @@ class Network:
                 raise (ArgumentError if rc in (_cabi.EINVAL, _cabi.EUNSUPPORTED) else RuntimeError)(msg)
             agg = B200Aggregator("+", device=dev, row_range=row_range, keep_tables=keep_tables, host_only=host_only)
             agg.handle, agg.device, agg._L = h, int(dev), L
+            agg._sizes = (self.im.lastidx_out, self.im.lastidx_aggr)
         # the one vertex batch / edge batch of the layout (what register_vertices! / register_edges! would return), without
         # per-component index arrays: indices=None stands for 1:n
         self.vertexbatches = [ComponentBatch("vertex", vertexm, None, 1, 1, 1, 1)]
