@@ -104,6 +104,16 @@ def test_fuzz_registry_networks_on_the_emulator(nd, monkeypatch, seed):
         nw.get_buffers(o, agg, cusim.dev(u), pd, 0.0)
         assert floored_rel_err(agg.numpy(), agg_ref) <= 1e-12, (seed, env, thr)
         assert floored_rel_err(o.numpy(), o_ref) <= 1e-12 and np.array_equal(np.isnan(o.numpy()), np.isnan(o_ref)), (seed, env)
+        # the aggregator's own aggregate!(a, aggbuf, o): the sequential sweep over the oracle's AggregationMap, added to
+        # what aggbuf holds -- one thread per slot, same order, bit-identical
+        o_r, a_r = rng.standard_normal(nw.im.lastidx_out), rng.standard_normal(nw.im.lastidx_aggr)
+        amap, first = onw.table("aggmap"), onw.aggmap_first
+        want = a_r.copy()
+        for k in np.nonzero(amap > 0)[0]:
+            want[amap[k] - 1] = want[amap[k] - 1] + o_r[first - 1 + k]
+        a_d = cusim.dev(a_r)
+        nw.layer.aggregator.aggregate(a_d, cusim.dev(o_r))
+        assert np.array_equal(a_d.numpy(), want), (seed, env)
         ud = cusim.dev(u)
         nw.rk4(ud, pd, 0.0, 1e-3, 3)
         assert floored_rel_err(ud.numpy(), onw.rk4(u, p, 0.0, 1e-3, 3)) <= 1e-11, (seed, env, thr)
