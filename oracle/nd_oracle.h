@@ -16,7 +16,14 @@
  *   - find_identical batching order             (test/utils_test.jl:43-61)
  *   - flat state/parameter layout pins          (test/symbolicindexing_test.jl:27-62,98-111)
  *   - the hand-worked 3-vertex layout           
- * The last-bit behaviour of Julia's Base.sin/cos is NOT pinned (libm used here).
+ *   - edges with states on their constraint     (test/diffusion_test.jl:96-129)
+ *   - loopback identities                       (src/post_utils.jl:105-234)
+ * The reference ships no stored golden vectors and could not be run to make any.
+ * PARITY UNPINNED for two things: the last-bit behaviour of Julia's Base.sin/cos
+ * (libm is used here) and the operation order of the fixed-step RK4 (the
+ * reference's stepper is OrdinaryDiffEq's, an external package; classical RK4 is
+ * restated).  Both sit inside the stated tolerances (1e-12 per RHS, 1e-9 per
+ * 1000-step trajectory).
  *
  * All indices in the emitted tables are 1-based int64, exactly as the
  * reference's IndexManager holds them.
