@@ -424,12 +424,19 @@ cudaError_t launch_edge_f(nd_b200_engine* e, const KParams& P, cudaStream_t st) 
     const HostEB& h = e->heb[(size_t)ob.b];
     EFParams Q;
     memset(&Q, 0, sizeof Q);
-    Q.kind = h.kind; Q.dim = h.dim; Q.pdim = h.pdim; Q.count = h.count; Q.state0 = h.state0; Q.p0 = h.p0;
-    Q.esrc_off = ob.d_es; Q.edst_off = ob.d_et; Q.ext = ob.d_ext; Q.extdim = ob.extdim;
+    // row-partitioned engines (all-gather exchange): every stateful batch is cut in the proportion of the owned row range --
+    // contiguous chunks that tile the batch when the ranks' row ranges tile the rows (distributed.py: edge_state_segments)
+    long long i0 = 0, i1 = h.count;
+    if (e->row_end - e->row_begin != e->nrows_total) {
+      i0 = h.count * (long long)e->row_begin / std::max<long long>(e->nrows_total, 1);
+      i1 = h.count * (long long)e->row_end / std::max<long long>(e->nrows_total, 1);
+    }
+    Q.kind = h.kind; Q.dim = h.dim; Q.pdim = h.pdim; Q.count = i1 - i0; Q.state0 = h.state0 + i0 * h.dim; Q.p0 = h.p0 + i0 * h.pdim;
+    Q.esrc_off = ob.d_es + i0; Q.edst_off = ob.d_et + i0; Q.ext = ob.d_ext ? ob.d_ext + i0 * ob.extdim : nullptr; Q.extdim = ob.extdim;
     Q.u = P.u; Q.gsrc = P.gsrc; Q.p = P.p; Q.du = P.du; Q.mode = P.mode; Q.stage = P.stage; Q.u0 = P.u0; Q.unext = P.unext;
     Q.ksum = P.ksum; Q.hs = P.hs; Q.h6 = P.h6; Q.t = P.t;
     const int T = 256;
-    const int nb = (int)((h.count + T - 1) / T);
+    const int nb = (int)((Q.count + T - 1) / T);
     if (nb == 0) continue;
     e->launches++;
     if (e->custom) {
@@ -732,7 +739,6 @@ struct EngineBuilder {
       if (eb.dim < 0 || eb.dim > (e->custom ? 16 : 2)) return fail(e, ND_B200_EUNSUPPORTED, "edge batch %d: dim %d", b + 1, eb.dim);
       if (eb.dim > 0) {
         // edges with states: outputs are StateMasks over a contiguous range of the edge's own states
-        if (d->row_end > 0 && (d->row_begin != 0 || d->row_end != e->nrows_total)) return fail(e, ND_B200_EUNSUPPORTED, "edges with states on a row-partitioned engine");
         if (d->gather_offset) return fail(e, ND_B200_EUNSUPPORTED, "edges with states on a halo engine");
         if (eb.state_first != state_expect) return fail(e, ND_B200_EINVAL, "edge batch %d: statestride.first %lld, expected %lld", b + 1, (long long)eb.state_first, state_expect);
         if (eb.mask_dst_first < 1 || eb.mask_dst_first + eb.outdim_dst - 1 > eb.dim) return fail(e, ND_B200_EINVAL, "edge batch %d: dst StateMask outside 1..dim", b + 1);

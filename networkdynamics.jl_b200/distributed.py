@@ -95,6 +95,22 @@ def state_segments(vertexbatches: Sequence[ComponentBatch], r0: int, r1: int) ->
     return segs
 
 
+def edge_state_segments(edgebatches: Sequence[ComponentBatch], r0: int, r1: int, nrows: int) -> List[Tuple[int, int]]:
+    """0-based [start, stop) ranges of the states of edges WITH states whose `f` the owner of rows [r0, r1) evaluates: every
+    such batch is cut in the proportion of the row range (launch_edge_f in csrc/nd_b200.cu uses the same floor divisions), so
+    the ranks' chunks are contiguous and tile the batch.  Their outputs are read by other ranks' rows from the all-gathered
+    state vector like any vertex state."""
+    segs = []
+    for b in edgebatches:
+        dim, n = b.model.dim, len(b)
+        if dim > 0 and n > 0:
+            i0, i1 = n * int(r0) // max(int(nrows), 1), n * int(r1) // max(int(nrows), 1)
+            if i0 < i1:
+                first = b.state_first - 1
+                segs.append((first + i0 * dim, first + i1 * dim))
+    return segs
+
+
 def owner_of_rows(rows: np.ndarray, row_ranges: Sequence[Tuple[int, int]]) -> np.ndarray:
     """rank that owns each row (row ranges are contiguous and ascending)"""
     ends = np.array([b for _, b in row_ranges], dtype=np.int64)
@@ -202,7 +218,10 @@ class PartitionedNetwork:
         self.rank, self.world, self.group = rank, world, group
         self.entry_counts = row_entry_counts(probe.im, probe.layer.edgebatches)
         self.row_ranges = partition_rows(self.entry_counts, world)
-        self.segments = [state_segments(probe.vertexbatches, a, b) for a, b in self.row_ranges]
+        nrows = int(self.entry_counts.size)
+        self.segments = [state_segments(probe.vertexbatches, a, b) + edge_state_segments(probe.layer.edgebatches, a, b, nrows)
+                         for a, b in self.row_ranges]
+        stateful_edges = any(b.model.dim > 0 for b in probe.layer.edgebatches)
         self.comm = None
         self.exchange_kind = "nccl"
         self.plan = None
@@ -219,6 +238,10 @@ class PartitionedNetwork:
                                                      gather_len=0 if plan is None else plan["gather_len"]))
 
         want_p2p = exchange in ("p2p", "auto") and world > 1
+        if want_p2p and stateful_edges:         # their states travel with the all-gather; the packed halo carries vertex outputs only
+            if exchange == "p2p":
+                raise RuntimeError("p2p exchange does not carry the states of edges with states: use exchange='nccl'")
+            want_p2p = False
         if want_p2p and not statemask_outputs(probe.vertexbatches, probe.im.vdepth):
             if exchange == "p2p":
                 raise RuntimeError("p2p exchange needs StateMask vertices (the gather source must be the state vector)")

@@ -223,6 +223,41 @@ def _worker_partitioned_class(rank, world, port, out_dir):
             assert np.max(np.abs(u.numpy() - onw.rk4(u0, p, 0.0, 1e-3, 3))) <= 1e-14
             assert not pn.comm_timed_out()
             pn.close()
+        # edges WITH states: every rank evaluates f for a contiguous chunk of each stateful batch; the chunks' states travel
+        # with the all-gather like vertex states (the packed NVLink halo carries vertex outputs only and is refused)
+        rng = np.random.default_rng(3)
+        g2 = nd.barabasi_albert(900, 3, seed=2)
+        vm2 = ([L.kuramoto_first(), L.diffusion_vertex()], rng.integers(0, 2, g2.nv))
+        em2 = ([L.relax_odeedge(), L.kuramoto_edge(), L.diffusion_odeedge()], rng.integers(0, 3, g2.ne))
+        onw2 = oracle_network(g2, vm2, em2)
+        u0 = rng.random(onw2.lastidx_dynamic)
+        p = 0.5 + rng.random(onw2.lastidx_p)
+        try:
+            PartitionedNetwork(g2, vm2, em2, rank=rank, world=world, exchange="p2p")
+            raise AssertionError("p2p exchange accepted edges with states")
+        except RuntimeError:
+            pass
+        pn = PartitionedNetwork(g2, vm2, em2, rank=rank, world=world, exchange="auto")
+        assert pn.exchange_kind == "nccl"
+        owned = np.zeros(u0.size, dtype=np.int64)
+        for a, b in pn.owned_segments:
+            owned[a:b] += 1
+        cover = torch.from_numpy(owned.copy())
+        dist.all_reduce(cover)
+        assert np.all(cover.numpy() == 1), "the ranks' segments tile the state vector"
+        assert owned[g2.nv:].any(), "this rank owns some edge states"
+        u = torch.full((pn.dim(),), float("nan"), dtype=torch.float64)
+        for a, b in pn.owned_segments:
+            u[a:b] = torch.from_numpy(u0[a:b])
+        pt = torch.from_numpy(p)
+        du = torch.full_like(u, float("nan"))
+        pn.rhs(du, u, pt, 0.0)
+        ref = onw2.rhs(u0, p)
+        assert np.max(np.abs(du.numpy()[owned == 1] - ref[owned == 1])) <= 1e-13
+        pn.rk4(u, pt, 0.0, 1e-3, 3)
+        pn.exchange(u)
+        assert np.max(np.abs(u.numpy() - onw2.rk4(u0, p, 0.0, 1e-3, 3))) <= 1e-13
+        pn.close()
     dist.barrier()
     dist.destroy_process_group()
 

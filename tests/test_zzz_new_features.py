@@ -72,9 +72,19 @@ def test_edges_with_states(nd, backend, kernel_mode):
     ud = B.dev(u)
     nw.rk4(ud, B.dev(p), 0.0, 1e-3, B.rk4_steps)
     assert floored_rel_err(B.host(ud), onw.rk4(u, p, 0.0, 1e-3, B.rk4_steps, threads=4)) <= TOL_TRAJ
-    # row-partitioned engines reject them (an edge's states would need an owner rank)
+    # row-partitioned engines (all-gather exchange): the owner of a row range also evaluates f for the same proportion of
+    # every stateful batch; two ranges write disjoint states that tile du.  The packed-halo layout refuses them.
+    ref, out = onw.rhs(u, p), np.full(nw.dim(), np.nan)
+    for a, b in ((0, n // 3), (n // 3, n)):
+        part = nd.Network(g, vm, em, aggregator=nd.B200Aggregator("+", row_range=(a, b), keep_tables=False))
+        dp = B.nan(nw.dim())
+        part(dp, B.dev(u), B.dev(p), 0.0)
+        w = ~np.isnan(B.host(dp))
+        assert not np.any(w & ~np.isnan(out)), "two row ranges wrote the same state"
+        out[w] = B.host(dp)[w]
+    assert floored_rel_err(out, ref) <= TOL_DU
     with pytest.raises(nd.ArgumentError):
-        nd.Network(g, vm, em, aggregator=nd.B200Aggregator("+", row_range=(0, n // 2)))
+        nd.Network(g, vm, em, aggregator=nd.B200Aggregator("+", row_range=(0, n // 2), gather_offset=np.arange(g.nv), gather_len=nw.dim()))
 
 
 def test_parameter_free_multi_batch_network(nd, backend, kernel_mode):
