@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name --format=csv > gpurun_out/smi_multi.txt 2>&1
 nvidia-smi topo -m >> gpurun_out/smi_multi.txt 2>&1
 if [ "$N" -le 4 ]; then
-  ( time timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -x -q ) > gpurun_out/pytest_multi.log 2>&1
+  ( time timeout 900 python -m pytest tests/test_gpu_multi.py tests/test_zzz_new_features.py tests/test_zzz_multi_stateful.py -m gpu -q -k "two_gpu" ) > gpurun_out/pytest_multi.log 2>&1
   echo "pytest rc=$?" >> gpurun_out/pytest_multi.log
   tail -8 gpurun_out/pytest_multi.log
 fi
