@@ -22,6 +22,30 @@ def test_stateful_custom_kinds_rk4_and_host_buffers(nd, backend):
     _check_rk4_and_host_buffers(nd, backend, stateful=True)
 
 
+def test_stateful_custom_kinds_on_row_partitioned_engines(nd, backend):
+    """user-supplied edges with states under a row partition (all-gather exchange): three row ranges write disjoint states
+    that tile du and equal the unpartitioned engine's result bit for bit"""
+    B = backend
+    for name, g, vms, vt, ems, et in _cases_stateful(nd):
+        vm, em = (vms, vt), (ems, et)
+        nw = nd.Network(g, vm, em)
+        rng = np.random.default_rng(2)
+        u, p = rng.random(nw.dim()), 0.5 + rng.random(nw.pdim())
+        full = B.nan(nw.dim())
+        nw(full, B.dev(u), B.dev(p), 0.3)
+        full, out = B.host(full), np.full(nw.dim(), np.nan)
+        cuts = [0, g.nv // 4, g.nv // 2 + 1, g.nv]
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            part = nd.Network(g, vm, em, aggregator=nd.B200Aggregator("+", row_range=(a, b), keep_tables=False))
+            dp = B.nan(nw.dim())
+            part(dp, B.dev(u), B.dev(p), 0.3)
+            dp = B.host(dp)
+            w = ~np.isnan(dp)
+            assert not np.any(w & ~np.isnan(out)), name
+            out[w] = dp[w]
+        assert np.array_equal(out, full), name
+
+
 def test_external_inputs(nd, backend, monkeypatch):
     """External inputs (src/external_inputs.jl, src/coreloop.jl:61): a component's f reads states / outputs of OTHER
     components -- vertices (f(dv, v, esum, ext, p, t)) and edges with states (f(de, e, vs, vd, ext, p, t)).  Sources: a
