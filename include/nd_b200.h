@@ -140,7 +140,11 @@ typedef struct nd_b200_desc {
   int64_t lastidx_dynamic, lastidx_p, lastidx_out, lastidx_aggr;
   /* Multi-GPU vertex partition: this engine evaluates aggregation-slot rows
    * [row_begin, row_end) (0-based, slot = (v_aggr.first-1)/edepth) and writes only their
-   * states in du.  row_end <= 0 means "all rows".                           */
+   * states in du.  row_end <= 0 means "all rows".  Edge batches WITH states: the engine also
+   * evaluates f for edges [count*row_begin/nrows, count*row_end/nrows) of each such batch (0-based
+   * positions in the batch, integer division) and writes their states -- contiguous chunks that tile
+   * the batch when the ranks' row ranges tile the rows.  Needs the complete u (all-gather exchange);
+   * not available together with gather_offset.                              */
   int64_t row_begin, row_end;
   /* rows with more than this many incoming entries are reduced by a whole thread block with a
    * fixed-shape tree instead of one sequential thread; <= 0 -> default (128); INT32_MAX ->
