@@ -778,7 +778,7 @@ struct EngineBuilder {
       // LoopbackConnection topology (src/construction.jl:52-80): a loopback edge starts at a LEAF (its only edge) -- the
       // injector -- and every feed-forward vertex is such an injector
       if (d->vdepth != d->edepth) return fail(e, ND_B200_EINVAL, "loopback edges need vdepth == edepth");
-      if (nrows_owned != e->nrows_total || d->gather_offset) return fail(e, ND_B200_EUNSUPPORTED, "loopback edges on a row-partitioned / halo engine");
+      if (d->gather_offset) return fail(e, ND_B200_EUNSUPPORTED, "loopback edges on a halo engine");   // row partitions with the complete u are fine
       if (!e->custom && d->vdepth != 1) return fail(e, ND_B200_EUNSUPPORTED, "loopback edges with vdepth %d need user-supplied kinds", d->vdepth);
       std::vector<int> deg((size_t)d->nv, 0);
       for (long long k = 0; k < d->ne; ++k) {

@@ -19,6 +19,7 @@ from typing import List, Sequence, Tuple
 import numpy as np
 
 from .network import B200Aggregator, B200Execution, ComponentBatch, IndexManager, Network
+from . import _cabi
 
 
 def row_of_vertex(im: IndexManager) -> np.ndarray:
@@ -221,7 +222,7 @@ class PartitionedNetwork:
         nrows = int(self.entry_counts.size)
         self.segments = [state_segments(probe.vertexbatches, a, b) + edge_state_segments(probe.layer.edgebatches, a, b, nrows)
                          for a, b in self.row_ranges]
-        stateful_edges = any(b.model.dim > 0 for b in probe.layer.edgebatches)
+        stateful_edges = any(b.model.dim > 0 or b.model.kernel_kind() == _cabi.E_LOOPBACK for b in probe.layer.edgebatches)
         self.comm = None
         self.exchange_kind = "nccl"
         self.plan = None
@@ -240,7 +241,7 @@ class PartitionedNetwork:
         want_p2p = exchange in ("p2p", "auto") and world > 1
         if want_p2p and stateful_edges:         # their states travel with the all-gather; the packed halo carries vertex outputs only
             if exchange == "p2p":
-                raise RuntimeError("p2p exchange does not carry the states of edges with states: use exchange='nccl'")
+                raise RuntimeError("p2p exchange carries neither the states of edges with states nor loopback connections: use exchange='nccl'")
             want_p2p = False
         if want_p2p and not statemask_outputs(probe.vertexbatches, probe.im.vdepth):
             if exchange == "p2p":

@@ -138,7 +138,7 @@ def test_fuzz_registry_networks_on_the_emulator(nd, monkeypatch, seed):
         # range from a complete state vector; the ranges tile du
         has_states = any(getattr(m, "dim", 0) > 0 for m in (em[0] if isinstance(em, tuple) else [em]))
         has_loopback = any(m.name == "loopback" for m in (em[0] if isinstance(em, tuple) else [em]))
-        if not has_loopback and g.nv >= 2:      # (edges with states: every range also evaluates its chunk of each stateful batch)
+        if g.nv >= 2:      # (edges with states: every range also evaluates its chunk of each stateful batch)
             cuts = sorted(set([0, g.nv] + [int(c) for c in rng.integers(0, g.nv + 1, int(rng.integers(1, 4)))]))
             out = np.full(nw.dim(), np.nan)
             for a, b in zip(cuts[:-1], cuts[1:]):

@@ -258,6 +258,32 @@ def _worker_partitioned_class(rank, world, port, out_dir):
         pn.exchange(u)
         assert np.max(np.abs(u.numpy() - onw2.rk4(u0, p, 0.0, 1e-3, 3))) <= 1e-13
         pn.close()
+        # LoopbackConnections: a ring of hubs, each with an injector leaf behind a loopback edge; the injector's row may
+        # live on another rank than its hub -- it reads the hub's output from the all-gathered u
+        m = 200
+        gs = np.concatenate([np.arange(1, m + 1), np.arange(m + 1, 2 * m + 1)])
+        gd = np.concatenate([np.roll(np.arange(1, m + 1), -1), np.arange(1, m + 1)])
+        g3 = nd.SimpleDiGraph(2 * m, gs, gd)
+        vm3 = [L.kuramoto_first()] * m + [L.kuramoto_second()] * m
+        em3 = ([L.kuramoto_edge(), L.loopback()], (g3.src > m).astype(np.int64))
+        onw3 = oracle_network(g3, vm3, em3)
+        u0 = rng.random(onw3.lastidx_dynamic)
+        p = 0.5 + rng.random(onw3.lastidx_p)
+        pn = PartitionedNetwork(g3, vm3, em3, rank=rank, world=world, exchange="auto")
+        assert pn.exchange_kind == "nccl"
+        u = torch.full((pn.dim(),), float("nan"), dtype=torch.float64)
+        for a, b in pn.owned_segments:
+            u[a:b] = torch.from_numpy(u0[a:b])
+        pt = torch.from_numpy(p)
+        du = torch.full_like(u, float("nan"))
+        pn.rhs(du, u, pt, 0.0)
+        ref = onw3.rhs(u0, p)
+        for a, b in pn.owned_segments:
+            assert np.max(np.abs(du[a:b].numpy() - ref[a:b])) <= 1e-13
+        pn.rk4(u, pt, 0.0, 1e-3, 3)
+        pn.exchange(u)
+        assert np.max(np.abs(u.numpy() - onw3.rk4(u0, p, 0.0, 1e-3, 3))) <= 1e-13
+        pn.close()
     dist.barrier()
     dist.destroy_process_group()
 

@@ -200,6 +200,17 @@ def test_loopback_connections_and_feed_forward_injectors(nd, backend, monkeypatc
         l_b = [b for b in nw.vertexbatches if b.model.name == "L_injector"][0]
         want_hub = (ginv * (V - v) + -1.0 * (v / R) + -1.0 * iL) / Cc
         assert abs(du[hub_b.state_first - 1] - want_hub) <= 1e-15 and du[l_b.state_first - 1] == v / Lind, mode
+        # row-partitioned engines with the complete u (all-gather exchange): the ranges tile du, injectors included
+        out = np.full(2, np.nan)
+        for a, b in ((0, 1), (1, 3), (3, 4)):
+            part = nd.Network(g, vms, ems, aggregator=nd.B200Aggregator("+", row_range=(a, b), keep_tables=False))
+            dp = B.nan(2)
+            part(dp, B.dev(u), B.dev(p), 0.0)
+            dp = B.host(dp)
+            w = ~np.isnan(dp)
+            assert not np.any(w & ~np.isnan(out)), mode
+            out[w] = dp[w]
+        assert np.array_equal(out, du), mode
         # twin (same batching / layout), get_buffers and RK4
         from helpers import model_types
         um, vt = model_types(vms, g.nv)
