@@ -869,7 +869,7 @@ struct EngineBuilder {
     for (int b = 0; b < d->n_vbatches; ++b) any_ext = any_ext || d->vbatches[b].extdim > 0;
     for (int b = 0; b < d->n_ebatches; ++b) any_ext = any_ext || d->ebatches[b].extdim > 0;
     if (!any_ext) return ND_B200_OK;
-    if (nrows_owned != e->nrows_total || d->gather_offset) return fail(e, ND_B200_EUNSUPPORTED, "external inputs on a row-partitioned / halo engine");
+    if (d->gather_offset) return fail(e, ND_B200_EUNSUPPORTED, "external inputs on a halo engine");   // row partitions with the complete u are fine
     if (d->lastidx_dynamic >= ND_EXT_FROM_VOUT || d->nv * (long long)d->vdepth >= ND_EXT_FROM_VOUT) return fail(e, ND_B200_EUNSUPPORTED, "networks with external inputs need offsets below 2^30");
     auto one = [&](int extdim, long long count, const int64_t* src, std::vector<int>& out, const char* what, int b) -> int {
       if (extdim <= 0) return ND_B200_OK;

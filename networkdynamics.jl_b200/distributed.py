@@ -222,7 +222,8 @@ class PartitionedNetwork:
         nrows = int(self.entry_counts.size)
         self.segments = [state_segments(probe.vertexbatches, a, b) + edge_state_segments(probe.layer.edgebatches, a, b, nrows)
                          for a, b in self.row_ranges]
-        stateful_edges = any(b.model.dim > 0 or b.model.kernel_kind() == _cabi.E_LOOPBACK for b in probe.layer.edgebatches)
+        stateful_edges = any(b.model.dim > 0 or b.model.kernel_kind() == _cabi.E_LOOPBACK or b.model.extdim > 0 for b in probe.layer.edgebatches) \
+            or any(b.model.extdim > 0 for b in probe.vertexbatches)
         self.comm = None
         self.exchange_kind = "nccl"
         self.plan = None
@@ -241,7 +242,7 @@ class PartitionedNetwork:
         want_p2p = exchange in ("p2p", "auto") and world > 1
         if want_p2p and stateful_edges:         # their states travel with the all-gather; the packed halo carries vertex outputs only
             if exchange == "p2p":
-                raise RuntimeError("p2p exchange carries neither the states of edges with states nor loopback connections: use exchange='nccl'")
+                raise RuntimeError("p2p exchange carries only vertex outputs (no edge states, loopback connections, external inputs): use exchange='nccl'")
             want_p2p = False
         if want_p2p and not statemask_outputs(probe.vertexbatches, probe.im.vdepth):
             if exchange == "p2p":

@@ -46,6 +46,20 @@ def test_stateful_custom_kinds_on_row_partitioned_engines(nd, backend):
         assert np.array_equal(out, full), name
 
 
+def _tiles(nd, B, g, vm, em, u, p, t, full, cuts):
+    """row-partitioned engines over `cuts` write disjoint states that tile du and equal the unpartitioned result"""
+    out = np.full(full.size, np.nan)
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        part = nd.Network(g, vm, em, aggregator=nd.B200Aggregator("+", row_range=(a, b), keep_tables=False))
+        dp = B.nan(full.size)
+        part(dp, B.dev(u), B.dev(p), t)
+        dp = B.host(dp)
+        w = ~np.isnan(dp)
+        assert not np.any(w & ~np.isnan(out))
+        out[w] = dp[w]
+    assert np.array_equal(out, full)
+
+
 def test_external_inputs(nd, backend, monkeypatch):
     """External inputs (src/external_inputs.jl, src/coreloop.jl:61): a component's f reads states / outputs of OTHER
     components -- vertices (f(dv, v, esum, ext, p, t)) and edges with states (f(de, e, vs, vd, ext, p, t)).  Sources: a
@@ -111,6 +125,7 @@ def test_external_inputs(nd, backend, monkeypatch):
             du = B.nan(nw.dim())
             nw(du, B.dev(u), B.dev(p), t)
             assert floored_rel_err(B.host(du), ref) <= 1e-12, (mode, t)
+            _tiles(nd, B, g, vms, ems, u, p, t, B.host(du), [0, g.nv // 3, g.nv // 2, g.nv])
         dt, x, t0 = 1e-2, u.copy(), 0.1
         for s in range(3):
             t = t0 + s * dt
@@ -143,6 +158,7 @@ def test_external_inputs(nd, backend, monkeypatch):
     du = B.nan(nw.dim())
     nw(du, B.dev(u), B.dev(p), 0.3)
     assert floored_rel_err(B.host(du), ONP.rhs(im, u, p, 0.3, extmap)[0]) <= 1e-12
+    _tiles(nd, B, g, vms, M["line2"], u, p, 0.3, B.host(du), [0, 7, 21, g.nv])
     # refusals: output of a static (feed-forward) edge; unknown symbol; registry kinds do not take external inputs
     g = nd.complete_graph(4)
     with pytest.raises(nd.ArgumentError, match="feed-forward"):
