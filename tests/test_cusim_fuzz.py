@@ -370,6 +370,19 @@ def test_fuzz_user_supplied_kinds(nd, monkeypatch, seed):
         o, agg = cusim.empty(nw.im.lastidx_out), cusim.empty(nw.im.lastidx_aggr)
         nw.get_buffers(o, agg, cusim.dev(u), pd, 0.4)
         assert floored_rel_err(agg.numpy(), agg_ref) <= 1e-12 and floored_rel_err(o.numpy(), o_ref) <= 1e-12, seed
+        # row-partitioned engines (complete u): random row ranges write disjoint states -- vertex rows plus a chunk of every
+        # stateful edge batch -- that tile du; rows below the long-row threshold sum in the same order (the thresholds agree)
+        thr = nw.layer.aggregator._opts["long_row_threshold"]
+        cuts = sorted(set([0, g.nv] + [int(c) for c in rng.integers(0, g.nv + 1, int(rng.integers(1, 4)))]))
+        out = np.full(nw.dim(), np.nan)
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            part = nd.Network(g, (vms, vt), (ems, et), aggregator=nd.B200Aggregator("+", long_row_threshold=thr, row_range=(a, b), keep_tables=False))
+            dp = cusim.empty(nw.dim())
+            part(dp, cusim.dev(u), pd, 0.4)
+            w = ~np.isnan(dp.numpy())
+            assert not np.any(w & ~np.isnan(out)), (seed, cuts)
+            out[w] = dp.numpy()[w]
+        assert np.array_equal(out, du.numpy()), (seed, cuts)
 
 
 @pytest.mark.parametrize("order,select", [("reverse", "dq_networks or registry_networks"),
