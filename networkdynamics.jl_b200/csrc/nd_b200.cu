@@ -16,6 +16,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -525,6 +527,13 @@ std::string custom_source(const nd_b200_engine* e, int vdepth) {
 // compile the generated source for sm_100a; on success load it (unless host_only) and fetch the kernels
 int compile_custom(nd_b200_engine* e, int vdepth, int edepth) {
   e->custom_src = custom_source(e, vdepth);
+  // process-wide cache of compiled modules: engines built from the same generated source and kernel instantiations (the
+  // ranks' row ranges of one network, a network rebuilt with another aggregator option) share one compilation
+  struct Compiled { std::vector<char> cubin; std::string lowered[5]; };
+  static std::mutex cache_mu;
+  static std::map<std::string, Compiled> cache;
+  const char* cache_env = getenv("ND_B200_NVRTC_CACHE");
+  const bool use_cache = !(cache_env && atoi(cache_env) == 0) && !e->host_only;
   nvrtcProgram prog = nullptr;
   if (nvrtcCreateProgram(&prog, e->custom_src.c_str(), "nd_b200_custom.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS)
     return fail(e, ND_B200_ECUDA, "nvrtcCreateProgram failed");
@@ -536,6 +545,26 @@ int compile_custom(nd_b200_engine* e, int vdepth, int edepth) {
   snprintf(nm[2], sizeof nm[2], "ndb::vertex_out_kernel");
   snprintf(nm[3], sizeof nm[3], "ndb::edge_out_kernel<%d, %d>", vdepth, edepth);
   snprintf(nm[4], sizeof nm[4], "ndb::edge_f_kernel<%d>", vdepth);
+  std::string key = e->custom_src;
+  for (int k = 0; k < 5; ++k) { key += "\n//"; key += nm[k]; }
+  Compiled hit;
+  bool have = false;
+  if (use_cache) {
+    std::lock_guard<std::mutex> lk(cache_mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { hit = it->second; have = true; }
+  }
+  if (have) {
+    nvrtcDestroyProgram(&prog);
+    CUDA_TRY(e, cudaSetDevice(e->device));
+    CUDA_TRY(e, cudaLibraryLoadData(&e->c_lib, hit.cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+    CUDA_TRY(e, cudaLibraryGetKernel(&e->c_fused, e->c_lib, hit.lowered[0].c_str()));
+    CUDA_TRY(e, cudaLibraryGetKernel(&e->c_jag, e->c_lib, hit.lowered[1].c_str()));
+    CUDA_TRY(e, cudaLibraryGetKernel(&e->c_vout, e->c_lib, hit.lowered[2].c_str()));
+    CUDA_TRY(e, cudaLibraryGetKernel(&e->c_eout, e->c_lib, hit.lowered[3].c_str()));
+    CUDA_TRY(e, cudaLibraryGetKernel(&e->c_ef, e->c_lib, hit.lowered[4].c_str()));
+    return ND_B200_OK;
+  }
   for (int k = 0; k < 5; ++k) nvrtcAddNameExpression(prog, nm[k]);
   const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "--fmad=false", "-lineinfo", "-default-device"};
   const nvrtcResult rc = nvrtcCompileProgram(prog, 5, opts);
@@ -560,6 +589,12 @@ int compile_custom(nd_b200_engine* e, int vdepth, int edepth) {
     lowered[k] = ln;
   }
   nvrtcDestroyProgram(&prog);
+  if (use_cache) {
+    std::lock_guard<std::mutex> lk(cache_mu);
+    Compiled& c = cache[key];
+    c.cubin = cubin;
+    for (int k = 0; k < 5; ++k) c.lowered[k] = lowered[k];
+  }
   CUDA_TRY(e, cudaSetDevice(e->device));
   CUDA_TRY(e, cudaLibraryLoadData(&e->c_lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
   CUDA_TRY(e, cudaLibraryGetKernel(&e->c_fused, e->c_lib, lowered[0].c_str()));
