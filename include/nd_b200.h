@@ -245,6 +245,11 @@ int nd_b200_export_jag(const nd_b200_engine*, int32_t* slices, uint16_t* lanes, 
 /* the CUDA source generated for an engine with user-supplied kinds (NULL otherwise); owned by the engine */
 const char* nd_b200_custom_source(const nd_b200_engine*);
 
+/* name of the kernel family that evaluates this engine's RHS: "rhs_fused_kernel" (tile kernel), "rhs_jag_kernel" (jagged
+ * warp slices), "rhs_js_kernel" (jagged slices streamed through shared memory by TMA bulk copies, persistent warps),
+ * "edge_pass_kernel+row_pass_kernel" (split mode); static string */
+const char* nd_b200_kernel_name(const nd_b200_engine*);
+
 /* kernel launches issued by this engine since creation (bench.py's gpu_launches) */
 int64_t nd_b200_launch_count(const nd_b200_engine*);
 /* average device time [ms] of the fused RHS kernel over the last `nd_b200_rhs` calls made while

@@ -67,7 +67,7 @@ EXPORTED_SYMBOLS = [
     "nd_b200_rhs_host", "nd_b200_get_buffers", "nd_b200_aggregate", "nd_b200_rk4", "nd_b200_export_sizes", "nd_b200_export_tables",
     "nd_b200_launch_count", "nd_b200_set_timing", "nd_b200_timings", "nd_b200_host_alloc", "nd_b200_host_free",
     "nd_b200_comm_create", "nd_b200_comm_export", "nd_b200_comm_open_peer", "nd_b200_comm_set_send", "nd_b200_rhs_local", "nd_b200_custom_source", "nd_b200_create_from_edgelist", "nd_b200_rhs_exchange", "nd_b200_comm_status",
-    "nd_b200_comm_last_error", "nd_b200_comm_destroy", "nd_b200_export_jag_sizes", "nd_b200_export_jag", "nd_b200_pack_params", "nd_b200_rk4_exchange",
+    "nd_b200_comm_last_error", "nd_b200_comm_destroy", "nd_b200_export_jag_sizes", "nd_b200_export_jag", "nd_b200_pack_params", "nd_b200_rk4_exchange", "nd_b200_kernel_name",
 ]
 IPC_HANDLE_BYTES = 64
 
@@ -175,6 +175,8 @@ def bind(L):
     L.nd_b200_export_jag.argtypes = [C.c_void_p, i32p, C.POINTER(C.c_uint16), i32p, i32p]
     L.nd_b200_custom_source.restype = C.c_char_p
     L.nd_b200_custom_source.argtypes = [C.c_void_p]
+    L.nd_b200_kernel_name.restype = C.c_char_p
+    L.nd_b200_kernel_name.argtypes = [C.c_void_p]
     L.nd_b200_launch_count.restype = C.c_int64
     L.nd_b200_launch_count.argtypes = [C.c_void_p]
     L.nd_b200_set_timing.restype = C.c_int

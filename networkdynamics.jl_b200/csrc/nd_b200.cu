@@ -58,6 +58,7 @@ struct nd_b200_engine {
   int long_thr = 128;
   int gather_from_u = 1;
   int ek = EK_GENERIC;        // edge kind of the single edge batch, or EK_GENERIC
+  bool compact = false;       // tile layout with compact entry words (offset | local row << 23 | side << 30), kernels <..., CR = true>
   int block = 256, ept = 8;   // launch shape of the fused kernel
   std::vector<HostVB> hvb;
   std::vector<HostEB> heb;
@@ -87,6 +88,13 @@ struct nd_b200_engine {
   int* d_jnbr = nullptr;
   int2* d_jent = nullptr;
   uint8_t* d_jebid = nullptr;
+  // streamed jagged kernel (rhs_js_kernel, ND_B200_KERNEL=js): persistent warps, each owning the contiguous slices
+  // [jwarp.x, jwarp.y); jag_len = length of the (padded) entry stream; launch parameters
+  int jstream = 0, js_u = 8, js_nst = 8, js_wps = 16;
+  int n_jwarps = 0;
+  long long jag_len = 0;
+  int2* d_jwarp = nullptr;
+  std::vector<int2> h_jwarp;
   // host-buffer pipeline (nd_b200_rhs_host): per thread block of the launch grid, the end of the parameter range it
   // reads and the rows it writes; launch_nblk >= 0 restricts a launch to blocks [P.blk_off, P.blk_off + launch_nblk)
   std::vector<int> blk_pmax, blk_rmin, blk_rmax;
@@ -267,6 +275,7 @@ void fill_params(const nd_b200_engine* e, KParams& P) {
   P.tiles = e->d_tiles; P.ntiles = e->ntiles; P.oidx = e->d_oidx; P.oedge = e->d_oedge;
   P.jslices = e->d_jslices; P.jlanes = e->d_jlanes; P.jnbr = e->d_jnbr; P.jent = e->d_jent; P.jebid = e->d_jebid;
   P.jlong = e->d_jlong; P.nslices = e->nslices; P.n_jag_blocks = e->n_jag_blocks;
+  P.jwarp = e->d_jwarp; P.n_jwarps = e->n_jwarps; P.n_jlong = e->n_jlong;
   P.halo = nullptr; P.halo_base = e->halo_base; P.wait_from = e->wait_from;
   P.ppack = e->pack_on ? e->d_ppack : nullptr;
 }
@@ -310,6 +319,20 @@ template <int VD, int ED, int EK, int PE>
 cudaError_t launch_shape(const nd_b200_engine* e, const KParams& P, cudaStream_t st) {
   const int grid = (e->launch_nblk >= 0 ? e->launch_nblk : e->nblocks) + P.n_pub + P.fence;
   if (grid == 0) return cudaSuccess;
+  if constexpr (EK != EK_GENERIC) {
+    if (e->compact) {   // compact entry words: default launch shape only (plan_tiles)
+      if constexpr (PE > 0) {
+        if (e->pack_on) {
+          if (e->halo_base != INT_MAX) ND_LAUNCH(grid, 128, st, (P), rhs_fused_kernel<VD, ED, EK, PE, 128, 4, true, true, true>);
+          else ND_LAUNCH(grid, 128, st, (P), rhs_fused_kernel<VD, ED, EK, PE, 128, 4, false, true, true>);
+          return cudaGetLastError();
+        }
+      }
+      if (e->halo_base != INT_MAX) ND_LAUNCH(grid, 128, st, (P), rhs_fused_kernel<VD, ED, EK, PE, 128, 4, true, false, true>);
+      else ND_LAUNCH(grid, 128, st, (P), rhs_fused_kernel<VD, ED, EK, PE, 128, 4, false, false, true>);
+      return cudaGetLastError();
+    }
+  }
   if constexpr (PE > 0 && EK != EK_GENERIC) {
     if (e->pack_on) {   // packed edge parameters: default launch shape only (checked by nd_b200_pack_params)
       if (e->halo_base != INT_MAX) ND_LAUNCH(grid, 128, st, (P), rhs_fused_kernel<VD, ED, EK, PE, 128, 4, true, true>);
@@ -336,6 +359,24 @@ cudaError_t launch_jag_u(const nd_b200_engine* e, const KParams& P, cudaStream_t
   const int grid = (e->launch_nblk >= 0 ? e->launch_nblk : e->n_jag_blocks + e->n_jlong) + P.n_pub + P.fence;
   if (grid == 0) return cudaSuccess;
   const int wps = e->jag_wps > 0 ? e->jag_wps : jag_warps_per_sm_default(EK);
+  if constexpr (VD == 1 && EK != EK_GENERIC && U >= 4) {
+    // deep variants (single-GPU, single edge batch): all index / parameter loads of U columns are issued back to back, then
+    // all U gathers -- three dependent memory levels per slice instead of 2 per pair of columns
+    if (e->halo_base == INT_MAX) {
+      if constexpr (PE > 0) {
+        if (e->pack_on) {
+          if (wps >= 48) ND_LAUNCH(grid, BLOCK, st, (P), rhs_jag_kernel<VD, ED, EK, PE, BLOCK, U, 48, false, true>);
+          else if (wps >= 32) ND_LAUNCH(grid, BLOCK, st, (P), rhs_jag_kernel<VD, ED, EK, PE, BLOCK, U, 32, false, true>);
+          else ND_LAUNCH(grid, BLOCK, st, (P), rhs_jag_kernel<VD, ED, EK, PE, BLOCK, U, 24, false, true>);
+          return cudaGetLastError();
+        }
+      }
+      if (wps >= 48) ND_LAUNCH(grid, BLOCK, st, (P), rhs_jag_kernel<VD, ED, EK, PE, BLOCK, U, 48, false>);
+      else if (wps >= 32) ND_LAUNCH(grid, BLOCK, st, (P), rhs_jag_kernel<VD, ED, EK, PE, BLOCK, U, 32, false>);
+      else ND_LAUNCH(grid, BLOCK, st, (P), rhs_jag_kernel<VD, ED, EK, PE, BLOCK, U, 24, false>);
+      return cudaGetLastError();
+    }
+  }
   if constexpr (PE > 0 && EK != EK_GENERIC && U == 2) {
     if (e->pack_on) {   // packed edge parameters: U = 2 only (checked by nd_b200_pack_params)
       if (e->halo_base != INT_MAX) {
@@ -357,6 +398,9 @@ cudaError_t launch_jag_u(const nd_b200_engine* e, const KParams& P, cudaStream_t
 }
 template <int VD, int ED, int EK, int PE>
 cudaError_t launch_jag_t(const nd_b200_engine* e, const KParams& P, cudaStream_t st) {
+  if constexpr (VD == 1 && EK != EK_GENERIC) {
+    if (e->jag_u >= 8) return launch_jag_u<VD, ED, EK, PE, 8>(e, P, st);
+  }
   return e->jag_u >= 4 ? launch_jag_u<VD, ED, EK, PE, 4>(e, P, st) : launch_jag_u<VD, ED, EK, PE, 2>(e, P, st);
 }
 cudaError_t launch_jag(nd_b200_engine* e, const KParams& P, cudaStream_t st) {
@@ -367,6 +411,57 @@ cudaError_t launch_jag(nd_b200_engine* e, const KParams& P, cudaStream_t st) {
     case ND_B200_E_DIFFUSION_NOP: return launch_jag_t<1, 1, ND_B200_E_DIFFUSION_NOP, 0>(e, P, st);
     case ND_B200_E_KURAMOTO: return launch_jag_t<1, 1, ND_B200_E_KURAMOTO, 1>(e, P, st);
     default: return launch_jag_t<1, 1, EK_GENERIC, 1>(e, P, st);
+  }
+}
+
+// ---- streamed jagged kernel launches -----------------------------------------------------------------------------------
+template <int EK, int PE, bool PK, int U, int NST, int MINB>
+cudaError_t launch_js_inst(const nd_b200_engine* e, const KParams& P, cudaStream_t st, bool prepare) {
+  const int wpb = JS_BLOCK / 32;
+  const int smem = js_warp_bytes(PE, PK, NST) * wpb;
+  if (prepare) {   // engine construction: opt in to the dynamic shared memory of this instantiation (not a stream operation)
+#ifndef ND_CUSIM
+    return cudaFuncSetAttribute(rhs_js_kernel<EK, PE, PK, U, NST, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+#else
+    return cudaSuccess;
+#endif
+  }
+  const int grid = std::max((e->n_jwarps + wpb - 1) / wpb, std::min(e->n_jlong, 148 * 4));
+  if (grid == 0) return cudaSuccess;
+#ifdef ND_CUSIM
+  ND_LAUNCH(grid, JS_BLOCK, st, (P), rhs_js_kernel<EK, PE, PK, U, NST, MINB>);
+#else
+  rhs_js_kernel<EK, PE, PK, U, NST, MINB><<<grid, JS_BLOCK, smem, st>>>(P);
+#endif
+  return cudaGetLastError();
+}
+template <int EK, int PE, bool PK>
+cudaError_t launch_js_shape(const nd_b200_engine* e, const KParams& P, cudaStream_t st, bool prepare) {
+  // (U, NST): gathers in flight per lane, chunks per ring; MINB caps registers so that js_wps warps fit
+  if (e->js_u >= 8) {
+    if (e->js_nst >= 8) return launch_js_inst<EK, PE, PK, 8, 8, 4>(e, P, st, prepare);
+    return launch_js_inst<EK, PE, PK, 8, 4, 6>(e, P, st, prepare);
+  }
+  if (e->js_nst >= 8) return launch_js_inst<EK, PE, PK, 4, 8, 4>(e, P, st, prepare);
+  return launch_js_inst<EK, PE, PK, 4, 4, 8>(e, P, st, prepare);
+}
+template <int EK, int PE>
+cudaError_t launch_js_t(const nd_b200_engine* e, const KParams& P, cudaStream_t st, bool prepare) {
+  if constexpr (PE > 0) {
+    if (prepare) {
+      cudaError_t c = launch_js_shape<EK, PE, true>(e, P, st, true);
+      if (c != cudaSuccess) return c;
+    } else if (e->pack_on) return launch_js_shape<EK, PE, true>(e, P, st, false);
+  }
+  return launch_js_shape<EK, PE, false>(e, P, st, prepare);
+}
+cudaError_t launch_js(nd_b200_engine* e, const KParams& P, cudaStream_t st, bool prepare = false) {
+  if (!prepare) e->launches += (e->n_jwarps + e->n_jlong > 0);
+  switch (e->ek) {
+    case ND_B200_E_DIFFUSION: return launch_js_t<ND_B200_E_DIFFUSION, 1>(e, P, st, prepare);
+    case ND_B200_E_DIFFUSION_NOP: return launch_js_t<ND_B200_E_DIFFUSION_NOP, 0>(e, P, st, prepare);
+    case ND_B200_E_KURAMOTO: return launch_js_t<ND_B200_E_KURAMOTO, 1>(e, P, st, prepare);
+    default: return cudaErrorInvalidConfiguration;
   }
 }
 
@@ -381,6 +476,7 @@ cudaError_t launch_custom(nd_b200_engine* e, const KParams& P, cudaStream_t st) 
 
 cudaError_t launch_fused(nd_b200_engine* e, const KParams& P, cudaStream_t st) {
   if (e->custom) return launch_custom(e, P, st);
+  if (e->jstream) return launch_js(e, P, st);
   if (e->jag) return launch_jag(e, P, st);
   if (e->split) {
     // edge pass (PASS 5) then row pass (aggregate + PASS 6); P.gsrc is the gather source of this evaluation
@@ -621,6 +717,7 @@ struct EngineBuilder {
   // CSR over the owned rows, entries in accumulation order
   std::vector<long long> cnt;
   std::vector<int> h_rowptr, h_nbr, h_epar;
+  std::vector<int> h_nbr_c;                  // tile layout, compact entry words (engine::compact)
   std::vector<uint8_t> h_ebid;
   bool keep = false, generic_edges = false, want_split = false;
   std::vector<int> h_oidx, h_es, h_et, h_eepar, h_eooff;   // split mode
@@ -1108,6 +1205,27 @@ struct EngineBuilder {
       }
     }
     for (const HostEB& h : e->heb) deb.push_back(EBDev{h.kind, h.coupling, h.pdim, h.dim});
+    // compact entry words for the specialised tile kernels: offset | local row << 23 | side << 30
+    {
+      const long long max_off = std::max<long long>(e->gather_from_u ? d->lastidx_dynamic : d->nv * (long long)d->vdepth, d->gather_offset ? d->gather_len : 0);
+      const bool specialised = !e->custom && !e->split && (d->vdepth == 2 ? true : e->ek != EK_GENERIC);
+      e->compact = specialised && e->block == 128 && e->ept == 4 && max_off < (1LL << ND_CR_OFF_BITS) && !getenv("ND_B200_NO_COMPACT");
+      if (e->compact) {
+        h_nbr_c.assign(h_nbr.size(), 0);
+        for (const int4& t : tiles) {
+          const bool lg = t.w < 0;
+          const int nr = lg ? 1 : ((t.w >> 16) & 0x1FF);
+          for (int r = 0; r < nr; ++r) {
+            const long long row = (long long)t.x + r - e->row_begin;
+            for (long long j = cnt[(size_t)row]; j < cnt[(size_t)row + 1]; ++j) {
+              const int w = h_nbr[(size_t)j];
+              const int side = w < 0, off = side ? ~w : w;
+              h_nbr_c[(size_t)j] = off | (r << ND_CR_OFF_BITS) | (side << 30);
+            }
+          }
+        }
+      }
+    }
     return ND_B200_OK;
   }
 
@@ -1120,6 +1238,7 @@ struct EngineBuilder {
     // vary (idle lanes in the jagged walk: ER cfg2 72 vs 76 us, BA cfg3 91 vs 148 us) or the graph is small (latency of the
     // per-lane walk: cfg1); the jagged kernel wins on large regular-degree graphs (cfg4 grid: RK4 step 45 vs 55 us).
     // auto = jagged iff lane utilisation of the walk >= 0.8 and there are enough rows to fill the machine.
+    int auto_window = 32;
     {
       long long sum_max = 0;
       for (long long r = 0; r < nrows_owned; r += 32) {
@@ -1129,23 +1248,56 @@ struct EngineBuilder {
       }
       const double util = sum_max > 0 ? (double)e->nentries / (32.0 * (double)sum_max) : 0.0;
       e->jag = (util >= 0.8 && nrows_owned >= 65536) ? 1 : 0;
+      // Irregular graphs WITHOUT hubs (Erdos-Renyi: configs 2 and 5): degree-bucketed slices over windows of 128 rows.
+      // Measured on B200 (profiles/r02d_sweep_jag_pipelined.jsonl, config 2): same speed as the tile kernel with live
+      // parameters (72.7 vs 72.1 us) and faster once the edge parameters are packed (58.4 vs 65 us); with power-law hubs
+      // (config 3) the tile kernel stays ahead (95 vs 122-137 us).
+      if (!e->jag && nrows_owned >= 65536 && d->vdepth == 1 && !e->custom && e->ek != EK_GENERIC) {
+        long long maxdeg = 0, sum128 = 0;
+        for (long long r = 0; r < nrows_owned; ++r) maxdeg = std::max(maxdeg, cnt[(size_t)r + 1] - cnt[(size_t)r]);
+        if (maxdeg <= 64) {
+          std::vector<long long> deg;
+          for (long long w0 = 0; w0 < nrows_owned; w0 += 128) {
+            deg.clear();
+            for (long long q = w0; q < std::min<long long>(w0 + 128, nrows_owned); ++q) deg.push_back(cnt[(size_t)q + 1] - cnt[(size_t)q]);
+            std::sort(deg.begin(), deg.end(), std::greater<long long>());
+            for (size_t k = 0; k < deg.size(); k += 32) sum128 += deg[k];     // longest lane of each slice
+          }
+          const double util128 = sum128 > 0 ? (double)e->nentries / (32.0 * (double)sum128) : 0.0;
+          if (util128 >= 0.7) { e->jag = 1; auto_window = 128; }
+        }
+      }
     }
+    // streamed jagged kernel (rhs_js_kernel): single-batch benchmark edge kinds, one vertex output, no halo layout
+    const bool js_ok = !e->custom && d->vdepth == 1 && e->edepth == 1 && e->gather_from_u && !d->gather_offset && !any_ode &&
+                       (e->ek == ND_B200_E_DIFFUSION || e->ek == ND_B200_E_DIFFUSION_NOP || e->ek == ND_B200_E_KURAMOTO) && e->c_maxdim <= ND_MAX_VDIM;
+    e->jstream = 0;
     if (const char* s = getenv("ND_B200_KERNEL")) {
       if (!strcmp(s, "jag")) e->jag = 1;
+      else if (!strcmp(s, "js") && js_ok) { e->jag = 1; e->jstream = 1; }
       else if (!strcmp(s, "fused") || !strcmp(s, "split") || !strcmp(s, "v1")) e->jag = 0;
     }
-    if (e->split) e->jag = 0;
-    if (d->long_row_threshold > 63 * 32) e->jag = 0;
+    if (e->split) { e->jag = 0; e->jstream = 0; }
+    if (d->long_row_threshold > 63 * 32) { e->jag = 0; e->jstream = 0; }
+    for (const HostVB& h : e->hvb) if (h.pdim > 4) e->jstream = 0;      // the kernel prefetches up to 4 vertex parameters
+    if (!e->jag) e->jstream = 0;
     e->jag_u = 2;
-    e->jag_wps = d->vdepth == 2 ? 32 : 48;   // spill-free register budgets, best measured
+    e->jag_wps = 32;   // spill-free register budget of the software-pipelined walk, best measured (profiles/r02d)
     jag_pe = any_epar || (generic_edges && !e->custom);   // kernels instantiated with PE > 0 read {nbr, epar} pairs
     if (e->jag) {
       e->jsplit = 32;
       if (const char* s = getenv("ND_B200_JAG_SPLIT")) e->jsplit = std::min(63, std::max(1, atoi(s)));
       if (const char* s = getenv("ND_B200_JAG_U")) e->jag_u = atoi(s);
       if (const char* s = getenv("ND_B200_JAG_WPS")) e->jag_wps = atoi(s);
-      int jwindow = 32;
-      if (const char* s = getenv("ND_B200_JAG_WINDOW")) { const int w = atoi(s); if (w == 64 || w == 128) jwindow = w; }
+      int jwindow = e->jstream ? 128 : auto_window;
+      if (const char* s = getenv("ND_B200_JAG_WINDOW")) { const int w = atoi(s); if (w == 32 || w == 64 || w == 128) jwindow = w; }
+      if (e->jstream) {
+        if (const char* s = getenv("ND_B200_JS_U")) e->js_u = atoi(s) >= 8 ? 8 : 4;
+        if (const char* s = getenv("ND_B200_JS_NST")) e->js_nst = atoi(s) >= 8 ? 8 : 4;
+        // resident warps per SM of the chosen instantiation (launch_js_shape: MINB blocks of 4 warps)
+        e->js_wps = e->js_u >= 8 ? (e->js_nst >= 8 ? 16 : 24) : (e->js_nst >= 8 ? 16 : 32);
+        if (const char* s = getenv("ND_B200_JS_WPS")) e->js_wps = std::max(1, std::min(64, atoi(s)));
+      }
       // rows longer than this are reduced by a whole block: explicit threshold if the caller gave one, else what a
       // slice can hold
       const long long block_thr = d->long_row_threshold > 0 ? std::min<long long>(d->long_row_threshold, 32LL * e->jsplit) : 32LL * e->jsplit;
@@ -1171,6 +1323,7 @@ struct EngineBuilder {
           for (int j = 0; j < maxlen; ++j)
             for (const Lane& L : lanes)
               if (L.len > j) order.push_back((int)(L.start + j));
+          if (e->jstream) while (order.size() & 3) order.push_back(-1);   // 16-byte granularity of the bulk copies
           jslices.push_back(make_int4(e0, (int)row0, (int)b, maxparts));
           for (int l = 0; l < 32; ++l) {
             uint16_t v = 0;
@@ -1234,17 +1387,23 @@ struct EngineBuilder {
         jlong.push_back(make_int4((int)order.size(), (int)lr.first, (int)deg, lr.second));
         for (long long j = 0; j < deg; ++j) order.push_back((int)(a + j));
       }
-      if ((long long)order.size() != e->nentries) return fail(e, ND_B200_EINVAL, "internal: jagged layout holds %lld of %lld entries", (long long)order.size(), e->nentries);
+      {
+        long long real = 0;
+        for (int o : order) real += o >= 0;
+        if (real != e->nentries) return fail(e, ND_B200_EINVAL, "internal: jagged layout holds %lld of %lld entries", real, e->nentries);
+      }
+      e->jag_len = (long long)order.size();
+      // padding slots (-1, streamed layout only) are never addressed by a lane; they hold offset 0
       if (jag_pe) {
         jent.resize(std::max<size_t>(order.size(), 1));
-        for (size_t k = 0; k < order.size(); ++k) jent[k] = make_int2(h_nbr[(size_t)order[k]], any_epar ? h_epar[(size_t)order[k]] : 0);
+        for (size_t k = 0; k < order.size(); ++k) jent[k] = order[k] < 0 ? make_int2(0, 0) : make_int2(h_nbr[(size_t)order[k]], any_epar ? h_epar[(size_t)order[k]] : 0);
       } else {
         jnbr.resize(std::max<size_t>(order.size(), 1));
-        for (size_t k = 0; k < order.size(); ++k) jnbr[k] = h_nbr[(size_t)order[k]];
+        for (size_t k = 0; k < order.size(); ++k) jnbr[k] = order[k] < 0 ? 0 : h_nbr[(size_t)order[k]];
       }
       if (!h_ebid.empty()) {
         jebid.resize(std::max<size_t>(order.size(), 1));
-        for (size_t k = 0; k < order.size(); ++k) jebid[k] = h_ebid[(size_t)order[k]];
+        for (size_t k = 0; k < order.size(); ++k) jebid[k] = order[k] < 0 ? 0 : h_ebid[(size_t)order[k]];
       }
       e->host_only = (d->flags & ND_B200_FLAG_HOST_ONLY) != 0;
       if (e->host_only) { e->h_jslices = jslices; e->h_jlong = jlong; e->h_jlanes = jlanes; e->h_jorder = order; }
@@ -1256,7 +1415,7 @@ struct EngineBuilder {
           const int4& S = jslices[sidx];
           const long long eend = sidx + 1 < jslices.size() ? jslices[sidx + 1].x : (jlong.empty() ? (long long)order.size() : jlong[0].x);
           int pm = e->blk_pmax[k];
-          for (long long q = S.x; q < eend; ++q) pm = std::max(pm, entry_pend(order[(size_t)q]));
+          for (long long q = S.x; q < eend; ++q) if (order[(size_t)q] >= 0) pm = std::max(pm, entry_pend(order[(size_t)q]));
           for (int l = 0; l < 32; ++l) {
             const uint16_t v = jlanes[sidx * 32 + (size_t)l];
             if (!((v >> 14) & 1)) break;
@@ -1277,6 +1436,39 @@ struct EngineBuilder {
       e->nslices = (int)jslices.size();
       e->n_jag_blocks = (e->nslices + 3) / 4;   // BLOCK = 128: four slices per thread block
       e->n_jlong = (int)jlong.size();
+      if (e->jstream) {
+        // persistent warps: js_wps warps on each SM, every warp owns a contiguous range of slices = one contiguous piece
+        // of the entry stream.  Ranges are balanced by cost (entries + a fixed share per slice for descriptors, own data
+        // and the vertex phase).  The slice table ends with a sentinel carrying the end of the last slice's entries.
+        const long long slice_end = jlong.empty() ? (long long)order.size() : (long long)jlong[0].x;
+        int nsm = 148;
+#ifndef ND_CUSIM
+        if (!e->host_only && !(d->flags & ND_B200_FLAG_HOST_ONLY)) {
+          int v = 0;
+          if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, e->device) == cudaSuccess && v > 0) nsm = v;
+        }
+#endif
+        const int nw = std::max(1, std::min(nsm * e->js_wps, e->nslices));
+        const long long fixed = 48;
+        long long total = 0;
+        for (int k = 0; k < e->nslices; ++k) total += ((k + 1 < e->nslices ? jslices[(size_t)k + 1].x : slice_end) - jslices[(size_t)k].x) + fixed;
+        e->h_jwarp.clear();
+        long long accum = 0;
+        int k0 = 0;
+        for (int wi = 0; wi < nw && e->nslices > 0; ++wi) {
+          const long long target = total * (wi + 1) / nw;
+          int k1 = k0;
+          while (k1 < e->nslices && (accum < target || k1 == k0) && (e->nslices - k1) > (nw - 1 - wi)) {
+            accum += ((k1 + 1 < e->nslices ? jslices[(size_t)k1 + 1].x : slice_end) - jslices[(size_t)k1].x) + fixed;
+            ++k1;
+          }
+          if (wi == nw - 1) k1 = e->nslices;
+          e->h_jwarp.push_back(make_int2(k0, k1));
+          k0 = k1;
+        }
+        e->n_jwarps = (int)e->h_jwarp.size();
+        jslices.push_back(make_int4((int)slice_end, 0, 0, 1));
+      }
       e->nblocks = e->n_jag_blocks + e->n_jlong;
       e->n_long = e->n_jlong;
     }
@@ -1333,12 +1525,18 @@ struct EngineBuilder {
         return ND_B200_ECUDA;
       if (jag_pe ? upload(e, &e->d_jent, jent) : upload(e, &e->d_jnbr, jnbr)) return ND_B200_ECUDA;
       if (!jebid.empty() && upload(e, &e->d_jebid, jebid)) return ND_B200_ECUDA;
+      if (e->jstream) {
+        if (upload(e, &e->d_jwarp, e->h_jwarp)) return ND_B200_ECUDA;
+        KParams P0;
+        fill_params(e, P0);
+        CUDA_TRY(e, launch_js(e, P0, nullptr, true));
+      }
       if (!e->gather_from_u) {
         for (int k = 0; k < 2; ++k) CUDA_TRY(e, cudaMalloc((void**)&e->d_vout[k], sizeof(double) * (size_t)(e->nrows_total * e->vdepth)));
       }
       return ND_B200_OK;
     }
-    if (upload(e, &e->d_rowptr, h_rowptr) || upload(e, &e->d_nbr, h_nbr) || upload(e, &e->d_blk_row, blk_row) ||
+    if (upload(e, &e->d_rowptr, h_rowptr) || upload(e, &e->d_nbr, e->compact ? h_nbr_c : h_nbr) || upload(e, &e->d_blk_row, blk_row) ||
         upload(e, &e->d_vb, dvb) || upload(e, &e->d_eb, deb))
       return ND_B200_ECUDA;
     if (any_epar && upload(e, &e->d_epar, h_epar)) return ND_B200_ECUDA;
@@ -1530,6 +1728,7 @@ void nd_b200_destroy(nd_b200_engine* e) {
   cudaFree(e->d_eebid); cudaFree(e->d_oedge);
   if (e->c_lib) cudaLibraryUnload(e->c_lib);
   cudaFree(e->d_jslices); cudaFree(e->d_jlanes); cudaFree(e->d_jnbr); cudaFree(e->d_jent); cudaFree(e->d_jebid); cudaFree(e->d_jlong);
+  cudaFree(e->d_jwarp);
   for (auto& ob : e->ode) { cudaFree(ob.d_es); cudaFree(ob.d_et); cudaFree(ob.d_ext); }
   for (int* q : e->d_vext) cudaFree(q);
   for (int* q : e->d_ffin) cudaFree(q);
@@ -1590,7 +1789,7 @@ int nd_b200_rhs_host(nd_b200_engine* e, double* du_host, const double* u_host, c
   for (int k = 0; k < K; ++k) cum[(size_t)k + 1] = (k == K - 1) ? 1.0 : 1.0 - std::ldexp(1.0, -(k + 1));
   const int nblk = (int)e->blk_pmax.size();
   const double last = std::ldexp(1.0, -(K - 1));   // fraction of the smallest piece
-  const bool pipelined = K > 1 && e->gather_from_u && !e->split && e->ode.empty() && (double)pb * last >= 16384.0 && (double)nblk * last >= 8.0 &&
+  const bool pipelined = K > 1 && e->gather_from_u && !e->split && !e->jstream && e->ode.empty() && (double)pb * last >= 16384.0 && (double)nblk * last >= 8.0 &&
                          nblk == e->nblocks && (e->row_end - e->row_begin == e->nrows_total);
   if (!pipelined) {
     CUDA_TRY(e, cudaMemcpyAsync(e->d_hu, u_host, nb, cudaMemcpyHostToDevice, st));
@@ -1661,21 +1860,22 @@ int nd_b200_pack_params(nd_b200_engine* e, const double* p, void* stream) {
   if (e->host_only) return fail(e, ND_B200_EUNSUPPORTED, "host-only engine");
   if (!p) { e->pack_on = false; return ND_B200_OK; }
   if (e->pack_pe <= 0 || e->split) return fail(e, ND_B200_EUNSUPPORTED, "packed edge parameters need ONE registry edge batch with parameters and a fused kernel");
-  if (e->jag ? e->jag_u != 2 : (e->block != 128 || e->ept != 4)) return fail(e, ND_B200_EUNSUPPORTED, "packed edge parameters are compiled for the default launch shape only");
+  if (e->jstream ? false : (e->jag ? (e->jag_u != 2 && (e->vdepth != 1 || e->halo_base != INT_MAX)) : (e->block != 128 || e->ept != 4))) return fail(e, ND_B200_EUNSUPPORTED, "packed edge parameters are compiled for the default launch shape only");
   if (e->nentries == 0) return ND_B200_OK;
   CUDA_TRY(e, cudaSetDevice(e->device));
   cudaStream_t st = (cudaStream_t)stream;
-  if (!e->d_ppack) CUDA_TRY(e, cudaMalloc((void**)&e->d_ppack, sizeof(double) * (size_t)e->nentries * (size_t)e->pack_pe));
+  const long long plen = e->jag ? e->jag_len : e->nentries;     // the streamed layout pads its slices
+  if (!e->d_ppack) CUDA_TRY(e, cudaMalloc((void**)&e->d_ppack, sizeof(double) * (size_t)plen * (size_t)e->pack_pe));
   const int T = 256;
-  const int nb = (int)((e->nentries + T - 1) / T);
+  const int nb = (int)((plen + T - 1) / T);
   if (e->jag) {
     if (!e->d_jnbr) {   // the PK kernels read a plain neighbour stream: extract it once from the {nbr, epar} pairs
-      CUDA_TRY(e, cudaMalloc((void**)&e->d_jnbr, sizeof(int) * (size_t)e->nentries));
-      ND_LAUNCH(nb, T, st, ((const int*)e->d_jent, e->nentries, e->d_jnbr), extract_nbr_kernel);
+      CUDA_TRY(e, cudaMalloc((void**)&e->d_jnbr, sizeof(int) * (size_t)plen));
+      ND_LAUNCH(nb, T, st, ((const int*)e->d_jent, plen, e->d_jnbr), extract_nbr_kernel);
       CUDA_TRY(e, cudaGetLastError());
       e->launches++;
     }
-    ND_LAUNCH(nb, T, st, ((const int*)e->d_jent, 2, 1, e->nentries, e->pack_pe, p, e->d_ppack), pack_params_kernel);
+    ND_LAUNCH(nb, T, st, ((const int*)e->d_jent, 2, 1, plen, e->pack_pe, p, e->d_ppack), pack_params_kernel);
   } else {
     ND_LAUNCH(nb, T, st, (e->d_epar, 1, 0, e->nentries, e->pack_pe, p, e->d_ppack), pack_params_kernel);
   }
@@ -1775,7 +1975,8 @@ int nd_b200_rk4(nd_b200_engine* e, double* u, const double* p, double t0, double
     // default: only where the gain does not depend on a measurement -- a parameter vector far beyond the 126 MB L2, whose
     // per-entry reads are isolated DRAM sectors, and enough stages to amortise the one packing pass
     const char* s = getenv("ND_B200_RK4_PACK");
-    const bool want = s ? atoi(s) > 0 : (sizeof(double) * (size_t)e->lastidx_p >= ((size_t)256 << 20) && nsteps >= 4);
+    // measured (profiles/r02d): 207 vs 266 us per step on config 2, 275 vs 329 us on Kuramoto / Erdos-Renyi
+    const bool want = s ? atoi(s) > 0 : nsteps >= 4;
     if (want && nd_b200_pack_params(e, p, stream) == ND_B200_OK) unpack.on = true;
   }
   if (!e->gather_from_u && !e->custom) CUDA_TRY(e, launch_vout(e, u, p, e->d_vout[0], st, t0));
@@ -1849,6 +2050,14 @@ int nd_b200_export_jag(const nd_b200_engine* e, int32_t* slices, uint16_t* lanes
 }
 
 const char* nd_b200_custom_source(const nd_b200_engine* e) { return (e && e->custom) ? e->custom_src.c_str() : nullptr; }
+
+const char* nd_b200_kernel_name(const nd_b200_engine* e) {
+  if (!e) return "";
+  if (e->jstream) return "rhs_js_kernel";
+  if (e->jag) return "rhs_jag_kernel";
+  if (e->split) return "edge_pass_kernel+row_pass_kernel";
+  return "rhs_fused_kernel";
+}
 
 int64_t nd_b200_launch_count(const nd_b200_engine* e) { return e ? e->launches : 0; }
 

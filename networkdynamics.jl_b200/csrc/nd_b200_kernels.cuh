@@ -154,6 +154,9 @@ struct KParams {
   const uint8_t* __restrict__ jebid;   // per entry edge batch id (EK_GENERIC)
   const int4* __restrict__ jlong;      // rows reduced by a whole block {entry base, row, entries, vertex batch}
   int nslices, n_jag_blocks;
+  // streamed jagged kernel (rhs_js_kernel): every warp of the (persistent) grid owns the contiguous slices [x, y)
+  const int2* __restrict__ jwarp;
+  int n_jwarps, n_jlong;
   // multi-GPU packed halo (jagged kernel only): gather offsets >= halo_base address the halo buffer that the peers'
   // publish kernels fill with exactly the remote vertex outputs this rank's rows read; slices >= wait_from_slice
   // (the ones that read remote outputs) wait for the arrival flags, interior slices run while the halo is in flight
@@ -537,21 +540,35 @@ __device__ __forceinline__ const double* gather_ptr(const KParams& P, int off) {
 // latency with many independent blocks), so registers are capped through the min-blocks launch bound.
 // Measured on B200 (profiles/r01_tuning.md): 64 resident warps/SM (32 registers) is best for the arithmetic-free
 // diffusion kernels, 48 warps/SM (40 registers) for the kernels that evaluate sin / complex division.
-__host__ __device__ constexpr int fused_warps_per_sm(int ek) {
-  return (ek == ND_B200_E_DIFFUSION || ek == ND_B200_E_DIFFUSION_NOP) ? 64 : 48;
+__host__ __device__ constexpr int fused_warps_per_sm(int ek, bool pk = false) {
+  // packed-parameter kernels hold their EPT parameters in registers from step (1) on (the stream's DRAM latency overlaps
+  // the gather instead of following the second barrier): 40 registers
+  return ((ek == ND_B200_E_DIFFUSION || ek == ND_B200_E_DIFFUSION_NOP) && !pk) ? 64 : 48;
 }
 // HALO = true: the multi-GPU variant (publishing blocks, flag waits, gathers from [u | halo]); the single-GPU variant
 // carries none of it (the 32-register diffusion kernels lose 9-19 % when that code shares their register allocation).
 // PK = true: edge parameters come from the engine's packed per-entry copy (coalesced with the index stream; no parameter
 // offsets are read) -- valid while the caller guarantees p is unchanged since nd_b200_pack_params (nd_b200_rk4 packs per call).
-template <int VD, int ED, int EK, int PE, int BLOCK, int EPT, bool HALO, bool PK = false>
-__global__ void __launch_bounds__(BLOCK, (fused_warps_per_sm(EK) * 32) / BLOCK) rhs_fused_kernel(const __grid_constant__ KParams P) {
+// CR = true ("compact rows", networks whose gather offsets stay below 2^23, single edge batch): an entry word is
+//   offset | local row << 23 | side << 30
+// so the entry threads know their row without the per-tile row-id table in shared memory (its byte scatter by the row
+// threads and the per-entry look-up were 1.7 M of the 5.5 M shared-memory wavefronts on config 2, profiles/r02c).
+constexpr int ND_CR_OFF_BITS = 23;
+template <int VD, int ED, int EK, int PE, int BLOCK, int EPT, bool HALO, bool PK = false, bool CR = false>
+__global__ void __launch_bounds__(BLOCK, (fused_warps_per_sm(EK, PK && PE == 1) * 32) / BLOCK) rhs_fused_kernel(const __grid_constant__ KParams P) {
+  static_assert(!CR || (EK != EK_GENERIC && BLOCK <= 128), "compact rows: 7 bits of local row, no state-entry flag");
   constexpr int TILE = BLOCK * EPT;
   static_assert(BLOCK <= 256, "row ids are stored as uint8");
-  __shared__ double s_val[TILE * ED];
+  // entry jj of local row r is staged at slot jj + r: one slot of padding per row.  The ordered row sums of step (6) read
+  // slot a_r + j + r from lane r; with row starts a_r ~ 8 r (mean degree 8) the unpadded layout puts the 16 lanes of a
+  // half warp on two 8-byte banks (8-way conflict, profiles/r01b: a third of the kernel's L1TEX wavefronts were shared
+  // memory); the skew spreads them over all 16.
+  // (only in the 40-register packed-parameter kernels: in the 32-register ones the extra index arithmetic spills)
+  constexpr int SKEW = (PK && PE == 1) ? 1 : 0;
+  __shared__ double s_val[(TILE + SKEW * BLOCK) * ED];
   __shared__ double s_self[BLOCK * VD];
   __shared__ int s_rp[BLOCK + 1];
-  __shared__ uint8_t s_rowid[TILE];
+  __shared__ uint8_t s_rowid[CR ? 4 : TILE];
 
   const int tid = threadIdx.x;
   if constexpr (HALO) {
@@ -582,8 +599,9 @@ __global__ void __launch_bounds__(BLOCK, (fused_warps_per_sm(EK) * 32) / BLOCK) 
     for (int q = 0; q < ED; ++q) part[q] = 0.0;
     for (int jj = tid; jj < ne; jj += BLOCK) {
       int nb = P.nbr[e0 + jj];
-      const int side = nb < 0;
-      nb = side ? ~nb : nb;
+      int side;
+      if constexpr (CR) { side = (nb >> 30) & 1; nb &= (1 << ND_CR_OFF_BITS) - 1; }
+      else { side = nb < 0; nb = side ? ~nb : nb; }
       bool st = false;
       if constexpr (EK == EK_GENERIC) { st = P.state_edges && (nb & ND_STATE_ENTRY_BIT); nb &= ~ND_STATE_ENTRY_BIT; }
       double xn[VD];
@@ -632,13 +650,16 @@ __global__ void __launch_bounds__(BLOCK, (fused_warps_per_sm(EK) * 32) / BLOCK) 
   // random gathers, and occupancy (many independent blocks in different phases) is what keeps L2 busy.
   // (1) coalesced index loads, issued first so they overlap the row bookkeeping
   int nb[EPT], ep[EPT];
+  double pk1[(PK && PE == 1) ? EPT : 1];       // packed single parameters: loaded with the indices
 #pragma unroll
   for (int k = 0; k < EPT; ++k) {
     const int jj = k * BLOCK + tid;
     nb[k] = 0; ep[k] = 0;
+    if constexpr (PK && PE == 1) pk1[k] = 0.0;
     if (jj < ne) {
       nb[k] = P.nbr[e0 + jj];
       if constexpr (PE > 0 && !PK) ep[k] = P.epar[e0 + jj];
+      if constexpr (PK && PE == 1) pk1[k] = P.ppack[e0 + jj];
     }
   }
   // (2) row pointers + own outputs of the block's rows
@@ -651,17 +672,19 @@ __global__ void __launch_bounds__(BLOCK, (fused_warps_per_sm(EK) * 32) / BLOCK) 
   }
   if (tid == 0) s_rp[nrows] = ne;
   __syncthreads();
-  // (3) entry -> local row map
-  if (tid < nrows) {
-    const int a = s_rp[tid], z = s_rp[tid + 1];
-    for (int jj = a; jj < z; ++jj) s_rowid[jj] = (uint8_t)tid;
+  // (3) entry -> local row map (compact rows: carried by the entry word)
+  if constexpr (!CR) {
+    if (tid < nrows) {
+      const int a = s_rp[tid], z = s_rp[tid + 1];
+      for (int jj = a; jj < z; ++jj) s_rowid[jj] = (uint8_t)tid;
+    }
   }
   // (4) the gather: EPT independent random reads per thread
   double xn[EPT][VD];
 #pragma unroll
   for (int k = 0; k < EPT; ++k) {
     const int jj = k * BLOCK + tid;
-    const int off = nb[k] < 0 ? ~nb[k] : nb[k];
+    const int off = CR ? (nb[k] & ((1 << ND_CR_OFF_BITS) - 1)) : (nb[k] < 0 ? ~nb[k] : nb[k]);
 #pragma unroll
     for (int q = 0; q < VD; ++q) xn[k][q] = 0.0;
     bool st = false;   // entry of an edge with states: read in step (5) from u
@@ -683,14 +706,14 @@ __global__ void __launch_bounds__(BLOCK, (fused_warps_per_sm(EK) * 32) / BLOCK) 
   for (int k = 0; k < EPT; ++k) {
     const int jj = k * BLOCK + tid;
     if (jj < ne) {
-      const int side = nb[k] < 0;
-      const int r = s_rowid[jj];
+      const int side = CR ? ((nb[k] >> 30) & 1) : (nb[k] < 0);
+      const int r = CR ? ((nb[k] >> ND_CR_OFF_BITS) & 127) : (int)s_rowid[jj];
       double self[VD];
 #pragma unroll
       for (int q = 0; q < VD; ++q) self[q] = s_self[r * VD + q];
       int kind = EK, coupling = coupling0;
       bool st = false;
-      int off = side ? ~nb[k] : nb[k];
+      int off = CR ? 0 : (side ? ~nb[k] : nb[k]);
       if constexpr (EK == EK_GENERIC) {
         const EBDev E = P.eb[P.ebid[e0 + jj]];
         kind = E.kind; coupling = E.coupling;
@@ -699,9 +722,9 @@ __global__ void __launch_bounds__(BLOCK, (fused_warps_per_sm(EK) * 32) / BLOCK) 
       }
       double val[ED];
       if (st) state_entry_value<ED>(P.u, coupling, side, off, val);
-      else entry_value<VD, ED>(kind, coupling, side, self, xn[k], PK ? P.ppack + (long long)(e0 + jj) * PE : P.p + ep[k], P.t, val);
+      else entry_value<VD, ED>(kind, coupling, side, self, xn[k], (PK && PE == 1) ? &pk1[k] : (PK ? P.ppack + (long long)(e0 + jj) * PE : P.p + ep[k]), P.t, val);
 #pragma unroll
-      for (int q = 0; q < ED; ++q) s_val[jj * ED + q] = val[q];
+      for (int q = 0; q < ED; ++q) s_val[(jj + SKEW * r) * ED + q] = val[q];
     }
   }
   __syncthreads();
@@ -710,7 +733,7 @@ __global__ void __launch_bounds__(BLOCK, (fused_warps_per_sm(EK) * 32) / BLOCK) 
     double acc[ED];
 #pragma unroll
     for (int q = 0; q < ED; ++q) acc[q] = 0.0;
-    const int a = s_rp[tid], z = s_rp[tid + 1];
+    const int a = s_rp[tid] + SKEW * tid, z = s_rp[tid + 1] + SKEW * tid;
     for (int jj = a; jj < z; ++jj) {
 #pragma unroll
       for (int q = 0; q < ED; ++q) acc[q] = acc[q] + s_val[jj * ED + q];
@@ -1173,39 +1196,58 @@ __global__ void __launch_bounds__(BLOCK, (WPS * 32) / BLOCK) rhs_jag_kernel(cons
 #pragma unroll
   for (int q = 0; q < ED; ++q) acc[q] = 0.0;
 
+  // The walk is software-pipelined: the index (and packed-parameter) loads of columns j+U .. j+2U-1 are issued BEFORE the
+  // gathers of columns j .. j+U-1 are waited for, so an iteration exposes one memory latency (the gather) instead of two
+  // dependent ones (index, then gather) -- profiles/r02b_jag128_packed: 22 % of the stall samples sat on the index load,
+  // 32 % on the gather.
   int base = S.x;
-  for (int j = 0;; j += U) {
+  bool actA[U];
+  int nbA[U], epA[U], posA[U];
+  double plA[U][PE > 0 ? PE : 1];
+  // stage A: slots of this lane in columns j .. j+U-1 and their coalesced index / packed-parameter loads
+  auto fetch = [&](int j) -> bool {
     const unsigned m0 = __ballot_sync(0xffffffffu, j < len);
-    if (m0 == 0u) break;
-    // (1) slots of this lane in the next U columns
-    int pos[U];
-    bool act[U];
+    if (m0 == 0u) return false;
 #pragma unroll
     for (int q = 0; q < U; ++q) {
-      act[q] = (j + q) < len;
-      const unsigned m = q == 0 ? m0 : __ballot_sync(0xffffffffu, act[q]);
-      pos[q] = base + __popc(m & lt);
+      actA[q] = (j + q) < len;
+      const unsigned m = q == 0 ? m0 : __ballot_sync(0xffffffffu, actA[q]);
+      posA[q] = base + __popc(m & lt);
       base += __popc(m);
-    }
-    // (2) coalesced index loads
-    int nb[U], ep[U];
+      nbA[q] = 0; epA[q] = 0;
 #pragma unroll
-    for (int q = 0; q < U; ++q) {
-      nb[q] = 0; ep[q] = 0;
-      if (act[q]) {
-        if constexpr (PE > 0 && !PK) { const int2 t2 = __ldcs(&P.jent[pos[q]]); nb[q] = t2.x; ep[q] = t2.y; }
-        else nb[q] = __ldcs(&P.jnbr[pos[q]]);
+      for (int k = 0; k < (PE > 0 ? PE : 1); ++k) plA[q][k] = 0.0;
+      if (actA[q]) {
+        if constexpr (PE > 0 && !PK) { const int2 t2 = __ldcs(&P.jent[posA[q]]); nbA[q] = t2.x; epA[q] = t2.y; }
+        else nbA[q] = __ldcs(&P.jnbr[posA[q]]);
+        if constexpr (PE > 0 && PK) {
+#pragma unroll
+          for (int k = 0; k < PE; ++k) plA[q][k] = __ldcs(&P.ppack[(long long)posA[q] * PE + k]);
+        }
       }
     }
-    // (3) the gathers and the edge parameters: 2U independent random reads per lane
-    double xn[U][VD], pl[U][PE > 0 ? PE : 1];
+    return true;
+  };
+  bool more = fetch(0);
+  for (int j = 0; more; j += U) {
+    // stage B operands of this iteration
+    bool act[U];
+    int nb[U], ep[U], pos[U];
+    double pl[U][PE > 0 ? PE : 1];
+#pragma unroll
+    for (int q = 0; q < U; ++q) {
+      act[q] = actA[q]; nb[q] = nbA[q]; ep[q] = epA[q]; pos[q] = posA[q];
+#pragma unroll
+      for (int k = 0; k < (PE > 0 ? PE : 1); ++k) pl[q][k] = plA[q][k];
+    }
+    // (3) the gathers and the live edge parameters: up to 2U independent random reads per lane
+    double xn[U][VD];
     int kind[U], coupling[U];
 #pragma unroll
     for (int q = 0; q < U; ++q) {
       const int off = nb[q] < 0 ? ~nb[q] : nb[q];
 #pragma unroll
       for (int k = 0; k < VD; ++k) xn[q][k] = 0.0;
-      pl[q][0] = 0.0;
       kind[q] = EK; coupling[q] = coupling0;
       bool st = false;   // entry of an edge with states: read in step (4) from u
       if constexpr (EK == EK_GENERIC) st = P.state_edges && (off & ND_STATE_ENTRY_BIT);
@@ -1225,12 +1267,15 @@ __global__ void __launch_bounds__(BLOCK, (WPS * 32) / BLOCK) rhs_jag_kernel(cons
           const EBDev E = P.eb[P.jebid[pos[q]]];
           kind[q] = E.kind; coupling[q] = E.coupling; pd = E.pdim;
         }
-        if constexpr (PE > 0) {
+        if constexpr (PE > 0 && !PK) {
 #pragma unroll
-          for (int k = 0; k < PE; ++k) pl[q][k] = PK ? __ldcs(&P.ppack[(long long)pos[q] * PE + k]) : (k < pd ? P.p[(long long)ep[q] + k] : 0.0);
+          for (int k = 0; k < PE; ++k) pl[q][k] = k < pd ? P.p[(long long)ep[q] + k] : 0.0;
         }
       }
     }
+    // stage A of the NEXT iteration, in flight while this iteration's gathers return (one output per vertex; the dq
+    // kernels' two-component gathers leave no registers for it: measured slower, profiles/r02d)
+    if constexpr (VD == 1) more = fetch(j + U);
     // (4) edge model + sequential accumulation in entry order
 #pragma unroll
     for (int q = 0; q < U; ++q) {
@@ -1245,6 +1290,7 @@ __global__ void __launch_bounds__(BLOCK, (WPS * 32) / BLOCK) rhs_jag_kernel(cons
         for (int d = 0; d < ED; ++d) acc[d] = acc[d] + val[d];
       }
     }
+    if constexpr (VD != 1) more = fetch(j + U);
   }
   // (5) rows cut into several lanes: the head lane adds the parts in order
   if (S.w > 1) {
@@ -1267,6 +1313,240 @@ __global__ void __launch_bounds__(BLOCK, (WPS * 32) / BLOCK) rhs_jag_kernel(cons
     double v[ND_MAX_VDIM];
     load_vertex_state(P, B, row, v);
     vertex_phase<VD, ED>(P, B, row, acc, self, v, P.p + B.p0 + (long long)(row - B.row0) * B.pdim);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// streamed jagged kernel: the jagged warp-slice walk of rhs_jag_kernel, fed by TMA bulk copies.
+//
+// Why (profiles/r02b_jag128_packed_cfg2_ncu_summary.txt, B200): rhs_jag_kernel issues only 47 K L1TEX wavefronts per SM on
+// config 2 (the tile kernel: 100 K) but keeps the L1TEX data pipe 45 % busy: every warp lives for ONE slice and walks a
+// chain of dependent long-latency loads -- slice descriptor -> lane descriptor -> own state, then per iteration index ->
+// gather -- so the kernel is bound by exposed latency (long scoreboard 21 per issue, 0.5 eligible warps per scheduler),
+// not by the gather rate (profiles/r02a_*: 0.83 random gathers per clock per SM, the LSU tag stage).  Here
+//   * warps are persistent: a warp owns a contiguous range of slices, i.e. ONE contiguous piece of the index / parameter
+//     streams;
+//   * that piece is streamed into a per-warp ring in shared memory by cp.async.bulk (TMA, SASS UBLKCP) in chunks of
+//     JS_CHUNK entries, NST chunks deep, completion on one mbarrier per chunk: the coalesced streams never pass through
+//     the LSU pipe as global loads and are in flight many iterations ahead of their use;
+//   * the index of a gather is then a 30-cycle shared-memory read, so the only long-latency load on the critical path
+//     is the gather itself, U of them in flight per lane;
+//   * descriptors, own state and vertex parameters of the NEXT slice are prefetched into registers.
+// Layout = the degree-bucketed jagged layout (window 128), every slice padded to a multiple of 4 entries (16-byte
+// alignment of the bulk copies).  Row sums stay in registers, in the reference's sequential order
+// (src/aggregators.jl:140-151).  Instantiated for the single-batch benchmark edge kinds with vdepth = edepth = 1.
+// ------------------------------------------------------------------------------------------------
+constexpr int JS_BLOCK = 128;
+constexpr int JS_CHUNK = 128;
+#ifdef ND_CUSIM
+#define ND_DYN_SMEM(name) static thread_local __attribute__((aligned(128))) unsigned char name[232448]
+__device__ __forceinline__ void js_bar_init(unsigned long long* bar) { *bar = 0; }
+__device__ __forceinline__ void js_fence_init() {}
+__device__ __forceinline__ void js_expect(unsigned long long*, unsigned) {}
+__device__ __forceinline__ void js_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long*) { memcpy(dst, src, bytes); }
+__device__ __forceinline__ void js_wait(unsigned long long*, unsigned) {}
+#else
+#define ND_DYN_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
+__device__ __forceinline__ unsigned js_smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void js_bar_init(unsigned long long* bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(js_smem_addr(bar)), "r"(1) : "memory");
+}
+__device__ __forceinline__ void js_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void js_expect(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(js_smem_addr(bar)), "r"(bytes) : "memory");
+}
+// global -> shared bulk copy (TMA); bytes and both addresses are multiples of 16
+__device__ __forceinline__ void js_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(js_smem_addr(dst)), "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(js_smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void js_wait(unsigned long long* bar, unsigned parity) {
+  const unsigned a = js_smem_addr(bar);
+  unsigned ok = 0;
+  do {
+    asm volatile("{ .reg .pred q; mbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2; selp.u32 %0, 1, 0, q; }"
+                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+  } while (!ok);
+}
+#endif
+
+__host__ __device__ constexpr int js_imin(int a, int b) { return a < b ? a : b; }
+__host__ __device__ constexpr int js_imax(int a, int b) { return a > b ? a : b; }
+__host__ __device__ constexpr int js_warp_bytes(int pe, bool pk, int nst) {
+  return nst * JS_CHUNK * ((pe > 0 && !pk) ? 8 : 4) + (pk ? nst * JS_CHUNK * 8 * pe : 0) + nst * 8;
+}
+
+template <int EK, int PE, bool PK, int U, int NST, int MINB>
+__global__ void __launch_bounds__(JS_BLOCK, MINB) rhs_js_kernel(const __grid_constant__ KParams P) {
+  constexpr bool LIVE = PE > 0 && !PK;          // parameters re-read from the caller's p through per-entry offsets
+  constexpr int RING = NST * JS_CHUNK;
+  constexpr int WB = js_warp_bytes(PE, PK, NST);
+  constexpr int IDXB = LIVE ? 8 : 4;
+  static_assert((NST & (NST - 1)) == 0 && NST >= 4 && U * 32 <= 2 * JS_CHUNK, "ring / unroll shape");
+  static_assert(PE <= 1, "one edge parameter at most (diffusion, Kuramoto)");
+  ND_DYN_SMEM(js_smem);
+  __shared__ double s_val[JS_BLOCK];            // long rows only
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  unsigned char* wbase = js_smem + wib * WB;
+  const int* r_nbr = reinterpret_cast<const int*>(wbase);
+  const int2* r_ent = reinterpret_cast<const int2*>(wbase);
+  const double* r_pk = reinterpret_cast<const double*>(wbase + RING * IDXB);
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(wbase + WB - NST * 8);
+  const int w = (int)blockIdx.x * (JS_BLOCK / 32) + wib;
+  int sb = 0, se = 0;
+  if (w < P.n_jwarps) { const int2 r = __ldg(&P.jwarp[w]); sb = r.x; se = r.y; }
+  const int coupling0 = P.n_eb > 0 ? P.eb[0].coupling : 0;
+  const unsigned lt = (1u << lane) - 1u;
+
+  if (sb < se) {
+    const int E0 = __ldg(&P.jslices[sb]).x, E1 = __ldg(&P.jslices[se]).x;     // jslices ends with a sentinel
+    const int etot = E1 - E0, nchunks = (etot + JS_CHUNK - 1) / JS_CHUNK;
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < NST; ++k) js_bar_init(bars + k);
+      js_fence_init();
+    }
+    __syncwarp();
+    int issued = 0, ready = 0;
+    // lane 0 starts the bulk copies of chunks [issued, lim); every lane tracks the count
+    auto issue_upto = [&](int lim) {
+      if (lane == 0) {
+        for (int c = issued; c < lim; ++c) {
+          const int st = c & (NST - 1);
+          const int n = js_imin(JS_CHUNK, etot - c * JS_CHUNK);       // multiple of 4
+          js_expect(bars + st, (unsigned)(n * IDXB + (PK ? n * 8 * PE : 0)));
+          const void* src = LIVE ? (const void*)(P.jent + E0 + (long long)c * JS_CHUNK) : (const void*)(P.jnbr + E0 + (long long)c * JS_CHUNK);
+          js_bulk_g2s(wbase + st * JS_CHUNK * IDXB, src, (unsigned)(n * IDXB), bars + st);
+          if constexpr (PK)
+            js_bulk_g2s(wbase + RING * IDXB + st * JS_CHUNK * 8 * PE, P.ppack + (long long)(E0 + (long long)c * JS_CHUNK) * PE, (unsigned)(n * 8 * PE), bars + st);
+        }
+      }
+      issued = js_imax(issued, lim);
+    };
+    issue_upto(js_imin(nchunks, NST));
+
+    // register prefetch: descriptors two slices ahead, own state / vertex parameters one slice ahead
+    int4 S0 = __ldg(&P.jslices[sb]);
+    unsigned d0 = __ldg(&P.jlanes[(long long)sb * 32 + lane]);
+    int4 S1 = S0; unsigned d1 = 0;
+    if (sb + 1 < se) { S1 = __ldg(&P.jslices[sb + 1]); d1 = __ldg(&P.jlanes[(long long)(sb + 1) * 32 + lane]); }
+    int curb = S0.z;
+    VBDev B = P.vb[curb];
+    double v0[ND_MAX_VDIM], pv0[4], v1[ND_MAX_VDIM], pv1[4];
+    auto load_own = [&](const VBDev& Bx, const int4& Sx, unsigned dx, double* v, double* pv) {
+#pragma unroll
+      for (int c = 0; c < ND_MAX_VDIM; ++c) v[c] = 0.0;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) pv[c] = 0.0;
+      if ((dx >> 14) & 1) {
+        const long long i = (long long)(Sx.y + (int)((dx >> 6) & 127)) - Bx.row0;
+        const long long so = Bx.state0 + i * Bx.dim;
+#pragma unroll
+        for (int c = 0; c < ND_MAX_VDIM; ++c) if (c < Bx.dim) v[c] = P.u[so + c];
+        if ((dx >> 13) & 1) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) if (c < Bx.pdim) pv[c] = P.p[Bx.p0 + i * Bx.pdim + c];
+        }
+      }
+    };
+    load_own(B, S0, d0, v0, pv0);
+
+    for (int s = sb; s < se; ++s) {
+      // prefetch: descriptors of s+2, own data of s+1 (same vertex batch; a batch change reloads at the top of s+1)
+      int4 S2 = S1; unsigned d2 = 0;
+      if (s + 2 < se) { S2 = __ldg(&P.jslices[s + 2]); d2 = __ldg(&P.jlanes[(long long)(s + 2) * 32 + lane]); }
+      const bool pre1 = (s + 1 < se) && S1.z == curb;
+      if (pre1) load_own(B, S1, d1, v1, pv1);
+
+      const int len = d0 & 63;
+      const int row = S0.y + (int)((d0 >> 6) & 127);
+      const bool head = (d0 >> 13) & 1, valid = (d0 >> 14) & 1;
+      const double self = v0[0];
+      double acc = 0.0;
+      int base = S0.x - E0;
+      for (int j = 0;; j += U) {
+        const unsigned m0 = __ballot_sync(0xffffffffu, j < len);
+        if (m0 == 0u) break;
+        int pos[U];
+        bool act[U];
+#pragma unroll
+        for (int q = 0; q < U; ++q) {
+          act[q] = (j + q) < len;
+          const unsigned m = q == 0 ? m0 : __ballot_sync(0xffffffffu, act[q]);
+          pos[q] = (base + __popc(m & lt)) & (RING - 1);
+          base += __popc(m);
+        }
+        // the chunks that hold entries below `base` must have landed
+        const int need = (base + JS_CHUNK - 1) / JS_CHUNK;
+        while (ready < need) { js_wait(bars + (ready & (NST - 1)), (unsigned)((ready / NST) & 1)); ++ready; }
+        int nb[U], ep[U];
+        double pl[U];
+#pragma unroll
+        for (int q = 0; q < U; ++q) {
+          nb[q] = 0; ep[q] = 0; pl[q] = 0.0;
+          if (act[q]) {
+            if constexpr (LIVE) { const int2 t2 = r_ent[pos[q]]; nb[q] = t2.x; ep[q] = t2.y; }
+            else nb[q] = r_nbr[pos[q]];
+            if constexpr (PK) pl[q] = r_pk[pos[q] * PE];
+          }
+        }
+        double xn[U];
+#pragma unroll
+        for (int q = 0; q < U; ++q) {
+          xn[q] = 0.0;
+          if (act[q]) {
+            xn[q] = P.gsrc[nb[q] < 0 ? ~nb[q] : nb[q]];
+            if constexpr (LIVE) pl[q] = P.p[ep[q]];
+          }
+        }
+        // ring slots below `base` rounded down to a chunk are free again: refill them
+        __syncwarp();
+        issue_upto(js_imin(nchunks, base / JS_CHUNK + NST));
+#pragma unroll
+        for (int q = 0; q < U; ++q) {
+          if (act[q]) {
+            double val;
+            entry_value<1, 1>(EK, coupling0, nb[q] < 0, &self, &xn[q], &pl[q], P.t, &val);
+            acc = acc + val;
+          }
+        }
+      }
+      // rows cut into several lanes: the head lane adds the parts in order
+      if (S0.w > 1) {
+        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+        const unsigned hmask = __ballot_sync(0xffffffffu, head);
+        const unsigned cont = vmask & ~hmask;
+        const unsigned above = lane == 31 ? 0u : (~cont >> (lane + 1));
+        const int nparts = 1 + (lane == 31 ? 0 : (above ? __ffs(above) - 1 : 31 - lane));
+        for (int k = 1; k < S0.w; ++k) {
+          const double vv = __shfl_down_sync(0xffffffffu, acc, k);
+          if (head && k < nparts) acc = acc + vv;
+        }
+      }
+      if (head) vertex_phase<1, 1>(P, B, row, &acc, &self, v0, pv0);
+      // rotate the prefetch registers
+      S0 = S1; d0 = d1; S1 = S2; d1 = d2;
+      if (s + 1 < se) {
+        if (pre1) {
+#pragma unroll
+          for (int c = 0; c < ND_MAX_VDIM; ++c) v0[c] = v1[c];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) pv0[c] = pv1[c];
+        } else {
+          curb = S0.z;
+          B = P.vb[curb];
+          load_own(B, S0, d0, v0, pv0);
+        }
+      }
+    }
+  }
+  // rows longer than a slice can hold: whole-block reduction, blocks take them round robin
+  if (P.n_jlong > 0) {
+    __syncthreads();
+    for (int q = (int)blockIdx.x; q < P.n_jlong; q += (int)gridDim.x) {
+      long_row_block<1, 1, EK, PE, JS_BLOCK, false, PK>(P, __ldg(&P.jlong[q]), s_val);
+      __syncthreads();
+    }
   }
 }
 

@@ -18,6 +18,7 @@ from dataclasses import dataclass
 from typing import List, Optional, Sequence
 
 import os
+import weakref
 
 import numpy as np
 
@@ -206,10 +207,18 @@ class B200Aggregator:
     (read as `nw.layer.aggregator.f`, test/testutils.jl:50)."""
 
     def __init__(self, f="+", *, device: Optional[int] = None, row_range=None, long_row_threshold: int = 0,
-                 keep_tables: bool = True, host_only: bool = False, gather_offset=None, gather_len: int = 0):
+                 keep_tables: bool = True, host_only: bool = False, gather_offset=None, gather_len: int = 0,
+                 edge_parameters: str = "auto"):
         if f not in ("+", sum, np.add) and getattr(f, "__name__", "") != "add":
             raise ArgumentError("B200Aggregator only supports + as the reducer (no CPU fallback for others)")
+        if edge_parameters not in ("auto", "live"):
+            raise ArgumentError("edge_parameters must be 'auto' or 'live'")
         self.f = "+"
+        # edge_parameters: "live" = every call re-reads the edge parameters from the caller's p through per-entry offsets;
+        # "auto" (default) = the same results, but when p is a device tensor that carries a modification counter (torch's
+        # `_version`) and two consecutive calls see the same unmodified p, the engine's packed per-entry copy is refreshed
+        # (nd_b200_pack_params) and used until p changes -- the explicit refresh of SURVEY.md section 7, made automatic.
+        self.edge_parameters = edge_parameters
         # host_only: build the engine's tables without touching a device (layout tests); such a network cannot be called
         # gather_offset / gather_len: multi-GPU packed halo layout (nd_b200_desc.gather_offset), see distributed.py
         self._opts = dict(device=device, row_range=row_range, long_row_threshold=long_row_threshold,
@@ -225,7 +234,7 @@ class B200Aggregator:
     def __call__(self, im: IndexManager, edgebatches: List[ComponentBatch]):
         """`aggregator(im, edgebatches)`; the vertex batches are read from the fully populated IndexManager
         (in Julia: rebuilt from im.v_* and im.vertexm, which are complete at src/construction.jl:198)."""
-        agg = B200Aggregator(self.f, **self._opts)
+        agg = B200Aggregator(self.f, edge_parameters=self.edge_parameters, **self._opts)
         agg._build(im, im.vertexbatches, edgebatches)
         return agg
 
@@ -348,7 +357,7 @@ class B200Aggregator:
 
 def get_aggr_constructor(agg: B200Aggregator):
     """src/aggregators.jl:287-292: recover the constructor closure from a built aggregator."""
-    return B200Aggregator(agg.f, **agg._opts)
+    return B200Aggregator(agg.f, edge_parameters=agg.edge_parameters, **agg._opts)
 
 
 def _current_device() -> int:
@@ -529,12 +538,55 @@ class Network:
         if len(kinds) != 1:
             raise ArgumentError("du, u and p must all live on the device or all on the host")
         if kinds.pop():
+            self._auto_pack(p, a_p, stream)
             rc = self._L.nd_b200_rhs(self.handle, a_du, a_u, a_p, float(t), _stream_handle(stream))
         else:
             rc = self._L.nd_b200_rhs_host(self.handle, a_du, a_u, a_p, float(t))
         if rc:
             self._fail(rc)
         return None
+
+    def _auto_pack(self, p, a_p, stream):
+        """edge_parameters="auto": keep the engine's packed copy of the edge parameters in step with p.  Reference
+        semantics are preserved -- p may be changed between calls (callbacks, docs/examples/cascading_failure.jl:107-110);
+        every in-place change of a torch tensor bumps its `_version`, which invalidates the packed copy.  The copy is only
+        (re)built when the SAME unmodified p is seen on two consecutive calls (an integrator's stages), so a parameter
+        vector that changes on every call never pays for packing."""
+        st = self.__dict__.setdefault("_pack_state", {"manual": False, "packable": True, "packed": None, "last": None})
+        if st["manual"] or not st["packable"] or p is None:
+            return
+        if getattr(self.layer.aggregator, "edge_parameters", "live") != "auto":
+            return
+        ver = getattr(p, "_version", None)
+        if ver is None:
+            return
+        # identity = the tensor OBJECT (held weakly: a new tensor that the caching allocator places at the same address
+        # with the same counter is a different p), its address and its modification counter
+        key = (a_p, int(ver))
+        try:
+            same_obj = st.get("ref") is not None and st["ref"]() is p
+            if not same_obj:
+                st["ref"] = weakref.ref(p)
+        except TypeError:
+            return
+        if not same_obj:                # another parameter vector: forget the packed copy, start counting afresh
+            if st["packed"] is not None:
+                self._L.nd_b200_pack_params(self.handle, None, _stream_handle(stream))
+                st["packed"] = None
+            st["last"] = key
+            return
+        if st["packed"] == key:
+            pass
+        elif st["last"] == key:
+            rc = self._L.nd_b200_pack_params(self.handle, a_p, _stream_handle(stream))
+            if rc:                      # no packed kernels for this network (several edge batches, user-supplied kinds ...)
+                st["packable"] = False
+            else:
+                st["packed"] = key
+        elif st["packed"] is not None:
+            self._L.nd_b200_pack_params(self.handle, None, _stream_handle(stream))
+            st["packed"] = None
+        st["last"] = key
 
     def get_buffers(self, o, aggbuf, u, p, t, *, stream=None):
         """`get_buffers(nw, u, p, t)` (src/coreloop.jl:103-109) into caller-provided device vectors."""
@@ -545,6 +597,7 @@ class Network:
         if n_o != self.im.lastidx_out or n_a != self.im.lastidx_aggr:
             raise ArgumentError("output / aggregation buffer has the wrong size")
         self._check_sizes(n_u, n_u, n_p, p is not None)
+        self._auto_pack(p, a_p, stream)
         rc = self._L.nd_b200_get_buffers(self.handle, a_o, a_a, a_u, a_p, float(t), _stream_handle(stream))
         if rc:
             self._fail(rc)
@@ -556,6 +609,7 @@ class Network:
         if not dev:
             raise ArgumentError("rk4 needs device-resident u")
         self._check_sizes(n_u, n_u, n_p, p is not None)
+        self._auto_pack(p, a_p, stream)
         rc = self._L.nd_b200_rk4(self.handle, a_u, a_p, float(t0), float(dt), int(nsteps), _stream_handle(stream))
         if rc:
             self._fail(rc)
@@ -570,6 +624,9 @@ class Network:
         rc = self._L.nd_b200_pack_params(self.handle, a_p, _stream_handle(stream))
         if rc:
             self._fail(rc)
+        # an explicit call takes the automatic refresh out of the picture: the caller owns the contract from here on
+        st = self.__dict__.setdefault("_pack_state", {"manual": False, "packable": True, "packed": None, "last": None})
+        st["manual"], st["packed"], st["last"] = True, None, None
 
     # -- introspection -----------------------------------------------------------------------------
     def engine_sizes(self):
@@ -596,11 +653,7 @@ class Network:
 
     def kernel_name(self) -> str:
         """name of the kernel family that evaluates this network (rhs_jag_kernel unless ND_B200_KERNEL selects a tile kernel)"""
-        sz = np.zeros(6, dtype=np.int64)
-        self._L.nd_b200_export_jag_sizes(self.handle, sz.ctypes.data_as(_cabi.i64p))
-        if sz[0] >= 0:
-            return "rhs_jag_kernel"
-        return "edge_pass_kernel+row_pass_kernel" if os.environ.get("ND_B200_KERNEL") == "split" else "rhs_fused_kernel"
+        return self._L.nd_b200_kernel_name(self.handle).decode()
 
     def custom_source(self) -> Optional[str]:
         """the CUDA source the engine generated for user-supplied component kinds (None for registry-only networks)"""

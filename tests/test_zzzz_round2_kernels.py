@@ -1,0 +1,143 @@
+"""Round-2 kernel work, parity against the CPU oracle (same bar as tests/test_gpu_parity.py):
+
+* rhs_js_kernel -- the jagged warp-slice walk fed by TMA bulk copies (cp.async.bulk + mbarrier rings, persistent warps);
+* the degree-bucketed jagged layout (window 128) chosen automatically for irregular graphs without hubs;
+* compact entry words of the tile kernels (offset | local row << 23 | side << 30) and the fallback without them;
+* edge_parameters="auto": the packed per-entry copy of the edge parameters follows p's modification counter.
+
+Sorts after the established parity tests (an unforeseen GPU-only failure here cannot mask them under `pytest -x`).
+"""
+import numpy as np
+import pytest
+
+from helpers import condition_params, floored_rel_err, oracle_network
+
+TOL_DU = 1e-12
+
+
+def _cases(nd, scale):
+    L = nd.Lib
+    rng = np.random.default_rng(5)
+    n = max(2000, int(40_000 * scale)) // 2 * 2
+    half = np.array([0] * (n // 2) + [1] * (n // 2))
+    yield "er-diffusion", nd.erdos_renyi(n, 4 * n, seed=1), L.diffusion_vertex(), L.diffusion_edge()
+    yield "er-nop", nd.erdos_renyi(n, 4 * n, seed=2), L.diffusion_vertex(), L.diffusion_edge_nop()
+    yield "ws-kuramoto", nd.watts_strogatz(n // 2, 10, 0.1, seed=1), L.kuramoto_first(), L.kuramoto_edge()
+    yield "ba-mixed", nd.barabasi_albert(n, 4, seed=1), ([L.kuramoto_first(), L.kuramoto_second()], rng.permutation(half)), L.kuramoto_edge()
+    yield "star", nd.SimpleGraph(5000, np.ones(4999, dtype=np.int64), np.arange(2, 5001)), L.kuramoto_first(), L.kuramoto_edge()
+    yield "isolated", nd.SimpleGraph(70, [1, 2], [2, 3]), L.diffusion_vertex(), L.diffusion_edge()
+
+
+@pytest.mark.parametrize("wps", ["1", "auto"])
+def test_streamed_jagged_kernel(nd, backend, monkeypatch, wps):
+    """ND_B200_KERNEL=js: live and packed parameters, fused RK4 epilogue; few warps (wps=1) make every warp's stream
+    wrap its shared-memory ring many times"""
+    monkeypatch.setenv("ND_B200_KERNEL", "js")
+    if wps != "auto":
+        monkeypatch.setenv("ND_B200_JS_WPS", wps)
+    B = backend
+    for name, g, vm, em in _cases(nd, B.scale):
+        nw = nd.Network(g, vm, em, aggregator=nd.B200Aggregator("+", edge_parameters="live"))
+        assert nw.kernel_name() == "rhs_js_kernel", name
+        onw = oracle_network(g, vm, em)
+        u = np.random.default_rng(1).random(nw.dim())
+        p = condition_params(nw, np.random.default_rng(2).random(nw.pdim()))
+        ref = onw.rhs(u, p)
+        ud, pd = B.dev(u), B.dev(p)
+        for packed in ([False, True] if em.pdim else [False]):
+            nw.pack_params(pd if packed else None)
+            du = B.nan(nw.dim())
+            nw(du, ud, pd, 0.0)
+            got = B.host(du)
+            assert not np.isnan(got).any(), (name, packed)
+            assert floored_rel_err(got, ref) <= TOL_DU, (name, packed)
+        nw.pack_params(None)
+        ur = B.dev(u)
+        nw.rk4(ur, pd, 0.0, 1e-3, 20)
+        assert np.max(np.abs(B.host(ur) - onw.rk4(u, p, 0.0, 1e-3, 20))) <= 1e-11, name
+
+
+def test_tile_kernel_without_compact_entry_words(nd, backend, monkeypatch):
+    """networks whose offsets do not fit 23 bits keep the row-id table in shared memory; force that path on a small one"""
+    monkeypatch.setenv("ND_B200_KERNEL", "fused")
+    B = backend
+    for compact in (True, False):
+        if not compact:
+            monkeypatch.setenv("ND_B200_NO_COMPACT", "1")
+        for name, g, vm, em in _cases(nd, B.scale):
+            nw = nd.Network(g, vm, em, aggregator=nd.B200Aggregator("+", edge_parameters="live"))
+            assert nw.kernel_name() == "rhs_fused_kernel"
+            onw = oracle_network(g, vm, em)
+            u = np.random.default_rng(3).random(nw.dim())
+            p = condition_params(nw, np.random.default_rng(4).random(nw.pdim()))
+            ref = onw.rhs(u, p)
+            ud, pd = B.dev(u), B.dev(p)
+            for packed in ([False, True] if em.pdim else [False]):
+                nw.pack_params(pd if packed else None)
+                du = B.nan(nw.dim())
+                nw(du, ud, pd, 0.0)
+                assert floored_rel_err(B.host(du), ref) <= TOL_DU, (name, compact, packed)
+
+
+def test_kernel_family_choice(nd):
+    """host-only engines: regular degrees -> jagged slices; irregular without hubs -> degree-bucketed jagged slices
+    (window 128); power-law hubs and small graphs -> tile kernel"""
+    L = nd.Lib
+    agg = lambda: nd.B200Aggregator("+", host_only=True, keep_tables=False)
+    grid = nd.Network(nd.grid_graph(300, 300), L.kuramoto_first(), L.kuramoto_edge(), aggregator=agg())
+    assert grid.kernel_name() == "rhs_jag_kernel"
+    er = nd.Network(nd.erdos_renyi(80_000, 320_000, seed=1), L.diffusion_vertex(), L.diffusion_edge(), aggregator=agg())
+    assert er.kernel_name() == "rhs_jag_kernel"
+    ba = nd.Network(nd.barabasi_albert(80_000, 4, seed=1), L.kuramoto_first(), L.kuramoto_edge(), aggregator=agg())
+    assert ba.kernel_name() == "rhs_fused_kernel"
+    small = nd.Network(nd.erdos_renyi(5_000, 20_000, seed=1), L.diffusion_vertex(), L.diffusion_edge(), aggregator=agg())
+    assert small.kernel_name() == "rhs_fused_kernel"
+
+
+@pytest.mark.gpu
+def test_automatic_parameter_packing_follows_p(nd, cuda):
+    """edge_parameters="auto" (default): results equal the oracle's for the CURRENT p at every call -- also after an
+    in-place change of p between calls (the packed copy must not survive it)"""
+    torch = cuda
+    L = nd.Lib
+    for g, vm, em in [(nd.erdos_renyi(100_000, 400_000, seed=1), L.diffusion_vertex(), L.diffusion_edge()),
+                      (nd.barabasi_albert(60_000, 4, seed=2), L.kuramoto_first(), L.kuramoto_edge())]:
+        nw = nd.Network(g, vm, em)
+        onw = oracle_network(g, vm, em)
+        u_h = np.random.default_rng(1).random(nw.dim())
+        p_h = np.random.default_rng(2).random(nw.pdim())
+        u, p = torch.from_numpy(u_h).cuda(), torch.from_numpy(p_h).cuda()
+        du = torch.empty_like(u)
+        states = []
+        for call in range(4):
+            du.fill_(float("nan"))
+            nw(du, u, p, 0.0)
+            torch.cuda.synchronize()
+            states.append(nw._pack_state["packed"] is not None)
+            assert floored_rel_err(du.cpu().numpy(), onw.rhs(u_h, p_h)) <= TOL_DU, call
+        assert states == [False, True, True, True], states      # packed from the second call with the same p on
+        p.mul_(0.5)                                              # a callback changes the parameters in place
+        p_h = p_h * 0.5
+        for call in range(3):
+            du.fill_(float("nan"))
+            nw(du, u, p, 0.0)
+            torch.cuda.synchronize()
+            assert floored_rel_err(du.cpu().numpy(), onw.rhs(u_h, p_h)) <= TOL_DU, ("after change", call)
+        # get_buffers and rk4 see the current p as well
+        p.add_(0.25)
+        p_h = p_h + 0.25
+        o = torch.empty(nw.im.lastidx_out, dtype=torch.float64, device="cuda")
+        agg = torch.empty(nw.im.lastidx_aggr, dtype=torch.float64, device="cuda")
+        nw.get_buffers(o, agg, u, p, 0.0)
+        torch.cuda.synchronize()
+        _, _, agg_ref = onw.rhs(u_h, p_h, return_bufs=True)
+        assert floored_rel_err(agg.cpu().numpy(), agg_ref) <= TOL_DU
+        ur = u.clone()
+        nw.rk4(ur, p, 0.0, 1e-3, 8)
+        torch.cuda.synchronize()
+        assert np.max(np.abs(ur.cpu().numpy() - onw.rk4(u_h, p_h, 0.0, 1e-3, 8))) <= 1e-11
+        # "live" never packs
+        nwl = nd.Network(g, vm, em, aggregator=nd.B200Aggregator("+", edge_parameters="live"))
+        for call in range(3):
+            nwl(du, u, p, 0.0)
+        assert nwl.__dict__.get("_pack_state", {"packed": None})["packed"] is None
