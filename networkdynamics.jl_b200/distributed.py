@@ -204,7 +204,8 @@ class PartitionedNetwork:
     evaluate the owned rows into `du` (only the owned entries of `du` are written)."""
 
     def __init__(self, g, vertexm, edgem, *, rank: int, world: int, group=None, device=None,
-                 long_row_threshold: int = 0, exchange: str = "auto", from_edgelist: bool = False):
+                 long_row_threshold: int = 0, exchange: str = "auto", from_edgelist: bool = False,
+                 edge_parameters: str = "auto"):
         """exchange: "p2p"  -- states are pushed into every rank's replica with NVLink peer stores by the engine's
         publish kernel and the RHS kernel waits on arrival flags (nd_b200_rhs_exchange; no NCCL on the data path);
         "nccl" -- torch.distributed collectives on the caller's `u`; "auto" -- p2p when the network allows it
@@ -232,12 +233,13 @@ class PartitionedNetwork:
             if from_edgelist:
                 return Network.from_edgelist(g, vertexm, edgem, device=device, row_range=self.row_ranges[rank], keep_tables=False,
                                              gather_offset=None if plan is None else plan["gather_offset"],
-                                             gather_len=0 if plan is None else plan["gather_len"])
+                                             gather_len=0 if plan is None else plan["gather_len"], edge_parameters=edge_parameters)
             return Network(g, vertexm, edgem, execution=B200Execution(),
                            aggregator=B200Aggregator("+", device=device, row_range=self.row_ranges[rank],
                                                      long_row_threshold=long_row_threshold, keep_tables=False,
                                                      gather_offset=None if plan is None else plan["gather_offset"],
-                                                     gather_len=0 if plan is None else plan["gather_len"]))
+                                                     gather_len=0 if plan is None else plan["gather_len"],
+                                                     edge_parameters=edge_parameters))
 
         want_p2p = exchange in ("p2p", "auto") and world > 1
         if want_p2p and stateful_edges:         # their states travel with the all-gather; the packed halo carries vertex outputs only
@@ -337,6 +339,10 @@ class PartitionedNetwork:
     def exchange(self, u):
         exchange_states(u, self.segments, self.group)
 
+    def parameter_segments(self):
+        """0-based [start, stop) ranges of the flat parameter vector this rank's rows read"""
+        return [(0, int(self.nw.pdim()))] if self.nw.pdim() else []
+
     def rhs_local(self, du, u, p, t, *, stream=None):
         """timing aid: the owned rows on the current halo content, no exchange (p2p engines only)"""
         from .network import _addr, _stream_handle
@@ -365,6 +371,9 @@ class PartitionedNetwork:
             a_u, _, n_u = _addr(u)
             a_p, _, n_p = _addr(p)
             self.nw._check_sizes(n_du, n_u, n_p, p is not None)
+            # per-rank packed copy of the edge parameters this rank's rows read, kept in step with p automatically
+            # (edge_parameters="auto"): removes the isolated reads of cut-edge parameters scattered over the whole p
+            self.nw._auto_pack(p, a_p, stream)
             rc = _cabi.lib().nd_b200_rhs_exchange(self.nw.handle, self.comm, a_du, a_u, a_p, float(t), _stream_handle(stream))
             if rc:
                 self.nw._fail(rc)
@@ -383,6 +392,7 @@ class PartitionedNetwork:
             a_u, _, n_u = _addr(u)
             a_p, _, n_p = _addr(p)
             self.nw._check_sizes(n_u, n_u, n_p, p is not None)
+            self.nw._auto_pack(p, a_p, stream)
             rc = _cabi.lib().nd_b200_rk4_exchange(self.nw.handle, self.comm, a_u, a_p, float(t0), float(dt), int(nsteps), _stream_handle(stream))
             if rc:
                 self.nw._fail(rc)

@@ -451,7 +451,7 @@ class Network:
     @classmethod
     def from_edgelist(cls, g, vertexm: VertexModel, edgem: EdgeModel, *, device: Optional[int] = None, row_range=None,
                       keep_tables: bool = False, host_only: bool = False, gather_offset=None, gather_len: int = 0,
-                      layout_only: bool = False):
+                      layout_only: bool = False, edge_parameters: str = "auto"):
         """Homogeneous network straight from the edge list (`nd_b200_create_from_edgelist`): one registry
         vertex model, one registry edge model.  Same flat `u` / `p` layout and same engine as `Network(g, vertexm, edgem)`,
         without the per-component host tables (BASELINE config 5 has 4e8 edges: six Int64 tables would be 19 GB)."""
@@ -487,7 +487,8 @@ class Network:
             if rc != _cabi.OK:
                 msg = L.nd_b200_last_error(None).decode()
                 raise (ArgumentError if rc in (_cabi.EINVAL, _cabi.EUNSUPPORTED) else RuntimeError)(msg)
-            agg = B200Aggregator("+", device=dev, row_range=row_range, keep_tables=keep_tables, host_only=host_only)
+            agg = B200Aggregator("+", device=dev, row_range=row_range, keep_tables=keep_tables, host_only=host_only,
+                                 edge_parameters=edge_parameters)
             agg.handle, agg.device, agg._L = h, int(dev), L
             agg._sizes = (self.im.lastidx_out, self.im.lastidx_aggr)
         # the one vertex batch / edge batch of the layout (what register_vertices! / register_edges! would return), without
