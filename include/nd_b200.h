@@ -28,7 +28,8 @@ enum {
   ND_B200_EINVAL = 1,        /* size / layout mismatch (src/coreloop.jl:2-7 raise ArgumentError) */
   ND_B200_EUNSUPPORTED = 2,  /* component kind / feature outside the kernel registry: NO CPU fallback */
   ND_B200_ECUDA = 3,
-  ND_B200_ENOMEM = 4
+  ND_B200_ENOMEM = 4,
+  ND_B200_ETIMEOUT = 5       /* multi-GPU: a peer's boundary outputs did not arrive within the spin budget (sticky) */
 };
 
 /* ---- kernel registry: vertex models ------------------------------------------------------- */
@@ -164,6 +165,8 @@ typedef struct nd_b200_desc {
 } nd_b200_desc;
 
 #define ND_B200_FLAG_NO_EXPORT 1  /* do not keep host copies of the CSR for nd_b200_export_tables */
+#define ND_B200_FLAG_ROW_RANGE 4  /* row_begin / row_end are a row partition even when it is EMPTY (row_begin == row_end);
+                                   * without the flag row_end <= 0 means "all rows" */
 #define ND_B200_FLAG_HOST_ONLY 2  /* build every table on the host and stop: no CUDA call is made, the engine can only
                                      export its tables (layout tests on machines without a GPU) */
 

@@ -15,7 +15,7 @@ from .components import (AntiSymmetric, ArgumentError, CudaFunction, Directed, E
                          RegisteredFunction, StateMask, Symmetric, VertexModel, VIndex)
 from .graphs import (SimpleDiGraph, SimpleGraph, barabasi_albert, complete_graph, erdos_renyi, grid_graph, locality_order, ne,
                      nv, path_graph, permute_graph, watts_strogatz)
-from .network import (B200Aggregator, B200Execution, ComponentBatch, ExecutionStyle, IndexManager, Network, dim,
+from .network import (B200Aggregator, B200Execution, ComponentBatch, ExecutionStyle, HaloTimeoutError, IndexManager, Network, dim,
                       find_identical, get_aggr_constructor, iscudacompatible, pdim, pinned_empty, usebuffer)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

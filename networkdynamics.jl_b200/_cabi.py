@@ -16,7 +16,7 @@ SOURCES = [os.path.join(_PKG, "csrc", "nd_b200.cu")]
 HEADERS = [os.path.join(_PKG, "csrc", "nd_b200_kernels.cuh"), os.path.join(_ROOT, "include", "nd_b200.h")]
 
 ABI_VERSION = 5
-OK, EINVAL, EUNSUPPORTED, ECUDA, ENOMEM = range(5)
+OK, EINVAL, EUNSUPPORTED, ECUDA, ENOMEM, ETIMEOUT = range(6)
 
 # registry ids (include/nd_b200.h)
 V_DIFFUSION, V_KURAMOTO_FIRST, V_KURAMOTO_SECOND, V_KURAMOTO_SECOND_BENCH, V_SWING_DQ = range(5)
@@ -25,6 +25,7 @@ ANTISYMMETRIC, SYMMETRIC, DIRECTED, FIDUCIAL = range(4)
 CUSTOM_KIND_BASE = 1000
 FLAG_NO_EXPORT = 1
 FLAG_HOST_ONLY = 2
+FLAG_ROW_RANGE = 4
 
 i64p = C.POINTER(C.c_int64)
 i32p = C.POINTER(C.c_int32)

@@ -825,7 +825,7 @@ struct EngineBuilder {
     e->gather_from_u = (all_statemask1 && d->vdepth == 1) ? 1 : 0;
 
     e->row_begin = 0; e->row_end = e->nrows_total;
-    if (d->row_end > 0) {
+    if (d->row_end > 0 || (d->flags & ND_B200_FLAG_ROW_RANGE)) {
       if (d->row_begin < 0 || d->row_begin > d->row_end || d->row_end > e->nrows_total) return fail(e, ND_B200_EINVAL, "row partition [%lld,%lld) outside 0..%lld", (long long)d->row_begin, (long long)d->row_end, e->nrows_total);
       e->row_begin = d->row_begin; e->row_end = d->row_end;
     }
@@ -1127,8 +1127,10 @@ struct EngineBuilder {
   int plan_tiles() {
     // ---- launch shape + thread-block row ranges ----------------------------------------------------
     e->block = 128; e->ept = 4;   // measured best on B200 for every registry family (profiles/r01_tuning.md)
-    if (const char* s = getenv("ND_B200_BLOCK")) e->block = atoi(s);
-    if (const char* s = getenv("ND_B200_EPT")) e->ept = atoi(s);
+    if (!e->custom) {             // run-time compiled kernels exist for the default launch shape only
+      if (const char* s = getenv("ND_B200_BLOCK")) e->block = atoi(s);
+      if (const char* s = getenv("ND_B200_EPT")) e->ept = atoi(s);
+    }
     if (!((e->block == 256 || e->block == 128) && (e->ept == 8 || e->ept == 4))) return fail(e, ND_B200_EINVAL, "ND_B200_BLOCK/ND_B200_EPT must be 128|256 / 4|8");
     const int tile = e->block * e->ept;
     e->n_long = 0;
@@ -1579,7 +1581,7 @@ int check_call(nd_b200_engine* e, const void* du, const void* u, const void* p) 
   return 0;
 }
 
-struct WaitSpec { const double* halo; const unsigned long long* flags; unsigned long long seq; int world; int* timeout; const HaloParams* pub; int n_pub; };
+struct WaitSpec { const double* halo; const unsigned long long* flags; unsigned long long seq; int world; int* timeout; const HaloParams* pub; int n_pub; int* timeout_host; long long budget; };
 
 int rhs_impl(nd_b200_engine* e, double* du, const double* u, const double* p, double t, cudaStream_t st, int mode,
              double* aggbuf, const WaitSpec* w = nullptr) {
@@ -1590,6 +1592,7 @@ int rhs_impl(nd_b200_engine* e, double* du, const double* u, const double* p, do
   P.gsrc = u;
   if (w) {
     P.halo = w->halo; P.wait_flags = w->flags; P.wait_seq = w->seq; P.wait_world = w->world; P.wait_timeout = w->timeout;
+    P.wait_timeout_host = w->timeout_host; P.wait_budget = w->budget;
     if (w->pub) {
       P.H = *w->pub; P.n_pub = w->n_pub;
       // no block of this launch would wait for the peers (no row reads the halo, or no rows at all): add the fence block
@@ -1752,6 +1755,7 @@ const char* nd_b200_last_error(const nd_b200_engine* e) { return e ? e->err.c_st
 
 int nd_b200_rhs(nd_b200_engine* e, double* du, const double* u, const double* p, double t, void* stream) {
   if (int rc = check_call(e, du, u, p)) return rc;
+  CUDA_TRY(e, cudaSetDevice(e->device));
   return rhs_impl(e, du, u, p, t, (cudaStream_t)stream, MODE_DU, nullptr);
 }
 
@@ -1891,6 +1895,7 @@ int nd_b200_get_buffers(nd_b200_engine* e, double* o, double* aggbuf, const doub
   if (!u || (e->lastidx_p > 0 && !p)) return fail(e, ND_B200_EINVAL, "u or p is NULL");
   if (e->h_esrc_off.size() != e->heb.size()) return fail(e, ND_B200_EUNSUPPORTED, "engine was created with ND_B200_FLAG_NO_EXPORT");
   if (e->halo_base != INT_MAX || e->host_only) return fail(e, ND_B200_EUNSUPPORTED, "nd_b200_get_buffers on a halo / host-only engine");
+  CUDA_TRY(e, cudaSetDevice(e->device));
   cudaStream_t st = (cudaStream_t)stream;
   const double* gsrc = u;
   if (!e->gather_from_u) {
@@ -2114,6 +2119,8 @@ struct nd_b200_comm {
   long long dst_off[HALO_MAX_WORLD] = {0};           // [r]: where this rank's block starts inside rank r's halo
   unsigned int* d_done = nullptr;
   int* d_timeout = nullptr;
+  int* h_timeout = nullptr;               // the sticky time-out mark again, in pinned (mapped) host memory: readable without a sync
+  long long timeout_clocks = 60000000000LL;   // spin budget of a waiting tile, clock64 ticks (~30 s; ND_B200_HALO_TIMEOUT_MS)
   unsigned long long seq = 0;
   std::string err;
   double* halo(int r, int parity) const { return reinterpret_cast<double*>(base[r] + (size_t)parity * halo_bytes); }
@@ -2155,6 +2162,16 @@ int nd_b200_comm_create(int32_t device, int32_t rank, int32_t world, int64_t hal
   if (ce == cudaSuccess) ce = cudaMemset(c->d_done, 0, sizeof(unsigned int));
   if (ce == cudaSuccess) ce = cudaMalloc((void**)&c->d_timeout, sizeof(int));
   if (ce == cudaSuccess) ce = cudaMemset(c->d_timeout, 0, sizeof(int));
+#ifdef ND_CUSIM
+  if (ce == cudaSuccess) ce = cudaHostAlloc((void**)&c->h_timeout, sizeof(int), cudaHostAllocDefault);
+#else
+  if (ce == cudaSuccess) ce = cudaHostAlloc((void**)&c->h_timeout, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable);
+#endif
+  if (ce == cudaSuccess) *c->h_timeout = 0;
+  if (const char* s = getenv("ND_B200_HALO_TIMEOUT_MS")) {
+    const double ms = atof(s);
+    if (ms > 0) c->timeout_clocks = (long long)(ms * 2.0e6);      // ~2 GHz SM clock
+  }
   if (ce == cudaSuccess) ce = cudaDeviceSynchronize();
   if (ce != cudaSuccess) {
     cfail(nullptr, ND_B200_ECUDA, "nd_b200_comm_create: %s", cudaGetErrorString(ce));
@@ -2211,6 +2228,7 @@ int nd_b200_comm_status(nd_b200_comm* c, int32_t* timed_out) {
   int v = 0;
   COMM_TRY(c, cudaSetDevice(c->device));
   COMM_TRY(c, cudaMemcpy(&v, c->d_timeout, sizeof v, cudaMemcpyDeviceToHost));
+  if (c->h_timeout && *(volatile int*)c->h_timeout) v = 1;
   *timed_out = v;
   return ND_B200_OK;
 }
@@ -2227,6 +2245,7 @@ void nd_b200_comm_destroy(nd_b200_comm* c) {
     if (r == c->rank) cudaFree(c->base[r]); else cudaIpcCloseMemHandle(c->base[r]);
   }
   cudaFree(c->d_done); cudaFree(c->d_timeout);
+  if (c->h_timeout) cudaFreeHost(c->h_timeout);
   delete c;
 }
 
@@ -2240,6 +2259,10 @@ int check_exchange(nd_b200_engine* e, nd_b200_comm* c, const char* who) {
   if (e->gather_len - e->lastidx_dynamic != c->halo_len) return fail(e, ND_B200_EINVAL, "comm halo holds %lld outputs, the engine expects %lld", c->halo_len, e->gather_len - e->lastidx_dynamic);
   for (int r = 0; r < c->world; ++r)
     if (!c->base[r]) return fail(e, ND_B200_EINVAL, "peer %d has not been opened", r);
+  // sticky: a tile of an earlier launch gave up waiting for a peer -- every result since then is poisoned (NaN)
+  if (c->h_timeout && *(volatile int*)c->h_timeout)
+    return fail(e, ND_B200_ETIMEOUT, "%s: an earlier exchange timed out waiting for a peer's boundary outputs (rank skew beyond the spin budget, "
+                "ND_B200_HALO_TIMEOUT_MS, or a dead peer); results since then are NaN -- recreate the comm", who);
   return ND_B200_OK;
 }
 // one exchange = the next sequence number: what the publishing blocks of this launch send (outputs packed from `src`) and
@@ -2257,7 +2280,7 @@ WaitSpec next_exchange(nd_b200_comm* c, const double* src, HaloParams& H) {
   H.world = c->world; H.rank = c->rank; H.seq = seq; H.src = src; H.done_counter = c->d_done;
   // publishing blocks: 128 threads each, ~8 outputs per thread, at least one (it raises the flags even when nothing is sent)
   const int n_pub = (int)std::max<long long>(1, std::min<long long>(148 * 16, (total + 1023) / 1024));
-  return WaitSpec{c->halo(c->rank, parity), c->flags(c->rank), seq, c->world, c->d_timeout, &H, n_pub};
+  return WaitSpec{c->halo(c->rank, parity), c->flags(c->rank), seq, c->world, c->d_timeout, &H, n_pub, c->h_timeout, c->timeout_clocks};
 }
 }  // namespace
 
@@ -2267,6 +2290,7 @@ int nd_b200_rhs_exchange(nd_b200_engine* e, nd_b200_comm* c, double* du, const d
                          void* stream) {
   if (int rc = check_call(e, du, u, p)) return rc;
   if (int rc = check_exchange(e, c, "nd_b200_rhs_exchange")) return rc;
+  CUDA_TRY(e, cudaSetDevice(e->device));
   HaloParams H;
   const WaitSpec w = next_exchange(c, u, H);
   return rhs_impl(e, du, u, p, t, (cudaStream_t)stream, MODE_DU, nullptr, &w);
@@ -2303,6 +2327,7 @@ int nd_b200_rk4_exchange(nd_b200_engine* e, nd_b200_comm* c, double* u, const do
       P.p = p; P.mode = MODE_RK; P.u0 = u; P.ksum = e->d_ksum; P.h6 = dt / 6.0;
       P.stage = s + 1; P.u = in[s]; P.gsrc = in[s]; P.unext = out[s]; P.hs = hs[s]; P.t = ts[s]; P.vout_next = nullptr;
       P.halo = w.halo; P.wait_flags = w.flags; P.wait_seq = w.seq; P.wait_world = w.world; P.wait_timeout = w.timeout;
+      P.wait_timeout_host = w.timeout_host; P.wait_budget = w.budget;
       P.H = H; P.n_pub = w.n_pub;
       const bool waits = e->jag ? (e->wait_from < e->nslices || e->n_jlong > 0) : (e->wait_from < e->nblocks);
       P.fence = waits ? 0 : 1;
@@ -2316,7 +2341,8 @@ int nd_b200_rk4_exchange(nd_b200_engine* e, nd_b200_comm* c, double* u, const do
 int nd_b200_rhs_local(nd_b200_engine* e, nd_b200_comm* c, double* du, const double* u, const double* p, double t, void* stream) {
   if (int rc = check_call(e, du, u, p)) return rc;
   if (!c || e->halo_base == INT_MAX) return fail(e, ND_B200_EINVAL, "nd_b200_rhs_local needs a halo engine and its comm");
-  WaitSpec w{c->halo(c->rank, (int)(c->seq & 1ull)), nullptr, 0, 0, nullptr, nullptr, 0};
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  WaitSpec w{c->halo(c->rank, (int)(c->seq & 1ull)), nullptr, 0, 0, nullptr, nullptr, 0, nullptr, 0};
   return rhs_impl(e, du, u, p, t, (cudaStream_t)stream, MODE_DU, nullptr, &w);
 }
 

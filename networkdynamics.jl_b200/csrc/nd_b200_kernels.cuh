@@ -146,6 +146,8 @@ struct KParams {
   unsigned long long wait_seq;
   int wait_world;
   int* wait_timeout;                   // set to 1 if a flag did not arrive within the spin budget
+  int* wait_timeout_host;              // the same mark in mapped host memory (the entry points refuse further exchanges)
+  long long wait_budget;               // spin budget in clock64 ticks
   // jagged ("warp-sliced") layout, see rhs_jag_kernel
   const int4* __restrict__ jslices;    // per 32-lane slice {entry base, first row, vertex batch, max parts of a split row}
   const uint16_t* __restrict__ jlanes; // per lane: len | rowrel<<6 (7 bits) | head<<13 | valid<<14
@@ -367,8 +369,19 @@ __device__ __forceinline__ void vertex_f(int kind, double* dv, const double* v, 
 // PASS 6 for one row + the epilogue selected by mode.  v = the vertex's states, pv = its parameters
 // (pointers into global or shared memory).
 template <int VD, int ED>
-__device__ __forceinline__ void vertex_phase(const KParams& P, const VBDev& B, int row, const double* acc,
+__device__ __forceinline__ void vertex_phase(const KParams& P, const VBDev& B, int row, const double* acc_in,
                                              const double* selfout, const double* vin, const double* pv) {
+  // multi-GPU: after a halo time-out the row sums were computed from stale or partial boundary outputs -- poison them so
+  // that the result cannot be mistaken for a valid one
+  double acc[ED];
+#pragma unroll
+  for (int d = 0; d < ED; ++d) acc[d] = acc_in[d];
+  if (P.wait_timeout != nullptr) {
+    if (*(volatile const int*)P.wait_timeout) {
+#pragma unroll
+      for (int d = 0; d < ED; ++d) acc[d] = acc[d] * (0.0 / 0.0) + (0.0 / 0.0);
+    }
+  }
   if (P.mode == MODE_AGG) {
 #pragma unroll
     for (int d = 0; d < ED; ++d) P.aggbuf[(long long)row * ED + d] = acc[d];
@@ -500,10 +513,12 @@ __device__ __forceinline__ void halo_wait(const KParams& P) {
   if (threadIdx.x < P.wait_world) {
     const long long t0 = clock64();
     while (ld_acquire_sys(P.wait_flags + threadIdx.x) < P.wait_seq) {
-      // ~2 s: a peer died or the ranks' call sequences diverged; do not hang the GPU.  The mark is sticky: once set,
-      // later tiles and calls give up at once (results are invalid anyway, nd_b200_comm_status reports it).
-      if (*(volatile int*)P.wait_timeout || clock64() - t0 > 4000000000LL) {
+      // budget exhausted (default 30 s, ND_B200_HALO_TIMEOUT_MS): a peer died or the ranks' call sequences diverged; do not
+      // hang the GPU.  The mark is sticky: once set, later tiles and calls give up at once, every row of such a launch
+      // writes NaN (vertex_phase) and the exchanging entry points return ND_B200_ETIMEOUT.
+      if (*(volatile int*)P.wait_timeout || clock64() - t0 > P.wait_budget) {
         *P.wait_timeout = 1;
+        if (P.wait_timeout_host) *(volatile int*)P.wait_timeout_host = 1;
         break;
       }
       __nanosleep(100);
@@ -519,8 +534,9 @@ __device__ __forceinline__ void halo_wait_warp(const KParams& P) {
   if (lane < P.wait_world) {
     const long long t0 = clock64();
     while (ld_acquire_sys(P.wait_flags + lane) < P.wait_seq) {
-      if (*(volatile int*)P.wait_timeout || clock64() - t0 > 4000000000LL) {
+      if (*(volatile int*)P.wait_timeout || clock64() - t0 > P.wait_budget) {
         *P.wait_timeout = 1;
+        if (P.wait_timeout_host) *(volatile int*)P.wait_timeout_host = 1;
         break;
       }
       __nanosleep(100);

@@ -79,6 +79,8 @@ def partition_rows(entry_counts: np.ndarray, world: int, prefer_equal_rows: floa
         cuts.append(int(np.searchsorted(w, total * r / world, side="left")))
     cuts.append(int(entry_counts.size))
     cuts = [min(max(c, cuts[i - 1] if i else 0), entry_counts.size) for i, c in enumerate(cuts)]
+    # a rank may end up with the EMPTY range (hub-first star graphs: the first row already exceeds a share); engines are
+    # created with ND_B200_FLAG_ROW_RANGE, so (a, a) means "no rows", not "all rows"
     return [(cuts[i], cuts[i + 1]) for i in range(world)]
 
 

@@ -200,6 +200,10 @@ def _expand_models(models, n, what):
 # ---------------------------------------------------------------------------------------------------
 # the aggregator that owns the engine
 # ---------------------------------------------------------------------------------------------------
+class HaloTimeoutError(RuntimeError):
+    """multi-GPU: a rank gave up waiting for a peer's boundary outputs (ND_B200_ETIMEOUT); results since then are NaN"""
+
+
 class B200Aggregator:
     """`B200Aggregator(+)` is, like every reference aggregator, a constructor closure: calling it with
     `(im, edgebatches)` after all batches are registered (src/construction.jl:198) builds the aggregator -- here
@@ -302,7 +306,8 @@ class B200Aggregator:
                           len(edgebatches), vb, eb, im.lastidx_dynamic, im.lastidx_p, im.lastidx_out,
                           im.lastidx_aggr, int(rr[0]), int(rr[1]), int(self._opts["long_row_threshold"]),
                           (0 if self._opts["keep_tables"] else _cabi.FLAG_NO_EXPORT)
-                          | (_cabi.FLAG_HOST_ONLY if self._opts["host_only"] else 0),
+                          | (_cabi.FLAG_HOST_ONLY if self._opts["host_only"] else 0)
+                          | (_cabi.FLAG_ROW_RANGE if self._opts["row_range"] is not None else 0),
                           None, 0)
         if customs:
             ck = (_cabi.CustomKind * len(customs))()
@@ -472,7 +477,8 @@ class Network:
                                   lastidx_out=nv * vertexm.outdim + ne * (osrc + edgem.outdim_dst), lastidx_aggr=nv * edepth)
         dev = _current_device() if device is None else device
         rr = row_range or (0, 0)
-        flags = (0 if keep_tables else _cabi.FLAG_NO_EXPORT) | (_cabi.FLAG_HOST_ONLY if host_only else 0)
+        flags = (0 if keep_tables else _cabi.FLAG_NO_EXPORT) | (_cabi.FLAG_HOST_ONLY if host_only else 0) \
+            | (_cabi.FLAG_ROW_RANGE if row_range is not None else 0)
         h = C.c_void_p()
         go = None
         if gather_offset is not None:           # row-partitioned engine with a packed halo (distributed.py)
@@ -516,6 +522,8 @@ class Network:
 
     def _fail(self, rc):
         msg = self._L.nd_b200_last_error(self.handle).decode()
+        if rc == _cabi.ETIMEOUT:
+            raise HaloTimeoutError(msg)
         raise (ArgumentError if rc in (_cabi.EINVAL, _cabi.EUNSUPPORTED) else RuntimeError)(msg)
 
     def _check_sizes(self, n_du, n_u, n_p, has_p):
@@ -591,10 +599,12 @@ class Network:
 
     def get_buffers(self, o, aggbuf, u, p, t, *, stream=None):
         """`get_buffers(nw, u, p, t)` (src/coreloop.jl:103-109) into caller-provided device vectors."""
-        a_o, _, n_o = _addr(o)
-        a_a, _, n_a = _addr(aggbuf)
-        a_u, _, n_u = _addr(u)
-        a_p, _, n_p = _addr(p)
+        a_o, dev_o, n_o = _addr(o)
+        a_a, dev_a, n_a = _addr(aggbuf)
+        a_u, dev_u, n_u = _addr(u)
+        a_p, dev_p, n_p = _addr(p)
+        if any(d is False for d in (dev_o, dev_a, dev_u, dev_p)):
+            raise ArgumentError("get_buffers needs device-resident o, aggbuf, u and p")
         if n_o != self.im.lastidx_out or n_a != self.im.lastidx_aggr:
             raise ArgumentError("output / aggregation buffer has the wrong size")
         self._check_sizes(n_u, n_u, n_p, p is not None)

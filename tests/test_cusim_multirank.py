@@ -260,3 +260,59 @@ def test_planning_in_chunks(nd, monkeypatch):
             assert np.array_equal(pl["gather_offset"], ref[r]["gather_offset"]) and pl["halo_lens"] == ref[r]["halo_lens"]
             assert all(np.array_equal(pl["sends"][q][0], ref[r]["sends"][q][0]) for q in pl["sends"])
         monkeypatch.undo()
+
+
+def test_hub_first_star_gives_an_empty_row_range_that_stays_empty(nd):
+    """partition_rows can hand a rank the EMPTY range (hub first); the engine must read (a, a) as "no rows", not as
+    "all rows" (ND_B200_FLAG_ROW_RANGE): results still equal the oracle's and the empty rank writes nothing"""
+    from networkdynamics_jl_b200 import distributed as D
+    assert D.partition_rows(np.array([100] + [1] * 100), 4)[0] == (0, 0)
+    n = 400
+    g = nd.SimpleGraph(n, np.ones(n - 1, dtype=np.int64), np.arange(2, n + 1))       # hub = vertex 1
+    out, ref, plans, sizes, _ = _run_world(nd, g, nd.Lib.kuramoto_first(), nd.Lib.kuramoto_edge(), 4, 6)
+    assert sizes[0]["nrows"] == 0 and sum(s["nrows"] for s in sizes) == n
+    assert np.max(np.abs(out - ref)) <= 1e-13          # the hub row is reduced by a block tree: association differs
+
+
+def test_halo_timeout_is_sticky_poisons_the_result_and_is_reported(nd, monkeypatch):
+    """a rank whose peer never publishes gives up after the (configurable) spin budget, writes NaN instead
+    of results computed from a stale halo, and every later exchange on that comm is refused with ND_B200_ETIMEOUT"""
+    import cusim
+    from networkdynamics_jl_b200 import distributed as D
+    monkeypatch.setenv("ND_B200_HALO_TIMEOUT_MS", "0.0005")       # ~1000 emulator "ticks" (ns)
+    g, vm, em = nd.erdos_renyi(600, 2400, seed=3), nd.Lib.diffusion_vertex(), nd.Lib.diffusion_edge()
+    with cusim.use() as L:
+        probe = nd.Network(g, vm, em, aggregator=null_aggregator)
+        rr = D.partition_rows(D.row_entry_counts(probe.im, probe.layer.edgebatches), 2)
+        plans = [D.halo_plan(probe.im, probe.layer.edgebatches, rr, r) for r in range(2)]
+        nws = [nd.Network(g, vm, em, aggregator=nd.B200Aggregator("+", device=r, row_range=rr[r], keep_tables=False,
+                                                                   gather_offset=plans[r]["gather_offset"], gather_len=plans[r]["gather_len"]))
+               for r in range(2)]
+        comms, handles = [], []
+        for r in range(2):
+            c = C.c_void_p()
+            assert L.nd_b200_comm_create(r, r, 2, plans[r]["halo_lens"][r], max(plans[r]["halo_lens"]), C.byref(c)) == 0
+            hb = C.create_string_buffer(nd._cabi.IPC_HANDLE_BYTES)
+            assert L.nd_b200_comm_export(c, hb) == 0
+            for peer, (offs, start) in plans[r]["sends"].items():
+                offs = np.ascontiguousarray(offs, dtype=np.int64)
+                assert L.nd_b200_comm_set_send(c, peer, offs.ctypes.data_as(nd._cabi.i64p), offs.size, start) == 0
+            comms.append(c); handles.append(hb)
+        for r in range(2):
+            for q in range(2):
+                assert L.nd_b200_comm_open_peer(comms[r], q, handles[q].raw) == 0
+        n = probe.dim()
+        u = np.random.default_rng(1).random(n)
+        p = np.random.default_rng(2).random(probe.pdim())
+        du = np.zeros(n)
+        # only rank 0 calls: rank 1 never raises its arrival flag
+        assert L.nd_b200_rhs_exchange(nws[0].handle, comms[0], _ptr(du), _ptr(u), _ptr(p), 0.0, None) == 0
+        v = C.c_int32(0)
+        assert L.nd_b200_comm_status(comms[0], C.byref(v)) == 0 and v.value == 1
+        a, b = D.state_segments(probe.vertexbatches, *rr[0])[0]
+        assert np.isnan(du[a:b]).any(), "rows that read the missing halo must not look valid"
+        rc = L.nd_b200_rhs_exchange(nws[0].handle, comms[0], _ptr(du), _ptr(u), _ptr(p), 0.0, None)
+        assert rc == nd._cabi.ETIMEOUT and "timed out" in L.nd_b200_last_error(nws[0].handle).decode()
+        for c in comms:
+            L.nd_b200_comm_destroy(c)
+        del nws
