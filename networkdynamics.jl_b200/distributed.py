@@ -48,6 +48,8 @@ def row_entry_counts(im: IndexManager, edgebatches: Sequence[ComponentBatch]) ->
     return cnt
 
 
+HALO_ALIGN = 16       # doubles: 128-byte alignment of every owner's block inside a reader's halo buffer
+
 _CHUNK = 1 << 25      # edges per pass: bounds the temporaries of the planning functions at config-5 scale (4e8 edges)
 
 
@@ -94,6 +96,19 @@ def state_segments(vertexbatches: Sequence[ComponentBatch], r0: int, r1: int) ->
         if lo < hi and dim > 0:
             first = b.state_first - 1
             segs.append((first + (lo - row) * dim, first + (hi - row) * dim))
+        row += n
+    return segs
+
+
+def param_segments(vertexbatches: Sequence[ComponentBatch], r0: int, r1: int) -> List[Tuple[int, int]]:
+    """0-based [start, stop) ranges of the flat parameter vector holding the vertex parameters of rows [r0, r1)"""
+    segs, row = [], 0
+    for b in vertexbatches:
+        n, pd = len(b), b.model.pdim
+        lo, hi = max(r0, row), min(r1, row + n)
+        if lo < hi and pd > 0:
+            first = b.p_first - 1
+            segs.append((first + (lo - row) * pd, first + (hi - row) * pd))
         row += n
     return segs
 
@@ -147,11 +162,18 @@ def halo_plan(im: IndexManager, edgebatches: Sequence[ComponentBatch], row_range
     vorder = np.lexsort((goff, vowner))
     need = [vorder[needed[r][vorder]] for r in range(world)]
     counts = np.array([np.bincount(vowner[n], minlength=world) for n in need], dtype=np.int64)   # [reader, owner]
-    starts = np.concatenate([np.zeros((world, 1), dtype=np.int64), np.cumsum(counts, axis=1)], axis=1)
-    halo_lens = [int(n.size) for n in need]
+    # every owner's block starts on a 128-byte boundary of the reader's halo buffer: the publishing blocks' warps then store
+    # whole aligned 256-byte pieces over NVLink (profiles/r02e_p2p_store_bench_raw.txt: 650-700 GB/s aligned, 480-500 GB/s
+    # when the destination is only 8-byte aligned).  Pad slots are never addressed.
+    padded = (counts + HALO_ALIGN - 1) // HALO_ALIGN * HALO_ALIGN
+    starts = np.concatenate([np.zeros((world, 1), dtype=np.int64), np.cumsum(padded, axis=1)], axis=1)
+    ustarts = np.concatenate([np.zeros((world, 1), dtype=np.int64), np.cumsum(counts, axis=1)], axis=1)
+    halo_lens = [int(starts[r, -1]) for r in range(world)]
     nstates = int(im.lastidx_dynamic)
     gather_offset = goff.copy()
-    gather_offset[need[rank]] = nstates + np.arange(need[rank].size, dtype=np.int64)
+    own = vowner[need[rank]]                          # need[rank] is ordered by (owner, state offset)
+    k = np.arange(need[rank].size, dtype=np.int64)
+    gather_offset[need[rank]] = nstates + starts[rank, own] + (k - ustarts[rank, own])
     sends = {}
     for r in range(world):
         if r == rank:
@@ -207,7 +229,7 @@ class PartitionedNetwork:
 
     def __init__(self, g, vertexm, edgem, *, rank: int, world: int, group=None, device=None,
                  long_row_threshold: int = 0, exchange: str = "auto", from_edgelist: bool = False,
-                 edge_parameters: str = "auto"):
+                 edge_parameters: str = "auto", local_parameters: bool = False):
         """exchange: "p2p"  -- states are pushed into every rank's replica with NVLink peer stores by the engine's
         publish kernel and the RHS kernel waits on arrival flags (nd_b200_rhs_exchange; no NCCL on the data path);
         "nccl" -- torch.distributed collectives on the caller's `u`; "auto" -- p2p when the network allows it
@@ -230,6 +252,48 @@ class PartitionedNetwork:
         self.comm = None
         self.exchange_kind = "nccl"
         self.plan = None
+        # local_parameters ("each rank owns ... the params of edges incident to its rows, cut-edge params
+        # duplicated on both sides"): this rank's engine is built on the subgraph of the edges INCIDENT to its rows (same
+        # vertices, same relative edge order -> same accumulation order per row), so its parameter vector holds the vertex
+        # parameters and only those edges' parameters: p_local = p_global[p_index].  u / du keep the global layout.
+        # (one edge batch only: with several, the subgraph's batches could be registered in another order than the full
+        # graph's, which would change the accumulation order inside a row)
+        self.local_parameters = bool(local_parameters) and world > 1 and not stateful_edges and len(probe.layer.edgebatches) == 1
+        self.global_pdim = int(probe.pdim())
+        self.p_index = None
+        self._vertex_pdim = int(sum(len(b) * b.model.pdim for b in probe.vertexbatches)) if not from_edgelist else int(g.nv * vertexm.pdim)
+        self._own_param_segs = param_segments(probe.vertexbatches, *self.row_ranges[rank]) if not from_edgelist else \
+            ([(self.row_ranges[rank][0] * vertexm.pdim, self.row_ranges[rank][1] * vertexm.pdim)] if vertexm.pdim else [])
+        g_full, edgem_full = g, edgem
+        if self.local_parameters:
+            src, dst = np.asarray(probe.im.edge_src), np.asarray(probe.im.edge_dst)
+            vowner = owner_of_rows(row_of_vertex(probe.im), self.row_ranges)
+            keep = np.nonzero((vowner[src - 1] == rank) | (vowner[dst - 1] == rank))[0]
+            g = type(g)(g.nv, src[keep], dst[keep], _canonical=True)
+            if from_edgelist:
+                pe = edgem.pdim
+                self.p_index = np.concatenate([np.arange(self._vertex_pdim, dtype=np.int64),
+                                               (self._vertex_pdim + keep[:, None] * pe + np.arange(pe, dtype=np.int64)[None, :]).ravel()])
+            else:
+                from .components import EdgeModel
+                if isinstance(edgem, EdgeModel):
+                    pass
+                elif isinstance(edgem, tuple):
+                    edgem = (edgem[0], np.asarray(edgem[1])[keep])
+                else:
+                    edgem = [edgem[i] for i in keep]
+                loc = Network(g, vertexm, edgem, execution=B200Execution(), aggregator=lambda im, eb: None)
+                widths = np.array([m.pdim for m in probe.im.edgem], dtype=np.int64)[np.asarray(probe.im.etype)[keep]]
+                gfirst = np.asarray(probe.im.e_para, dtype=np.int64)[keep] - 1
+                lfirst = np.asarray(loc.im.e_para, dtype=np.int64) - 1
+                idx = np.arange(int(loc.pdim()), dtype=np.int64)          # vertex part: identical layout
+                for w in np.unique(widths):
+                    if w == 0:
+                        continue
+                    m = widths == w
+                    cols = np.arange(int(w), dtype=np.int64)[None, :]
+                    idx[(lfirst[m][:, None] + cols).ravel()] = (gfirst[m][:, None] + cols).ravel()
+                self.p_index = idx
 
         def engine(plan):
             if from_edgelist:
@@ -253,6 +317,7 @@ class PartitionedNetwork:
                 raise RuntimeError("p2p exchange needs StateMask vertices (the gather source must be the state vector)")
             want_p2p = False
         if want_p2p:
+            # the plan needs every rank's needs (where this rank's block starts inside a peer's halo): full graph
             self.plan = halo_plan(probe.im, probe.layer.edgebatches, self.row_ranges, rank)
             self.nw = engine(self.plan)
             try:
@@ -342,8 +407,26 @@ class PartitionedNetwork:
         exchange_states(u, self.segments, self.group)
 
     def parameter_segments(self):
-        """0-based [start, stop) ranges of the flat parameter vector this rank's rows read"""
-        return [(0, int(self.nw.pdim()))] if self.nw.pdim() else []
+        """0-based [start, stop) ranges of THIS RANK's parameter vector that its rows read: with local_parameters the vertex
+        parameters of its rows and the whole (incident-edge) edge block; otherwise the whole global vector (the parameters
+        of cut edges are scattered over it)"""
+        if not self.nw.pdim():
+            return []
+        if self.local_parameters:
+            segs = list(self._own_param_segs)
+            if self.nw.pdim() > self._vertex_pdim:
+                segs.append((self._vertex_pdim, int(self.nw.pdim())))
+            return segs
+        return [(0, int(self.nw.pdim()))]
+
+    def localize_parameters(self, p):
+        """this rank's parameter vector from the reference's flat (global) one: p[p_index] (numpy array or torch tensor)"""
+        if not self.local_parameters:
+            return p
+        if isinstance(p, np.ndarray):
+            return np.ascontiguousarray(p[self.p_index])
+        import torch
+        return p.index_select(0, torch.from_numpy(self.p_index).to(p.device)).contiguous()
 
     def rhs_local(self, du, u, p, t, *, stream=None):
         """timing aid: the owned rows on the current halo content, no exchange (p2p engines only)"""

@@ -223,6 +223,25 @@ def _worker_partitioned_class(rank, world, port, out_dir):
             assert np.max(np.abs(u.numpy() - onw.rk4(u0, p, 0.0, 1e-3, 3))) <= 1e-14
             assert not pn.comm_timed_out()
             pn.close()
+            # local parameters: the rank's engine on the subgraph of the edges incident to its rows; its
+            # parameter vector = vertex parameters + those edges' parameters; same du, bit for bit
+            pl = PartitionedNetwork(g, vm, em, rank=rank, world=world, exchange="nccl", from_edgelist=from_edgelist, local_parameters=True)
+            assert pl.local_parameters and pl.global_pdim == p.size and pl.pdim() < p.size
+            ploc = pl.localize_parameters(p)
+            assert ploc.size == pl.pdim() and np.array_equal(ploc[:g.nv * vm.pdim], p[:g.nv * vm.pdim])
+            u = torch.full((pl.dim(),), float("nan"), dtype=torch.float64)
+            for a, b in pl.owned_segments:
+                u[a:b] = torch.from_numpy(u0[a:b])
+            # parameters outside parameter_segments() are never read: poison them
+            pmask = np.zeros(ploc.size, dtype=bool)
+            for a, b in pl.parameter_segments():
+                pmask[a:b] = True
+            ploc = np.where(pmask, ploc, np.nan)
+            du = torch.full_like(u, float("nan"))
+            pl.rhs(du, u, torch.from_numpy(ploc), 0.0)
+            for a, b in pl.owned_segments:
+                assert np.array_equal(du[a:b].numpy(), ref[a:b]), ("local parameters", from_edgelist)
+            pl.close()
         # edges WITH states: every rank evaluates f for a contiguous chunk of each stateful batch; the chunks' states travel
         # with the all-gather like vertex states (the packed NVLink halo carries vertex outputs only and is refused)
         rng = np.random.default_rng(3)

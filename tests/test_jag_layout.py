@@ -174,7 +174,8 @@ def test_halo_plan_and_interior_first_order(nd, monkeypatch):
                     assert np.all(np.diff(offs) > 0)
                     assert np.all(np.isnan(halo[start:start + offs.size])), "blocks of different owners overlap"
                     halo[start:start + offs.size] = u0[offs]
-            assert not np.isnan(halo).any(), "every halo slot is written by exactly one peer"
+            written = ~np.isnan(halo)
+            assert written.sum() == plan["need"].size, "every needed output is written by exactly one peer (the rest is alignment padding)"
             own = np.full(im.lastidx_dynamic, np.nan)
             for a, b in D.state_segments(probe.vertexbatches, *rr[r]):
                 own[a:b] = u0[a:b]
