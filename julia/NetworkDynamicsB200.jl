@@ -260,5 +260,30 @@ function pack_params!(nw::Network{<:B200Execution}, p)
     nothing
 end
 
+# ---- printing (src/show.jl:46-49 prints every reference aggregator as Name(repr(f))) ----------------------------------
+Base.show(io::IO, s::B200Aggregator) = print(io, "B200Aggregator($(repr(s.f)))")
+Base.show(io::IO, ::B200Execution{buffered}) where {buffered} = print(io, "B200Execution{$buffered}()")
+
+# ---- get_buffers (src/coreloop.jl:103-109: `nw(nothing, u, p, t; RET=Val(:buf_init))` returns (o, aggbuf, extbuf)) ------
+# The engine never materialises `o` / `aggbuf` during the RHS; nd_b200_get_buffers fills caller-owned device vectors in the
+# reference's layouts (vertex outputs, then per edge the src range and the dst range; aggregation slots).  External inputs
+# have no buffer in the engine (they are gathered inside the vertex phase), so the third element is `nothing` unless the
+# network has them, in which case the call is refused like every unsupported path (no CPU fallback).
+function NetworkDynamics.get_buffers(nw::Network{<:B200Execution}, u::CuArray{Float64}, p, t; initbufs=true, kwargs...)
+    isempty(kwargs) || throw(ArgumentError("B200Execution: get_buffers takes no perturbation keywords"))
+    NetworkDynamics.has_external_input(nw.im) &&
+        throw(ArgumentError("B200Execution: get_buffers of a network with external inputs is not supported (no CPU fallback)"))
+    length(u) == nw.im.lastidx_dynamic || throw(ArgumentError("u does not have expected size $(nw.im.lastidx_dynamic)"))
+    h = nw.layer.aggregator.handle
+    o = CUDA.fill(NaN, nw.im.lastidx_out)            # fill!(o, NaN), src/coreloop.jl:26 (entries no component writes stay NaN)
+    aggbuf = CUDA.zeros(Float64, nw.im.lastidx_aggr)
+    pp = NetworkDynamics.pdim(nw) > 0 ? pointer(p::CuArray{Float64}) : CuPtr{Float64}(0)
+    rc = ccall((:nd_b200_get_buffers, libnd_b200), Cint,
+               (Ptr{Cvoid}, CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, Cdouble, Ptr{Cvoid}),
+               h, pointer(o), pointer(aggbuf), pointer(u), pp, Float64(t), stream().handle)
+    _check(rc, h)
+    (o, aggbuf, nothing)
+end
+
 export B200Execution, B200Aggregator, rk4!, pack_params!
 end # module

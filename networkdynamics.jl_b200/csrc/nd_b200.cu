@@ -82,6 +82,10 @@ struct nd_b200_engine {
   double* d_oedge = nullptr;
   // jagged layout (ND_B200_KERNEL=jag): warp slices, see rhs_jag_kernel
   int jag = 0, jag_u = 2, jag_wps = 0, jsplit = 32;
+  int jag_persist = 0, jag_block = 128;   // persistent warps (rhs_jag_persist_kernel) / 64-thread blocks, ND_B200_JAG_PERSIST, ND_B200_JAG_BLOCK
+  int num_sms = 148;
+  unsigned long long* d_coop_bar = nullptr;   // arrival counter of the persistent RK4 kernel's grid barrier
+  int jaga = 0, jaga_ch = 8, jaga_wps = 48;   // asynchronous-gather variant of the jagged kernel (rhs_jaga_kernel), columns per chunk
   int nslices = 0, n_jag_blocks = 0, n_jlong = 0;
   int4 *d_jslices = nullptr, *d_jlong = nullptr;
   uint16_t* d_jlanes = nullptr;
@@ -414,6 +418,124 @@ cudaError_t launch_jag(nd_b200_engine* e, const KParams& P, cudaStream_t st) {
   }
 }
 
+// ---- persistent jagged kernel / 64-thread blocks (single GPU, one vertex output, single-batch registry edge kinds) ------
+template <int EK, int PE, bool PK>
+cudaError_t launch_jag_alt_t(const nd_b200_engine* e, const KParams& P, cudaStream_t st) {
+  const int wps = e->jag_wps > 0 ? e->jag_wps : 32;
+  if (e->jag_persist) {
+    const int grid = std::min((e->nslices + 3) / 4, e->num_sms * ((wps >= 64 ? 64 : wps >= 48 ? 48 : 32) / 4));
+    if (std::max(grid, std::min(e->n_jlong, 1)) == 0) return cudaSuccess;
+    const int g = std::max(grid, 1);
+    if (e->jag_u >= 4) {
+      if (wps >= 48) ND_LAUNCH(g, 128, st, (P), rhs_jag_persist_kernel<1, 1, EK, PE, 128, 4, 48, PK>);
+      else ND_LAUNCH(g, 128, st, (P), rhs_jag_persist_kernel<1, 1, EK, PE, 128, 4, 32, PK>);
+    } else {
+      if (wps >= 64) ND_LAUNCH(g, 128, st, (P), rhs_jag_persist_kernel<1, 1, EK, PE, 128, 2, 64, PK>);
+      else if (wps >= 48) ND_LAUNCH(g, 128, st, (P), rhs_jag_persist_kernel<1, 1, EK, PE, 128, 2, 48, PK>);
+      else ND_LAUNCH(g, 128, st, (P), rhs_jag_persist_kernel<1, 1, EK, PE, 128, 2, 32, PK>);
+    }
+    return cudaGetLastError();
+  }
+  // 64-thread blocks: two slices per block
+  KParams Q = P;
+  Q.n_jag_blocks = (e->nslices + 1) / 2;
+  const int grid = Q.n_jag_blocks + e->n_jlong;
+  if (grid == 0) return cudaSuccess;
+  if (wps >= 64) ND_LAUNCH(grid, 64, st, (Q), rhs_jag_kernel<1, 1, EK, PE, 64, 2, 64, false, PK>);
+  else if (wps >= 48) ND_LAUNCH(grid, 64, st, (Q), rhs_jag_kernel<1, 1, EK, PE, 64, 2, 48, false, PK>);
+  else ND_LAUNCH(grid, 64, st, (Q), rhs_jag_kernel<1, 1, EK, PE, 64, 2, 32, false, PK>);
+  return cudaGetLastError();
+}
+template <int EK, int PE>
+cudaError_t launch_jag_alt_p(const nd_b200_engine* e, const KParams& P, cudaStream_t st) {
+  if constexpr (PE > 0) {
+    if (e->pack_on) return launch_jag_alt_t<EK, PE, true>(e, P, st);
+  }
+  return launch_jag_alt_t<EK, PE, false>(e, P, st);
+}
+bool jag_alt_ok(const nd_b200_engine* e, const KParams& P) {
+  return (e->jag_persist || e->jag_block == 64) && e->vdepth == 1 && e->edepth == 1 && e->halo_base == INT_MAX && e->launch_nblk < 0 &&
+         P.blk_off == 0 && (e->ek == ND_B200_E_DIFFUSION || e->ek == ND_B200_E_DIFFUSION_NOP || e->ek == ND_B200_E_KURAMOTO);
+}
+cudaError_t launch_jag_alt(nd_b200_engine* e, const KParams& P, cudaStream_t st) {
+  e->launches += (e->n_jag_blocks + e->n_jlong > 0);
+  switch (e->ek) {
+    case ND_B200_E_DIFFUSION: return launch_jag_alt_p<ND_B200_E_DIFFUSION, 1>(e, P, st);
+    case ND_B200_E_DIFFUSION_NOP: return launch_jag_alt_p<ND_B200_E_DIFFUSION_NOP, 0>(e, P, st);
+    default: return launch_jag_alt_p<ND_B200_E_KURAMOTO, 1>(e, P, st);
+  }
+}
+
+// ---- persistent cooperative RK4 (rk4_jag_coop_kernel) ---------------------------------------------------------------------
+constexpr int COOP_BLOCK = 256;
+template <int VD, int ED, int EK, int PE, bool PK>
+cudaError_t launch_rk4_coop_t(nd_b200_engine* e, const KParams& P, const CoopArgs& R, cudaStream_t st, bool query, int* max_grid) {
+#ifndef ND_CUSIM
+  auto kern = rk4_jag_coop_kernel<VD, ED, EK, PE, COOP_BLOCK, 2, PK>;
+  int per_sm = 0;
+  cudaError_t c = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, COOP_BLOCK, 0);
+  if (c != cudaSuccess) return c;
+  const int cap = per_sm * e->num_sms;
+  if (query) { *max_grid = cap; return cudaSuccess; }
+  const int want = std::max((e->nslices + COOP_BLOCK / 32 - 1) / (COOP_BLOCK / 32), std::min(e->n_jlong, cap));
+  const int grid = std::max(1, std::min(cap, want));
+  void* args[] = {const_cast<KParams*>(&P), const_cast<CoopArgs*>(&R)};
+  return cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)grid), dim3(COOP_BLOCK), args, 0, st);
+#else
+  (void)e; (void)P; (void)R; (void)st; (void)query; (void)max_grid;
+  return cudaErrorInvalidConfiguration;
+#endif
+}
+template <int VD, int ED, int EK, int PE>
+cudaError_t launch_rk4_coop_p(nd_b200_engine* e, const KParams& P, const CoopArgs& R, cudaStream_t st, bool query, int* max_grid) {
+  if constexpr (PE > 0 && EK != EK_GENERIC) {
+    if (e->pack_on) return launch_rk4_coop_t<VD, ED, EK, PE, true>(e, P, R, st, query, max_grid);
+  }
+  return launch_rk4_coop_t<VD, ED, EK, PE, false>(e, P, R, st, query, max_grid);
+}
+cudaError_t launch_rk4_coop(nd_b200_engine* e, const KParams& P, const CoopArgs& R, cudaStream_t st, bool query = false, int* max_grid = nullptr) {
+  if (e->vdepth == 2) return launch_rk4_coop_p<2, 2, ND_B200_E_LINE_DQ, 3>(e, P, R, st, query, max_grid);
+  switch (e->ek) {
+    case ND_B200_E_DIFFUSION: return launch_rk4_coop_p<1, 1, ND_B200_E_DIFFUSION, 1>(e, P, R, st, query, max_grid);
+    case ND_B200_E_DIFFUSION_NOP: return launch_rk4_coop_p<1, 1, ND_B200_E_DIFFUSION_NOP, 0>(e, P, R, st, query, max_grid);
+    case ND_B200_E_KURAMOTO: return launch_rk4_coop_p<1, 1, ND_B200_E_KURAMOTO, 1>(e, P, R, st, query, max_grid);
+    default: return launch_rk4_coop_p<1, 1, EK_GENERIC, 1>(e, P, R, st, query, max_grid);
+  }
+}
+
+// ---- asynchronous-gather jagged kernel launches ----------------------------------------------------------------------
+template <int EK, int PE, bool PK>
+cudaError_t launch_jaga_t(const nd_b200_engine* e, const KParams& P, cudaStream_t st) {
+  const int grid = (e->launch_nblk >= 0 ? e->launch_nblk : e->n_jag_blocks + e->n_jlong) + P.n_pub + P.fence;
+  if (grid == 0) return cudaSuccess;
+  if (e->halo_base != INT_MAX) ND_LAUNCH(grid, 128, st, (P), rhs_jaga_kernel<EK, PE, PK, 8, 48, true>);
+  else if (e->jaga_ch >= 16) ND_LAUNCH(grid, 128, st, (P), rhs_jaga_kernel<EK, PE, PK, 16, 24, false>);
+  else if (e->jaga_ch >= 8) {
+    if (e->jaga_wps >= 48) ND_LAUNCH(grid, 128, st, (P), rhs_jaga_kernel<EK, PE, PK, 8, 48, false>);
+    else ND_LAUNCH(grid, 128, st, (P), rhs_jaga_kernel<EK, PE, PK, 8, 32, false>);
+  } else {
+    if (e->jaga_wps >= 64) ND_LAUNCH(grid, 128, st, (P), rhs_jaga_kernel<EK, PE, PK, 4, 64, false>);
+    else ND_LAUNCH(grid, 128, st, (P), rhs_jaga_kernel<EK, PE, PK, 4, 48, false>);
+  }
+  return cudaGetLastError();
+}
+template <int EK, int PE>
+cudaError_t launch_jaga_p(const nd_b200_engine* e, const KParams& P, cudaStream_t st) {
+  if constexpr (PE > 0) {
+    if (e->pack_on) return launch_jaga_t<EK, PE, true>(e, P, st);
+  }
+  return launch_jaga_t<EK, PE, false>(e, P, st);
+}
+cudaError_t launch_jaga(nd_b200_engine* e, const KParams& P, cudaStream_t st) {
+  e->launches += (e->n_jag_blocks + e->n_jlong > 0);
+  switch (e->ek) {
+    case ND_B200_E_DIFFUSION: return launch_jaga_p<ND_B200_E_DIFFUSION, 1>(e, P, st);
+    case ND_B200_E_DIFFUSION_NOP: return launch_jaga_p<ND_B200_E_DIFFUSION_NOP, 0>(e, P, st);
+    case ND_B200_E_KURAMOTO: return launch_jaga_p<ND_B200_E_KURAMOTO, 1>(e, P, st);
+    default: return cudaErrorInvalidConfiguration;
+  }
+}
+
 // ---- streamed jagged kernel launches -----------------------------------------------------------------------------------
 template <int EK, int PE, bool PK, int U, int NST, int MINB>
 cudaError_t launch_js_inst(const nd_b200_engine* e, const KParams& P, cudaStream_t st, bool prepare) {
@@ -477,6 +599,8 @@ cudaError_t launch_custom(nd_b200_engine* e, const KParams& P, cudaStream_t st) 
 cudaError_t launch_fused(nd_b200_engine* e, const KParams& P, cudaStream_t st) {
   if (e->custom) return launch_custom(e, P, st);
   if (e->jstream) return launch_js(e, P, st);
+  if (e->jaga) return launch_jaga(e, P, st);
+  if (e->jag && jag_alt_ok(e, P)) return launch_jag_alt(e, P, st);
   if (e->jag) return launch_jag(e, P, st);
   if (e->split) {
     // edge pass (PASS 5) then row pass (aggregate + PASS 6); P.gsrc is the gather source of this evaluation
@@ -761,6 +885,13 @@ struct EngineBuilder {
       return fail(e, ND_B200_EINVAL, "descriptor with missing tables");
     if (d->vdepth < 1 || (d->ne > 0 && d->edepth < 1)) return fail(e, ND_B200_EINVAL, "vdepth / edepth must be positive");
     e->device = d->device;
+#ifndef ND_CUSIM
+    if (!(d->flags & ND_B200_FLAG_HOST_ONLY)) {
+      int sms = 0;
+      if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device) == cudaSuccess && sms > 0) e->num_sms = sms;
+      else cudaGetLastError();
+    }
+#endif
     e->nv = d->nv; e->ne = d->ne; e->vdepth = d->vdepth; e->edepth = d->ne > 0 ? d->edepth : d->vdepth;
     e->lastidx_dynamic = d->lastidx_dynamic; e->lastidx_p = d->lastidx_p;
     e->lastidx_out = d->lastidx_out; e->lastidx_aggr = d->lastidx_aggr;
@@ -1274,15 +1405,24 @@ struct EngineBuilder {
     const bool js_ok = !e->custom && d->vdepth == 1 && e->edepth == 1 && e->gather_from_u && !d->gather_offset && !any_ode &&
                        (e->ek == ND_B200_E_DIFFUSION || e->ek == ND_B200_E_DIFFUSION_NOP || e->ek == ND_B200_E_KURAMOTO) && e->c_maxdim <= ND_MAX_VDIM;
     e->jstream = 0;
+    // asynchronous-gather jagged kernel (rhs_jaga_kernel): single-batch benchmark edge kinds, one vertex output
+    const bool jaga_ok = !e->custom && d->vdepth == 1 && e->edepth == 1 && !any_ode &&
+                         (e->ek == ND_B200_E_DIFFUSION || e->ek == ND_B200_E_DIFFUSION_NOP || e->ek == ND_B200_E_KURAMOTO) && e->c_maxdim <= ND_MAX_VDIM;
+    e->jaga = 0;
     if (const char* s = getenv("ND_B200_KERNEL")) {
       if (!strcmp(s, "jag")) e->jag = 1;
+      else if (!strcmp(s, "jaga") && jaga_ok) { e->jag = 1; e->jaga = 1; }
       else if (!strcmp(s, "js") && js_ok) { e->jag = 1; e->jstream = 1; }
       else if (!strcmp(s, "fused") || !strcmp(s, "split") || !strcmp(s, "v1")) e->jag = 0;
     }
     if (e->split) { e->jag = 0; e->jstream = 0; }
     if (d->long_row_threshold > 63 * 32) { e->jag = 0; e->jstream = 0; }
     for (const HostVB& h : e->hvb) if (h.pdim > 4) e->jstream = 0;      // the kernel prefetches up to 4 vertex parameters
-    if (!e->jag) e->jstream = 0;
+    if (!e->jag) { e->jstream = 0; e->jaga = 0; }
+    if (const char* s = getenv("ND_B200_JAG_PERSIST")) e->jag_persist = atoi(s) > 0;
+    if (const char* s = getenv("ND_B200_JAG_BLOCK")) e->jag_block = atoi(s) == 64 ? 64 : 128;
+    if (const char* s = getenv("ND_B200_JAGA_CH")) e->jaga_ch = atoi(s);
+    if (const char* s = getenv("ND_B200_JAGA_WPS")) e->jaga_wps = atoi(s);
     e->jag_u = 2;
     e->jag_wps = 32;   // spill-free register budget of the software-pipelined walk, best measured (profiles/r02d)
     jag_pe = any_epar || (generic_edges && !e->custom);   // kernels instantiated with PE > 0 read {nbr, epar} pairs
@@ -1739,7 +1879,7 @@ void nd_b200_destroy(nd_b200_engine* e) {
   for (int* q : e->d_esrc_off) cudaFree(q);
   for (int* q : e->d_edst_off) cudaFree(q);
   cudaFree(e->d_aggrow); cudaFree(e->d_aggidx);
-  cudaFree(e->d_tmpA); cudaFree(e->d_tmpB); cudaFree(e->d_ksum);
+  cudaFree(e->d_tmpA); cudaFree(e->d_tmpB); cudaFree(e->d_ksum); cudaFree(e->d_coop_bar);
   cudaFree(e->d_hu); cudaFree(e->d_hp); cudaFree(e->d_hdu);
   if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
   if (e->s_copy) cudaStreamDestroy(e->s_copy);
@@ -1985,6 +2125,34 @@ int nd_b200_rk4(nd_b200_engine* e, double* u, const double* p, double t0, double
     if (want && nd_b200_pack_params(e, p, stream) == ND_B200_OK) unpack.on = true;
   }
   if (!e->gather_from_u && !e->custom) CUDA_TRY(e, launch_vout(e, u, p, e->d_vout[0], st, t0));
+#ifndef ND_CUSIM
+  // Small graphs (one stage = about one wave of thread blocks): all steps and stages in ONE cooperative launch with grid-wide
+  // barriers between the stages (rk4_jag_coop_kernel).  ND_B200_RK4_COOP=1 / 0 forces / forbids it.
+  if (e->jag && !e->jaga && !e->jstream && !e->custom && e->ode.empty() && !e->split && e->jag_u <= 2) {
+    const char* s = getenv("ND_B200_RK4_COOP");
+    bool want = s ? atoi(s) > 0 : true;
+    if (want) {
+      KParams P;
+      fill_params(e, P);
+      P.p = p; P.mode = MODE_RK; P.u0 = u; P.ksum = e->d_ksum; P.h6 = dt / 6.0;
+      CoopArgs R;
+      R.u = u; R.tmpA = e->d_tmpA; R.tmpB = e->d_tmpB; R.vout0 = e->d_vout[0]; R.vout1 = e->d_vout[1];
+      R.t0 = t0; R.dt = dt; R.nsteps = nsteps;
+      int cap = 0;
+      CUDA_TRY(e, launch_rk4_coop(e, P, R, st, true, &cap));
+      // default: only while every warp of the resident grid walks at most two slices per stage
+      if (!s) want = (long long)e->nslices <= 2LL * cap * (COOP_BLOCK / 32) && cap > 0;
+      if (want && cap > 0) {
+        if (!e->d_coop_bar) CUDA_TRY(e, cudaMalloc((void**)&e->d_coop_bar, sizeof(unsigned long long)));
+        CUDA_TRY(e, cudaMemsetAsync(e->d_coop_bar, 0, sizeof(unsigned long long), st));
+        R.barrier = e->d_coop_bar;
+        CUDA_TRY(e, launch_rk4_coop(e, P, R, st));
+        e->launches += 1;
+        return ND_B200_OK;
+      }
+    }
+  }
+#endif
   // The registry models are autonomous, so one captured step can be replayed for every t.  User-supplied kinds may read
   // t: their steps are enqueued one by one with the right stage times.
   if (e->custom) {
@@ -2059,6 +2227,7 @@ const char* nd_b200_custom_source(const nd_b200_engine* e) { return (e && e->cus
 const char* nd_b200_kernel_name(const nd_b200_engine* e) {
   if (!e) return "";
   if (e->jstream) return "rhs_js_kernel";
+  if (e->jaga) return "rhs_jaga_kernel";
   if (e->jag) return "rhs_jag_kernel";
   if (e->split) return "edge_pass_kernel+row_pass_kernel";
   return "rhs_fused_kernel";

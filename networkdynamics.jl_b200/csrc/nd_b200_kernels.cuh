@@ -1172,27 +1172,9 @@ __device__ __forceinline__ void long_row_block(const KParams& P, const int4 d, d
   }
 }
 
-template <int VD, int ED, int EK, int PE, int BLOCK, int U, int WPS, bool HALO, bool PK = false>
-__global__ void __launch_bounds__(BLOCK, (WPS * 32) / BLOCK) rhs_jag_kernel(const __grid_constant__ KParams P) {
-  __shared__ double s_val[BLOCK * ED];   // long rows only
-  if constexpr (HALO) {
-    if ((int)blockIdx.x < P.n_pub) { publish_block(P.H, blockIdx.x, P.n_pub); return; }
-    if (P.fence && blockIdx.x == gridDim.x - 1) { halo_wait(P); return; }
-  }
-  const int bid = (int)blockIdx.x - (HALO ? P.n_pub : 0) + P.blk_off;
-  if (bid >= P.n_jag_blocks) {
-    if constexpr (HALO) halo_wait(P);
-    long_row_block<VD, ED, EK, PE, BLOCK, HALO, PK>(P, __ldg(&P.jlong[bid - P.n_jag_blocks]), s_val);
-    return;
-  }
-  const int lane = threadIdx.x & 31;
-  const int sl = bid * (BLOCK / 32) + (threadIdx.x >> 5);
-  if (sl >= P.nslices) return;           // warp-uniform
-  if constexpr (HALO) {
-    if (sl >= P.wait_from) halo_wait_warp(P);   // this slice reads the halo
-  }
-  const int4 S = __ldg(&P.jslices[sl]);
-  const unsigned desc = __ldg(&P.jlanes[(long long)sl * 32 + lane]);
+// one 32-lane slice of the jagged layout, executed by one warp (body of rhs_jag_kernel and of the persistent RK4 kernel)
+template <int VD, int ED, int EK, int PE, int U, bool HALO, bool PK>
+__device__ __forceinline__ void jag_slice(const KParams& P, const int4 S, const unsigned desc, const int lane) {
   const int len = desc & 63;
   const int row = S.y + ((desc >> 6) & 127);
   const bool head = (desc >> 13) & 1, valid = (desc >> 14) & 1;
@@ -1329,6 +1311,278 @@ __global__ void __launch_bounds__(BLOCK, (WPS * 32) / BLOCK) rhs_jag_kernel(cons
     double v[ND_MAX_VDIM];
     load_vertex_state(P, B, row, v);
     vertex_phase<VD, ED>(P, B, row, acc, self, v, P.p + B.p0 + (long long)(row - B.row0) * B.pdim);
+  }
+}
+
+template <int VD, int ED, int EK, int PE, int BLOCK, int U, int WPS, bool HALO, bool PK = false>
+__global__ void __launch_bounds__(BLOCK, (WPS * 32) / BLOCK) rhs_jag_kernel(const __grid_constant__ KParams P) {
+  __shared__ double s_val[BLOCK * ED];   // long rows only
+  if constexpr (HALO) {
+    if ((int)blockIdx.x < P.n_pub) { publish_block(P.H, blockIdx.x, P.n_pub); return; }
+    if (P.fence && blockIdx.x == gridDim.x - 1) { halo_wait(P); return; }
+  }
+  const int bid = (int)blockIdx.x - (HALO ? P.n_pub : 0) + P.blk_off;
+  if (bid >= P.n_jag_blocks) {
+    if constexpr (HALO) halo_wait(P);
+    long_row_block<VD, ED, EK, PE, BLOCK, HALO, PK>(P, __ldg(&P.jlong[bid - P.n_jag_blocks]), s_val);
+    return;
+  }
+  const int lane = threadIdx.x & 31;
+  const int sl = bid * (BLOCK / 32) + (threadIdx.x >> 5);
+  if (sl >= P.nslices) return;           // warp-uniform
+  if constexpr (HALO) {
+    if (sl >= P.wait_from) halo_wait_warp(P);   // this slice reads the halo
+  }
+  jag_slice<VD, ED, EK, PE, U, HALO, PK>(P, __ldg(&P.jslices[sl]), __ldg(&P.jlanes[(long long)sl * 32 + lane]), lane);
+}
+
+// persistent variant (ND_B200_JAG_PERSIST=1, single GPU): the grid is sized to the machine, warps stride over the slices and
+// load the NEXT slice's descriptors before walking the current one.  rhs_jag_kernel's achieved occupancy on config 2 is
+// 56 % of the SM's warp slots against 75 % allocated (profiles/r02b_jag128_packed_cfg2_ncu_summary.txt): a block's slot
+// stays occupied until its slowest warp ends, and every fresh warp starts with three dependent loads.
+template <int VD, int ED, int EK, int PE, int BLOCK, int U, int WPS, bool PK = false>
+__global__ void __launch_bounds__(BLOCK, (WPS * 32) / BLOCK) rhs_jag_persist_kernel(const __grid_constant__ KParams P) {
+  __shared__ double s_val[BLOCK * ED];   // long rows only
+  const int lane = threadIdx.x & 31;
+  const int nwarps = (int)gridDim.x * (BLOCK / 32);
+  int sl = (int)blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5);
+  if (sl < P.nslices) {
+    int4 S = __ldg(&P.jslices[sl]);
+    unsigned desc = __ldg(&P.jlanes[(long long)sl * 32 + lane]);
+    while (true) {
+      const int nx = sl + nwarps;
+      int4 Sn = S;
+      unsigned dn = 0;
+      if (nx < P.nslices) { Sn = __ldg(&P.jslices[nx]); dn = __ldg(&P.jlanes[(long long)nx * 32 + lane]); }
+      jag_slice<VD, ED, EK, PE, U, false, PK>(P, S, desc, lane);
+      if (nx >= P.nslices) break;
+      sl = nx; S = Sn; desc = dn;
+    }
+  }
+  if (P.n_jlong > 0) {
+    __syncthreads();
+    for (int b = (int)blockIdx.x; b < P.n_jlong; b += (int)gridDim.x) {
+      long_row_block<VD, ED, EK, PE, BLOCK, false, PK>(P, __ldg(&P.jlong[b]), s_val);
+      __syncthreads();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// persistent cooperative RK4 (rk4_jag_coop_kernel): ALL steps and stages of nd_b200_rk4 in ONE launch.
+//
+// Why: on graphs of config-1 / config-4 size a stage kernel is one wave of thread blocks whose duration is a chain of
+// dependent memory latencies (~6 us) plus the launch gap of the next graph node -- 11.6 us per stage on config 4
+// (profiles/r02d_sweep_defaults.jsonl: 46.5 us per RK4 step) for 26 MB of L2-resident traffic.  Here the grid is launched
+// once (cudaLaunchCooperativeKernel: every block resident), warps stride over the slices of the jagged layout, and the four
+// stages of every step are separated by a grid-wide barrier (one atomic arrival per block on a monotonic counter, acquire
+// spin by thread 0, gpu-scope fences on both sides -- the fence also invalidates the SM's L1, so the next stage's gathers
+// see the other blocks' stage outputs).  Stage algebra, buffers and operation order are those of rk4_step_enqueue /
+// vertex_phase: results are bit-identical to the graph-replayed stages.
+// ------------------------------------------------------------------------------------------------
+struct CoopArgs {
+  double* u;                       // state vector (in: u(t0), out: u(t0 + nsteps*dt))
+  double* tmpA;                    // stage inputs 2 and 4
+  double* tmpB;                    // stage input 3
+  double* vout0;                   // materialised vertex outputs, ping-pong (networks whose vertex g is not a state copy)
+  double* vout1;
+  double t0, dt;
+  long long nsteps;
+  unsigned long long* barrier;     // monotonic arrival counter, zeroed before the launch
+};
+#ifdef ND_CUSIM
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+#else
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+#endif
+__device__ __forceinline__ void grid_barrier(unsigned long long* ctr, unsigned long long target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ctr, 1ULL);
+    while (ld_acquire_gpu(ctr) < target) {}
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+template <int VD, int ED, int EK, int PE, int BLOCK, int U, bool PK>
+__global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) rk4_jag_coop_kernel(const __grid_constant__ KParams P0, const __grid_constant__ CoopArgs R) {
+  __shared__ double s_val[BLOCK * ED];   // long rows only
+  KParams P = P0;
+  const int lane = threadIdx.x & 31;
+  const int nwarps = (int)gridDim.x * (BLOCK / 32);
+  const int gw = (int)blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5);
+  const double h2 = 0.5 * R.dt;
+  unsigned long long target = 0;
+  for (long long step = 0; step < R.nsteps; ++step) {
+    const double t = R.t0 + (double)step * R.dt;
+#pragma unroll 1
+    for (int s = 0; s < 4; ++s) {
+      P.stage = s + 1;
+      P.u = s == 0 ? R.u : (s == 2 ? R.tmpB : R.tmpA);
+      P.unext = s == 0 ? R.tmpA : (s == 1 ? R.tmpB : (s == 2 ? R.tmpA : R.u));
+      P.hs = s == 2 ? R.dt : (s == 3 ? 0.0 : h2);
+      P.t = s == 0 ? t : (s == 3 ? t + R.dt : t + h2);
+      if (P0.gather_from_u) { P.gsrc = P.u; P.vout_next = nullptr; }
+      else { P.gsrc = (s & 1) ? R.vout1 : R.vout0; P.vout_next = (s & 1) ? R.vout0 : R.vout1; }
+      for (int sl = gw; sl < P0.nslices; sl += nwarps)
+        jag_slice<VD, ED, EK, PE, U, false, PK>(P, __ldg(&P0.jslices[sl]), __ldg(&P0.jlanes[(long long)sl * 32 + lane]), lane);
+      for (int b = (int)blockIdx.x; b < P0.n_jlong; b += (int)gridDim.x) {
+        long_row_block<VD, ED, EK, PE, BLOCK, false, PK>(P, __ldg(&P0.jlong[b]), s_val);
+        __syncthreads();
+      }
+      target += gridDim.x;
+      grid_barrier(R.barrier, target);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// asynchronous-gather jagged kernel (rhs_jaga_kernel): the layout of rhs_jag_kernel, the gathers as LDGSTS.
+//
+// Why (profiles/r02b_jag128_packed_cfg2_ncu_summary.txt): rhs_jag_kernel keeps the L1TEX pipe only 45 % busy on config 2 --
+// it is bound by the number of gathers IN FLIGHT, not by the gather rate: a lane holds U = 2 gathered values in registers per
+// iteration, ~2 K gathers per SM, while tools/gather_bench.cu needs >= 8 K per SM to reach the tag-stage rate
+// (profiles/r02a_gather_bench_raw.txt: ILP1 47 us, ILP4 35 us, ILP8 33 us).  Registers are the limit of the register-gather
+// form (U = 8 was measured slower, profiles/r02c_sweep_jag_deep_unroll.jsonl).  Here the gathered values never wait in
+// registers: for a chunk of CH columns of its slice the warp
+//   (1) counts the chunk's entries (CH ballots) -- they are one contiguous piece of the slice's entry stream;
+//   (2) walks that piece 32 entries at a time: coalesced index (and packed-parameter position) loads, then ONE cp.async
+//       (LDGSTS, 8 bytes) per entry that copies the neighbour's output -- and the entry's edge parameter -- straight into
+//       the warp's panel in shared memory; up to 32*CH gathers per warp in flight at no register cost;
+//   (3) waits for the group (cp.async.wait_group + __syncwarp), then every lane reads ITS row's entries from the panel
+//       (consecutive lanes read consecutive words: conflict-free) and adds them in the reference's sequential order
+//       (src/aggregators.jl:140-151) -- bit-identical to rhs_jag_kernel.
+// Single vertex output, single-batch registry edge kinds (vdepth = edepth = 1), rows split over lanes and whole-block rows
+// exactly as in rhs_jag_kernel.
+// ------------------------------------------------------------------------------------------------
+#ifdef ND_CUSIM
+__device__ __forceinline__ void cp_async_f64(double* dst, const double* src) { *dst = *src; }
+__device__ __forceinline__ void cp_async_commit() {}
+__device__ __forceinline__ void cp_async_wait_all() {}
+#else
+__device__ __forceinline__ void cp_async_f64(double* dst, const double* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+#endif
+
+template <int EK, int PE, bool PK, int CH, int WPS, bool HALO>
+__global__ void __launch_bounds__(128, (WPS * 32) / 128) rhs_jaga_kernel(const __grid_constant__ KParams P) {
+  constexpr int BLOCK = 128;
+  static_assert(PE <= 1, "one parameter per edge");
+  __shared__ double s_x[BLOCK / 32][CH * 32];                    // gathered neighbour outputs of the chunk
+  __shared__ double s_p[BLOCK / 32][PE > 0 ? CH * 32 : 1];       // the entries' edge parameters
+  __shared__ unsigned char s_side[BLOCK / 32][CH * 32];          // 1: the row is the edge's src
+  if constexpr (HALO) {
+    if ((int)blockIdx.x < P.n_pub) { publish_block(P.H, blockIdx.x, P.n_pub); return; }
+    if (P.fence && blockIdx.x == gridDim.x - 1) { halo_wait(P); return; }
+  }
+  const int bid = (int)blockIdx.x - (HALO ? P.n_pub : 0) + P.blk_off;
+  if (bid >= P.n_jag_blocks) {
+    if constexpr (HALO) halo_wait(P);
+    static_assert(CH * 32 * (BLOCK / 32) >= BLOCK, "panel too small for the block tree");
+    long_row_block<1, 1, EK, PE, BLOCK, HALO, PK>(P, __ldg(&P.jlong[bid - P.n_jag_blocks]), &s_x[0][0]);
+    return;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sl = bid * (BLOCK / 32) + warp;
+  if (sl >= P.nslices) return;           // warp-uniform
+  if constexpr (HALO) {
+    if (sl >= P.wait_from) halo_wait_warp(P);   // this slice reads the halo
+  }
+  const int4 S = __ldg(&P.jslices[sl]);
+  const unsigned desc = __ldg(&P.jlanes[(long long)sl * 32 + lane]);
+  const int len = desc & 63;
+  const int row = S.y + ((desc >> 6) & 127);
+  const bool head = (desc >> 13) & 1, valid = (desc >> 14) & 1;
+  const VBDev& B = P.vb[S.z];
+  const int coupling0 = P.n_eb > 0 ? P.eb[0].coupling : 0;
+  const unsigned lt = (1u << lane) - 1u;
+  double* sx = s_x[warp];
+  double* sp = s_p[warp];
+  unsigned char* ss = s_side[warp];
+
+  double self = 0.0;
+  if (valid) self = P.gsrc[P.gather_from_u ? (B.state0 + (long long)(row - B.row0) * B.dim) : (long long)row];
+  double acc = 0.0;
+  int cb = S.x;
+  for (int c0 = 0;; c0 += CH) {
+    // (1) this lane's positions inside the chunk, the chunk's entry count
+    const unsigned m0 = __ballot_sync(0xffffffffu, c0 < len);
+    if (m0 == 0u) break;
+    unsigned posw[(CH + 1) / 2];         // positions inside the chunk (< 32*CH <= 65536), two per word
+    int n_c = 0;
+#pragma unroll
+    for (int q = 0; q < CH; ++q) {
+      const unsigned m = q == 0 ? m0 : __ballot_sync(0xffffffffu, c0 + q < len);
+      const unsigned pq = (unsigned)(n_c + __popc(m & lt));
+      if (q & 1) posw[q >> 1] |= pq << 16; else posw[q >> 1] = pq;
+      n_c += __popc(m);
+    }
+    // (2) the chunk's entries, 32 at a time: coalesced index loads, asynchronous gathers into the panel
+    int nbq[CH], epq[CH];
+#pragma unroll
+    for (int q = 0; q < CH; ++q) {
+      const int i = q * 32 + lane;
+      nbq[q] = 0; epq[q] = 0;
+      if (i < n_c) {
+        if constexpr (PE > 0 && !PK) { const int2 t2 = __ldcs(&P.jent[cb + i]); nbq[q] = t2.x; epq[q] = t2.y; }
+        else nbq[q] = __ldcs(&P.jnbr[cb + i]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < CH; ++q) {
+      const int i = q * 32 + lane;
+      if (i < n_c) {
+        const int side = nbq[q] < 0;
+        const int off = side ? ~nbq[q] : nbq[q];
+        cp_async_f64(sx + i, gather_ptr<HALO>(P, off));
+        if constexpr (PE > 0) cp_async_f64(sp + i, PK ? P.ppack + (cb + i) : P.p + epq[q]);
+        ss[i] = (unsigned char)side;
+      }
+    }
+    cp_async_commit();
+    cp_async_wait_all();
+    __syncwarp();
+    // (3) edge model + sequential accumulation in entry order
+#pragma unroll
+    for (int q = 0; q < CH; ++q) {
+      if (c0 + q < len) {
+        const int pq = (int)((posw[q >> 1] >> ((q & 1) * 16)) & 0xffffu);
+        const double xn = sx[pq];
+        double pl = 0.0;
+        if constexpr (PE > 0) pl = sp[pq];
+        double val;
+        entry_value<1, 1>(EK, coupling0, ss[pq], &self, &xn, &pl, P.t, &val);
+        acc = acc + val;
+      }
+    }
+    __syncwarp();       // the next chunk overwrites the panel
+    cb += n_c;
+  }
+  // rows cut into several lanes: the head lane adds the parts in order (as in rhs_jag_kernel)
+  if (S.w > 1) {
+    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+    const unsigned hmask = __ballot_sync(0xffffffffu, head);
+    const unsigned cont = vmask & ~hmask;
+    const unsigned above = lane == 31 ? 0u : (~cont >> (lane + 1));
+    const int nparts = 1 + (lane == 31 ? 0 : (above ? __ffs(above) - 1 : 31 - lane));
+    for (int k = 1; k < S.w; ++k) {
+      const double v = __shfl_down_sync(0xffffffffu, acc, k);
+      if (head && k < nparts) acc = acc + v;
+    }
+  }
+  if (head) {
+    double v[ND_MAX_VDIM];
+    load_vertex_state(P, B, row, v);
+    vertex_phase<1, 1>(P, B, row, &acc, &self, v, P.p + B.p0 + (long long)(row - B.row0) * B.pdim);
   }
 }
 

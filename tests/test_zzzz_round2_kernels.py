@@ -57,6 +57,51 @@ def test_streamed_jagged_kernel(nd, backend, monkeypatch, wps):
         assert np.max(np.abs(B.host(ur) - onw.rk4(u, p, 0.0, 1e-3, 20))) <= 1e-11, name
 
 
+@pytest.mark.parametrize("ch", ["4", "8", "16"])
+def test_async_gather_jagged_kernel(nd, backend, monkeypatch, ch):
+    """ND_B200_KERNEL=jaga: the jagged layout with cp.async (LDGSTS) gathers into a per-warp shared-memory panel; live and
+    packed parameters, fused RK4 epilogue; every chunk width (rows longer than the chunk take several rounds, rows longer
+    than 32 are split over lanes, the hub of the star goes to the whole-block path)"""
+    monkeypatch.setenv("ND_B200_KERNEL", "jaga")
+    monkeypatch.setenv("ND_B200_JAGA_CH", ch)
+    B = backend
+    for name, g, vm, em in _cases(nd, B.scale):
+        if name == "ba-mixed":
+            continue        # two vertex batches are fine, but keep one hub-heavy single-kind case below instead
+        nw = nd.Network(g, vm, em, aggregator=nd.B200Aggregator("+", edge_parameters="live"))
+        assert nw.kernel_name() == "rhs_jaga_kernel", name
+        onw = oracle_network(g, vm, em)
+        u = np.random.default_rng(1).random(nw.dim())
+        p = condition_params(nw, np.random.default_rng(2).random(nw.pdim()))
+        ref = onw.rhs(u, p)
+        ud, pd = B.dev(u), B.dev(p)
+        for packed in ([False, True] if em.pdim else [False]):
+            nw.pack_params(pd if packed else None)
+            du = B.nan(nw.dim())
+            nw(du, ud, pd, 0.0)
+            got = B.host(du)
+            assert not np.isnan(got).any(), (name, packed)
+            assert floored_rel_err(got, ref) <= TOL_DU, (name, packed)
+        nw.pack_params(None)
+        ur = B.dev(u)
+        nw.rk4(ur, pd, 0.0, 1e-3, 20)
+        assert np.max(np.abs(B.host(ur) - onw.rk4(u, p, 0.0, 1e-3, 20))) <= 1e-11, name
+    # power-law hubs, two vertex batches
+    L = nd.Lib
+    n = max(2000, int(20_000 * B.scale)) // 2 * 2
+    half = np.array([0] * (n // 2) + [1] * (n // 2))
+    g = nd.barabasi_albert(n, 4, seed=3)
+    vm = ([L.kuramoto_first(), L.kuramoto_second()], np.random.default_rng(7).permutation(half))
+    nw = nd.Network(g, vm, L.kuramoto_edge(), aggregator=nd.B200Aggregator("+", edge_parameters="live"))
+    assert nw.kernel_name() == "rhs_jaga_kernel"
+    onw = oracle_network(g, vm, L.kuramoto_edge())
+    u = np.random.default_rng(1).random(nw.dim())
+    p = condition_params(nw, np.random.default_rng(2).random(nw.pdim()))
+    du = B.nan(nw.dim())
+    nw(du, B.dev(u), B.dev(p), 0.0)
+    assert floored_rel_err(B.host(du), onw.rhs(u, p)) <= TOL_DU
+
+
 def test_tile_kernel_without_compact_entry_words(nd, backend, monkeypatch):
     """networks whose offsets do not fit 23 bits keep the row-id table in shared memory; force that path on a small one"""
     monkeypatch.setenv("ND_B200_KERNEL", "fused")
