@@ -82,10 +82,13 @@ struct nd_b200_engine {
   double* d_oedge = nullptr;
   // jagged layout (ND_B200_KERNEL=jag): warp slices, see rhs_jag_kernel
   int jag = 0, jag_u = 2, jag_wps = 0, jsplit = 32;
+  int jag_win = 0;                            // window mode of rhs_jag_kernel: every block = one 128-row window (slice table padded)
   int jag_persist = 0, jag_block = 128;   // persistent warps (rhs_jag_persist_kernel) / 64-thread blocks, ND_B200_JAG_PERSIST, ND_B200_JAG_BLOCK
   int num_sms = 148;
   unsigned long long* d_coop_bar = nullptr;   // arrival counter of the persistent RK4 kernel's grid barrier
   int jaga = 0, jaga_ch = 8, jaga_wps = 48;   // asynchronous-gather variant of the jagged kernel (rhs_jaga_kernel), columns per chunk
+  int pf_dist = 0;                            // L2 prefetch distance of the jagged kernels' entry streams (entries), ND_B200_PF_DIST
+  int jagb = 0;                               // batched variant (rhs_jagb_kernel); shares ND_B200_JAGA_CH / ND_B200_JAGA_WPS
   int nslices = 0, n_jag_blocks = 0, n_jlong = 0;
   int4 *d_jslices = nullptr, *d_jlong = nullptr;
   uint16_t* d_jlanes = nullptr;
@@ -280,6 +283,7 @@ void fill_params(const nd_b200_engine* e, KParams& P) {
   P.jslices = e->d_jslices; P.jlanes = e->d_jlanes; P.jnbr = e->d_jnbr; P.jent = e->d_jent; P.jebid = e->d_jebid;
   P.jlong = e->d_jlong; P.nslices = e->nslices; P.n_jag_blocks = e->n_jag_blocks;
   P.jwarp = e->d_jwarp; P.n_jwarps = e->n_jwarps; P.n_jlong = e->n_jlong;
+  P.pf_dist = e->pf_dist; P.jag_len = e->jag_len;
   P.halo = nullptr; P.halo_base = e->halo_base; P.wait_from = e->wait_from;
   P.ppack = e->pack_on ? e->d_ppack : nullptr;
 }
@@ -363,6 +367,23 @@ cudaError_t launch_jag_u(const nd_b200_engine* e, const KParams& P, cudaStream_t
   const int grid = (e->launch_nblk >= 0 ? e->launch_nblk : e->n_jag_blocks + e->n_jlong) + P.n_pub + P.fence;
   if (grid == 0) return cudaSuccess;
   const int wps = e->jag_wps > 0 ? e->jag_wps : jag_warps_per_sm_default(EK);
+  if constexpr (VD == 1 && ED == 1 && EK != EK_GENERIC && U == 2) {
+    if (e->jag_win) {   // window mode: block = 128-row window (coalesced own outputs / du / vertex data)
+      const bool halo = e->halo_base != INT_MAX;
+      if constexpr (PE > 0) {
+        if (e->pack_on) {
+          if (halo) { if (wps >= 48) ND_LAUNCH(grid, BLOCK, st, (P), rhs_jag_kernel<VD, ED, EK, PE, BLOCK, U, 48, true, true, true>); else ND_LAUNCH(grid, BLOCK, st, (P), rhs_jag_kernel<VD, ED, EK, PE, BLOCK, U, 32, true, true, true>); }
+          else if (wps >= 48) ND_LAUNCH(grid, BLOCK, st, (P), rhs_jag_kernel<VD, ED, EK, PE, BLOCK, U, 48, false, true, true>);
+          else ND_LAUNCH(grid, BLOCK, st, (P), rhs_jag_kernel<VD, ED, EK, PE, BLOCK, U, 32, false, true, true>);
+          return cudaGetLastError();
+        }
+      }
+      if (halo) { if (wps >= 48) ND_LAUNCH(grid, BLOCK, st, (P), rhs_jag_kernel<VD, ED, EK, PE, BLOCK, U, 48, true, false, true>); else ND_LAUNCH(grid, BLOCK, st, (P), rhs_jag_kernel<VD, ED, EK, PE, BLOCK, U, 32, true, false, true>); }
+      else if (wps >= 48) ND_LAUNCH(grid, BLOCK, st, (P), rhs_jag_kernel<VD, ED, EK, PE, BLOCK, U, 48, false, false, true>);
+      else ND_LAUNCH(grid, BLOCK, st, (P), rhs_jag_kernel<VD, ED, EK, PE, BLOCK, U, 32, false, false, true>);
+      return cudaGetLastError();
+    }
+  }
   if constexpr (VD == 1 && EK != EK_GENERIC && U >= 4) {
     // deep variants (single-GPU, single edge batch): all index / parameter loads of U columns are issued back to back, then
     // all U gathers -- three dependent memory levels per slice instead of 2 per pair of columns
@@ -467,7 +488,7 @@ cudaError_t launch_jag_alt(nd_b200_engine* e, const KParams& P, cudaStream_t st)
 }
 
 // ---- persistent cooperative RK4 (rk4_jag_coop_kernel) ---------------------------------------------------------------------
-constexpr int COOP_BLOCK = 256;
+constexpr int COOP_BLOCK = 1024;   // one block per SM: 148 arrivals per grid barrier
 template <int VD, int ED, int EK, int PE, bool PK>
 cudaError_t launch_rk4_coop_t(nd_b200_engine* e, const KParams& P, const CoopArgs& R, cudaStream_t st, bool query, int* max_grid) {
 #ifndef ND_CUSIM
@@ -500,6 +521,44 @@ cudaError_t launch_rk4_coop(nd_b200_engine* e, const KParams& P, const CoopArgs&
     case ND_B200_E_DIFFUSION_NOP: return launch_rk4_coop_p<1, 1, ND_B200_E_DIFFUSION_NOP, 0>(e, P, R, st, query, max_grid);
     case ND_B200_E_KURAMOTO: return launch_rk4_coop_p<1, 1, ND_B200_E_KURAMOTO, 1>(e, P, R, st, query, max_grid);
     default: return launch_rk4_coop_p<1, 1, EK_GENERIC, 1>(e, P, R, st, query, max_grid);
+  }
+}
+
+// ---- batched jagged kernel launches ------------------------------------------------------------------------------------
+template <int EK, int PE, bool PK>
+cudaError_t launch_jagb_t(const nd_b200_engine* e, const KParams& P, cudaStream_t st) {
+  const int grid = (e->launch_nblk >= 0 ? e->launch_nblk : e->n_jag_blocks + e->n_jlong) + P.n_pub + P.fence;
+  if (grid == 0) return cudaSuccess;
+  const int ch = e->jaga_ch, wps = e->jaga_wps;
+  if (e->halo_base != INT_MAX) ND_LAUNCH(grid, 128, st, (P), rhs_jagb_kernel<EK, PE, PK, 8, 32, true>);
+  else if (ch >= 16) ND_LAUNCH(grid, 128, st, (P), rhs_jagb_kernel<EK, PE, PK, 16, 24, false>);
+  else if (ch >= 8) {
+    if (wps >= 48) ND_LAUNCH(grid, 128, st, (P), rhs_jagb_kernel<EK, PE, PK, 8, 48, false>);
+    else if (wps >= 40) ND_LAUNCH(grid, 128, st, (P), rhs_jagb_kernel<EK, PE, PK, 8, 40, false>);
+    else ND_LAUNCH(grid, 128, st, (P), rhs_jagb_kernel<EK, PE, PK, 8, 32, false>);
+  } else if (ch >= 6) {
+    if (wps >= 48) ND_LAUNCH(grid, 128, st, (P), rhs_jagb_kernel<EK, PE, PK, 6, 48, false>);
+    else ND_LAUNCH(grid, 128, st, (P), rhs_jagb_kernel<EK, PE, PK, 6, 40, false>);
+  } else {
+    if (wps >= 64) ND_LAUNCH(grid, 128, st, (P), rhs_jagb_kernel<EK, PE, PK, 4, 64, false>);
+    else ND_LAUNCH(grid, 128, st, (P), rhs_jagb_kernel<EK, PE, PK, 4, 48, false>);
+  }
+  return cudaGetLastError();
+}
+template <int EK, int PE>
+cudaError_t launch_jagb_p(const nd_b200_engine* e, const KParams& P, cudaStream_t st) {
+  if constexpr (PE > 0) {
+    if (e->pack_on) return launch_jagb_t<EK, PE, true>(e, P, st);
+  }
+  return launch_jagb_t<EK, PE, false>(e, P, st);
+}
+cudaError_t launch_jagb(nd_b200_engine* e, const KParams& P, cudaStream_t st) {
+  e->launches += (e->n_jag_blocks + e->n_jlong > 0);
+  switch (e->ek) {
+    case ND_B200_E_DIFFUSION: return launch_jagb_p<ND_B200_E_DIFFUSION, 1>(e, P, st);
+    case ND_B200_E_DIFFUSION_NOP: return launch_jagb_p<ND_B200_E_DIFFUSION_NOP, 0>(e, P, st);
+    case ND_B200_E_KURAMOTO: return launch_jagb_p<ND_B200_E_KURAMOTO, 1>(e, P, st);
+    default: return cudaErrorInvalidConfiguration;
   }
 }
 
@@ -599,6 +658,7 @@ cudaError_t launch_custom(nd_b200_engine* e, const KParams& P, cudaStream_t st) 
 cudaError_t launch_fused(nd_b200_engine* e, const KParams& P, cudaStream_t st) {
   if (e->custom) return launch_custom(e, P, st);
   if (e->jstream) return launch_js(e, P, st);
+  if (e->jagb) return launch_jagb(e, P, st);
   if (e->jaga) return launch_jaga(e, P, st);
   if (e->jag && jag_alt_ok(e, P)) return launch_jag_alt(e, P, st);
   if (e->jag) return launch_jag(e, P, st);
@@ -1408,19 +1468,24 @@ struct EngineBuilder {
     // asynchronous-gather jagged kernel (rhs_jaga_kernel): single-batch benchmark edge kinds, one vertex output
     const bool jaga_ok = !e->custom && d->vdepth == 1 && e->edepth == 1 && !any_ode &&
                          (e->ek == ND_B200_E_DIFFUSION || e->ek == ND_B200_E_DIFFUSION_NOP || e->ek == ND_B200_E_KURAMOTO) && e->c_maxdim <= ND_MAX_VDIM;
-    e->jaga = 0;
+    e->jaga = 0; e->jagb = 0;
     if (const char* s = getenv("ND_B200_KERNEL")) {
       if (!strcmp(s, "jag")) e->jag = 1;
       else if (!strcmp(s, "jaga") && jaga_ok) { e->jag = 1; e->jaga = 1; }
+      else if (!strcmp(s, "jagb") && jaga_ok) { e->jag = 1; e->jagb = 1; }
       else if (!strcmp(s, "js") && js_ok) { e->jag = 1; e->jstream = 1; }
       else if (!strcmp(s, "fused") || !strcmp(s, "split") || !strcmp(s, "v1")) e->jag = 0;
     }
     if (e->split) { e->jag = 0; e->jstream = 0; }
     if (d->long_row_threshold > 63 * 32) { e->jag = 0; e->jstream = 0; }
     for (const HostVB& h : e->hvb) if (h.pdim > 4) e->jstream = 0;      // the kernel prefetches up to 4 vertex parameters
-    if (!e->jag) { e->jstream = 0; e->jaga = 0; }
+    if (!e->jag) { e->jstream = 0; e->jaga = 0; e->jagb = 0; }
     if (const char* s = getenv("ND_B200_JAG_PERSIST")) e->jag_persist = atoi(s) > 0;
     if (const char* s = getenv("ND_B200_JAG_BLOCK")) e->jag_block = atoi(s) == 64 ? 64 : 128;
+    // L2 prefetch of the entry streams, one cp.async.bulk.prefetch.L2 per slice and stream, 600 K entries (about half a wave of
+    // resident warps) ahead: measured 1.5-3 % on the large Erdos-Renyi configs (profiles/r02l_sweep_l2_prefetch.jsonl)
+    e->pf_dist = (e->jag && !e->custom && e->nentries >= 2000000) ? 600000 : 0;
+    if (const char* s = getenv("ND_B200_PF_DIST")) e->pf_dist = std::max(0, atoi(s));
     if (const char* s = getenv("ND_B200_JAGA_CH")) e->jaga_ch = atoi(s);
     if (const char* s = getenv("ND_B200_JAGA_WPS")) e->jaga_wps = atoi(s);
     e->jag_u = 2;
@@ -1443,6 +1508,12 @@ struct EngineBuilder {
       // rows longer than this are reduced by a whole block: explicit threshold if the caller gave one, else what a
       // slice can hold
       const long long block_thr = d->long_row_threshold > 0 ? std::min<long long>(d->long_row_threshold, 32LL * e->jsplit) : 32LL * e->jsplit;
+      // window mode (rhs_jag_kernel<..., WIN>): 128-row windows, one vertex output, registry kinds; ND_B200_JAG_WIN=0 disables
+      // Opt-in (ND_B200_JAG_WIN=1): measured on config 2 (profiles/r02m_sweep_window_mode.jsonl) it moves 0.7 M fewer sectors
+      // through the L1 but the two block barriers cost more than that (66.8 vs 59.0 us at 32 warps per SM, 57.5 at 48).
+      const bool pad_windows = jwindow == 128 && !e->jstream && d->vdepth == 1 && e->edepth == 1 && !e->custom && !any_ode &&
+                               getenv("ND_B200_JAG_WIN") && atoi(getenv("ND_B200_JAG_WIN")) > 0;
+      e->jag_win = pad_windows ? 1 : 0;
       std::vector<int> order;
       order.reserve((size_t)e->nentries);
       struct Lane { int rowrel, len, head; long long start; };
@@ -1504,6 +1575,12 @@ struct EngineBuilder {
               maxparts = std::max(maxparts, nparts);
             }
             flush();
+            if (pad_windows) {   // window mode: a thread block (four slices) never spans two windows
+              while (jslices.size() & 3) {
+                jslices.push_back(make_int4((int)order.size(), (int)w0, (int)b, 1));
+                for (int l = 0; l < 32; ++l) jlanes.push_back(0);
+              }
+            }
           }
         } else {
         for (long long r = lo; r < hi; ++r) {
@@ -2128,9 +2205,11 @@ int nd_b200_rk4(nd_b200_engine* e, double* u, const double* p, double t0, double
 #ifndef ND_CUSIM
   // Small graphs (one stage = about one wave of thread blocks): all steps and stages in ONE cooperative launch with grid-wide
   // barriers between the stages (rk4_jag_coop_kernel).  ND_B200_RK4_COOP=1 / 0 forces / forbids it.
-  if (e->jag && !e->jaga && !e->jstream && !e->custom && e->ode.empty() && !e->split && e->jag_u <= 2) {
+  if (e->jag && !e->jaga && !e->jagb && !e->jstream && !e->custom && e->ode.empty() && !e->split && e->jag_u <= 2) {
     const char* s = getenv("ND_B200_RK4_COOP");
-    bool want = s ? atoi(s) > 0 : true;
+    // Opt-in: measured SLOWER than the graph-replayed stages (profiles/r02g_sweep_rk4_coop.jsonl: config 4 57.4 vs 47.2 us per
+    // step, config 1 41.5 vs 35.2) -- four grid barriers per step cost more than the launch gaps they remove.
+    bool want = s ? atoi(s) > 0 : false;
     if (want) {
       KParams P;
       fill_params(e, P);
@@ -2141,7 +2220,6 @@ int nd_b200_rk4(nd_b200_engine* e, double* u, const double* p, double t0, double
       int cap = 0;
       CUDA_TRY(e, launch_rk4_coop(e, P, R, st, true, &cap));
       // default: only while every warp of the resident grid walks at most two slices per stage
-      if (!s) want = (long long)e->nslices <= 2LL * cap * (COOP_BLOCK / 32) && cap > 0;
       if (want && cap > 0) {
         if (!e->d_coop_bar) CUDA_TRY(e, cudaMalloc((void**)&e->d_coop_bar, sizeof(unsigned long long)));
         CUDA_TRY(e, cudaMemsetAsync(e->d_coop_bar, 0, sizeof(unsigned long long), st));
@@ -2227,6 +2305,7 @@ const char* nd_b200_custom_source(const nd_b200_engine* e) { return (e && e->cus
 const char* nd_b200_kernel_name(const nd_b200_engine* e) {
   if (!e) return "";
   if (e->jstream) return "rhs_js_kernel";
+  if (e->jagb) return "rhs_jagb_kernel";
   if (e->jaga) return "rhs_jaga_kernel";
   if (e->jag) return "rhs_jag_kernel";
   if (e->split) return "edge_pass_kernel+row_pass_kernel";

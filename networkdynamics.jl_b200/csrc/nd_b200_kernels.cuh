@@ -166,6 +166,10 @@ struct KParams {
   int halo_base;
   int wait_from;                       // first slice (jagged) / tile (tile kernel) that reads the halo
   int blk_off;                         // this launch covers thread blocks [blk_off, blk_off + gridDim.x) of the full grid
+  // jagged kernels: every slice asks the L2 (cp.async.bulk.prefetch.L2, off the LSU path) for the piece of the entry streams
+  // that lies pf_dist entries ahead of its own piece; 0 = off.  The slices' pieces tile the streams, so do the prefetches.
+  int pf_dist;
+  long long jag_len;                   // length of the jagged entry streams
   // multi-GPU: the first n_pub thread blocks of the grid pack this rank's boundary outputs into the peers' halo buffers
   // (NVLink stores) and raise the arrival flags; interior tiles follow, tiles that read the halo come last
   int n_pub;
@@ -1172,23 +1176,61 @@ __device__ __forceinline__ void long_row_block(const KParams& P, const int4 d, d
   }
 }
 
+// L2 prefetch of [p + first, p + first + count) elements, issued by one lane (16-byte granules; cp.async.bulk.prefetch.L2)
+template <class T>
+__device__ __forceinline__ void l2_prefetch_range(const T* p, long long first, int count, long long limit) {
+#ifndef ND_CUSIM
+  if (first >= limit || count <= 0) return;
+  if (first + count > limit) count = (int)(limit - first);
+  const unsigned long long a0 = (unsigned long long)(p + first) & ~15ULL;
+  const unsigned long long a1 = ((unsigned long long)(p + first + count) + 15ULL) & ~15ULL;
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"((unsigned)(a1 - a0)) : "memory");
+#else
+  (void)p; (void)first; (void)count; (void)limit;
+#endif
+}
+__device__ __forceinline__ int warp_sum(int v) {
+#ifndef ND_CUSIM
+  return __reduce_add_sync(0xffffffffu, v);
+#else
+  return v;
+#endif
+}
+
 // one 32-lane slice of the jagged layout, executed by one warp (body of rhs_jag_kernel and of the persistent RK4 kernel)
-template <int VD, int ED, int EK, int PE, int U, bool HALO, bool PK>
-__device__ __forceinline__ void jag_slice(const KParams& P, const int4 S, const unsigned desc, const int lane) {
+// WIN = true (rhs_jag_kernel's window mode): the block's four slices hold the rows of ONE 128-row window; the rows' own
+// outputs come from the block's shared-memory copy of the window (loaded coalesced) and the row sums are handed back
+// through shared memory, so that the vertex phase runs one thread per row in natural row order.
+template <int VD, int ED, int EK, int PE, int U, bool HALO, bool PK, bool WIN = false>
+__device__ __forceinline__ void jag_slice(const KParams& P, const int4 S, const unsigned desc, const int lane,
+                                          const double* s_self = nullptr, double* s_acc = nullptr, unsigned char* s_flag = nullptr) {
   const int len = desc & 63;
   const int row = S.y + ((desc >> 6) & 127);
   const bool head = (desc >> 13) & 1, valid = (desc >> 14) & 1;
   const VBDev B = P.vb[S.z];
   const int coupling0 = P.n_eb > 0 ? P.eb[0].coupling : 0;
   const unsigned lt = (1u << lane) - 1u;
+  if (P.pf_dist > 0) {                   // warp-uniform
+    const int es = warp_sum(len);
+    if (lane == 0) {
+      if constexpr (PE > 0 && !PK) l2_prefetch_range(P.jent, (long long)S.x + P.pf_dist, es, P.jag_len);
+      else {
+        l2_prefetch_range(P.jnbr, (long long)S.x + P.pf_dist, es, P.jag_len);
+        if constexpr (PE > 0) l2_prefetch_range(P.ppack, ((long long)S.x + P.pf_dist) * PE, es * PE, P.jag_len * PE);
+      }
+    }
+  }
 
   double self[VD];
 #pragma unroll
   for (int k = 0; k < VD; ++k) self[k] = 0.0;
   if (valid) {
-    const long long sidx = P.gather_from_u ? (B.state0 + (long long)(row - B.row0) * B.dim) : (long long)row * VD;
+    if constexpr (WIN) self[0] = s_self[(desc >> 6) & 127];
+    else {
+      const long long sidx = P.gather_from_u ? (B.state0 + (long long)(row - B.row0) * B.dim) : (long long)row * VD;
 #pragma unroll
-    for (int k = 0; k < VD; ++k) self[k] = P.gsrc[sidx + k];
+      for (int k = 0; k < VD; ++k) self[k] = P.gsrc[sidx + k];
+    }
   }
   double acc[ED];
 #pragma unroll
@@ -1308,15 +1350,25 @@ __device__ __forceinline__ void jag_slice(const KParams& P, const int4 S, const 
   }
   // (6) vertex model
   if (head) {
-    double v[ND_MAX_VDIM];
-    load_vertex_state(P, B, row, v);
-    vertex_phase<VD, ED>(P, B, row, acc, self, v, P.p + B.p0 + (long long)(row - B.row0) * B.pdim);
+    if constexpr (WIN) { s_acc[(desc >> 6) & 127] = acc[0]; s_flag[(desc >> 6) & 127] = 1; }
+    else {
+      double v[ND_MAX_VDIM];
+      load_vertex_state(P, B, row, v);
+      vertex_phase<VD, ED>(P, B, row, acc, self, v, P.p + B.p0 + (long long)(row - B.row0) * B.pdim);
+    }
   }
 }
 
-template <int VD, int ED, int EK, int PE, int BLOCK, int U, int WPS, bool HALO, bool PK = false>
+// WIN = true (degree-bucketed layout with 128-row windows, one vertex output; the engine pads every window to four slices):
+// a block IS a window.  Bucketing deals the window's rows to the lanes by degree, so a lane's own output, its du and its
+// vertex data sit anywhere in the window: profiles/r02h_cfg2_ncu_source.csv counts 681 K L2 sectors for each of the three
+// accesses where 250 K would do -- and the L2 sector rate is what bounds this kernel.  Here the block loads
+// the window's outputs once, coalesced, and runs the vertex phase one thread per row in natural order.
+template <int VD, int ED, int EK, int PE, int BLOCK, int U, int WPS, bool HALO, bool PK = false, bool WIN = false>
 __global__ void __launch_bounds__(BLOCK, (WPS * 32) / BLOCK) rhs_jag_kernel(const __grid_constant__ KParams P) {
-  __shared__ double s_val[BLOCK * ED];   // long rows only
+  __shared__ double s_val[BLOCK * ED];   // long rows; WIN: the rows' sums
+  __shared__ double s_self[WIN ? BLOCK : 1];
+  __shared__ unsigned char s_flag[WIN ? BLOCK : 1];
   if constexpr (HALO) {
     if ((int)blockIdx.x < P.n_pub) { publish_block(P.H, blockIdx.x, P.n_pub); return; }
     if (P.fence && blockIdx.x == gridDim.x - 1) { halo_wait(P); return; }
@@ -1329,11 +1381,35 @@ __global__ void __launch_bounds__(BLOCK, (WPS * 32) / BLOCK) rhs_jag_kernel(cons
   }
   const int lane = threadIdx.x & 31;
   const int sl = bid * (BLOCK / 32) + (threadIdx.x >> 5);
-  if (sl >= P.nslices) return;           // warp-uniform
-  if constexpr (HALO) {
-    if (sl >= P.wait_from) halo_wait_warp(P);   // this slice reads the halo
+  if constexpr (WIN) {
+    static_assert(!WIN || (VD == 1 && ED == 1 && BLOCK == 128), "window mode: one vertex output, 128-row windows");
+    // the engine pads the slice table to whole blocks in this mode: every warp has a slice
+    const int4 S = __ldg(&P.jslices[sl]);
+    const unsigned desc = __ldg(&P.jlanes[(long long)sl * 32 + lane]);
+    const VBDev& B = P.vb[S.z];
+    const int t = threadIdx.x;
+    const int rowt = S.y + t;             // S.y = first row of the window, the same in the block's four slices
+    s_flag[t] = 0;
+    if (rowt < B.row0 + B.nrows) s_self[t] = P.gsrc[P.gather_from_u ? (B.state0 + (long long)(rowt - B.row0) * B.dim) : (long long)rowt];
+    __syncthreads();
+    if constexpr (HALO) {
+      if (sl >= P.wait_from) halo_wait_warp(P);   // this slice reads the halo
+    }
+    jag_slice<VD, ED, EK, PE, U, HALO, PK, true>(P, S, desc, lane, s_self, s_val, s_flag);
+    __syncthreads();
+    if (s_flag[t]) {
+      const double acc = s_val[t], self = s_self[t];
+      double v[ND_MAX_VDIM];
+      load_vertex_state(P, B, rowt, v);
+      vertex_phase<VD, ED>(P, B, rowt, &acc, &self, v, P.p + B.p0 + (long long)(rowt - B.row0) * B.pdim);
+    }
+  } else {
+    if (sl >= P.nslices) return;           // warp-uniform
+    if constexpr (HALO) {
+      if (sl >= P.wait_from) halo_wait_warp(P);   // this slice reads the halo
+    }
+    jag_slice<VD, ED, EK, PE, U, HALO, PK>(P, __ldg(&P.jslices[sl]), __ldg(&P.jlanes[(long long)sl * 32 + lane]), lane);
   }
-  jag_slice<VD, ED, EK, PE, U, HALO, PK>(P, __ldg(&P.jslices[sl]), __ldg(&P.jlanes[(long long)sl * 32 + lane]), lane);
 }
 
 // persistent variant (ND_B200_JAG_PERSIST=1, single GPU): the grid is sized to the machine, warps stride over the slices and
@@ -1411,7 +1487,7 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* ctr, unsigned l
 }
 
 template <int VD, int ED, int EK, int PE, int BLOCK, int U, bool PK>
-__global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) rk4_jag_coop_kernel(const __grid_constant__ KParams P0, const __grid_constant__ CoopArgs R) {
+__global__ void __launch_bounds__(BLOCK, 1024 / BLOCK >= 1 ? 1024 / BLOCK : 1) rk4_jag_coop_kernel(const __grid_constant__ KParams P0, const __grid_constant__ CoopArgs R) {
   __shared__ double s_val[BLOCK * ED];   // long rows only
   KParams P = P0;
   const int lane = threadIdx.x & 31;
@@ -1561,6 +1637,159 @@ __global__ void __launch_bounds__(128, (WPS * 32) / 128) rhs_jaga_kernel(const _
         if constexpr (PE > 0) pl = sp[pq];
         double val;
         entry_value<1, 1>(EK, coupling0, ss[pq], &self, &xn, &pl, P.t, &val);
+        acc = acc + val;
+      }
+    }
+    __syncwarp();       // the next chunk overwrites the panel
+    cb += n_c;
+  }
+  // rows cut into several lanes: the head lane adds the parts in order (as in rhs_jag_kernel)
+  if (S.w > 1) {
+    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+    const unsigned hmask = __ballot_sync(0xffffffffu, head);
+    const unsigned cont = vmask & ~hmask;
+    const unsigned above = lane == 31 ? 0u : (~cont >> (lane + 1));
+    const int nparts = 1 + (lane == 31 ? 0 : (above ? __ffs(above) - 1 : 31 - lane));
+    for (int k = 1; k < S.w; ++k) {
+      const double v = __shfl_down_sync(0xffffffffu, acc, k);
+      if (head && k < nparts) acc = acc + v;
+    }
+  }
+  if (head) {
+    double v[ND_MAX_VDIM];
+    load_vertex_state(P, B, row, v);
+    vertex_phase<1, 1>(P, B, row, &acc, &self, v, P.p + B.p0 + (long long)(row - B.row0) * B.pdim);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// batched jagged kernel (rhs_jagb_kernel): the layout of rhs_jag_kernel, three dependent memory round trips per chunk.
+//
+// Why (profiles/r02h_cfg2_ncu_source.csv, rhs_jag_kernel on config 2): 39 % of the warp samples sit on the first use of a
+// gathered value, 8 % on the index of the next pair of columns, 6 % on the slice descriptor; a slice walks 5.1 iterations of
+// two columns, each one an exposed gather round trip, with 25 resident warps x 64 gathers = ~600 gathers in flight per SM on
+// average where the tag stage needs ~1500 (tools/path_gather_bench.cu: 0.84 per clock x ~1750 clocks of loaded latency).
+// Here a warp takes CH columns of its slice at once:
+//   (1) CH ballots give every lane its positions and the chunk's entry count (one contiguous piece of the entry stream);
+//   (2) the piece is loaded 32 entries at a time -- CH coalesced index loads and CH coalesced packed-parameter loads per
+//       lane, all independent -- and parked in the warp's panel in shared memory (plain stores);
+//   (3) every lane reads ITS entries' indices back (consecutive lanes read consecutive words), issues up to CH gathers
+//       back to back into registers, then adds the edge values in the reference's sequential order
+//       (src/aggregators.jl:140-151) -- bit-identical to rhs_jag_kernel.
+// Rows of up to CH entries cost descriptor -> stream -> gather round trips in total, with 32*CH gathers per warp in flight.
+// ------------------------------------------------------------------------------------------------
+template <int EK, int PE, bool PK, int CH, int WPS, bool HALO>
+__global__ void __launch_bounds__(128, (WPS * 32) / 128) rhs_jagb_kernel(const __grid_constant__ KParams P) {
+  constexpr int BLOCK = 128;
+  static_assert(PE <= 1, "one parameter per edge");
+  __shared__ int s_nb[BLOCK / 32][CH * 32];                      // the chunk's index words
+  __shared__ double s_p[BLOCK / 32][PE > 0 ? CH * 32 : 1];       // PK: the entries' edge parameters; else their offsets in p
+  __shared__ double s_val[BLOCK];                                // long rows only
+  if constexpr (HALO) {
+    if ((int)blockIdx.x < P.n_pub) { publish_block(P.H, blockIdx.x, P.n_pub); return; }
+    if (P.fence && blockIdx.x == gridDim.x - 1) { halo_wait(P); return; }
+  }
+  const int bid = (int)blockIdx.x - (HALO ? P.n_pub : 0) + P.blk_off;
+  if (bid >= P.n_jag_blocks) {
+    if constexpr (HALO) halo_wait(P);
+    long_row_block<1, 1, EK, PE, BLOCK, HALO, PK>(P, __ldg(&P.jlong[bid - P.n_jag_blocks]), s_val);
+    return;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sl = bid * (BLOCK / 32) + warp;
+  if (sl >= P.nslices) return;           // warp-uniform
+  if constexpr (HALO) {
+    if (sl >= P.wait_from) halo_wait_warp(P);   // this slice reads the halo
+  }
+  const int4 S = __ldg(&P.jslices[sl]);
+  const unsigned desc = __ldg(&P.jlanes[(long long)sl * 32 + lane]);
+  const int len = desc & 63;
+  const int row = S.y + ((desc >> 6) & 127);
+  const bool head = (desc >> 13) & 1, valid = (desc >> 14) & 1;
+  const VBDev& B = P.vb[S.z];
+  const int coupling0 = P.n_eb > 0 ? P.eb[0].coupling : 0;
+  const unsigned lt = (1u << lane) - 1u;
+  if (P.pf_dist > 0) {                   // warp-uniform
+    const int es = warp_sum(len);
+    if (lane == 0) {
+      if constexpr (PE > 0 && !PK) l2_prefetch_range(P.jent, (long long)S.x + P.pf_dist, es, P.jag_len);
+      else {
+        l2_prefetch_range(P.jnbr, (long long)S.x + P.pf_dist, es, P.jag_len);
+        if constexpr (PE > 0) l2_prefetch_range(P.ppack, ((long long)S.x + P.pf_dist) * PE, es * PE, P.jag_len * PE);
+      }
+    }
+  }
+  int* snb = s_nb[warp];
+  double* sp = s_p[warp];
+
+  double self = 0.0;
+  if (valid) self = P.gsrc[P.gather_from_u ? (B.state0 + (long long)(row - B.row0) * B.dim) : (long long)row];
+  double acc = 0.0;
+  int cb = S.x;
+  for (int c0 = 0;; c0 += CH) {
+    // (1) this lane's positions inside the chunk, the chunk's entry count
+    const unsigned m0 = __ballot_sync(0xffffffffu, c0 < len);
+    if (m0 == 0u) break;
+    unsigned posw[(CH + 1) / 2];         // positions inside the chunk (< 32*CH), two per word
+    int n_c = 0;
+#pragma unroll
+    for (int q = 0; q < CH; ++q) {
+      const unsigned m = q == 0 ? m0 : __ballot_sync(0xffffffffu, c0 + q < len);
+      const unsigned pq = (unsigned)(n_c + __popc(m & lt));
+      if (q & 1) posw[q >> 1] |= pq << 16; else posw[q >> 1] = pq;
+      n_c += __popc(m);
+    }
+    // (2) the chunk's piece of the entry stream -> panel
+    {
+      int nbq[CH];
+      double plq[PE > 0 ? CH : 1];
+#pragma unroll
+      for (int q = 0; q < CH; ++q) {
+        const int i = q * 32 + lane;
+        nbq[q] = 0;
+        if constexpr (PE > 0) plq[q] = 0.0;
+        if (i < n_c) {
+          if constexpr (PE > 0 && !PK) { const int2 t2 = __ldcs(&P.jent[cb + i]); nbq[q] = t2.x; plq[q] = (double)t2.y; }   // offsets < 2^31: exact
+          else nbq[q] = __ldcs(&P.jnbr[cb + i]);
+          if constexpr (PE > 0 && PK) plq[q] = __ldcs(&P.ppack[cb + i]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < CH; ++q) {
+        const int i = q * 32 + lane;
+        if (i < n_c) {
+          snb[i] = nbq[q];
+          if constexpr (PE > 0) sp[i] = plq[q];
+        }
+      }
+    }
+    __syncwarp();
+    // (3) this lane's gathers, all in flight together; then edge model + sequential accumulation in entry order
+    double xn[CH];
+    double plv[(PE > 0 && !PK) ? CH : 1];      // live parameters: a second gather per entry, issued with the first
+    unsigned sides = 0;
+#pragma unroll
+    for (int q = 0; q < CH; ++q) {
+      xn[q] = 0.0;
+      if (c0 + q < len) {
+        const int pq = (int)((posw[q >> 1] >> ((q & 1) * 16)) & 0xffffu);
+        const int nb = snb[pq];
+        const int side = nb < 0;
+        sides |= (unsigned)side << q;
+        xn[q] = *gather_ptr<HALO>(P, side ? ~nb : nb);
+        if constexpr (PE > 0 && !PK) plv[q] = P.p[(long long)sp[pq]];
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < CH; ++q) {
+      if (c0 + q < len) {
+        const int pq = (int)((posw[q >> 1] >> ((q & 1) * 16)) & 0xffffu);
+        double pl = 0.0;
+        if constexpr (PE > 0) {
+          if constexpr (PK) pl = sp[pq]; else pl = plv[q];
+        }
+        double val;
+        entry_value<1, 1>(EK, coupling0, (int)((sides >> q) & 1u), &self, &xn[q], &pl, P.t, &val);
         acc = acc + val;
       }
     }

@@ -57,19 +57,23 @@ def test_streamed_jagged_kernel(nd, backend, monkeypatch, wps):
         assert np.max(np.abs(B.host(ur) - onw.rk4(u, p, 0.0, 1e-3, 20))) <= 1e-11, name
 
 
-@pytest.mark.parametrize("ch", ["4", "8", "16"])
-def test_async_gather_jagged_kernel(nd, backend, monkeypatch, ch):
-    """ND_B200_KERNEL=jaga: the jagged layout with cp.async (LDGSTS) gathers into a per-warp shared-memory panel; live and
-    packed parameters, fused RK4 epilogue; every chunk width (rows longer than the chunk take several rounds, rows longer
-    than 32 are split over lanes, the hub of the star goes to the whole-block path)"""
-    monkeypatch.setenv("ND_B200_KERNEL", "jaga")
+@pytest.mark.parametrize("ch", ["4", "6", "8", "16"])
+@pytest.mark.parametrize("kern", ["jaga", "jagb"])
+def test_chunked_jagged_kernels(nd, backend, monkeypatch, ch, kern):
+    """ND_B200_KERNEL=jaga: the jagged layout with cp.async (LDGSTS) gathers into a per-warp shared-memory panel;
+    ND_B200_KERNEL=jagb: the chunk's index / parameter stream parked in the panel, the gathers issued back to back into
+    registers.  Live and packed parameters, fused RK4 epilogue; every chunk width (rows longer than the chunk take several
+    rounds, rows longer than 32 are split over lanes, the hub of the star goes to the whole-block path)"""
+    if kern == "jaga" and ch == "6":
+        pytest.skip("rhs_jaga_kernel is instantiated for 4, 8 and 16 columns per chunk")
+    monkeypatch.setenv("ND_B200_KERNEL", kern)
     monkeypatch.setenv("ND_B200_JAGA_CH", ch)
     B = backend
     for name, g, vm, em in _cases(nd, B.scale):
         if name == "ba-mixed":
             continue        # two vertex batches are fine, but keep one hub-heavy single-kind case below instead
         nw = nd.Network(g, vm, em, aggregator=nd.B200Aggregator("+", edge_parameters="live"))
-        assert nw.kernel_name() == "rhs_jaga_kernel", name
+        assert nw.kernel_name() == f"rhs_{kern}_kernel", name
         onw = oracle_network(g, vm, em)
         u = np.random.default_rng(1).random(nw.dim())
         p = condition_params(nw, np.random.default_rng(2).random(nw.pdim()))
@@ -93,13 +97,47 @@ def test_async_gather_jagged_kernel(nd, backend, monkeypatch, ch):
     g = nd.barabasi_albert(n, 4, seed=3)
     vm = ([L.kuramoto_first(), L.kuramoto_second()], np.random.default_rng(7).permutation(half))
     nw = nd.Network(g, vm, L.kuramoto_edge(), aggregator=nd.B200Aggregator("+", edge_parameters="live"))
-    assert nw.kernel_name() == "rhs_jaga_kernel"
+    assert nw.kernel_name() == f"rhs_{kern}_kernel"
     onw = oracle_network(g, vm, L.kuramoto_edge())
     u = np.random.default_rng(1).random(nw.dim())
     p = condition_params(nw, np.random.default_rng(2).random(nw.pdim()))
     du = B.nan(nw.dim())
     nw(du, B.dev(u), B.dev(p), 0.0)
     assert floored_rel_err(B.host(du), onw.rhs(u, p)) <= TOL_DU
+
+
+@pytest.mark.parametrize("wps", ["32", "48"])
+def test_jagged_kernel_window_mode_and_l2_prefetch(nd, backend, monkeypatch, wps):
+    """ND_B200_JAG_WIN=1: a thread block = one 128-row window (own outputs loaded coalesced into shared memory, row sums
+    handed to one thread per row for the vertex phase); ND_B200_PF_DIST: cp.async.bulk.prefetch.L2 of the entry streams.
+    Same entries, same order: results bit-identical to the plain jagged kernel."""
+    monkeypatch.setenv("ND_B200_KERNEL", "jag")
+    monkeypatch.setenv("ND_B200_JAG_WINDOW", "128")
+    monkeypatch.setenv("ND_B200_JAG_WPS", wps)
+    B = backend
+    for name, g, vm, em in _cases(nd, B.scale):
+        onw = oracle_network(g, vm, em)
+        got = {}
+        for mode, env in (("plain", {"ND_B200_JAG_WIN": "0", "ND_B200_PF_DIST": "0"}), ("win+pf", {"ND_B200_JAG_WIN": "1", "ND_B200_PF_DIST": "3000"})):
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            nw = nd.Network(g, vm, em, aggregator=nd.B200Aggregator("+", edge_parameters="live"))
+            assert nw.kernel_name() == "rhs_jag_kernel", name
+            u = np.random.default_rng(1).random(nw.dim())
+            p = condition_params(nw, np.random.default_rng(2).random(nw.pdim()))
+            ud, pd = B.dev(u), B.dev(p)
+            for packed in ([False, True] if em.pdim else [False]):
+                nw.pack_params(pd if packed else None)
+                du = B.nan(nw.dim())
+                nw(du, ud, pd, 0.0)
+                got[(mode, packed)] = B.host(du)
+                assert floored_rel_err(got[(mode, packed)], onw.rhs(u, p)) <= TOL_DU, (name, mode, packed)
+            nw.pack_params(None)
+            ur = B.dev(u)
+            nw.rk4(ur, pd, 0.0, 1e-3, 10)
+            got[(mode, "rk4")] = B.host(ur)
+        for key in [k for k in got if k[0] == "plain"]:
+            assert np.array_equal(got[key], got[("win+pf", key[1])]), (name, key)
 
 
 def test_tile_kernel_without_compact_entry_words(nd, backend, monkeypatch):
@@ -186,3 +224,36 @@ def test_automatic_parameter_packing_follows_p(nd, cuda):
         for call in range(3):
             nwl(du, u, p, 0.0)
         assert nwl.__dict__.get("_pack_state", {"packed": None})["packed"] is None
+
+
+@pytest.mark.gpu
+def test_persistent_cooperative_rk4(nd, cuda, monkeypatch):
+    """ND_B200_RK4_COOP=1: all steps and stages in one cooperative launch with grid-wide barriers (rk4_jag_coop_kernel);
+    states equal the graph-replayed stages bit for bit and the oracle's RK4 within the trajectory bar"""
+    torch = cuda
+    L = nd.Lib
+    monkeypatch.setenv("ND_B200_KERNEL", "jag")
+    half = np.array([0] * 10_000 + [1] * 10_000)
+    cases = [("grid-dq", nd.grid_graph(100, 120), L.swing_dq(), L.line_dq()),
+             ("ws-kuramoto", nd.watts_strogatz(10_000, 10, 0.1, seed=1), L.kuramoto_first(), L.kuramoto_edge()),
+             ("ba-mixed", nd.barabasi_albert(20_000, 4, seed=1), ([L.kuramoto_first(), L.kuramoto_second()], np.random.default_rng(3).permutation(half)), L.kuramoto_edge()),
+             ("er-diffusion", nd.erdos_renyi(300_000, 1_200_000, seed=1), L.diffusion_vertex(), L.diffusion_edge())]
+    for name, g, vm, em in cases:
+        onw = oracle_network(g, vm, em)
+        out = {}
+        for coop in ("0", "1"):
+            monkeypatch.setenv("ND_B200_RK4_COOP", coop)
+            nw = nd.Network(g, vm, em)
+            u = np.random.default_rng(1).random(nw.dim())
+            p = condition_params(nw, np.random.default_rng(2).random(nw.pdim()))
+            ud, pd = torch.from_numpy(u).cuda(), torch.from_numpy(p).cuda()
+            n0 = nw.launch_count()
+            nw.rk4(ud, pd, 0.0, 1e-3, 100)
+            torch.cuda.synchronize()
+            out[coop] = (ud.cpu().numpy(), nw.launch_count() - n0)
+        if name == "ba-mixed":      # hubs: the whole-block tree of 1024 threads associates differently from the 128-thread one
+            assert floored_rel_err(out["1"][0], out["0"][0]) <= 1e-12, name
+        else:
+            assert np.array_equal(out["0"][0], out["1"][0]), name
+        assert out["1"][1] < out["0"][1], (name, out["0"][1], out["1"][1])     # one launch (+ packing) instead of 400
+        assert floored_rel_err(out["1"][0], onw.rk4(u, p, 0.0, 1e-3, 100, threads=4)) <= 1e-9, name
