@@ -485,8 +485,10 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
 __device__ __forceinline__ void publish_block(const HaloParams& H, int bid, int nblocks) {
   const long long tid = (long long)bid * blockDim.x + threadIdx.x;
   const long long nthreads = (long long)nblocks * blockDim.x;
-  for (int r = 0; r < H.world; ++r) {
-    if (r == H.rank) continue;
+  // peers in rotated order (rank+1, rank+2, ...): at every moment each destination receives from ONE source instead of all
+  // ranks storing into rank 0 first, then rank 1, ... (N=8, config 2: 100 us of exposed halo for 46 us of wire time before)
+  for (int k = 1; k < H.world; ++k) {
+    const int r = (H.rank + k) % H.world;
     const long long n = H.send_n[r];
     const int* __restrict__ idx = H.send_idx[r];
     double* __restrict__ dst = H.halo[r] + H.dst_off[r];
