@@ -13,7 +13,8 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.environ.get("ND_B200_LIB") or os.path.join(_PKG, "libnd_b200.so")   # override: A/B builds while tuning
 SOURCES = [os.path.join(_PKG, "csrc", "nd_b200.cu")]
-HEADERS = [os.path.join(_PKG, "csrc", "nd_b200_kernels.cuh"), os.path.join(_ROOT, "include", "nd_b200.h")]
+HEADERS = [os.path.join(_PKG, "csrc", "nd_b200_kernels.cuh"), os.path.join(_ROOT, "include", "nd_b200.h")] + \
+          [os.path.join(_PKG, "csrc", n) for n in ("nd_b200_launch.inc", "nd_b200_custom.inc", "nd_b200_build.inc", "nd_b200_comm.inc")]
 
 ABI_VERSION = 5
 OK, EINVAL, EUNSUPPORTED, ECUDA, ENOMEM, ETIMEOUT = range(6)
