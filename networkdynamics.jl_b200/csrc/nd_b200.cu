@@ -27,11 +27,29 @@ using namespace ndb;
 // ND_CUSIM: tests/cusim/ compiles this very file with g++ against an emulation of the CUDA runtime that executes the kernel
 // sources thread by thread on the CPU (fibers, warp collectives, block barriers) so that the CPU test suite exercises the
 // real kernels and launch logic.  That build is a test double: it is never part of libnd_b200.so and the package never loads it.
+thread_local bool g_pdl_launch = false;   // see nd_launch_kernel below
 #ifdef ND_CUSIM
 #define ND_LAUNCH(grid, block, stream, args, ...) \
   cusim::launch(dim3((unsigned)(grid)), dim3((unsigned)(block)), (stream), [=]() { __VA_ARGS__ args; })
 #else
-#define ND_LAUNCH(grid, block, stream, args, ...) __VA_ARGS__<<<(grid), (block), 0, (stream)>>> args
+// nd_launch_kernel: plain <<<>>> launch, or -- while g_pdl_launch is set (the stage kernels captured by nd_b200_rk4) -- a
+// launch with cudaLaunchAttributeProgrammaticStreamSerialization (programmatic dependent launch, see pdl_wait() in the kernels)
+#define ND_UNPACK(...) __VA_ARGS__
+#define ND_LAUNCH(grid, block, stream, args, ...) nd_launch_kernel(__VA_ARGS__, dim3((unsigned)(grid)), dim3((unsigned)(block)), (stream), ND_UNPACK args)
+template <class... KA, class... A>
+inline void nd_launch_kernel(void (*kernel)(KA...), dim3 grid, dim3 block, cudaStream_t st, A&&... a) {
+  if (g_pdl_launch) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KA>(a)...);
+  } else {
+    kernel<<<grid, block, 0, st>>>(static_cast<KA>(a)...);
+  }
+}
 #endif
 
 namespace {
@@ -82,6 +100,7 @@ struct nd_b200_engine {
   double* d_oedge = nullptr;
   // jagged layout (ND_B200_KERNEL=jag): warp slices, see rhs_jag_kernel
   int jag = 0, jag_u = 2, jag_wps = 0, jsplit = 32;
+  int rk4_pdl = 0;                            // programmatic dependent launch between the stage kernels of nd_b200_rk4's graph (ND_B200_RK4_PDL)
   int jag_win = 0;                            // window mode of rhs_jag_kernel: every block = one 128-row window (slice table padded)
   int jag_persist = 0, jag_block = 128;   // persistent warps (rhs_jag_persist_kernel) / 64-thread blocks, ND_B200_JAG_PERSIST, ND_B200_JAG_BLOCK
   int num_sms = 148;
@@ -750,7 +769,15 @@ int nd_b200_rk4(nd_b200_engine* e, double* u, const double* p, double t0, double
     CUDA_TRY(e, cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal));
     const long long launches_before = e->launches;
     int rc = ND_B200_OK;
+    // the captured stage kernels are chained by programmatic dependencies (rk4_pdl == 2 while capturing): measured
+    // (profiles/r02w_sweep_rk4_pdl.jsonl) config 4 48.1 -> 45.6 us per step, config 1 18.1 -> 16.0, config 2 unchanged; the tile
+    // kernel on config-4-size graphs loses (47.7 -> 50.8), so it is on for jagged layouts and for small tile grids only.
+    // ND_B200_RK4_PDL=1 / 0 forces / forbids it.
+    e->rk4_pdl = (e->jag || e->nblocks <= 4 * e->num_sms) ? 1 : 0;
+    if (const char* s = getenv("ND_B200_RK4_PDL")) e->rk4_pdl = atoi(s) > 0 ? 1 : 0;
+    if (e->rk4_pdl) e->rk4_pdl = 2;
     for (int s = 0; s < per_graph && rc == ND_B200_OK; ++s) rc = rk4_step_enqueue(e, u, p, t0 + s * dt, dt, e->cap_stream);
+    if (e->rk4_pdl) e->rk4_pdl = 1;
     cudaError_t ce = cudaStreamEndCapture(e->cap_stream, &e->graph);
     e->launches = launches_before;   // captured, not launched
     if (rc != ND_B200_OK) return rc;

@@ -477,6 +477,19 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
 }
 #endif
 
+// Programmatic dependent launch (the stage kernels of nd_b200_rk4's captured graph): a kernel launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization may become resident while its predecessor in the stream is still running;
+// pdl_wait() (griddepcontrol.wait) returns once the predecessor has completed and its writes are visible -- it must precede the
+// first read of anything the predecessor wrote (states, outputs, k-sums); pdl_launch_dependents() lets the successor start
+// launching.  Both are no-ops in a launch without the attribute.
+#ifdef ND_CUSIM
+__device__ __forceinline__ void pdl_wait() {}
+__device__ __forceinline__ void pdl_launch_dependents() {}
+#else
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
 // pack + publish, executed by the first n_pub thread blocks of the RHS grid: for every peer, gather the outputs it
 // needs from the owner's state vector (ascending offsets: the reads are nearly coalesced) and store them contiguously
 // into the peer's halo buffer (coalesced NVLink stores).  The last publishing block to finish raises this rank's arrival
@@ -608,6 +621,9 @@ __global__ void __launch_bounds__(BLOCK, (fused_warps_per_sm(EK, PK && PE == 1) 
   const int coupling0 = P.n_eb > 0 ? P.eb[0].coupling : 0;
   if constexpr (HALO) {
     if (bid >= P.wait_from) halo_wait(P);   // this tile reads the halo (block-uniform)
+  } else {
+    pdl_launch_dependents();
+    pdl_wait();                             // everything above reads engine-owned tables only
   }
 
   // ---------------- long row: whole block reduces one row with a fixed-shape tree -----------------
@@ -1223,17 +1239,6 @@ __device__ __forceinline__ void jag_slice(const KParams& P, const int4 S, const 
     }
   }
 
-  double self[VD];
-#pragma unroll
-  for (int k = 0; k < VD; ++k) self[k] = 0.0;
-  if (valid) {
-    if constexpr (WIN) self[0] = s_self[(desc >> 6) & 127];
-    else {
-      const long long sidx = P.gather_from_u ? (B.state0 + (long long)(row - B.row0) * B.dim) : (long long)row * VD;
-#pragma unroll
-      for (int k = 0; k < VD; ++k) self[k] = P.gsrc[sidx + k];
-    }
-  }
   double acc[ED];
 #pragma unroll
   for (int q = 0; q < ED; ++q) acc[q] = 0.0;
@@ -1271,6 +1276,20 @@ __device__ __forceinline__ void jag_slice(const KParams& P, const int4 S, const 
     return true;
   };
   bool more = fetch(0);
+  // everything up to here read engine-owned tables (and the packed parameter copy) only: under programmatic dependent launch
+  // the index loads above are in flight while the previous stage kernel drains
+  if constexpr (!HALO && !WIN) pdl_wait();
+  double self[VD];
+#pragma unroll
+  for (int k = 0; k < VD; ++k) self[k] = 0.0;
+  if (valid) {
+    if constexpr (WIN) self[0] = s_self[(desc >> 6) & 127];
+    else {
+      const long long sidx = P.gather_from_u ? (B.state0 + (long long)(row - B.row0) * B.dim) : (long long)row * VD;
+#pragma unroll
+      for (int k = 0; k < VD; ++k) self[k] = P.gsrc[sidx + k];
+    }
+  }
   for (int j = 0; more; j += U) {
     // stage B operands of this iteration
     bool act[U];
@@ -1376,9 +1395,12 @@ __global__ void __launch_bounds__(BLOCK, (WPS * 32) / BLOCK) rhs_jag_kernel(cons
     if (P.fence && blockIdx.x == gridDim.x - 1) { halo_wait(P); return; }
   }
   const int bid = (int)blockIdx.x - (HALO ? P.n_pub : 0) + P.blk_off;
+  if constexpr (!HALO) pdl_launch_dependents();
   if (bid >= P.n_jag_blocks) {
     if constexpr (HALO) halo_wait(P);
-    long_row_block<VD, ED, EK, PE, BLOCK, HALO, PK>(P, __ldg(&P.jlong[bid - P.n_jag_blocks]), s_val);
+    const int4 dl = __ldg(&P.jlong[bid - P.n_jag_blocks]);
+    if constexpr (!HALO) pdl_wait();
+    long_row_block<VD, ED, EK, PE, BLOCK, HALO, PK>(P, dl, s_val);
     return;
   }
   const int lane = threadIdx.x & 31;
@@ -1392,6 +1414,7 @@ __global__ void __launch_bounds__(BLOCK, (WPS * 32) / BLOCK) rhs_jag_kernel(cons
     const int t = threadIdx.x;
     const int rowt = S.y + t;             // S.y = first row of the window, the same in the block's four slices
     s_flag[t] = 0;
+    if constexpr (!HALO) pdl_wait();      // descriptors above are engine-owned tables
     if (rowt < B.row0 + B.nrows) s_self[t] = P.gsrc[P.gather_from_u ? (B.state0 + (long long)(rowt - B.row0) * B.dim) : (long long)rowt];
     __syncthreads();
     if constexpr (HALO) {
@@ -1410,7 +1433,7 @@ __global__ void __launch_bounds__(BLOCK, (WPS * 32) / BLOCK) rhs_jag_kernel(cons
     if constexpr (HALO) {
       if (sl >= P.wait_from) halo_wait_warp(P);   // this slice reads the halo
     }
-    jag_slice<VD, ED, EK, PE, U, HALO, PK>(P, __ldg(&P.jslices[sl]), __ldg(&P.jlanes[(long long)sl * 32 + lane]), lane);
+    jag_slice<VD, ED, EK, PE, U, HALO, PK>(P, __ldg(&P.jslices[sl]), __ldg(&P.jlanes[(long long)sl * 32 + lane]), lane);   // calls pdl_wait()
   }
 }
 
