@@ -259,3 +259,91 @@ def test_loopback_known_answers(nd):
     inj_states = onw.table("v_data")[n] - 1
     M, D, Pm = p[onw.table("v_para")[n] - 1: onw.table("v_para")[n] + 2]
     assert du[inj_states + 1] == 1.0 / M * (Pm - D * u[inj_states + 1] + u[0])
+
+
+def _kuramoto_path4_fixpoint(nd):
+    """test/linear_analysis_test.jl:42-61 ("Kuramoto system test"): path_graph(4), Lib.kuramoto_second() vertices with
+    Pm = [1, -0.5, -0.5, 0], M = 1, D = 0.2, Lib.kuramoto_edge() with K = 2; the reference finds a fixpoint of it and asserts
+    `isfixpoint(s0)`.  With the reference's conventions (test/ComponentLibrary.jl:51-67: e = K sin(theta_src - theta_dst) enters
+    dst with +, src with - (AntiSymmetric); dv2 = 1/M (Pm - D w + acc); p = (M, D, Pm)) the fixpoint is closed form:
+        node 4: sin(th3 - th4) = 0;  node 1: 1 - 2 sin(th1 - th2) = 0;  node 3: -0.5 + 2 sin(th2 - th3) = 0;  node 2: balanced
+    => theta = (pi/6 + asin(1/4), asin(1/4), 0, 0) + c, omega = 0.  Any sign / parameter-order slip leaves |du| = O(1)."""
+    g = nd.path_graph(4)
+    vm, em = nd.Lib.kuramoto_second(), nd.Lib.kuramoto_edge()
+    nw = nd.Network(g, vm, em, aggregator=nd.B200Aggregator("+", host_only=True))
+    c = 0.37
+    theta = np.array([np.pi / 6 + np.arcsin(0.25), np.arcsin(0.25), 0.0, 0.0]) + c
+    u = np.zeros(nw.dim())
+    u[0::2] = theta                                   # (delta_i, omega_i) interleaved: one homogeneous batch
+    p = np.zeros(nw.pdim())
+    p[0:12:3], p[1:12:3], p[2:12:3] = 1.0, 0.2, [1.0, -0.5, -0.5, 0.0]   # (M, D, Pm) per vertex
+    p[12:15] = 2.0                                    # K per edge
+    return g, vm, em, u, p
+
+
+def test_kuramoto_fixpoint_of_the_reference_linear_analysis_test(nd):
+    """the oracle (C and Python twin) evaluates du = 0 at the closed-form fixpoint of test/linear_analysis_test.jl:42-61 --
+    a reference-held pin of the Kuramoto edge + inertial vertex arithmetic (signs, AntiSymmetric direction, parameter order)"""
+    g, vm, em, u, p = _kuramoto_path4_fixpoint(nd)
+    onw = oracle_network(g, vm, em)
+    du = onw.rhs(u, p)
+    assert np.max(np.abs(du)) <= 4e-16, du
+    from helpers import model_types
+    uv, vt = model_types(vm, g.nv)
+    ue, et = model_types(em, g.ne)
+    du_twin, _, _ = ONP.rhs(_np_im(g, uv, vt, ue, et), u, p)
+    assert np.max(np.abs(du_twin)) <= 4e-16
+    # off the fixpoint the residual is what the conventions say: more mechanical power on node 1 accelerates node 1 only
+    p2 = p.copy()
+    p2[2] += 0.25
+    du2 = onw.rhs(u, p2)
+    assert abs(du2[1] - 0.25) <= 1e-15 and np.max(np.abs(np.delete(du2, 1))) <= 4e-16
+    # relabelling every edge's direction is the same physics under AntiSymmetric coupling; a Symmetric wrapper is not
+    flipped = oracle_network(nd.SimpleGraph(4, g.dst, g.src), vm, em)
+    assert np.max(np.abs(flipped.rhs(u, p))) <= 4e-16
+    sym = nd.EdgeModel(g=nd.Symmetric(nd.Lib.kuramoto_edge_f), outdim=1, pdim=1, psym=("K",), name="kuramoto_sym")
+    assert np.max(np.abs(oracle_network(g, vm, sym).rhs(u, p))) > 0.5
+
+
+def _dq_two_bus_fixpoint(nd, R=0.0):
+    """Two `SwingDQ` buses (test/ComponentLibrary.jl:139-160: u = V (cos th, sin th), Pel = u_r i_r + u_i i_i,
+    dw = 1/M (Pmech - D w + Pel)) joined by one `StaticPowerLineDQ` (:212-245: idst = active / (R + jX) (Vsrc - Vdst), isrc = -idst).
+    Closed form from those equations: the power delivered to the dst bus is Re(Vdst conj(idst)), to the src bus Re(Vsrc conj(isrc));
+    for R = 0 that is the textbook power-angle relation +-(V^2 / X) sin(th_src - th_dst).  Choosing Pmech = minus the delivered power
+    makes (th, w = 0) a fixpoint."""
+    g = nd.SimpleGraph(2, [1], [2])
+    vm, em = nd.Lib.swing_dq(), nd.Lib.line_dq()
+    nw = nd.Network(g, vm, em, aggregator=nd.B200Aggregator("+", host_only=True))
+    V, X, d = 1.05, 0.8, np.pi / 6
+    ths, thd = 0.4 + d, 0.4
+    Vs, Vd = V * np.exp(1j * ths), V * np.exp(1j * thd)
+    idst = (Vs - Vd) / complex(R, X)
+    Pdst, Psrc = (Vd * np.conj(idst)).real, (Vs * np.conj(-idst)).real
+    u = np.array([ths, 0.0, thd, 0.0])
+    p = np.array([2.0, 0.3, -Psrc, V,   1.5, 0.1, -Pdst, V,   R, X, 1.0])      # (M, D, Pmech, V) per bus, (R, X, active)
+    assert nw.dim() == 4 and nw.pdim() == 11
+    return g, vm, em, u, p, (Psrc, Pdst, V, X, d)
+
+
+def test_dq_swing_and_line_fixpoint_closed_form(nd):
+    """the hand-written equivalents of the MTK dq models (oracle, C and Python twin) reproduce the closed-form fixpoint of the
+    equations they restate; for R = 0 the delivered power is the power-angle relation"""
+    from helpers import model_types
+    for R in (0.0, 0.25):
+        g, vm, em, u, p, (Psrc, Pdst, V, X, d) = _dq_two_bus_fixpoint(nd, R)
+        if R == 0.0:
+            assert abs(Pdst - V * V / X * np.sin(d)) <= 1e-15 and abs(Psrc + V * V / X * np.sin(d)) <= 1e-15
+        else:
+            assert Psrc + Pdst < 0.0            # a resistive line dissipates
+        onw = oracle_network(g, vm, em)
+        du = onw.rhs(u, p)
+        assert np.max(np.abs(du)) <= 1e-15, (R, du)
+        uv, vt = model_types(vm, g.nv)
+        ue, et = model_types(em, g.ne)
+        du_twin, _, _ = ONP.rhs(_np_im(g, uv, vt, ue, et), u, p)
+        assert np.max(np.abs(du_twin)) <= 1e-15
+        # an opened line (active = 0) leaves each machine with its mechanical power only: dw = Pmech / M
+        p0 = p.copy()
+        p0[10] = 0.0
+        du0 = onw.rhs(u, p0)
+        assert np.allclose(du0, [0.0, p[2] / p[0], 0.0, p[6] / p[4]], rtol=0, atol=1e-15)

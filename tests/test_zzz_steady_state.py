@@ -6,6 +6,8 @@
   its mass-matrix solver; a state-free vertex with a computed output is the same network for an explicit stepper.
 * test/diffusion_test.jl:119-129 -- |x(t) - exp(-tL) x0| < 1e-6 on the device (the oracle-side form is in
   tests/test_oracle_pins.py).
+* test/linear_analysis_test.jl:42-61 -- the Kuramoto system whose fixpoint the reference finds and asserts: the engine evaluates
+  du = 0 at the closed-form fixpoint and stays on it through the fused RK4.
 """
 import math
 
@@ -57,3 +59,42 @@ def test_diffusion_trajectory_matches_matrix_exponential(nd, backend):
     want = expm(-1.0 * g.laplacian().toarray() if hasattr(g.laplacian(), "toarray") else -1.0 * np.asarray(g.laplacian())) @ x0
     assert np.max(np.abs(B.host(ud) - want)) < 1e-6
     assert floored_rel_err(B.host(ud), want) < 1e-6
+
+
+def test_kuramoto_fixpoint_of_the_reference_linear_analysis_test(nd, backend):
+    """closed-form fixpoint of test/linear_analysis_test.jl:42-61 (derivation: tests/test_oracle_pins.py): du = 0 on the engine in
+    both kernel families, and 200 fused RK4 steps do not leave it"""
+    from test_oracle_pins import _kuramoto_path4_fixpoint
+    B = backend
+    g, vm, em, u, p = _kuramoto_path4_fixpoint(nd)
+    nw = nd.Network(g, vm, em)
+    du = B.nan(nw.dim())
+    nw(du, B.dev(u), B.dev(p), 0.0)
+    assert np.max(np.abs(B.host(du))) <= 1e-15
+    ud = B.dev(u)
+    nw.rk4(ud, B.dev(p), 0.0, 1e-2, 200)
+    assert np.max(np.abs(B.host(ud) - u)) <= 1e-13
+    # a perturbed state relaxes back (D > 0: the fixpoint is linearly stable, `is_linear_stable(s0; marginally_stable=true)`)
+    u1 = u.copy()
+    u1[0] += 0.05
+    ud = B.dev(u1)
+    nw.rk4(ud, B.dev(p), 0.0, 1e-2, 20000)
+    got = B.host(ud)
+    assert np.max(np.abs(got[1::2])) <= 1e-6                       # omega -> 0
+    th = got[0::2]
+    assert abs((th[0] - th[1]) - np.pi / 6) <= 1e-6 and abs((th[1] - th[2]) - np.arcsin(0.25)) <= 1e-6 and abs(th[2] - th[3]) <= 1e-6
+
+
+def test_dq_swing_and_line_fixpoint_closed_form(nd, backend):
+    """closed-form fixpoint of the dq swing buses + static dq line (derivation: tests/test_oracle_pins.py) on the engine"""
+    from test_oracle_pins import _dq_two_bus_fixpoint
+    B = backend
+    for R in (0.0, 0.25):
+        g, vm, em, u, p, _ = _dq_two_bus_fixpoint(nd, R)
+        nw = nd.Network(g, vm, em)
+        du = B.nan(nw.dim())
+        nw(du, B.dev(u), B.dev(p), 0.0)
+        assert np.max(np.abs(B.host(du))) <= 2e-15, R
+        ud = B.dev(u)
+        nw.rk4(ud, B.dev(p), 0.0, 1e-2, 100)
+        assert np.max(np.abs(B.host(ud) - u)) <= 1e-12, R
