@@ -41,8 +41,9 @@ def build(force: bool = False) -> str:
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
     cmd = [cxx, "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-w", "-DND_CUSIM=1",
            f'-DCUSIM_INCLUDE_DIR="{_DIR}"', "-I", _DIR, "-I", os.path.join(_ROOT, "include"), "-x", "c++"] + srcs + \
-          ["-o", LIB_PATH, "-ldl", "-lpthread"]
+          ["-o", LIB_PATH + f".tmp{os.getpid()}", "-ldl", "-lpthread"]
     subprocess.check_call(cmd)
+    os.replace(LIB_PATH + f".tmp{os.getpid()}", LIB_PATH)     # atomic: concurrent test workers never load a half-written library
     return LIB_PATH
 
 
