@@ -100,6 +100,14 @@ struct nd_b200_engine {
   double* d_oedge = nullptr;
   // jagged layout (ND_B200_KERNEL=jag): warp slices, see rhs_jag_kernel
   int jag = 0, jag_u = 2, jag_wps = 0, jsplit = 32;
+  // column-blocked evaluation (ND_B200_L2_BLOCKS, see nd_b200_create): `blocks` are complete engines over the SAME rows, each
+  // holding only the entries whose neighbour output lies in [col_lo, col_hi) of the gather source; nd_b200_rhs runs them in
+  // ascending column order, the row sums travel through d_blockacc
+  std::vector<nd_b200_engine*> blocks;
+  double* d_blockacc = nullptr;
+  bool col_filter = false;                    // this engine IS one of those blocks
+  long long col_lo = 0, col_hi = 0;
+  bool cols_sorted = false;                   // every row's entries are in ascending neighbour-offset order (set by build_csr)
   int rk4_pdl = 0;                            // programmatic dependent launch between the stage kernels of nd_b200_rk4's graph (ND_B200_RK4_PDL)
   int jag_win = 0;                            // window mode of rhs_jag_kernel: every block = one 128-row window (slice table padded)
   int jag_persist = 0, jag_block = 128;   // persistent warps (rhs_jag_persist_kernel) / 64-thread blocks, ND_B200_JAG_PERSIST, ND_B200_JAG_BLOCK
@@ -326,6 +334,23 @@ struct WaitSpec { const double* halo; const unsigned long long* flags; unsigned 
 int rhs_impl(nd_b200_engine* e, double* du, const double* u, const double* p, double t, cudaStream_t st, int mode,
              double* aggbuf, const WaitSpec* w = nullptr) {
   if (e->halo_base != INT_MAX && !w) return fail(e, ND_B200_EINVAL, "this engine reads a halo buffer (gather_offset): call it through nd_b200_rhs_exchange");
+  if (!e->blocks.empty() && mode == MODE_DU && !w && !e->timing) {
+    // column-blocked evaluation: block b adds its entries on top of the sums of blocks 0 .. b-1 (same entry order as one pass,
+    // because every row's entries are in ascending column order); the last block applies the vertex model
+    const size_t nb = e->blocks.size();
+    for (size_t b = 0; b < nb; ++b) {
+      nd_b200_engine* sub = e->blocks[b];
+      KParams Q;
+      fill_params(sub, Q);
+      Q.u = u; Q.gsrc = u; Q.p = p; Q.t = t;
+      Q.acc_in = b > 0 ? e->d_blockacc : nullptr;
+      if (b + 1 < nb) { Q.mode = MODE_AGG; Q.aggbuf = e->d_blockacc; }
+      else { Q.mode = MODE_DU; Q.du = du; }
+      CUDA_TRY(e, launch_fused(sub, Q, st));
+    }
+    e->launches += (long long)nb;
+    return ND_B200_OK;
+  }
   KParams P;
   fill_params(e, P);
   P.u = u; P.p = p; P.du = du; P.mode = mode; P.aggbuf = aggbuf; P.t = t;
@@ -412,6 +437,35 @@ int nd_b200_create(const nd_b200_desc* desc, nd_b200_engine** out) {
     nd_b200_destroy(e);
     return rc;
   }
+  // ---- column-blocked evaluation (opt-in, ND_B200_L2_BLOCKS=<k>|auto) --------------------------------------------------------
+  // When the vertex outputs do not fit the L2, every gather miss fills a 128-byte line from DRAM (config 5 at full size: 103.7 GB
+  // per RHS).  With k blocks the RHS becomes k launches, block b gathering only from the b-th k-th of the outputs
+  // (L2 resident for its whole launch).  Single GPU, jagged layout, one vertex output, registry kinds, rows in ascending neighbour
+  // order (sorted edge lists) -- otherwise the switch is ignored.
+  if (const char* sblk = getenv("ND_B200_L2_BLOCKS")) {
+    const long long table_bytes = 8LL * e->lastidx_dynamic;
+    long long k = !strcmp(sblk, "auto") ? (table_bytes > 96LL << 20 ? (table_bytes + (48LL << 20) - 1) / (48LL << 20) : 0) : atoll(sblk);
+    k = std::min<long long>(k, 64);
+    const bool ok = k >= 2 && e->jag && !e->jaga && !e->jagb && !e->jstream && !e->custom && !e->split && e->ode.empty() && e->vdepth == 1 &&
+                    e->edepth == 1 && e->gather_from_u && e->halo_base == INT_MAX && e->row_end - e->row_begin == e->nrows_total &&
+                    e->cols_sorted && !e->host_only && e->ek != EK_GENERIC && !e->jag_win && !e->jag_persist && e->jag_block != 64;
+    if (ok) {
+      const long long width = (e->lastidx_dynamic + k - 1) / k;
+      for (long long b = 0; b < k && rc == ND_B200_OK; ++b) {
+        nd_b200_engine* sub = new (std::nothrow) nd_b200_engine();
+        if (!sub) { rc = fail(e, ND_B200_ENOMEM, "out of host memory"); break; }
+        sub->col_filter = true; sub->col_lo = b * width; sub->col_hi = std::min<long long>((b + 1) * width, e->lastidx_dynamic);
+        nd_b200_desc dsub = *desc;
+        dsub.flags |= ND_B200_FLAG_NO_EXPORT;
+        try { rc = build_engine(sub, &dsub); } catch (...) { rc = fail(sub, ND_B200_ENOMEM, "out of host memory while building a column block"); }
+        if (rc != ND_B200_OK) { e->err = sub->err; nd_b200_destroy(sub); break; }
+        e->blocks.push_back(sub);
+      }
+      if (rc == ND_B200_OK && cudaMalloc((void**)&e->d_blockacc, sizeof(double) * (size_t)e->nrows_total * (size_t)e->edepth) != cudaSuccess)
+        rc = fail(e, ND_B200_ECUDA, "cudaMalloc of the column-block row sums failed");
+      if (rc != ND_B200_OK) { g_create_error = e->err; nd_b200_destroy(e); return rc; }
+    }
+  }
   *out = e;
   return ND_B200_OK;
 }
@@ -462,8 +516,11 @@ int nd_b200_create_from_edgelist(int32_t device, int64_t nv, int64_t ne, const i
 
 void nd_b200_destroy(nd_b200_engine* e) {
   if (!e) return;
+  for (nd_b200_engine* sub : e->blocks) nd_b200_destroy(sub);
+  e->blocks.clear();
   if (e->host_only) { delete e; return; }
   cudaSetDevice(e->device);
+  cudaFree(e->d_blockacc);
   destroy_graph(e);
   cudaFree(e->d_rowptr); cudaFree(e->d_nbr); cudaFree(e->d_epar); cudaFree(e->d_blk_row); cudaFree(e->d_ebid);
   cudaFree(e->d_vb); cudaFree(e->d_eb); cudaFree(e->d_vout[0]); cudaFree(e->d_vout[1]);
@@ -602,6 +659,8 @@ int nd_b200_rhs_host(nd_b200_engine* e, double* du_host, const double* u_host, c
 int nd_b200_pack_params(nd_b200_engine* e, const double* p, void* stream) {
   if (!e) return ND_B200_EINVAL;
   if (e->host_only) return fail(e, ND_B200_EUNSUPPORTED, "host-only engine");
+  for (nd_b200_engine* sub : e->blocks)       // column blocks keep their own packed copies
+    if (int rc = nd_b200_pack_params(sub, p, stream)) { e->err = sub->err; return rc; }
   if (!p) { e->pack_on = false; return ND_B200_OK; }
   if (e->pack_pe <= 0 || e->split) return fail(e, ND_B200_EUNSUPPORTED, "packed edge parameters need ONE registry edge batch with parameters and a fused kernel");
   if (e->jstream ? false : (e->jag ? (e->jag_u != 2 && (e->vdepth != 1 || e->halo_base != INT_MAX)) : (e->block != 128 || e->ept != 4))) return fail(e, ND_B200_EUNSUPPORTED, "packed edge parameters are compiled for the default launch shape only");

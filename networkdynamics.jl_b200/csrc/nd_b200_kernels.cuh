@@ -170,6 +170,9 @@ struct KParams {
   // that lies pf_dist entries ahead of its own piece; 0 = off.  The slices' pieces tile the streams, so do the prefetches.
   int pf_dist;
   long long jag_len;                   // length of the jagged entry streams
+  // column-blocked evaluation (graphs whose vertex outputs exceed the L2, see nd_b200_create): this launch adds the entries of ONE
+  // block of neighbour columns; acc_in (nullable) holds the rows' sums over the blocks before it, [row * edepth + d]
+  const double* acc_in;
   // multi-GPU: the first n_pub thread blocks of the grid pack this rank's boundary outputs into the peers' halo buffers
   // (NVLink stores) and raise the arrival flags; interior tiles follow, tiles that read the halo come last
   int n_pub;
@@ -1189,6 +1192,12 @@ __device__ __forceinline__ void long_row_block(const KParams& P, const int4 d, d
     double acc[ED], v[ND_MAX_VDIM];
 #pragma unroll
     for (int q = 0; q < ED; ++q) acc[q] = s_val[q];
+    if constexpr (!HALO) {
+      if (P.acc_in != nullptr) {
+#pragma unroll
+        for (int q = 0; q < ED; ++q) acc[q] = P.acc_in[(long long)r0 * ED + q] + acc[q];
+      }
+    }
     load_vertex_state(P, B, r0, v);
     vertex_phase<VD, ED>(P, B, r0, acc, self, v, P.p + B.p0 + (long long)(r0 - B.row0) * B.pdim);
   }
@@ -1242,6 +1251,12 @@ __device__ __forceinline__ void jag_slice(const KParams& P, const int4 S, const 
   double acc[ED];
 #pragma unroll
   for (int q = 0; q < ED; ++q) acc[q] = 0.0;
+  if constexpr (!HALO && !WIN) {
+    if (P.acc_in != nullptr && head) {     // the row's sum over the earlier column blocks comes first (entry order is kept)
+#pragma unroll
+      for (int q = 0; q < ED; ++q) acc[q] = P.acc_in[(long long)row * ED + q];
+    }
+  }
 
   // The walk is software-pipelined: the index (and packed-parameter) loads of columns j+U .. j+2U-1 are issued BEFORE the
   // gathers of columns j .. j+U-1 are waited for, so an iteration exposes one memory latency (the gather) instead of two

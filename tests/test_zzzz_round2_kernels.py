@@ -144,6 +144,61 @@ def test_jagged_kernel_window_mode_and_l2_prefetch(nd, backend, monkeypatch, wps
             assert np.array_equal(got[key], got[("win+pf", key[1])]), (name, key)
 
 
+@pytest.mark.parametrize("k", ["3", "7"])
+def test_column_blocked_evaluation(nd, backend, monkeypatch, k):
+    """ND_B200_L2_BLOCKS=k: the RHS as k launches, launch b adding only the entries whose neighbour lies in the b-th block of the
+    vertex outputs (L2 resident for graphs whose outputs exceed the L2), the row sums carried between the launches.  Rows in
+    ascending neighbour order (sorted edge lists) keep the reference's accumulation order: bit-identical to the single pass."""
+    monkeypatch.setenv("ND_B200_KERNEL", "jag")
+    B = backend
+    L = nd.Lib
+    n = max(3000, int(30_000 * B.scale))
+    star = nd.SimpleGraph(5000, np.ones(4999, dtype=np.int64), np.arange(2, 5001))
+    cases = [("er-diffusion", nd.erdos_renyi(n, 4 * n, seed=1), L.diffusion_vertex(), L.diffusion_edge(), True),
+             ("er-kuramoto", nd.erdos_renyi(n, 8 * n, seed=2), L.kuramoto_first(), L.kuramoto_edge(), True),
+             ("er-nop", nd.erdos_renyi(n, 4 * n, seed=3), L.diffusion_vertex(), L.diffusion_edge_nop(), True),
+             ("star", star, L.kuramoto_first(), L.kuramoto_edge(), True),            # the hub is a whole-block row
+             ("isolated", nd.SimpleGraph(70, [1, 2], [2, 3]), L.diffusion_vertex(), L.diffusion_edge(), True),
+             ("ba-hubs", nd.barabasi_albert(n, 4, seed=1), L.kuramoto_first(), L.kuramoto_edge(), None)]
+    for name, g, vm, em, expect_blocked in cases:
+        onw = oracle_network(g, vm, em)
+        out = {}
+        for mode in ("plain", "blocked", "blocked-edgelist"):
+            if mode == "plain":
+                monkeypatch.delenv("ND_B200_L2_BLOCKS", raising=False)
+            else:
+                monkeypatch.setenv("ND_B200_L2_BLOCKS", k)
+            if mode == "blocked-edgelist":
+                nw = nd.Network.from_edgelist(g, vm, em)
+            else:
+                nw = nd.Network(g, vm, em)
+            assert nw.kernel_name() == "rhs_jag_kernel", name
+            u = np.random.default_rng(1).random(nw.dim())
+            p = condition_params(nw, np.random.default_rng(2).random(nw.pdim()))
+            ud, pd = B.dev(u), B.dev(p)
+            per_call = []
+            for call in range(3):                    # the third call runs from the packed parameter copies of every block
+                du = B.nan(nw.dim())
+                n0 = nw.launch_count()
+                nw(du, ud, pd, 0.0)
+                got = B.host(du)
+                per_call.append(nw.launch_count() - n0)
+                assert floored_rel_err(got, onw.rhs(u, p)) <= TOL_DU, (name, mode, call)
+                out[(mode, call)] = got
+            if mode != "plain" and expect_blocked:
+                assert per_call[0] == int(k), (name, mode, per_call)      # k launches per RHS (later calls add the packing kernels)
+            if mode == "plain":
+                assert per_call[0] == 1
+            # the other entry points keep working on a blocked engine (they use the unblocked layout)
+            ur = B.dev(u)
+            nw.rk4(ur, pd, 0.0, 1e-3, 5)
+            assert np.max(np.abs(B.host(ur) - onw.rk4(u, p, 0.0, 1e-3, 5))) <= 1e-11, (name, mode)
+        for call in range(3):
+            if name not in ("star", "ba-hubs"):   # rows cut into lane parts / whole-block rows associate per block; all others: sequential
+                assert np.array_equal(out[("plain", call)], out[("blocked", call)]), (name, call)
+                assert np.array_equal(out[("plain", call)], out[("blocked-edgelist", call)]), (name, call)
+
+
 def test_tile_kernel_without_compact_entry_words(nd, backend, monkeypatch):
     """networks whose offsets do not fit 23 bits keep the row-id table in shared memory; force that path on a small one"""
     monkeypatch.setenv("ND_B200_KERNEL", "fused")
